@@ -1,0 +1,159 @@
+/* rsigpu.h -- C ABI of the B200-native `rsicnv rsi` read-depth -> CNV-call hot path.
+ *
+ * The reference (yhwu/rsicnv) has no plugin / FFI interface: the path sits behind its process
+ * boundary and a handful of free functions that mutate a caller-owned depth array and talk through
+ * `rsi::` globals.  This header DEFINES the boundary a maintainer would bind
+ * instead of those functions.  Each entry point names the reference seam it replaces (file:line
+ * relative to the reference's src/).  Plain C types only; every call returns an int status and
+ * never exits the process; all host buffers are caller-owned; one host thread per context; contexts
+ * are independent (one per contig / GPU), unlike the reference's non-re-entrant globals.
+ */
+#ifndef RSIGPU_H
+#define RSIGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSIGPU_OK 0
+#define RSIGPU_E_CUDA 1        /* a CUDA runtime call failed (see rsigpu_last_error) */
+#define RSIGPU_E_ARG 2         /* bad argument / call order */
+#define RSIGPU_E_RANGE 3       /* input outside what the kernels are sized for (see message) */
+#define RSIGPU_E_CAPACITY 4    /* output buffer too small */
+#define RSIGPU_E_NODEVICE 5    /* no CUDA device: there is NO CPU fallback */
+
+#define RSIGPU_TYPE_DEL 0
+#define RSIGPU_TYPE_DUP 1
+#define RSIGPU_TYPE_UNKNOWN 2
+
+#define RSIGPU_TRANS_NBN 0     /* -NB  (default)  rsi.cpp:51,2028 */
+#define RSIGPU_TRANS_MED 1     /* -MED            rsi.cpp:2027    */
+#define RSIGPU_TRANS_ALL 2     /* -ALL            rsi.cpp:2029    */
+
+typedef struct rsigpu_ctx rsigpu_ctx;
+
+/* The tunables get_parameters() fills (rsi.cpp:1986-2068); defaults = rsi.cpp:34-98. */
+typedef struct rsigpu_params {
+  int32_t m;          /* -m   bin size, forced odd (rsi.cpp:2061-2064)          default 101 */
+  int32_t minq;       /* -q   minimum mapping quality                            default 0   */
+  int32_t min_baseQ;  /* -Q   minimum base quality (code default 13, rsi.cpp:58) default 13  */
+  int32_t gcadjust;   /* 0 = -NOGC                                               default 1   */
+  int32_t trans;      /* RSIGPU_TRANS_*                                          default NBN */
+  int32_t merge;      /* 0 = -nomerge                                            default 1   */
+  int32_t maxchkbp;   /* -maxchkbp                                               default 100000 */
+  int32_t reserved_;
+  double cap;         /* -cap, <=1 disables                                      default 4.0 */
+  double threshold;   /* -threshold (MED only), <=0 = unset                      default -1  */
+  double epsilon;     /* -e                                                      default 1.5 */
+  double chklen;      /* -reflen                                                 default 2.5 */
+} rsigpu_params;
+
+/* Flat mirror of cnv_st (rsi.h:8-51); both status (-9 = deleted) and geno are carried verbatim. */
+typedef struct rsigpu_cnv {
+  int32_t tid, type, geno, status, start, end, length, sc1, sc2, pair;
+  double score, p1, p2, cnvmed, cnvsd, cnviqr, refmed, refsd, refiqr, q0;
+  int32_t rp, pad_;
+} rsigpu_cnv;
+
+/* One batch of decoded BAM records of ONE contig, position-sorted, as structure-of-arrays.
+ * Field meanings = bam1_core_t (samtools-0.1.18/bam.h:131-155).  HOST pointers. */
+typedef struct rsigpu_read_batch {
+  int64_t n_reads;
+  int32_t tid;                /* core.tid of every read in the batch                       */
+  int32_t reserved_;
+  const int32_t* pos;         /* [n] core.pos, 0-based                                      */
+  const int32_t* mpos;        /* [n] core.mpos                                              */
+  const int32_t* isize;       /* [n] core.isize                                             */
+  const int32_t* mtid;        /* [n] core.mtid                                              */
+  const uint16_t* flag;       /* [n] core.flag                                              */
+  const uint8_t* mapq;        /* [n] core.qual                                              */
+  const uint32_t* cigar_off;  /* [n+1] offsets into cigar[] (n_cigar = difference)          */
+  const uint32_t* cigar;      /* BAM-encoded ops, len<<4|op, ops MIDNSHP=X = 0..8           */
+  const uint64_t* qual_off;   /* [n+1] offsets into qual[] (l_qseq = difference)            */
+  const uint8_t* qual;        /* base qualities (Phred, 0xff = absent)                      */
+} rsigpu_read_batch;
+
+/* which-array selectors for rsigpu_get_array (parity tests, `-s`) */
+#define RSIGPU_ARR_RAW_DEPTH 0   /* int32[L]   per-base depth before GC/cap (what `-s` dumps, loaddata.cpp:340-344) */
+#define RSIGPU_ARR_DEPTH 1       /* int32[L']  after GC adjust, cap and N-compaction (RD as detectcnv sees it)    */
+#define RSIGPU_ARR_BIN_MED 2     /* float[nb]  median_transfer output  (rsi.cpp:1363)                              */
+#define RSIGPU_ARR_BIN_NBN 3     /* float[nb]  negative_binomial_transfer output (rsi.cpp:1120)                    */
+#define RSIGPU_ARR_BIN_MEDINT 4  /* int32[nb]  RDmedint (rsi.cpp:1819)                                             */
+#define RSIGPU_ARR_BIN_STATUS 5  /* int32[nb]  RSI status after the second rsistatus pass (rsi.cpp:1329/1482)      */
+#define RSIGPU_ARR_NOSEQ_BEG 6   /* int32[k]   rsi::noncodelist starts, 0-based inclusive (loaddata.cpp:243)       */
+#define RSIGPU_ARR_NOSEQ_END 7   /* int32[k]   rsi::noncodelist ends                                               */
+#define RSIGPU_ARR_BIN_STATUS1 8 /* int32[nb]  status after pass 1 + filterstatus (rsi.cpp:1305/1455)              */
+#define RSIGPU_ARR_SEGMENTS 9    /* rsigpu_cnv[k] candidates leaving rsicnvnbn/rsicnvmed (bin coordinates)         */
+#define RSIGPU_ARR_BLOCKS 10     /* rsigpu_cnv[k] after areblockscnv (bin coordinates)                             */
+#define RSIGPU_ARR_PREMERGE 11   /* rsigpu_cnv[k] after bins->bases + 2x optimize_with_derivative + sort           */
+#define RSIGPU_ARR_MERGED 12     /* rsigpu_cnv[k] after mergesegments + sort                                       */
+#define RSIGPU_ARR_DETECTED 13   /* rsigpu_cnv[k] detectcnv output (before sd_filters)                             */
+
+/* chromosome-level scalars for the output row / log (rsi::RDmedian, rsi::RDsd, ...) */
+typedef struct rsigpu_chr_stats {
+  double rdmedian, rdsd;            /* rsi.cpp:2202-2203                                      */
+  double tmedian, tlamda;           /* second-pass values (rsi::nbnmedian/nbnlamda or med*)   */
+  double rdmad;                     /* negative_binomial_transfer's MAD (rsi.cpp:1138)        */
+  int32_t target_len, compact_len;  /* L and L' (after N removal)                             */
+  int32_t nbins, lmax;
+  int32_t isize_mean, isize_sd;     /* bam_rd_pr_stats sample (pairrd.cpp:236-241), -1 if none */
+  int32_t n_noseq, reserved_;
+} rsigpu_chr_stats;
+
+int rsigpu_default_params(rsigpu_params* p);
+
+/* Context = what one iteration of the reference's chromosome loop owns (rsi.cpp:2189-2217). */
+int rsigpu_create(int device, const rsigpu_params* p, rsigpu_ctx** out);
+void rsigpu_destroy(rsigpu_ctx* c);
+const char* rsigpu_last_error(const rsigpu_ctx* c);
+int rsigpu_num_devices(void);
+
+/* read_fasta output for one contig (readref.cpp:10-86): `len` ASCII bytes, newlines stripped.
+ * Replaces the GC bitmap + get_noseq_regions steps (loaddata.cpp:290-295, 243-273).  HOST pointer. */
+int rsigpu_set_reference(rsigpu_ctx* c, const uint8_t* fasta, int32_t len, int32_t tid);
+
+/* Depth-file input: the array load_data_from_text builds (loaddata.cpp:496-517); the host parses
+ * the text (rsicnv_parse_depth_text in the CLI).  HOST pointer, len must equal the reference length. */
+int rsigpu_set_depth(rsigpu_ctx* c, const int32_t* depth, int32_t len);
+
+/* BAM input: replaces the hot loop of load_data_from_bam (loaddata.cpp:312-335) and
+ * resolve_cigar_pos (samfunctions.cpp:38-100).  push() only stages a batch in HBM (and keeps the
+ * per-read summary cnv_stat needs); the pileup kernel runs in rsigpu_run / rsigpu_pileup_end. */
+int rsigpu_pileup_begin(rsigpu_ctx* c, int32_t target_len);
+int rsigpu_pileup_push(rsigpu_ctx* c, const rsigpu_read_batch* b);
+int rsigpu_pileup_end(rsigpu_ctx* c);
+
+/* The seams, in the order main() calls them (rsi.cpp:2197-2211).  All asynchronous on the
+ * context's stream except where a result is copied to the host. */
+int rsigpu_load_finish(rsigpu_ctx* c);   /* checkgccontent + apply_cap + concatenate_data + RDmedian/RDsd: gccontent.cpp:95, loaddata.cpp:229, 48, rsi.cpp:2202 */
+int rsigpu_detectcnv(rsigpu_ctx* c);     /* detectcnv, rsi.cpp:1795-1945 */
+int rsigpu_sd_filters(rsigpu_ctx* c);    /* sd_filters, rsi.cpp:1753-1792 */
+int rsigpu_cnv_stat(rsigpu_ctx* c);      /* cnv_stat + bam_rd_pr_stats, pairrd.cpp:622-748, 112-260 (BAM input only) */
+int rsigpu_get_calls(rsigpu_ctx* c, rsigpu_cnv* out, int32_t cap, int32_t* n);  /* rows write_cnv_to_file would print */
+
+/* Everything above on the staged inputs, one host synchronisation at the end. */
+int rsigpu_run(rsigpu_ctx* c, rsigpu_cnv* out, int32_t cap, int32_t* n);
+
+int rsigpu_get_chr_stats(rsigpu_ctx* c, rsigpu_chr_stats* out);
+/* copies min(count, cap) elements of the selected device array to `out`, *count = elements available */
+int rsigpu_get_array(rsigpu_ctx* c, int32_t which, void* out, int64_t cap, int64_t* count);
+
+/* cnv_format1 (rsi.cpp:581-631): one table row, or the column header when cnv == NULL. */
+int rsigpu_format_row(const rsigpu_cnv* cnv, const char* chrom, double rdmedian, double rdsd, char* buf, int32_t cap);
+
+/* timing / accounting for bench.py: kernels launched by this context since creation, and the
+ * device time (ms, CUDA events on the context's stream) of the last rsigpu_run by stage:
+ * [0]=pileup [1]=load_finish [2]=detect bins+scan [3]=candidates [4]=sd_filters+cnv_stat [5]=total */
+int64_t rsigpu_launch_count(const rsigpu_ctx* c);
+int rsigpu_last_stage_ms(const rsigpu_ctx* c, float* ms6);
+/* per-kernel device time of the last rsigpu_run when profiling is on (rsigpu_set_profile(c,1)):
+ * writes up to cap (name, ms, launches) triples; returns the number of distinct kernels */
+int rsigpu_set_profile(rsigpu_ctx* c, int on);
+int rsigpu_get_profile(const rsigpu_ctx* c, char* names, int32_t name_stride, float* ms, int32_t* launches, int32_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSIGPU_H */

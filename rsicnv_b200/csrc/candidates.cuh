@@ -1,0 +1,657 @@
+// candidates.cuh -- the candidate stage of the rsi path as one cooperative thread block per contig.
+//
+// Replaces (reference file:line, relative to src/):
+//   isitcnv            rsi.cpp:101-172     cnv_test_stats()
+//   isitcnvwrap        rsi.cpp:175-287     cnv_test()            (neighbour walk: SURVEY.md A.1)
+//   multisegments      rsi.cpp:368-410     SubsegIter
+//   areblockscnv       rsi.cpp:415-546     blocks_test()
+//   sortcnvstartposition rsi.cpp:549-577   list_sort()
+//   optimize_with_derivative rsi.cpp:889-944  edge_refine()
+//   mergesegments      rsi.cpp:694-885     merge_segments()
+//   detectcnv tail     rsi.cpp:1860-1931   candidates_main()
+//   expand_coordinate  rsi.cpp:1524-1551   expand_coord()
+//   sd_filters         rsi.cpp:1753-1792   sd_filter_list()
+//   partition_stat_tp  wufunctions.cpp:363-424  cta_hist_stat()
+//   alglib::pnorm      alglib/specialfunctions.cpp:3152-3302  phi()
+//
+// Design: the reference walks neighbours one base at a time and copies whole call lists for every
+// trial merge.  Here the walk is decomposed into "free" stretches (accepted = not an outlier) and
+// "call zones" (first non-outlier triggers the jump), each handled with block-wide scans, so a
+// candidate costs O(len / nthreads) steps; trial lists are overlays (two substituted entries)
+// instead of copies; histogram quantiles are built with atomics and read with a chunked scan.
+// Thread 0 owns all list mutation; every helper returns block-uniform values.
+#pragma once
+#include "../../include/rsigpu.h"
+#include "cta.cuh"
+
+namespace rsigpu {
+
+typedef rsigpu_cnv Cnv;
+
+enum { CAND_ERR_HIST = 1, CAND_ERR_REFCAP = 2, CAND_ERR_LISTCAP = 4, CAND_ERR_DEGENERATE = 8 };
+
+struct CandCfg {
+  int m, maxchkbp, merge, tid;
+  double chklen, minmlen, buffer, p;
+  double rdmedian;  // rsi::RDmedian at the time of the call
+  double rdsd;      // rsi::RDsd
+  int span;         // rsi::end - rsi::start + 1 (length of the per-base array after N removal)
+};
+
+struct CandScratch {
+  int* ref;        int ref_cap;   // gathered neighbours
+  int* sub;        int sub_cap;   // sub-sampled ref + cnv (>= maxchkbp*10 + 2)
+  long long* pref;                // ref_cap + 1 prefix sums
+  float* rm;                      // ref_cap running means
+  unsigned* hist;  int hist_cap;  // histogram buckets
+  int* err;                       // sticky error bits (CAND_ERR_*)
+};
+
+RSI_DEV Cnv cnv_default() {  // cnv_st(), rsi.h:30-50
+  Cnv c;
+  c.tid = -1; c.type = RSIGPU_TYPE_UNKNOWN; c.geno = 0; c.status = 0; c.start = 0; c.end = 0; c.length = 0;
+  c.sc1 = 0; c.sc2 = 0; c.pair = 0; c.score = 0.0; c.p1 = 1.0; c.p2 = 1.0; c.cnvmed = 0; c.cnvsd = 0; c.cnviqr = 0;
+  c.refmed = 0; c.refsd = 0; c.refiqr = 0; c.q0 = -1.0; c.rp = -1; c.pad_ = 0;
+  return c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Phi(x) = (1 + erf(x / sqrt 2)) / 2 with the Cephes rational approximations ALGLIB uses.
+RSI_DEV double horner(const double* k, int n, double x) {  // k[0] is the leading coefficient
+  double r = 0.0;
+  for (int i = 0; i < n; ++i) r = k[i] + x * r;
+  return r;
+}
+RSI_DEV double erfc_tail(double x) {  // 0.5 <= x < 10
+  const double P[8] = {0.5641877825507397413087057563, 9.675807882987265400604202961, 77.08161730368428609781633646,
+                       368.5196154710010637133875746, 1143.262070703886173606073338, 2320.439590251635247384768711,
+                       2898.0293292167655611275846, 1826.3348842295112592168999};
+  const double Q[9] = {1.0, 17.14980943627607849376131193, 137.1255960500622202878443578, 661.7361207107653469211984771,
+                       2094.384367789539593790281779, 4429.612803883682726711528526, 6089.5424232724435504633068,
+                       4958.82756472114071495438422, 1826.3348842295112595576438};
+  return exp(-(x * x)) * horner(P, 8, x) / horner(Q, 9, x);
+}
+RSI_DEV double erf_small(double x) {  // 0 <= x < 0.5
+  const double P[7] = {0.007547728033418631287834, -0.288805137207594084924010, 14.3383842191748205576712,
+                       38.0140318123903008244444, 3017.82788536507577809226, 7404.07142710151470082064,
+                       80437.3630960840172832162};
+  const double Q[6] = {1.00000000000000000000000, 38.0190713951939403753468, 658.070155459240506326937,
+                       6379.60017324428279487120, 34216.5257924628539769006, 80437.3630960840172826266};
+  double xsq = x * x;
+  return 1.1283791670955125738961589031 * x * horner(P, 7, xsq) / horner(Q, 6, xsq);
+}
+RSI_DEV double phi(double v) {
+  double z = v / 1.41421356237309504880;
+  double s = z > 0 ? 1.0 : (z < 0 ? -1.0 : 0.0);
+  double a = fabs(z), e;
+  if (a < 0.5) e = s * erf_small(a);
+  else if (a >= 10) e = s;
+  else e = s * (1 - erfc_tail(a));
+  return 0.5 * (e + 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Histogram quartiles/median of x[0..n): bucket (x-ymin)/dy+0.5, value ymin+b*dy at the first bucket
+// whose running count reaches n/4, n/2, 3n/4; mean/min/max when the range is below dy.
+template <class T>
+RSI_DEVN void cta_hist_stat(const Cta& c, const CandScratch& S, const T* x, int n, double dy, double q[3]) {
+  double mn = 1e300, mx = -1e300, sm = 0.0;
+  for (int i = c.tid; i < n; i += c.nthr) {
+    double v = (double)x[i];
+    mn = v < mn ? v : mn; mx = v > mx ? v : mx; sm += v;
+  }
+  mn = c.reduce(mn, MinOp()); mx = c.reduce(mx, MaxOp()); sm = c.reduce(sm, SumOp());
+  q[0] = mn; q[1] = sm / (double)n; q[2] = mx;
+  if ((mx - mn) < dy) return;
+  const size_t np = (size_t)((mx - mn) / dy + 2);
+  if (np + 1 > (size_t)S.hist_cap) { if (c.tid == 0) *S.err |= CAND_ERR_HIST; return; }
+  for (size_t b = c.tid; b <= np; b += c.nthr) S.hist[b] = 0u;
+  c.sync();
+  for (int i = c.tid; i < n; i += c.nthr) {
+    double idx = ((double)x[i] - mn) / dy + 0.5;
+    cta_atomic_inc(&S.hist[(size_t)idx]);
+  }
+  c.sync();
+  const unsigned long long r4 = (unsigned long long)n / 4, r2 = (unsigned long long)n / 2, r34 = (unsigned long long)n * 3 / 4;
+  const size_t chunk = (np + c.nthr - 1) / c.nthr;
+  const size_t b0 = (size_t)c.tid * chunk, b1 = (b0 + chunk < np) ? b0 + chunk : np;
+  long long local = 0;
+  for (size_t b = b0; b < b1; ++b) local += S.hist[b];
+  long long tot;
+  long long run = c.scan_excl(local, &tot);
+  if (c.tid == 0) { c.bc[8] = q[0]; c.bc[9] = q[1]; c.bc[10] = q[2]; }
+  c.sync();
+  for (size_t b = b0; b < b1; ++b) {
+    unsigned long long cnt = S.hist[b], before = (unsigned long long)run, after = before + cnt;
+    if (before < r4 && after >= r4) c.bc[8] = mn + b * dy;
+    if (before < r2 && after >= r2) c.bc[9] = mn + b * dy;
+    if (before < r34 && after >= r34) c.bc[10] = mn + b * dy;
+    run += (long long)cnt;
+  }
+  c.sync();
+  q[0] = c.bc[8]; q[1] = c.bc[9]; q[2] = c.bc[10];
+  c.sync();
+}
+
+// ---------------------------------------------------------------------------------------------
+// A call list with up to two substituted entries (what the reference builds by copying the list).
+struct ListView {
+  const Cnv* base; int n;
+  int oi0; const Cnv* o0;
+  int oi1; const Cnv* o1;
+  RSI_DEV const Cnv& at(int j) const { return j == oi0 ? *o0 : (j == oi1 ? *o1 : base[j]); }
+};
+RSI_DEV ListView plain_view(const Cnv* base, int n) { ListView v; v.base = base; v.n = n; v.oi0 = -1; v.o0 = nullptr; v.oi1 = -1; v.o1 = nullptr; return v; }
+
+RSI_DEV bool nb_accept(int v, int flag, double up, double lo) {
+  if (flag == RSIGPU_TYPE_DEL && v > up) return false;
+  if (flag == RSIGPU_TYPE_DUP && v < lo) return false;
+  return true;
+}
+
+// Scan positions lo..hi (dir=+1) or hi..lo (dir=-1); store the first `want` accepted values to
+// dst[0..), in scan order.  Returns how many were stored (block-uniform).
+RSI_DEVN int cta_collect(const Cta& c, const int* RD, int lo, int hi, int dir, int flag, double up, double lw, int want, int* dst) {
+  int got = 0;
+  const int len = hi - lo + 1;
+  for (int base = 0; base < len && got < want; base += c.nthr) {
+    int j = base + c.tid, v = 0, ok = 0;
+    if (j < len) { v = RD[dir > 0 ? lo + j : hi - j]; ok = nb_accept(v, flag, up, lw) ? 1 : 0; }
+    int tot, ex = c.scan_excl(ok, &tot);
+    if (ok && got + ex < want) dst[got + ex] = v;
+    got = got + tot < want ? got + tot : want;
+  }
+  c.sync();
+  return got;
+}
+// First accepted position in scan order, or -1 (block-uniform).
+RSI_DEVN int cta_find_first(const Cta& c, const int* RD, int lo, int hi, int dir, int flag, double up, double lw) {
+  const int len = hi - lo + 1;
+  for (int base = 0; base < len; base += c.nthr) {
+    int j = base + c.tid, best = 0x7fffffff;
+    if (j < len && nb_accept(RD[dir > 0 ? lo + j : hi - j], flag, up, lw)) best = j;
+    best = c.reduce(best, MinOp());
+    if (best != 0x7fffffff) return dir > 0 ? lo + best : hi - best;
+  }
+  return -1;
+}
+
+// isitcnv: statistics of the candidate against the running mean of its neighbours; fills *out.
+RSI_DEVN void cnv_test_stats(const Cta& c, const CandCfg& P, const CandScratch& S, const int* ref, int nref, const int* cnv, int ncnv, Cnv* out) {
+  const int d = ncnv, nr = nref - d;
+  if (nr <= 0 || d <= 0) {  // the reference aborts here (Array bounds throw)
+    if (c.tid == 0) { out->status = -9; out->geno = 0; *S.err |= CAND_ERR_DEGENERATE; }
+    c.sync();
+    return;
+  }
+  // exact integer prefix sums of the neighbours (the reference slides a double sum of ints: exact)
+  long long carry = 0;
+  if (c.tid == 0) S.pref[0] = 0;
+  for (int base = 0; base < nref; base += c.nthr) {
+    int j = base + c.tid;
+    long long v = j < nref ? (long long)ref[j] : 0, tot;
+    long long ex = c.scan_excl(v, &tot);
+    if (j < nref) S.pref[j + 1] = carry + ex + v;
+    carry += tot;
+  }
+  c.sync();
+  double s1 = 0.0, s2 = 0.0;
+  for (int i = c.tid; i < nr; i += c.nthr) {
+    float mnv = (float)((double)(S.pref[i + d] - S.pref[i]) / (double)d);
+    S.rm[i] = mnv;
+    s1 += (double)mnv; s2 += (double)mnv * (double)mnv;
+  }
+  c.sync();
+  s1 = c.reduce(s1, SumOp()); s2 = c.reduce(s2, SumOp());
+  double rq[3], cq[3];
+  cta_hist_stat(c, S, S.rm, nr, 0.01, rq);
+  cta_hist_stat(c, S, cnv, ncnv, 1.0, cq);
+  long long a1 = 0, a2 = 0;
+  for (int i = c.tid; i < ncnv; i += c.nthr) { long long v = cnv[i]; a1 += v; a2 += v * v; }
+  a1 = c.reduce(a1, SumOp()); a2 = c.reduce(a2, SumOp());
+  if (c.tid == 0) {
+    double rmean = s1 / double(nr);
+    double rsd = sqrt(s2 / double(nr) - rmean * rmean);
+    const double rmed = rq[1];
+    if (rsd < 1E-3) rsd = rmed / 40.0 + 1E-3;
+    double cmean = (double)a1 / double(ncnv);
+    out->length = out->end - out->start + 1;
+    out->cnvmed = cq[1];
+    out->cnvsd = sqrt((double)a2 / double(ncnv) - cmean * cmean);
+    out->cnviqr = cq[2] - cq[0];
+    out->refmed = rmed;
+    out->refiqr = rq[2] - rq[0];
+    out->refsd = out->refiqr / 1.349;
+    out->geno = 1; out->status = 1;
+    int flag = out->cnvmed > P.rdmedian ? RSIGPU_TYPE_DUP : RSIGPU_TYPE_DEL;
+    if (out->type == RSIGPU_TYPE_UNKNOWN) out->type = flag;
+    if (out->type != flag) out->status = -9;  // "basic assignment error": geno stays 1
+    else if (out->type == RSIGPU_TYPE_DEL) {
+      double reference = rmed < P.rdmedian ? rmed : P.rdmedian;
+      if (reference < 0.8 * P.rdmedian) reference = 0.8 * P.rdmedian;
+      double nu = (3.0 * out->cnvmed - 2.0 * reference) / rsd;
+      out->p1 = phi(nu);
+      if (nu > 0) { out->status = -9; out->geno = 0; }
+    } else {
+      double reference = rmed > P.rdmedian ? rmed : P.rdmedian;
+      double nu = (2.5 * out->cnvmed - 3.0 * reference) / rsd / 1.5;
+      out->p1 = 1.0 - phi(nu);
+      if (nu < 0) { out->status = -9; out->geno = 0; }
+    }
+  }
+  c.sync();
+}
+
+// isitcnvwrap: gather <= chklen*d accepted neighbours per side around entry `ci` of the (overlaid)
+// list, then run the test.  `out` is the entry being tested (view.at(ci) must alias it).
+RSI_DEVN void cnv_test(const Cta& c, const CandCfg& P, const CandScratch& S, const int* RD, int n, const ListView& V, int ci, Cnv* out) {
+  const Cnv& me = V.at(ci);
+  const int flag = me.type, start = me.start, end = me.end;
+  const int cnvlen = end - start + 1, nl = V.n;
+  const int pts = P.maxchkbp * 10;
+  int d = cnvlen;
+  if (n == P.span) { if (d < P.m * P.minmlen) d = (int)(P.m * P.minmlen); }
+  if (n < P.span / 2) { if (d < P.minmlen) d = (int)P.minmlen + 1; }
+  const int refsize = (int)(P.chklen * d * 2);
+  const int buffer = (int)(cnvlen * P.buffer + 1);
+  const double up = P.rdmedian * 3.0, lw = P.rdmedian * 0.15;
+
+  // ---- left side, nearest first, then reversed into ascending position order
+  int i = start - buffer, idx = ci - 1;
+  while (i > 0 && idx > 0 && i < V.at(idx).start) --idx;
+  while (idx > 0 && V.at(idx).status == -9) --idx;
+  int k = (int)(P.chklen * d - 1);
+  if (n - end < P.chklen * d) k = refsize - 1 - n + end;
+  int nleft = 0;
+  const int left_want = k + 1;
+  bool overflow = false;
+  while (i > 2 && nleft < left_want) {
+    int lo = 2, zone = 0;
+    if (idx >= 0) {
+      const int s = V.at(idx).start, e = V.at(idx).end;
+      if (s > i - 1) { idx = -1; continue; }       // call lies right of the walk: it can never match again
+      if (e < i - 1) lo = e + 1 > 2 ? e + 1 : 2;   // free stretch down to the call's end
+      else { zone = 1; lo = s > 2 ? s : 2; }       // inside the call: first non-outlier triggers the jump
+    }
+    if (!zone) {
+      int want = left_want - nleft;
+      if (nleft + (want < i - lo ? want : i - lo) > S.ref_cap) { overflow = true; break; }
+      nleft += cta_collect(c, RD, lo, i - 1, -1, flag, up, lw, want, S.ref + nleft);
+      i = lo;
+    } else {
+      int f = cta_find_first(c, RD, lo, i - 1, -1, flag, up, lw);
+      if (f >= 0) { i = V.at(idx).start - 1; --idx; while (idx > 0 && V.at(idx).status == -9) --idx; }
+      else { i = lo; idx = -1; }
+    }
+  }
+  for (int j = c.tid; j < nleft / 2; j += c.nthr) { int a = S.ref[j], b = S.ref[nleft - 1 - j]; S.ref[j] = b; S.ref[nleft - 1 - j] = a; }
+  c.sync();
+
+  // ---- right side, ascending
+  int kk = nleft;
+  i = end + buffer; idx = ci + 1;
+  while (i < n - 2 && idx < nl && i > V.at(idx).end) ++idx;
+  while (idx < nl - 1 && V.at(idx).status == -9) ++idx;
+  while (!overflow && i < n - 2 && kk < refsize) {
+    int hi = n - 2, zone = 0;
+    if (idx < nl) {
+      const int s = V.at(idx).start, e = V.at(idx).end;
+      if (e < i + 1) { idx = nl; continue; }       // call lies left of the walk
+      if (s > i + 1) hi = s - 1 < n - 2 ? s - 1 : n - 2;
+      else { zone = 1; hi = e < n - 2 ? e : n - 2; }
+    }
+    if (!zone) {
+      int want = refsize - kk;
+      if (kk + (want < hi - i ? want : hi - i) > S.ref_cap) { overflow = true; break; }
+      kk += cta_collect(c, RD, i + 1, hi, +1, flag, up, lw, want, S.ref + kk);
+      i = hi;
+    } else {
+      int f = cta_find_first(c, RD, i + 1, hi, +1, flag, up, lw);
+      if (f >= 0) { i = V.at(idx).end + 1; ++idx; while (idx < nl - 1 && V.at(idx).status == -9) ++idx; }
+      else { i = hi; idx = nl; }
+    }
+  }
+  if (overflow) {
+    if (c.tid == 0) { *S.err |= CAND_ERR_REFCAP; out->status = -9; out->geno = 0; }
+    c.sync();
+    return;
+  }
+  const int* ref = S.ref; int nref = kk;
+  const int* cnv = RD + start; int ncnv = cnvlen;
+  if (nref + ncnv > pts) {  // sub-sample both to ~pts points, rsi.cpp:264-282
+    const int tot = nref + ncnv;
+    const int dref = (int)((double)nref / (double)tot * (double)pts);
+    const int dcnv = (int)((double)ncnv / (double)tot * (double)pts);
+    if (dref + dcnv > S.sub_cap) { if (c.tid == 0) { *S.err |= CAND_ERR_REFCAP; out->status = -9; out->geno = 0; } c.sync(); return; }
+    for (int a = c.tid; a < dcnv; a += c.nthr) S.sub[dref + a] = cnv[(int)(double(a) / double(dcnv) * double(ncnv))];
+    for (int a = c.tid; a < dref; a += c.nthr) S.sub[a] = ref[(int)(double(a) / double(dref) * double(nref))];
+    c.sync();
+    for (int a = c.tid; a < dref; a += c.nthr) S.ref[a] = S.sub[a];
+    c.sync();
+    nref = dref; cnv = S.sub + dref; ncnv = dcnv;
+  }
+  cnv_test_stats(c, P, S, ref, nref, cnv, ncnv, out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stable sort by start (after un-reversing entries): rank sort, O(n^2 / nthreads).
+RSI_DEVN void list_sort(const Cta& c, Cnv* list, int n, Cnv* tmp) {
+  for (int j = c.tid; j < n; j += c.nthr) if (list[j].start > list[j].end) { int t = list[j].start; list[j].start = list[j].end; list[j].end = t; }
+  c.sync();
+  for (int j = c.tid; j < n; j += c.nthr) {
+    int r = 0; const int sj = list[j].start;
+    for (int t = 0; t < n; ++t) { int st = list[t].start; r += (st < sj || (st == sj && t < j)) ? 1 : 0; }
+    tmp[r] = list[j];
+  }
+  c.sync();
+  for (int j = c.tid; j < n; j += c.nthr) list[j] = tmp[j];
+  c.sync();
+}
+
+// optimize_with_derivative for one call: dd(i) = sum RD[i-len,i) - sum RD[i,i+len) for i in
+// [nstart,nend); start -> first arg-max (DEL) / arg-min (DUP) over the first 2*disp values, end ->
+// the opposite over the last 2*disp; an extremum at offset 0 (or none beyond 0) changes nothing.
+RSI_DEVN void edge_refine(const Cta& c, const int* RD, int n, Cnv* cv) {
+  const int len = cv->end - cv->start + 1;
+  const int disp = 250 > len / 4 ? 250 : len / 4;
+  const int ns = cv->start - disp, ne = cv->end + disp;
+  const int type = cv->type;
+  c.sync();
+  if (ns < 2 * len || ne > n - 2 * len) return;
+  const int ndd = ne - ns;
+  long long a = 0;
+  for (int j = c.tid; j < len; j += c.nthr) a += (long long)RD[ns - len + j] - (long long)RD[ns + j];
+  const long long dd0 = c.reduce(a, SumOp());
+  const int tail0 = ndd - 2 * disp;
+  ValIdx headbest; headbest.v = 0.0; headbest.i = -1;   // running extremum over the head window
+  ValIdx tailbest; tailbest.v = 0.0; tailbest.i = -1;
+  const double hs = type == RSIGPU_TYPE_DEL ? 1.0 : -1.0;  // DEL: head max / tail min; DUP: head min / tail max
+  long long carry = dd0;
+  for (int base = 0; base < ndd; base += c.nthr) {
+    int j = base + c.tid;  // dd index
+    long long inc = 0;
+    if (j < ndd && j >= 1) { int p = ns + j; inc = -(long long)RD[p - 1 - len] + 2ll * RD[p - 1] - (long long)RD[p - 1 + len]; }
+    long long tot, ex = c.scan_excl(inc, &tot);
+    double ddj = (double)(carry + ex + inc);
+    if (j < ndd && (type == RSIGPU_TYPE_DEL || type == RSIGPU_TYPE_DUP)) {
+      if (j < 2 * disp && hs * ddj > headbest.v) { headbest.v = hs * ddj; headbest.i = j; }
+      if (j >= tail0 && -hs * ddj > tailbest.v) { tailbest.v = -hs * ddj; tailbest.i = j; }
+    }
+    carry += tot;
+  }
+  // per-thread candidates are each thread's first strict maximum in ascending j; merge with first-index ties
+  if (headbest.i < 0) { headbest.v = 0.0; headbest.i = 0x7fffffffffffll; }
+  if (tailbest.i < 0) { tailbest.v = 0.0; tailbest.i = 0x7fffffffffffll; }
+  headbest = c.reduce(headbest, ArgMaxFirst());
+  tailbest = c.reduce(tailbest, ArgMaxFirst());
+  c.sync();
+  if (c.tid == 0) {
+    if (headbest.v > 0.0 && headbest.i > 0 && headbest.i < ndd) cv->start = ns + (int)headbest.i;
+    if (tailbest.v > 0.0 && tailbest.i > 0 && tailbest.i < ndd) cv->end = ne - ndd + (int)tailbest.i;
+  }
+  c.sync();
+}
+
+RSI_DEVN double cta_mean(const Cta& c, const int* RD, int lo, int hi) {  // mean_tp: exact integer sum / count
+  long long a = 0;
+  for (int j = lo + c.tid; j <= hi; j += c.nthr) a += RD[j];
+  a = c.reduce(a, SumOp());
+  return (double)a / double(hi - lo + 1);
+}
+
+// remove status == -9 entries in place, keeping order (thread 0)
+RSI_DEV int list_drop_deleted(const Cta& c, Cnv* list, int n) {
+  int w = n;
+  c.sync();
+  if (c.tid == 0) { w = 0; for (int j = 0; j < n; ++j) if (list[j].status != -9) { if (w != j) list[w] = list[j]; ++w; } }
+  return cta_bcast(c, w, 0);
+}
+
+// mergesegments.  `ov` = two scratch entries in global memory for the overlays.
+RSI_DEVN int merge_segments(const Cta& c, const CandCfg& P, const CandScratch& S, const int* RD, int n, Cnv* list, int nl, Cnv* ov) {
+  Cnv* A = ov; Cnv* B = ov + 1;
+  for (int i = 0; i < nl - 1; ++i) {
+    c.sync();
+    const Cnv x = list[i], y = list[i + 1];
+    if (x.type != y.type) continue;
+    const int mxs = x.start > y.start ? x.start : y.start, mne = x.end < y.end ? x.end : y.end;
+    if (!(mxs < mne)) continue;
+    if (c.tid == 0) {
+      *A = x; A->start = x.start < y.start ? x.start : y.start; A->end = x.end > y.end ? x.end : y.end;
+      *B = *A; B->status = -9;
+    }
+    c.sync();
+    ListView V = plain_view(list, nl); V.oi0 = i; V.o0 = A; V.oi1 = i + 1; V.o1 = B;
+    cnv_test(c, P, S, RD, n, V, i, A);
+    int geno = A->geno;
+    c.sync();
+    if (geno == 0) {
+      if (c.tid == 0) { *A = x; *B = y; B->status = -9; }
+      c.sync();
+      cnv_test(c, P, S, RD, n, V, i, A);
+      if (c.tid == 0) { A->status = -9; B->status = 0; }
+      c.sync();
+      cnv_test(c, P, S, RD, n, V, i + 1, B);
+      if (c.tid == 0) {
+        if (B->p1 < A->p1) *A = *B;
+        if (A->p1 > P.p) { list[i].status = -9; list[i + 1].status = -9; }
+      }
+      c.sync();
+      geno = A->geno;
+      c.sync();
+    }
+    if (geno == 0) continue;
+    if (c.tid == 0) { list[i] = *A; list[i].status = -9; list[i + 1] = *A; list[i + 1].status = 0; }
+    c.sync();
+  }
+  nl = list_drop_deleted(c, list, nl);
+  if (!P.merge) return nl;
+  for (int i = 0; i < nl - 1; ++i) {
+    c.sync();
+    const Cnv x = list[i], y = list[i + 1];
+    if (x.type != y.type) continue;
+    if (x.geno == 0 || y.geno == 0) continue;
+    const int gap = y.start - x.end;
+    if (gap > (x.end - x.start) * P.chklen * 0.7 && gap > (y.end - y.start) * P.chklen * 0.7) continue;
+    const double m1 = cta_mean(c, RD, x.start, x.end), m2 = cta_mean(c, RD, y.start, y.end);
+    const double cm = (m1 * (x.end - x.start) + m2 * (y.end - y.start)) / ((x.end - x.start) + (y.end - y.start));
+    const double mm = cta_mean(c, RD, x.start, y.end);
+    if (x.type == RSIGPU_TYPE_DEL && mm > cm + 1.5 * y.refsd + 1.5 * x.refsd) continue;
+    if (x.type == RSIGPU_TYPE_DUP && mm < cm - 1.5 * y.refsd - 1.5 * x.refsd) continue;
+    if (c.tid == 0) { *A = x; A->end = y.end; *B = *A; B->status = -9; }
+    c.sync();
+    ListView V = plain_view(list, nl); V.oi0 = i; V.o0 = A; V.oi1 = i + 1; V.o1 = B;
+    cnv_test(c, P, S, RD, n, V, i, A);
+    const int geno = A->geno;
+    c.sync();
+    if (geno == 0) continue;
+    if (c.tid == 0) { list[i] = *A; list[i + 1] = *A; list[i].status = -9; }
+    c.sync();
+  }
+  return list_drop_deleted(c, list, nl);
+}
+
+// multisegments as a generator: nested sub-level runs of a failed segment, in the reference's
+// order (level ascending, position ascending), the last run of every level dropped.
+struct SubsegIter {
+  int seg_start, len, lo, hi, level, pos, open, s0, s1;
+};
+RSI_DEV void subseg_begin(SubsegIter& it, const Cnv& seg, const int* status) {
+  it.seg_start = seg.start; it.len = seg.end - seg.start + 1;
+  const int* s2 = status + seg.start;
+  it.lo = s2[0]; it.hi = s2[0];
+  for (int i = 0; i < it.len; ++i) { it.lo = s2[i] < it.lo ? s2[i] : it.lo; it.hi = s2[i] > it.hi ? s2[i] : it.hi; }
+  it.level = it.lo; it.pos = 0; it.open = 0; it.s0 = it.s1 = 0;
+}
+RSI_DEV bool subseg_in_level(int v, int lev) { return v != 0 && ((lev < 0 && v < 0 && v >= lev) || (lev > 0 && v > 0 && v <= lev)); }
+// thread 0 only; returns true and fills (a,b) (absolute bin coordinates) for the next sub-segment
+RSI_DEV bool subseg_next(SubsegIter& it, const int* status, int* a, int* b) {
+  const int* s2 = status + it.seg_start;
+  while (it.level < it.hi) {
+    if (it.level == 0) { ++it.level; it.pos = 0; it.open = 0; continue; }
+    if (it.pos == 0 && !it.open) {  // levelcount test
+      int hits = 0;
+      for (int i = 0; i < it.len; ++i) hits += s2[i] == it.level;
+      if (hits == 0) { ++it.level; continue; }
+    }
+    while (it.pos < it.len) {
+      int i = it.pos++;
+      if (!subseg_in_level(s2[i], it.level)) continue;
+      if (!it.open) { it.open = 1; it.s0 = it.s1 = i; continue; }
+      if (i - it.s1 <= 1) { it.s1 = i; continue; }
+      *a = it.s0 + it.seg_start; *b = it.s1 + it.seg_start;
+      it.s0 = it.s1 = i;
+      return true;
+    }
+    ++it.level; it.pos = 0; it.open = 0;  // the open run of this level is never emitted
+  }
+  return false;
+}
+
+// areblockscnv on the bin arrays.
+RSI_DEVN void blocks_test(const Cta& c, const CandCfg& P, const CandScratch& S, const int* medint, const int* status, int nb, Cnv* list, int nl, Cnv* ov) {
+  for (int i = 0; i < nl; ++i) cnv_test(c, P, S, medint, nb, plain_view(list, nl), i, &list[i]);
+  Cnv* T = ov;       // entry under test (overlay of list[i])
+  Cnv* best = ov + 1;
+  for (int i = 0; i < nl; ++i) {
+    c.sync();
+    const Cnv orig = list[i];
+    if (orig.status != -9) continue;
+    if ((orig.type == RSIGPU_TYPE_DEL && orig.cnvmed < 0.7 * orig.refmed) || (orig.type == RSIGPU_TYPE_DUP && orig.cnvmed > 1.3 * orig.refmed)) {
+      if (c.tid == 0) { list[i].geno = 1; list[i].p1 = P.p; }
+      c.sync();
+      continue;
+    }
+    SubsegIter it;
+    if (c.tid == 0) { subseg_begin(it, orig, status); *best = orig; }
+    int have_pass = 0, bestlen = -1;  // thread 0's view
+    for (;;) {
+      int a = 0, b = 0, more = 0;
+      if (c.tid == 0) more = subseg_next(it, status, &a, &b) ? 1 : 0;
+      more = cta_bcast(c, more, 1);
+      if (!more) break;
+      if (c.tid == 0) { *T = cnv_default(); T->start = a; T->end = b; T->type = orig.type; }
+      c.sync();
+      ListView V = plain_view(list, nl); V.oi0 = i; V.o0 = T;
+      cnv_test(c, P, S, medint, nb, V, i, T);
+      if (c.tid == 0 && T->geno != 0) {
+        // The reference scans the sub-segments from the last to the first and replaces its pick by
+        // every STRICTLY longer passing one (the first passing one unconditionally when the
+        // original failed with geno 0) => the longest passing sub-segment, latest-generated on
+        // ties; when the original kept geno 1 it additionally has to be longer than the original.
+        const bool qualifies = orig.geno == 0 || T->length > orig.length;
+        if (qualifies && T->length >= bestlen) { *best = *T; bestlen = T->length; have_pass = 1; }
+      }
+      c.sync();
+    }
+    (void)have_pass;
+    if (c.tid == 0) list[i] = *best;
+    c.sync();
+  }
+}
+
+// expand_coordinate: compacted index -> reference coordinate through the N-interval table
+RSI_DEV int expand_coord(int p, const int* nbeg, const int* nend, int nn) {
+  if (nn == 0) return p;
+  int dx = 0, prev_brk = 0, prev_inc = 0;
+  for (int i = 0; i < nn; ++i) {
+    dx += nend[i] - nbeg[i] + 1;
+    int brk = nend[i] + 1 - dx;
+    if (i == 0 && p < brk) return p;
+    if (i > 0 && p >= prev_brk && p < brk) return p + prev_inc;
+    prev_brk = brk; prev_inc = dx;
+  }
+  return p + prev_inc;  // p >= last break
+}
+
+// sd_filters (thread 0)
+RSI_DEV int sd_filter_list(const CandCfg& P, Cnv* list, int n) {
+  const int minlen = P.m * 2 > 500 ? P.m * 2 : 500;
+  const double tsd = P.rdsd / 1.2;
+  int w = 0;
+  for (int j = 0; j < n; ++j) {
+    const Cnv& x = list[j];
+    bool keep = true;
+    int span = x.end - x.start; if (span < 0) span = -span;
+    if (span < 1000) keep = false;
+    if (x.type == RSIGPU_TYPE_DEL) {
+      if (x.p1 > 0.2) keep = false;
+      if (x.refsd > 0.6 * tsd) keep = false;
+      if (x.cnvsd > 1.3 * tsd) keep = false;
+      if (x.cnvsd * P.rdmedian > 2.5 * x.cnvmed * tsd) keep = false;
+      const double mn = P.rdmedian < x.refmed ? P.rdmedian : x.refmed;
+      if (x.cnvmed < 0.66 * mn && x.cnvsd < tsd && span > 800) keep = true;
+    }
+    if (x.type == RSIGPU_TYPE_DUP) {
+      if (x.p1 > 0.05) keep = false;
+      if (x.refsd > 0.6 * tsd) keep = false;
+      if (x.cnvsd * P.rdmedian > 2.0 * x.cnvmed * tsd) keep = false;
+    }
+    if (span < minlen) keep = false;
+    if (keep) { if (w != j) list[w] = list[j]; ++w; }
+  }
+  return w;
+}
+
+// Dump buffers for the parity tests (RSIGPU_ARR_SEGMENTS .. DETECTED)
+struct CandDumps { Cnv* blocks; int* n_blocks; Cnv* premerge; int* n_premerge; Cnv* merged; int* n_merged; int cap; };
+RSI_DEV void dump_list(const Cta& c, const Cnv* list, int n, Cnv* dst, int* ndst, int cap) {
+  if (!dst) return;
+  for (int j = c.tid; j < n && j < cap; j += c.nthr) dst[j] = list[j];
+  if (c.tid == 0) *ndst = n;
+  c.sync();
+}
+
+// detectcnv from areblockscnv onwards (rsi.cpp:1839-1931).  `list` holds the rsi segments of one
+// transformation in bin coordinates (nl of them); the result (reference coordinates) is left in
+// `list`, its length returned.  For -ALL the caller runs blocks_test per transformation and passes
+// skip_blocks = 1 with the concatenated list.
+RSI_DEVN int candidates_main(const Cta& c, CandCfg P, const CandScratch& S, const int* RD, int n, const int* medint, const int* status, int nb,
+                             const int* nbeg, const int* nend, int nn, Cnv* list, int nl, Cnv* tmp, Cnv* ov, const CandDumps& D, int skip_blocks) {
+  if (!skip_blocks) blocks_test(c, P, S, medint, status, nb, list, nl, ov);
+  dump_list(c, list, nl, D.blocks, D.n_blocks, D.cap);
+  list_sort(c, list, nl, tmp);
+  // bins -> bases
+  c.sync();
+  if (c.tid == 0) {
+    int w = 0;
+    for (int j = 0; j < nl; ++j) {
+      Cnv x = list[j];
+      if (x.geno == 0) continue;
+      if (x.start == x.end) continue;
+      x.start = x.start * P.m + P.m / 2;
+      x.end = x.end * P.m + P.m / 2;
+      if (x.start < 0) x.start = 0;
+      if (x.end > n - 1) x.end = n - 1;
+      x.length = x.end - x.start + 1;
+      x.tid = P.tid;
+      list[w++] = x;
+    }
+    nl = w;
+  }
+  nl = cta_bcast(c, nl, 2);
+  for (int rep = 0; rep < 2; ++rep) for (int j = 0; j < nl; ++j) edge_refine(c, RD, n, &list[j]);
+  list_sort(c, list, nl, tmp);
+  dump_list(c, list, nl, D.premerge, D.n_premerge, D.cap);
+  nl = merge_segments(c, P, S, RD, n, list, nl, ov);
+  list_sort(c, list, nl, tmp);
+  dump_list(c, list, nl, D.merged, D.n_merged, D.cap);
+  // final test on the per-base array, score, N-overlap filter, coordinates back to the reference
+  for (int j = 0; j < nl; ++j) {
+    cnv_test(c, P, S, RD, n, plain_view(list, nl), j, &list[j]);
+    if (c.tid == 0) {
+      Cnv& x = list[j];
+      const double len = double(x.end - x.start + 1) / double(P.m);
+      x.score = (x.cnvmed - P.rdmedian) * sqrt(len);
+      const int p1 = expand_coord(x.start, nbeg, nend, nn), p2 = expand_coord(x.end, nbeg, nend, nn);
+      for (int k = 0; k < nn; ++k) { int a = p1 > nbeg[k] ? p1 : nbeg[k], b = p2 < nend[k] ? p2 : nend[k]; if (a <= b) x.status = -9; }
+    }
+    c.sync();
+  }
+  nl = list_drop_deleted(c, list, nl);
+  if (c.tid == 0) for (int j = 0; j < nl; ++j) { list[j].start = expand_coord(list[j].start, nbeg, nend, nn); list[j].end = expand_coord(list[j].end, nbeg, nend, nn); }
+  c.sync();
+  return nl;
+}
+
+}  // namespace rsigpu

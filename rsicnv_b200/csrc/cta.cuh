@@ -1,0 +1,137 @@
+// cta.cuh -- cooperative-thread-array primitives used by the candidate stage (candidates.cuh).
+//
+// The candidate logic of the path (isitcnvwrap / areblockscnv / mergesegments ..., SURVEY.md §8a
+// a19-a25) is list-sequential on the outside and data-parallel on the inside, so it runs as ONE
+// thread block per contig: thread 0 does the list bookkeeping, all threads do the gathers, scans,
+// histograms and reductions.  Everything here is written against `Cta`, which on the GPU wraps
+// threadIdx / __syncthreads / warp shuffles.  When this header is compiled WITHOUT nvcc (only
+// tests/hostsim does that) `Cta` degenerates to a 1-thread block so the same control flow can be
+// unit-tested against the oracle on a machine without a GPU.  The product never takes that path:
+// librsigpu.so is built by nvcc only and there is no host entry into this code.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define RSI_DEV __device__ __forceinline__
+#define RSI_DEVN __device__ __noinline__
+#else
+#define RSI_DEV inline
+#define RSI_DEVN inline
+#endif
+
+namespace rsigpu {
+
+struct MinOp { template <class T> RSI_DEV T operator()(T a, T b) const { return b < a ? b : a; } };
+struct MaxOp { template <class T> RSI_DEV T operator()(T a, T b) const { return b > a ? b : a; } };
+struct SumOp { template <class T> RSI_DEV T operator()(T a, T b) const { return a + b; } };
+
+// (value, index) pair for arg-max / arg-min with "first index wins" ties
+struct ValIdx { double v; long long i; };
+struct ArgMaxFirst { RSI_DEV ValIdx operator()(ValIdx a, ValIdx b) const { return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a; } };
+struct ArgMinFirst { RSI_DEV ValIdx operator()(ValIdx a, ValIdx b) const { return (b.v < a.v || (b.v == a.v && b.i < a.i)) ? b : a; } };
+
+#if defined(__CUDACC__)
+
+template <class T>
+RSI_DEV T shfl_xor_any(T v, int lane_mask) {
+  static_assert(sizeof(T) % 4 == 0, "4-byte multiple");
+  unsigned w[sizeof(T) / 4];
+  memcpy(w, &v, sizeof(T));
+#pragma unroll
+  for (int k = 0; k < (int)(sizeof(T) / 4); ++k) w[k] = __shfl_xor_sync(0xffffffffu, w[k], lane_mask);
+  memcpy(&v, w, sizeof(T));
+  return v;
+}
+
+struct Cta {
+  int tid, nthr;
+  unsigned char* red;  // shared scratch, >= 33 * 16 bytes
+  double* bc;          // shared broadcast area, >= 16 doubles
+
+  RSI_DEV void sync() const { __syncthreads(); }
+
+  // block-wide reduction, result returned to every thread
+  template <class T, class Op>
+  RSI_DEV T reduce(T v, Op op) const {
+    static_assert(sizeof(T) <= 16, "reduce payload");
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = op(v, shfl_xor_any(v, o));
+    T* slots = reinterpret_cast<T*>(red);
+    const int warp = tid >> 5, lane = tid & 31, nw = (nthr + 31) >> 5;
+    __syncthreads();
+    if (lane == 0) slots[warp] = v;
+    __syncthreads();
+    T r = slots[0];
+    for (int w = 1; w < nw; ++w) r = op(r, slots[w]);
+    return r;
+  }
+  // block-wide exclusive prefix sum of one value per thread (thread order); *total to every thread
+  template <class T>
+  RSI_DEV T scan_excl(T v, T* total) const {
+    const int warp = tid >> 5, lane = tid & 31, nw = (nthr + 31) >> 5;
+    T inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      T up = shfl_up_any(inc, o);
+      if (lane >= o) inc += up;
+    }
+    T* slots = reinterpret_cast<T*>(red);
+    __syncthreads();
+    if (lane == 31) slots[warp] = inc;
+    __syncthreads();
+    T base = 0, tot = 0;
+    for (int w = 0; w < nw; ++w) { T s = slots[w]; if (w < warp) base += s; tot += s; }
+    *total = tot;
+    return base + inc - v;
+  }
+  template <class T>
+  static RSI_DEV T shfl_up_any(T v, int d) {
+    unsigned w[sizeof(T) / 4];
+    memcpy(w, &v, sizeof(T));
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(T) / 4); ++k) w[k] = __shfl_up_sync(0xffffffffu, w[k], d);
+    memcpy(&v, w, sizeof(T));
+    return v;
+  }
+};
+
+RSI_DEV void cta_atomic_inc(unsigned* p) { atomicAdd(p, 1u); }
+RSI_DEV void cta_atomic_max(int* p, int v) { atomicMax(p, v); }
+RSI_DEV void cta_atomic_min(int* p, int v) { atomicMin(p, v); }
+
+#else  // ---- host simulation: a block of one thread (tests/hostsim only) ----
+
+struct Cta {
+  int tid = 0, nthr = 1;
+  unsigned char* red = nullptr;
+  double* bc = nullptr;
+  void sync() const {}
+  template <class T, class Op> T reduce(T v, Op) const { return v; }
+  template <class T> T scan_excl(T v, T* total) const { *total = v; return T(0); }
+};
+inline void cta_atomic_inc(unsigned* p) { *p += 1u; }
+inline void cta_atomic_max(int* p, int v) { if (v > *p) *p = v; }
+inline void cta_atomic_min(int* p, int v) { if (v < *p) *p = v; }
+
+#endif
+
+// thread 0 publishes a value (<= 8 bytes) to the whole block through the broadcast area
+template <class T>
+RSI_DEV T cta_bcast(const Cta& c, T v, int slot) {
+#if defined(__CUDACC__)
+  static_assert(sizeof(T) <= 8, "bcast payload");
+  c.sync();
+  if (c.tid == 0) memcpy(&c.bc[slot], &v, sizeof(T));
+  c.sync();
+  T r;
+  memcpy(&r, &c.bc[slot], sizeof(T));
+  return r;
+#else
+  (void)c; (void)slot;
+  return v;
+#endif
+}
+
+}  // namespace rsigpu

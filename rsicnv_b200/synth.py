@@ -157,3 +157,45 @@ def write_depth_file(path: str, depth: np.ndarray, chunk: int = 4_000_000) -> No
             pos = np.arange(a + 1, a + 1 + len(d))
             f.write("\n".join(f"{p}\t{v}" for p, v in zip(pos.tolist(), d.tolist())).encode())
             f.write(b"\n")
+
+
+def stress_events(L: int, seed: int, n_blocks) -> list[tuple[int, int, float]]:
+    """Adversarial event layout for the candidate stage: same-type neighbours separated by short gaps
+    (merge paths), nested copy-number levels (multi-level RSI status -> multisegments), weak events
+    that fail the depth test, events hugging contig ends and N blocks."""
+    rng = np.random.default_rng(seed + 101)
+    ev: list[tuple[int, int, float]] = []
+    free = []
+    prev = 0
+    for a, b in sorted(n_blocks) + [(L, L)]:
+        if a - prev > 60_000:
+            free.append((prev + 3_000, a - 3_000))
+        prev = b
+    factors = [0.5, 1.5, 0.0, 2.0, 0.8, 1.2, 0.65, 1.35]
+    for lo, hi in free:
+        p = lo + int(rng.integers(500, 4_000))
+        while p < hi - 40_000:
+            kind = int(rng.integers(0, 5))
+            f = factors[int(rng.integers(0, len(factors)))]
+            ln = int(rng.choice([600, 1200, 2500, 5000, 9000, 20000]))
+            if kind == 0:      # isolated
+                ev.append((p, p + ln, f)); p += ln
+            elif kind == 1:    # two same-type events with a short gap
+                g = int(rng.choice([150, 400, 900, 2500]))
+                ev.append((p, p + ln, f)); ev.append((p + ln + g, p + 2 * ln + g, f)); p += 2 * ln + g
+            elif kind == 2:    # nested: outer mild, inner strong
+                inner = ln // 3
+                ev.append((p, p + ln, 0.6 if f < 1 else 1.4))
+                ev.append((p + inner, p + 2 * inner, 0.1 if f < 1 else 2.2)); p += ln
+            elif kind == 3:    # staircase of three levels
+                ev.append((p, p + ln, 0.75 if f < 1 else 1.25)); ev.append((p + ln, p + 2 * ln, 0.5 if f < 1 else 1.5))
+                ev.append((p + 2 * ln, p + 3 * ln, 0.25 if f < 1 else 1.75)); p += 3 * ln
+            else:              # opposite types back to back
+                ev.append((p, p + ln, 0.5)); ev.append((p + ln + 300, p + 2 * ln + 300, 1.5)); p += 2 * ln + 300
+            p += int(rng.integers(3_000, 60_000))
+    return [(s, e, f) for s, e, f in ev if e < L]
+
+
+def apply_events(cn: np.ndarray, events) -> None:
+    for s, e, f in events:
+        cn[s:e] = f
