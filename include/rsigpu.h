@@ -153,6 +153,10 @@ int rsigpu_last_stage_ms(const rsigpu_ctx* c, float* ms6);
 int rsigpu_set_profile(rsigpu_ctx* c, int on);
 int rsigpu_get_profile(const rsigpu_ctx* c, char* names, int32_t name_stride, float* ms, int32_t* launches, int32_t cap);
 
+/* test hook: filterstatus' level-0 float sum (rsi.cpp:967-974) as 0 = one sequential FADD chain,
+ * 1 = the exact block-scan form (default); both must give identical bits. */
+int rsigpu_set_level0_mode(rsigpu_ctx* c, int mode);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,279 @@
+"""Python host-side mirror of the reference's seams for the `rsicnv rsi` path, over the C ABI in
+include/rsigpu.h (ctypes; no torch types cross the boundary).
+
+The method names follow the reference functions they stand for (file:line relative to the reference's
+src/): `load_finish` = checkgccontent + apply_cap + concatenate_data + the chromosome statistics of
+main() (gccontent.cpp:95, loaddata.cpp:229, 48, rsi.cpp:2202), `detectcnv` (rsi.cpp:1795),
+`sd_filters` (rsi.cpp:1753), `cnv_stat` (pairrd.cpp:622), `write_cnv_to_file` (rsi.cpp:1592).
+
+There is no CPU implementation behind this module: the shared library is built by nvcc for sm_100a and
+`load_library()` raises if it is missing; `Context()` raises if there is no CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.join(_HERE, "librsigpu.so")
+
+TYPE_NAMES = ("DEL", "DUP", "UNKNOWN")
+TRANS = {"NBN": 0, "NB": 0, "MED": 1, "ALL": 2}
+
+ARR_RAW_DEPTH, ARR_DEPTH, ARR_BIN_MED, ARR_BIN_NBN, ARR_BIN_MEDINT, ARR_BIN_STATUS, ARR_NOSEQ_BEG, ARR_NOSEQ_END, \
+    ARR_BIN_STATUS1, ARR_SEGMENTS, ARR_BLOCKS, ARR_PREMERGE, ARR_MERGED, ARR_DETECTED = range(14)
+_ARR_DTYPE = {ARR_RAW_DEPTH: np.int32, ARR_DEPTH: np.int32, ARR_BIN_MED: np.float32, ARR_BIN_NBN: np.float32,
+              ARR_BIN_MEDINT: np.int32, ARR_BIN_STATUS: np.int32, ARR_NOSEQ_BEG: np.int32, ARR_NOSEQ_END: np.int32,
+              ARR_BIN_STATUS1: np.int32}
+
+ERRORS = {1: "CUDA error", 2: "bad argument / call order", 3: "input outside the supported range", 4: "output buffer too small",
+          5: "no CUDA device (there is no CPU fallback)"}
+
+
+class RsiGpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"rsigpu error {code} ({ERRORS.get(code, '?')}): {msg}")
+        self.code = code
+
+
+class Params(C.Structure):
+    """rsigpu_params: the tunables get_parameters() fills (rsi.cpp:1986-2068)"""
+    _fields_ = [("m", C.c_int32), ("minq", C.c_int32), ("min_baseQ", C.c_int32), ("gcadjust", C.c_int32), ("trans", C.c_int32),
+                ("merge", C.c_int32), ("maxchkbp", C.c_int32), ("reserved_", C.c_int32), ("cap", C.c_double),
+                ("threshold", C.c_double), ("epsilon", C.c_double), ("chklen", C.c_double)]
+
+
+class Cnv(C.Structure):
+    """rsigpu_cnv: flat mirror of cnv_st (rsi.h:8-51)"""
+    _fields_ = [(n, C.c_int32) for n in ("tid", "type", "geno", "status", "start", "end", "length", "sc1", "sc2", "pair")] + \
+               [(n, C.c_double) for n in ("score", "p1", "p2", "cnvmed", "cnvsd", "cnviqr", "refmed", "refsd", "refiqr", "q0")] + \
+               [("rp", C.c_int32), ("pad_", C.c_int32)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_ if n != "pad_"}
+
+
+class ReadBatch(C.Structure):
+    _fields_ = [("n_reads", C.c_int64), ("tid", C.c_int32), ("reserved_", C.c_int32), ("pos", C.c_void_p), ("mpos", C.c_void_p),
+                ("isize", C.c_void_p), ("mtid", C.c_void_p), ("flag", C.c_void_p), ("mapq", C.c_void_p), ("cigar_off", C.c_void_p),
+                ("cigar", C.c_void_p), ("qual_off", C.c_void_p), ("qual", C.c_void_p)]
+
+
+class ChrStats(C.Structure):
+    _fields_ = [("rdmedian", C.c_double), ("rdsd", C.c_double), ("tmedian", C.c_double), ("tlamda", C.c_double), ("rdmad", C.c_double),
+                ("target_len", C.c_int32), ("compact_len", C.c_int32), ("nbins", C.c_int32), ("lmax", C.c_int32),
+                ("isize_mean", C.c_int32), ("isize_sd", C.c_int32), ("n_noseq", C.c_int32), ("reserved_", C.c_int32)]
+
+
+EXPORTS = ("rsigpu_default_params", "rsigpu_create", "rsigpu_destroy", "rsigpu_last_error", "rsigpu_num_devices", "rsigpu_set_reference",
+           "rsigpu_set_depth", "rsigpu_pileup_begin", "rsigpu_pileup_push", "rsigpu_pileup_end", "rsigpu_load_finish", "rsigpu_detectcnv",
+           "rsigpu_sd_filters", "rsigpu_cnv_stat", "rsigpu_get_calls", "rsigpu_run", "rsigpu_get_chr_stats", "rsigpu_get_array",
+           "rsigpu_format_row", "rsigpu_launch_count", "rsigpu_last_stage_ms", "rsigpu_set_profile", "rsigpu_get_profile",
+           "rsigpu_set_level0_mode")
+
+_libs: dict[str, C.CDLL] = {}
+
+
+def load_library(path: str | None = None) -> C.CDLL:
+    path = os.path.abspath(path or DEFAULT_LIB)
+    if path in _libs:
+        return _libs[path]
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: build it with `make lib` (nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(path)
+    lib.rsigpu_last_error.restype = C.c_char_p
+    lib.rsigpu_launch_count.restype = C.c_int64
+    lib.rsigpu_destroy.restype = None
+    for name in EXPORTS:
+        getattr(lib, name)  # raises AttributeError if the ABI is incomplete
+    _libs[path] = lib
+    return lib
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+class Context:
+    """One contig on one GPU: what one iteration of the reference's chromosome loop owns (rsi.cpp:2189-2217)."""
+
+    def __init__(self, device: int = 0, lib: str | None = None, m=101, minq=0, min_baseQ=13, cap=4.0, gcadjust=True, trans="NBN",
+                 merge=True, threshold=-1.0, epsilon=1.5, chklen=2.5, maxchkbp=100000):
+        self.lib = load_library(lib)
+        p = Params()
+        self.lib.rsigpu_default_params(C.byref(p))
+        p.m = m; p.minq = minq; p.min_baseQ = min_baseQ; p.cap = cap; p.gcadjust = 1 if gcadjust else 0
+        p.trans = TRANS[trans] if isinstance(trans, str) else int(trans)
+        p.merge = 1 if merge else 0; p.threshold = threshold; p.epsilon = epsilon; p.chklen = chklen; p.maxchkbp = maxchkbp
+        self.params = p
+        self.m = m if m % 2 == 1 else m + 1
+        h = C.c_void_p()
+        rc = self.lib.rsigpu_create(C.c_int(device), C.byref(p), C.byref(h))
+        if rc != 0:
+            raise RsiGpuError(rc, "rsigpu_create failed")
+        self.h = h
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rsigpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise RsiGpuError(rc, (self.lib.rsigpu_last_error(self.h) or b"").decode())
+
+    # ---- inputs
+    def set_reference(self, fasta: np.ndarray, tid: int = 0):
+        """read_fasta output for one contig (readref.cpp:10-86): uint8 ASCII, newlines stripped"""
+        fasta = np.ascontiguousarray(fasta, dtype=np.uint8)
+        self._ck(self.lib.rsigpu_set_reference(self.h, _ptr(fasta), C.c_int32(len(fasta)), C.c_int32(tid)))
+        self.L = len(fasta)
+
+    def set_reference_ptr(self, ptr: int, n: int, tid: int = 0):
+        self._ck(self.lib.rsigpu_set_reference(self.h, C.c_void_p(ptr), C.c_int32(n), C.c_int32(tid)))
+        self.L = n
+
+    def set_depth(self, depth: np.ndarray):
+        """the array load_data_from_text builds (loaddata.cpp:496-517)"""
+        depth = np.ascontiguousarray(depth, dtype=np.int32)
+        self._keep = [depth]
+        self._ck(self.lib.rsigpu_set_depth(self.h, _ptr(depth), C.c_int32(len(depth))))
+
+    def set_depth_ptr(self, ptr: int, n: int):
+        self._ck(self.lib.rsigpu_set_depth(self.h, C.c_void_p(ptr), C.c_int32(n)))
+
+    def pileup_begin(self):
+        self._ck(self.lib.rsigpu_pileup_begin(self.h, C.c_int32(self.L)))
+
+    def pileup_push(self, reads: dict, tid: int = 0):
+        """reads: dict of numpy arrays pos, mpos, isize, mtid (int32), flag (uint16), mapq (uint8), cigar_off (uint32, n+1),
+        cigar (uint32), qual_off (uint64, n+1), qual (uint8) -- one position-sorted batch of one contig"""
+        b = ReadBatch()
+        keep = {}
+        for name, dt in (("pos", np.int32), ("mpos", np.int32), ("isize", np.int32), ("mtid", np.int32), ("flag", np.uint16),
+                         ("mapq", np.uint8), ("cigar_off", np.uint32), ("cigar", np.uint32), ("qual_off", np.uint64), ("qual", np.uint8)):
+            keep[name] = np.ascontiguousarray(reads[name], dtype=dt)
+            setattr(b, name, keep[name].ctypes.data)
+        b.n_reads = len(keep["pos"]); b.tid = tid
+        self._ck(self.lib.rsigpu_pileup_push(self.h, C.byref(b)))
+
+    def pileup_end(self):
+        self._ck(self.lib.rsigpu_pileup_end(self.h))
+
+    # ---- the seams, in the order main() calls them (rsi.cpp:2197-2211)
+    def load_finish(self):
+        self._ck(self.lib.rsigpu_load_finish(self.h))
+
+    def detectcnv(self):
+        self._ck(self.lib.rsigpu_detectcnv(self.h))
+
+    def sd_filters(self):
+        self._ck(self.lib.rsigpu_sd_filters(self.h))
+
+    def cnv_stat(self):
+        self._ck(self.lib.rsigpu_cnv_stat(self.h))
+
+    def calls(self, cap: int = 65536) -> list[Cnv]:
+        n = C.c_int32(0)
+        buf = (Cnv * cap)()
+        self._ck(self.lib.rsigpu_get_calls(self.h, buf, C.c_int32(cap), C.byref(n)))
+        return [_copy_cnv(buf[i]) for i in range(n.value)]
+
+    def run(self, cap: int = 65536) -> list[Cnv]:
+        n = C.c_int32(0)
+        buf = (Cnv * cap)()
+        self._ck(self.lib.rsigpu_run(self.h, buf, C.c_int32(cap), C.byref(n)))
+        return [_copy_cnv(buf[i]) for i in range(n.value)]
+
+    def run_count(self, buf, cap: int) -> int:
+        """rsigpu_run into a caller-owned (Cnv * cap) buffer; returns the number of calls (bench hot loop)"""
+        n = C.c_int32(0)
+        self._ck(self.lib.rsigpu_run(self.h, buf, C.c_int32(cap), C.byref(n)))
+        return n.value
+
+    # ---- outputs
+    def chr_stats(self) -> ChrStats:
+        s = ChrStats()
+        self._ck(self.lib.rsigpu_get_chr_stats(self.h, C.byref(s)))
+        return s
+
+    def array(self, which: int):
+        cnt = C.c_int64(0)
+        self._ck(self.lib.rsigpu_get_array(self.h, C.c_int32(which), None, C.c_int64(0), C.byref(cnt)))
+        n = cnt.value
+        if which >= ARR_SEGMENTS:
+            buf = (Cnv * max(n, 1))()
+            self._ck(self.lib.rsigpu_get_array(self.h, C.c_int32(which), buf, C.c_int64(n), C.byref(cnt)))
+            return [_copy_cnv(buf[i]) for i in range(n)]
+        out = np.zeros(max(n, 1), _ARR_DTYPE[which])
+        self._ck(self.lib.rsigpu_get_array(self.h, C.c_int32(which), _ptr(out), C.c_int64(n), C.byref(cnt)))
+        return out[:n]
+
+    def launch_count(self) -> int:
+        return int(self.lib.rsigpu_launch_count(self.h))
+
+    def stage_ms(self):
+        a = (C.c_float * 6)()
+        self._ck(self.lib.rsigpu_last_stage_ms(self.h, a))
+        return dict(zip(("pileup", "load_finish", "detect", "candidates", "stat", "total"), [float(x) for x in a]))
+
+    def set_profile(self, on: bool):
+        self._ck(self.lib.rsigpu_set_profile(self.h, C.c_int(1 if on else 0)))
+
+    def profile(self):
+        cap, stride = 128, 48
+        names = C.create_string_buffer(cap * stride)
+        ms = (C.c_float * cap)(); ln = (C.c_int32 * cap)()
+        k = self.lib.rsigpu_get_profile(self.h, names, C.c_int32(stride), ms, ln, C.c_int32(cap))
+        out = []
+        for i in range(min(k, cap)):
+            nm = names.raw[i * stride:(i + 1) * stride].split(b"\0", 1)[0].decode()
+            out.append((nm, float(ms[i]), int(ln[i])))
+        return out
+
+    def set_level0_mode(self, mode: int):
+        self._ck(self.lib.rsigpu_set_level0_mode(self.h, C.c_int(mode)))
+
+
+def _copy_cnv(src: Cnv) -> Cnv:
+    c = Cnv()
+    C.memmove(C.byref(c), C.byref(src), C.sizeof(Cnv))
+    return c
+
+
+def format_row(lib: C.CDLL, cnv: Cnv | None, chrom: str, rdmedian: float, rdsd: float) -> str:
+    """cnv_format1 (rsi.cpp:581-631); cnv=None gives the column header"""
+    buf = C.create_string_buffer(1024)
+    rc = lib.rsigpu_format_row(C.byref(cnv) if cnv is not None else None, C.c_char_p(chrom.encode()), C.c_double(rdmedian),
+                               C.c_double(rdsd), buf, C.c_int32(1024))
+    if rc != 0:
+        raise RsiGpuError(rc, "format_row")
+    return buf.value.decode()
+
+
+def write_cnv_to_file(path: str, lib: C.CDLL, calls: list[Cnv], chrom: str, rdmedian: float, rdsd: float, input_name: str,
+                      gcadjusted: bool, append: bool):
+    """write_cnv_to_file (rsi.cpp:1592-1616): header lines once, then one row per call, appended per contig"""
+    with open(path, "a" if append else "w") as f:
+        if not append:
+            f.write(f"#input {input_name}\n")
+            if gcadjusted:
+                f.write("#GC adjusted\n")
+            f.write(format_row(lib, None, "", 0, 0) + "\n")
+        for c in calls:
+            f.write(format_row(lib, c, chrom, rdmedian, rdsd) + "\n")

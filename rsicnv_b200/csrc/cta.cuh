@@ -5,7 +5,7 @@
 // thread block per contig: thread 0 does the list bookkeeping, all threads do the gathers, scans,
 // histograms and reductions.  Everything here is written against `Cta`, which on the GPU wraps
 // threadIdx / __syncthreads / warp shuffles.  When this header is compiled WITHOUT nvcc (only
-// tests/hostsim does that) `Cta` degenerates to a 1-thread block so the same control flow can be
+// tests/hostsim/sim.cpp does that) `Cta` degenerates to a 1-thread block so the same control flow can be
 // unit-tested against the oracle on a machine without a GPU.  The product never takes that path:
 // librsigpu.so is built by nvcc only and there is no host entry into this code.
 #pragma once
@@ -13,7 +13,9 @@
 #include <stdint.h>
 #include <string.h>
 
-#if defined(__CUDACC__)
+#if defined(__CUDACC__) || defined(RSI_SIM)
+#include "rt.cuh"
+#define RSI_CTA_PARALLEL 1
 #define RSI_DEV __device__ __forceinline__
 #define RSI_DEVN __device__ __noinline__
 #else
@@ -32,7 +34,7 @@ struct ValIdx { double v; long long i; };
 struct ArgMaxFirst { RSI_DEV ValIdx operator()(ValIdx a, ValIdx b) const { return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a; } };
 struct ArgMinFirst { RSI_DEV ValIdx operator()(ValIdx a, ValIdx b) const { return (b.v < a.v || (b.v == a.v && b.i < a.i)) ? b : a; } };
 
-#if defined(__CUDACC__)
+#if defined(RSI_CTA_PARALLEL)
 
 template <class T>
 RSI_DEV T shfl_xor_any(T v, int lane_mask) {
@@ -120,7 +122,7 @@ inline void cta_atomic_min(int* p, int v) { if (v < *p) *p = v; }
 // thread 0 publishes a value (<= 8 bytes) to the whole block through the broadcast area
 template <class T>
 RSI_DEV T cta_bcast(const Cta& c, T v, int slot) {
-#if defined(__CUDACC__)
+#if defined(RSI_CTA_PARALLEL)
   static_assert(sizeof(T) <= 8, "bcast payload");
   c.sync();
   if (c.tid == 0) memcpy(&c.bc[slot], &v, sizeof(T));

@@ -1,0 +1,276 @@
+// k_pileup.cuh -- BAM-input kernels on position-sorted read batches staged in HBM as SoA.
+//
+// Replaces (reference file:line relative to src/):
+//   load_data_from_bam hot loop  loaddata.cpp:312-335  +  resolve_cigar_pos  samfunctions.cpp:38-100   k_read_ends, k_pileup_tile
+//   bam_calend                   samtools-0.1.18/bam.c:17-27                                            k_read_ends
+//   bam_rd_pr_stats (insert-size sample)  pairrd.cpp:112-260 (order of tests: SURVEY.md A.2)            k_isize_stats
+//   cnv_stat                     pairrd.cpp:622-748                                                     k_cnv_stat
+//
+// Pileup design: a block OWNS a tile of reference positions.  It binary-searches the sorted read
+// starts for the reads that can touch the tile, every thread walks the CIGAR of its reads and turns
+// each maximal stretch of M/= bases with quality >= Q into +1/-1 events in a shared-memory
+// difference array (clipped to the tile), a block-wide scan turns events into depth and the tile is
+// stored once with coalesced 16-byte stores: no global atomics, no zero-fill, no read-modify-write.
+#pragma once
+#include "k_seg.cuh"
+
+namespace rsigpu {
+
+struct ReadSoA {
+  i64 n;
+  int tid;
+  const int* pos; const int* mpos; const int* isize; const int* mtid;
+  const u16* flag; const u8* mapq;
+  const u32* cigar_off; const u32* cigar;
+  const u64* qual_off; const u8* qual;
+  int* calend;   // bam_calend per read (pos + 1 for reads without CIGAR)
+};
+enum { BF_PROPER = 2, BF_REV = 16, BF_MREV = 32, BF_SECONDARY = 256, BF_DUP = 1024 };
+enum { PU_T = 8192, PU_NT = 256 };
+
+// per read: bam_calend, and the largest reference extent any of its counted bases can reach
+// (reference coordinates advance on M, D, N and S from the first M/D/=/X op: samfunctions.cpp:59-100)
+__global__ void k_read_ends(ReadSoA R, int* max_extent, int* sorted_bad) {
+  int mx = 0, bad = 0;
+  for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < R.n; r += (i64)gridDim.x * blockDim.x) {
+    const u32 c0 = R.cigar_off[r], c1 = R.cigar_off[r + 1];
+    u32 end = (u32)R.pos[r], ext = 0; bool anchored = false;
+    for (u32 k = c0; k < c1; ++k) {
+      const u32 op = R.cigar[k] & 15u, l = R.cigar[k] >> 4;
+      if (op == 0 || op == 2 || op == 3) end += l;
+      if (op == 0 || op == 2 || op == 7 || op == 8) anchored = true;
+      if (anchored && (op == 0 || op == 2 || op == 3 || op == 4)) ext += l;
+    }
+    // an '=' op does not advance the reference coordinate but its bases are counted from there on
+    u32 eqmax = 0;
+    for (u32 k = c0; k < c1; ++k) { const u32 op = R.cigar[k] & 15u, l = R.cigar[k] >> 4; if (op == 7 && l > eqmax) eqmax = l; }
+    ext += eqmax;
+    R.calend[r] = c1 > c0 ? (int)end : R.pos[r] + 1;
+    mx = imax(mx, (int)ext);
+    if (r > 0 && R.pos[r] < R.pos[r - 1]) bad = 1;
+  }
+  if (mx) atomicMax(max_extent, mx);
+  if (bad) atomicOr(sorted_bad, 1);
+}
+
+__global__ void __launch_bounds__(PU_NT) k_pileup_tile(ReadSoA R, int* __restrict__ rd, int L, int minq, int min_baseQ, const int* max_extent) {
+  RSI_CTA_SETUP(c);
+  __shared__ int diff[PU_T + 1 + (PU_T + 1) / 32 + 1];   // entry i lives at i + i/32: conflict-free 32-per-thread scan
+#define PU_DI(i) ((i) + ((i) >> 5))
+  __shared__ int s_r0, s_r1;
+  const int ntiles = (L + PU_T - 1) / PU_T;
+  const int ext = *max_extent;
+  for (int tile = (int)blockIdx.x; tile < ntiles; tile += (int)gridDim.x) {
+    const int t0 = tile * PU_T, t1 = imin(t0 + PU_T, L);
+    c.sync();
+    for (int k = c.tid; k < PU_T + 1 + (PU_T + 1) / 32 + 1; k += PU_NT) diff[k] = 0;
+    if (c.tid == 0) {  // reads with pos in [t0 - ext, t1)
+      i64 lo = 0, hi = R.n; const int want = t0 - ext;
+      while (lo < hi) { i64 mid = (lo + hi) >> 1; if (R.pos[mid] < want) lo = mid + 1; else hi = mid; }
+      s_r0 = (int)lo;
+      hi = R.n;
+      while (lo < hi) { i64 mid = (lo + hi) >> 1; if (R.pos[mid] < t1) lo = mid + 1; else hi = mid; }
+      s_r1 = (int)lo;
+    }
+    c.sync();
+    for (int r = s_r0 + c.tid; r < s_r1; r += PU_NT) {
+      const int pos = R.pos[r];
+      if (pos == 0) continue;
+      if ((int)R.mapq[r] < minq) continue;
+      const int fl = R.flag[r];
+      if (fl & (BF_SECONDARY | BF_DUP)) continue;
+      const u32 c0 = R.cigar_off[r], c1 = R.cigar_off[r + 1];
+      // reference / query coordinate at the start of each op
+      u32 k = c0, q = 0;
+      while (k < c1) { const u32 op = R.cigar[k] & 15u; if (op == 0 || op == 2 || op == 7 || op == 8) break; if (op == 1 || op == 4) q += R.cigar[k] >> 4; ++k; }
+      if (k == c1) continue;                       // no M/D/=/X op: nothing is counted
+      u32 e = (u32)pos + 1;
+      const u8* qual = R.qual + R.qual_off[r];
+      for (; k < c1; ++k) {
+        const u32 op = R.cigar[k] & 15u, l = R.cigar[k] >> 4;
+        if (op == 0 || op == 7) {
+          int p = (int)e - 1;                      // 0-based position of the op's first base
+          // maximal stretches of bases with quality >= Q, clipped to the tile and to L
+          const int jb = imax(0, t0 - p), je = imin((int)l, imin(t1, L) - p);
+          int open = -1;
+          for (int j = jb; j < je; ++j) {
+            const bool ok = (int)qual[q + (u32)j] >= min_baseQ;
+            if (ok && open < 0) open = j;
+            if (!ok && open >= 0) { atomicAdd(&diff[PU_DI(p + open - t0)], 1); atomicAdd(&diff[PU_DI(p + j - t0)], -1); open = -1; }
+          }
+          if (open >= 0) { atomicAdd(&diff[PU_DI(p + open - t0)], 1); atomicAdd(&diff[PU_DI(p + je - t0)], -1); }
+        }
+        if (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) q += l;
+        if (op == 0 || op == 2 || op == 3 || op == 4) e += l;
+      }
+    }
+    c.sync();
+    // difference array -> depth, PU_T / PU_NT consecutive positions per thread
+    const int per = PU_T / PU_NT;
+    int loc[PU_T / PU_NT]; int s = 0;
+#pragma unroll
+    for (int j = 0; j < per; ++j) { s += diff[PU_DI(c.tid * per + j)]; loc[j] = s; }
+    int tot;
+    const int ex = c.scan_excl(s, &tot);
+#pragma unroll
+    for (int j = 0; j < per; j += 4) {
+      const int p = t0 + c.tid * per + j;
+      if (p < L) *reinterpret_cast<int4*>(rd + p) = make_int4(loc[j] + ex, loc[j + 1] + ex, loc[j + 2] + ex, loc[j + 3] + ex);
+    }
+  }
+#undef PU_DI
+}
+
+// ---------------------------------------------------------------------------------------------
+// Insert-size sample.  `keep`-filtered reads in file order from the first one overlapping 10 Mbp;
+// sums run up to and including the read that trips a stop rule.
+__global__ void __launch_bounds__(1024) k_isize_stats(ReadSoA R, int tid_len, const int* max_extent, DevState* st) {
+  RSI_CTA_SETUP(c);
+  __shared__ int s_lastpos, s_segstart, s_segidx, s_stop;
+  const u32 beg = 10000000u, end = 349250621u;
+  i64 lo = 0, hi = R.n;
+  { const int want = (int)beg - *max_extent - 1; while (lo < hi) { i64 mid = (lo + hi) >> 1; if (R.pos[mid] < want) lo = mid + 1; else hi = mid; } }
+  const i64 r_first = lo;
+  if (c.tid == 0) { s_lastpos = -10000; s_segstart = 0; s_segidx = 0; s_stop = 0; }
+  c.sync();
+  double s = 0, s2 = 0, cn = 0;
+  i64 kept_before = 0;   // kept reads before this chunk
+  for (i64 r0 = r_first; r0 < R.n; r0 += c.nthr) {
+    const i64 r = r0 + c.tid;
+    bool kept = false, prop = false, stopA = false; int pos = 0, isz = 0;
+    if (r < R.n) {
+      pos = R.pos[r];
+      const u32 re = (u32)R.calend[r];
+      const bool overl = (u32)pos < end && re > beg;
+      const int mt = R.mtid[r]; const int fl = R.flag[r];
+      kept = overl && !(mt != R.tid && mt > 0) && !(fl & BF_SECONDARY) && !(fl & BF_DUP);
+      prop = kept && (fl & BF_PROPER) && mt == R.tid;
+      isz = R.isize[r];
+      // bam_calend proper for the stop rule (reads without CIGAR: pos)
+      const int rpe = (R.cigar_off[r + 1] > R.cigar_off[r]) ? (int)re : pos;
+      stopA = kept && (pos >= tid_len || rpe >= tid_len);
+    }
+    // past the region: the iterator stops at the first read with pos >= end
+    const int past = (r < R.n && (u32)pos >= end) ? 1 : 0;
+    // rank among the kept reads, gap starts
+    int tot;
+    const int ex = c.scan_excl(kept ? 1 : 0, &tot);
+    const i64 kidx = kept_before + ex;
+    // previous kept position: max-scan of positions (sorted input => the previous kept read has the largest pos so far)
+    int prevpos = kept ? pos : -0x7fffffff;
+    {  // inclusive max-scan across the block, then shift by one kept element
+      int v = prevpos;
+      const int lane = c.tid & 31, warp = c.tid >> 5;
+      for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v = imax(v, u); }
+      int* slots = reinterpret_cast<int*>(c.red);
+      c.sync(); if (lane == 31) slots[warp] = v; c.sync();
+      int pre = -0x7fffffff; for (int w = 0; w < warp; ++w) pre = imax(pre, slots[w]);
+      int upv = __shfl_up_sync(0xffffffffu, v, 1);
+      prevpos = imax(pre, lane ? upv : -0x7fffffff);   // max over earlier threads of this chunk
+      c.sync();
+    }
+    prevpos = imax(prevpos, s_lastpos);
+    const bool gap = kept && pos > prevpos + 1000;
+    // segment start (position and kept-rank) of the most recent gap at or before each kept read
+    i64 key = gap ? ((kidx << 32) | (i64)(u32)pos) : -1;     // max-scan on the kept rank
+    {
+      i64 v = key;
+      const int lane = c.tid & 31, warp = c.tid >> 5;
+      for (int o = 1; o < 32; o <<= 1) { i64 u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v = lmax(v, u); }
+      i64* slots = reinterpret_cast<i64*>(c.red);
+      c.sync(); if (lane == 31) slots[warp] = v; c.sync();
+      i64 pre = -1; for (int w = 0; w < warp; ++w) pre = lmax(pre, slots[w]);
+      key = lmax(v, pre);
+      c.sync();
+    }
+    int seg_idx, seg_pos;
+    if (key >= 0) { seg_idx = (int)(key >> 32); seg_pos = (int)(key & 0xffffffff); } else { seg_idx = s_segidx; seg_pos = s_segstart; }
+    const i64 count = kidx - seg_idx + 1;
+    const bool stopB = kept && !stopA && (count > 1000000 || (pos - seg_pos) > 1000000);
+    int stop_at = (stopA || stopB || past) ? c.tid : 0x7fffffff;
+    stop_at = c.reduce(stop_at, MinOp());
+    if (prop && c.tid <= stop_at && !(past && c.tid == stop_at)) {
+      s += (double)(isz < 0 ? -isz : isz);
+      s2 += (double)(int)((u32)isz * (u32)isz);
+      cn += 1;
+    }
+    if (stop_at != 0x7fffffff) break;
+    c.sync();
+    if (c.tid == c.nthr - 1) {   // carry the running state to the next chunk
+      s_lastpos = imax(s_lastpos, imax(prevpos, kept ? pos : -0x7fffffff));
+      if (key >= 0) { s_segidx = seg_idx; s_segstart = seg_pos; }
+    }
+    kept_before += tot;
+    c.sync();
+  }
+  s = c.reduce(s, SumOp()); s2 = c.reduce(s2, SumOp()); cn = c.reduce(cn, SumOp());
+  if (c.tid == 0) {
+    int im = -1, isd = -1;
+    if (cn > 2) {
+      s /= cn;
+      const double sd = sqrt((s2 - cn * s * s) / cn);
+      im = (int)s; isd = (int)sd;
+    }
+    st->isize_mean = im; st->isize_sd = isd;
+  }
+}
+
+// One block per call: Q0 fraction and supporting read pairs.  dis[k] = the carried DIS of call k.
+__global__ void __launch_bounds__(256) k_cnv_stat(ReadSoA R, Cnv* calls, int ncalls, const int* max_extent, DevState* st) {
+  RSI_CTA_SETUP(c);
+  const int im = st->isize_mean, isd = st->isize_sd;
+  for (int k = (int)blockIdx.x; k < ncalls; k += (int)gridDim.x) {
+    int DIS = 1000;
+    for (int j = 0; j <= k; ++j) {   // DIS is carried from call to call (pairrd.cpp:655-656)
+      int b = calls[j].start, e = calls[j].end; if (b > e) { int t = b; b = e; e = t; }
+      DIS = imax(DIS, e - b + 1); DIS = imin(DIS, 5000);
+    }
+    int beg = calls[k].start, end = calls[k].end; if (beg > end) { int t = beg; beg = end; end = t; }
+    const int type = calls[k].type;
+    const int LEN = end - beg + 1;
+    int p1e = beg - DIS; const int p2e = end + DIS;
+    if (p1e < 1) p1e = 1;
+    i64 lo = 0, hi = R.n;
+    { const int want = p1e - *max_extent - 1; while (lo < hi) { i64 mid = (lo + hi) >> 1; if (R.pos[mid] < want) lo = mid + 1; else hi = mid; } }
+    const i64 ra = lo;
+    hi = R.n;
+    while (lo < hi) { i64 mid = (lo + hi) >> 1; if ((u32)R.pos[mid] < (u32)p2e) lo = mid + 1; else hi = mid; }
+    const i64 rb = lo;
+    u32 qall = 0, q0 = 0, rp = 0;
+    for (i64 r = ra + c.tid; r < rb; r += c.nthr) {
+      const int nc = (int)(R.cigar_off[r + 1] - R.cigar_off[r]);
+      const int rbeg = R.pos[r], rend = R.calend[r];
+      if (!((u32)rend > (u32)p1e && (u32)rbeg < (u32)p2e)) continue;
+      if (nc <= 1) continue;
+      if (rend > beg && rbeg < end) { ++qall; if (R.mapq[r] == 0) ++q0; }
+      const int mt = R.mtid[r];
+      if (mt != R.tid && mt > 0) continue;
+      const int F = R.flag[r];
+      if ((F & BF_REV) == 0 && (F & BF_MREV) == 0) continue;
+      if ((F & BF_REV) > 0 && (F & BF_MREV) > 0) continue;
+      int r1 = rend, r2 = R.mpos[r];
+      if (type == RSIGPU_TYPE_DEL) {
+        if (r2 - r1 < im + isd * 3) continue;
+        const int ov = imin(r2, end) - imax(r1, beg);
+        if (ov < 0) continue;
+        if (abs(r1 - beg) + abs(r2 - end) < im + isd * 3) { ++rp; continue; }
+        if ((double)ov < LEN * 0.5) continue;
+        if ((double)ov < (r2 - r1) * 0.5) continue;
+        ++rp;
+      } else if (type == RSIGPU_TYPE_DUP) {
+        if (r2 - r1 > im - isd * 3) continue;
+        if (abs(r1 - beg) + abs(r2 - end) < im + isd * 3) { ++rp; continue; }
+        if (r1 > r2) { int t = r1; r1 = r2; r2 = t; }
+        const int ov = imin(r2, end) - imax(r1, beg);
+        if ((double)ov < LEN * 0.5) continue;
+        if ((double)ov < (r2 - r1) * 0.5) continue;
+        ++rp;
+      }
+    }
+    qall = c.reduce(qall, SumOp()); q0 = c.reduce(q0, SumOp()); rp = c.reduce(rp, SumOp());
+    if (c.tid == 0) { calls[k].q0 = (double)q0 / ((double)qall + 0.00001); calls[k].rp = (int)rp; }
+    c.sync();
+  }
+}
+
+}  // namespace rsigpu

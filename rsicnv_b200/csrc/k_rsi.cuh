@@ -1,0 +1,453 @@
+// k_rsi.cuh -- Robust Segment Identification on the bin arrays.
+//
+// Replaces (reference file:line relative to src/):
+//   rsicnvnbn / rsicnvmed (scalars)   rsi.cpp:1262-1360, 1402-1515   k_rsi_params1, k_rsi_params2
+//   rsistatus + runmeantp             rsi.cpp:1191-1259, wufunctions.cpp:572-647   k_rsi_scan, k_rsi_cnt_del, k_rsi_cnt_dup, k_rsi_status
+//   filterstatus_tp                   rsi.cpp:948-1057               k_nz_scatter, k_level0_chain*, k_level_sums, k_filter_params, k_filter_trim
+//   get_continuous_segments           rsi.cpp:291-326                run detection inside k_rsi_status / k_filter_trim / k_runs_scatter
+//   get_rsi_segments                  rsi.cpp:1060-1117              k_runs_scatter, k_run_argmax
+//
+// rsistatus is evaluated in its order-free form: every (L, i) window is tested
+// independently on an EXACT window sum (fixed-point prefix sums in shared memory), hits record the
+// smallest covering L per bin with shared/global atomicMin, and the reference's "L ascending,
+// first writer wins, stop once 20% is marked" rule is applied afterwards from a histogram over L.
+#pragma once
+#include "k_quant.cuh"
+
+namespace rsigpu {
+
+enum { S_NT = 256, S_T = 1024, S_H = LMAX_CAP / 2 + 2, S_N = S_T + 2 * S_H };
+enum { MINL_INF = 0x7f7f7f7f };
+
+// ---- scalars before the first rsistatus pass (which: 0 = NBN on the transformed bins, 1 = MED on the medians)
+__global__ void k_rsi_params1(const float* __restrict__ t, DevState* st, int which, double threshold) {
+  if (threadIdx.x || blockIdx.x) return;
+  const double tmedian = which == 0 ? st->qj[0].q[1] : st->rdmedian;
+  st->tmedian = tmedian;
+}
+__global__ void k_rsi_params2(const float* __restrict__ t, DevState* st, int which, double threshold, int slot) {
+  if (threadIdx.x || blockIdx.x) return;
+  const double tmedian = st->tmedian;
+  const double tsigma = st->qj[slot].q[1] / 0.6745;
+  double tlamda = st->factor * tsigma, target, dev;
+  int calmax;
+  if (which == 0) {
+    const float d20 = t[2] - t[0];
+    target = (double)d20 * sqrt(2.5);
+    tlamda = tlamda > target ? tlamda : target;
+    const double dnb = (double)fabsf(d20) + 0.0001;
+    const double x = tlamda * 2 / dnb;
+    calmax = (int)(x * x);
+    dev = tsigma * 3.0;
+  } else {
+    target = tmedian * sqrt(2.0);
+    tlamda = tlamda > target ? tlamda : target;
+    if (threshold > 0) tlamda = tmedian * threshold;
+    const double x = tlamda * 4 / (tmedian + 0.001);
+    calmax = (int)(x * x);
+    dev = tmedian * 0.6;
+  }
+  int Lmax = st->Lmax_base;
+  if (Lmax < calmax) Lmax = calmax;
+  if (Lmax > LMAX_CAP) { st->err |= ERR_LMAX; Lmax = LMAX_CAP; }
+  st->tsigma = tsigma; st->tlamda = tlamda; st->target = target; st->dev = dev; st->Lmax = Lmax;
+  for (int L = 0; L < LMAX_CAP + 2; ++L) { st->cnt_del[L] = 0; st->cnt_dup[L] = 0; }
+  for (int l = 0; l < 2 * LMAX_CAP + 3; ++l) { st->lvl_sum[l] = 0.f; st->lvl_cnt[l] = 0; }
+  st->st_lo = 0; st->st_hi = 0; st->last_run_start = -1; st->n_nonzero = 0;
+}
+// re-estimation on the unmarked bins after filterstatus (rsi.cpp:1307-1318 / 1457-1468)
+__global__ void k_rsi_params3(DevState* st, int slot_med, int slot_sig) {
+  if (threadIdx.x || blockIdx.x) return;
+  const u32 k = st->qj[slot_med].n;
+  st->n_unmarked = k;
+  if (k > (u32)(st->nb / 2)) {
+    st->tmedian = st->qj[slot_med].q[1];
+    st->tsigma = st->qj[slot_sig].q[1] / 0.6745;
+    const double tl = st->factor * st->tsigma;
+    st->tlamda = tl > st->target ? tl : st->target;
+  }
+  st->out_tmedian = st->tmedian; st->out_tlamda = st->tlamda;
+  for (int L = 0; L < LMAX_CAP + 2; ++L) { st->cnt_del[L] = 0; st->cnt_dup[L] = 0; }
+  st->st_lo = 0; st->st_hi = 0; st->last_run_start = -1; st->n_nonzero = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// window-median test of rsistatus (alglib::median over RDmedint[i1..i2], rsi.cpp:1209/1238) from
+// prefix counts; only the rare tie case (exactly half of an even window on each side of the limit)
+// looks at the values.
+__device__ bool window_median_ok(const int* __restrict__ medint, int i1, int L, int c_in, double lim, int sign) {
+  // sign < 0 (DEL): c_in = #{v <= lim}, pass iff median <= lim;  sign > 0 (DUP): c_in = #{v >= lim}, pass iff median >= lim
+  if (L & 1) return c_in >= (L - 1) / 2 + 1;
+  if (c_in >= L / 2 + 1) return true;
+  if (c_in <= L / 2 - 1) return false;
+  int a, b;
+  if (sign < 0) {
+    a = -0x7fffffff - 1; b = 0x7fffffff;  // a = max{v <= lim}, b = min{v > lim}
+    for (int j = 0; j < L; ++j) { const int v = medint[i1 + j]; if ((double)v <= lim) a = imax(a, v); else b = imin(b, v); }
+    return 0.5 * ((double)a + (double)b) <= lim;
+  }
+  a = -0x7fffffff - 1; b = 0x7fffffff;    // a = max{v < lim}, b = min{v >= lim}
+  for (int j = 0; j < L; ++j) { const int v = medint[i1 + j]; if ((double)v >= lim) b = imin(b, v); else a = imax(a, v); }
+  return 0.5 * ((double)a + (double)b) >= lim;
+}
+
+// One block = S_T window centres; loops over every window length.  Dynamic shared memory:
+//   P[S_N+1] i64 fixed-point prefix | sq[LMAX_CAP+1] double | cle[S_N+1], cge[S_N+1] u16 | mdel[S_N], mdup[S_N] u32
+__global__ void __launch_bounds__(S_NT) k_rsi_scan(const float* __restrict__ t, const int* __restrict__ medint, u32* __restrict__ minl_del,
+                                                    u32* __restrict__ minl_dup, DevState* st) {
+  RSI_DYN_SMEM(smem);
+  RSI_CTA_SETUP(c);
+  i64* P = reinterpret_cast<i64*>(smem);
+  double* sq = reinterpret_cast<double*>(P + (S_N + 1));
+  u32* mdel = reinterpret_cast<u32*>(sq + (LMAX_CAP + 1));
+  u32* mdup = mdel + S_N;
+  u16* cle = reinterpret_cast<u16*>(mdup + S_N);
+  u16* cge = cle + (S_N + 1);
+  const int nb = st->nb, Lmax = st->Lmax;
+  const double tmed = st->tmedian, tlam = st->tlamda, limd = st->lim_del, limu = st->lim_dup;
+  const int H = Lmax / 2 + 2;
+  const int c0 = (int)blockIdx.x * S_T;
+  const int base = c0 - H;                       // smem index k <-> bin base + k
+  const int N = S_T + 2 * H;
+  const int tid = c.tid;
+  // ---- stage: fixed-point values, limit flags, block-wide exclusive prefix
+  const int chunk = (N + S_NT - 1) / S_NT;
+  const int k0 = imin(tid * chunk, N), k1 = imin(k0 + chunk, N);
+  i64 ls = 0; int ld = 0, lu = 0, bad = 0; float tmax = 0.f; int lowexp = 1000;
+  for (int k = k0; k < k1; ++k) {
+    const int b = base + k;
+    if (b < 0 || b >= nb) continue;
+    const float x = t[b];
+    const i64 fx = (i64)((double)x * 68719476736.0);    // * 2^FX_SHIFT
+    if ((double)fx * (1.0 / 68719476736.0) != (double)x || !(x >= 0.f) || x >= 16384.f) bad = 1;
+    if (x > 0.f) {
+      const u32 u = __float_as_uint(x);
+      const int e = (int)((u >> 23) & 0xff) - 127 - 23;
+      const u32 man = (u & 0x7fffff) | 0x800000;
+      lowexp = imin(lowexp, e + (__ffs((int)man) - 1));
+      tmax = x > tmax ? x : tmax;
+    }
+    ls += fx;
+    const int v = medint[b];
+    ld += ((double)v <= limd) ? 1 : 0; lu += ((double)v >= limu) ? 1 : 0;
+  }
+  i64 tots; int totd, totu;
+  i64 rs = c.scan_excl(ls, &tots);
+  int rd_ = c.scan_excl(ld, &totd);
+  int ru = c.scan_excl(lu, &totu);
+  for (int k = k0; k < k1; ++k) {
+    const int b = base + k;
+    P[k] = rs; cle[k] = (u16)rd_; cge[k] = (u16)ru;
+    if (b >= 0 && b < nb) {
+      rs += (i64)((double)t[b] * 68719476736.0);
+      const int v = medint[b];
+      rd_ += ((double)v <= limd) ? 1 : 0; ru += ((double)v >= limu) ? 1 : 0;
+    }
+  }
+  if (tid == 0) { P[N] = tots; cle[N] = (u16)totd; cge[N] = (u16)totu; }
+  for (int k = tid; k < N; k += S_NT) { mdel[k] = MINL_INF; mdup[k] = MINL_INF; }
+  for (int L = tid; L <= Lmax; L += S_NT) sq[L] = sqrt((double)L);
+  // exactness of the reference's own double window sums: all partial sums need <= 53 significant bits
+  tmax = c.reduce(tmax, MaxOp()); lowexp = c.reduce(lowexp, MinOp()); bad = c.reduce(bad, MaxOp());
+  if (tid == 0) {
+    const int span = Lmax > 8192 ? Lmax : 8192;
+    if (bad || (lowexp < 1000 && (double)tmax * (double)span >= ldexp(1.0, 53 + lowexp))) atomicOr(&st->err, (int)ERR_FIXEDPOINT);
+  }
+  c.sync();
+  // ---- every window length, every centre of the tile
+  for (int L = 1; L <= Lmax; ++L) {
+    const int h = L / 2;
+    const double sL = sq[L], dL = (double)L;
+    const int ilo = h + 1, ihi = nb - h - 1;        // centres i with ilo <= i < ihi
+#pragma unroll
+    for (int r = 0; r < S_T / S_NT; ++r) {
+      const int i = c0 + tid + r * S_NT;
+      if (i < ilo || i >= ihi) continue;
+      const int k1w = i - h - base;                 // smem index of the window start
+      const i64 s = P[k1w + L] - P[k1w];
+      const float mean = (float)__ddiv_rn((double)s * (1.0 / 68719476736.0), dL);
+      const double score = __dmul_rn((double)mean - tmed, sL);
+      const bool hd = !(score > -tlam), hu = !(score < tlam);
+      if (!(hd || hu)) continue;
+      for (int pass = 0; pass < 2; ++pass) {
+        const int sign = pass == 0 ? -1 : 1;
+        if (sign < 0 ? !hd : !hu) continue;
+        const double lim = sign < 0 ? limd : limu;
+        const u16* cp = sign < 0 ? cle : cge;
+        const int cin = (int)cp[k1w + L] - (int)cp[k1w];
+        int i1 = i - h, i2 = i1 + L - 1;
+        if (!window_median_ok(medint, i1, L, cin, lim, sign)) continue;
+        // shrink both ends (rsi.cpp:1212-1215 / 1241-1244); the loops are unguarded in the reference
+        if (sign < 0) {
+          while (i1 < nb && (double)t[i1] > tmed) ++i1;
+          while (i1 < nb && (double)medint[i1] > lim) ++i1;
+          while (i2 >= 0 && (double)t[i2] > tmed) --i2;
+          while (i2 >= 0 && (double)medint[i2] > lim) --i2;
+        } else {
+          while (i1 < nb && (double)t[i1] < tmed) ++i1;
+          while (i1 < nb && (double)medint[i1] < lim) ++i1;
+          while (i2 >= 0 && (double)t[i2] < tmed) --i2;
+          while (i2 >= 0 && (double)medint[i2] < lim) --i2;
+        }
+        u32* mm = sign < 0 ? mdel : mdup;
+        for (int j = i1; j <= i2; ++j) atomicMin(&mm[j - base], (u32)L);
+      }
+    }
+  }
+  c.sync();
+  for (int k = tid; k < N; k += S_NT) {
+    const int b = base + k;
+    if (b < 0 || b >= nb) continue;
+    if (mdel[k] != MINL_INF) atomicMin(&minl_del[b], mdel[k]);
+    if (mdup[k] != MINL_INF) atomicMin(&minl_dup[b], mdup[k]);
+  }
+}
+
+// ---- the "stop once more than 20% is marked" rule (rsi.cpp:1225, 1255) from the histogram over L
+__device__ int rsi_lbreak(const u32* cnt, int Lmax, int nb) {
+  u64 cum = 0;
+  for (int L = 1; L <= Lmax; ++L) { cum += cnt[L]; if ((double)cum / (double)nb > 0.2) return L; }
+  return Lmax;
+}
+__global__ void k_rsi_cnt_del(const u32* __restrict__ minl_del, DevState* st) {
+  const int nb = st->nb, Lmax = st->Lmax;
+  for (int j = (int)(blockIdx.x * blockDim.x + threadIdx.x); j < nb; j += (int)(gridDim.x * blockDim.x)) {
+    const u32 l = minl_del[j];
+    if (l <= (u32)Lmax) atomicAdd(&st->cnt_del[l], 1u);
+  }
+}
+__global__ void k_rsi_cnt_dup(const u32* __restrict__ minl_del, const u32* __restrict__ minl_dup, DevState* st) {
+  __shared__ int s_lb;
+  const int nb = st->nb, Lmax = st->Lmax;
+  if (threadIdx.x == 0) { s_lb = rsi_lbreak(st->cnt_del, Lmax, nb); if (blockIdx.x == 0) st->lbreak_del = s_lb; }
+  __syncthreads();
+  const u32 lb = (u32)s_lb;
+  for (int j = (int)(blockIdx.x * blockDim.x + threadIdx.x); j < nb; j += (int)(gridDim.x * blockDim.x)) {
+    if (minl_del[j] <= lb) continue;                 // written by the DEL pass: not writable any more
+    const u32 l = minl_dup[j];
+    if (l <= (u32)Lmax) atomicAdd(&st->cnt_dup[l], 1u);
+  }
+}
+__device__ __forceinline__ int rsi_status_of(const u32* __restrict__ minl_del, const u32* __restrict__ minl_dup, int j, u32 lbd, u32 lbu) {
+  const u32 a = minl_del[j];
+  if (a <= lbd) return -(int)a;
+  const u32 b = minl_dup[j];
+  if (b <= lbu) return (int)b;
+  return 0;
+}
+__device__ __forceinline__ bool same_run(int prev, int cur) { return prev != 0 && cur != 0 && ((prev > 0) == (cur > 0)); }
+
+// status array + its range, the number of marked bins per 1024-bin tile (for the ordered
+// compactions that follow) and the start of the last run.
+__global__ void k_rsi_status(const u32* __restrict__ minl_del, const u32* __restrict__ minl_dup, int* __restrict__ status, int* __restrict__ tile_nz,
+                             DevState* st) {
+  RSI_CTA_SETUP(c);
+  __shared__ int s_lb;
+  const int nb = st->nb, Lmax = st->Lmax;
+  if (c.tid == 0) { s_lb = rsi_lbreak(st->cnt_dup, Lmax, nb); if (blockIdx.x == 0) st->lbreak_dup = s_lb; }
+  c.sync();
+  const u32 lbd = (u32)st->lbreak_del, lbu = (u32)s_lb;
+  int lo = 0, hi = 0, last = -1;
+  const int ntiles = (nb + 1023) / 1024;
+  for (int tile = (int)blockIdx.x; tile < ntiles; tile += (int)gridDim.x) {
+    int nz = 0;
+    for (int j = tile * 1024 + c.tid; j < imin(nb, tile * 1024 + 1024); j += c.nthr) {
+      const int s = rsi_status_of(minl_del, minl_dup, j, lbd, lbu);
+      status[j] = s;
+      if (s) {
+        ++nz; lo = imin(lo, s); hi = imax(hi, s);
+        const int prev = j > 0 ? rsi_status_of(minl_del, minl_dup, j - 1, lbd, lbu) : 0;
+        if (!same_run(prev, s)) last = imax(last, j);
+      }
+    }
+    nz = c.reduce(nz, SumOp());
+    if (c.tid == 0) tile_nz[tile] = nz;
+  }
+  lo = c.reduce(lo, MinOp()); hi = c.reduce(hi, MaxOp()); last = c.reduce(last, MaxOp());
+  if (c.tid == 0) { atomicMin(&st->st_lo, lo); atomicMax(&st->st_hi, hi); atomicMax(&st->last_run_start, last); }
+}
+
+// ---------------------------------------------------------------------------------------------
+// filterstatus_tp.  Ordered list of the marked bins (index order) for the per-level sums.
+__global__ void k_nz_scatter(const int* __restrict__ status, const int* __restrict__ tile_nz, int* __restrict__ nz_idx, DevState* st) {
+  RSI_CTA_SETUP(c);
+  const int nb = st->nb;
+  const int ntiles = (nb + 1023) / 1024;
+  for (int tile = (int)blockIdx.x; tile < ntiles; tile += (int)gridDim.x) {
+    int off = 0;
+    for (int k = c.tid; k < tile; k += c.nthr) off += tile_nz[k];
+    off = c.reduce(off, SumOp());
+    if (tile == ntiles - 1 && c.tid == 0) st->n_nonzero = off + tile_nz[tile];
+    if (tile_nz[tile] == 0) continue;
+    for (int j0 = tile * 1024; j0 < imin(nb, tile * 1024 + 1024); j0 += c.nthr) {
+      const int j = j0 + c.tid;
+      const int f = (j < nb && j < tile * 1024 + 1024 && status[j] != 0) ? 1 : 0;
+      int tot;
+      const int ex = c.scan_excl(f, &tot);
+      if (f) nz_idx[off + ex] = j;
+      off += tot;
+    }
+  }
+}
+
+// Level-0 sum: the reference adds the unmarked bins one after the other into a FLOAT (rsi.cpp:967-974),
+// so the result depends on the order and on every intermediate rounding.  Plain sequential form:
+__global__ void k_level0_chain_seq(const float* __restrict__ t, const int* __restrict__ status, DevState* st) {
+  if (threadIdx.x || blockIdx.x) return;
+  const int nb = st->nb;
+  float s = 0.f; u32 n = 0;
+  for (int i = 0; i < nb; ++i) if (status[i] == 0) { s = __fadd_rn(s, t[i]); ++n; }
+  const int l0 = -st->st_lo;
+  st->lvl_sum[l0] = s; st->lvl_cnt[l0] = n;
+}
+
+// The same sum, exactly, with one thread block: while the accumulator S stays inside one binade its
+// ulp u is fixed, S = N*u, and adding x = q*u + r moves N by q + [r > u/2] (+ the parity of N + q on
+// an exact tie, round-to-nearest-even).  Such steps are functions of N's parity and compose
+// associatively, so a block-wide scan applies thousands of additions at once; the scan stops at the
+// element that carries S into the next binade, which is added with a real FADD, and restarts there.
+struct ParStep { i64 d0, d1; };   // increment of N for incoming parity 0 / 1
+__device__ __forceinline__ ParStep par_compose(ParStep a, ParStep b) {  // a first, then b
+  ParStep r;
+  r.d0 = a.d0 + ((a.d0 & 1) ? b.d1 : b.d0);
+  r.d1 = a.d1 + (((1 + a.d1) & 1) ? b.d1 : b.d0);
+  return r;
+}
+__device__ __forceinline__ ParStep par_elem(double x, double u, double inv_u) {
+  // x >= 0; q = floor(x/u) clamped; r = x - q*u
+  double qd = floor(x * inv_u);
+  if (qd > 33554432.0) qd = 33554432.0;      // 2^25: anything >= 2^24 ends the binade anyway
+  const i64 q = (i64)qd;
+  const double r = x - qd * u;               // exact: u is a power of two and x has <= 24 significant bits
+  const double half = 0.5 * u;
+  ParStep s;
+  if (r > half) { s.d0 = q + 1; s.d1 = q + 1; }
+  else if (r == half) { s.d0 = q + (q & 1); s.d1 = q + ((q + 1) & 1); }
+  else { s.d0 = q; s.d1 = q; }
+  return s;
+}
+enum { CH_NT = 1024, CH_K = 8 };
+__global__ void __launch_bounds__(CH_NT) k_level0_chain_scan(const float* __restrict__ t, const int* __restrict__ status, DevState* st) {
+  RSI_CTA_SETUP(c);
+  __shared__ ParStep s_w[CH_NT / 32];
+  __shared__ float s_S; __shared__ int s_next;
+  const int nb = st->nb, tid = c.tid, lane = tid & 31, warp = tid >> 5;
+  float S = 0.f; int i0 = 0;
+  u32 n = 0;
+  for (int i = tid; i < nb; i += CH_NT) n += status[i] == 0 ? 1u : 0u;
+  n = c.reduce(n, SumOp());
+  while (i0 < nb) {
+    if (!(S > 0.f)) {  // accumulator still zero (or not a positive normal): plain sequential adds until it is
+      if (tid == 0) {
+        int i = i0; float s = S;
+        while (i < nb && !(s > 0.f)) { if (status[i] == 0) s = __fadd_rn(s, t[i]); ++i; }
+        s_S = s; s_next = i;
+      }
+      c.sync(); S = s_S; i0 = s_next; c.sync();
+      continue;
+    }
+    const int e = (int)((__float_as_uint(S) >> 23) & 0xff) - 127;   // S in [2^e, 2^(e+1))
+    const double u = ldexp(1.0, e - 23), inv_u = ldexp(1.0, 23 - e);
+    const i64 N0 = (i64)((double)S * inv_u);
+    const int b0 = i0 + tid * CH_K;
+    float xv[CH_K]; bool use[CH_K];
+    ParStep acc; acc.d0 = 0; acc.d1 = 0;
+#pragma unroll
+    for (int k = 0; k < CH_K; ++k) {
+      const int i = b0 + k;
+      use[k] = i < nb && status[i] == 0;
+      xv[k] = use[k] ? t[i] : 0.f;
+      if (use[k]) acc = par_compose(acc, par_elem((double)xv[k], u, inv_u));
+    }
+    // inclusive scan of the per-thread steps across the block
+    ParStep inc = acc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      ParStep up; up.d0 = __shfl_up_sync(0xffffffffu, inc.d0, o); up.d1 = __shfl_up_sync(0xffffffffu, inc.d1, o);
+      if (lane >= o) inc = par_compose(up, inc);
+    }
+    c.sync();
+    if (lane == 31) s_w[warp] = inc;
+    c.sync();
+    ParStep pre; pre.d0 = 0; pre.d1 = 0;
+    for (int w = 0; w < warp; ++w) pre = par_compose(pre, s_w[w]);
+    ParStep tot = pre;
+    for (int w = warp; w < CH_NT / 32; ++w) tot = par_compose(tot, s_w[w]);
+    // exclusive prefix of this thread = pre o (inclusive of the previous lane)
+    ParStep prev; prev.d0 = __shfl_up_sync(0xffffffffu, inc.d0, 1); prev.d1 = __shfl_up_sync(0xffffffffu, inc.d1, 1);
+    ParStep ex = lane == 0 ? pre : par_compose(pre, prev);
+    const int p0 = (int)(N0 & 1);
+    i64 N = N0 + (p0 ? ex.d1 : ex.d0);
+    // walk the own elements with the actual N; the first element that leaves the binade ends the scan
+    int cross = 0x7fffffff; float Sx = 0.f;
+    if (N < 16777216) {
+#pragma unroll
+      for (int k = 0; k < CH_K; ++k) {
+        if (!use[k] || cross != 0x7fffffff) continue;
+        const ParStep s = par_elem((double)xv[k], u, inv_u);
+        const i64 d = (N & 1) ? s.d1 : s.d0;
+        if (N + d >= 16777216) { cross = b0 + k; Sx = __fadd_rn((float)((double)N * u), xv[k]); }
+        else N += d;
+      }
+    }
+    const int first = c.reduce(cross, MinOp());
+    if (first == 0x7fffffff) {
+      S = (float)((double)(N0 + (p0 ? tot.d1 : tot.d0)) * u);
+      i0 += CH_NT * CH_K;
+    } else {
+      if (cross == first) s_S = Sx;
+      c.sync();
+      S = s_S; i0 = first + 1;
+      c.sync();
+    }
+  }
+  if (tid == 0) { const int l0 = -st->st_lo; st->lvl_sum[l0] = S; st->lvl_cnt[l0] = n; }
+}
+
+// sums of the non-zero levels: one thread per level walks the ordered list of marked bins
+__global__ void k_level_sums(const float* __restrict__ t, const int* __restrict__ status, const int* __restrict__ nz_idx, DevState* st) {
+  const int lo = st->st_lo, hi = st->st_hi, nz = st->n_nonzero;
+  const int lvl = lo + (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (lvl > hi || lvl == 0) return;
+  float s = 0.f; u32 n = 0;
+  for (int k = 0; k < nz; ++k) {
+    const int j = nz_idx[k];
+    if (status[j] == lvl) { s = __fadd_rn(s, t[j]); ++n; }
+  }
+  st->lvl_sum[lvl - lo] = s; st->lvl_cnt[lvl - lo] = n;
+}
+
+__global__ void k_filter_params(DevState* st) {
+  if (threadIdx.x || blockIdx.x) return;
+  const int lo = st->st_lo, hi = st->st_hi, nl = hi - lo + 1;
+  const double dev = st->dev;
+  st->filt_on = 0;
+  for (int l = 0; l < nl; ++l) if (st->lvl_cnt[l] != 0) st->lvl_sum[l] = (float)((double)st->lvl_sum[l] / (double)st->lvl_cnt[l]);
+  const float m0 = st->lvl_sum[-lo];
+  int ldel = lo, ladd = hi;
+  for (int l = 0; l < nl; ++l) if ((double)st->lvl_sum[l] < (double)m0 - dev) { ldel = l + lo; break; }
+  for (int l = nl - 1; l >= 0; --l) if ((double)st->lvl_sum[l] > (double)m0 + dev) { ladd = l + lo; break; }
+  if (ldel > 0 || ladd < 0 || ldel > ladd) return;
+  st->filt_tdel = (double)m0 - dev; st->filt_tadd = (double)m0 + dev;
+  st->filt_on = 1;
+}
+
+// trim both edges of every run but the last (rsi.cpp:1027-1046); one thread per run start
+__global__ void k_filter_trim(const float* __restrict__ t, const int* __restrict__ sin, int* __restrict__ sout, DevState* st) {
+  const int nb = st->nb, last = st->last_run_start;
+  if (!st->filt_on) return;
+  const double tdel = st->filt_tdel, tadd = st->filt_tadd;
+  for (int j = (int)(blockIdx.x * blockDim.x + threadIdx.x); j < nb; j += (int)(gridDim.x * blockDim.x)) {
+    const int s = sin[j];
+    if (s == 0 || j == last) continue;
+    if (j > 0 && same_run(sin[j - 1], s)) continue;
+    int i1 = j, i2 = j;
+    while (i2 + 1 < nb && same_run(sin[i2], sin[i2 + 1])) ++i2;
+    while (((double)t[i1] > tdel && sin[i1] < 0) || ((double)t[i1] < tadd && sin[i1] > 0)) { sout[i1] = 0; ++i1; if (i1 >= i2) break; }
+    // (the reference works in place; positions cleared by the first loop are never re-examined here
+    //  except for a single-bin run, where clearing it twice changes nothing)
+    while (((double)t[i2] > tdel && sin[i2] < 0) || ((double)t[i2] < tadd && sin[i2] > 0)) { sout[i2] = 0; --i2; if (i2 <= i1) break; }
+  }
+}
+
+}  // namespace rsigpu

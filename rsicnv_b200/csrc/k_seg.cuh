@@ -1,0 +1,147 @@
+// k_seg.cuh -- runs of the final status array and the best-scoring window of every run, then the
+// one-block candidate stage.
+//
+// Replaces (reference file:line relative to src/):
+//   get_continuous_segments   rsi.cpp:291-326     k_runs_count, k_runs_scatter  (the last run is never emitted)
+//   get_rsi_segments          rsi.cpp:1060-1117   k_run_argmax  (first maximum in (L ascending, start ascending) order)
+//   rsicnvnbn/rsicnvmed tail  rsi.cpp:1340-1345   k_candidates, thread 0: keep |score| >= tlamda/2
+//   areblockscnv .. detectcnv tail, sd_filters    k_candidates -> candidates.cuh
+#pragma once
+#include "candidates.cuh"
+#include "k_rsi.cuh"
+
+namespace rsigpu {
+
+__global__ void k_runs_count(const int* __restrict__ status, int* __restrict__ tile_rs, DevState* st) {
+  RSI_CTA_SETUP(c);
+  const int nb = st->nb;
+  const int ntiles = (nb + 1023) / 1024;
+  for (int tile = (int)blockIdx.x; tile < ntiles; tile += (int)gridDim.x) {
+    int n = 0;
+    for (int j = tile * 1024 + c.tid; j < imin(nb, tile * 1024 + 1024); j += c.nthr) {
+      const int s = status[j];
+      if (s != 0 && !(j > 0 && same_run(status[j - 1], s))) ++n;
+    }
+    n = c.reduce(n, SumOp());
+    if (c.tid == 0) tile_rs[tile] = n;
+  }
+}
+// runs[2k], runs[2k+1] = first / last bin of run k, in position order, the last run dropped
+__global__ void k_runs_scatter(const int* __restrict__ status, const int* __restrict__ tile_rs, int* __restrict__ runs, int cap, DevState* st) {
+  RSI_CTA_SETUP(c);
+  const int nb = st->nb, last = st->last_run_start;
+  const int ntiles = (nb + 1023) / 1024;
+  for (int tile = (int)blockIdx.x; tile < ntiles; tile += (int)gridDim.x) {
+    int off = 0;
+    for (int k = c.tid; k < tile; k += c.nthr) off += tile_rs[k];
+    off = c.reduce(off, SumOp());
+    if (tile == ntiles - 1 && c.tid == 0) {
+      int n = off + tile_rs[tile];
+      n = n > 0 ? n - 1 : 0;
+      if (n > cap) { atomicOr(&st->err, (int)ERR_LISTCAP); n = cap; }
+      st->n_runs = n;
+    }
+    if (tile_rs[tile] == 0) continue;
+    for (int j0 = tile * 1024; j0 < imin(nb, tile * 1024 + 1024); j0 += c.nthr) {
+      const int j = j0 + c.tid;
+      int f = 0;
+      if (j < nb && j < tile * 1024 + 1024) { const int s = status[j]; f = (s != 0 && !(j > 0 && same_run(status[j - 1], s))) ? 1 : 0; }
+      int tot;
+      const int ex = c.scan_excl(f, &tot);
+      if (f && j != last && off + ex < cap) {
+        int e = j;
+        while (e + 1 < nb && same_run(status[e], status[e + 1])) ++e;
+        runs[2 * (off + ex)] = j; runs[2 * (off + ex) + 1] = e;
+      }
+      off += tot;
+    }
+  }
+}
+
+// One block per run: fixed-point prefix of the run in global scratch (pfx[a .. b+1], disjoint per run),
+// then every (L, j) window; score = |sum/L - tmedian| * sqrt(L) in double (the reference slides a
+// double sum over float bins, exact under the condition k_rsi_scan checks).
+struct SegBest { double v; u64 key; };
+struct SegBestOp { __device__ __forceinline__ SegBest operator()(SegBest a, SegBest b) const { return (b.v > a.v || (b.v == a.v && b.key < a.key)) ? b : a; } };
+
+__global__ void __launch_bounds__(256) k_run_argmax(const float* __restrict__ t, const int* __restrict__ status, const int* __restrict__ runs,
+                                                     i64* __restrict__ pfx, Cnv* __restrict__ segs, DevState* st) {
+  RSI_CTA_SETUP(c);
+  const int nruns = st->n_runs;
+  const double tmed = st->tmedian;
+  for (int r = (int)blockIdx.x; r < nruns; r += (int)gridDim.x) {
+    const int a = runs[2 * r], b = runs[2 * r + 1], n = b - a + 1;
+    i64* P = pfx + a + r;   // n + 1 entries; "+ r" keeps consecutive runs' (n+1)-entry windows disjoint
+    i64 carry = 0;
+    c.sync();
+    if (c.tid == 0) P[0] = 0;
+    for (int j0 = 0; j0 < n; j0 += c.nthr) {
+      const int j = j0 + c.tid;
+      const i64 v = j < n ? (i64)((double)t[a + j] * 68719476736.0) : 0;
+      i64 tot;
+      const i64 ex = c.scan_excl(v, &tot);
+      if (j < n) P[j + 1] = carry + ex + v;
+      carry += tot;
+    }
+    c.sync();
+    SegBest best; best.v = 0.0; best.key = ~0ull;
+    for (int L = 1; L <= n; ++L) {
+      const double dL = (double)L, sL = sqrt(dL);
+      for (int j = c.tid; j + L <= n; j += c.nthr) {
+        const double sum = (double)(P[j + L] - P[j]) * (1.0 / 68719476736.0);
+        const double sc = __dmul_rn(fabs(__ddiv_rn(sum, dL) - tmed), sL);
+        const u64 key = ((u64)L << 32) | (u64)j;
+        if (sc > best.v || (sc == best.v && key < best.key)) { best.v = sc; best.key = key; }
+      }
+    }
+    best = c.reduce(best, SegBestOp());
+    if (c.tid == 0) {
+      int ns = a, ne = b;
+      if (best.v > 0.0 && best.key != ~0ull) { const int L = (int)(best.key >> 32), j = (int)(best.key & 0xffffffffu); ns = a + j; ne = a + j + L - 1; }
+      Cnv x = cnv_default();
+      x.start = ns; x.end = ne;
+      if (status[ns] > 0) { x.type = RSIGPU_TYPE_DUP; x.score = best.v; } else { x.type = RSIGPU_TYPE_DEL; x.score = -best.v; }
+      segs[r] = x;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct CandArgs {
+  const int* rdc; const int* medint; const int* status;
+  const int* nbeg; const int* nend;
+  Cnv* segs;          // in: one entry per run (k_run_argmax); reused as the working list
+  Cnv* tmp; Cnv* ov;  // list-sized scratch, 2-entry overlay scratch
+  Cnv* d_segments; Cnv* d_blocks; Cnv* d_premerge; Cnv* d_merged; Cnv* d_detected; Cnv* d_calls;
+  int* n_dump;        // [0]=segments [1]=blocks [2]=premerge [3]=merged
+  int list_cap;
+  CandScratch S;
+  int maxchkbp, merge, tid; double chklen;
+};
+
+__global__ void __launch_bounds__(1024) k_candidates(CandArgs A, DevState* st) {
+  RSI_CTA_SETUP(c);
+  CandCfg P;
+  P.m = st->m; P.maxchkbp = A.maxchkbp; P.merge = A.merge; P.tid = A.tid; P.chklen = A.chklen; P.minmlen = 3.01; P.buffer = 0.05; P.p = 0.05;
+  P.rdmedian = st->rdmedian; P.rdsd = st->rdsd; P.span = st->Lc;
+  const int n_runs = st->n_runs;
+  int nl = 0;
+  if (c.tid == 0) {
+    const double half = st->tlamda * 0.5;
+    for (int r = 0; r < n_runs; ++r) if (!(fabs(A.segs[r].score) < half)) { if (nl != r) A.segs[nl] = A.segs[r]; ++nl; }
+  }
+  nl = cta_bcast(c, nl, 3);
+  dump_list(c, A.segs, nl, A.d_segments, &A.n_dump[0], A.list_cap);
+  CandDumps D;
+  D.blocks = A.d_blocks; D.n_blocks = &A.n_dump[1]; D.premerge = A.d_premerge; D.n_premerge = &A.n_dump[2];
+  D.merged = A.d_merged; D.n_merged = &A.n_dump[3]; D.cap = A.list_cap;
+  nl = candidates_main(c, P, A.S, A.rdc, st->Lc, A.medint, A.status, st->nb, A.nbeg, A.nend, st->n_noseq, A.segs, nl, A.tmp, A.ov, D, 0);
+  for (int j = c.tid; j < nl; j += c.nthr) A.d_detected[j] = A.segs[j];
+  c.sync();
+  if (c.tid == 0) { st->n_detected = nl; nl = sd_filter_list(P, A.segs, nl); st->n_calls = nl; }
+  nl = cta_bcast(c, nl, 4);
+  for (int j = c.tid; j < nl; j += c.nthr) A.d_calls[j] = A.segs[j];
+  if (c.tid == 0 && *A.S.err) { st->cand_err = *A.S.err; st->err |= ERR_CAND; }
+}
+
+}  // namespace rsigpu

@@ -1,0 +1,668 @@
+// rsigpu.cu -- context, stream orchestration and the C ABI (include/rsigpu.h) of the B200-native
+// `rsicnv rsi` hot path.  One context = one contig = what one iteration of the reference's chromosome
+// loop owns (rsi.cpp:2189-2217).  Every stage is a short sequence of kernel launches on the context's
+// stream; scalars travel between kernels in a device-resident DevState, so the host synchronises only
+// (1) once after the per-base stage, to build the negative-binomial table with the box's libm
+// (bit-exact by construction, SURVEY.md hard part 3), and (2) when results are copied back.
+// There is NO CPU implementation behind this API: without a CUDA device every call fails.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/rsigpu.h"
+#include "k_pileup.cuh"
+
+using namespace rsigpu;
+
+namespace {
+
+#define CK(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess) { c->fail(std::string(#call) + ": " + cudaGetErrorString(e_)); return RSIGPU_E_CUDA; } \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr; size_t cap = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc((void**)&p, n * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+template <class T>
+struct DevVec {   // growable device array filled by appends from the host
+  T* p = nullptr; size_t n = 0, cap = 0;
+  cudaError_t append(const T* h, size_t cnt, cudaStream_t s) {
+    if (n + cnt > cap) {
+      size_t ncap = std::max(n + cnt, cap * 2);
+      T* q = nullptr;
+      cudaError_t e = cudaMalloc((void**)&q, ncap * sizeof(T) + 64);
+      if (e != cudaSuccess) return e;
+      if (n) { e = cudaMemcpyAsync(q, p, n * sizeof(T), cudaMemcpyDeviceToDevice, s); if (e != cudaSuccess) return e; }
+      cudaStreamSynchronize(s);
+      if (p) cudaFree(p);
+      p = q; cap = ncap;
+    }
+    cudaError_t e = cudaMemcpyAsync(p + n, h, cnt * sizeof(T), cudaMemcpyHostToDevice, s);
+    n += cnt;
+    return e;
+  }
+  void clear() { n = 0; }
+  void release() { if (p) cudaFree(p); p = nullptr; n = cap = 0; }
+};
+
+const int LIST_CAP = 65536;          // runs / segments / calls per contig
+const int CHIST_RCAP = 8192;         // value range of the class histograms
+const size_t LUT_CAP = 1u << 24;
+
+__global__ void k_add_u32(u32* a, size_t n, u32 v) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) a[i] += v;
+}
+__global__ void k_add_u64(u64* a, size_t n, u64 v) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) a[i] += v;
+}
+
+}  // namespace
+
+struct rsigpu_ctx {
+  int device = 0, n_sm = 1;
+  rsigpu_params P;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int L = 0, Lc = 0, nb = 0, tid = 0;
+  bool have_ref = false, have_depth = false, have_reads = false, loaded = false, detected = false, filtered = false;
+  int level0_mode = 1;   // 1 = block-scan chain (default), 0 = plain sequential chain (cross-check)
+  // per-base
+  DevBuf<u8> d_fasta; DevBuf<int> d_raw, d_rdc, d_nseq;  // d_nseq: nbeg | nend | ncum
+  std::vector<int> h_nbeg, h_nend;
+  DevState* d_st = nullptr; DevState* h_st = nullptr;
+  DevBuf<u32> d_hist_all, d_chist, d_thist, d_tothist, d_fq_hist;
+  // bins
+  DevBuf<float> d_bin_med, d_bin_nbn, d_lut; DevBuf<int> d_bin_medint, d_status, d_status1, d_tile, d_nz_idx, d_runs; DevBuf<i64> d_bin_sum, d_pfx;
+  DevBuf<u32> d_minl_del, d_minl_dup;
+  float* h_lut = nullptr; size_t h_lut_cap = 0;
+  // lists
+  DevBuf<Cnv> d_lists;   // segs | tmp | ov(2) | segments | blocks | premerge | merged | detected | calls
+  DevBuf<int> d_misc;    // n_dump[4] | cand_err | max_extent | sorted_bad | n_begN | n_endN
+  DevBuf<int> d_ref, d_sub; DevBuf<i64> d_pref; DevBuf<float> d_rm; DevBuf<u32> d_chist_c;
+  DevBuf<int> d_nrun_beg, d_nrun_end;
+  std::vector<Cnv> h_detected, h_calls, h_dump[4];
+  // reads
+  DevVec<int> r_pos, r_mpos, r_isize, r_mtid; DevVec<u16> r_flag; DevVec<u8> r_mapq, r_qual; DevVec<u32> r_cigar_off, r_cigar; DevVec<u64> r_qual_off;
+  DevBuf<int> r_calend;
+  // accounting
+  int64_t launches = 0;
+  float stage_ms[6] = {0, 0, 0, 0, 0, 0};
+  cudaEvent_t ev[8] = {};
+  bool profile = false;
+  std::map<std::string, std::pair<float, int>> prof;
+  std::vector<std::string> prof_order;
+
+  void fail(const std::string& m) { err = m; }
+  Cnv* list(int k) const { return d_lists.p + (size_t)k * LIST_CAP; }
+};
+
+namespace {
+
+struct KTimer {
+  rsigpu_ctx* c; const char* name; cudaEvent_t a, b;
+  KTimer(rsigpu_ctx* c_, const char* n) : c(c_), name(n), a(nullptr), b(nullptr) {
+    c->launches++;
+    if (c->profile) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, c->stream); }
+  }
+  ~KTimer() {
+    if (!c->profile) return;
+    cudaEventRecord(b, c->stream); cudaEventSynchronize(b);
+    float ms = 0; cudaEventElapsedTime(&ms, a, b);
+    auto it = c->prof.find(name);
+    if (it == c->prof.end()) { c->prof[name] = std::make_pair(ms, 1); c->prof_order.push_back(name); }
+    else { it->second.first += ms; it->second.second += 1; }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+  }
+};
+#define KL(name, grid, block, smem, ...)                                \
+  do { KTimer kt_(c, #name); RSI_LAUNCH(name, grid, block, smem, c->stream, __VA_ARGS__); } while (0)
+
+template <class T> T* field_ptr(DevState* base, T DevState::*m) { return &(base->*m); }
+
+int map_dev_err(rsigpu_ctx* c, int e, int cand) {
+  if (!e) return RSIGPU_OK;
+  std::string m = "device-side range check failed:";
+  if (e & ERR_DEPTH_RANGE) m += " depth outside [0, 2^24);";
+  if (e & ERR_HIST_RANGE) m += " adjusted depth beyond the histogram range (65536 / class range 8192);";
+  if (e & ERR_LMAX) m += " RSI Lmax above 2048;";
+  if (e & ERR_FIXEDPOINT) m += " bin values make the reference's window sums inexact;";
+  if (e & ERR_FQ_BINS) m += " float quantile needs more than 2^22 buckets;";
+  if (e & ERR_LISTCAP) m += " more than 65536 runs;";
+  if (e & ERR_CAND) m += " candidate-stage scratch overflow (code " + std::to_string(cand) + ");";
+  if (e & ERR_DEGENERATE) m += " degenerate depth distribution (median or MAD is zero);";
+  if (e & ERR_PILEUP) m += " malformed read batch;";
+  c->fail(m);
+  return RSIGPU_E_RANGE;
+}
+
+int grid_for(int n_items, int per_block, int cap) { int g = (n_items + per_block - 1) / per_block; if (g < 1) g = 1; return g > cap ? cap : g; }
+
+double nb_formula(double sum, double m2, double r) {  // rsi.cpp:1155-1156
+  return 2.0 * sqrt(r) * log(sqrt((sum + 0.25) / (m2 * r - 0.5)) + sqrt(1.0 + (sum + 0.25) / (m2 * r - 0.5)));
+}
+
+// one histogram quantile of a bin array (k_quant.cuh)
+void quantile(rsigpu_ctx* c, const float* x, const int* status, int masked, int mode, const double* center, int slot) {
+  const int g = grid_for(c->nb, 256 * 8, c->n_sm * 4);
+  KL(k_fq_minmax, g, 256, 0, x, status, masked, mode, center, c->d_st, slot);
+  KL(k_fq_hist, g, 256, 0, x, status, masked, mode, center, c->d_fq_hist.p, c->d_st, slot);
+  KL(k_fq_pick, 1, 1024, 0, c->d_fq_hist.p, c->d_st, slot);
+}
+
+int set_smem_attrs() {
+  static bool done = false;
+  if (done) return 0;
+  done = true;
+  cudaFuncSetAttribute(k_gc_table, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(GC_STRATA * A_NT * 8 + LD_FAB + (LD_PRE + 8) * 2));
+  cudaFuncSetAttribute(k_gc_adjust, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(B_K * B_NT * 2 + GC_STRATA * 8 + LD_FAB + (LD_PRE + 8) * 2));
+  cudaFuncSetAttribute(k_bins, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(C_K * C_NT * 2 + C_TP * 4));
+  cudaFuncSetAttribute(k_rsi_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((S_N + 1) * 8 + (LMAX_CAP + 1) * 8 + 2 * S_N * 4 + 2 * (S_N + 1) * 2));
+  return 0;
+}
+
+// ---- the RSI stage for one transformation (rsicnvnbn: which = 0, rsicnvmed: which = 1)
+int run_rsi(rsigpu_ctx* c, int which, const float* t) {
+  DevState* st = c->d_st;
+  const int nb = c->nb, slot0 = which == 0 ? 0 : 4;
+  const int gb = grid_for(nb, 1024, c->n_sm * 8);
+  const size_t scan_smem = (S_N + 1) * 8 + (LMAX_CAP + 1) * 8 + 2 * S_N * 4 + 2 * (S_N + 1) * 2;
+  if (which == 0) quantile(c, t, nullptr, 0, QM_ID, nullptr, slot0);
+  KL(k_rsi_params1, 1, 32, 0, t, st, which, c->P.threshold);
+  quantile(c, t, nullptr, 0, QM_ABSDEV, field_ptr(st, &DevState::tmedian), slot0 + 1);
+  KL(k_rsi_params2, 1, 32, 0, t, st, which, c->P.threshold, slot0 + 1);
+  for (int pass = 0; pass < 2; ++pass) {
+    CK(cudaMemsetAsync(c->d_minl_del.p, 0x7f, (size_t)nb * 4, c->stream));
+    CK(cudaMemsetAsync(c->d_minl_dup.p, 0x7f, (size_t)nb * 4, c->stream));
+    KL(k_rsi_scan, (nb + S_T - 1) / S_T, S_NT, scan_smem, t, c->d_bin_medint.p, c->d_minl_del.p, c->d_minl_dup.p, st);
+    KL(k_rsi_cnt_del, gb, 256, 0, c->d_minl_del.p, st);
+    KL(k_rsi_cnt_dup, gb, 256, 0, c->d_minl_del.p, c->d_minl_dup.p, st);
+    int* status = pass == 0 ? c->d_status1.p : c->d_status.p;
+    KL(k_rsi_status, gb, 256, 0, c->d_minl_del.p, c->d_minl_dup.p, status, c->d_tile.p, st);
+    if (pass == 1) break;
+    // filterstatus (rsi.cpp:948-1057) on the first-pass status, in place via a second buffer
+    KL(k_nz_scatter, gb, 256, 0, status, c->d_tile.p, c->d_nz_idx.p, st);
+    if (c->level0_mode) KL(k_level0_chain_scan, 1, CH_NT, 0, t, status, st);
+    else KL(k_level0_chain_seq, 1, 32, 0, t, status, st);
+    KL(k_level_sums, (2 * LMAX_CAP + 3 + 127) / 128, 128, 0, t, status, c->d_nz_idx.p, st);
+    KL(k_filter_params, 1, 32, 0, st);
+    CK(cudaMemcpyAsync(c->d_status.p, status, (size_t)nb * 4, cudaMemcpyDeviceToDevice, c->stream));
+    KL(k_filter_trim, gb, 256, 0, t, c->d_status.p, status, st);
+    quantile(c, t, status, 1, QM_ID, nullptr, slot0 + 2);
+    quantile(c, t, status, 1, QM_ABSDEV, &(st->qj[slot0 + 2].q[1]), slot0 + 3);
+    KL(k_rsi_params3, 1, 32, 0, st, slot0 + 2, slot0 + 3);
+  }
+  // get_rsi_segments on the second-pass status
+  KL(k_runs_count, gb, 256, 0, c->d_status.p, c->d_tile.p, st);
+  KL(k_runs_scatter, gb, 256, 0, c->d_status.p, c->d_tile.p, c->d_runs.p, LIST_CAP, st);
+  KL(k_run_argmax, c->n_sm * 4, 256, 0, t, c->d_status.p, c->d_runs.p, c->d_pfx.p, c->list(0), st);
+  return RSIGPU_OK;
+}
+
+ReadSoA read_view(rsigpu_ctx* c) {
+  ReadSoA R;
+  R.n = (i64)c->r_pos.n; R.tid = c->tid;
+  R.pos = c->r_pos.p; R.mpos = c->r_mpos.p; R.isize = c->r_isize.p; R.mtid = c->r_mtid.p; R.flag = c->r_flag.p; R.mapq = c->r_mapq.p;
+  R.cigar_off = c->r_cigar_off.p; R.cigar = c->r_cigar.p; R.qual_off = c->r_qual_off.p; R.qual = c->r_qual.p; R.calend = c->r_calend.p;
+  return R;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rsigpu_default_params(rsigpu_params* p) {
+  if (!p) return RSIGPU_E_ARG;
+  memset(p, 0, sizeof *p);
+  p->m = 101; p->minq = 0; p->min_baseQ = 13; p->gcadjust = 1; p->trans = RSIGPU_TRANS_NBN; p->merge = 1; p->maxchkbp = 100000;
+  p->cap = 4.0; p->threshold = -1.0; p->epsilon = 1.5; p->chklen = 2.5;
+  return RSIGPU_OK;
+}
+
+int rsigpu_num_devices(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int rsigpu_create(int device, const rsigpu_params* p, rsigpu_ctx** out) {
+  if (!p || !out) return RSIGPU_E_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return RSIGPU_E_NODEVICE;
+  if (p->trans != RSIGPU_TRANS_NBN && p->trans != RSIGPU_TRANS_MED) return RSIGPU_E_ARG;   // -ALL: not built yet
+  rsigpu_ctx* c = new rsigpu_ctx();
+  c->device = device; c->P = *p;
+  if (c->P.m % 2 != 1) c->P.m += 1;   // rsi.cpp:2061-2064
+  if (c->P.m < 3 || c->P.m > C_TP) { delete c; return RSIGPU_E_ARG; }
+  if (cudaSetDevice(device) != cudaSuccess) { delete c; return RSIGPU_E_CUDA; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return RSIGPU_E_CUDA; }
+  c->n_sm = prop.multiProcessorCount;
+  set_smem_attrs();
+  bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaMalloc((void**)&c->d_st, sizeof(DevState)) == cudaSuccess;
+  ok = ok && cudaMallocHost((void**)&c->h_st, sizeof(DevState)) == cudaSuccess;
+  for (int k = 0; k < 8 && ok; ++k) ok = cudaEventCreate(&c->ev[k]) == cudaSuccess;
+  ok = ok && c->d_hist_all.ensure(HIST_ALL_BINS) == cudaSuccess && c->d_chist.ensure((size_t)MAD_CLASSES * CHIST_RCAP) == cudaSuccess;
+  ok = ok && c->d_thist.ensure(CHIST_RCAP) == cudaSuccess && c->d_tothist.ensure(CHIST_RCAP) == cudaSuccess;
+  ok = ok && c->d_fq_hist.ensure((size_t)FQ_BINS_CAP + 8) == cudaSuccess;
+  ok = ok && c->d_lists.ensure((size_t)LIST_CAP * 9 + 8) == cudaSuccess && c->d_misc.ensure(64) == cudaSuccess;
+  ok = ok && c->d_runs.ensure((size_t)LIST_CAP * 2 + 8) == cudaSuccess;
+  ok = ok && c->d_chist_c.ensure(1u << 22) == cudaSuccess && c->d_sub.ensure((size_t)p->maxchkbp * 10 + 64) == cudaSuccess;
+  ok = ok && c->d_nrun_beg.ensure(1 << 20) == cudaSuccess && c->d_nrun_end.ensure(1 << 20) == cudaSuccess;
+  if (ok) ok = cudaMemsetAsync(c->d_fq_hist.p, 0, ((size_t)FQ_BINS_CAP + 8) * 4, c->stream) == cudaSuccess;
+  if (!ok) { rsigpu_destroy(c); return RSIGPU_E_CUDA; }
+  *out = c;
+  return RSIGPU_OK;
+}
+
+void rsigpu_destroy(rsigpu_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  c->d_fasta.release(); c->d_raw.release(); c->d_rdc.release(); c->d_nseq.release();
+  c->d_hist_all.release(); c->d_chist.release(); c->d_thist.release(); c->d_tothist.release(); c->d_fq_hist.release();
+  c->d_bin_med.release(); c->d_bin_nbn.release(); c->d_lut.release(); c->d_bin_medint.release(); c->d_status.release(); c->d_status1.release();
+  c->d_tile.release(); c->d_nz_idx.release(); c->d_runs.release(); c->d_bin_sum.release(); c->d_pfx.release(); c->d_minl_del.release(); c->d_minl_dup.release();
+  c->d_lists.release(); c->d_misc.release(); c->d_ref.release(); c->d_sub.release(); c->d_pref.release(); c->d_rm.release(); c->d_chist_c.release();
+  c->d_nrun_beg.release(); c->d_nrun_end.release(); c->r_calend.release();
+  c->r_pos.release(); c->r_mpos.release(); c->r_isize.release(); c->r_mtid.release(); c->r_flag.release(); c->r_mapq.release(); c->r_qual.release();
+  c->r_cigar_off.release(); c->r_cigar.release(); c->r_qual_off.release();
+  if (c->d_st) cudaFree(c->d_st);
+  if (c->h_st) cudaFreeHost(c->h_st);
+  if (c->h_lut) cudaFreeHost(c->h_lut);
+  for (int k = 0; k < 8; ++k) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char* rsigpu_last_error(const rsigpu_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+// a3 + a4: N runs on the device, padding / merging of the few hundred intervals on the host
+int rsigpu_set_reference(rsigpu_ctx* c, const uint8_t* fasta, int32_t len, int32_t tid) {
+  if (!c || !fasta) return RSIGPU_E_ARG;
+  if (len < 1000) { c->fail("contig shorter than 1000 bases"); return RSIGPU_E_RANGE; }
+  cudaSetDevice(c->device);
+  c->L = len; c->tid = tid;
+  c->have_ref = true; c->have_depth = false; c->have_reads = false; c->loaded = false; c->detected = false; c->filtered = false;
+  const size_t padded = ((size_t)len + 15) / 16 * 16 + 512;
+  CK(c->d_fasta.ensure(padded));
+  CK(cudaMemsetAsync(c->d_fasta.p + len, 0, padded - (size_t)len, c->stream));
+  CK(cudaMemcpyAsync(c->d_fasta.p, fasta, (size_t)len, cudaMemcpyHostToDevice, c->stream));
+  int* n2 = c->d_misc.p + 8;
+  CK(cudaMemsetAsync(n2, 0, 8, c->stream));
+  const int cap = 1 << 20;
+  KL(k_n_runs, grid_for(len, 256 * 16, c->n_sm * 8), 256, 0, c->d_fasta.p, len, c->d_nrun_beg.p, c->d_nrun_end.p, n2, n2 + 1, cap);
+  int hn[2];
+  CK(cudaMemcpyAsync(hn, n2, 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (hn[0] != hn[1] || hn[0] > cap) { c->fail("more than 2^20 N runs"); return RSIGPU_E_RANGE; }
+  std::vector<int> b(hn[0]), e(hn[0]);
+  if (hn[0]) {
+    CK(cudaMemcpyAsync(b.data(), c->d_nrun_beg.p, (size_t)hn[0] * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(e.data(), c->d_nrun_end.p, (size_t)hn[0] * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    std::sort(b.begin(), b.end()); std::sort(e.begin(), e.end());
+  }
+  // get_noseq_regions (loaddata.cpp:243-273): pad by max(50, m/4), clamp, re-merge overlapping or touching runs
+  const int dx = std::max(50, c->P.m / 4);
+  c->h_nbeg.clear(); c->h_nend.clear();
+  for (int k = 0; k < hn[0]; ++k) {
+    const int pb = std::max(b[k] - dx, 0), pe = std::min(e[k] + dx, len - 1);
+    if (!c->h_nend.empty() && pb <= c->h_nend.back() + 1) c->h_nend.back() = std::max(c->h_nend.back(), pe);
+    else { c->h_nbeg.push_back(pb); c->h_nend.push_back(pe); }
+  }
+  const int nn = (int)c->h_nbeg.size();
+  std::vector<int> pack(3 * (size_t)nn + 4, 0);
+  int removed = 0;
+  for (int k = 0; k < nn; ++k) { pack[k] = c->h_nbeg[k]; pack[nn + k] = c->h_nend[k]; pack[2 * nn + k] = removed; removed += c->h_nend[k] - c->h_nbeg[k] + 1; }
+  CK(c->d_nseq.ensure(3 * (size_t)nn + 4));
+  CK(cudaMemcpyAsync(c->d_nseq.p, pack.data(), (3 * (size_t)nn + 4) * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->Lc = len - removed;
+  c->nb = c->Lc / c->P.m;
+  if (c->nb < 64) { c->fail("fewer than 64 bins after N removal"); return RSIGPU_E_RANGE; }
+  return RSIGPU_OK;
+}
+
+int rsigpu_set_depth(rsigpu_ctx* c, const int32_t* depth, int32_t len) {
+  if (!c || !depth) return RSIGPU_E_ARG;
+  if (!c->have_ref || len != c->L) { c->fail("set_depth: call set_reference first with the same length"); return RSIGPU_E_ARG; }
+  cudaSetDevice(c->device);
+  const size_t padded = ((size_t)len + LD_TILE - 1) / LD_TILE * LD_TILE + 64;
+  CK(c->d_raw.ensure(padded));
+  CK(cudaMemcpyAsync(c->d_raw.p, depth, (size_t)len * 4, cudaMemcpyHostToDevice, c->stream));
+  c->have_depth = true; c->have_reads = false; c->loaded = false; c->detected = false; c->filtered = false;
+  return RSIGPU_OK;
+}
+
+int rsigpu_pileup_begin(rsigpu_ctx* c, int32_t target_len) {
+  if (!c) return RSIGPU_E_ARG;
+  if (!c->have_ref || target_len != c->L) { c->fail("pileup_begin: call set_reference first with the same length"); return RSIGPU_E_ARG; }
+  c->r_pos.clear(); c->r_mpos.clear(); c->r_isize.clear(); c->r_mtid.clear(); c->r_flag.clear(); c->r_mapq.clear(); c->r_qual.clear();
+  c->r_cigar_off.clear(); c->r_cigar.clear(); c->r_qual_off.clear();
+  c->have_reads = false; c->have_depth = false; c->loaded = false; c->detected = false; c->filtered = false;
+  return RSIGPU_OK;
+}
+
+int rsigpu_pileup_push(rsigpu_ctx* c, const rsigpu_read_batch* b) {
+  if (!c || !b || b->n_reads < 0) return RSIGPU_E_ARG;
+  if (b->n_reads == 0) return RSIGPU_OK;
+  cudaSetDevice(c->device);
+  const size_t n = (size_t)b->n_reads;
+  const size_t nc = b->cigar_off[n], nq = (size_t)b->qual_off[n];
+  const size_t r0 = c->r_pos.n, c0 = c->r_cigar.n, q0 = c->r_qual.n;
+  if (c0 + nc >= 0xffffffffull) { c->fail("more than 2^32 CIGAR ops in one contig"); return RSIGPU_E_RANGE; }
+  CK(c->r_pos.append(b->pos, n, c->stream)); CK(c->r_mpos.append(b->mpos, n, c->stream)); CK(c->r_isize.append(b->isize, n, c->stream));
+  CK(c->r_mtid.append(b->mtid, n, c->stream)); CK(c->r_flag.append(b->flag, n, c->stream)); CK(c->r_mapq.append(b->mapq, n, c->stream));
+  CK(c->r_cigar.append(b->cigar, nc, c->stream)); CK(c->r_qual.append(b->qual, nq, c->stream));
+  // offsets: entry r0 of the previous batch (its end) equals this batch's first entry after rebasing
+  if (r0) { c->r_cigar_off.n = r0; c->r_qual_off.n = r0; }
+  CK(c->r_cigar_off.append(b->cigar_off, n + 1, c->stream)); CK(c->r_qual_off.append(reinterpret_cast<const u64*>(b->qual_off), n + 1, c->stream));
+  if (c0) KL(k_add_u32, grid_for((int)std::min<size_t>(n + 1, 1u << 30), 1024, c->n_sm * 4), 256, 0, c->r_cigar_off.p + r0, n + 1, (u32)c0);
+  if (q0) KL(k_add_u64, grid_for((int)std::min<size_t>(n + 1, 1u << 30), 1024, c->n_sm * 4), 256, 0, c->r_qual_off.p + r0, n + 1, (u64)q0);
+  // the caller's buffers may be reused as soon as this returns
+  CK(cudaStreamSynchronize(c->stream));
+  return RSIGPU_OK;
+}
+
+int rsigpu_pileup_end(rsigpu_ctx* c) {
+  if (!c) return RSIGPU_E_ARG;
+  cudaSetDevice(c->device);
+  const size_t padded = ((size_t)c->L + LD_TILE - 1) / LD_TILE * LD_TILE + 64;
+  CK(c->d_raw.ensure(padded));
+  int* mx = c->d_misc.p + 5;   // max_extent, sorted_bad
+  CK(cudaMemsetAsync(mx, 0, 8, c->stream));
+  if (c->r_pos.n == 0) {
+    CK(cudaMemsetAsync(c->d_raw.p, 0, padded * 4, c->stream));
+  } else {
+    CK(c->r_calend.ensure(c->r_pos.n + 8));
+    ReadSoA R = read_view(c);
+    KL(k_read_ends, grid_for((int)std::min<size_t>(c->r_pos.n, 1u << 30), 256, c->n_sm * 16), 256, 0, R, mx, mx + 1);
+    KL(k_pileup_tile, grid_for(c->L, PU_T, c->n_sm * 4), PU_NT, 0, R, c->d_raw.p, c->L, c->P.minq, c->P.min_baseQ, mx);
+    int h[2];
+    CK(cudaMemcpyAsync(h, mx, 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (h[1]) { c->fail("read batch is not sorted by position"); return RSIGPU_E_ARG; }
+  }
+  c->have_reads = true; c->have_depth = true; c->loaded = false; c->detected = false; c->filtered = false;
+  return RSIGPU_OK;
+}
+
+// a7 + a8 + a9 + chromosome statistics + bin arrays (median_transfer, negative_binomial_transfer)
+int rsigpu_load_finish(rsigpu_ctx* c) {
+  if (!c) return RSIGPU_E_ARG;
+  if (!c->have_ref || !c->have_depth) { c->fail("load_finish: no reference or depth staged"); return RSIGPU_E_ARG; }
+  cudaSetDevice(c->device);
+  const int L = c->L, nb = c->nb, nn = (int)c->h_nbeg.size(), m = c->P.m;
+  // buffers
+  CK(c->d_rdc.ensure((size_t)c->Lc + 64));
+  CK(c->d_bin_med.ensure(nb + 8)); CK(c->d_bin_nbn.ensure(nb + 8)); CK(c->d_bin_medint.ensure(nb + 8)); CK(c->d_bin_sum.ensure(nb + 8));
+  CK(c->d_status.ensure(nb + 8)); CK(c->d_status1.ensure(nb + 8)); CK(c->d_nz_idx.ensure(nb + 8)); CK(c->d_tile.ensure(nb / 1024 + 8));
+  CK(c->d_minl_del.ensure(nb + 8)); CK(c->d_minl_dup.ensure(nb + 8)); CK(c->d_pfx.ensure((size_t)nb + LIST_CAP + 8));
+  CK(c->d_ref.ensure((size_t)c->Lc + 64)); CK(c->d_pref.ensure((size_t)c->Lc + 64)); CK(c->d_rm.ensure((size_t)c->Lc + 64));
+  // device state
+  DevState* h = c->h_st;
+  memset(h, 0, sizeof(DevState));
+  h->L = L; h->Lc = c->Lc; h->nb = nb; h->m = m; h->n_noseq = nn; h->gc_on = c->P.gcadjust ? 1 : 0; h->cap_on = c->P.cap > 1 ? 1 : 0;
+  h->trans = c->P.trans; h->cap = c->P.cap; h->rd_min = 0x7fffffff; h->rd_max = -0x7fffffff - 1;
+  h->nb_tmin_ord = 0xffffffffu;
+  h->factor = sqrt(2.0 * (1.0 + c->P.epsilon) * log(3.1E9));   // rsi.cpp:1829
+  h->Lmax_base = std::max(10000 / m, 20);                        // rsi.cpp:1831
+  h->isize_mean = -1; h->isize_sd = -1;
+  CK(cudaEventRecord(c->ev[1], c->stream));
+  CK(cudaMemcpyAsync(c->d_st, h, sizeof(DevState), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemsetAsync(c->d_hist_all.p, 0, (size_t)HIST_ALL_BINS * 4, c->stream));
+  CK(cudaMemsetAsync(c->d_chist.p, 0, (size_t)MAD_CLASSES * CHIST_RCAP * 4, c->stream));
+  CK(cudaMemsetAsync(c->d_thist.p, 0, (size_t)CHIST_RCAP * 4, c->stream));
+  CK(cudaMemsetAsync(c->d_misc.p, 0, 5 * 4, c->stream));
+  const int* nbeg = c->d_nseq.p; const int* nend = nbeg + nn; const int* ncum = nbeg + 2 * nn;
+  const int ntiles = (L + LD_TILE - 1) / LD_TILE;
+  const size_t smA = (size_t)GC_STRATA * A_NT * 8 + LD_FAB + (LD_PRE + 8) * 2;
+  const size_t smB = (size_t)B_K * B_NT * 2 + GC_STRATA * 8 + LD_FAB + (LD_PRE + 8) * 2;
+  KL(k_gc_table, std::min(ntiles, c->n_sm), A_NT, smA, c->d_raw.p, c->d_fasta.p, c->d_st);
+  KL(k_gc_finalize, 1, 256, 0, c->d_fasta.p, c->d_st);
+  KL(k_gc_adjust, std::min(ntiles, c->n_sm * 2), B_NT, smB, c->d_raw.p, c->d_fasta.p, c->d_rdc.p, nbeg, nend, ncum, c->d_hist_all.p, c->d_st);
+  KL(k_cap_params, 1, 1024, 0, c->d_hist_all.p, c->d_st, CHIST_RCAP);
+  const int bpt = std::max(1, std::min(64, C_TP / m));
+  const int ntc = std::max(1, (nb + bpt - 1) / bpt);
+  KL(k_bins, std::min(ntc, c->n_sm), C_NT, (size_t)C_K * C_NT * 2 + C_TP * 4, c->d_rdc.p, c->d_bin_med.p, c->d_bin_medint.p, c->d_bin_sum.p, c->d_chist.p,
+     c->d_thist.p, c->d_st, bpt);
+  KL(k_chr_stats, 1, 1024, 0, c->d_chist.p, c->d_thist.p, c->d_tothist.p, c->d_st);
+  CK(cudaMemcpyAsync(h, c->d_st, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (h->err) return map_dev_err(c, h->err, h->cand_err);
+  // negative_binomial_transfer's table over the bin sums, with the host's libm (rsi.cpp:1142-1163)
+  const double rdmedian = h->rdmedian, r = rdmedian / h->rdmad;
+  const size_t lut_n = (size_t)h->max_binsum + 1;
+  if (lut_n > LUT_CAP) { c->fail("bin sums above 2^24: depth too high for the transform table"); return RSIGPU_E_RANGE; }
+  if (lut_n > c->h_lut_cap) {
+    if (c->h_lut) cudaFreeHost(c->h_lut);
+    c->h_lut = nullptr; c->h_lut_cap = 0;
+    CK(cudaMallocHost((void**)&c->h_lut, lut_n * 2 * sizeof(float)));
+    c->h_lut_cap = lut_n * 2;
+  }
+  CK(c->d_lut.ensure(lut_n + 8));
+  for (size_t s = 0; s < lut_n; ++s) c->h_lut[s] = (float)nb_formula((double)s, (double)m, r);
+  double anchors[3];
+  anchors[0] = nb_formula(rdmedian * m, (double)m, r);
+  anchors[1] = nb_formula(rdmedian / 2.0 * (double)m, (double)m, r);
+  anchors[2] = nb_formula(rdmedian * 1.5 * (double)m, (double)m, r);
+  h->med_nbt_raw = anchors[0]; h->del_nbt_raw = anchors[1]; h->dup_nbt_raw = anchors[2];
+  CK(cudaMemcpyAsync(c->d_lut.p, c->h_lut, lut_n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(field_ptr(c->d_st, &DevState::med_nbt_raw), &h->med_nbt_raw, 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  const int gb = grid_for(nb, 1024, c->n_sm * 8);
+  KL(k_nb_gather, gb, 256, 0, c->d_bin_sum.p, c->d_lut.p, (int)lut_n, c->d_bin_nbn.p, c->d_st);
+  KL(k_nb_scale, gb, 256, 0, c->d_bin_nbn.p, c->d_st);
+  CK(cudaEventRecord(c->ev[2], c->stream));
+  c->loaded = true; c->detected = false; c->filtered = false;
+  return RSIGPU_OK;
+}
+
+// detectcnv (rsi.cpp:1795-1945) incl. the list that sd_filters would keep
+int rsigpu_detectcnv(rsigpu_ctx* c) {
+  if (!c) return RSIGPU_E_ARG;
+  if (!c->loaded) { c->fail("detectcnv: call load_finish first"); return RSIGPU_E_ARG; }
+  cudaSetDevice(c->device);
+  DevState* h = c->h_st;
+  c->h_detected.clear(); c->h_calls.clear();
+  for (int k = 0; k < 4; ++k) c->h_dump[k].clear();
+  if (h->rdmedian < 5) {   // "Read depths too low", rsi.cpp:1809-1812
+    CK(cudaEventRecord(c->ev[3], c->stream)); CK(cudaEventRecord(c->ev[4], c->stream));
+    c->detected = true;
+    return RSIGPU_OK;
+  }
+  const int which = c->P.trans == RSIGPU_TRANS_MED ? 1 : 0;
+  int rc = run_rsi(c, which, which ? c->d_bin_med.p : c->d_bin_nbn.p);
+  if (rc) return rc;
+  CK(cudaEventRecord(c->ev[3], c->stream));
+  const int nn = (int)c->h_nbeg.size();
+  CandArgs A;
+  A.rdc = c->d_rdc.p; A.medint = c->d_bin_medint.p; A.status = c->d_status.p; A.nbeg = c->d_nseq.p; A.nend = c->d_nseq.p + nn;
+  A.segs = c->list(0); A.tmp = c->list(1); A.ov = c->list(2);
+  A.d_segments = c->list(3); A.d_blocks = c->list(4); A.d_premerge = c->list(5); A.d_merged = c->list(6); A.d_detected = c->list(7); A.d_calls = c->list(8);
+  A.n_dump = c->d_misc.p; A.list_cap = LIST_CAP;
+  A.S.ref = c->d_ref.p; A.S.ref_cap = (int)std::min<size_t>(c->d_ref.cap, 0x7fffffff); A.S.sub = c->d_sub.p; A.S.sub_cap = (int)c->d_sub.cap;
+  A.S.pref = c->d_pref.p; A.S.rm = c->d_rm.p; A.S.hist = c->d_chist_c.p; A.S.hist_cap = (int)c->d_chist_c.cap; A.S.err = c->d_misc.p + 4;
+  A.maxchkbp = c->P.maxchkbp; A.merge = c->P.merge; A.tid = c->tid; A.chklen = c->P.chklen;
+  KL(k_candidates, 1, 1024, 0, A, c->d_st);
+  CK(cudaEventRecord(c->ev[4], c->stream));
+  CK(cudaMemcpyAsync(h, c->d_st, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
+  int nd[4];
+  CK(cudaMemcpyAsync(nd, c->d_misc.p, 16, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (h->err) return map_dev_err(c, h->err, h->cand_err);
+  c->h_detected.resize(h->n_detected); c->h_calls.resize(h->n_calls);
+  if (h->n_detected) CK(cudaMemcpyAsync(c->h_detected.data(), c->list(7), sizeof(Cnv) * h->n_detected, cudaMemcpyDeviceToHost, c->stream));
+  if (h->n_calls) CK(cudaMemcpyAsync(c->h_calls.data(), c->list(8), sizeof(Cnv) * h->n_calls, cudaMemcpyDeviceToHost, c->stream));
+  for (int k = 0; k < 4; ++k) {
+    const int n = std::min(nd[k], LIST_CAP);
+    c->h_dump[k].resize(n);
+    if (n) CK(cudaMemcpyAsync(c->h_dump[k].data(), c->list(3 + k), sizeof(Cnv) * n, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  c->detected = true; c->filtered = false;
+  return RSIGPU_OK;
+}
+
+int rsigpu_sd_filters(rsigpu_ctx* c) {
+  if (!c) return RSIGPU_E_ARG;
+  if (!c->detected) { c->fail("sd_filters: call detectcnv first"); return RSIGPU_E_ARG; }
+  c->filtered = true;   // k_candidates already produced the filtered list next to the unfiltered one
+  return RSIGPU_OK;
+}
+
+// a26 + a27 on the read summaries kept by pileup_push
+int rsigpu_cnv_stat(rsigpu_ctx* c) {
+  if (!c) return RSIGPU_E_ARG;
+  if (!c->detected) { c->fail("cnv_stat: call detectcnv first"); return RSIGPU_E_ARG; }
+  if (!c->have_reads) { c->fail("cnv_stat: BAM input only (pairrd.cpp:622)"); return RSIGPU_E_ARG; }
+  cudaSetDevice(c->device);
+  std::vector<Cnv>& v = c->filtered ? c->h_calls : c->h_detected;
+  Cnv* d = c->filtered ? c->list(8) : c->list(7);
+  if (v.empty() || c->r_pos.n == 0) return RSIGPU_OK;
+  ReadSoA R = read_view(c);
+  int* mx = c->d_misc.p + 5;
+  KL(k_isize_stats, 1, 1024, 0, R, c->L, mx, c->d_st);
+  KL(k_cnv_stat, std::min((int)v.size(), c->n_sm * 4), 256, 0, R, d, (int)v.size(), mx, c->d_st);
+  CK(cudaMemcpyAsync(v.data(), d, sizeof(Cnv) * v.size(), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(&c->h_st->isize_mean, field_ptr(c->d_st, &DevState::isize_mean), 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return RSIGPU_OK;
+}
+
+int rsigpu_get_calls(rsigpu_ctx* c, rsigpu_cnv* out, int32_t cap, int32_t* n) {
+  if (!c || !n) return RSIGPU_E_ARG;
+  if (!c->detected) { c->fail("get_calls: call detectcnv first"); return RSIGPU_E_ARG; }
+  const std::vector<Cnv>& v = c->filtered ? c->h_calls : c->h_detected;
+  *n = (int32_t)v.size();
+  if ((int)v.size() > cap) return RSIGPU_E_CAPACITY;
+  if (out && !v.empty()) memcpy(out, v.data(), sizeof(Cnv) * v.size());
+  return RSIGPU_OK;
+}
+
+int rsigpu_run(rsigpu_ctx* c, rsigpu_cnv* out, int32_t cap, int32_t* n) {
+  if (!c) return RSIGPU_E_ARG;
+  cudaSetDevice(c->device);
+  int rc;
+  CK(cudaEventRecord(c->ev[0], c->stream));
+  if ((rc = rsigpu_load_finish(c)) != RSIGPU_OK) return rc;
+  if ((rc = rsigpu_detectcnv(c)) != RSIGPU_OK) return rc;
+  if ((rc = rsigpu_sd_filters(c)) != RSIGPU_OK) return rc;
+  if (c->have_reads && (rc = rsigpu_cnv_stat(c)) != RSIGPU_OK) return rc;
+  CK(cudaEventRecord(c->ev[5], c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  float ms = 0;
+  c->stage_ms[0] = 0;
+  cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->stage_ms[1] = ms;
+  cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); c->stage_ms[2] = ms;
+  cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]); c->stage_ms[3] = ms;
+  cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]); c->stage_ms[4] = ms;
+  cudaEventElapsedTime(&ms, c->ev[0], c->ev[5]); c->stage_ms[5] = ms;
+  return rsigpu_get_calls(c, out, cap, n);
+}
+
+int rsigpu_get_chr_stats(rsigpu_ctx* c, rsigpu_chr_stats* o) {
+  if (!c || !o) return RSIGPU_E_ARG;
+  if (!c->loaded) { c->fail("get_chr_stats: call load_finish first"); return RSIGPU_E_ARG; }
+  const DevState* h = c->h_st;
+  memset(o, 0, sizeof *o);
+  o->rdmedian = h->rdmedian; o->rdsd = h->rdsd; o->tmedian = h->out_tmedian; o->tlamda = h->out_tlamda; o->rdmad = h->rdmad;
+  o->target_len = c->L; o->compact_len = c->Lc; o->nbins = c->nb; o->lmax = h->Lmax; o->isize_mean = h->isize_mean; o->isize_sd = h->isize_sd;
+  o->n_noseq = (int)c->h_nbeg.size();
+  return RSIGPU_OK;
+}
+
+int rsigpu_get_array(rsigpu_ctx* c, int32_t which, void* out, int64_t cap, int64_t* count) {
+  if (!c || !count) return RSIGPU_E_ARG;
+  cudaSetDevice(c->device);
+  const void* src = nullptr; size_t esz = 4; int64_t n = 0; bool host = false;
+  switch (which) {
+    case RSIGPU_ARR_RAW_DEPTH: if (!c->have_depth) return RSIGPU_E_ARG; src = c->d_raw.p; n = c->L; break;
+    case RSIGPU_ARR_DEPTH: if (!c->loaded) return RSIGPU_E_ARG; src = c->d_rdc.p; n = c->Lc; break;
+    case RSIGPU_ARR_BIN_MED: if (!c->loaded) return RSIGPU_E_ARG; src = c->d_bin_med.p; n = c->nb; break;
+    case RSIGPU_ARR_BIN_NBN: if (!c->loaded) return RSIGPU_E_ARG; src = c->d_bin_nbn.p; n = c->nb; break;
+    case RSIGPU_ARR_BIN_MEDINT: if (!c->loaded) return RSIGPU_E_ARG; src = c->d_bin_medint.p; n = c->nb; break;
+    case RSIGPU_ARR_BIN_STATUS: if (!c->detected) return RSIGPU_E_ARG; src = c->d_status.p; n = c->nb; break;
+    case RSIGPU_ARR_BIN_STATUS1: if (!c->detected) return RSIGPU_E_ARG; src = c->d_status1.p; n = c->nb; break;
+    case RSIGPU_ARR_NOSEQ_BEG: src = c->h_nbeg.data(); n = (int64_t)c->h_nbeg.size(); host = true; break;
+    case RSIGPU_ARR_NOSEQ_END: src = c->h_nend.data(); n = (int64_t)c->h_nend.size(); host = true; break;
+    case RSIGPU_ARR_SEGMENTS: case RSIGPU_ARR_BLOCKS: case RSIGPU_ARR_PREMERGE: case RSIGPU_ARR_MERGED: {
+      if (!c->detected) return RSIGPU_E_ARG;
+      const std::vector<Cnv>& v = c->h_dump[which - RSIGPU_ARR_SEGMENTS];
+      src = v.data(); n = (int64_t)v.size(); esz = sizeof(Cnv); host = true; break;
+    }
+    case RSIGPU_ARR_DETECTED: if (!c->detected) return RSIGPU_E_ARG; src = c->h_detected.data(); n = (int64_t)c->h_detected.size(); esz = sizeof(Cnv); host = true; break;
+    default: return RSIGPU_E_ARG;
+  }
+  *count = n;
+  const int64_t k = std::min(n, cap);
+  if (!out || k <= 0) return RSIGPU_OK;
+  if (host) { memcpy(out, src, (size_t)k * esz); return RSIGPU_OK; }
+  CK(cudaMemcpyAsync(out, src, (size_t)k * esz, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return RSIGPU_OK;
+}
+
+// cnv_format1 (rsi.cpp:581-631); default ostream formatting of doubles = %g
+int rsigpu_format_row(const rsigpu_cnv* cnv, const char* chrom, double rdmedian, double rdsd, char* buf, int32_t cap) {
+  if (!buf || cap <= 0) return RSIGPU_E_ARG;
+  if (!cnv) {
+    int k = snprintf(buf, (size_t)cap, "#CHROM\tSTART\tEND\tTYPE\tSCORE\tLENGTH\tCNV_MED(CNV_SD);NEIGHBOR_MED(NEIGHBOR_RUNMEANSD);CHR_MED(CHR_SD)\tRP=#support_read_pairs;Q0=#fraction_of_Q0_reads\tMETHOD");
+    return k < cap ? RSIGPU_OK : RSIGPU_E_CAPACITY;
+  }
+  static const char* T[] = {"DEL", "DUP", "UNKNOWN"};
+  const double q1 = cnv->p1 < 1.0E-10 ? 99 : -10.0 * log(cnv->p1) / log(10.0);
+  const int ty = cnv->type >= 0 && cnv->type <= 2 ? cnv->type : 2;
+  int k = snprintf(buf, (size_t)cap, "%s\t%d\t%d\t%s\t%d\t%d\t%g(%g);%g(%g);%g(%g)\tRP=%d;Q0=%g\trsi", chrom ? chrom : "", cnv->start, cnv->end, T[ty],
+                   (int)q1, cnv->end - cnv->start + 1, cnv->cnvmed, cnv->cnviqr / 1.349, cnv->refmed, cnv->refiqr / 1.349, rdmedian, rdsd, cnv->rp, cnv->q0);
+  return k < cap ? RSIGPU_OK : RSIGPU_E_CAPACITY;
+}
+
+int64_t rsigpu_launch_count(const rsigpu_ctx* c) { return c ? c->launches : 0; }
+int rsigpu_last_stage_ms(const rsigpu_ctx* c, float* ms6) {
+  if (!c || !ms6) return RSIGPU_E_ARG;
+  for (int k = 0; k < 6; ++k) ms6[k] = c->stage_ms[k];
+  return RSIGPU_OK;
+}
+int rsigpu_set_profile(rsigpu_ctx* c, int on) {
+  if (!c) return RSIGPU_E_ARG;
+  c->profile = on != 0; c->prof.clear(); c->prof_order.clear();
+  return RSIGPU_OK;
+}
+int rsigpu_get_profile(const rsigpu_ctx* c, char* names, int32_t name_stride, float* ms, int32_t* launches, int32_t cap) {
+  if (!c) return 0;
+  int k = 0;
+  for (const std::string& nm : c->prof_order) {
+    if (k < cap) {
+      auto it = c->prof.find(nm);
+      if (names && name_stride > 0) { strncpy(names + (size_t)k * name_stride, nm.c_str(), (size_t)name_stride - 1); names[(size_t)k * name_stride + name_stride - 1] = 0; }
+      if (ms) ms[k] = it->second.first;
+      if (launches) launches[k] = it->second.second;
+    }
+    ++k;
+  }
+  return k;
+}
+
+// test hook: 0 = sequential float chain for filterstatus' level-0 sum, 1 = block-scan form (default)
+int rsigpu_set_level0_mode(rsigpu_ctx* c, int mode) { if (!c) return RSIGPU_E_ARG; c->level0_mode = mode ? 1 : 0; return RSIGPU_OK; }
+
+}  // extern "C"

@@ -1,0 +1,390 @@
+// cusim.h -- TEST-ONLY single-process emulation of the CUDA execution model (x86-64 Linux).
+//
+// There is no GPU in the development container, so the CUDA sources of rsicnv_b200/csrc are ALSO
+// compiled with g++ against this header (-DRSI_SIM) into tests/hostsim/librsigpu_sim.so, which the
+// CPU test-suite drives through the same C-ABI as the real library.  Every thread of a block is a
+// fiber; blocks run one after the other; __syncthreads and the warp collectives are scheduling
+// points.  CUSIM_ORDER=0/1/2 (forward / reverse / rotating) changes the order in which the fibers
+// of a block are resumed so that a missing barrier shows up as a parity failure in at least one
+// order.  Nothing here is ever linked into the product library (rsicnv_b200/librsigpu.so is built by
+// nvcc only and has no CPU path).
+#pragma once
+#if !defined(__x86_64__)
+#error "cusim.h supports x86-64 only"
+#endif
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __noinline__
+#define __restrict__
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __align__(n) __attribute__((aligned(n)))
+
+struct uint3 { unsigned x, y, z; };
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+};
+struct int4 { int x, y, z, w; };
+struct uint4 { unsigned x, y, z, w; };
+struct int2 { int x, y; };
+struct uint2 { unsigned x, y; };
+struct float4 { float x, y, z, w; };
+inline int4 make_int4(int a, int b, int c, int d) { return int4{a, b, c, d}; }
+inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { return uint4{a, b, c, d}; }
+inline int2 make_int2(int a, int b) { return int2{a, b}; }
+
+namespace cusim {
+
+struct Warp {
+  alignas(16) unsigned char slot[32][16];
+  alignas(16) unsigned char result[32][16];
+  unsigned arrived = 0, ready = 0, alive = 0;
+};
+struct Fiber {
+  void* sp = nullptr;
+  char* stack = nullptr;
+  bool done = false;
+  unsigned long long bar_gen_wait = 0;
+};
+struct State {
+  std::vector<Fiber> fib;
+  std::vector<Warp> warps;
+  int nthreads = 0, cur = -1, live = 0;
+  unsigned long long bar_gen = 0; int bar_arrived = 0; int bar_acc_or = 0, bar_acc_and = 1, bar_acc_cnt = 0;
+  int bar_res_or[2] = {0, 0}, bar_res_and[2] = {1, 1}, bar_res_cnt[2] = {0, 0};
+  void* sched_sp = nullptr;
+  std::function<void()> body;
+  unsigned char* dyn_smem = nullptr;
+  unsigned long long progress = 0;
+  dim3 block_dim, grid_dim;
+};
+inline State& S() { static State s; return s; }
+
+inline uint3& tIdx() { static uint3 v; return v; }
+inline uint3& bIdx() { static uint3 v; return v; }
+inline dim3& bDim() { static dim3 v; return v; }
+inline dim3& gDim() { static dim3 v; return v; }
+
+// ---- context switch: save callee-saved registers on the current stack, swap stack pointers
+extern "C" void cusim_switch(void** save_sp, void* new_sp);
+#if defined(CUSIM_IMPL)
+asm(R"(
+.text
+.globl cusim_switch
+.type cusim_switch,@function
+cusim_switch:
+  pushq %rbp
+  pushq %rbx
+  pushq %r12
+  pushq %r13
+  pushq %r14
+  pushq %r15
+  movq %rsp, (%rdi)
+  movq %rsi, %rsp
+  popq %r15
+  popq %r14
+  popq %r13
+  popq %r12
+  popq %rbx
+  popq %rbp
+  ret
+.size cusim_switch,.-cusim_switch
+)");
+#endif
+
+inline void yield_to_sched() {
+  State& s = S();
+  Fiber& f = s.fib[s.cur];
+  cusim_switch(&f.sp, s.sched_sp);
+}
+void fiber_entry();
+#if defined(CUSIM_IMPL)
+void fiber_entry() {
+  State& s = S();
+  s.body();
+  Fiber& f = s.fib[s.cur];
+  f.done = true;
+  s.live--;
+  s.warps[s.cur >> 5].alive &= ~(1u << (s.cur & 31));
+  s.progress++;
+  // a thread that exits releases a barrier the others are waiting on
+  if (s.live > 0 && s.bar_arrived == s.live) {
+    int slot = (int)(s.bar_gen & 1);
+    s.bar_res_or[slot] = s.bar_acc_or; s.bar_res_and[slot] = s.bar_acc_and; s.bar_res_cnt[slot] = s.bar_acc_cnt;
+    s.bar_acc_or = 0; s.bar_acc_and = 1; s.bar_acc_cnt = 0; s.bar_arrived = 0; s.bar_gen++;
+  }
+  cusim_switch(&f.sp, s.sched_sp);
+  std::abort();
+}
+#endif
+
+static const size_t kStack = 96 * 1024;
+
+inline void set_indices(int t) {
+  State& s = S();
+  uint3& ti = tIdx();
+  ti.x = t % s.block_dim.x; ti.y = (t / s.block_dim.x) % s.block_dim.y; ti.z = t / (s.block_dim.x * s.block_dim.y);
+}
+
+void run_block(int order_mode);
+#if defined(CUSIM_IMPL)
+void run_block(int order_mode) {
+  State& s = S();
+  const int n = s.nthreads;
+  s.live = n; s.bar_gen = 0; s.bar_arrived = 0; s.bar_acc_or = 0; s.bar_acc_and = 1; s.bar_acc_cnt = 0;
+  const int nw = (n + 31) / 32;
+  s.warps.assign(nw, Warp());
+  for (int t = 0; t < n; ++t) s.warps[t >> 5].alive |= 1u << (t & 31);
+  for (int t = 0; t < n; ++t) {
+    Fiber& f = s.fib[t];
+    f.done = false; f.bar_gen_wait = 0;
+    // initial frame: six zeroed callee-saved registers, then the entry address for `ret`
+    uintptr_t top = ((uintptr_t)(f.stack + kStack)) & ~(uintptr_t)15;
+    void** sp = (void**)top;
+    *--sp = nullptr;                 // fake return address slot (keeps rsp%16==8 at entry)
+    *--sp = (void*)&fiber_entry;
+    for (int k = 0; k < 6; ++k) *--sp = nullptr;
+    f.sp = (void*)sp;
+  }
+  unsigned long long rounds = 0;
+  while (s.live > 0) {
+    unsigned long long before = s.progress;
+    for (int k = 0; k < n; ++k) {
+      int t = k;
+      if (order_mode == 1) t = n - 1 - k;
+      else if (order_mode == 2) t = (int)((k + rounds * 7) % (unsigned long long)n);
+      Fiber& f = s.fib[t];
+      if (f.done) continue;
+      s.cur = t;
+      set_indices(t);
+      cusim_switch(&s.sched_sp, f.sp);
+    }
+    ++rounds;
+    if (s.progress == before) {
+      std::fprintf(stderr, "cusim: deadlock (divergent barrier / collective) in block (%u,%u,%u)\n", bIdx().x, bIdx().y, bIdx().z);
+      std::abort();
+    }
+  }
+}
+#endif
+
+inline int order_mode() {
+  static int m = -1;
+  if (m < 0) { const char* e = std::getenv("CUSIM_ORDER"); m = e ? std::atoi(e) : 0; }
+  return m;
+}
+
+void launch(dim3 grid, dim3 block, size_t smem, std::function<void()> body);
+#if defined(CUSIM_IMPL)
+void launch(dim3 grid, dim3 block, size_t smem, std::function<void()> body) {
+  State& s = S();
+  if (s.cur >= 0 && s.live > 0) { std::fprintf(stderr, "cusim: nested launch\n"); std::abort(); }
+  const int n = (int)(block.x * block.y * block.z);
+  if (n <= 0 || n > 1024) { std::fprintf(stderr, "cusim: bad block size %d\n", n); std::abort(); }
+  if ((int)s.fib.size() < n) {
+    size_t old = s.fib.size();
+    s.fib.resize(n);
+    for (size_t t = old; t < (size_t)n; ++t) s.fib[t].stack = (char*)std::malloc(kStack);
+  }
+  std::vector<unsigned char> dyn(smem + 64);
+  s.nthreads = n; s.block_dim = block; s.grid_dim = grid; s.body = std::move(body);
+  bDim() = block; gDim() = grid;
+  for (unsigned z = 0; z < grid.z; ++z)
+    for (unsigned y = 0; y < grid.y; ++y)
+      for (unsigned x = 0; x < grid.x; ++x) {
+        std::memset(dyn.data(), 0xCD, dyn.size());  // shared memory is NOT zero-initialised on a GPU
+        s.dyn_smem = (unsigned char*)(((uintptr_t)dyn.data() + 15) & ~(uintptr_t)15);
+        bIdx().x = x; bIdx().y = y; bIdx().z = z;
+        run_block(order_mode());
+      }
+  s.cur = -1; s.live = 0;
+}
+#endif
+
+// ---- block barrier
+inline int barrier(int pred, int kind) {  // kind 0 plain, 1 or, 2 and, 3 count
+  State& s = S();
+  Fiber& f = s.fib[s.cur];
+  s.bar_acc_or |= (pred != 0); s.bar_acc_and &= (pred != 0); s.bar_acc_cnt += (pred != 0);
+  const unsigned long long gen = s.bar_gen;
+  s.bar_arrived++;
+  s.progress++;
+  if (s.bar_arrived == s.live) {
+    int slot = (int)(gen & 1);
+    s.bar_res_or[slot] = s.bar_acc_or; s.bar_res_and[slot] = s.bar_acc_and; s.bar_res_cnt[slot] = s.bar_acc_cnt;
+    s.bar_acc_or = 0; s.bar_acc_and = 1; s.bar_acc_cnt = 0; s.bar_arrived = 0; s.bar_gen++;
+  } else {
+    f.bar_gen_wait = gen;
+    while (s.bar_gen == gen) yield_to_sched();
+  }
+  int slot = (int)(gen & 1);
+  return kind == 1 ? s.bar_res_or[slot] : kind == 2 ? s.bar_res_and[slot] : kind == 3 ? s.bar_res_cnt[slot] : 0;
+}
+
+// ---- warp collective: the last lane to arrive computes every participant's result
+template <class T, class R, class F>
+inline R warp_coll(unsigned mask, const T& val, F f) {
+  static_assert(sizeof(T) <= 16 && sizeof(R) <= 16, "payload");
+  State& s = S();
+  Warp& W = s.warps[s.cur >> 5];
+  const int lane = s.cur & 31;
+  const unsigned bit = 1u << lane;
+  mask &= W.alive;
+  if (!(mask & bit)) { std::fprintf(stderr, "cusim: lane %d not in its own mask\n", lane); std::abort(); }
+  std::memcpy(W.slot[lane], &val, sizeof(T));
+  W.arrived |= bit;
+  s.progress++;
+  if ((W.arrived & mask) == mask) {
+    T vals[32];
+    for (int l = 0; l < 32; ++l) std::memcpy(&vals[l], W.slot[l], sizeof(T));
+    for (int l = 0; l < 32; ++l)
+      if (mask & (1u << l)) { R r = f(l, vals, mask); std::memcpy(W.result[l], &r, sizeof(R)); }
+    W.ready |= mask;
+    W.arrived &= ~mask;
+  } else {
+    while (!(W.ready & bit)) yield_to_sched();
+  }
+  W.ready &= ~bit;
+  R r;
+  std::memcpy(&r, W.result[lane], sizeof(R));
+  return r;
+}
+
+}  // namespace cusim
+
+#define threadIdx (cusim::tIdx())
+#define blockIdx (cusim::bIdx())
+#define blockDim (cusim::bDim())
+#define gridDim (cusim::gDim())
+static const int warpSize = 32;
+
+inline void __syncthreads() { cusim::barrier(0, 0); }
+inline int __syncthreads_or(int p) { return cusim::barrier(p, 1); }
+inline int __syncthreads_and(int p) { return cusim::barrier(p, 2); }
+inline int __syncthreads_count(int p) { return cusim::barrier(p, 3); }
+inline void __syncwarp(unsigned mask = 0xffffffffu) {
+  cusim::warp_coll<int, int>(mask, 0, [](int, const int*, unsigned) { return 0; });
+}
+inline void __threadfence() {}
+inline void __threadfence_block() {}
+inline unsigned __activemask() { return cusim::S().warps[cusim::S().cur >> 5].alive; }
+
+template <class T> inline T __shfl_sync(unsigned mask, T v, int src, int width = 32) {
+  return cusim::warp_coll<T, T>(mask, v, [=](int l, const T* a, unsigned) { int base = l & ~(width - 1); return a[base + (src & (width - 1))]; });
+}
+template <class T> inline T __shfl_xor_sync(unsigned mask, T v, int lm, int width = 32) {
+  return cusim::warp_coll<T, T>(mask, v, [=](int l, const T* a, unsigned) { int o = l ^ lm; return (o / width == l / width && o < 32) ? a[o] : a[l]; });
+}
+template <class T> inline T __shfl_up_sync(unsigned mask, T v, unsigned d, int width = 32) {
+  return cusim::warp_coll<T, T>(mask, v, [=](int l, const T* a, unsigned) { int o = l - (int)d; return (o >= (l & ~(width - 1))) ? a[o] : a[l]; });
+}
+template <class T> inline T __shfl_down_sync(unsigned mask, T v, unsigned d, int width = 32) {
+  return cusim::warp_coll<T, T>(mask, v, [=](int l, const T* a, unsigned) { int o = l + (int)d; return (o < (l & ~(width - 1)) + width) ? a[o] : a[l]; });
+}
+inline unsigned __ballot_sync(unsigned mask, int p) {
+  return cusim::warp_coll<int, unsigned>(mask, p, [](int, const int* a, unsigned m) { unsigned r = 0; for (int l = 0; l < 32; ++l) if ((m >> l & 1) && a[l]) r |= 1u << l; return r; });
+}
+inline int __any_sync(unsigned mask, int p) { return __ballot_sync(mask, p) != 0; }
+inline int __all_sync(unsigned mask, int p) {
+  return cusim::warp_coll<int, int>(mask, p, [](int, const int* a, unsigned m) { for (int l = 0; l < 32; ++l) if ((m >> l & 1) && !a[l]) return 0; return 1; });
+}
+template <class T> inline unsigned __match_any_sync(unsigned mask, T v) {
+  return cusim::warp_coll<T, unsigned>(mask, v, [](int me, const T* a, unsigned m) { unsigned r = 0; for (int l = 0; l < 32; ++l) if ((m >> l & 1) && a[l] == a[me]) r |= 1u << l; return r; });
+}
+template <class T> inline T __reduce_add_sync(unsigned mask, T v) {
+  return cusim::warp_coll<T, T>(mask, v, [](int, const T* a, unsigned m) { T r = 0; for (int l = 0; l < 32; ++l) if (m >> l & 1) r += a[l]; return r; });
+}
+template <class T> inline T __reduce_min_sync(unsigned mask, T v) {
+  return cusim::warp_coll<T, T>(mask, v, [](int me, const T* a, unsigned m) { T r = a[me]; for (int l = 0; l < 32; ++l) if ((m >> l & 1) && a[l] < r) r = a[l]; return r; });
+}
+template <class T> inline T __reduce_max_sync(unsigned mask, T v) {
+  return cusim::warp_coll<T, T>(mask, v, [](int me, const T* a, unsigned m) { T r = a[me]; for (int l = 0; l < 32; ++l) if ((m >> l & 1) && a[l] > r) r = a[l]; return r; });
+}
+inline unsigned __reduce_or_sync(unsigned mask, unsigned v) {
+  return cusim::warp_coll<unsigned, unsigned>(mask, v, [](int, const unsigned* a, unsigned m) { unsigned r = 0; for (int l = 0; l < 32; ++l) if (m >> l & 1) r |= a[l]; return r; });
+}
+
+// ---- atomics (one fiber runs at a time)
+template <class T> inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
+template <class T> inline T atomicSub(T* p, T v) { T o = *p; *p = o - v; return o; }
+template <class T> inline T atomicMin(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
+template <class T> inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }
+template <class T> inline T atomicOr(T* p, T v) { T o = *p; *p = o | v; return o; }
+template <class T> inline T atomicAnd(T* p, T v) { T o = *p; *p = o & v; return o; }
+template <class T> inline T atomicExch(T* p, T v) { T o = *p; *p = v; return o; }
+template <class T> inline T atomicCAS(T* p, T c, T v) { T o = *p; if (o == c) *p = v; return o; }
+
+// ---- intrinsics
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
+inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }
+inline int __clzll(long long v) { return v == 0 ? 64 : __builtin_clzll((unsigned long long)v); }
+inline int __ffs(int v) { return __builtin_ffs(v); }
+inline int __ffsll(long long v) { return __builtin_ffsll(v); }
+inline unsigned __brev(unsigned v) { unsigned r = 0; for (int i = 0; i < 32; ++i) if (v >> i & 1) r |= 1u << (31 - i); return r; }
+inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
+inline unsigned __float_as_uint(float f) { unsigned i; std::memcpy(&i, &f, 4); return i; }
+inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
+inline float __uint_as_float(unsigned i) { float f; std::memcpy(&f, &i, 4); return f; }
+inline long long __double_as_longlong(double d) { long long i; std::memcpy(&i, &d, 8); return i; }
+inline double __longlong_as_double(long long i) { double d; std::memcpy(&d, &i, 8); return d; }
+template <class T> inline T __ldg(const T* p) { return *p; }
+inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
+inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
+inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
+inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
+inline double __ll2double_rn(long long v) { return (double)v; }
+inline float __double2float_rn(double v) { return (float)v; }
+using std::max;
+using std::min;
+
+// ---- the slice of the runtime API the host side of librsigpu uses
+typedef int cudaError_t;
+typedef void* cudaStream_t;
+struct CusimEvent { std::chrono::steady_clock::time_point t; };
+typedef CusimEvent* cudaEvent_t;
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1 };
+enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3, cudaMemcpyHostToHost = 0 };
+enum { cudaStreamNonBlocking = 1, cudaHostAllocDefault = 0, cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+struct cudaDeviceProp { int multiProcessorCount; size_t sharedMemPerBlockOptin; char name[64]; };
+inline const char* cudaGetErrorString(cudaError_t) { return "cusim error"; }
+inline cudaError_t cudaGetLastError() { return 0; }
+inline cudaError_t cudaPeekAtLastError() { return 0; }
+inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return 0; }
+inline cudaError_t cudaSetDevice(int) { return 0; }
+inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { p->multiProcessorCount = 4; p->sharedMemPerBlockOptin = 227 * 1024; std::strcpy(p->name, "cusim"); return 0; }
+inline cudaError_t cudaMalloc(void** p, size_t n) { *p = std::malloc(n ? n : 1); if (!*p) return cudaErrorMemoryAllocation; std::memset(*p, 0xA5, n); return 0; }
+template <class T> inline cudaError_t cudaMalloc(T** p, size_t n) { return cudaMalloc((void**)p, n); }
+inline cudaError_t cudaFree(void* p) { std::free(p); return 0; }
+inline cudaError_t cudaMallocHost(void** p, size_t n) { *p = std::malloc(n ? n : 1); return *p ? 0 : cudaErrorMemoryAllocation; }
+template <class T> inline cudaError_t cudaMallocHost(T** p, size_t n) { return cudaMallocHost((void**)p, n); }
+inline cudaError_t cudaFreeHost(void* p) { std::free(p); return 0; }
+inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memcpy(d, s, n); return 0; }
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { std::memcpy(d, s, n); return 0; }
+inline cudaError_t cudaMemset(void* d, int v, size_t n) { std::memset(d, v, n); return 0; }
+inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { std::memset(d, v, n); return 0; }
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return 0; }
+inline cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = nullptr; return 0; }
+inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+inline cudaError_t cudaDeviceSynchronize() { return 0; }
+inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new CusimEvent(); return 0; }
+inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return 0; }
+inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) { e->t = std::chrono::steady_clock::now(); return 0; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
+inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) { *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count(); return 0; }
+template <class F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { return 0; }
