@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""bench.py -- Gbases/s of the B200-native `rsicnv rsi` depth -> CNV-call path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload chr19_bam|chr19_depth]
+
+One "step" = one pass of the hot path over one synthetic b37-chr19-shaped contig (59,128,983 bp, 30x, 20
+planted DEL/DUP) per GPU.  `value` = bases of all contigs processed per second with the inputs already
+resident in HBM (device time, CUDA events on the launching stream, max over ranks); `e2e` = the same
+through the C ABI with pinned HOST buffers, host<->device copies inside the timed region.  N > 1: one
+process per GPU (torchrun), contigs are independent units => no data-path collective, weak scaling.
+`--impl reference` times the reference's own CPU implementation (oracle/_ref, built from
+/root/reference by oracle/Makefile.ref) on the box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from rsicnv_b200 import synth  # noqa: E402
+
+CHR19 = synth.CHR19_LEN
+METRIC = "Gbases/s depth->RSI CNV calls"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)"""
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index; self.proc = None; self.lines = []
+
+    def start(self):
+        q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_inputs(seed: int, L: int):
+    fa = synth.make_fasta(L, seed)
+    depth, events = synth.make_depth(L, seed, fa, n_events=20)
+    return fa, depth, events
+
+
+# algorithmic HBM bytes of one launch of each streaming kernel (DESIGN.md "kernels"); L = contig, Lc = after N removal
+def kernel_bytes(name: str, L: int, Lc: int, reads_bytes: int = 0):
+    return {
+        "k_gc_table": 5 * L,          # depth 4 + FASTA 1, read once
+        "k_gc_adjust": 9 * L,         # depth 4 + FASTA 1 read, adjusted depth 4 written
+        "k_bins": 4 * Lc,             # compacted depth read once
+        "k_pileup_tile": reads_bytes + 4 * L,
+    }.get(name, 0)
+
+
+def ref_worker(args):
+    """one reference-CPU process: the reference's own functions on an in-memory contig (oracle/_ref/libref_harness.so)"""
+    seed, L, kind = args
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from bind import Lib
+    fa, depth, _ = make_inputs(seed, L)
+    r = Lib(kind); r.set_params()
+    t0 = time.perf_counter()
+    res = r.depth_path(depth, fa, 3)
+    return time.perf_counter() - t0, len(res["calls"])
+
+
+def ref_kind():
+    """"reference" = the unmodified reference objects built into oracle/_ref; "port" = the oracle restatement"""
+    if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_harness.so")):
+        return "ref", "reference"
+    if not os.path.exists(os.path.join(ROOT, "oracle", "librsi_oracle.so")):
+        subprocess.run(["make", "-s", "oracle"], cwd=ROOT, check=True)
+    return "oracle", "port"
+
+
+def time_reference(sample_len: int, procs: int, seed0: int):
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    lib_kind = ref_kind()[0]
+    with ctx.Pool(procs) as pool:
+        t0 = time.perf_counter()
+        out = pool.map(ref_worker, [(seed0 + i, sample_len, lib_kind) for i in range(procs)])
+        wall = time.perf_counter() - t0
+    cpu = max(o[0] for o in out)       # slowest worker's compute time (input synthesis excluded)
+    return cpu, wall, out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="chr19_depth", choices=["chr19_depth"])
+    ap.add_argument("--len", type=int, default=CHR19, help="contig length (debug; the contract uses the default)")
+    ap.add_argument("--cpu-sample", type=int, default=12_000_000)
+    ap.add_argument("--profile-steps", type=int, default=2)
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    L = a.len
+    workload = f"{a.workload}: rsicnv rsi -d <synthetic chr19-shaped depth, {L} bp, 30x NB-like, 20 planted DEL/DUP> -c 19 -f <synthetic FASTA> -m 101 -np"
+    config = {"workload": workload, "contigs_per_step_per_gpu": 1, "contig_bp": L, "m": 101, "parallelism": f"contig-sharded x{world}",
+              "l2": "inputs (depth 4 B/base + FASTA 1 B/base = %.0f MB per contig) are larger than the 126 MB L2" % (5 * L / 1e6)}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        procs = min(os.cpu_count() or 1, 32)
+        sample = min(a.cpu_sample, L)
+        kind = ref_kind()[1]
+        times = []
+        for s in range(a.warmup + a.steps):
+            if s < a.warmup and s > 0:
+                continue  # one warm-up pass is enough for a CPU job (page cache / import)
+            cpu, wall, out = time_reference(sample, procs, 1000 + 97 * s)
+            if s >= a.warmup:
+                times.append(cpu)
+        ms = 1e3 * float(np.mean(times))
+        val = procs * sample / (ms / 1e3) / 1e9
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Gbases/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/f64", "data": "synthetic",
+                "config": config,
+                "cpu_baseline": {"value": val, "unit": "Gbases/s", "cores": procs, "kind": kind,
+                                 "sample": f"{procs} processes x one {sample} bp synthetic contig each through the reference's own checkgccontent..detectcnv..sd_filters "
+                                           f"(in-memory depth array, same boundary as the C ABI; text parsing excluded)"},
+                "e2e": {"value": val, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from rsicnv_b200 import api
+
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: the product has no CPU path"}))
+        return 2
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    fa, depth, events = make_inputs(19 + rank, L)
+    # pinned host buffers (the e2e leg copies from these every step)
+    fa_pin = torch.from_numpy(fa).pin_memory(); dp_pin = torch.from_numpy(depth).pin_memory()
+    ctx = api.Context(device=local)
+    buf = (api.Cnv * 65536)()
+
+    def stage_inputs():
+        ctx.set_reference_ptr(fa_pin.data_ptr(), L)
+        ctx.set_depth_ptr(dp_pin.data_ptr(), L)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident leg: inputs staged once, each step = the whole hot path on the resident contig
+    stage_inputs()
+    for _ in range(a.warmup):
+        ncalls = ctx.run_count(buf, 65536)
+    sampler = ClockSampler(local); sampler.start()
+    barrier()
+    l0 = ctx.launch_count()
+    t0 = time.perf_counter()
+    dev_ms = 0.0; stages = None
+    for _ in range(a.steps):
+        ncalls = ctx.run_count(buf, 65536)
+        sm = ctx.stage_ms(); dev_ms += sm["total"]
+        stages = sm if stages is None else {k: stages[k] + sm[k] for k in sm}
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    clocks = sampler.stop()
+    launches = ctx.launch_count() - l0
+    st = ctx.chr_stats()
+    # ---- end-to-end leg: pinned host buffers -> H2D -> hot path -> calls on the host, every step
+    for _ in range(max(1, a.warmup // 2)):
+        stage_inputs(); ctx.run_count(buf, 65536)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        stage_inputs(); ne = ctx.run_count(buf, 65536)
+    barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - t0)
+    # ---- per-kernel device times (extra profiled steps, CUDA events around every launch on the context's stream)
+    ctx.set_profile(True)
+    for _ in range(a.profile_steps):
+        ctx.run_count(buf, 65536)
+    prof = ctx.profile()
+    ctx.set_profile(False)
+
+    t = torch.tensor([dev_ms, wall_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, wall_ms, e2e_ms = [float(x) for x in t.tolist()]
+    if rank == 0:
+        peak, peak_src = peaks()
+        total_bases = world * L * a.steps
+        value = total_bases / (dev_ms / 1e3) / 1e9
+        kern = []
+        for name, ms, n in prof:
+            b = kernel_bytes(name, L, st.compact_len)
+            avg = ms / max(n, 1)
+            kern.append({"kernel": name, "launches_per_step": n / a.profile_steps, "avg_ms": avg, "ms_per_step": ms / a.profile_steps,
+                         "algorithmic_bytes": b, "gbs": (b / 1e9) / (avg / 1e3) if b and avg > 0 else None})
+        kern.sort(key=lambda k: -k["ms_per_step"])
+        top = kern[0] if kern else None
+        stream = [k for k in kern if k["algorithmic_bytes"]]
+        roof = None
+        if top:
+            ach = top["gbs"] or 0.0
+            roof = {"bound": "hbm", "kernel": top["kernel"], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "peak_source": peak_src, "share_of_step": top["ms_per_step"] / max(sum(k["ms_per_step"] for k in kern), 1e-9),
+                    "how": "algorithmic bytes per launch / average launch duration (CUDA events on the context's stream, %d extra profiled steps)" % a.profile_steps,
+                    "streaming_kernels": [{"kernel": k["kernel"], "gbs": k["gbs"], "frac": (k["gbs"] or 0) / peak, "ms": k["avg_ms"]} for k in stream]}
+        line = {"metric": METRIC, "value": value, "unit": "Gbases/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": dev_ms / a.steps, "wall_ms_per_step": wall_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "int32 depth / f64 statistics", "data": "synthetic", "config": config, "clocks": clocks,
+                "e2e": {"value": total_bases / (e2e_ms / 1e3) / 1e9, "unit": "Gbases/s", "h2d_bytes_per_step": 5 * L, "d2h_bytes_per_step": int(ne * 128 + 53000),
+                        "ms_per_step": e2e_ms / a.steps},
+                "gpu_launches": int(launches), "calls_per_contig": int(ncalls), "roofline": roof,
+                "stage_ms_per_step": {k: v / a.steps for k, v in (stages or {}).items()}, "kernels": kern[:12]}
+        if world == 1:
+            sample = min(a.cpu_sample, L)
+            cpu, _, out = time_reference(sample, 1, 19)
+            line["cpu_baseline"] = {"value": sample / cpu / 1e9, "unit": "Gbases/s", "cores": 1, "kind": ref_kind()[1],
+                                    "sample": f"one {sample} bp synthetic contig through checkgccontent..detectcnv..sd_filters on one host core "
+                                              f"(the reference is single-threaded; in-memory depth array, text parsing excluded)"}
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

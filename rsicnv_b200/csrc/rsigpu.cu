@@ -448,7 +448,14 @@ int rsigpu_load_finish(rsigpu_ctx* c) {
   KL(k_chr_stats, 1, 1024, 0, c->d_chist.p, c->d_thist.p, c->d_tothist.p, c->d_st);
   CK(cudaMemcpyAsync(h, c->d_st, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  const bool low_depth = h->rdmedian < 5;   // "Read depths too low": detectcnv returns without calls (rsi.cpp:1809-1812)
+  if (low_depth) h->err &= ~ERR_DEGENERATE;
   if (h->err) return map_dev_err(c, h->err, h->cand_err);
+  if (low_depth) {
+    CK(cudaEventRecord(c->ev[2], c->stream));
+    c->loaded = true; c->detected = false; c->filtered = false;
+    return RSIGPU_OK;
+  }
   // negative_binomial_transfer's table over the bin sums, with the host's libm (rsi.cpp:1142-1163)
   const double rdmedian = h->rdmedian, r = rdmedian / h->rdmad;
   const size_t lut_n = (size_t)h->max_binsum + 1;
