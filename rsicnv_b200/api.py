@@ -71,7 +71,7 @@ EXPORTS = ("rsigpu_default_params", "rsigpu_create", "rsigpu_destroy", "rsigpu_l
            "rsigpu_set_depth", "rsigpu_pileup_begin", "rsigpu_pileup_push", "rsigpu_pileup_end", "rsigpu_load_finish", "rsigpu_detectcnv",
            "rsigpu_sd_filters", "rsigpu_cnv_stat", "rsigpu_get_calls", "rsigpu_run", "rsigpu_get_chr_stats", "rsigpu_get_array",
            "rsigpu_format_row", "rsigpu_launch_count", "rsigpu_last_stage_ms", "rsigpu_set_profile", "rsigpu_get_profile",
-           "rsigpu_set_level0_mode")
+           "rsigpu_set_level0_mode", "rsigpu_debug_state")
 
 _libs: dict[str, C.CDLL] = {}
 
@@ -245,6 +245,15 @@ class Context:
             nm = names.raw[i * stride:(i + 1) * stride].split(b"\0", 1)[0].decode()
             out.append((nm, float(ms[i]), int(ln[i])))
         return out
+
+    DEBUG_FIELDS = ("err", "rd_min", "rd_max", "pos_sum", "pos_cnt", "rdmean", "cap_median", "cap_thr", "capv", "hist_base", "chist_R", "rdmedian",
+                    "rdsd", "rdmad", "max_binsum", "gstar", "gc_tab80", "gc_tab90", "gc_tab100", "gc_cnt90", "tmedian", "tsigma", "tlamda", "Lmax",
+                    "lbreak_del", "lbreak_dup", "n_runs", "n_nonzero", "st_lo", "st_hi", "lvl0_sum", "filt_on")
+
+    def debug_state(self) -> dict:
+        a = (C.c_double * 64)()
+        n = self.lib.rsigpu_debug_state(self.h, a, C.c_int32(64))
+        return dict(zip(self.DEBUG_FIELDS, [float(a[i]) for i in range(n)]))
 
     def set_level0_mode(self, mode: int):
         self._ck(self.lib.rsigpu_set_level0_mode(self.h, C.c_int(mode)))

@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(C_NT) k_bins(int* __restrict__ rdc, float* __r
 
 // RDmedian, RDsd (rsi.cpp:2202-2203) and negative_binomial_transfer's MAD (rsi.cpp:1128-1140) from the
 // class histograms.  One block; thread c < 31 walks class c.
-__global__ void k_chr_stats(const u32* chist, const u32* thist, u32* tot_hist, DevState* st) {
+__global__ void __launch_bounds__(1024) k_chr_stats(const u32* chist, const u32* thist, u32* tot_hist, DevState* st) {
   RSI_CTA_SETUP(c);
   __shared__ double s_mad[MAD_CLASSES];
   const int R = st->chist_R, Lc = st->Lc;

@@ -269,7 +269,7 @@ __device__ void cta_hist_pick(const Cta& c, const CT* hist, int nbins, u64 r0, u
 
 // apply_cap's parameters: median of the adjusted depths over all L positions, threshold med*cap,
 // replacement value int(med*cap); also the value range of the class histograms of k_bins.
-__global__ void k_cap_params(const u32* hist_all, DevState* st, int chist_rcap) {
+__global__ void __launch_bounds__(1024) k_cap_params(const u32* hist_all, DevState* st, int chist_rcap) {
   RSI_CTA_SETUP(c);
   const u64 n = (u64)st->L;
   int pick[3], fnz, lnz;

@@ -72,7 +72,7 @@ __global__ void k_fq_hist(const float* __restrict__ x, const int* __restrict__ s
   }
 }
 
-__global__ void k_fq_pick(u32* hist, DevState* st, int slot) {
+__global__ void __launch_bounds__(1024) k_fq_pick(u32* hist, DevState* st, int slot) {
   RSI_CTA_SETUP(c);
   QuantJob* j = &st->qj[slot];
   double ymin, ymax; u64 np;

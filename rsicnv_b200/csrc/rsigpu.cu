@@ -25,6 +25,7 @@ namespace {
   do {                                                                                            \
     cudaError_t e_ = (call);                                                                      \
     if (e_ != cudaSuccess) { c->fail(std::string(#call) + ": " + cudaGetErrorString(e_)); return RSIGPU_E_CUDA; } \
+    if (!c->launch_err.empty()) { c->fail("kernel launch failed: " + c->launch_err); c->launch_err.clear(); return RSIGPU_E_CUDA; } \
   } while (0)
 
 template <class T>
@@ -109,6 +110,7 @@ struct rsigpu_ctx {
   std::map<std::string, std::pair<float, int>> prof;
   std::vector<std::string> prof_order;
 
+  std::string launch_err;
   void fail(const std::string& m) { err = m; }
   Cnv* list(int k) const { return d_lists.p + (size_t)k * LIST_CAP; }
 };
@@ -131,8 +133,13 @@ struct KTimer {
     cudaEventDestroy(a); cudaEventDestroy(b);
   }
 };
-#define KL(name, grid, block, smem, ...)                                \
-  do { KTimer kt_(c, #name); RSI_LAUNCH(name, grid, block, smem, c->stream, __VA_ARGS__); } while (0)
+#define KL(name, grid, block, smem, ...)                                                          \
+  do {                                                                                            \
+    KTimer kt_(c, #name);                                                                         \
+    RSI_LAUNCH(name, grid, block, smem, c->stream, __VA_ARGS__);                                  \
+    cudaError_t le_ = cudaGetLastError();                                                         \
+    if (le_ != cudaSuccess && c->launch_err.empty()) c->launch_err = std::string(#name) + ": " + cudaGetErrorString(le_); \
+  } while (0)
 
 template <class T> T* field_ptr(DevState* base, T DevState::*m) { return &(base->*m); }
 
@@ -667,6 +674,20 @@ int rsigpu_get_profile(const rsigpu_ctx* c, char* names, int32_t name_stride, fl
     ++k;
   }
   return k;
+}
+
+// test hook: selected device scalars of the last load_finish / detectcnv (host copy), as doubles
+int rsigpu_debug_state(const rsigpu_ctx* c, double* out, int32_t cap) {
+  if (!c || !out) return RSIGPU_E_ARG;
+  const DevState* h = c->h_st;
+  const double v[] = {(double)h->err, (double)h->rd_min, (double)h->rd_max, (double)h->pos_sum, (double)h->pos_cnt, h->rdmean, h->cap_median, h->cap_thr,
+                      (double)h->capv, (double)h->hist_base, (double)h->chist_R, h->rdmedian, h->rdsd, h->rdmad, (double)h->max_binsum, (double)h->gstar,
+                      h->gc_tab[80], h->gc_tab[90], h->gc_tab[100], (double)h->gc_cnt[90], h->tmedian, h->tsigma, h->tlamda, (double)h->Lmax,
+                      (double)h->lbreak_del, (double)h->lbreak_dup, (double)h->n_runs, (double)h->n_nonzero, (double)h->st_lo, (double)h->st_hi,
+                      (double)h->lvl_sum[-h->st_lo < 0 ? 0 : -h->st_lo], (double)h->filt_on};
+  const int n = (int)(sizeof v / sizeof v[0]);
+  for (int k = 0; k < n && k < cap; ++k) out[k] = v[k];
+  return n;
 }
 
 // test hook: 0 = sequential float chain for filterstatus' level-0 sum, 1 = block-scan form (default)
