@@ -43,7 +43,8 @@ struct CandScratch {
   int* sub;        int sub_cap;   // sub-sampled ref + cnv (>= maxchkbp*10 + 2)
   long long* pref;                // ref_cap + 1 prefix sums
   float* rm;                      // ref_cap running means
-  unsigned* hist;  int hist_cap;  // histogram buckets
+  unsigned* hist;  int hist_cap;  // histogram buckets (global memory fallback)
+  unsigned* shist; int shist_cap; // histogram buckets in shared memory (preferred when they fit)
   int* err;                       // sticky error bits (CAND_ERR_*)
 };
 
@@ -104,25 +105,30 @@ RSI_DEVN void cta_hist_stat(const Cta& c, const CandScratch& S, const T* x, int 
   q[0] = mn; q[1] = sm / (double)n; q[2] = mx;
   if ((mx - mn) < dy) return;
   const size_t np = (size_t)((mx - mn) / dy + 2);
-  if (np + 1 > (size_t)S.hist_cap) { if (c.tid == 0) *S.err |= CAND_ERR_HIST; return; }
-  for (size_t b = c.tid; b <= np; b += c.nthr) S.hist[b] = 0u;
+  unsigned* H = (S.shist && np + 1 <= (size_t)S.shist_cap) ? S.shist : S.hist;
+  if (H == S.hist && np + 1 > (size_t)S.hist_cap) { if (c.tid == 0) *S.err |= CAND_ERR_HIST; return; }
+  for (size_t b = c.tid; b <= np; b += c.nthr) H[b] = 0u;
   c.sync();
-  for (int i = c.tid; i < n; i += c.nthr) {
-    double idx = ((double)x[i] - mn) / dy + 0.5;
-    cta_atomic_inc(&S.hist[(size_t)idx]);
+  // neighbouring samples mostly share a bucket: one atomic per distinct bucket of a warp
+  for (int base = 0; base < n; base += c.nthr) {
+    const int i = base + c.tid;
+    const bool valid = i < n;
+    size_t b = 0;
+    if (valid) { double idx = ((double)x[i] - mn) / dy + 0.5; b = (size_t)idx; }
+    cta_hist_add(H, b, valid);
   }
   c.sync();
   const unsigned long long r4 = (unsigned long long)n / 4, r2 = (unsigned long long)n / 2, r34 = (unsigned long long)n * 3 / 4;
   const size_t chunk = (np + c.nthr - 1) / c.nthr;
-  const size_t b0 = (size_t)c.tid * chunk, b1 = (b0 + chunk < np) ? b0 + chunk : np;
+  const size_t b0 = (size_t)c.tid * chunk < np ? (size_t)c.tid * chunk : np, b1 = (b0 + chunk < np) ? b0 + chunk : np;
   long long local = 0;
-  for (size_t b = b0; b < b1; ++b) local += S.hist[b];
+  for (size_t b = b0; b < b1; ++b) local += H[b];
   long long tot;
   long long run = c.scan_excl(local, &tot);
   if (c.tid == 0) { c.bc[8] = q[0]; c.bc[9] = q[1]; c.bc[10] = q[2]; }
   c.sync();
   for (size_t b = b0; b < b1; ++b) {
-    unsigned long long cnt = S.hist[b], before = (unsigned long long)run, after = before + cnt;
+    unsigned long long cnt = H[b], before = (unsigned long long)run, after = before + cnt;
     if (before < r4 && after >= r4) c.bc[8] = mn + b * dy;
     if (before < r2 && after >= r2) c.bc[9] = mn + b * dy;
     if (before < r34 && after >= r34) c.bc[10] = mn + b * dy;
@@ -150,16 +156,25 @@ RSI_DEV bool nb_accept(int v, int flag, double up, double lo) {
 }
 
 // Scan positions lo..hi (dir=+1) or hi..lo (dir=-1); store the first `want` accepted values to
-// dst[0..), in scan order.  Returns how many were stored (block-uniform).
+// dst[0..), in scan order.  Returns how many were stored (block-uniform).  Every thread takes a
+// CONTIGUOUS slice of a super-chunk sized to what is still wanted, so one block scan serves
+// thousands of positions.
 RSI_DEVN int cta_collect(const Cta& c, const int* RD, int lo, int hi, int dir, int flag, double up, double lw, int want, int* dst) {
   int got = 0;
   const int len = hi - lo + 1;
-  for (int base = 0; base < len && got < want; base += c.nthr) {
-    int j = base + c.tid, v = 0, ok = 0;
-    if (j < len) { v = RD[dir > 0 ? lo + j : hi - j]; ok = nb_accept(v, flag, up, lw) ? 1 : 0; }
-    int tot, ex = c.scan_excl(ok, &tot);
-    if (ok && got + ex < want) dst[got + ex] = v;
+  int pos = 0;
+  while (pos < len && got < want) {
+    int sc = want - got + c.nthr;               // nearly every position is accepted
+    if (sc > len - pos) sc = len - pos;
+    const int per = (sc + c.nthr - 1) / c.nthr;
+    const int j0 = pos + (c.tid * per < sc ? c.tid * per : sc), j1 = pos + ((c.tid + 1) * per < sc ? (c.tid + 1) * per : sc);
+    int cnt = 0;
+    for (int j = j0; j < j1; ++j) cnt += nb_accept(RD[dir > 0 ? lo + j : hi - j], flag, up, lw) ? 1 : 0;
+    int tot, ex = c.scan_excl(cnt, &tot);
+    int w = got + ex;
+    for (int j = j0; j < j1 && w < want; ++j) { const int v = RD[dir > 0 ? lo + j : hi - j]; if (nb_accept(v, flag, up, lw)) dst[w++] = v; }
     got = got + tot < want ? got + tot : want;
+    pos += sc;
   }
   c.sync();
   return got;
@@ -167,9 +182,12 @@ RSI_DEVN int cta_collect(const Cta& c, const int* RD, int lo, int hi, int dir, i
 // First accepted position in scan order, or -1 (block-uniform).
 RSI_DEVN int cta_find_first(const Cta& c, const int* RD, int lo, int hi, int dir, int flag, double up, double lw) {
   const int len = hi - lo + 1;
-  for (int base = 0; base < len; base += c.nthr) {
-    int j = base + c.tid, best = 0x7fffffff;
-    if (j < len && nb_accept(RD[dir > 0 ? lo + j : hi - j], flag, up, lw)) best = j;
+  for (int base = 0; base < len; base += c.nthr * 8) {
+    int best = 0x7fffffff;
+    for (int k = 0; k < 8; ++k) {
+      const int j = base + k * c.nthr + c.tid;
+      if (j < len && j < best && nb_accept(RD[dir > 0 ? lo + j : hi - j], flag, up, lw)) best = j;
+    }
     best = c.reduce(best, MinOp());
     if (best != 0x7fffffff) return dir > 0 ? lo + best : hi - best;
   }
@@ -185,14 +203,14 @@ RSI_DEVN void cnv_test_stats(const Cta& c, const CandCfg& P, const CandScratch& 
     return;
   }
   // exact integer prefix sums of the neighbours (the reference slides a double sum of ints: exact)
-  long long carry = 0;
-  if (c.tid == 0) S.pref[0] = 0;
-  for (int base = 0; base < nref; base += c.nthr) {
-    int j = base + c.tid;
-    long long v = j < nref ? (long long)ref[j] : 0, tot;
-    long long ex = c.scan_excl(v, &tot);
-    if (j < nref) S.pref[j + 1] = carry + ex + v;
-    carry += tot;
+  {
+    const int per = (nref + c.nthr - 1) / c.nthr;
+    const int j0 = c.tid * per < nref ? c.tid * per : nref, j1 = (c.tid + 1) * per < nref ? (c.tid + 1) * per : nref;
+    long long loc = 0, tot;
+    for (int j = j0; j < j1; ++j) loc += (long long)ref[j];
+    long long run = c.scan_excl(loc, &tot);
+    if (c.tid == 0) S.pref[0] = 0;
+    for (int j = j0; j < j1; ++j) { run += (long long)ref[j]; S.pref[j + 1] = run; }
   }
   c.sync();
   double s1 = 0.0, s2 = 0.0;
@@ -366,18 +384,22 @@ RSI_DEVN void edge_refine(const Cta& c, const int* RD, int n, Cnv* cv) {
   ValIdx headbest; headbest.v = 0.0; headbest.i = -1;   // running extremum over the head window
   ValIdx tailbest; tailbest.v = 0.0; tailbest.i = -1;
   const double hs = type == RSIGPU_TYPE_DEL ? 1.0 : -1.0;  // DEL: head max / tail min; DUP: head min / tail max
-  long long carry = dd0;
-  for (int base = 0; base < ndd; base += c.nthr) {
-    int j = base + c.tid;  // dd index
-    long long inc = 0;
-    if (j < ndd && j >= 1) { int p = ns + j; inc = -(long long)RD[p - 1 - len] + 2ll * RD[p - 1] - (long long)RD[p - 1 + len]; }
-    long long tot, ex = c.scan_excl(inc, &tot);
-    double ddj = (double)(carry + ex + inc);
-    if (j < ndd && (type == RSIGPU_TYPE_DEL || type == RSIGPU_TYPE_DUP)) {
-      if (j < 2 * disp && hs * ddj > headbest.v) { headbest.v = hs * ddj; headbest.i = j; }
-      if (j >= tail0 && -hs * ddj > tailbest.v) { tailbest.v = -hs * ddj; tailbest.i = j; }
+  {
+    // dd(j) = dd(0) + sum_{1<=k<=j} inc(k); every thread owns a contiguous slice of j
+    const int per = (ndd + c.nthr - 1) / c.nthr;
+    const int j0 = c.tid * per < ndd ? c.tid * per : ndd, j1 = (c.tid + 1) * per < ndd ? (c.tid + 1) * per : ndd;
+    long long loc = 0, tot;
+    for (int j = j0; j < j1; ++j) if (j >= 1) { const int p = ns + j; loc += -(long long)RD[p - 1 - len] + 2ll * RD[p - 1] - (long long)RD[p - 1 + len]; }
+    long long run = dd0 + c.scan_excl(loc, &tot);
+    const bool typed = type == RSIGPU_TYPE_DEL || type == RSIGPU_TYPE_DUP;
+    for (int j = j0; j < j1; ++j) {
+      if (j >= 1) { const int p = ns + j; run += -(long long)RD[p - 1 - len] + 2ll * RD[p - 1] - (long long)RD[p - 1 + len]; }
+      const double ddj = (double)run;
+      if (typed) {
+        if (j < 2 * disp && hs * ddj > headbest.v) { headbest.v = hs * ddj; headbest.i = j; }
+        if (j >= tail0 && -hs * ddj > tailbest.v) { tailbest.v = -hs * ddj; tailbest.i = j; }
+      }
     }
-    carry += tot;
   }
   // per-thread candidates are each thread's first strict maximum in ascending j; merge with first-index ties
   if (headbest.i < 0) { headbest.v = 0.0; headbest.i = 0x7fffffffffffll; }

@@ -100,6 +100,13 @@ struct Cta {
 };
 
 RSI_DEV void cta_atomic_inc(unsigned* p) { atomicAdd(p, 1u); }
+// histogram increment called by ALL threads of a warp together (valid = this lane has a sample):
+// lanes that hit the same bucket are merged into one atomic
+RSI_DEV void cta_hist_add(unsigned* h, size_t b, bool valid) {
+  const unsigned long long key = valid ? (unsigned long long)b : ~0ull;
+  const unsigned m = __match_any_sync(0xffffffffu, key);
+  if (valid && (int)(threadIdx.x & 31) == __ffs((int)m) - 1) atomicAdd(&h[b], (unsigned)__popc(m));
+}
 RSI_DEV void cta_atomic_max(int* p, int v) { atomicMax(p, v); }
 RSI_DEV void cta_atomic_min(int* p, int v) { atomicMin(p, v); }
 
@@ -114,6 +121,7 @@ struct Cta {
   template <class T> T scan_excl(T v, T* total) const { *total = v; return T(0); }
 };
 inline void cta_atomic_inc(unsigned* p) { *p += 1u; }
+inline void cta_hist_add(unsigned* h, size_t b, bool valid) { if (valid) h[b] += 1u; }
 inline void cta_atomic_max(int* p, int v) { if (v > *p) *p = v; }
 inline void cta_atomic_min(int* p, int v) { if (v < *p) *p = v; }
 

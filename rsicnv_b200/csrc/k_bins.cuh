@@ -49,10 +49,17 @@ __global__ void __launch_bounds__(C_NT) k_bins(int* __restrict__ rdc, float* __r
     for (int q0 = 0; q0 < np; q0 += C_TP) {                    // (only the tail of a tiny contig can exceed C_TP)
       const int nq = imin(C_TP, np - q0);
       if (q0) c.sync();
-      for (int q = tid; q < nq; q += C_NT) {
-        int v = rdc[B + q0 + q];
-        if (cap_on && (double)v > thr) { v = capv; rdc[B + q0 + q] = v; }
-        vals[q] = v;
+      for (int qb = 0; qb < nq; qb += C_NT * 8) {   // 8 independent loads in flight per thread before any (aliasing) store
+        int v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const int q = qb + k * C_NT + tid; v[k] = q < nq ? rdc[B + q0 + q] : 0; }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int q = qb + k * C_NT + tid;
+          if (q >= nq) continue;
+          if (cap_on && (double)v[k] > thr) { v[k] = capv; rdc[B + q0 + q] = capv; }
+          vals[q] = v[k];
+        }
       }
       c.sync();
       if (tid < C_CT) {

@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(S_NT) k_rsi_scan(const float* __restrict__ t, 
           while (i2 >= 0 && (double)medint[i2] < lim) --i2;
         }
         u32* mm = sign < 0 ? mdel : mdup;
-        for (int j = i1; j <= i2; ++j) atomicMin(&mm[j - base], (u32)L);
+        for (int j = i1; j <= i2; ++j) if (mm[j - base] > (u32)L) atomicMin(&mm[j - base], (u32)L);   // most bins already carry a smaller L
       }
     }
   }
@@ -269,7 +269,8 @@ __global__ void k_rsi_status(const u32* __restrict__ minl_del, const u32* __rest
 
 // ---------------------------------------------------------------------------------------------
 // filterstatus_tp.  Ordered list of the marked bins (index order) for the per-level sums.
-__global__ void k_nz_scatter(const int* __restrict__ status, const int* __restrict__ tile_nz, int* __restrict__ nz_idx, DevState* st) {
+__global__ void k_nz_scatter(const float* __restrict__ t, const int* __restrict__ status, const int* __restrict__ tile_nz, int* __restrict__ nz_lvl,
+                             float* __restrict__ nz_val, DevState* st) {
   RSI_CTA_SETUP(c);
   const int nb = st->nb;
   const int ntiles = (nb + 1023) / 1024;
@@ -284,7 +285,7 @@ __global__ void k_nz_scatter(const int* __restrict__ status, const int* __restri
       const int f = (j < nb && j < tile * 1024 + 1024 && status[j] != 0) ? 1 : 0;
       int tot;
       const int ex = c.scan_excl(f, &tot);
-      if (f) nz_idx[off + ex] = j;
+      if (f) { nz_lvl[off + ex] = status[j]; nz_val[off + ex] = t[j]; }
       off += tot;
     }
   }
@@ -404,17 +405,23 @@ __global__ void __launch_bounds__(CH_NT) k_level0_chain_scan(const float* __rest
   if (tid == 0) { const int l0 = -st->st_lo; st->lvl_sum[l0] = S; st->lvl_cnt[l0] = n; }
 }
 
-// sums of the non-zero levels: one thread per level walks the ordered list of marked bins
-__global__ void k_level_sums(const float* __restrict__ t, const int* __restrict__ status, const int* __restrict__ nz_idx, DevState* st) {
+// sums of the non-zero levels: one thread per level; the ordered (level, value) list of the marked
+// bins is staged through shared memory in chunks that every thread scans (broadcast reads)
+__global__ void __launch_bounds__(128) k_level_sums(const int* __restrict__ nz_lvl, const float* __restrict__ nz_val, DevState* st) {
+  __shared__ int s_l[1024];
+  __shared__ float s_v[1024];
   const int lo = st->st_lo, hi = st->st_hi, nz = st->n_nonzero;
   const int lvl = lo + (int)(blockIdx.x * blockDim.x + threadIdx.x);
-  if (lvl > hi || lvl == 0) return;
+  if ((int)(blockIdx.x * blockDim.x) + lo > hi) return;   // whole block beyond the last level
   float s = 0.f; u32 n = 0;
-  for (int k = 0; k < nz; ++k) {
-    const int j = nz_idx[k];
-    if (status[j] == lvl) { s = __fadd_rn(s, t[j]); ++n; }
+  for (int k0 = 0; k0 < nz; k0 += 1024) {
+    const int cnt = imin(1024, nz - k0);
+    __syncthreads();
+    for (int k = (int)threadIdx.x; k < cnt; k += (int)blockDim.x) { s_l[k] = nz_lvl[k0 + k]; s_v[k] = nz_val[k0 + k]; }
+    __syncthreads();
+    for (int k = 0; k < cnt; ++k) if (s_l[k] == lvl) { s = __fadd_rn(s, s_v[k]); ++n; }
   }
-  st->lvl_sum[lvl - lo] = s; st->lvl_cnt[lvl - lo] = n;
+  if (lvl <= hi && lvl != 0) { st->lvl_sum[lvl - lo] = s; st->lvl_cnt[lvl - lo] = n; }
 }
 
 __global__ void k_filter_params(DevState* st) {

@@ -119,8 +119,11 @@ struct CandArgs {
   int maxchkbp, merge, tid; double chklen;
 };
 
+enum { CAND_SHIST = 16384 };
 __global__ void __launch_bounds__(1024) k_candidates(CandArgs A, DevState* st) {
   RSI_CTA_SETUP(c);
+  RSI_DYN_SMEM(smem);
+  A.S.shist = reinterpret_cast<unsigned*>(smem); A.S.shist_cap = CAND_SHIST;
   CandCfg P;
   P.m = st->m; P.maxchkbp = A.maxchkbp; P.merge = A.merge; P.tid = A.tid; P.chklen = A.chklen; P.minmlen = 3.01; P.buffer = 0.05; P.p = 0.05;
   P.rdmedian = st->rdmedian; P.rdsd = st->rdsd; P.span = st->Lc;

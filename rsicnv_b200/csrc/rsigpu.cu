@@ -90,7 +90,7 @@ struct rsigpu_ctx {
   DevState* d_st = nullptr; DevState* h_st = nullptr;
   DevBuf<u32> d_hist_all, d_chist, d_thist, d_tothist, d_fq_hist;
   // bins
-  DevBuf<float> d_bin_med, d_bin_nbn, d_lut; DevBuf<int> d_bin_medint, d_status, d_status1, d_tile, d_nz_idx, d_runs; DevBuf<i64> d_bin_sum, d_pfx;
+  DevBuf<float> d_bin_med, d_bin_nbn, d_lut, d_nz_val; DevBuf<int> d_bin_medint, d_status, d_status1, d_tile, d_nz_idx, d_runs; DevBuf<i64> d_bin_sum, d_pfx;
   DevBuf<u32> d_minl_del, d_minl_dup;
   float* h_lut = nullptr; size_t h_lut_cap = 0;
   // lists
@@ -180,6 +180,7 @@ int set_smem_attrs() {
   cudaFuncSetAttribute(k_gc_table, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(GC_STRATA * A_NT * 8 + LD_FAB + (LD_PRE + 8) * 2));
   cudaFuncSetAttribute(k_gc_adjust, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(B_K * B_NT * 2 + GC_STRATA * 8 + LD_FAB + (LD_PRE + 8) * 2));
   cudaFuncSetAttribute(k_bins, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(C_K * C_NT * 2 + C_TP * 4));
+  cudaFuncSetAttribute(k_candidates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CAND_SHIST * 4));
   cudaFuncSetAttribute(k_rsi_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((S_N + 1) * 8 + (LMAX_CAP + 1) * 8 + 2 * S_N * 4 + 2 * (S_N + 1) * 2));
   return 0;
 }
@@ -204,10 +205,10 @@ int run_rsi(rsigpu_ctx* c, int which, const float* t) {
     KL(k_rsi_status, gb, 256, 0, c->d_minl_del.p, c->d_minl_dup.p, status, c->d_tile.p, st);
     if (pass == 1) break;
     // filterstatus (rsi.cpp:948-1057) on the first-pass status, in place via a second buffer
-    KL(k_nz_scatter, gb, 256, 0, status, c->d_tile.p, c->d_nz_idx.p, st);
+    KL(k_nz_scatter, gb, 256, 0, t, status, c->d_tile.p, c->d_nz_idx.p, c->d_nz_val.p, st);
     if (c->level0_mode) KL(k_level0_chain_scan, 1, CH_NT, 0, t, status, st);
     else KL(k_level0_chain_seq, 1, 32, 0, t, status, st);
-    KL(k_level_sums, (2 * LMAX_CAP + 3 + 127) / 128, 128, 0, t, status, c->d_nz_idx.p, st);
+    KL(k_level_sums, (2 * LMAX_CAP + 3 + 127) / 128, 128, 0, c->d_nz_idx.p, c->d_nz_val.p, st);
     KL(k_filter_params, 1, 32, 0, st);
     CK(cudaMemcpyAsync(c->d_status.p, status, (size_t)nb * 4, cudaMemcpyDeviceToDevice, c->stream));
     KL(k_filter_trim, gb, 256, 0, t, c->d_status.p, status, st);
@@ -287,7 +288,7 @@ void rsigpu_destroy(rsigpu_ctx* c) {
   c->d_fasta.release(); c->d_raw.release(); c->d_rdc.release(); c->d_nseq.release();
   c->d_hist_all.release(); c->d_chist.release(); c->d_thist.release(); c->d_tothist.release(); c->d_fq_hist.release();
   c->d_bin_med.release(); c->d_bin_nbn.release(); c->d_lut.release(); c->d_bin_medint.release(); c->d_status.release(); c->d_status1.release();
-  c->d_tile.release(); c->d_nz_idx.release(); c->d_runs.release(); c->d_bin_sum.release(); c->d_pfx.release(); c->d_minl_del.release(); c->d_minl_dup.release();
+  c->d_tile.release(); c->d_nz_idx.release(); c->d_nz_val.release(); c->d_runs.release(); c->d_bin_sum.release(); c->d_pfx.release(); c->d_minl_del.release(); c->d_minl_dup.release();
   c->d_lists.release(); c->d_misc.release(); c->d_ref.release(); c->d_sub.release(); c->d_pref.release(); c->d_rm.release(); c->d_chist_c.release();
   c->d_nrun_beg.release(); c->d_nrun_end.release(); c->r_calend.release();
   c->r_pos.release(); c->r_mpos.release(); c->r_isize.release(); c->r_mtid.release(); c->r_flag.release(); c->r_mapq.release(); c->r_qual.release();
@@ -422,7 +423,7 @@ int rsigpu_load_finish(rsigpu_ctx* c) {
   // buffers
   CK(c->d_rdc.ensure((size_t)c->Lc + 64));
   CK(c->d_bin_med.ensure(nb + 8)); CK(c->d_bin_nbn.ensure(nb + 8)); CK(c->d_bin_medint.ensure(nb + 8)); CK(c->d_bin_sum.ensure(nb + 8));
-  CK(c->d_status.ensure(nb + 8)); CK(c->d_status1.ensure(nb + 8)); CK(c->d_nz_idx.ensure(nb + 8)); CK(c->d_tile.ensure(nb / 1024 + 8));
+  CK(c->d_status.ensure(nb + 8)); CK(c->d_status1.ensure(nb + 8)); CK(c->d_nz_idx.ensure(nb + 8)); CK(c->d_nz_val.ensure(nb + 8)); CK(c->d_tile.ensure(nb / 1024 + 8));
   CK(c->d_minl_del.ensure(nb + 8)); CK(c->d_minl_dup.ensure(nb + 8)); CK(c->d_pfx.ensure((size_t)nb + LIST_CAP + 8));
   CK(c->d_ref.ensure((size_t)c->Lc + 64)); CK(c->d_pref.ensure((size_t)c->Lc + 64)); CK(c->d_rm.ensure((size_t)c->Lc + 64));
   // device state
@@ -516,7 +517,7 @@ int rsigpu_detectcnv(rsigpu_ctx* c) {
   A.S.ref = c->d_ref.p; A.S.ref_cap = (int)std::min<size_t>(c->d_ref.cap, 0x7fffffff); A.S.sub = c->d_sub.p; A.S.sub_cap = (int)c->d_sub.cap;
   A.S.pref = c->d_pref.p; A.S.rm = c->d_rm.p; A.S.hist = c->d_chist_c.p; A.S.hist_cap = (int)c->d_chist_c.cap; A.S.err = c->d_misc.p + 4;
   A.maxchkbp = c->P.maxchkbp; A.merge = c->P.merge; A.tid = c->tid; A.chklen = c->P.chklen;
-  KL(k_candidates, 1, 1024, 0, A, c->d_st);
+  KL(k_candidates, 1, 1024, (size_t)CAND_SHIST * 4, A, c->d_st);
   CK(cudaEventRecord(c->ev[4], c->stream));
   CK(cudaMemcpyAsync(h, c->d_st, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
   int nd[4];
