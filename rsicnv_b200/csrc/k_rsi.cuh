@@ -16,8 +16,9 @@
 
 namespace rsigpu {
 
-enum { S_NT = 256, S_T = 1024, S_H = LMAX_CAP / 2 + 2, S_N = S_T + 2 * S_H };
+enum { S_NT = 256, S_T = 1024, S_H = LMAX_CAP / 2 + 2 };
 enum { MINL_INF = 0x7f7f7f7f };
+
 
 // ---- scalars before the first rsistatus pass (which: 0 = NBN on the transformed bins, 1 = MED on the medians)
 __global__ void k_rsi_params1(const float* __restrict__ t, DevState* st, int which, double threshold) {
@@ -91,45 +92,100 @@ __device__ bool window_median_ok(const int* __restrict__ medint, int i1, int L, 
   return 0.5 * ((double)a + (double)b) >= lim;
 }
 
-// One block = S_T window centres; loops over every window length.  Dynamic shared memory:
-//   P[S_N+1] i64 fixed-point prefix | sq[LMAX_CAP+1] double | cle[S_N+1], cge[S_N+1] u16 | mdel[S_N], mdup[S_N] u32
+// One block OWNS S_T bins and evaluates every window (centre in the tile or within Lmax/2 of it, every
+// length) that can mark them.  The reference's end trimming (rsi.cpp:1212-1215 / 1241-1244) moves a
+// window [s, e] to [nextB(nextA(s)), prevB(prevA(e))] (A: bin value on the far side of tmedian, B: bin
+// median beyond the limit), so bin j is written by that window iff
+//        s <= SA(j) = prevA(prevB(j))   and   e >= EA(j) = nextA(nextB(j)),
+// i.e. iff SOME hit centre lies in [EA(j) - (L-1) + L/2, SA(j) + L/2].  Hits of one length are kept as a
+// bit per centre (one __ballot_sync word per 32 centres), each thread tests the centre range of the
+// bins it owns and remembers the first (smallest) L in registers: no atomics, no per-hit loops, and the
+// result does not depend on how hits cluster.  Dynamic shared memory (NB = S_T + 2*LMAX_CAP staged bins):
+//   P[NB+1] i64 | sq[LMAX_CAP+1] f64 | SA/EA x DEL/DUP [4][S_T] i32 | cle,cge [NB+1] u16 | hit words [2][2][S_NC/32+1] u32
+enum { S_NB = S_T + 2 * LMAX_CAP, S_NC = S_T + 2 * S_H };
+#define RSI_SCAN_SMEM ((size_t)(S_NB + 1) * 8 + (size_t)(LMAX_CAP + 1) * 8 + (size_t)4 * S_T * 4 + (size_t)2 * (S_NB + 2) * 2 + (size_t)4 * (S_NC / 32 + 2) * 4)
+
+// prev / next index with a condition, over the staged bins (block-wide max / min scans, thread-contiguous)
+__device__ void scan_prev_next(const Cta& c, const u8* cond, int N, int* prevv, int* nextv) {
+  const int per = (N + c.nthr - 1) / c.nthr;
+  const int k0 = imin(c.tid * per, N), k1 = imin(k0 + per, N);
+  int last = -1;
+  for (int k = k0; k < k1; ++k) if (cond[k]) last = k;
+  // exclusive max-scan of `last` across threads
+  int v = last;
+  const int lane = c.tid & 31, warp = c.tid >> 5, nw = (c.nthr + 31) >> 5;
+  for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v = imax(v, u); }
+  int* slots = reinterpret_cast<int*>(c.red);
+  c.sync(); if (lane == 31) slots[warp] = v; c.sync();
+  int pre = -1; for (int w = 0; w < warp; ++w) pre = imax(pre, slots[w]);
+  int up = __shfl_up_sync(0xffffffffu, v, 1);
+  int run = imax(pre, lane ? up : -1);
+  for (int k = k0; k < k1; ++k) { if (cond[k]) run = k; prevv[k] = run; }
+  c.sync();
+  // reverse: first index >= k with cond
+  int first = 0x7fffffff;
+  for (int k = k1 - 1; k >= k0; --k) if (cond[k]) first = k;
+  v = first;
+  for (int o = 1; o < 32; o <<= 1) { int u = __shfl_down_sync(0xffffffffu, v, o); if (lane + o < 32) v = imin(v, u); }
+  if (lane == 0) slots[warp] = v; c.sync();
+  int post = 0x7fffffff; for (int w = warp + 1; w < nw; ++w) post = imin(post, slots[w]);
+  int dn = __shfl_down_sync(0xffffffffu, v, 1);
+  run = imin(post, lane < 31 ? dn : 0x7fffffff);
+  for (int k = k1 - 1; k >= k0; --k) { if (cond[k]) run = k; nextv[k] = run; }
+  c.sync();
+}
+
 __global__ void __launch_bounds__(S_NT) k_rsi_scan(const float* __restrict__ t, const int* __restrict__ medint, u32* __restrict__ minl_del,
-                                                    u32* __restrict__ minl_dup, DevState* st) {
+                                                    u32* __restrict__ minl_dup, int* __restrict__ scratch, DevState* st) {
   RSI_DYN_SMEM(smem);
   RSI_CTA_SETUP(c);
   i64* P = reinterpret_cast<i64*>(smem);
-  double* sq = reinterpret_cast<double*>(P + (S_N + 1));
-  u32* mdel = reinterpret_cast<u32*>(sq + (LMAX_CAP + 1));
-  u32* mdup = mdel + S_N;
-  u16* cle = reinterpret_cast<u16*>(mdup + S_N);
-  u16* cge = cle + (S_N + 1);
+  double* sq = reinterpret_cast<double*>(P + (S_NB + 1));
+  int* SAEA = reinterpret_cast<int*>(sq + (LMAX_CAP + 1));        // [0]=SA_del [1]=EA_del [2]=SA_dup [3]=EA_dup, S_T each
+  u16* cle = reinterpret_cast<u16*>(SAEA + 4 * S_T);
+  u16* cge = cle + (S_NB + 2);
+  u32* hw = reinterpret_cast<u32*>(cge + (S_NB + 2));              // [buf][sign][word]
+  const int NW = S_NC / 32 + 2;
   const int nb = st->nb, Lmax = st->Lmax;
   const double tmed = st->tmedian, tlam = st->tlamda, limd = st->lim_del, limu = st->lim_dup;
-  const int H = Lmax / 2 + 2;
   const int c0 = (int)blockIdx.x * S_T;
-  const int base = c0 - H;                       // smem index k <-> bin base + k
-  const int N = S_T + 2 * H;
-  const int tid = c.tid;
-  // ---- stage: fixed-point values, limit flags, block-wide exclusive prefix
+  const int HB = Lmax + 1;                        // staged bins: [c0 - HB, c0 + S_T + HB)
+  const int base = c0 - HB;                       // smem index k <-> bin base + k
+  const int N = S_T + 2 * HB;
+  const int HC = Lmax / 2 + 2;                    // centres:     [c0 - HC, c0 + S_T + HC)
+  const int cbase = c0 - HC;
+  const int NC = S_T + 2 * HC;
+  const int tid = c.tid, lane = tid & 31, warp = tid >> 5;
+  // per-block global scratch for the prev/next arrays (8 x N ints) and condition bytes
+  int* sc = scratch + (size_t)blockIdx.x * (8 * (size_t)S_NB + 2 * (size_t)S_NB);
+  int* pv[4]; int* nx[4];
+  for (int k = 0; k < 4; ++k) { pv[k] = sc + (size_t)(2 * k) * S_NB; nx[k] = sc + (size_t)(2 * k + 1) * S_NB; }
+  u8* cond = reinterpret_cast<u8*>(sc + 8 * (size_t)S_NB);   // 4 x S_NB bytes: A_del, B_del, A_dup, B_dup
+  // ---- stage: fixed-point values, limit flags, block-wide exclusive prefix, trimming conditions
   const int chunk = (N + S_NT - 1) / S_NT;
   const int k0 = imin(tid * chunk, N), k1 = imin(k0 + chunk, N);
   i64 ls = 0; int ld = 0, lu = 0, bad = 0; float tmax = 0.f; int lowexp = 1000;
   for (int k = k0; k < k1; ++k) {
     const int b = base + k;
-    if (b < 0 || b >= nb) continue;
-    const float x = t[b];
-    const i64 fx = (i64)((double)x * 68719476736.0);    // * 2^FX_SHIFT
-    if ((double)fx * (1.0 / 68719476736.0) != (double)x || !(x >= 0.f) || x >= 16384.f) bad = 1;
-    if (x > 0.f) {
-      const u32 u = __float_as_uint(x);
-      const int e = (int)((u >> 23) & 0xff) - 127 - 23;
-      const u32 man = (u & 0x7fffff) | 0x800000;
-      lowexp = imin(lowexp, e + (__ffs((int)man) - 1));
-      tmax = x > tmax ? x : tmax;
+    u8 ca = 0, cb = 0, cc = 0, cd = 0;
+    if (b >= 0 && b < nb) {
+      const float x = t[b];
+      const i64 fx = (i64)((double)x * 68719476736.0);    // * 2^FX_SHIFT
+      if ((double)fx * (1.0 / 68719476736.0) != (double)x || !(x >= 0.f) || x >= 16384.f) bad = 1;
+      if (x > 0.f) {
+        const u32 u = __float_as_uint(x);
+        const int e = (int)((u >> 23) & 0xff) - 127 - 23;
+        const u32 man = (u & 0x7fffff) | 0x800000;
+        lowexp = imin(lowexp, e + (__ffs((int)man) - 1));
+        tmax = x > tmax ? x : tmax;
+      }
+      ls += fx;
+      const int v = medint[b];
+      ld += ((double)v <= limd) ? 1 : 0; lu += ((double)v >= limu) ? 1 : 0;
+      ca = !((double)x > tmed); cb = !((double)v > limd);      // DEL loops run while t > tmed / medint > lim
+      cc = !((double)x < tmed); cd = !((double)v < limu);      // DUP loops run while t < tmed / medint < lim
     }
-    ls += fx;
-    const int v = medint[b];
-    ld += ((double)v <= limd) ? 1 : 0; lu += ((double)v >= limu) ? 1 : 0;
+    cond[k] = ca; cond[S_NB + k] = cb; cond[2 * S_NB + k] = cc; cond[3 * S_NB + k] = cd;
   }
   i64 tots; int totd, totu;
   i64 rs = c.scan_excl(ls, &tots);
@@ -145,7 +201,6 @@ __global__ void __launch_bounds__(S_NT) k_rsi_scan(const float* __restrict__ t, 
     }
   }
   if (tid == 0) { P[N] = tots; cle[N] = (u16)totd; cge[N] = (u16)totu; }
-  for (int k = tid; k < N; k += S_NT) { mdel[k] = MINL_INF; mdup[k] = MINL_INF; }
   for (int L = tid; L <= Lmax; L += S_NT) sq[L] = sqrt((double)L);
   // exactness of the reference's own double window sums: all partial sums need <= 53 significant bits
   tmax = c.reduce(tmax, MaxOp()); lowexp = c.reduce(lowexp, MinOp()); bad = c.reduce(bad, MaxOp());
@@ -154,52 +209,80 @@ __global__ void __launch_bounds__(S_NT) k_rsi_scan(const float* __restrict__ t, 
     if (bad || (lowexp < 1000 && (double)tmax * (double)span >= ldexp(1.0, 53 + lowexp))) atomicOr(&st->err, (int)ERR_FIXEDPOINT);
   }
   c.sync();
-  // ---- every window length, every centre of the tile
-  for (int L = 1; L <= Lmax; ++L) {
-    const int h = L / 2;
-    const double sL = sq[L], dL = (double)L;
-    const int ilo = h + 1, ihi = nb - h - 1;        // centres i with ilo <= i < ihi
-#pragma unroll
-    for (int r = 0; r < S_T / S_NT; ++r) {
-      const int i = c0 + tid + r * S_NT;
-      if (i < ilo || i >= ihi) continue;
-      const int k1w = i - h - base;                 // smem index of the window start
-      const i64 s = P[k1w + L] - P[k1w];
-      const float mean = (float)__ddiv_rn((double)s * (1.0 / 68719476736.0), dL);
-      const double score = __dmul_rn((double)mean - tmed, sL);
-      const bool hd = !(score > -tlam), hu = !(score < tlam);
-      if (!(hd || hu)) continue;
-      for (int pass = 0; pass < 2; ++pass) {
-        const int sign = pass == 0 ? -1 : 1;
-        if (sign < 0 ? !hd : !hu) continue;
-        const double lim = sign < 0 ? limd : limu;
-        const u16* cp = sign < 0 ? cle : cge;
-        const int cin = (int)cp[k1w + L] - (int)cp[k1w];
-        int i1 = i - h, i2 = i1 + L - 1;
-        if (!window_median_ok(medint, i1, L, cin, lim, sign)) continue;
-        // shrink both ends (rsi.cpp:1212-1215 / 1241-1244); the loops are unguarded in the reference
-        if (sign < 0) {
-          while (i1 < nb && (double)t[i1] > tmed) ++i1;
-          while (i1 < nb && (double)medint[i1] > lim) ++i1;
-          while (i2 >= 0 && (double)t[i2] > tmed) --i2;
-          while (i2 >= 0 && (double)medint[i2] > lim) --i2;
-        } else {
-          while (i1 < nb && (double)t[i1] < tmed) ++i1;
-          while (i1 < nb && (double)medint[i1] < lim) ++i1;
-          while (i2 >= 0 && (double)t[i2] < tmed) --i2;
-          while (i2 >= 0 && (double)medint[i2] < lim) --i2;
-        }
-        u32* mm = sign < 0 ? mdel : mdup;
-        for (int j = i1; j <= i2; ++j) if (mm[j - base] > (u32)L) atomicMin(&mm[j - base], (u32)L);   // most bins already carry a smaller L
-      }
+  for (int k = 0; k < 4; ++k) scan_prev_next(c, cond + (size_t)k * S_NB, N, pv[k], nx[k]);
+  // SA(j) = prevA(prevB(j)), EA(j) = nextA(nextB(j)) for the owned bins (smem indices; -1 / INF = none in range)
+  for (int r = tid; r < S_T; r += S_NT) {
+    const int k = HB + r;
+    for (int sgn = 0; sgn < 2; ++sgn) {
+      const int pb = pv[2 * sgn + 1][k];
+      SAEA[(2 * sgn) * S_T + r] = pb < 0 ? -1 : pv[2 * sgn][pb];
+      const int nbk = nx[2 * sgn + 1][k];
+      SAEA[(2 * sgn + 1) * S_T + r] = nbk == 0x7fffffff ? 0x7fffffff : nx[2 * sgn][nbk];
     }
   }
   c.sync();
-  for (int k = tid; k < N; k += S_NT) {
-    const int b = base + k;
-    if (b < 0 || b >= nb) continue;
-    if (mdel[k] != MINL_INF) atomicMin(&minl_del[b], mdel[k]);
-    if (mdup[k] != MINL_INF) atomicMin(&minl_dup[b], mdup[k]);
+  u32 ml_del[S_T / S_NT], ml_dup[S_T / S_NT];
+#pragma unroll
+  for (int r = 0; r < S_T / S_NT; ++r) { ml_del[r] = MINL_INF; ml_dup[r] = MINL_INF; }
+  const int nwords = (NC + 31) / 32;
+  // ---- every window length
+  for (int L = 1; L <= Lmax; ++L) {
+    const int h = L / 2;
+    const double sL = sq[L], dL = (double)L;
+    const int ilo = h + 1, ihi = nb - h - 1;        // valid centres: ilo <= i < ihi
+    u32* hwd = hw + (size_t)((L & 1) * 2) * NW;     // double-buffered hit words: one barrier per length
+    u32* hwu = hwd + NW;
+    for (int w = warp; w < nwords; w += S_NT / 32) {
+      const int ci = w * 32 + lane;                 // centre index within [0, NC)
+      const int i = cbase + ci;
+      bool hd = false, hu = false;
+      if (ci < NC && i >= ilo && i < ihi) {
+        const int kw = i - h - base;                // smem index of the window start
+        const i64 s = P[kw + L] - P[kw];
+        const float mean = (float)__ddiv_rn((double)s * (1.0 / 68719476736.0), dL);
+        const double score = __dmul_rn((double)mean - tmed, sL);
+        hd = !(score > -tlam); hu = !(score < tlam);
+        if (hd) hd = window_median_ok(medint, i - h, L, (int)cle[kw + L] - (int)cle[kw], limd, -1);
+        if (hu) hu = window_median_ok(medint, i - h, L, (int)cge[kw + L] - (int)cge[kw], limu, +1);
+      }
+      const u32 bd = __ballot_sync(0xffffffffu, hd), bu = __ballot_sync(0xffffffffu, hu);
+      if (lane == 0) { hwd[w] = bd; hwu[w] = bu; }
+    }
+    c.sync();
+#pragma unroll
+    for (int r = 0; r < S_T / S_NT; ++r) {
+      const int jr = tid + r * S_NT;                // owned bin, smem index HB + jr
+      const int j = c0 + jr;
+      if (j >= nb) continue;
+#pragma unroll
+      for (int sgn = 0; sgn < 2; ++sgn) {
+        if ((sgn ? ml_dup[r] : ml_del[r]) != MINL_INF) continue;
+        const int sa = SAEA[(2 * sgn) * S_T + jr], ea = SAEA[(2 * sgn + 1) * S_T + jr];
+        if (sa < 0 || ea == 0x7fffffff) continue;
+        // windows [s, e] (smem indices) with s <= sa, e = s + L - 1 >= ea; centre smem index = s + h
+        int slo = ea - (L - 1), shi = sa;
+        if (slo > shi) continue;
+        // to centre indices within [0, NC): centre bin = base + s + h  =>  ci = s + h + base - cbase
+        int clo = slo + h + (base - cbase), chi = shi + h + (base - cbase);
+        if (clo < 0) clo = 0;
+        if (chi > NC - 1) chi = NC - 1;
+        if (clo > chi) continue;
+        const u32* hwp = sgn ? hwu : hwd;
+        bool any = false;
+        for (int w = clo >> 5; w <= (chi >> 5) && !any; ++w) {
+          u32 m = hwp[w];
+          if (w == (clo >> 5)) m &= 0xffffffffu << (clo & 31);
+          if (w == (chi >> 5)) m &= 0xffffffffu >> (31 - (chi & 31));
+          any = m != 0;
+        }
+        if (any) { if (sgn) ml_dup[r] = (u32)L; else ml_del[r] = (u32)L; }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < S_T / S_NT; ++r) {
+    const int j = c0 + tid + r * S_NT;
+    if (j < nb) { minl_del[j] = ml_del[r]; minl_dup[j] = ml_dup[r]; }
   }
 }
 

@@ -97,7 +97,7 @@ struct rsigpu_ctx {
   DevBuf<Cnv> d_lists;   // segs | tmp | ov(2) | segments | blocks | premerge | merged | detected | calls
   DevBuf<int> d_misc;    // n_dump[4] | cand_err | max_extent | sorted_bad | n_begN | n_endN
   DevBuf<int> d_ref, d_sub; DevBuf<i64> d_pref; DevBuf<float> d_rm; DevBuf<u32> d_chist_c;
-  DevBuf<int> d_nrun_beg, d_nrun_end;
+  DevBuf<int> d_nrun_beg, d_nrun_end, d_scan_scratch;
   std::vector<Cnv> h_detected, h_calls, h_dump[4];
   // reads
   DevVec<int> r_pos, r_mpos, r_isize, r_mtid; DevVec<u16> r_flag; DevVec<u8> r_mapq, r_qual; DevVec<u32> r_cigar_off, r_cigar; DevVec<u64> r_qual_off;
@@ -181,7 +181,7 @@ int set_smem_attrs() {
   cudaFuncSetAttribute(k_gc_adjust, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(B_K * B_NT * 2 + GC_STRATA * 8 + LD_FAB + (LD_PRE + 8) * 2));
   cudaFuncSetAttribute(k_bins, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(C_K * C_NT * 2 + C_TP * 4));
   cudaFuncSetAttribute(k_candidates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CAND_SHIST * 4));
-  cudaFuncSetAttribute(k_rsi_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((S_N + 1) * 8 + (LMAX_CAP + 1) * 8 + 2 * S_N * 4 + 2 * (S_N + 1) * 2));
+  cudaFuncSetAttribute(k_rsi_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SCAN_SMEM);
   return 0;
 }
 
@@ -190,15 +190,13 @@ int run_rsi(rsigpu_ctx* c, int which, const float* t) {
   DevState* st = c->d_st;
   const int nb = c->nb, slot0 = which == 0 ? 0 : 4;
   const int gb = grid_for(nb, 1024, c->n_sm * 8);
-  const size_t scan_smem = (S_N + 1) * 8 + (LMAX_CAP + 1) * 8 + 2 * S_N * 4 + 2 * (S_N + 1) * 2;
+  const size_t scan_smem = RSI_SCAN_SMEM;
   if (which == 0) quantile(c, t, nullptr, 0, QM_ID, nullptr, slot0);
   KL(k_rsi_params1, 1, 32, 0, t, st, which, c->P.threshold);
   quantile(c, t, nullptr, 0, QM_ABSDEV, field_ptr(st, &DevState::tmedian), slot0 + 1);
   KL(k_rsi_params2, 1, 32, 0, t, st, which, c->P.threshold, slot0 + 1);
   for (int pass = 0; pass < 2; ++pass) {
-    CK(cudaMemsetAsync(c->d_minl_del.p, 0x7f, (size_t)nb * 4, c->stream));
-    CK(cudaMemsetAsync(c->d_minl_dup.p, 0x7f, (size_t)nb * 4, c->stream));
-    KL(k_rsi_scan, (nb + S_T - 1) / S_T, S_NT, scan_smem, t, c->d_bin_medint.p, c->d_minl_del.p, c->d_minl_dup.p, st);
+    KL(k_rsi_scan, (nb + S_T - 1) / S_T, S_NT, scan_smem, t, c->d_bin_medint.p, c->d_minl_del.p, c->d_minl_dup.p, c->d_scan_scratch.p, st);
     KL(k_rsi_cnt_del, gb, 256, 0, c->d_minl_del.p, st);
     KL(k_rsi_cnt_dup, gb, 256, 0, c->d_minl_del.p, c->d_minl_dup.p, st);
     int* status = pass == 0 ? c->d_status1.p : c->d_status.p;
@@ -290,7 +288,7 @@ void rsigpu_destroy(rsigpu_ctx* c) {
   c->d_bin_med.release(); c->d_bin_nbn.release(); c->d_lut.release(); c->d_bin_medint.release(); c->d_status.release(); c->d_status1.release();
   c->d_tile.release(); c->d_nz_idx.release(); c->d_nz_val.release(); c->d_runs.release(); c->d_bin_sum.release(); c->d_pfx.release(); c->d_minl_del.release(); c->d_minl_dup.release();
   c->d_lists.release(); c->d_misc.release(); c->d_ref.release(); c->d_sub.release(); c->d_pref.release(); c->d_rm.release(); c->d_chist_c.release();
-  c->d_nrun_beg.release(); c->d_nrun_end.release(); c->r_calend.release();
+  c->d_nrun_beg.release(); c->d_nrun_end.release(); c->d_scan_scratch.release(); c->r_calend.release();
   c->r_pos.release(); c->r_mpos.release(); c->r_isize.release(); c->r_mtid.release(); c->r_flag.release(); c->r_mapq.release(); c->r_qual.release();
   c->r_cigar_off.release(); c->r_cigar.release(); c->r_qual_off.release();
   if (c->d_st) cudaFree(c->d_st);
@@ -424,7 +422,7 @@ int rsigpu_load_finish(rsigpu_ctx* c) {
   CK(c->d_rdc.ensure((size_t)c->Lc + 64));
   CK(c->d_bin_med.ensure(nb + 8)); CK(c->d_bin_nbn.ensure(nb + 8)); CK(c->d_bin_medint.ensure(nb + 8)); CK(c->d_bin_sum.ensure(nb + 8));
   CK(c->d_status.ensure(nb + 8)); CK(c->d_status1.ensure(nb + 8)); CK(c->d_nz_idx.ensure(nb + 8)); CK(c->d_nz_val.ensure(nb + 8)); CK(c->d_tile.ensure(nb / 1024 + 8));
-  CK(c->d_minl_del.ensure(nb + 8)); CK(c->d_minl_dup.ensure(nb + 8)); CK(c->d_pfx.ensure((size_t)nb + LIST_CAP + 8));
+  CK(c->d_scan_scratch.ensure((size_t)((nb + S_T - 1) / S_T) * 10 * S_NB + 64)); CK(c->d_minl_del.ensure(nb + 8)); CK(c->d_minl_dup.ensure(nb + 8)); CK(c->d_pfx.ensure((size_t)nb + LIST_CAP + 8));
   CK(c->d_ref.ensure((size_t)c->Lc + 64)); CK(c->d_pref.ensure((size_t)c->Lc + 64)); CK(c->d_rm.ensure((size_t)c->Lc + 64));
   // device state
   DevState* h = c->h_st;
