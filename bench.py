@@ -91,13 +91,22 @@ def make_inputs(seed: int, L: int):
     return fa, depth, events
 
 
+def make_bam_inputs(seed: int, L: int, coverage: float = 30.0):
+    fa = synth.make_fasta(L, seed)
+    reads, events = synth.make_reads(L, seed, fa, coverage=coverage, n_events=20)
+    return fa, reads, events
+
+
+READ_FIELDS = ("pos", "mpos", "isize", "mtid", "flag", "mapq", "cigar_off", "cigar", "qual_off", "qual")
+
+
 # algorithmic HBM bytes of one launch of each streaming kernel (DESIGN.md "kernels"); L = contig, Lc = after N removal
 def kernel_bytes(name: str, L: int, Lc: int, reads_bytes: int = 0):
     return {
         "k_gc_table": 5 * L,          # depth 4 + FASTA 1, read once
         "k_gc_adjust": 9 * L,         # depth 4 + FASTA 1 read, adjusted depth 4 written
         "k_bins": 4 * Lc,             # compacted depth read once
-        "k_pileup_tile": reads_bytes + 4 * L,
+        "k_pileup_tile": reads_bytes + 4 * L,   # every read record once (core fields + CIGAR + qualities) + depth written once
     }.get(name, 0)
 
 
@@ -111,6 +120,49 @@ def ref_worker(args):
     t0 = time.perf_counter()
     res = r.depth_path(depth, fa, 3)
     return time.perf_counter() - t0, len(res["calls"])
+
+
+def ref_bam_worker(args):
+    """one reference-CPU process on the BAM path: the UNMODIFIED reference CLI on its own sorted + indexed synthetic BAM"""
+    seed, L, workdir = args
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from bind import REF_BAMTOOL, REF_BIN
+    d = os.path.join(workdir, f"s{seed}")
+    os.makedirs(d, exist_ok=True)
+    fa, reads, _ = make_bam_inputs(seed, L)
+    synth.write_fasta(os.path.join(d, "t.fa"), "19", fa)
+    synth.write_bam(os.path.join(d, "t.bam"), [("19", L)], {0: reads})
+    subprocess.run([REF_BAMTOOL, "index", os.path.join(d, "t.bam")], check=True)
+    t0 = time.perf_counter()
+    subprocess.run([REF_BIN, "rsi", "-b", os.path.join(d, "t.bam"), "-f", os.path.join(d, "t.fa"), "-q", "0", "-Q", "10", "-np", "-o", os.path.join(d, "out.txt")],
+                   check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    dt = time.perf_counter() - t0
+    ncalls = sum(1 for ln in open(os.path.join(d, "out.txt")) if not ln.startswith("#"))
+    return dt, ncalls
+
+
+def ref_bam_port_worker(args):
+    """fallback when oracle/_ref is absent: the oracle restatement of the same path on the read SoA"""
+    seed, L, _ = args
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from bind import Lib, oracle_bam_path
+    fa, reads, _ = make_bam_inputs(seed, L)
+    o = Lib("oracle")
+    t0 = time.perf_counter()
+    res = oracle_bam_path(o, reads, fa, minq=0, min_baseQ=10)
+    return time.perf_counter() - t0, len(res["calls"])
+
+
+def time_reference_bam(sample_len: int, procs: int, seed0: int):
+    import multiprocessing as mp
+    import tempfile
+    ctx = mp.get_context("spawn")
+    have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "rsicnv"))
+    if not have_ref:
+        ref_kind()
+    with tempfile.TemporaryDirectory() as td, ctx.Pool(procs) as pool:
+        out = pool.map(ref_bam_worker if have_ref else ref_bam_port_worker, [(seed0 + i, sample_len, td) for i in range(procs)])
+    return max(o[0] for o in out), out, ("reference" if have_ref else "port")
 
 
 def ref_kind():
@@ -140,16 +192,22 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="chr19_depth", choices=["chr19_depth"])
+    ap.add_argument("--workload", default="chr19_bam", choices=["chr19_bam", "chr19_depth"])
     ap.add_argument("--len", type=int, default=CHR19, help="contig length (debug; the contract uses the default)")
-    ap.add_argument("--cpu-sample", type=int, default=12_000_000)
+    ap.add_argument("--cpu-sample", type=int, default=12_000_000, help="contig length of the bounded CPU-reference sample (> 10 Mbp for the BAM path)")
     ap.add_argument("--profile-steps", type=int, default=2)
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     L = a.len
-    workload = f"{a.workload}: rsicnv rsi -d <synthetic chr19-shaped depth, {L} bp, 30x NB-like, 20 planted DEL/DUP> -c 19 -f <synthetic FASTA> -m 101 -np"
-    config = {"workload": workload, "contigs_per_step_per_gpu": 1, "contig_bp": L, "m": 101, "parallelism": f"contig-sharded x{world}",
-              "l2": "inputs (depth 4 B/base + FASTA 1 B/base = %.0f MB per contig) are larger than the 126 MB L2" % (5 * L / 1e6)}
+    bam = a.workload == "chr19_bam"
+    if bam:
+        workload = (f"chr19_bam (BASELINE.json configs[1]): rsicnv rsi -b <simulated sorted chr19-shaped BAM, {L} bp, 30x 2x100bp pairs, 20 planted DEL/DUP> "
+                    f"-f <synthetic FASTA> -q 0 -Q 10 -m 101 -np (full pileup + RP/Q0 path; reads enter the C ABI as decoded SoA batches)")
+        l2 = "inputs (read SoA ~150 B/read x 17.7 M reads + FASTA) are far larger than the 126 MB L2"
+    else:
+        workload = f"chr19_depth (BASELINE.json configs[0]): rsicnv rsi -d <synthetic chr19-shaped depth, {L} bp, 30x NB-like, 20 planted DEL/DUP> -c 19 -f <synthetic FASTA> -m 101 -np"
+        l2 = "inputs (depth 4 B/base + FASTA 1 B/base = %.0f MB per contig) are larger than the 126 MB L2" % (5 * L / 1e6)
+    config = {"workload": workload, "contigs_per_step_per_gpu": 1, "contig_bp": L, "m": 101, "parallelism": f"contig-sharded x{world}", "l2": l2}
 
     if a.impl == "reference":
         if rank != 0:
@@ -161,7 +219,10 @@ def main():
         for s in range(a.warmup + a.steps):
             if s < a.warmup and s > 0:
                 continue  # one warm-up pass is enough for a CPU job (page cache / import)
-            cpu, wall, out = time_reference(sample, procs, 1000 + 97 * s)
+            if bam:
+                cpu, out, kind = time_reference_bam(sample, procs, 1000 + 97 * s)
+            else:
+                cpu, wall, out = time_reference(sample, procs, 1000 + 97 * s)
             if s >= a.warmup:
                 times.append(cpu)
         ms = 1e3 * float(np.mean(times))
@@ -170,8 +231,9 @@ def main():
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/f64", "data": "synthetic",
                 "config": config,
                 "cpu_baseline": {"value": val, "unit": "Gbases/s", "cores": procs, "kind": kind,
-                                 "sample": f"{procs} processes x one {sample} bp synthetic contig each through the reference's own checkgccontent..detectcnv..sd_filters "
-                                           f"(in-memory depth array, same boundary as the C ABI; text parsing excluded)"},
+                                 "sample": (f"{procs} processes x one {sample} bp 30x synthetic BAM each through the unmodified `rsicnv rsi -b` CLI (BGZF/BAM decode included)" if bam else
+                                            f"{procs} processes x one {sample} bp synthetic contig each through the reference's own checkgccontent..detectcnv..sd_filters "
+                                            f"(in-memory depth array, same boundary as the C ABI; text parsing excluded)")},
                 "e2e": {"value": val, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
@@ -186,15 +248,37 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    fa, depth, events = make_inputs(19 + rank, L)
     # pinned host buffers (the e2e leg copies from these every step)
-    fa_pin = torch.from_numpy(fa).pin_memory(); dp_pin = torch.from_numpy(depth).pin_memory()
-    ctx = api.Context(device=local)
+    reads_bytes = 0
+    if bam:
+        fa, reads, events = make_bam_inputs(19 + rank, L)
+        pins = {k: torch.from_numpy(reads[k]).pin_memory() for k in READ_FIELDS}
+        batch = api.ReadBatch()
+        batch.n_reads = len(reads["pos"]); batch.tid = 0
+        for k in READ_FIELDS:
+            setattr(batch, k, pins[k].data_ptr())
+        nreads = len(reads["pos"])
+        h2d = L + sum(int(pins[k].numel() * pins[k].element_size()) for k in READ_FIELDS)
+        # bytes the pileup kernel has to read once: pos, flag, mapq, CIGAR offsets + ops, quality offsets + qualities
+        reads_bytes = sum(int(pins[k].numel() * pins[k].element_size()) for k in ("pos", "flag", "mapq", "cigar_off", "cigar", "qual_off", "qual"))
+        config["reads"] = nreads
+        ctx = api.Context(device=local, minq=0, min_baseQ=10)
+    else:
+        fa, depth, events = make_inputs(19 + rank, L)
+        dp_pin = torch.from_numpy(depth).pin_memory()
+        h2d = 5 * L
+        ctx = api.Context(device=local)
+    fa_pin = torch.from_numpy(fa).pin_memory()
     buf = (api.Cnv * 65536)()
 
     def stage_inputs():
         ctx.set_reference_ptr(fa_pin.data_ptr(), L)
-        ctx.set_depth_ptr(dp_pin.data_ptr(), L)
+        if bam:
+            ctx.pileup_begin()
+            ctx._ck(ctx.lib.rsigpu_pileup_push(ctx.h, C.byref(batch)))
+            ctx.have_reads()
+        else:
+            ctx.set_depth_ptr(dp_pin.data_ptr(), L)
 
     def barrier():
         torch.cuda.synchronize()
@@ -246,7 +330,7 @@ def main():
         value = total_bases / (dev_ms / 1e3) / 1e9
         kern = []
         for name, ms, n in prof:
-            b = kernel_bytes(name, L, st.compact_len)
+            b = kernel_bytes(name, L, st.compact_len, reads_bytes)
             avg = ms / max(n, 1)
             kern.append({"kernel": name, "launches_per_step": n / a.profile_steps, "avg_ms": avg, "ms_per_step": ms / a.profile_steps,
                          "algorithmic_bytes": b, "gbs": (b / 1e9) / (avg / 1e3) if b and avg > 0 else None})
@@ -262,17 +346,23 @@ def main():
                     "streaming_kernels": [{"kernel": k["kernel"], "gbs": k["gbs"], "frac": (k["gbs"] or 0) / peak, "ms": k["avg_ms"]} for k in stream]}
         line = {"metric": METRIC, "value": value, "unit": "Gbases/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": dev_ms / a.steps, "wall_ms_per_step": wall_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "int32 depth / f64 statistics", "data": "synthetic", "config": config, "clocks": clocks,
-                "e2e": {"value": total_bases / (e2e_ms / 1e3) / 1e9, "unit": "Gbases/s", "h2d_bytes_per_step": 5 * L, "d2h_bytes_per_step": int(ne * 128 + 53000),
+                "dtype": "u8 qualities -> int32 depth / f64 statistics", "data": "synthetic", "config": config, "clocks": clocks,
+                "e2e": {"value": total_bases / (e2e_ms / 1e3) / 1e9, "unit": "Gbases/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(ne * 128 + 53000),
                         "ms_per_step": e2e_ms / a.steps},
                 "gpu_launches": int(launches), "calls_per_contig": int(ncalls), "roofline": roof,
                 "stage_ms_per_step": {k: v / a.steps for k, v in (stages or {}).items()}, "kernels": kern[:12]}
         if world == 1:
             sample = min(a.cpu_sample, L)
-            cpu, _, out = time_reference(sample, 1, 19)
-            line["cpu_baseline"] = {"value": sample / cpu / 1e9, "unit": "Gbases/s", "cores": 1, "kind": ref_kind()[1],
-                                    "sample": f"one {sample} bp synthetic contig through checkgccontent..detectcnv..sd_filters on one host core "
-                                              f"(the reference is single-threaded; in-memory depth array, text parsing excluded)"}
+            if bam:
+                cpu, out, kind = time_reference_bam(sample, 1, 19)
+                line["cpu_baseline"] = {"value": sample / cpu / 1e9, "unit": "Gbases/s", "cores": 1, "kind": kind,
+                                        "sample": f"one {sample} bp 30x synthetic BAM through the unmodified `rsicnv rsi -b ... -q 0 -Q 10 -np` CLI on one host core "
+                                                  f"(the reference is single-threaded; BGZF/BAM decode included, BAM in page cache)"}
+            else:
+                cpu, _, out = time_reference(sample, 1, 19)
+                line["cpu_baseline"] = {"value": sample / cpu / 1e9, "unit": "Gbases/s", "cores": 1, "kind": ref_kind()[1],
+                                        "sample": f"one {sample} bp synthetic contig through checkgccontent..detectcnv..sd_filters on one host core "
+                                                  f"(the reference is single-threaded; in-memory depth array, text parsing excluded)"}
         print(json.dumps(line))
     ctx.close()
     if world > 1:

@@ -123,7 +123,8 @@ int rsigpu_set_depth(rsigpu_ctx* c, const int32_t* depth, int32_t len);
  * per-read summary cnv_stat needs); the pileup kernel runs in rsigpu_run / rsigpu_pileup_end. */
 int rsigpu_pileup_begin(rsigpu_ctx* c, int32_t target_len);
 int rsigpu_pileup_push(rsigpu_ctx* c, const rsigpu_read_batch* b);
-int rsigpu_pileup_end(rsigpu_ctx* c);
+int rsigpu_pileup_end(rsigpu_ctx* c);      /* runs the pileup kernels now: the raw depth becomes readable (-s) */
+int rsigpu_pileup_commit(rsigpu_ctx* c);   /* only marks the staged batches complete; rsigpu_run runs the pileup as its first stage */
 
 /* The seams, in the order main() calls them (rsi.cpp:2197-2211).  All asynchronous on the
  * context's stream except where a result is copied to the host. */

@@ -71,7 +71,7 @@ EXPORTS = ("rsigpu_default_params", "rsigpu_create", "rsigpu_destroy", "rsigpu_l
            "rsigpu_set_depth", "rsigpu_pileup_begin", "rsigpu_pileup_push", "rsigpu_pileup_end", "rsigpu_load_finish", "rsigpu_detectcnv",
            "rsigpu_sd_filters", "rsigpu_cnv_stat", "rsigpu_get_calls", "rsigpu_run", "rsigpu_get_chr_stats", "rsigpu_get_array",
            "rsigpu_format_row", "rsigpu_launch_count", "rsigpu_last_stage_ms", "rsigpu_set_profile", "rsigpu_get_profile",
-           "rsigpu_set_level0_mode", "rsigpu_debug_state")
+           "rsigpu_set_level0_mode", "rsigpu_debug_state", "rsigpu_pileup_commit")
 
 _libs: dict[str, C.CDLL] = {}
 
@@ -173,7 +173,12 @@ class Context:
         self._ck(self.lib.rsigpu_pileup_push(self.h, C.byref(b)))
 
     def pileup_end(self):
+        """runs the pileup kernels now (so that the raw depth can be read back); `run()` re-runs them as its first stage"""
         self._ck(self.lib.rsigpu_pileup_end(self.h))
+
+    def have_reads(self):
+        """marks the staged batches as complete WITHOUT running the pileup yet (rsigpu_run does it as its first stage)"""
+        self._ck(self.lib.rsigpu_pileup_commit(self.h))
 
     # ---- the seams, in the order main() calls them (rsi.cpp:2197-2211)
     def load_finish(self):

@@ -97,9 +97,16 @@ RSI_DEV double phi(double v) {
 template <class T>
 RSI_DEVN void cta_hist_stat(const Cta& c, const CandScratch& S, const T* x, int n, double dy, double q[3]) {
   double mn = 1e300, mx = -1e300, sm = 0.0;
-  for (int i = c.tid; i < n; i += c.nthr) {
-    double v = (double)x[i];
-    mn = v < mn ? v : mn; mx = v > mx ? v : mx; sm += v;
+  {
+    int i = c.tid;
+    for (; i + 3 * c.nthr < n; i += 4 * c.nthr) {   // four independent loads in flight per thread
+      const T a0 = x[i], a1 = x[i + c.nthr], a2 = x[i + 2 * c.nthr], a3 = x[i + 3 * c.nthr];
+      const double v0 = (double)a0, v1 = (double)a1, v2 = (double)a2, v3 = (double)a3;
+      mn = v0 < mn ? v0 : mn; mx = v0 > mx ? v0 : mx; mn = v1 < mn ? v1 : mn; mx = v1 > mx ? v1 : mx;
+      mn = v2 < mn ? v2 : mn; mx = v2 > mx ? v2 : mx; mn = v3 < mn ? v3 : mn; mx = v3 > mx ? v3 : mx;
+      sm += v0; sm += v1; sm += v2; sm += v3;
+    }
+    for (; i < n; i += c.nthr) { double v = (double)x[i]; mn = v < mn ? v : mn; mx = v > mx ? v : mx; sm += v; }
   }
   mn = c.reduce(mn, MinOp()); mx = c.reduce(mx, MaxOp()); sm = c.reduce(sm, SumOp());
   q[0] = mn; q[1] = sm / (double)n; q[2] = mx;
@@ -110,12 +117,16 @@ RSI_DEVN void cta_hist_stat(const Cta& c, const CandScratch& S, const T* x, int 
   for (size_t b = c.tid; b <= np; b += c.nthr) H[b] = 0u;
   c.sync();
   // neighbouring samples mostly share a bucket: one atomic per distinct bucket of a warp
-  for (int base = 0; base < n; base += c.nthr) {
-    const int i = base + c.tid;
-    const bool valid = i < n;
-    size_t b = 0;
-    if (valid) { double idx = ((double)x[i] - mn) / dy + 0.5; b = (size_t)idx; }
-    cta_hist_add(H, b, valid);
+  for (int base = 0; base < n; base += 4 * c.nthr) {
+    T a[4]; bool valid[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const int i = base + k * c.nthr + c.tid; valid[k] = i < n; a[k] = valid[k] ? x[i] : T(0); }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      size_t b = 0;
+      if (valid[k]) { double idx = ((double)a[k] - mn) / dy + 0.5; b = (size_t)idx; }
+      cta_hist_add(H, b, valid[k]);
+    }
   }
   c.sync();
   const unsigned long long r4 = (unsigned long long)n / 4, r2 = (unsigned long long)n / 2, r34 = (unsigned long long)n * 3 / 4;
@@ -169,6 +180,7 @@ RSI_DEVN int cta_collect(const Cta& c, const int* RD, int lo, int hi, int dir, i
     const int per = (sc + c.nthr - 1) / c.nthr;
     const int j0 = pos + (c.tid * per < sc ? c.tid * per : sc), j1 = pos + ((c.tid + 1) * per < sc ? (c.tid + 1) * per : sc);
     int cnt = 0;
+#pragma unroll 8
     for (int j = j0; j < j1; ++j) cnt += nb_accept(RD[dir > 0 ? lo + j : hi - j], flag, up, lw) ? 1 : 0;
     int tot, ex = c.scan_excl(cnt, &tot);
     int w = got + ex;
@@ -207,6 +219,7 @@ RSI_DEVN void cnv_test_stats(const Cta& c, const CandCfg& P, const CandScratch& 
     const int per = (nref + c.nthr - 1) / c.nthr;
     const int j0 = c.tid * per < nref ? c.tid * per : nref, j1 = (c.tid + 1) * per < nref ? (c.tid + 1) * per : nref;
     long long loc = 0, tot;
+#pragma unroll 8
     for (int j = j0; j < j1; ++j) loc += (long long)ref[j];
     long long run = c.scan_excl(loc, &tot);
     if (c.tid == 0) S.pref[0] = 0;
@@ -214,10 +227,26 @@ RSI_DEVN void cnv_test_stats(const Cta& c, const CandCfg& P, const CandScratch& 
   }
   c.sync();
   double s1 = 0.0, s2 = 0.0;
-  for (int i = c.tid; i < nr; i += c.nthr) {
-    float mnv = (float)((double)(S.pref[i + d] - S.pref[i]) / (double)d);
-    S.rm[i] = mnv;
-    s1 += (double)mnv; s2 += (double)mnv * (double)mnv;
+  {
+    const long long* __restrict__ pf = S.pref;
+    float* __restrict__ rmo = S.rm;
+    int i = c.tid;
+    for (; i + 3 * c.nthr < nr; i += 4 * c.nthr) {
+      long long w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) w[k] = pf[i + k * c.nthr + d] - pf[i + k * c.nthr];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float mnv = (float)((double)w[k] / (double)d);
+        rmo[i + k * c.nthr] = mnv;
+        s1 += (double)mnv; s2 += (double)mnv * (double)mnv;
+      }
+    }
+    for (; i < nr; i += c.nthr) {
+      float mnv = (float)((double)(pf[i + d] - pf[i]) / (double)d);
+      rmo[i] = mnv;
+      s1 += (double)mnv; s2 += (double)mnv * (double)mnv;
+    }
   }
   c.sync();
   s1 = c.reduce(s1, SumOp()); s2 = c.reduce(s2, SumOp());
@@ -225,6 +254,7 @@ RSI_DEVN void cnv_test_stats(const Cta& c, const CandCfg& P, const CandScratch& 
   cta_hist_stat(c, S, S.rm, nr, 0.01, rq);
   cta_hist_stat(c, S, cnv, ncnv, 1.0, cq);
   long long a1 = 0, a2 = 0;
+#pragma unroll 4
   for (int i = c.tid; i < ncnv; i += c.nthr) { long long v = cnv[i]; a1 += v; a2 += v * v; }
   a1 = c.reduce(a1, SumOp()); a2 = c.reduce(a2, SumOp());
   if (c.tid == 0) {

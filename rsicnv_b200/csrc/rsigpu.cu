@@ -389,8 +389,8 @@ int rsigpu_pileup_push(rsigpu_ctx* c, const rsigpu_read_batch* b) {
   return RSIGPU_OK;
 }
 
-int rsigpu_pileup_end(rsigpu_ctx* c) {
-  if (!c) return RSIGPU_E_ARG;
+// the pileup kernels on the staged reads -> raw depth (a5)
+static int run_pileup(rsigpu_ctx* c) {
   cudaSetDevice(c->device);
   const size_t padded = ((size_t)c->L + LD_TILE - 1) / LD_TILE * LD_TILE + 64;
   CK(c->d_raw.ensure(padded));
@@ -403,18 +403,35 @@ int rsigpu_pileup_end(rsigpu_ctx* c) {
     ReadSoA R = read_view(c);
     KL(k_read_ends, grid_for((int)std::min<size_t>(c->r_pos.n, 1u << 30), 256, c->n_sm * 16), 256, 0, R, mx, mx + 1);
     KL(k_pileup_tile, grid_for(c->L, PU_T, c->n_sm * 4), PU_NT, 0, R, c->d_raw.p, c->L, c->P.minq, c->P.min_baseQ, mx);
-    int h[2];
-    CK(cudaMemcpyAsync(h, mx, 8, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    if (h[1]) { c->fail("read batch is not sorted by position"); return RSIGPU_E_ARG; }
   }
-  c->have_reads = true; c->have_depth = true; c->loaded = false; c->detected = false; c->filtered = false;
+  c->have_depth = true;
+  return RSIGPU_OK;
+}
+
+int rsigpu_pileup_end(rsigpu_ctx* c) {
+  if (!c) return RSIGPU_E_ARG;
+  if (!c->have_ref) { c->fail("pileup_end: call set_reference / pileup_begin first"); return RSIGPU_E_ARG; }
+  int rc = run_pileup(c);
+  if (rc) return rc;
+  int h[2] = {0, 0};
+  CK(cudaMemcpyAsync(h, c->d_misc.p + 5, 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (h[1]) { c->fail("read batch is not sorted by position"); return RSIGPU_E_ARG; }
+  c->have_reads = true; c->loaded = false; c->detected = false; c->filtered = false;
+  return RSIGPU_OK;
+}
+
+int rsigpu_pileup_commit(rsigpu_ctx* c) {
+  if (!c) return RSIGPU_E_ARG;
+  if (!c->have_ref) { c->fail("pileup_commit: call set_reference / pileup_begin first"); return RSIGPU_E_ARG; }
+  c->have_reads = true; c->have_depth = false; c->loaded = false; c->detected = false; c->filtered = false;
   return RSIGPU_OK;
 }
 
 // a7 + a8 + a9 + chromosome statistics + bin arrays (median_transfer, negative_binomial_transfer)
 int rsigpu_load_finish(rsigpu_ctx* c) {
   if (!c) return RSIGPU_E_ARG;
+  if (c->have_ref && c->have_reads && !c->have_depth) { int rc = run_pileup(c); if (rc) return rc; }
   if (!c->have_ref || !c->have_depth) { c->fail("load_finish: no reference or depth staged"); return RSIGPU_E_ARG; }
   cudaSetDevice(c->device);
   const int L = c->L, nb = c->nb, nn = (int)c->h_nbeg.size(), m = c->P.m;
@@ -454,6 +471,12 @@ int rsigpu_load_finish(rsigpu_ctx* c) {
   KL(k_chr_stats, 1, 1024, 0, c->d_chist.p, c->d_thist.p, c->d_tothist.p, c->d_st);
   CK(cudaMemcpyAsync(h, c->d_st, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  if (c->have_reads) {
+    int sb = 0;
+    CK(cudaMemcpyAsync(&sb, c->d_misc.p + 6, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (sb) { c->fail("read batch is not sorted by position"); return RSIGPU_E_ARG; }
+  }
   const bool low_depth = h->rdmedian < 5;   // "Read depths too low": detectcnv returns without calls (rsi.cpp:1809-1812)
   if (low_depth) h->err &= ~ERR_DEGENERATE;
   if (h->err) return map_dev_err(c, h->err, h->cand_err);
@@ -576,6 +599,7 @@ int rsigpu_run(rsigpu_ctx* c, rsigpu_cnv* out, int32_t cap, int32_t* n) {
   cudaSetDevice(c->device);
   int rc;
   CK(cudaEventRecord(c->ev[0], c->stream));
+  if (c->have_reads && (rc = run_pileup(c)) != RSIGPU_OK) return rc;   // BAM input: the pileup is the first stage of the path
   if ((rc = rsigpu_load_finish(c)) != RSIGPU_OK) return rc;
   if ((rc = rsigpu_detectcnv(c)) != RSIGPU_OK) return rc;
   if ((rc = rsigpu_sd_filters(c)) != RSIGPU_OK) return rc;
@@ -583,7 +607,7 @@ int rsigpu_run(rsigpu_ctx* c, rsigpu_cnv* out, int32_t cap, int32_t* n) {
   CK(cudaEventRecord(c->ev[5], c->stream));
   CK(cudaStreamSynchronize(c->stream));
   float ms = 0;
-  c->stage_ms[0] = 0;
+  cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->stage_ms[0] = ms;
   cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->stage_ms[1] = ms;
   cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); c->stage_ms[2] = ms;
   cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]); c->stage_ms[3] = ms;

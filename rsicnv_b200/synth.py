@@ -199,3 +199,185 @@ def stress_events(L: int, seed: int, n_blocks) -> list[tuple[int, int, float]]:
 def apply_events(cn: np.ndarray, events) -> None:
     for s, e, f in events:
         cn[s:e] = f
+
+
+# --------------------------------------------------------------------------------------------
+# reads (BAM path).  Structure-of-arrays exactly as include/rsigpu.h's rsigpu_read_batch takes them.
+READ_LEN = 100
+F_PAIRED, F_PROPER, F_REV, F_MREV, F_R1, F_R2, F_SECONDARY, F_DUP = 1, 2, 16, 32, 64, 128, 256, 1024
+
+
+def make_reads(L: int, seed: int, fasta: np.ndarray | None = None, coverage: float = 30.0, events=None, n_events: int = 8,
+               lens=EVENT_LENS, tid: int = 0, discordant_per_edge: int = 12, frac_clip=0.15, frac_indel=0.03, frac_lowq=0.09,
+               frac_dup=0.01, frac_mapq0=0.02, frac_secondary=0.002):
+    """2x100 bp FR pairs, insert ~ N(400,30), copy-number-thinned starts for the planted events, spanning
+    discordant pairs at DEL edges and everted pairs at DUP edges.  Returns (dict of numpy arrays sorted by pos, events)."""
+    rng = np.random.default_rng(seed + 1000)
+    if fasta is None:
+        fasta = make_fasta(L, seed)
+    n_blocks = _n_runs(fasta)
+    if events is None:
+        events = plant_events(L, seed, n_events, n_blocks, lens)
+    RL = READ_LEN
+    n_pairs = int(coverage * L / (2 * RL))
+    # candidate fragment starts, thinned by copy number (max factor 1.5 -> oversample by 1.5)
+    n_try = int(n_pairs * 1.5)
+    start = rng.integers(2, L - 700, n_try, dtype=np.int64)
+    cn = np.ones(L, np.float32)
+    for s, e, f in events:
+        cn[s:e] = f
+    isn = fasta == ord("N")
+    cn[isn] = 0
+    keep = rng.random(n_try, dtype=np.float32) * 1.5 < cn[start]
+    start = start[keep]
+    ins = np.clip(np.rint(rng.normal(400, 30, len(start))), 250, 650).astype(np.int64)
+    # drop fragments that touch N
+    cs = np.concatenate(([0], np.cumsum(isn, dtype=np.int64)))
+    ok = (cs[np.minimum(start + ins, L)] - cs[start]) == 0
+    start, ins = start[ok], ins[ok]
+    p1 = start; p2 = start + ins - RL
+    extra = []
+    # discordant pairs supporting the events
+    for s, e, f in events:
+        k = discordant_per_edge
+        if f < 1:   # deletion: pairs spanning it, mates ~ (e - s) + 400 apart
+            a = s - rng.integers(120, 300, k); b = e + rng.integers(20, 200, k)
+            extra.append((a, b, np.full(k, 0)))
+        else:       # duplication: everted pairs (read 1 near the end, mate near the start)
+            a = e - rng.integers(120, 300, k); b = s + rng.integers(20, 200, k)
+            extra.append((a, b, np.full(k, 1)))
+    n_norm = len(p1)
+    pos1 = [p1]; pos2 = [p2]; kind = [np.full(n_norm, -1)]
+    for a, b, kk in extra:
+        pos1.append(a.astype(np.int64)); pos2.append(b.astype(np.int64)); kind.append(kk)
+    p1 = np.concatenate(pos1); p2 = np.concatenate(pos2); kind = np.concatenate(kind)
+    n = len(p1)
+    # per-read arrays: read 1 (forward) and read 2 (reverse)
+    pos = np.concatenate((p1, p2)).astype(np.int32)
+    mpos = np.concatenate((p2, p1)).astype(np.int32)
+    isz = (p2 + RL - p1)
+    isize = np.concatenate((isz, -isz)).astype(np.int32)
+    proper = np.concatenate((kind < 0, kind < 0))
+    flag = np.concatenate((np.full(n, F_PAIRED | F_MREV | F_R1), np.full(n, F_PAIRED | F_REV | F_R2))).astype(np.uint16)
+    flag[proper] |= F_PROPER
+    nr = 2 * n
+    u = rng.random(nr)
+    flag[u < frac_dup] |= F_DUP
+    flag[(u >= frac_dup) & (u < frac_dup + frac_secondary)] |= F_SECONDARY
+    mapq = np.full(nr, 60, np.uint8)
+    mapq[rng.random(nr) < frac_mapq0] = 0
+    mtid = np.full(nr, tid, np.int32)
+    # CIGARs: 100M | xS yM | yM xS | 50M 2D 50M | 50M 2I 48M
+    u = rng.random(nr)
+    ctype = np.zeros(nr, np.int8)
+    ctype[u < frac_clip / 2] = 1
+    ctype[(u >= frac_clip / 2) & (u < frac_clip)] = 2
+    ctype[(u >= frac_clip) & (u < frac_clip + frac_indel / 2)] = 3
+    ctype[(u >= frac_clip + frac_indel / 2) & (u < frac_clip + frac_indel)] = 4
+    x = rng.integers(5, 31, nr).astype(np.uint32)
+    ncig = np.where(ctype == 0, 1, np.where(ctype <= 2, 2, 3)).astype(np.uint32)
+    order = np.argsort(pos, kind="stable")
+    pos, mpos, isize, flag, mapq, mtid, ctype, x, ncig = (a[order] for a in (pos, mpos, isize, flag, mapq, mtid, ctype, x, ncig))
+    cigar_off = np.concatenate(([0], np.cumsum(ncig, dtype=np.uint64))).astype(np.uint32)
+    cigar = np.zeros(int(cigar_off[-1]), np.uint32)
+    o = cigar_off[:-1]
+    M, I, D, S = 0, 1, 2, 4
+    m0 = ctype == 0; cigar[o[m0]] = (RL << 4) | M
+    m1 = ctype == 1; cigar[o[m1]] = (x[m1] << 4) | S; cigar[o[m1] + 1] = ((RL - x[m1]) << 4) | M
+    m2 = ctype == 2; cigar[o[m2]] = ((RL - x[m2]) << 4) | M; cigar[o[m2] + 1] = (x[m2] << 4) | S
+    m3 = ctype == 3; cigar[o[m3]] = (50 << 4) | M; cigar[o[m3] + 1] = (2 << 4) | D; cigar[o[m3] + 2] = (50 << 4) | M
+    m4 = ctype == 4; cigar[o[m4]] = (50 << 4) | M; cigar[o[m4] + 1] = (2 << 4) | I; cigar[o[m4] + 2] = (48 << 4) | M
+    qual_off = (np.arange(nr + 1, dtype=np.uint64) * RL)
+    qual = np.full(nr * RL, 30, np.uint8)
+    lowq = np.flatnonzero(rng.random(nr) < frac_lowq)
+    st = rng.integers(0, RL - 10, len(lowq))
+    idx = (lowq[:, None] * RL + st[:, None] + np.arange(10)[None, :]).ravel()
+    qual[idx] = 2
+    reads = dict(pos=pos, mpos=mpos, isize=isize, mtid=mtid, flag=flag, mapq=mapq, cigar_off=cigar_off, cigar=cigar,
+                 qual_off=qual_off, qual=qual)
+    return reads, events
+
+
+def write_bam(path: str, contigs: list[tuple[str, int]], reads_by_tid: dict[int, dict], level: int = 1) -> None:
+    """Minimal BAM (BGZF) writer for the synthetic reads: one record per read, name 'r', sequence all 'A'
+    (the path never looks at bases), qualities as given.  Layout: SURVEY.md Appendix B."""
+    import struct
+    import zlib
+    text = "@HD\tVN:1.0\tSO:coordinate\n" + "".join(f"@SQ\tSN:{n}\tLN:{l}\n" for n, l in contigs)
+    hdr = bytearray(b"BAM\x01") + struct.pack("<i", len(text)) + text.encode() + struct.pack("<i", len(contigs))
+    for n, l in contigs:
+        hdr += struct.pack("<i", len(n) + 1) + n.encode() + b"\x00" + struct.pack("<i", l)
+    chunks = [bytes(hdr)]
+    for tid in sorted(reads_by_tid):
+        R = reads_by_tid[tid]
+        nr = len(R["pos"])
+        ncig = np.diff(R["cigar_off"].astype(np.int64)); lq = np.diff(R["qual_off"].astype(np.int64))
+        lname = 2  # "r\0"
+        size = 32 + lname + 4 * ncig + (lq + 1) // 2 + lq   # block_size payload (without the 4-byte length)
+        offs = np.concatenate(([0], np.cumsum(size + 4)))
+        buf = np.zeros(int(offs[-1]), np.uint8)
+        o = offs[:-1]
+
+        def put32(off, val):
+            v = np.ascontiguousarray(np.asarray(val).astype("<u4")).view(np.uint8).reshape(-1, 4)
+            for k in range(4):
+                buf[o + off + k] = v[:, k]
+        pos = R["pos"].astype(np.int64)
+        # reg2bin needs the alignment end: sum of M/D/N lengths
+        cl = (R["cigar"] >> 4).astype(np.int64); cop = R["cigar"] & 15
+        refl = np.where((cop == 0) | (cop == 2) | (cop == 3), cl, 0)
+        csum = np.concatenate(([0], np.cumsum(refl)))
+        end = pos + (csum[R["cigar_off"][1:].astype(np.int64)] - csum[R["cigar_off"][:-1].astype(np.int64)])
+        b = _reg2bin(pos, np.maximum(end, pos + 1))
+        put32(0, size)
+        put32(4, np.full(nr, tid)); put32(8, R["pos"])
+        put32(12, (b.astype(np.uint32) << 16) | (R["mapq"].astype(np.uint32) << 8) | lname)
+        put32(16, (R["flag"].astype(np.uint32) << 16) | ncig.astype(np.uint32))
+        put32(20, lq); put32(24, R["mtid"]); put32(28, R["mpos"]); put32(32, R["isize"])
+        buf[o + 36] = ord("r")
+        # cigar ops
+        co = R["cigar_off"].astype(np.int64)
+        for k in range(int(ncig.max()) if nr else 0):
+            sel = np.flatnonzero(ncig > k)
+            v = np.ascontiguousarray(R["cigar"][co[sel] + k].astype("<u4")).view(np.uint8).reshape(-1, 4)
+            for bb in range(4):
+                buf[o[sel] + 38 + 4 * k + bb] = v[:, bb]
+        # packed sequence (all 'A' = 1) and qualities
+        soff = o + 38 + 4 * ncig
+        nseq = (lq + 1) // 2
+        if nr and np.all(lq == lq[0]):
+            l0 = int(lq[0]); ns0 = int(nseq[0])
+            ii = (soff[:, None] + np.arange(ns0)[None, :]).ravel()
+            buf[ii] = 0x11
+            if l0 % 2:
+                buf[soff + ns0 - 1] = 0x10
+            qi = (soff[:, None] + ns0 + np.arange(l0)[None, :]).ravel()
+            buf[qi] = R["qual"]
+        else:
+            qo = R["qual_off"].astype(np.int64)
+            for r in range(nr):
+                buf[soff[r]:soff[r] + nseq[r]] = 0x11
+                buf[soff[r] + nseq[r]:soff[r] + nseq[r] + lq[r]] = R["qual"][qo[r]:qo[r + 1]]
+        chunks.append(buf.tobytes())
+    data = b"".join(chunks)
+    with open(path, "wb") as f:
+        BS = 65280
+        for a in range(0, len(data), BS):
+            blk = data[a:a + BS]
+            co = zlib.compressobj(level, zlib.DEFLATED, -15)
+            comp = co.compress(blk) + co.flush()
+            f.write(b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(comp) + 25) + comp +
+                    struct.pack("<II", zlib.crc32(blk) & 0xffffffff, len(blk)))
+        f.write(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
+
+
+def _reg2bin(beg, end):
+    """UCSC binning (samtools bam.h:bam_reg2bin), vectorised"""
+    end = end - 1
+    out = np.zeros(len(beg), np.int64)
+    done = np.zeros(len(beg), bool)
+    for shift, base in ((14, 4681), (17, 585), (20, 73), (23, 9), (26, 1)):
+        m = ~done & ((beg >> shift) == (end >> shift))
+        out[m] = base + (beg[m] >> shift)
+        done |= m
+    return out

@@ -272,5 +272,46 @@ class Lib:
         return buf.value.decode()
 
 
+def _rp(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def oracle_pileup(o: "Lib", reads: dict, L: int) -> np.ndarray:
+    """load_data_from_bam's hot loop on the read SoA (oracle only)"""
+    rd = np.zeros(L, np.int32)
+    o.lib.ocl_pileup(C.c_int64(len(reads["pos"])), C.c_int(0), _rp(reads["pos"], C.c_int32), _rp(reads["flag"], C.c_uint16),
+                     _rp(reads["mapq"], C.c_uint8), _rp(reads["cigar_off"], C.c_uint32), _rp(reads["cigar"], C.c_uint32),
+                     _rp(reads["qual_off"], C.c_uint64), _rp(reads["qual"], C.c_uint8), _rp(rd, C.c_int32), C.c_int(L))
+    return rd
+
+
+def oracle_cnv_stat(o: "Lib", reads: dict, L: int, calls: list) -> list:
+    """cnv_stat + bam_rd_pr_stats on the read SoA (oracle only); returns the annotated calls"""
+    a = Lib._arr(calls)
+    o.lib.ocl_cnv_stat(C.c_int64(len(reads["pos"])), C.c_int(0), _rp(reads["pos"], C.c_int32), _rp(reads["mpos"], C.c_int32),
+                       _rp(reads["isize"], C.c_int32), _rp(reads["mtid"], C.c_int32), _rp(reads["flag"], C.c_uint16), _rp(reads["mapq"], C.c_uint8),
+                       _rp(reads["cigar_off"], C.c_uint32), _rp(reads["cigar"], C.c_uint32), C.c_int(L), a, C.c_int(len(calls)))
+    return Lib._copy(a, len(calls))
+
+
+def oracle_isize(o: "Lib", reads: dict, L: int):
+    out = np.zeros(2, np.int32)
+    o.lib.ocl_isize_stats(C.c_int64(len(reads["pos"])), C.c_int(0), _rp(reads["pos"], C.c_int32), _rp(reads["mpos"], C.c_int32),
+                          _rp(reads["isize"], C.c_int32), _rp(reads["mtid"], C.c_int32), _rp(reads["flag"], C.c_uint16),
+                          _rp(reads["cigar_off"], C.c_uint32), _rp(reads["cigar"], C.c_uint32), C.c_int(L), _rp(out, C.c_int32))
+    return int(out[0]), int(out[1])
+
+
+def oracle_bam_path(o: "Lib", reads: dict, fasta, **params):
+    """the whole BAM path on the oracle: pileup -> depth path -> sd_filters -> cnv_stat; returns dict(raw, calls, stats)"""
+    o.set_params(**params)
+    L = len(fasta)
+    raw = oracle_pileup(o, reads, L)
+    o.set_params(**params)
+    res = o.depth_path(raw, fasta, 3)
+    calls = oracle_cnv_stat(o, reads, L, res["calls"]) if res["calls"] else []
+    return dict(raw=raw, calls=calls, stats=res["stats"])
+
+
 def have_ref() -> bool:
     return os.path.exists(REF_SO)

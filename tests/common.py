@@ -65,3 +65,41 @@ def run_depth_case(lib_path, oracle, fa, d, check_bins=True, level0_modes=(1,), 
         return calls, ctx.launch_count()
     finally:
         ctx.close()
+
+
+def split_reads(reads, cuts):
+    """position-sorted SoA -> consecutive batches with batch-relative offsets (what a BAM decoder would push)"""
+    co, qo = reads["cigar_off"], reads["qual_off"]
+    out = []
+    edges = [0] + list(cuts) + [len(reads["pos"])]
+    for lo, hi in zip(edges[:-1], edges[1:]):
+        d = {k: reads[k][lo:hi] for k in ("pos", "mpos", "isize", "mtid", "flag", "mapq")}
+        d["cigar_off"] = (co[lo:hi + 1] - co[lo]).astype(np.uint32); d["cigar"] = reads["cigar"][co[lo]:co[hi]]
+        d["qual_off"] = (qo[lo:hi + 1] - qo[lo]).astype(np.uint64); d["qual"] = reads["qual"][qo[lo]:qo[hi]]
+        out.append(d)
+    return out
+
+
+def run_bam_case(lib_path, oracle, fa, reads, n_batches=3, **kw):
+    """the whole BAM path through the C ABI (pileup -> load_finish -> detectcnv -> sd_filters -> cnv_stat) vs the oracle"""
+    from bind import oracle_bam_path, oracle_isize
+    want = oracle_bam_path(oracle, reads, fa, **oracle_params(kw))
+    n = len(reads["pos"])
+    cuts = [n * (k + 1) // n_batches for k in range(n_batches - 1)]
+    ctx = api.Context(lib=lib_path, **kw)
+    try:
+        ctx.set_reference(fa)
+        ctx.pileup_begin()
+        for b in split_reads(reads, cuts):
+            ctx.pileup_push(b)
+        ctx.pileup_end()
+        assert np.array_equal(ctx.array(api.ARR_RAW_DEPTH), want["raw"]), "pileup depth"
+        calls = ctx.run()
+        st = ctx.chr_stats()
+        assert st.rdmedian == want["stats"][0] and st.rdsd == want["stats"][1]
+        assert_calls_equal(calls, want["calls"], "bam path")
+        if calls:
+            assert (st.isize_mean, st.isize_sd) == oracle_isize(oracle, reads, len(fa))
+        return calls, st
+    finally:
+        ctx.close()

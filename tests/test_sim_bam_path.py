@@ -1,0 +1,51 @@
+"""BAM-input path (pileup, insert-size sample, RP / Q0 counts) of the CUDA sources under the fiber emulator,
+against the oracle on the same read batches."""
+import numpy as np
+import pytest
+
+from common import run_bam_case
+from rsicnv_b200 import synth
+
+L = 10_600_000   # every BAM contig must exceed 10 Mbp: bam_rd_pr_stats samples from 10 Mbp on (SURVEY hard part 9)
+
+
+@pytest.fixture(scope="module")
+def case():
+    fa = synth.make_fasta(L, 3)
+    reads, ev = synth.make_reads(L, 3, fa, coverage=12, n_events=6, lens=(3000, 8000, 20000))
+    return fa, reads, ev
+
+
+def test_bam_path_matches_oracle(case, sim_lib, oracle):
+    fa, reads, _ = case
+    calls, st = run_bam_case(sim_lib, oracle, fa, reads, n_batches=3, min_baseQ=10, minq=0)
+    assert len(calls) >= 3 and any(c.rp > 0 for c in calls)
+
+
+def test_pileup_filters(sim_lib, oracle):
+    """mapq / base-quality thresholds, CIGARs with =/X/N/H/P ops and reads hanging over the contig end"""
+    from bind import oracle_pileup
+    from rsicnv_b200 import api
+    Ls = 300_000
+    fa = synth.make_fasta(Ls, 8)
+    reads, _ = synth.make_reads(Ls, 8, fa, coverage=8, n_events=0, frac_mapq0=0.3, frac_lowq=0.5)
+    rng = np.random.default_rng(5)
+    # rewrite some CIGARs to exotic but legal shapes of the same query length
+    cig = reads["cigar"].copy(); co = reads["cigar_off"]
+    one = np.flatnonzero(np.diff(co.astype(np.int64)) == 3)
+    for r in one[:: 3]:
+        k = co[r]
+        cig[k] = (50 << 4) | 7; cig[k + 1] = (3 << 4) | 3; cig[k + 2] = (50 << 4) | 0      # 50= 3N 50M
+    for r in one[1:: 3]:
+        k = co[r]
+        cig[k] = (5 << 4) | 5; cig[k + 1] = (60 << 4) | 0; cig[k + 2] = (40 << 4) | 8      # 5H 60M 40X
+    reads["cigar"] = cig
+    # reads that run past the end of the contig, and one at position 0 (dropped by the reference)
+    reads["pos"][-50:] = np.sort(rng.integers(Ls - 80, Ls - 1, 50)).astype(np.int32)
+    reads["pos"][0] = 0
+    for minq, Q in ((0, 13), (20, 0), (1, 31)):
+        oracle.set_params(minq=minq, min_baseQ=Q)
+        want = oracle_pileup(oracle, reads, Ls)
+        with api.Context(lib=sim_lib, minq=minq, min_baseQ=Q) as ctx:
+            ctx.set_reference(fa); ctx.pileup_begin(); ctx.pileup_push(reads); ctx.pileup_end()
+            assert np.array_equal(ctx.array(api.ARR_RAW_DEPTH), want), (minq, Q)
