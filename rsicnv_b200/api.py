@@ -253,7 +253,9 @@ class Context:
 
     DEBUG_FIELDS = ("err", "rd_min", "rd_max", "pos_sum", "pos_cnt", "rdmean", "cap_median", "cap_thr", "capv", "hist_base", "chist_R", "rdmedian",
                     "rdsd", "rdmad", "max_binsum", "gstar", "gc_tab80", "gc_tab90", "gc_tab100", "gc_cnt90", "tmedian", "tsigma", "tlamda", "Lmax",
-                    "lbreak_del", "lbreak_dup", "n_runs", "n_nonzero", "st_lo", "st_hi", "lvl0_sum", "filt_on")
+                    "lbreak_del", "lbreak_dup", "n_runs", "n_nonzero", "st_lo", "st_hi", "lvl0_sum", "filt_on", "cand_redone",
+                    "cp_tests", "cp_left", "cp_reverse", "cp_right", "cp_prefix", "cp_runmean", "cp_hist_ref", "cp_hist_cnv", "cp_sums", "cp_edge_refine",
+                    "cp_merge", "cp_final", "cp_blocks", "cp_sort", "cp_cnvlen_total", "cp_nref_total")
 
     def debug_state(self) -> dict:
         a = (C.c_double * 64)()

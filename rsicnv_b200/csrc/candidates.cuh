@@ -46,7 +46,18 @@ struct CandScratch {
   unsigned* hist;  int hist_cap;  // histogram buckets (global memory fallback)
   unsigned* shist; int shist_cap; // histogram buckets in shared memory (preferred when they fit)
   int* err;                       // sticky error bits (CAND_ERR_*)
+  long long* prof;                // optional per-phase clock64 totals (thread 0), 16 slots, may be null
 };
+
+#if defined(__CUDACC__)
+RSI_DEV long long cand_clock() { return clock64(); }
+#else
+inline long long cand_clock() { return 0; }
+#endif
+// phase timer: thread 0 adds the elapsed clocks since *t0 to slot k and restarts the timer
+RSI_DEV void cand_tick(const Cta& c, const CandScratch& S, int k, long long* t0) {
+  if (S.prof && c.tid == 0) { const long long t = cand_clock(); S.prof[k] += t - *t0; *t0 = t; }
+}
 
 RSI_DEV Cnv cnv_default() {  // cnv_st(), rsi.h:30-50
   Cnv c;
@@ -167,30 +178,57 @@ RSI_DEV bool nb_accept(int v, int flag, double up, double lo) {
 }
 
 // Scan positions lo..hi (dir=+1) or hi..lo (dir=-1); store the first `want` accepted values to
-// dst[0..), in scan order.  Returns how many were stored (block-uniform).  Every thread takes a
-// CONTIGUOUS slice of a super-chunk sized to what is still wanted, so one block scan serves
-// thousands of positions.
+// dst[0..), in scan order.  Returns how many were stored (block-uniform).
+#if defined(RSI_CTA_PARALLEL)
+// Every WARP takes a contiguous segment of a super-chunk sized to what is still wanted; lanes read
+// stride-1 (coalesced), __ballot_sync + popc give the compaction offsets, one exchange of the 32 warp
+// counts per super-chunk.
 RSI_DEVN int cta_collect(const Cta& c, const int* RD, int lo, int hi, int dir, int flag, double up, double lw, int want, int* dst) {
-  int got = 0;
+  int got = 0, pos = 0;
   const int len = hi - lo + 1;
-  int pos = 0;
+  const int lane = c.tid & 31, warp = c.tid >> 5, nw = c.nthr >> 5;
+  int* slots = reinterpret_cast<int*>(c.red);
   while (pos < len && got < want) {
     int sc = want - got + c.nthr;               // nearly every position is accepted
     if (sc > len - pos) sc = len - pos;
-    const int per = (sc + c.nthr - 1) / c.nthr;
-    const int j0 = pos + (c.tid * per < sc ? c.tid * per : sc), j1 = pos + ((c.tid + 1) * per < sc ? (c.tid + 1) * per : sc);
+    const int seg = (((sc + nw - 1) / nw) + 31) & ~31;
+    const int w0 = pos + (warp * seg < sc ? warp * seg : sc), w1 = pos + ((warp + 1) * seg < sc ? (warp + 1) * seg : sc);
     int cnt = 0;
-#pragma unroll 8
-    for (int j = j0; j < j1; ++j) cnt += nb_accept(RD[dir > 0 ? lo + j : hi - j], flag, up, lw) ? 1 : 0;
-    int tot, ex = c.scan_excl(cnt, &tot);
-    int w = got + ex;
-    for (int j = j0; j < j1 && w < want; ++j) { const int v = RD[dir > 0 ? lo + j : hi - j]; if (nb_accept(v, flag, up, lw)) dst[w++] = v; }
+    for (int j0 = w0; j0 < w1; j0 += 32) {
+      const int j = j0 + lane;
+      const bool ok = j < w1 && nb_accept(RD[dir > 0 ? lo + j : hi - j], flag, up, lw);
+      cnt += __popc(__ballot_sync(0xffffffffu, ok));
+    }
+    c.sync();
+    if (lane == 0) slots[warp] = cnt;
+    c.sync();
+    int base = 0, tot = 0;
+    for (int w = 0; w < nw; ++w) { const int v = slots[w]; if (w < warp) base += v; tot += v; }
+    int off = got + base;
+    for (int j0 = w0; j0 < w1 && off < want; j0 += 32) {
+      const int j = j0 + lane;
+      int v = 0; bool ok = false;
+      if (j < w1) { v = RD[dir > 0 ? lo + j : hi - j]; ok = nb_accept(v, flag, up, lw); }
+      const unsigned bm = __ballot_sync(0xffffffffu, ok);
+      const int my = off + __popc(bm & ((1u << lane) - 1u));
+      if (ok && my < want) dst[my] = v;
+      off += __popc(bm);
+    }
     got = got + tot < want ? got + tot : want;
     pos += sc;
   }
   c.sync();
   return got;
 }
+#else
+RSI_DEVN int cta_collect(const Cta& c, const int* RD, int lo, int hi, int dir, int flag, double up, double lw, int want, int* dst) {
+  int got = 0;
+  const int len = hi - lo + 1;
+  for (int j = 0; j < len && got < want; ++j) { const int v = RD[dir > 0 ? lo + j : hi - j]; if (nb_accept(v, flag, up, lw)) dst[got++] = v; }
+  (void)c;
+  return got;
+}
+#endif
 // First accepted position in scan order, or -1 (block-uniform).
 RSI_DEVN int cta_find_first(const Cta& c, const int* RD, int lo, int hi, int dir, int flag, double up, double lw) {
   const int len = hi - lo + 1;
@@ -206,26 +244,55 @@ RSI_DEVN int cta_find_first(const Cta& c, const int* RD, int lo, int hi, int dir
   return -1;
 }
 
+// pref[0] = 0, pref[j+1] = ref[0] + .. + ref[j]  (exact integer prefix sums)
+#if defined(RSI_CTA_PARALLEL)
+RSI_DEVN void cta_prefix_i32(const Cta& c, const int* ref, int n, long long* pref) {
+  const int lane = c.tid & 31, warp = c.tid >> 5, nw = c.nthr >> 5;
+  const int seg = (((n + nw - 1) / nw) + 31) & ~31;
+  const int w0 = warp * seg < n ? warp * seg : n, w1 = (warp + 1) * seg < n ? (warp + 1) * seg : n;
+  long long loc = 0;
+#pragma unroll 4
+  for (int j = w0 + lane; j < w1; j += 32) loc += (long long)ref[j];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) loc += __shfl_xor_sync(0xffffffffu, loc, o);
+  long long* slots = reinterpret_cast<long long*>(c.red);
+  c.sync();
+  if (lane == 0) slots[warp] = loc;
+  c.sync();
+  long long carry = 0;
+  for (int w = 0; w < warp; ++w) carry += slots[w];
+  if (c.tid == 0) pref[0] = 0;
+  for (int j0 = w0; j0 < w1; j0 += 32) {
+    const int j = j0 + lane;
+    long long inc = j < w1 ? (long long)ref[j] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const long long u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+    if (j < w1) pref[j + 1] = carry + inc;
+    carry += __shfl_sync(0xffffffffu, inc, 31);
+  }
+  c.sync();
+}
+#else
+RSI_DEVN void cta_prefix_i32(const Cta& c, const int* ref, int n, long long* pref) {
+  long long run = 0; pref[0] = 0;
+  for (int j = 0; j < n; ++j) { run += ref[j]; pref[j + 1] = run; }
+  (void)c;
+}
+#endif
+
 // isitcnv: statistics of the candidate against the running mean of its neighbours; fills *out.
 RSI_DEVN void cnv_test_stats(const Cta& c, const CandCfg& P, const CandScratch& S, const int* ref, int nref, const int* cnv, int ncnv, Cnv* out) {
   const int d = ncnv, nr = nref - d;
+  long long t0 = cand_clock();
   if (nr <= 0 || d <= 0) {  // the reference aborts here (Array bounds throw)
     if (c.tid == 0) { out->status = -9; out->geno = 0; *S.err |= CAND_ERR_DEGENERATE; }
     c.sync();
     return;
   }
   // exact integer prefix sums of the neighbours (the reference slides a double sum of ints: exact)
-  {
-    const int per = (nref + c.nthr - 1) / c.nthr;
-    const int j0 = c.tid * per < nref ? c.tid * per : nref, j1 = (c.tid + 1) * per < nref ? (c.tid + 1) * per : nref;
-    long long loc = 0, tot;
-#pragma unroll 8
-    for (int j = j0; j < j1; ++j) loc += (long long)ref[j];
-    long long run = c.scan_excl(loc, &tot);
-    if (c.tid == 0) S.pref[0] = 0;
-    for (int j = j0; j < j1; ++j) { run += (long long)ref[j]; S.pref[j + 1] = run; }
-  }
+  cta_prefix_i32(c, ref, nref, S.pref);
   c.sync();
+  cand_tick(c, S, 4, &t0);
   double s1 = 0.0, s2 = 0.0;
   {
     const long long* __restrict__ pf = S.pref;
@@ -250,13 +317,17 @@ RSI_DEVN void cnv_test_stats(const Cta& c, const CandCfg& P, const CandScratch& 
   }
   c.sync();
   s1 = c.reduce(s1, SumOp()); s2 = c.reduce(s2, SumOp());
+  cand_tick(c, S, 5, &t0);
   double rq[3], cq[3];
   cta_hist_stat(c, S, S.rm, nr, 0.01, rq);
+  cand_tick(c, S, 6, &t0);
   cta_hist_stat(c, S, cnv, ncnv, 1.0, cq);
+  cand_tick(c, S, 7, &t0);
   long long a1 = 0, a2 = 0;
 #pragma unroll 4
   for (int i = c.tid; i < ncnv; i += c.nthr) { long long v = cnv[i]; a1 += v; a2 += v * v; }
   a1 = c.reduce(a1, SumOp()); a2 = c.reduce(a2, SumOp());
+  cand_tick(c, S, 8, &t0);
   if (c.tid == 0) {
     double rmean = s1 / double(nr);
     double rsd = sqrt(s2 / double(nr) - rmean * rmean);
@@ -305,6 +376,8 @@ RSI_DEVN void cnv_test(const Cta& c, const CandCfg& P, const CandScratch& S, con
   const double up = P.rdmedian * 3.0, lw = P.rdmedian * 0.15;
 
   // ---- left side, nearest first, then reversed into ascending position order
+  long long t0 = cand_clock();
+  if (S.prof && c.tid == 0) { S.prof[0] += 1; S.prof[14] += cnvlen; }
   int i = start - buffer, idx = ci - 1;
   while (i > 0 && idx > 0 && i < V.at(idx).start) --idx;
   while (idx > 0 && V.at(idx).status == -9) --idx;
@@ -332,8 +405,10 @@ RSI_DEVN void cnv_test(const Cta& c, const CandCfg& P, const CandScratch& S, con
       else { i = lo; idx = -1; }
     }
   }
+  cand_tick(c, S, 1, &t0);
   for (int j = c.tid; j < nleft / 2; j += c.nthr) { int a = S.ref[j], b = S.ref[nleft - 1 - j]; S.ref[j] = b; S.ref[nleft - 1 - j] = a; }
   c.sync();
+  cand_tick(c, S, 2, &t0);
 
   // ---- right side, ascending
   int kk = nleft;
@@ -364,6 +439,8 @@ RSI_DEVN void cnv_test(const Cta& c, const CandCfg& P, const CandScratch& S, con
     c.sync();
     return;
   }
+  cand_tick(c, S, 3, &t0);
+  if (S.prof && c.tid == 0) S.prof[15] += kk;
   const int* ref = S.ref; int nref = kk;
   const int* cnv = RD + start; int ncnv = cnvlen;
   if (nref + ncnv > pts) {  // sub-sample both to ~pts points, rsi.cpp:264-282
@@ -415,14 +492,40 @@ RSI_DEVN void edge_refine(const Cta& c, const int* RD, int n, Cnv* cv) {
   ValIdx tailbest; tailbest.v = 0.0; tailbest.i = -1;
   const double hs = type == RSIGPU_TYPE_DEL ? 1.0 : -1.0;  // DEL: head max / tail min; DUP: head min / tail max
   {
-    // dd(j) = dd(0) + sum_{1<=k<=j} inc(k); every thread owns a contiguous slice of j
-    const int per = (ndd + c.nthr - 1) / c.nthr;
-    const int j0 = c.tid * per < ndd ? c.tid * per : ndd, j1 = (c.tid + 1) * per < ndd ? (c.tid + 1) * per : ndd;
-    long long loc = 0, tot;
-    for (int j = j0; j < j1; ++j) if (j >= 1) { const int p = ns + j; loc += -(long long)RD[p - 1 - len] + 2ll * RD[p - 1] - (long long)RD[p - 1 + len]; }
-    long long run = dd0 + c.scan_excl(loc, &tot);
+    // dd(j) = dd(0) + sum_{1<=k<=j} inc(k); a warp owns a contiguous slice of j, lanes stride-1
     const bool typed = type == RSIGPU_TYPE_DEL || type == RSIGPU_TYPE_DUP;
-    for (int j = j0; j < j1; ++j) {
+#if defined(RSI_CTA_PARALLEL)
+    const int lane = c.tid & 31, warp = c.tid >> 5, nw = c.nthr >> 5;
+    const int seg = (((ndd + nw - 1) / nw) + 31) & ~31;
+    const int w0 = warp * seg < ndd ? warp * seg : ndd, w1 = (warp + 1) * seg < ndd ? (warp + 1) * seg : ndd;
+    long long loc = 0;
+#pragma unroll 2
+    for (int j = w0 + lane; j < w1; j += 32) if (j >= 1) { const int p = ns + j; loc += -(long long)RD[p - 1 - len] + 2ll * RD[p - 1] - (long long)RD[p - 1 + len]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) loc += __shfl_xor_sync(0xffffffffu, loc, o);
+    long long* slots = reinterpret_cast<long long*>(c.red);
+    c.sync();
+    if (lane == 0) slots[warp] = loc;
+    c.sync();
+    long long carry = dd0;
+    for (int w = 0; w < warp; ++w) carry += slots[w];
+    for (int j0 = w0; j0 < w1; j0 += 32) {
+      const int j = j0 + lane;
+      long long inc = 0;
+      if (j < w1 && j >= 1) { const int p = ns + j; inc = -(long long)RD[p - 1 - len] + 2ll * RD[p - 1] - (long long)RD[p - 1 + len]; }
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const long long u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+      if (j < w1 && typed) {
+        const double ddj = (double)(carry + inc);
+        if (j < 2 * disp && hs * ddj > headbest.v) { headbest.v = hs * ddj; headbest.i = j; }
+        if (j >= tail0 && -hs * ddj > tailbest.v) { tailbest.v = -hs * ddj; tailbest.i = j; }
+      }
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    c.sync();
+#else
+    long long run = dd0;
+    for (int j = 0; j < ndd; ++j) {
       if (j >= 1) { const int p = ns + j; run += -(long long)RD[p - 1 - len] + 2ll * RD[p - 1] - (long long)RD[p - 1 + len]; }
       const double ddj = (double)run;
       if (typed) {
@@ -430,6 +533,7 @@ RSI_DEVN void edge_refine(const Cta& c, const int* RD, int n, Cnv* cv) {
         if (j >= tail0 && -hs * ddj > tailbest.v) { tailbest.v = -hs * ddj; tailbest.i = j; }
       }
     }
+#endif
   }
   // per-thread candidates are each thread's first strict maximum in ascending j; merge with first-index ties
   if (headbest.i < 0) { headbest.v = 0.0; headbest.i = 0x7fffffffffffll; }
@@ -654,18 +758,25 @@ RSI_DEV void dump_list(const Cta& c, const Cnv* list, int n, Cnv* dst, int* ndst
   c.sync();
 }
 
-// detectcnv from areblockscnv onwards (rsi.cpp:1839-1931).  `list` holds the rsi segments of one
-// transformation in bin coordinates (nl of them); the result (reference coordinates) is left in
-// `list`, its length returned.  For -ALL the caller runs blocks_test per transformation and passes
-// skip_blocks = 1 with the concatenated list.
-RSI_DEVN int candidates_main(const Cta& c, CandCfg P, const CandScratch& S, const int* RD, int n, const int* medint, const int* status, int nb,
-                             const int* nbeg, const int* nend, int nn, Cnv* list, int nl, Cnv* tmp, Cnv* ov, const CandDumps& D, int skip_blocks) {
+// detectcnv from areblockscnv onwards (rsi.cpp:1839-1931), in three stages so that the per-call work
+// between them can run one call per thread block:
+//   stage A (one block): areblockscnv on the bin arrays, sort, bins -> bases
+//   [edge_refine x2 per call: independent calls -> one block each]
+//   stage B (one block): sort, mergesegments, sort; scratch offsets for the speculative final tests
+//   [final isitcnvwrap per call, speculatively assuming that no earlier call fails: one block each]
+//   stage C (one block): accept the speculative results up to the first failing call, redo the rest in
+//                        order, score, drop N overlaps, map back to reference coordinates
+// `list` holds the rsi segments of one transformation in bin coordinates (nl of them); the result
+// (reference coordinates) is left in `list`, its length returned.
+RSI_DEVN int cand_stage_a(const Cta& c, const CandCfg& P, const CandScratch& S, int n, const int* medint, const int* status, int nb,
+                          Cnv* list, int nl, Cnv* tmp, Cnv* ov, const CandDumps& D, int skip_blocks) {
+  long long tm = cand_clock();
   if (!skip_blocks) blocks_test(c, P, S, medint, status, nb, list, nl, ov);
+  cand_tick(c, S, 12, &tm);
   dump_list(c, list, nl, D.blocks, D.n_blocks, D.cap);
   list_sort(c, list, nl, tmp);
-  // bins -> bases
   c.sync();
-  if (c.tid == 0) {
+  if (c.tid == 0) {   // bins -> bases
     int w = 0;
     for (int j = 0; j < nl; ++j) {
       Cnv x = list[j];
@@ -682,28 +793,84 @@ RSI_DEVN int candidates_main(const Cta& c, CandCfg P, const CandScratch& S, cons
     nl = w;
   }
   nl = cta_bcast(c, nl, 2);
-  for (int rep = 0; rep < 2; ++rep) for (int j = 0; j < nl; ++j) edge_refine(c, RD, n, &list[j]);
+  cand_tick(c, S, 13, &tm);
+  return nl;
+}
+
+// number of scratch entries isitcnvwrap may gather for a call on the per-base array (capacity of RDref, rsi.cpp:199)
+RSI_DEV long long cand_ref_need(const CandCfg& P, const Cnv& x) {
+  int d = x.end - x.start + 1;
+  if (d < P.m * P.minmlen) d = (int)(P.m * P.minmlen);
+  return (long long)(P.chklen * d * 2) + 64;
+}
+
+RSI_DEVN int cand_stage_b(const Cta& c, const CandCfg& P, const CandScratch& S, const int* RD, int n, Cnv* list, int nl, Cnv* tmp, Cnv* ov,
+                          const CandDumps& D, long long* spec_off, long long spec_cap, int* spec_on) {
+  long long tm = cand_clock();
   list_sort(c, list, nl, tmp);
   dump_list(c, list, nl, D.premerge, D.n_premerge, D.cap);
   nl = merge_segments(c, P, S, RD, n, list, nl, ov);
+  cand_tick(c, S, 10, &tm);
   list_sort(c, list, nl, tmp);
   dump_list(c, list, nl, D.merged, D.n_merged, D.cap);
-  // final test on the per-base array, score, N-overlap filter, coordinates back to the reference
-  for (int j = 0; j < nl; ++j) {
-    cnv_test(c, P, S, RD, n, plain_view(list, nl), j, &list[j]);
-    if (c.tid == 0) {
+  if (spec_off && c.tid == 0) {   // disjoint scratch slices for the speculative per-call tests
+    long long off = 0;
+    for (int j = 0; j < nl; ++j) { spec_off[j] = off; off += cand_ref_need(P, list[j]); }
+    spec_off[nl] = off;
+    *spec_on = off <= spec_cap ? 1 : 0;
+  }
+  c.sync();
+  return nl;
+}
+
+// one call's final test into res[j] (the list itself stays as it was, so every block sees the same neighbours)
+RSI_DEVN void cand_final_one(const Cta& c, const CandCfg& P, const CandScratch& S, const int* RD, int n, const Cnv* list, int nl, int j, Cnv* res) {
+  if (c.tid == 0) res[j] = list[j];
+  c.sync();
+  ListView V = plain_view(list, nl); V.oi0 = j; V.o0 = &res[j];
+  cnv_test(c, P, S, RD, n, V, j, &res[j]);
+}
+
+RSI_DEVN int cand_stage_c(const Cta& c, const CandCfg& P, const CandScratch& S, const int* RD, int n, const int* nbeg, const int* nend, int nn,
+                          Cnv* list, int nl, const Cnv* res, int spec_valid, int* first_bad_out = nullptr) {
+  long long tm = cand_clock();
+  // The final tests run in list order and a call that FAILS (status -9) changes the neighbour walk of the
+  // calls after it.  The speculative results assumed that nobody failed: they are exact up to and including
+  // the first failing call; from there on the tests are redone in order.
+  int first_bad = nl;
+  if (spec_valid) {
+    if (c.tid == 0) { for (int j = 0; j < nl; ++j) if (res[j].status == -9) { first_bad = j; break; } }
+    first_bad = cta_bcast(c, first_bad, 5);
+    if (first_bad_out && c.tid == 0) *first_bad_out = nl - first_bad;   // number of calls redone in order
+    const int upto = first_bad < nl ? first_bad + 1 : nl;
+    for (int j = c.tid; j < upto; j += c.nthr) list[j] = res[j];
+    c.sync();
+  } else first_bad = -1;
+  for (int j = (spec_valid ? first_bad + 1 : 0); j < nl; ++j) cnv_test(c, P, S, RD, n, plain_view(list, nl), j, &list[j]);
+  if (c.tid == 0) {
+    for (int j = 0; j < nl; ++j) {
       Cnv& x = list[j];
       const double len = double(x.end - x.start + 1) / double(P.m);
       x.score = (x.cnvmed - P.rdmedian) * sqrt(len);
       const int p1 = expand_coord(x.start, nbeg, nend, nn), p2 = expand_coord(x.end, nbeg, nend, nn);
       for (int k = 0; k < nn; ++k) { int a = p1 > nbeg[k] ? p1 : nbeg[k], b = p2 < nend[k] ? p2 : nend[k]; if (a <= b) x.status = -9; }
     }
-    c.sync();
   }
+  c.sync();
+  cand_tick(c, S, 11, &tm);
   nl = list_drop_deleted(c, list, nl);
   if (c.tid == 0) for (int j = 0; j < nl; ++j) { list[j].start = expand_coord(list[j].start, nbeg, nend, nn); list[j].end = expand_coord(list[j].end, nbeg, nend, nn); }
   c.sync();
   return nl;
+}
+
+// the whole stage in one block (tests/hostsim/sim.cpp; also the reference order of operations)
+RSI_DEVN int candidates_main(const Cta& c, CandCfg P, const CandScratch& S, const int* RD, int n, const int* medint, const int* status, int nb,
+                             const int* nbeg, const int* nend, int nn, Cnv* list, int nl, Cnv* tmp, Cnv* ov, const CandDumps& D, int skip_blocks) {
+  nl = cand_stage_a(c, P, S, n, medint, status, nb, list, nl, tmp, ov, D, skip_blocks);
+  for (int rep = 0; rep < 2; ++rep) for (int j = 0; j < nl; ++j) edge_refine(c, RD, n, &list[j]);
+  nl = cand_stage_b(c, P, S, RD, n, list, nl, tmp, ov, D, nullptr, 0, nullptr);
+  return cand_stage_c(c, P, S, RD, n, nbeg, nend, nn, list, nl, nullptr, 0);
 }
 
 }  // namespace rsigpu

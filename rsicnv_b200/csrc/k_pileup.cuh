@@ -53,6 +53,19 @@ __global__ void k_read_ends(ReadSoA R, int* max_extent, int* sorted_bad) {
   if (bad) atomicOr(sorted_bad, 1);
 }
 
+// per-byte `quality >= Q` of four packed qualities: 0xff per passing byte
+__device__ __forceinline__ u32 qual_ge4(u32 w, u32 thr4, bool all, bool none) {
+  if (all) return 0xffffffffu;
+  if (none) return 0u;
+#if defined(RSI_SIM)
+  u32 m = 0;
+  for (int k = 0; k < 4; ++k) if (((w >> (8 * k)) & 0xff) >= ((thr4 >> (8 * k)) & 0xff)) m |= 0xffu << (8 * k);
+  return m;
+#else
+  return __vcmpgeu4(w, thr4);
+#endif
+}
+
 __global__ void __launch_bounds__(PU_NT) k_pileup_tile(ReadSoA R, int* __restrict__ rd, int L, int minq, int min_baseQ, const int* max_extent) {
   RSI_CTA_SETUP(c);
   __shared__ int diff[PU_T + 1 + (PU_T + 1) / 32 + 1];   // entry i lives at i + i/32: conflict-free 32-per-thread scan
@@ -60,6 +73,8 @@ __global__ void __launch_bounds__(PU_NT) k_pileup_tile(ReadSoA R, int* __restric
   __shared__ int s_r0, s_r1;
   const int ntiles = (L + PU_T - 1) / PU_T;
   const int ext = *max_extent;
+  const bool q_all = min_baseQ <= 0, q_none = min_baseQ > 255;
+  const u32 qthr4 = (u32)(min_baseQ & 0xff) * 0x01010101u;
   for (int tile = (int)blockIdx.x; tile < ntiles; tile += (int)gridDim.x) {
     const int t0 = tile * PU_T, t1 = imin(t0 + PU_T, L);
     c.sync();
@@ -93,10 +108,20 @@ __global__ void __launch_bounds__(PU_NT) k_pileup_tile(ReadSoA R, int* __restric
           // maximal stretches of bases with quality >= Q, clipped to the tile and to L
           const int jb = imax(0, t0 - p), je = imin((int)l, imin(t1, L) - p);
           int open = -1;
-          for (int j = jb; j < je; ++j) {
-            const bool ok = (int)qual[q + (u32)j] >= min_baseQ;
+          const u8* qp = qual + q;
+          int j = jb;
+          // bytes up to the next 4-byte boundary, then whole words (four quality tests per compare), then the tail
+          while (j < je) {
+            if ((((size_t)(qp + j)) & 3) == 0 && j + 4 <= je) {
+              const u32 w = *reinterpret_cast<const u32*>(qp + j);
+              const u32 m = qual_ge4(w, qthr4, q_all, q_none);
+              if (m == 0xffffffffu) { if (open < 0) open = j; j += 4; continue; }
+              if (m == 0u) { if (open >= 0) { atomicAdd(&diff[PU_DI(p + open - t0)], 1); atomicAdd(&diff[PU_DI(p + j - t0)], -1); open = -1; } j += 4; continue; }
+            }
+            const bool ok = (int)qp[j] >= min_baseQ;
             if (ok && open < 0) open = j;
             if (!ok && open >= 0) { atomicAdd(&diff[PU_DI(p + open - t0)], 1); atomicAdd(&diff[PU_DI(p + j - t0)], -1); open = -1; }
+            ++j;
           }
           if (open >= 0) { atomicAdd(&diff[PU_DI(p + open - t0)], 1); atomicAdd(&diff[PU_DI(p + je - t0)], -1); }
         }
@@ -124,81 +149,105 @@ __global__ void __launch_bounds__(PU_NT) k_pileup_tile(ReadSoA R, int* __restric
 // ---------------------------------------------------------------------------------------------
 // Insert-size sample.  `keep`-filtered reads in file order from the first one overlapping 10 Mbp;
 // sums run up to and including the read that trips a stop rule.
+enum { IS_K = 8 };   // consecutive reads per thread and iteration
 __global__ void __launch_bounds__(1024) k_isize_stats(ReadSoA R, int tid_len, const int* max_extent, DevState* st) {
   RSI_CTA_SETUP(c);
-  __shared__ int s_lastpos, s_segstart, s_segidx, s_stop;
+  __shared__ int s_lastpos, s_segstart, s_segidx;
   const u32 beg = 10000000u, end = 349250621u;
   i64 lo = 0, hi = R.n;
   { const int want = (int)beg - *max_extent - 1; while (lo < hi) { i64 mid = (lo + hi) >> 1; if (R.pos[mid] < want) lo = mid + 1; else hi = mid; } }
   const i64 r_first = lo;
-  if (c.tid == 0) { s_lastpos = -10000; s_segstart = 0; s_segidx = 0; s_stop = 0; }
+  if (c.tid == 0) { s_lastpos = -10000; s_segstart = 0; s_segidx = 0; }
   c.sync();
+  const int lane = c.tid & 31, warp = c.tid >> 5;
   double s = 0, s2 = 0, cn = 0;
   i64 kept_before = 0;   // kept reads before this chunk
-  for (i64 r0 = r_first; r0 < R.n; r0 += c.nthr) {
-    const i64 r = r0 + c.tid;
-    bool kept = false, prop = false, stopA = false; int pos = 0, isz = 0;
-    if (r < R.n) {
-      pos = R.pos[r];
-      const u32 re = (u32)R.calend[r];
-      const bool overl = (u32)pos < end && re > beg;
-      const int mt = R.mtid[r]; const int fl = R.flag[r];
-      kept = overl && !(mt != R.tid && mt > 0) && !(fl & BF_SECONDARY) && !(fl & BF_DUP);
-      prop = kept && (fl & BF_PROPER) && mt == R.tid;
-      isz = R.isize[r];
-      // bam_calend proper for the stop rule (reads without CIGAR: pos)
-      const int rpe = (R.cigar_off[r + 1] > R.cigar_off[r]) ? (int)re : pos;
-      stopA = kept && (pos >= tid_len || rpe >= tid_len);
+  for (i64 r0 = r_first; r0 < R.n; r0 += (i64)c.nthr * IS_K) {
+    const i64 rb = r0 + (i64)c.tid * IS_K;
+    int pos[IS_K], isz[IS_K]; bool kept[IS_K], prop[IS_K], stopA[IS_K], past[IS_K];
+    int nkept = 0, lastkept = -0x7fffffff;
+#pragma unroll
+    for (int k = 0; k < IS_K; ++k) {
+      const i64 r = rb + k;
+      kept[k] = prop[k] = stopA[k] = past[k] = false; pos[k] = 0; isz[k] = 0;
+      if (r < R.n) {
+        pos[k] = R.pos[r];
+        const u32 re = (u32)R.calend[r];
+        const bool overl = (u32)pos[k] < end && re > beg;
+        const int mt = R.mtid[r]; const int fl = R.flag[r];
+        kept[k] = overl && !(mt != R.tid && mt > 0) && !(fl & BF_SECONDARY) && !(fl & BF_DUP);
+        prop[k] = kept[k] && (fl & BF_PROPER) && mt == R.tid;
+        isz[k] = R.isize[r];
+        const int rpe = (R.cigar_off[r + 1] > R.cigar_off[r]) ? (int)re : pos[k];   // bam_calend proper
+        stopA[k] = kept[k] && (pos[k] >= tid_len || rpe >= tid_len);
+        past[k] = (u32)pos[k] >= end;          // the iterator stops at the first read with pos >= end
+        if (kept[k]) { ++nkept; lastkept = pos[k]; }
+      }
     }
-    // past the region: the iterator stops at the first read with pos >= end
-    const int past = (r < R.n && (u32)pos >= end) ? 1 : 0;
-    // rank among the kept reads, gap starts
+    // exclusive sum-scan of kept counts and exclusive max-scan of the last kept position across threads
     int tot;
-    const int ex = c.scan_excl(kept ? 1 : 0, &tot);
-    const i64 kidx = kept_before + ex;
-    // previous kept position: max-scan of positions (sorted input => the previous kept read has the largest pos so far)
-    int prevpos = kept ? pos : -0x7fffffff;
-    {  // inclusive max-scan across the block, then shift by one kept element
-      int v = prevpos;
-      const int lane = c.tid & 31, warp = c.tid >> 5;
+    const int ex = c.scan_excl(nkept, &tot);
+    int prevpos;
+    {
+      int v = lastkept;
       for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v = imax(v, u); }
       int* slots = reinterpret_cast<int*>(c.red);
       c.sync(); if (lane == 31) slots[warp] = v; c.sync();
       int pre = -0x7fffffff; for (int w = 0; w < warp; ++w) pre = imax(pre, slots[w]);
       int upv = __shfl_up_sync(0xffffffffu, v, 1);
-      prevpos = imax(pre, lane ? upv : -0x7fffffff);   // max over earlier threads of this chunk
+      prevpos = imax(pre, lane ? upv : -0x7fffffff);
       c.sync();
     }
     prevpos = imax(prevpos, s_lastpos);
-    const bool gap = kept && pos > prevpos + 1000;
-    // segment start (position and kept-rank) of the most recent gap at or before each kept read
-    i64 key = gap ? ((kidx << 32) | (i64)(u32)pos) : -1;     // max-scan on the kept rank
+    // gaps inside the thread's reads; the most recent gap key = (kept rank << 32 | pos)
+    i64 kidx[IS_K]; i64 key = -1; int pp = prevpos; i64 kk = kept_before + ex;
+    i64 keyat[IS_K];
+#pragma unroll
+    for (int k = 0; k < IS_K; ++k) {
+      kidx[k] = kk;
+      if (kept[k]) { if (pos[k] > pp + 1000) key = (kk << 32) | (i64)(u32)pos[k]; pp = pos[k]; ++kk; }
+      keyat[k] = key;    // latest gap at or before read k within this thread (or -1)
+    }
+    // inclusive max-scan of the threads' last keys -> exclusive prefix for this thread
+    i64 prekey;
     {
       i64 v = key;
-      const int lane = c.tid & 31, warp = c.tid >> 5;
       for (int o = 1; o < 32; o <<= 1) { i64 u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v = lmax(v, u); }
       i64* slots = reinterpret_cast<i64*>(c.red);
       c.sync(); if (lane == 31) slots[warp] = v; c.sync();
       i64 pre = -1; for (int w = 0; w < warp; ++w) pre = lmax(pre, slots[w]);
-      key = lmax(v, pre);
+      i64 upv = __shfl_up_sync(0xffffffffu, v, 1);
+      prekey = lmax(pre, lane ? upv : (i64)-1);
       c.sync();
     }
-    int seg_idx, seg_pos;
-    if (key >= 0) { seg_idx = (int)(key >> 32); seg_pos = (int)(key & 0xffffffff); } else { seg_idx = s_segidx; seg_pos = s_segstart; }
-    const i64 count = kidx - seg_idx + 1;
-    const bool stopB = kept && !stopA && (count > 1000000 || (pos - seg_pos) > 1000000);
-    int stop_at = (stopA || stopB || past) ? c.tid : 0x7fffffff;
-    stop_at = c.reduce(stop_at, MinOp());
-    if (prop && c.tid <= stop_at && !(past && c.tid == stop_at)) {
-      s += (double)(isz < 0 ? -isz : isz);
-      s2 += (double)(int)((u32)isz * (u32)isz);
-      cn += 1;
+    // stop rules; first stopping read of the chunk
+    int stop_at = 0x7fffffff;
+#pragma unroll
+    for (int k = 0; k < IS_K; ++k) {
+      if (stop_at != 0x7fffffff) break;
+      const i64 kf = lmax(keyat[k], prekey);
+      int seg_idx, seg_pos;
+      if (kf >= 0) { seg_idx = (int)(kf >> 32); seg_pos = (int)(kf & 0xffffffff); } else { seg_idx = s_segidx; seg_pos = s_segstart; }
+      const i64 count = kidx[k] - seg_idx + 1;
+      const bool stopB = kept[k] && !stopA[k] && (count > 1000000 || (pos[k] - seg_pos) > 1000000);
+      if (stopA[k] || stopB || past[k]) stop_at = c.tid * IS_K + k;
     }
-    if (stop_at != 0x7fffffff) break;
+    const int first_stop = c.reduce(stop_at, MinOp());
+#pragma unroll
+    for (int k = 0; k < IS_K; ++k) {
+      const int id = c.tid * IS_K + k;
+      if (prop[k] && id <= first_stop && !(past[k] && id == first_stop)) {
+        s += (double)(isz[k] < 0 ? -isz[k] : isz[k]);
+        s2 += (double)(int)((u32)isz[k] * (u32)isz[k]);
+        cn += 1;
+      }
+    }
+    if (first_stop != 0x7fffffff) break;
     c.sync();
     if (c.tid == c.nthr - 1) {   // carry the running state to the next chunk
-      s_lastpos = imax(s_lastpos, imax(prevpos, kept ? pos : -0x7fffffff));
-      if (key >= 0) { s_segidx = seg_idx; s_segstart = seg_pos; }
+      s_lastpos = imax(s_lastpos, imax(prevpos, lastkept));
+      const i64 kf = lmax(key, prekey);
+      if (kf >= 0) { s_segidx = (int)(kf >> 32); s_segstart = (int)(kf & 0xffffffff); }
     }
     kept_before += tot;
     c.sync();

@@ -120,13 +120,27 @@ struct CandArgs {
 };
 
 enum { CAND_SHIST = 16384 };
-__global__ void __launch_bounds__(1024) k_candidates(CandArgs A, DevState* st) {
-  RSI_CTA_SETUP(c);
-  RSI_DYN_SMEM(smem);
-  A.S.shist = reinterpret_cast<unsigned*>(smem); A.S.shist_cap = CAND_SHIST;
+struct CandSpec { long long* off; Cnv* res; int* on; int* nl; long long cap; int* ref; long long* pref; float* rm; };
+
+__device__ __forceinline__ CandCfg cand_cfg(const CandArgs& A, const DevState* st) {
   CandCfg P;
   P.m = st->m; P.maxchkbp = A.maxchkbp; P.merge = A.merge; P.tid = A.tid; P.chklen = A.chklen; P.minmlen = 3.01; P.buffer = 0.05; P.p = 0.05;
   P.rdmedian = st->rdmedian; P.rdsd = st->rdsd; P.span = st->Lc;
+  return P;
+}
+__device__ __forceinline__ CandDumps cand_dumps(const CandArgs& A) {
+  CandDumps D;
+  D.blocks = A.d_blocks; D.n_blocks = &A.n_dump[1]; D.premerge = A.d_premerge; D.n_premerge = &A.n_dump[2];
+  D.merged = A.d_merged; D.n_merged = &A.n_dump[3]; D.cap = A.list_cap;
+  return D;
+}
+
+// stage A: keep |score| >= tlamda/2 (rsi.cpp:1340-1345), areblockscnv, sort, bins -> bases
+__global__ void __launch_bounds__(1024) k_cand_a(CandArgs A, CandSpec X, DevState* st) {
+  RSI_CTA_SETUP(c);
+  RSI_DYN_SMEM(smem);
+  A.S.shist = reinterpret_cast<unsigned*>(smem); A.S.shist_cap = CAND_SHIST;
+  const CandCfg P = cand_cfg(A, st);
   const int n_runs = st->n_runs;
   int nl = 0;
   if (c.tid == 0) {
@@ -135,10 +149,55 @@ __global__ void __launch_bounds__(1024) k_candidates(CandArgs A, DevState* st) {
   }
   nl = cta_bcast(c, nl, 3);
   dump_list(c, A.segs, nl, A.d_segments, &A.n_dump[0], A.list_cap);
-  CandDumps D;
-  D.blocks = A.d_blocks; D.n_blocks = &A.n_dump[1]; D.premerge = A.d_premerge; D.n_premerge = &A.n_dump[2];
-  D.merged = A.d_merged; D.n_merged = &A.n_dump[3]; D.cap = A.list_cap;
-  nl = candidates_main(c, P, A.S, A.rdc, st->Lc, A.medint, A.status, st->nb, A.nbeg, A.nend, st->n_noseq, A.segs, nl, A.tmp, A.ov, D, 0);
+  nl = cand_stage_a(c, P, A.S, st->Lc, A.medint, A.status, st->nb, A.segs, nl, A.tmp, A.ov, cand_dumps(A), 0);
+  if (c.tid == 0) *X.nl = nl;
+}
+// optimize_with_derivative twice per call; calls are independent of each other
+__global__ void __launch_bounds__(1024) k_cand_edge(CandArgs A, CandSpec X, DevState* st) {
+  RSI_CTA_SETUP(c);
+  const int nl = *X.nl;
+  long long tm = cand_clock();
+  for (int j = (int)blockIdx.x; j < nl; j += (int)gridDim.x) { edge_refine(c, A.rdc, st->Lc, &A.segs[j]); edge_refine(c, A.rdc, st->Lc, &A.segs[j]); }
+  if (blockIdx.x == 0) cand_tick(c, A.S, 9, &tm);
+}
+__global__ void __launch_bounds__(1024) k_cand_b(CandArgs A, CandSpec X, DevState* st) {
+  RSI_CTA_SETUP(c);
+  RSI_DYN_SMEM(smem);
+  A.S.shist = reinterpret_cast<unsigned*>(smem); A.S.shist_cap = CAND_SHIST;
+  const CandCfg P = cand_cfg(A, st);
+  int nl = cand_stage_b(c, P, A.S, A.rdc, st->Lc, A.segs, *X.nl, A.tmp, A.ov, cand_dumps(A), X.off, X.cap, X.on);
+  c.sync();
+  if (c.tid == 0) *X.nl = nl;
+}
+// speculative final test, one call per block, each with its own scratch slice
+__global__ void __launch_bounds__(1024) k_cand_final(CandArgs A, CandSpec X, DevState* st) {
+  RSI_CTA_SETUP(c);
+  RSI_DYN_SMEM(smem);
+  if (!*X.on) return;
+  const CandCfg P = cand_cfg(A, st);
+  const int nl = *X.nl;
+  long long tm = cand_clock();
+  for (int j = (int)blockIdx.x; j < nl; j += (int)gridDim.x) {
+    CandScratch S = A.S;
+    S.shist = reinterpret_cast<unsigned*>(smem); S.shist_cap = CAND_SHIST;
+    S.hist = nullptr; S.hist_cap = 0;                 // no shared global fallback: an overflow flags the call for the in-order pass
+    S.ref = X.ref + X.off[j]; S.pref = X.pref + X.off[j] + j; S.rm = X.rm + X.off[j];
+    S.ref_cap = (int)(X.off[j + 1] - X.off[j]) - 8;
+    S.prof = blockIdx.x == 0 ? A.S.prof : nullptr;
+    cand_final_one(c, P, S, A.rdc, st->Lc, A.segs, nl, j, X.res);
+    c.sync();
+  }
+  if (blockIdx.x == 0) cand_tick(c, A.S, 6, &tm);
+}
+__global__ void __launch_bounds__(1024) k_cand_c(CandArgs A, CandSpec X, DevState* st) {
+  RSI_CTA_SETUP(c);
+  RSI_DYN_SMEM(smem);
+  A.S.shist = reinterpret_cast<unsigned*>(smem); A.S.shist_cap = CAND_SHIST;
+  const CandCfg P = cand_cfg(A, st);
+  int spec = *X.on;
+  if (c.tid == 0 && spec && (*A.S.err & (CAND_ERR_HIST | CAND_ERR_REFCAP))) { *A.S.err &= ~(CAND_ERR_HIST | CAND_ERR_REFCAP); spec = 0; }   // a slice overflowed: redo everything in order
+  spec = cta_bcast(c, spec, 6);
+  int nl = cand_stage_c(c, P, A.S, A.rdc, st->Lc, A.nbeg, A.nend, st->n_noseq, A.segs, *X.nl, X.res, spec, &st->cand_redone);
   for (int j = c.tid; j < nl; j += c.nthr) A.d_detected[j] = A.segs[j];
   c.sync();
   if (c.tid == 0) { st->n_detected = nl; nl = sd_filter_list(P, A.segs, nl); st->n_calls = nl; }

@@ -90,19 +90,20 @@ struct rsigpu_ctx {
   DevState* d_st = nullptr; DevState* h_st = nullptr;
   DevBuf<u32> d_hist_all, d_chist, d_thist, d_tothist, d_fq_hist;
   // bins
-  DevBuf<float> d_bin_med, d_bin_nbn, d_lut, d_nz_val; DevBuf<int> d_bin_medint, d_status, d_status1, d_tile, d_nz_idx, d_runs; DevBuf<i64> d_bin_sum, d_pfx;
+  DevBuf<float> d_bin_med, d_bin_nbn, d_lut, d_nz_val; DevBuf<int> d_bin_medint, d_status, d_status1, d_tile, d_nz_idx, d_runs; DevBuf<i64> d_bin_sum, d_pfx, d_cprof;
   DevBuf<u32> d_minl_del, d_minl_dup;
   float* h_lut = nullptr; size_t h_lut_cap = 0;
   // lists
   DevBuf<Cnv> d_lists;   // segs | tmp | ov(2) | segments | blocks | premerge | merged | detected | calls
   DevBuf<int> d_misc;    // n_dump[4] | cand_err | max_extent | sorted_bad | n_begN | n_endN
-  DevBuf<int> d_ref, d_sub; DevBuf<i64> d_pref; DevBuf<float> d_rm; DevBuf<u32> d_chist_c;
+  DevBuf<int> d_ref, d_sub, d_spec_ref; DevBuf<i64> d_pref, d_spec_pref, d_spec_off; DevBuf<float> d_rm, d_spec_rm; DevBuf<u32> d_chist_c;
   DevBuf<int> d_nrun_beg, d_nrun_end, d_scan_scratch;
   std::vector<Cnv> h_detected, h_calls, h_dump[4];
   // reads
   DevVec<int> r_pos, r_mpos, r_isize, r_mtid; DevVec<u16> r_flag; DevVec<u8> r_mapq, r_qual; DevVec<u32> r_cigar_off, r_cigar; DevVec<u64> r_qual_off;
   DevBuf<int> r_calend;
   // accounting
+  long long h_cprof[16] = {};
   int64_t launches = 0;
   float stage_ms[6] = {0, 0, 0, 0, 0, 0};
   cudaEvent_t ev[8] = {};
@@ -180,7 +181,10 @@ int set_smem_attrs() {
   cudaFuncSetAttribute(k_gc_table, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(GC_STRATA * A_NT * 8 + LD_FAB + (LD_PRE + 8) * 2));
   cudaFuncSetAttribute(k_gc_adjust, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(B_K * B_NT * 2 + GC_STRATA * 8 + LD_FAB + (LD_PRE + 8) * 2));
   cudaFuncSetAttribute(k_bins, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(C_K * C_NT * 2 + C_TP * 4));
-  cudaFuncSetAttribute(k_candidates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CAND_SHIST * 4));
+  cudaFuncSetAttribute(k_cand_a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CAND_SHIST * 4));
+  cudaFuncSetAttribute(k_cand_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CAND_SHIST * 4));
+  cudaFuncSetAttribute(k_cand_c, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CAND_SHIST * 4));
+  cudaFuncSetAttribute(k_cand_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CAND_SHIST * 4));
   cudaFuncSetAttribute(k_rsi_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SCAN_SMEM);
   return 0;
 }
@@ -269,8 +273,8 @@ int rsigpu_create(int device, const rsigpu_params* p, rsigpu_ctx** out) {
   ok = ok && c->d_hist_all.ensure(HIST_ALL_BINS) == cudaSuccess && c->d_chist.ensure((size_t)MAD_CLASSES * CHIST_RCAP) == cudaSuccess;
   ok = ok && c->d_thist.ensure(CHIST_RCAP) == cudaSuccess && c->d_tothist.ensure(CHIST_RCAP) == cudaSuccess;
   ok = ok && c->d_fq_hist.ensure((size_t)FQ_BINS_CAP + 8) == cudaSuccess;
-  ok = ok && c->d_lists.ensure((size_t)LIST_CAP * 9 + 8) == cudaSuccess && c->d_misc.ensure(64) == cudaSuccess;
-  ok = ok && c->d_runs.ensure((size_t)LIST_CAP * 2 + 8) == cudaSuccess;
+  ok = ok && c->d_lists.ensure((size_t)LIST_CAP * 10 + 8) == cudaSuccess && c->d_misc.ensure(64) == cudaSuccess;
+  ok = ok && c->d_runs.ensure((size_t)LIST_CAP * 2 + 8) == cudaSuccess && c->d_cprof.ensure(16) == cudaSuccess;
   ok = ok && c->d_chist_c.ensure(1u << 22) == cudaSuccess && c->d_sub.ensure((size_t)p->maxchkbp * 10 + 64) == cudaSuccess;
   ok = ok && c->d_nrun_beg.ensure(1 << 20) == cudaSuccess && c->d_nrun_end.ensure(1 << 20) == cudaSuccess;
   if (ok) ok = cudaMemsetAsync(c->d_fq_hist.p, 0, ((size_t)FQ_BINS_CAP + 8) * 4, c->stream) == cudaSuccess;
@@ -286,8 +290,8 @@ void rsigpu_destroy(rsigpu_ctx* c) {
   c->d_fasta.release(); c->d_raw.release(); c->d_rdc.release(); c->d_nseq.release();
   c->d_hist_all.release(); c->d_chist.release(); c->d_thist.release(); c->d_tothist.release(); c->d_fq_hist.release();
   c->d_bin_med.release(); c->d_bin_nbn.release(); c->d_lut.release(); c->d_bin_medint.release(); c->d_status.release(); c->d_status1.release();
-  c->d_tile.release(); c->d_nz_idx.release(); c->d_nz_val.release(); c->d_runs.release(); c->d_bin_sum.release(); c->d_pfx.release(); c->d_minl_del.release(); c->d_minl_dup.release();
-  c->d_lists.release(); c->d_misc.release(); c->d_ref.release(); c->d_sub.release(); c->d_pref.release(); c->d_rm.release(); c->d_chist_c.release();
+  c->d_tile.release(); c->d_nz_idx.release(); c->d_nz_val.release(); c->d_runs.release(); c->d_bin_sum.release(); c->d_pfx.release(); c->d_cprof.release(); c->d_minl_del.release(); c->d_minl_dup.release();
+  c->d_lists.release(); c->d_misc.release(); c->d_ref.release(); c->d_sub.release(); c->d_pref.release(); c->d_rm.release(); c->d_chist_c.release(); c->d_spec_ref.release(); c->d_spec_pref.release(); c->d_spec_off.release(); c->d_spec_rm.release();
   c->d_nrun_beg.release(); c->d_nrun_end.release(); c->d_scan_scratch.release(); c->r_calend.release();
   c->r_pos.release(); c->r_mpos.release(); c->r_isize.release(); c->r_mtid.release(); c->r_flag.release(); c->r_mapq.release(); c->r_qual.release();
   c->r_cigar_off.release(); c->r_cigar.release(); c->r_qual_off.release();
@@ -441,6 +445,8 @@ int rsigpu_load_finish(rsigpu_ctx* c) {
   CK(c->d_status.ensure(nb + 8)); CK(c->d_status1.ensure(nb + 8)); CK(c->d_nz_idx.ensure(nb + 8)); CK(c->d_nz_val.ensure(nb + 8)); CK(c->d_tile.ensure(nb / 1024 + 8));
   CK(c->d_scan_scratch.ensure((size_t)((nb + S_T - 1) / S_T) * 10 * S_NB + 64)); CK(c->d_minl_del.ensure(nb + 8)); CK(c->d_minl_dup.ensure(nb + 8)); CK(c->d_pfx.ensure((size_t)nb + LIST_CAP + 8));
   CK(c->d_ref.ensure((size_t)c->Lc + 64)); CK(c->d_pref.ensure((size_t)c->Lc + 64)); CK(c->d_rm.ensure((size_t)c->Lc + 64));
+  CK(c->d_spec_ref.ensure(2 * (size_t)c->Lc + 128)); CK(c->d_spec_pref.ensure(2 * (size_t)c->Lc + LIST_CAP + 128)); CK(c->d_spec_rm.ensure(2 * (size_t)c->Lc + 128));
+  CK(c->d_spec_off.ensure(LIST_CAP + 8));
   // device state
   DevState* h = c->h_st;
   memset(h, 0, sizeof(DevState));
@@ -536,13 +542,24 @@ int rsigpu_detectcnv(rsigpu_ctx* c) {
   A.d_segments = c->list(3); A.d_blocks = c->list(4); A.d_premerge = c->list(5); A.d_merged = c->list(6); A.d_detected = c->list(7); A.d_calls = c->list(8);
   A.n_dump = c->d_misc.p; A.list_cap = LIST_CAP;
   A.S.ref = c->d_ref.p; A.S.ref_cap = (int)std::min<size_t>(c->d_ref.cap, 0x7fffffff); A.S.sub = c->d_sub.p; A.S.sub_cap = (int)c->d_sub.cap;
-  A.S.pref = c->d_pref.p; A.S.rm = c->d_rm.p; A.S.hist = c->d_chist_c.p; A.S.hist_cap = (int)c->d_chist_c.cap; A.S.err = c->d_misc.p + 4;
+  A.S.pref = c->d_pref.p; A.S.rm = c->d_rm.p; A.S.hist = c->d_chist_c.p; A.S.hist_cap = (int)c->d_chist_c.cap; A.S.err = c->d_misc.p + 4; A.S.prof = c->profile ? c->d_cprof.p : nullptr;
+  if (c->profile) CK(cudaMemsetAsync(c->d_cprof.p, 0, 16 * 8, c->stream));
   A.maxchkbp = c->P.maxchkbp; A.merge = c->P.merge; A.tid = c->tid; A.chklen = c->P.chklen;
-  KL(k_candidates, 1, 1024, (size_t)CAND_SHIST * 4, A, c->d_st);
+  CandSpec X;
+  X.off = c->d_spec_off.p; X.res = c->list(9); X.on = c->d_misc.p + 12; X.nl = c->d_misc.p + 13;
+  X.cap = (long long)c->d_spec_ref.cap - 64; X.ref = c->d_spec_ref.p; X.pref = c->d_spec_pref.p; X.rm = c->d_spec_rm.p;
+  CK(cudaMemsetAsync(c->d_misc.p + 12, 0, 8, c->stream));
+  const int gcalls = c->n_sm;
+  KL(k_cand_a, 1, 1024, (size_t)CAND_SHIST * 4, A, X, c->d_st);
+  KL(k_cand_edge, gcalls, 1024, 0, A, X, c->d_st);
+  KL(k_cand_b, 1, 1024, (size_t)CAND_SHIST * 4, A, X, c->d_st);
+  KL(k_cand_final, gcalls, 1024, (size_t)CAND_SHIST * 4, A, X, c->d_st);
+  KL(k_cand_c, 1, 1024, (size_t)CAND_SHIST * 4, A, X, c->d_st);
   CK(cudaEventRecord(c->ev[4], c->stream));
   CK(cudaMemcpyAsync(h, c->d_st, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
   int nd[4];
   CK(cudaMemcpyAsync(nd, c->d_misc.p, 16, cudaMemcpyDeviceToHost, c->stream));
+  if (c->profile) CK(cudaMemcpyAsync(c->h_cprof, c->d_cprof.p, 16 * 8, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   if (h->err) return map_dev_err(c, h->err, h->cand_err);
   c->h_detected.resize(h->n_detected); c->h_calls.resize(h->n_calls);
@@ -707,10 +724,11 @@ int rsigpu_debug_state(const rsigpu_ctx* c, double* out, int32_t cap) {
                       (double)h->capv, (double)h->hist_base, (double)h->chist_R, h->rdmedian, h->rdsd, h->rdmad, (double)h->max_binsum, (double)h->gstar,
                       h->gc_tab[80], h->gc_tab[90], h->gc_tab[100], (double)h->gc_cnt[90], h->tmedian, h->tsigma, h->tlamda, (double)h->Lmax,
                       (double)h->lbreak_del, (double)h->lbreak_dup, (double)h->n_runs, (double)h->n_nonzero, (double)h->st_lo, (double)h->st_hi,
-                      (double)h->lvl_sum[-h->st_lo < 0 ? 0 : -h->st_lo], (double)h->filt_on};
+                      (double)h->lvl_sum[-h->st_lo < 0 ? 0 : -h->st_lo], (double)h->filt_on, (double)h->cand_redone};
   const int n = (int)(sizeof v / sizeof v[0]);
   for (int k = 0; k < n && k < cap; ++k) out[k] = v[k];
-  return n;
+  for (int k = 0; k < 16 && n + k < cap; ++k) out[n + k] = (double)c->h_cprof[k];   // candidate-stage phase clocks (profile mode)
+  return n + 16;
 }
 
 // test hook: 0 = sequential float chain for filterstatus' level-0 sum, 1 = block-scan form (default)

@@ -89,6 +89,7 @@ struct DevState {
   int n_runs, n_segs;
   // ---- final list
   int n_calls, n_detected;
+  int cand_redone, pad3_;      // calls whose speculative final test had to be redone in order
   // ---- pair statistics (bam_rd_pr_stats, pairrd.cpp:112-260)
   int isize_mean, isize_sd;
   // ---- scratch for the quantile jobs

@@ -15,7 +15,7 @@ struct Sim {
     int cap = n + 16;
     ref.resize(cap); sub.resize(2000016); pref.resize(cap + 1); rm.resize(cap); hist.resize(1 << 22);
     S.ref = ref.data(); S.ref_cap = cap; S.sub = sub.data(); S.sub_cap = (int)sub.size(); S.pref = pref.data(); S.rm = rm.data();
-    S.hist = hist.data(); S.hist_cap = (int)hist.size(); S.shist = nullptr; S.shist_cap = 0; S.err = &err;
+    S.hist = hist.data(); S.hist_cap = (int)hist.size(); S.shist = nullptr; S.shist_cap = 0; S.err = &err; S.prof = nullptr;
     cta.bc = bc;
   }
 };

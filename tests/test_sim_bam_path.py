@@ -49,3 +49,25 @@ def test_pileup_filters(sim_lib, oracle):
         with api.Context(lib=sim_lib, minq=minq, min_baseQ=Q) as ctx:
             ctx.set_reference(fa); ctx.pileup_begin(); ctx.pileup_push(reads); ctx.pileup_end()
             assert np.array_equal(ctx.array(api.ARR_RAW_DEPTH), want), (minq, Q)
+
+
+def test_isize_sample_with_gaps_and_foreign_mates(sim_lib, oracle):
+    """bam_rd_pr_stats' reset rule (a gap of more than 1 kb restarts the sample), mates on other contigs, reads
+    without CIGAR -- the order of the tests is SURVEY.md A.2"""
+    fa = synth.make_fasta(L, 4)
+    reads, _ = synth.make_reads(L, 4, fa, coverage=10, n_events=4, lens=(3000, 8000, 20000))
+    pos = reads["pos"]
+    drop = ((pos >= 10_100_000) & (pos < 10_103_000)) | ((pos >= 10_300_000) & (pos < 10_301_500)) | ((pos >= 10_450_000) & (pos < 10_450_900))
+    keep = ~drop
+    co = reads["cigar_off"].astype(np.int64); qo = reads["qual_off"].astype(np.int64)
+    nc = np.diff(co)[keep]; nq = np.diff(qo)[keep]
+    ckeep = np.repeat(keep, np.diff(co)); qkeep = np.repeat(keep, np.diff(qo))
+    r2 = {k: reads[k][keep] for k in ("pos", "mpos", "isize", "mtid", "flag", "mapq")}
+    r2["cigar"] = reads["cigar"][ckeep]; r2["qual"] = reads["qual"][qkeep]
+    r2["cigar_off"] = np.concatenate(([0], np.cumsum(nc))).astype(np.uint32); r2["qual_off"] = np.concatenate(([0], np.cumsum(nq))).astype(np.uint64)
+    rng = np.random.default_rng(9)
+    n = len(r2["pos"])
+    r2["mtid"] = r2["mtid"].copy(); r2["mtid"][rng.random(n) < 0.01] = 3      # mate elsewhere: skipped
+    r2["mtid"][rng.random(n) < 0.005] = -1                                      # mate unmapped: kept, not proper
+    calls, st = run_bam_case(sim_lib, oracle, fa, r2, n_batches=2, min_baseQ=10, minq=0)
+    assert len(calls) >= 1 and st.isize_mean > 0
