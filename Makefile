@@ -5,11 +5,17 @@ NVFLAGS   := -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -f
 CSRC      := rsicnv_b200/csrc
 HDRS      := $(wildcard $(CSRC)/*.cuh) include/rsigpu.h
 
-all: lib oracle sim
+all: lib cli oracle sim
 
 lib: rsicnv_b200/librsigpu.so
 rsicnv_b200/librsigpu.so: $(CSRC)/rsigpu.cu $(HDRS)
 	$(NVCC) $(NVFLAGS) -shared $< -o $@ 2> build_ptxas.log || (cat build_ptxas.log; exit 1)
+
+# the host program (argv, BGZF/BAM, FASTA, depth text, output table) over the C ABI
+cli: rsicnv_b200/bin/rsicnv
+rsicnv_b200/bin/rsicnv: rsicnv_b200/host/main.cpp rsicnv_b200/host/bam_reader.cpp rsicnv_b200/host/bam_reader.hpp include/rsigpu.h rsicnv_b200/librsigpu.so
+	mkdir -p rsicnv_b200/bin
+	$(CXX) -O2 -std=c++17 -Wall rsicnv_b200/host/main.cpp rsicnv_b200/host/bam_reader.cpp -o $@ -Lrsicnv_b200 -lrsigpu -lz -lpthread '-Wl,-rpath,$$ORIGIN/..'
 
 oracle: oracle/librsi_oracle.so
 oracle/librsi_oracle.so: oracle/rsi_oracle.cpp
@@ -26,5 +32,5 @@ ref:
 	$(MAKE) -f oracle/Makefile.ref -j8
 
 clean:
-	rm -f rsicnv_b200/librsigpu.so oracle/librsi_oracle.so tests/hostsim/*.so build_ptxas.log
+	rm -rf rsicnv_b200/bin rsicnv_b200/librsigpu.so oracle/librsi_oracle.so tests/hostsim/*.so build_ptxas.log
 .PHONY: all lib oracle sim ref clean

@@ -1,0 +1,136 @@
+#include "bam_reader.hpp"
+
+#include <string.h>
+#include <zlib.h>
+
+#include <thread>
+
+namespace rsihost {
+
+namespace {
+inline uint32_t rd32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+inline uint16_t rd16(const uint8_t* p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+
+struct Block { size_t coff, clen, uoff, ulen; };
+
+bool inflate_block(const uint8_t* src, size_t clen, uint8_t* dst, size_t ulen) {
+  // src points at the 18-byte header; payload = clen - 18 - 8 bytes of raw deflate
+  z_stream zs;
+  memset(&zs, 0, sizeof zs);
+  if (inflateInit2(&zs, -15) != Z_OK) return false;
+  zs.next_in = const_cast<Bytef*>(src + 18); zs.avail_in = (uInt)(clen - 26);
+  zs.next_out = dst; zs.avail_out = (uInt)ulen;
+  int rc = inflate(&zs, Z_FINISH);
+  inflateEnd(&zs);
+  if (rc != Z_STREAM_END || zs.total_out != ulen) return false;
+  return (uint32_t)crc32(crc32(0L, Z_NULL, 0), dst, (uInt)ulen) == rd32(src + clen - 8);
+}
+}  // namespace
+
+bool BamReader::open(const std::string& path, std::string* err) {
+  close();
+  f_ = fopen(path.c_str(), "rb");
+  if (!f_) { *err = "cannot open " + path; return false; }
+  eof_ = false; buf_.clear(); off_ = 0;
+  if (!fill(12, err)) return false;
+  if (buf_.size() - off_ < 12 || memcmp(&buf_[off_], "BAM\1", 4) != 0) { *err = path + " is not a BAM file"; return false; }
+  const uint32_t l_text = rd32(&buf_[off_ + 4]);
+  if (!fill(12 + (size_t)l_text, err)) return false;
+  const uint32_t n_ref = rd32(&buf_[off_ + 8 + l_text]);
+  off_ += 12 + l_text;
+  hdr_.name.clear(); hdr_.len.clear();
+  for (uint32_t i = 0; i < n_ref; ++i) {
+    if (!fill(4, err)) return false;
+    const uint32_t l_name = rd32(&buf_[off_]);
+    if (!fill(8 + (size_t)l_name, err) || buf_.size() - off_ < 8 + (size_t)l_name) { *err = "truncated BAM header"; return false; }
+    hdr_.name.push_back(std::string((const char*)&buf_[off_ + 4], l_name ? l_name - 1 : 0));
+    hdr_.len.push_back((int32_t)rd32(&buf_[off_ + 4 + l_name]));
+    off_ += 8 + l_name;
+  }
+  return true;
+}
+
+void BamReader::close() {
+  if (f_) fclose(f_);
+  f_ = nullptr;
+}
+
+// read up to ~32 MiB of compressed blocks, inflate them on several threads, append to buf_
+bool BamReader::read_block_group(std::string* err) {
+  if (eof_) return true;
+  std::vector<uint8_t> comp;
+  std::vector<Block> blocks;
+  size_t utotal = 0;
+  const size_t target = (size_t)32 << 20;
+  while (comp.size() < target) {
+    uint8_t h[18];
+    size_t got = fread(h, 1, 18, f_);
+    if (got == 0) { eof_ = true; break; }
+    if (got != 18 || h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4) || rd16(h + 10) != 6 || h[12] != 'B' || h[13] != 'C') { *err = "bad BGZF block header"; return false; }
+    const size_t clen = (size_t)rd16(h + 16) + 1;
+    const size_t at = comp.size();
+    comp.resize(at + clen);
+    memcpy(&comp[at], h, 18);
+    if (fread(&comp[at + 18], 1, clen - 18, f_) != clen - 18) { *err = "truncated BGZF block"; return false; }
+    const size_t ulen = rd32(&comp[at + clen - 4]);
+    blocks.push_back(Block{at, clen, utotal, ulen});
+    utotal += ulen;
+  }
+  if (blocks.empty()) return true;
+  // compact the consumed prefix before growing
+  if (off_ > 0) { buf_.erase(buf_.begin(), buf_.begin() + (ptrdiff_t)off_); off_ = 0; }
+  const size_t base = buf_.size();
+  buf_.resize(base + utotal);
+  const int nt = threads_ < 1 ? 1 : threads_;
+  std::vector<std::thread> pool;
+  std::vector<int> ok(nt, 1);
+  for (int t = 0; t < nt; ++t)
+    pool.emplace_back([&, t]() {
+      for (size_t b = (size_t)t; b < blocks.size(); b += (size_t)nt)
+        if (blocks[b].ulen && !inflate_block(&comp[blocks[b].coff], blocks[b].clen, &buf_[base + blocks[b].uoff], blocks[b].ulen)) ok[t] = 0;
+    });
+  for (auto& th : pool) th.join();
+  for (int t = 0; t < nt; ++t) if (!ok[t]) { *err = "BGZF inflate / CRC error"; return false; }
+  return true;
+}
+
+bool BamReader::fill(size_t want, std::string* err) {
+  while (buf_.size() - off_ < want && !eof_) if (!read_block_group(err)) return false;
+  return true;
+}
+
+bool BamReader::next_contig(ContigReads* out, std::string* err) {
+  out->clear();
+  out->cigar_off.push_back(0); out->qual_off.push_back(0);
+  for (;;) {
+    if (!fill(4, err)) return false;
+    if (buf_.size() - off_ < 4) break;   // end of file
+    const uint32_t bs = rd32(&buf_[off_]);
+    if (!fill(4 + (size_t)bs, err)) return false;
+    if (buf_.size() - off_ < 4 + (size_t)bs || bs < 32) { *err = "truncated BAM record"; return false; }
+    const uint8_t* r = &buf_[off_ + 4];
+    const int32_t tid = (int32_t)rd32(r);
+    if (tid < 0) { off_ = buf_.size(); eof_ = true; break; }   // unplaced reads come last in a sorted BAM
+    if (out->tid >= 0 && tid != out->tid) break;             // next contig starts: leave the record for the next call
+    out->tid = tid;
+    const uint32_t bmq = rd32(r + 8), fnc = rd32(r + 12);
+    const uint32_t l_name = bmq & 0xff, n_cig = fnc & 0xffff, l_seq = rd32(r + 16);
+    if (32 + (size_t)l_name + 4 * (size_t)n_cig + (l_seq + 1) / 2 + l_seq > bs) { *err = "corrupt BAM record"; return false; }
+    out->pos.push_back((int32_t)rd32(r + 4));
+    out->mapq.push_back((uint8_t)((bmq >> 8) & 0xff));
+    out->flag.push_back((uint16_t)(fnc >> 16));
+    out->mtid.push_back((int32_t)rd32(r + 20));
+    out->mpos.push_back((int32_t)rd32(r + 24));
+    out->isize.push_back((int32_t)rd32(r + 28));
+    const uint8_t* cg = r + 32 + l_name;
+    for (uint32_t k = 0; k < n_cig; ++k) out->cigar.push_back(rd32(cg + 4 * k));
+    out->cigar_off.push_back((uint32_t)out->cigar.size());
+    const uint8_t* q = cg + 4 * n_cig + (l_seq + 1) / 2;
+    out->qual.insert(out->qual.end(), q, q + l_seq);
+    out->qual_off.push_back((uint64_t)out->qual.size());
+    off_ += 4 + (size_t)bs;
+  }
+  return out->tid >= 0;
+}
+
+}  // namespace rsihost

@@ -1,0 +1,315 @@
+// rsicnv (B200-native) -- host program of the `rsicnv rsi` path.
+//
+// Keeps the reference CLI (get_parameters, rsi.cpp:1986-2068: -f -b -d -c -m -q -Q -cap -NOGC -MED -NB -o, plus
+// the flags the reference accepts and ignores) and the exact output table (cnv_format1 / write_cnv_to_file,
+// rsi.cpp:581-631, 1592-1616).  The host side decodes BGZF/BAM (bam_reader.cpp), reads the FASTA through its
+// .fai index (read_fasta, readref.cpp:10-86), parses depth files (load_data_from_text, loaddata.cpp:496-517) and
+// writes the table; everything else runs on the GPU through the C ABI in include/rsigpu.h.  Contigs are
+// independent units (rsi.cpp:2189-2217): with `-gpus N` they are dealt to N GPUs, longest first, one host
+// thread and one context per GPU, and the rows are written in BAM-header order.
+//
+// Extra sub-command for the tests (no GPU needed):  rsicnv decode -b in.bam -c CHR -o prefix
+//   writes the decoded structure-of-arrays of one contig as raw little-endian files prefix.<field>.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <fstream>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/rsigpu.h"
+#include "bam_reader.hpp"
+
+using namespace rsihost;
+
+namespace {
+
+struct Opt {
+  std::string function = "rsi", rdfile, bamfile, reffile, outfile = "rsiout.txt", chr = "1-22XY";
+  bool saverd = false;
+  int gpus = 1, threads = 8;
+  rsigpu_params P;
+};
+
+int usage() {
+  fprintf(stderr,
+          "Usage:\n  rsicnv rsi -f REF -b BAM [options]\n  rsicnv rsi -f REF -d RDFILE -c CHR [options]\n"
+          "Options:\n   -o  STR  outputfile [rsiout.txt]\n   -c  STR  chromosome [1-22XY]\n   -m  INT  bin size, odd [101]\n"
+          "   -q  INT  minimum mapping quality [0]\n   -Q  INT  minimum base quality [13]\n   -cap FLT cap depth at FLT x median, <=1 off [4]\n"
+          "   -NOGC    no GC adjustment\n   -MED | -NB  transformation [NB]\n   -s       save raw depth to <out>.<chr>_rd (BAM input)\n"
+          "   -gpus INT  GPUs to shard contigs over [1]   -threads INT  host inflate threads [8]\n");
+  return 0;
+}
+
+bool parse(int argc, char** argv, Opt* o) {
+  rsigpu_default_params(&o->P);
+  std::vector<std::string> a(argv, argv + argc);
+  if (a.size() < 2) return false;
+  if (a[1][0] != '-') {
+    o->function = a[1]; a[1] = "";
+    if (o->function != "rsi" && o->function != "decode") { fprintf(stderr, "no such function %s (this build implements `rsi`)\n", o->function.c_str()); return false; }
+  }
+  auto val = [&](size_t i) { return i + 1 < a.size() ? a[i + 1] : std::string(); };
+  for (size_t i = 1; i < a.size(); ++i) {
+    const std::string k = a[i];
+    auto two = [&]() { a[i] = ""; if (i + 1 < a.size()) a[i + 1] = ""; };
+    if (k == "-d") { o->rdfile = val(i); two(); continue; }
+    if (k == "-b") { o->bamfile = val(i); two(); continue; }
+    if (k == "-f") { o->reffile = val(i); two(); continue; }
+    if (k == "-v") { two(); continue; }
+    if (k == "-o") { o->outfile = val(i); two(); continue; }
+    if (k == "-c") { o->chr = val(i); two(); continue; }
+    if (k == "-s") { o->saverd = true; a[i] = ""; continue; }
+    if (k == "-m") { o->P.m = atoi(val(i).c_str()); two(); continue; }
+    if (k == "-q") { o->P.minq = atoi(val(i).c_str()); two(); continue; }
+    if (k == "-Q") { o->P.min_baseQ = atoi(val(i).c_str()); two(); continue; }
+    if (k == "-L" || k == "-p") { two(); continue; }                    // parsed and unused on this path (rsi.cpp:2018-2019)
+    if (k == "-np" || k == "-debug" || k == "-hist" || k == "-overlap" || k == "-combine" || k == "-nocode") { a[i] = ""; continue; }
+    if (k == "-threshold") { o->P.threshold = atof(val(i).c_str()); two(); continue; }
+    if (k == "-e") { o->P.epsilon = atof(val(i).c_str()); two(); continue; }
+    if (k == "-cap") { o->P.cap = atof(val(i).c_str()); two(); continue; }
+    if (k == "-reflen") { o->P.chklen = atof(val(i).c_str()); two(); continue; }
+    if (k == "-maxchkbp") { o->P.maxchkbp = atoi(val(i).c_str()); two(); continue; }
+    if (k == "-MED") { o->P.trans = RSIGPU_TRANS_MED; a[i] = ""; continue; }
+    if (k == "-NB") { o->P.trans = RSIGPU_TRANS_NBN; a[i] = ""; continue; }
+    if (k == "-ALL") { o->P.trans = RSIGPU_TRANS_ALL; a[i] = ""; continue; }
+    if (k == "-nomerge") { o->P.merge = 0; a[i] = ""; continue; }
+    if (k == "-NOGC") { o->P.gcadjust = 0; a[i] = ""; continue; }
+    if (k == "-gpus") { o->gpus = atoi(val(i).c_str()); two(); continue; }
+    if (k == "-threads") { o->threads = atoi(val(i).c_str()); two(); continue; }
+  }
+  bool bad = false;
+  for (size_t i = 1; i < a.size(); ++i) if (!a[i].empty()) { fprintf(stderr, "unknown option %s\n", a[i].c_str()); bad = true; }
+  if (bad) return false;
+  if (o->rdfile.empty() && o->bamfile.empty()) { fprintf(stderr, "need input file \n"); return false; }
+  if (o->reffile.empty() && o->function == "rsi") { fprintf(stderr, "need reference file \n"); return false; }
+  if (o->outfile == o->bamfile || o->outfile == o->rdfile) { fprintf(stderr, "output file is same as input file \n"); return false; }
+  if (!o->rdfile.empty() && (o->chr.empty() || o->chr == "1-22XY")) { fprintf(stderr, "readdepth file and chromosome must be specified together\n"); return false; }
+  if (o->P.m % 2 != 1) { o->P.m += 1; fprintf(stderr, "m is changed to %d\n", o->P.m); }
+  if (o->P.trans == RSIGPU_TRANS_ALL) { fprintf(stderr, "-ALL is not built yet in this implementation (use -NB or -MED)\n"); return false; }
+  return true;
+}
+
+// read_fasta (readref.cpp:10-86): contig `chr` or "chr"+chr through the .fai index, newlines stripped
+bool read_fasta(const std::string& ref, const std::string& chr, std::string* out, std::string* err) {
+  std::ifstream fai((ref + ".fai").c_str());
+  if (!fai) { *err = "cannot open " + ref + ".fai"; return false; }
+  std::string name; long long len = 0, off = 0, lb = 0, lw = 0; bool found = false;
+  while (fai >> name >> len >> off >> lb >> lw) { if (name == chr || name == "chr" + chr) { found = true; break; } }
+  if (!found) { *err = "reference has no contig " + chr; return false; }
+  FILE* f = fopen(ref.c_str(), "rb");
+  if (!f) { *err = "cannot open " + ref; return false; }
+  const long long nbytes = len + (lb > 0 ? (len / lb) * (lw - lb) : 0);
+  std::vector<char> raw((size_t)nbytes + 1);
+  fseeko(f, (off_t)off, SEEK_SET);
+  const size_t got = fread(raw.data(), 1, (size_t)nbytes, f);
+  fclose(f);
+  out->clear(); out->reserve((size_t)len);
+  for (size_t i = 0; i < got && (long long)out->size() < len; ++i) if (raw[i] != '\n' && raw[i] != '\r') out->push_back(raw[i]);
+  return true;
+}
+
+// load_data_from_text's parse loop (loaddata.cpp:496-517): `pos depth` lines, '#' and empty lines skipped,
+// pos < 1 skipped, pos >= L ends the file, a token that is not a number reads as 0 (istream >> int)
+bool parse_depth_text(const std::string& path, int L, std::vector<int32_t>* rd, std::string* err) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) { *err = "Cannot open file " + path; return false; }
+  rd->assign((size_t)L, 0);
+  std::vector<char> buf((size_t)64 << 20);
+  std::string carry;
+  bool done = false;
+  auto take_int = [](const char*& p, const char* e) {
+    while (p < e && (*p == ' ' || *p == '\t' || *p == '\r' || *p == '\v' || *p == '\f')) ++p;
+    bool neg = false; const char* s = p;
+    if (p < e && (*p == '-' || *p == '+')) { neg = *p == '-'; ++p; }
+    long long v = 0; bool any = false;
+    while (p < e && *p >= '0' && *p <= '9') { v = v * 10 + (*p - '0'); if (v > 0x7fffffffLL) v = 0x7fffffffLL; ++p; any = true; }
+    if (!any) { p = s; return std::make_pair(0LL, false); }
+    return std::make_pair(neg ? -v : v, true);
+  };
+  auto line = [&](const char* p, const char* e) {
+    if (e - p < 1 || *p == '#') return;
+    auto a = take_int(p, e);
+    long long pos = a.first, d = 0;
+    if (a.second) d = take_int(p, e).first;
+    if (pos < 1) return;
+    if (pos >= L) { done = true; return; }
+    (*rd)[(size_t)pos - 1] = (int32_t)d;
+  };
+  while (!done) {
+    const size_t got = fread(buf.data(), 1, buf.size(), f);
+    if (got == 0) break;
+    const char* p = buf.data(); const char* e = p + got;
+    if (!carry.empty()) {
+      const char* nl = (const char*)memchr(p, '\n', (size_t)(e - p));
+      if (!nl) { carry.append(p, e); continue; }
+      carry.append(p, nl);
+      line(carry.data(), carry.data() + carry.size());
+      carry.clear(); p = nl + 1;
+    }
+    while (!done && p < e) {
+      const char* nl = (const char*)memchr(p, '\n', (size_t)(e - p));
+      if (!nl) { carry.assign(p, e); break; }
+      line(p, nl); p = nl + 1;
+    }
+  }
+  if (!done && !carry.empty()) line(carry.data(), carry.data() + carry.size());
+  fclose(f);
+  return true;
+}
+
+struct ContigResult {
+  std::string name; bool done = false; std::string err;
+  std::vector<rsigpu_cnv> calls; double rdmedian = 0, rdsd = 0;
+};
+
+bool run_contig(rsigpu_ctx* c, const Opt& o, const std::string& name, int tid, const std::string& fasta, const std::vector<int32_t>* depth,
+                const ContigReads* reads, ContigResult* res) {
+  auto fail = [&](const char* what) { res->err = std::string(what) + ": " + rsigpu_last_error(c); return false; };
+  if (rsigpu_set_reference(c, (const uint8_t*)fasta.data(), (int32_t)fasta.size(), tid)) return fail("set_reference");
+  if (depth) {
+    if (rsigpu_set_depth(c, depth->data(), (int32_t)depth->size())) return fail("set_depth");
+  } else {
+    if (rsigpu_pileup_begin(c, (int32_t)fasta.size())) return fail("pileup_begin");
+    rsigpu_read_batch b; memset(&b, 0, sizeof b);
+    b.n_reads = (int64_t)reads->n(); b.tid = tid;
+    b.pos = reads->pos.data(); b.mpos = reads->mpos.data(); b.isize = reads->isize.data(); b.mtid = reads->mtid.data(); b.flag = reads->flag.data();
+    b.mapq = reads->mapq.data(); b.cigar_off = reads->cigar_off.data(); b.cigar = reads->cigar.data(); b.qual_off = reads->qual_off.data(); b.qual = reads->qual.data();
+    if (rsigpu_pileup_push(c, &b)) return fail("pileup_push");
+    if (o.saverd) {
+      if (rsigpu_pileup_end(c)) return fail("pileup_end");
+      std::vector<int32_t> raw(fasta.size()); int64_t cnt = 0;
+      if (rsigpu_get_array(c, RSIGPU_ARR_RAW_DEPTH, raw.data(), (int64_t)raw.size(), &cnt)) return fail("get raw depth");
+      const std::string fn = o.outfile + "." + name + "_rd";   // loaddata.cpp:340-344, 464-470
+      FILE* f = fopen(fn.c_str(), "w");
+      if (f) { for (size_t i = 0; i < raw.size(); ++i) fprintf(f, "%zu\t%d\n", i + 1, raw[i]); fclose(f); }
+    } else if (rsigpu_pileup_commit(c)) return fail("pileup_commit");
+  }
+  int32_t n = 0;
+  res->calls.resize(65536);
+  if (rsigpu_run(c, res->calls.data(), (int32_t)res->calls.size(), &n)) return fail("run");
+  res->calls.resize((size_t)n);
+  rsigpu_chr_stats st;
+  if (rsigpu_get_chr_stats(c, &st)) return fail("chr_stats");
+  res->rdmedian = st.rdmedian; res->rdsd = st.rdsd;
+  return true;
+}
+
+void write_table(const Opt& o, const std::vector<ContigResult>& all) {
+  FILE* f = fopen(o.outfile.c_str(), "w");
+  if (!f) { fprintf(stderr, "cannot write %s\n", o.outfile.c_str()); return; }
+  char row[2048];
+  bool header = false;
+  for (const ContigResult& r : all) {
+    if (!r.done) continue;
+    if (!header) {   // write_cnv_to_file prints the header with the first processed contig (rsi.cpp:1598-1607)
+      if (!o.rdfile.empty()) fprintf(f, "#input %s %s\n", o.rdfile.c_str(), r.name.c_str());
+      if (!o.bamfile.empty()) fprintf(f, "#input %s\n", o.bamfile.c_str());
+      if (o.P.gcadjust) fprintf(f, "#GC adjusted\n");
+      rsigpu_format_row(nullptr, "", 0, 0, row, sizeof row);
+      fprintf(f, "%s\n", row);
+      header = true;
+    }
+    for (const rsigpu_cnv& c : r.calls) { rsigpu_format_row(&c, r.name.c_str(), r.rdmedian, r.rdsd, row, sizeof row); fprintf(f, "%s\n", row); }
+  }
+  fclose(f);
+}
+
+int do_decode(const Opt& o) {
+  BamReader br(o.threads); std::string err;
+  if (!br.open(o.bamfile, &err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+  ContigReads cr;
+  while (br.next_contig(&cr, &err)) {
+    if (br.header().name[(size_t)cr.tid] != o.chr) continue;
+    auto dump = [&](const char* field, const void* p, size_t bytes) {
+      FILE* f = fopen((o.outfile + "." + field).c_str(), "wb");
+      if (f) { fwrite(p, 1, bytes, f); fclose(f); }
+    };
+    dump("pos", cr.pos.data(), cr.pos.size() * 4); dump("mpos", cr.mpos.data(), cr.mpos.size() * 4); dump("isize", cr.isize.data(), cr.isize.size() * 4);
+    dump("mtid", cr.mtid.data(), cr.mtid.size() * 4); dump("flag", cr.flag.data(), cr.flag.size() * 2); dump("mapq", cr.mapq.data(), cr.mapq.size());
+    dump("cigar_off", cr.cigar_off.data(), cr.cigar_off.size() * 4); dump("cigar", cr.cigar.data(), cr.cigar.size() * 4);
+    dump("qual_off", cr.qual_off.data(), cr.qual_off.size() * 8); dump("qual", cr.qual.data(), cr.qual.size());
+    printf("%s\t%zu reads\n", o.chr.c_str(), cr.n());
+    return 0;
+  }
+  if (!err.empty()) fprintf(stderr, "%s\n", err.c_str());
+  fprintf(stderr, "BAM file doesn't have %s\n", o.chr.c_str());
+  return 1;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  Opt o;
+  if (!parse(argc, argv, &o)) return usage();
+  if (o.function == "decode") return do_decode(o);
+  const int ndev = rsigpu_num_devices();
+  if (ndev <= 0) { fprintf(stderr, "no CUDA device: this implementation has no CPU path\n"); return 2; }
+  const int ng = std::max(1, std::min(o.gpus, ndev));
+  std::vector<rsigpu_ctx*> ctx((size_t)ng, nullptr);
+  for (int g = 0; g < ng; ++g) if (rsigpu_create(g, &o.P, &ctx[(size_t)g])) { fprintf(stderr, "cannot create a context on GPU %d\n", g); return 2; }
+  std::vector<ContigResult> results;
+  std::string err;
+  if (!o.rdfile.empty()) {   // depth-file input: one contig (rsi.cpp:2133-2136, 2192-2195)
+    results.resize(1); results[0].name = o.chr;
+    std::string fasta; std::vector<int32_t> rd;
+    if (!read_fasta(o.reffile, o.chr, &fasta, &err) || !parse_depth_text(o.rdfile, (int)fasta.size(), &rd, &err)) { fprintf(stderr, "%s\n", err.c_str()); return 0; }
+    fprintf(stderr, "#processing %s\n", o.chr.c_str());
+    results[0].done = run_contig(ctx[0], o, o.chr, 0, fasta, &rd, nullptr, &results[0]);
+    if (!results[0].done) fprintf(stderr, "%s\n", results[0].err.c_str());
+  } else {
+    BamReader br(o.threads);
+    if (!br.open(o.bamfile, &err)) { fprintf(stderr, "%s\n", err.c_str()); return 0; }
+    const BamHeader& h = br.header();
+    results.resize(h.name.size());
+    for (size_t i = 0; i < h.name.size(); ++i) results[i].name = h.name[i];
+    if (o.chr != "1-22XY" && std::find(h.name.begin(), h.name.end(), o.chr) == h.name.end()) { fprintf(stderr, "BAM file doesn't have %s\n", o.chr.c_str()); return 0; }
+    // contigs stream out of the file in header order; each GPU has one worker thread that takes the next decoded contig
+    std::mutex mu;
+    std::vector<std::thread> workers((size_t)ng);
+    ContigReads cr;
+    // longest-processing-time assignment from the header lengths (1.038 imbalance for b37 on 8 GPUs)
+    std::vector<int> gpu_of(h.name.size(), 0);
+    {
+      std::vector<size_t> order;
+      for (size_t i = 0; i < h.name.size(); ++i)
+        if (h.name[i].find("MT") == std::string::npos && h.name[i].find(".") == std::string::npos && (o.chr == "1-22XY" || h.name[i] == o.chr)) order.push_back(i);
+      std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return h.len[a] > h.len[b]; });
+      std::vector<long long> load((size_t)ng, 0);
+      for (size_t i : order) { const int g = (int)(std::min_element(load.begin(), load.end()) - load.begin()); gpu_of[i] = g; load[(size_t)g] += h.len[i]; }
+    }
+    while (br.next_contig(&cr, &err)) {
+      const std::string& name = h.name[(size_t)cr.tid];
+      if (name.find("MT") != std::string::npos || name.find(".") != std::string::npos) continue;   // rsi.cpp:2119-2120
+      if (o.chr != "1-22XY" && name != o.chr) continue;
+      const int g = gpu_of[(size_t)cr.tid];
+      if (workers[(size_t)g].joinable()) workers[(size_t)g].join();
+      fprintf(stderr, "#processing %s (%zu reads) on GPU %d\n", name.c_str(), cr.n(), g);
+      ContigReads* mine = new ContigReads(std::move(cr));
+      cr = ContigReads();
+      const int tid = mine->tid;
+      workers[(size_t)g] = std::thread([&, g, tid, mine]() {
+        std::string fasta, e2;
+        ContigResult& r = results[(size_t)tid];
+        if (!read_fasta(o.reffile, r.name, &fasta, &e2)) r.err = e2;
+        else {
+          if ((int)fasta.size() != h.len[(size_t)tid]) fprintf(stderr, "reference and target not same size %zu\t%d\n", fasta.size(), h.len[(size_t)tid]);
+          r.done = run_contig(ctx[(size_t)g], o, r.name, tid, fasta, nullptr, mine, &r);
+        }
+        if (!r.done) { std::lock_guard<std::mutex> lk(mu); fprintf(stderr, "%s: %s\n", r.name.c_str(), r.err.c_str()); }
+        delete mine;
+      });
+    }
+    for (auto& w : workers) if (w.joinable()) w.join();
+    if (!err.empty()) fprintf(stderr, "%s\n", err.c_str());
+  }
+  write_table(o, results);
+  fprintf(stderr, "output written to %s\n", o.outfile.c_str());
+  for (rsigpu_ctx* c : ctx) rsigpu_destroy(c);
+  return 0;
+}

@@ -1,0 +1,93 @@
+"""The C++ host program (rsicnv_b200/bin/rsicnv): BGZF/BAM decoding and argument handling without a GPU;
+with a GPU, the whole CLI against the unmodified reference CLI on the same files (tables must be identical
+apart from the `#input` line, which echoes the path)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from bind import REF_BAMTOOL, REF_BIN, have_ref
+from rsicnv_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "rsicnv_b200", "bin", "rsicnv")
+FIELDS = (("pos", np.int32), ("mpos", np.int32), ("isize", np.int32), ("mtid", np.int32), ("flag", np.uint16), ("mapq", np.uint8),
+          ("cigar_off", np.uint32), ("cigar", np.uint32), ("qual_off", np.uint64), ("qual", np.uint8))
+
+
+@pytest.fixture(scope="module")
+def cli():
+    if not os.path.exists(CLI):
+        subprocess.run(["make", "-s", "cli"], cwd=ROOT, check=True)
+    return CLI
+
+
+def test_bam_decoder_round_trip(cli, tmp_path):
+    r1, _ = synth.make_reads(400_000, 3, None, coverage=6, n_events=0, tid=0)
+    r2, _ = synth.make_reads(500_000, 4, None, coverage=3, n_events=0, tid=1, frac_indel=0.3)
+    bam = str(tmp_path / "t.bam")
+    synth.write_bam(bam, [("1", 400_000), ("2", 500_000), ("MT", 1000)], {0: r1, 1: r2})
+    for name, want in (("1", r1), ("2", r2)):
+        out = subprocess.run([cli, "decode", "-b", bam, "-c", name, "-o", str(tmp_path / "d")], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        for f, dt in FIELDS:
+            assert np.array_equal(np.fromfile(str(tmp_path / ("d." + f)), dtype=dt), want[f]), (name, f)
+    out = subprocess.run([cli, "decode", "-b", bam, "-c", "7", "-o", str(tmp_path / "d")], capture_output=True, text=True)
+    assert out.returncode != 0 and "doesn't have 7" in out.stderr
+
+
+def test_argument_errors(cli, tmp_path):
+    for args, msg in ((["rsi"], "need input file"), (["rsi", "-b", "x.bam"], "need reference file"), (["rsi", "-d", "x.rd", "-f", "x.fa"], "must be specified together"),
+                      (["rsi", "-b", "x.bam", "-f", "x.fa", "-bogus"], "unknown option -bogus"), (["plot", "-b", "x.bam"], "no such function")):
+        out = subprocess.run([cli] + args, capture_output=True, text=True)
+        assert msg in out.stderr, (args, out.stderr)
+
+
+def _table(path):
+    return [ln for ln in open(path).read().splitlines() if not ln.startswith("#input")]
+
+
+@pytest.mark.gpu
+def test_cli_bam_two_contigs_matches_reference(cli, tmp_path):
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    L1, L2 = 10_600_000, 10_450_000
+    fa1 = synth.make_fasta(L1, 3); fa2 = synth.make_fasta(L2, 4)
+    r1, _ = synth.make_reads(L1, 3, fa1, coverage=12, n_events=6, lens=(3000, 8000, 20000), tid=0)
+    r2, _ = synth.make_reads(L2, 4, fa2, coverage=10, n_events=5, lens=(3000, 8000, 20000), tid=1)
+    bam = str(tmp_path / "t.bam"); fasta = str(tmp_path / "t.fa")
+    synth.write_bam(bam, [("1", L1), ("2", L2), ("MT", 16569), ("GL000207.1", 4262)], {0: r1, 1: r2})
+    synth.write_fasta_multi(fasta, [("1", fa1), ("2", fa2)])
+    subprocess.run([REF_BAMTOOL, "index", bam], check=True)
+    common = ["rsi", "-b", bam, "-f", fasta, "-q", "0", "-Q", "10", "-np"]
+    subprocess.run([REF_BIN] + common + ["-o", str(tmp_path / "ref.txt")], check=True, capture_output=True)
+    out = subprocess.run([cli] + common + ["-gpus", "2", "-o", str(tmp_path / "ours.txt")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert _table(str(tmp_path / "ours.txt")) == _table(str(tmp_path / "ref.txt"))
+    assert len(_table(str(tmp_path / "ours.txt"))) > 6
+    # one chromosome only, other knobs
+    common = ["rsi", "-b", bam, "-f", fasta, "-c", "2", "-m", "51", "-NOGC", "-MED", "-np"]
+    subprocess.run([REF_BIN] + common + ["-o", str(tmp_path / "ref2.txt")], check=True, capture_output=True)
+    out = subprocess.run([cli] + common + ["-o", str(tmp_path / "ours2.txt")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert _table(str(tmp_path / "ours2.txt")) == _table(str(tmp_path / "ref2.txt"))
+
+
+@pytest.mark.gpu
+def test_cli_depth_file_matches_reference(cli, tmp_path):
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    L = 3_000_017
+    fa = synth.make_fasta(L, 5)
+    d, _ = synth.make_depth(L, 5, fa, n_events=12, lens=(2000, 5000, 10000, 30000))
+    fasta = str(tmp_path / "c.fa"); rd = str(tmp_path / "c.rd")
+    synth.write_fasta(fasta, "19", fa)
+    synth.write_depth_file(rd, d)
+    with open(rd, "a") as f:
+        f.write("# a comment\n\n12\tjunk\nnot a number\n")     # parser corner cases of loaddata.cpp:506-517
+    common = ["rsi", "-d", rd, "-c", "19", "-f", fasta, "-m", "101", "-np"]
+    subprocess.run([REF_BIN] + common + ["-o", str(tmp_path / "ref.txt")], check=True, capture_output=True)
+    out = subprocess.run([cli] + common + ["-o", str(tmp_path / "ours.txt")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert open(str(tmp_path / "ours.txt")).read() == open(str(tmp_path / "ref.txt")).read()
