@@ -8,14 +8,16 @@
 //   RDmedian / RDsd in main()          rsi.cpp:2202-2203        k_chr_stats (from the value histograms: exact integer sums)
 //
 // One pass over the compacted depth (4 B/base read; capped values are written back only where they
-// changed).  The strided sub-sample histograms use private shared-memory columns [value][thread]
-// with a fixed class per thread (thread t counts the bases whose compacted index is t mod 31).
+// changed).  The 31 strided sub-sample histograms live in one private [class][value] table per warp:
+// a warp counts 31 CONSECUTIVE bases per step, which fall into 31 different classes, so the plain
+// read-modify-writes of its lanes never collide.
 #pragma once
 #include "k_load.cuh"
 
 namespace rsigpu {
 
-enum { C_NT = 256, C_K = 256, C_CT = 248 /* 8 * 31 counting threads */, C_TP = 8192 /* max staged bases */ };
+enum { C_NT = 512, C_NW = C_NT / 32, C_K = 128, C_TP = 8192 /* max staged bases */ };
+#define RSI_SMEM_C ((size_t)C_NW * MAD_CLASSES * C_K * 2 + (size_t)C_TP * 4)
 
 __device__ __forceinline__ i64 warp_sum_i64(i64 v) {
 #pragma unroll
@@ -29,16 +31,16 @@ __global__ void __launch_bounds__(C_NT) k_bins(int* __restrict__ rdc, float* __r
                                                 i64* __restrict__ bin_sum, u32* chist, u32* thist, DevState* st, int bins_per_tile) {
   RSI_DYN_SMEM(smem);
   RSI_CTA_SETUP(c);
-  u16* col = reinterpret_cast<u16*>(smem);                 // [C_K][C_NT]
-  int* vals = reinterpret_cast<int*>(smem + (size_t)C_K * C_NT * 2);
+  u16* ct = reinterpret_cast<u16*>(smem);                  // [C_NW][MAD_CLASSES][C_K]
+  int* vals = reinterpret_cast<int*>(smem + (size_t)C_NW * MAD_CLASSES * C_K * 2);
   const int tid = c.tid, lane = tid & 31, warp = tid >> 5;
   const int Lc = st->Lc, m = st->m, nb = st->nb, R = st->chist_R, cap_on = st->cap_on, capv = st->capv;
   const double thr = st->cap_thr;
   const int sub31 = MAD_CLASSES * (Lc / MAD_CLASSES);
   int wb = 0;
   if (R > C_K) { wb = (int)st->cap_median - C_K / 2; if (wb < 0) wb = 0; if (wb > R - C_K) wb = R - C_K; }
-  for (int k = tid; k < C_K * C_NT; k += C_NT) col[k] = 0;
-  const int cls = tid % MAD_CLASSES, sl = tid / MAD_CLASSES;   // counting threads: tid < C_CT
+  for (int k = tid; k < C_NW * MAD_CLASSES * C_K; k += C_NT) ct[k] = 0;
+  u16* wt = ct + (size_t)warp * MAD_CLASSES * C_K;
   i64 mx = 0;
   const int ntiles = nb > 0 ? (nb + bins_per_tile - 1) / bins_per_tile : 1;
   for (int tile = (int)blockIdx.x; tile < ntiles; tile += (int)gridDim.x) {
@@ -49,12 +51,12 @@ __global__ void __launch_bounds__(C_NT) k_bins(int* __restrict__ rdc, float* __r
     for (int q0 = 0; q0 < np; q0 += C_TP) {                    // (only the tail of a tiny contig can exceed C_TP)
       const int nq = imin(C_TP, np - q0);
       if (q0) c.sync();
-      for (int qb = 0; qb < nq; qb += C_NT * 8) {   // 8 independent loads in flight per thread before any (aliasing) store
-        int v[8];
+      for (int qb = 0; qb < nq; qb += C_NT * 4) {   // 4 independent loads in flight per thread before any (aliasing) store
+        int v[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { const int q = qb + k * C_NT + tid; v[k] = q < nq ? rdc[B + q0 + q] : 0; }
+        for (int k = 0; k < 4; ++k) { const int q = qb + k * C_NT + tid; v[k] = q < nq ? rdc[B + q0 + q] : 0; }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < 4; ++k) {
           const int q = qb + k * C_NT + tid;
           if (q >= nq) continue;
           if (cap_on && (double)v[k] > thr) { v[k] = capv; rdc[B + q0 + q] = capv; }
@@ -62,18 +64,22 @@ __global__ void __launch_bounds__(C_NT) k_bins(int* __restrict__ rdc, float* __r
         }
       }
       c.sync();
-      if (tid < C_CT) {
+      {
         const int Bq = B + q0;
-        int first = cls - Bq % MAD_CLASSES; if (first < 0) first += MAD_CLASSES;
-        for (int q = first + MAD_CLASSES * sl; q < nq; q += C_CT) {
-          const int v = vals[q], w = v - wb;
-          if (Bq + q >= sub31) { if (v >= 0 && v < R) atomicAdd(&thist[v], 1u); }
-          else if ((unsigned)w < (unsigned)C_K) col[w * C_NT + tid] += 1;
-          else if (v >= 0 && v < R) atomicAdd(&chist[cls * R + v], 1u);
+        // warp-steps of 31 consecutive bases: 31 distinct classes, lane 31 idles
+        for (int s0 = warp * 31; s0 < nq; s0 += C_NW * 31) {
+          const int q = s0 + lane;
+          if (lane < 31 && q < nq) {
+            const int v = vals[q], w = v - wb, cls = (Bq + q) % MAD_CLASSES;
+            if (Bq + q >= sub31) { if (v >= 0 && v < R) atomicAdd(&thist[v], 1u); }
+            else if ((unsigned)w < (unsigned)C_K) wt[cls * C_K + w] += 1;
+            else if (v >= 0 && v < R) atomicAdd(&chist[cls * R + v], 1u);
+          }
+          __syncwarp();
         }
       }
       if (q0 == 0) {
-        for (int b = warp; b < nbt; b += C_NT / 32) {
+        for (int b = warp; b < nbt; b += C_NW) {
           const int* x = vals + b * m;
           int lo = 0x7fffffff, hi = -0x7fffffff - 1; i64 s = 0;
           for (int j = lane; j < m; j += 32) { const int v = x[j]; lo = imin(lo, v); hi = imax(hi, v); s += v; }
@@ -95,7 +101,7 @@ __global__ void __launch_bounds__(C_NT) k_bins(int* __restrict__ rdc, float* __r
   for (int item = tid; item < MAD_CLASSES * C_K; item += C_NT) {
     const int cl = item / C_K, w = item % C_K;
     u32 s = 0;
-    for (int k = 0; k < C_CT / MAD_CLASSES; ++k) s += col[w * C_NT + cl + MAD_CLASSES * k];
+    for (int k = 0; k < C_NW; ++k) s += ct[((size_t)k * MAD_CLASSES + cl) * C_K + w];
     if (s && wb + w < R) atomicAdd(&chist[cl * R + wb + w], s);
   }
   mx = c.reduce(mx, MaxOp());

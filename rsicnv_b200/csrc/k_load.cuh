@@ -8,10 +8,11 @@
 //
 // Layout in HBM: raw depth int32[L] and FASTA bytes[L] (both padded to a multiple of 16 bytes and a
 // further 256 bytes so vector loads never leave the allocation); the compacted depth int32[Lc].
-// The histogram-type accumulations (GC strata table, value histogram) use per-thread PRIVATE
-// columns in shared memory (entry [key][thread], conflict-free, no atomics): neighbouring bases
-// have nearly equal keys, so shared/global atomics would serialise.  Columns are flushed once per
-// block at the end of a persistent loop over tiles.
+// The histogram-type accumulations (GC strata table, value histogram) use one PRIVATE table per WARP in
+// shared memory: a warp handles 32 consecutive bases per step, lanes with the same key are merged with
+// __match_any_sync / __reduce_add_sync and the group leader does a plain read-modify-write -- no atomics
+// (neighbouring bases have nearly equal keys, so shared/global atomics would serialise).  Tables are
+// flushed once per block at the end of a persistent loop over tiles.
 #pragma once
 #include "cta.cuh"
 #include "state.cuh"
@@ -25,7 +26,7 @@ namespace rsigpu {
   c.tid = (int)threadIdx.x; c.nthr = (int)blockDim.x; c.red = cta_red_; c.bc = cta_bc_;
 
 enum { LD_TILE = 4096, LD_FAB = LD_TILE + 240, LD_PRE = LD_TILE + 208 };
-enum { A_NT = 128, B_NT = 256, B_K = 128 };
+enum { A_NT = 512, A_NW = A_NT / 32, B_NT = 512, B_NW = B_NT / 32, B_K = 256 };
 
 // ---------------------------------------------------------------------------------------------
 // N runs of the contig (uppercase 'N' only): run starts and run ends are appended (unordered) to two
@@ -70,42 +71,42 @@ __device__ int tile_gc_prefix(const Cta& c, const u8* __restrict__ fa, int L, in
 
 // ---------------------------------------------------------------------------------------------
 // Pass A: mean of the positive depths and the per-stratum depth sums / counts (5 B/base read).
-// Private columns: col[g * A_NT + tid] packs (count << 40 | sum).
+// Dynamic shared memory: tsum[A_NW][GC_STRATA] u64 | tcnt[A_NW][GC_STRATA] u32 | fab | pre
+#define RSI_SMEM_A ((size_t)A_NW * GC_STRATA * 12 + LD_FAB + (LD_PRE + 8) * 2)
 __global__ void __launch_bounds__(A_NT) k_gc_table(const int* __restrict__ rd, const u8* __restrict__ fa, DevState* st) {
   RSI_DYN_SMEM(smem);
   RSI_CTA_SETUP(c);
   const int L = st->L, do_gc = st->gc_on;
-  u64* col = reinterpret_cast<u64*>(smem);
-  u8* fab = smem + (size_t)GC_STRATA * A_NT * 8;
+  u64* tsum = reinterpret_cast<u64*>(smem);
+  u32* tcnt = reinterpret_cast<u32*>(tsum + A_NW * GC_STRATA);
+  u8* fab = reinterpret_cast<u8*>(tcnt + A_NW * GC_STRATA);
   u16* pre = reinterpret_cast<u16*>(fab + LD_FAB);
-  const int tid = c.tid;
-  if (do_gc) for (int k = tid; k < GC_STRATA * A_NT; k += A_NT) col[k] = 0ull;
+  const int tid = c.tid, lane = tid & 31, warp = tid >> 5;
+  if (do_gc) for (int k = tid; k < A_NW * GC_STRATA; k += A_NT) { tsum[k] = 0ull; tcnt[k] = 0u; }
+  u64* wsum = tsum + warp * GC_STRATA; u32* wcnt = tcnt + warp * GC_STRATA;
   u64 psum = 0, pcnt = 0;
   int vmin = 0x7fffffff, vmax = -0x7fffffff - 1;
   const int ntiles = (L + LD_TILE - 1) / LD_TILE;
   for (int tile = (int)blockIdx.x; tile < ntiles; tile += (int)gridDim.x) {
     const int t0 = tile * LD_TILE, t1 = imin(t0 + LD_TILE, L);
-    int4 v[LD_TILE / 4 / A_NT];
+    int v[LD_TILE / A_NT];
 #pragma unroll
-    for (int j = 0; j < LD_TILE / 4 / A_NT; ++j) v[j] = reinterpret_cast<const int4*>(rd + t0)[j * A_NT + tid];
+    for (int j = 0; j < LD_TILE / A_NT; ++j) v[j] = rd[t0 + warp * (LD_TILE / A_NW) + j * 32 + lane];   // a warp owns 256 consecutive bases
     int wlo = 0;
     if (do_gc) { c.sync(); wlo = tile_gc_prefix(c, fa, L, t0, t1, fab, pre); }
 #pragma unroll
-    for (int j = 0; j < LD_TILE / 4 / A_NT; ++j) {
-      const int p0 = t0 + 4 * (j * A_NT + tid);
-      const int vv[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int p = p0 + e;
-        if (p >= t1) continue;
-        const int x = vv[e];
-        vmin = imin(vmin, x); vmax = imax(vmax, x);
-        if (x > 0) { psum += (u64)x; pcnt += 1; }
-        if (do_gc) {
-          const int lo = gc_lo(p, L) - wlo;
-          const int g = (int)pre[lo + GC_WIN] - (int)pre[lo];
-          col[g * A_NT + tid] += (u64)(u32)(x & 0xffffff) | (1ull << 40);
-        }
+    for (int j = 0; j < LD_TILE / A_NT; ++j) {
+      const int p = t0 + warp * (LD_TILE / A_NW) + j * 32 + lane;
+      const bool valid = p < t1;
+      const int x = v[j];
+      if (valid) { vmin = imin(vmin, x); vmax = imax(vmax, x); if (x > 0) { psum += (u64)x; pcnt += 1; } }
+      if (do_gc) {
+        int g = 0x10000 + lane;    // invalid lanes: a key nobody shares
+        if (valid) { const int lo = gc_lo(p, L) - wlo; g = (int)pre[lo + GC_WIN] - (int)pre[lo]; }
+        const unsigned m = __match_any_sync(0xffffffffu, g);
+        const int sum = __reduce_add_sync(m, valid ? (x & 0xffffff) : 0);
+        if (valid && lane == __ffs((int)m) - 1) { wsum[g] += (u64)(u32)sum; wcnt[g] += (u32)__popc(m); }
+        __syncwarp();
       }
     }
   }
@@ -113,10 +114,7 @@ __global__ void __launch_bounds__(A_NT) k_gc_table(const int* __restrict__ rd, c
   if (do_gc) {
     for (int g = tid; g < GC_STRATA; g += A_NT) {
       u64 s = 0, n = 0;
-      for (int j = 0; j < A_NT; ++j) {
-        const u64 e = col[g * A_NT + ((j + tid) & (A_NT - 1))];
-        s += e & ((1ull << 40) - 1); n += e >> 40;
-      }
+      for (int w = 0; w < A_NW; ++w) { s += tsum[w * GC_STRATA + g]; n += tcnt[w * GC_STRATA + g]; }
       if (n) { atomicAdd(&st->gc_sum[g], s); atomicAdd(&st->gc_cnt[g], n); }
     }
   }
@@ -159,6 +157,8 @@ __global__ void k_gc_finalize(const u8* __restrict__ fa, DevState* st) {
 // Pass B: GC adjust (out-of-place map + the 21st pseudo-slice quirk), value histogram of
 // ALL positions for apply_cap's median, and the N-compacted store (9 B/base: 4+1 read, 4 written).
 // noseq intervals: nbeg/nend (0-based inclusive), ncum[k] = bases removed by intervals 0..k-1.
+// Dynamic shared memory: vh[B_NW][B_K] u32 | tab[GC_STRATA] f64 | fab | pre
+#define RSI_SMEM_B ((size_t)B_NW * B_K * 4 + GC_STRATA * 8 + LD_FAB + (LD_PRE + 8) * 2)
 __global__ void __launch_bounds__(B_NT) k_gc_adjust(const int* __restrict__ rd, const u8* __restrict__ fa, int* __restrict__ rdc,
                                                      const int* __restrict__ nbeg, const int* __restrict__ nend, const int* __restrict__ ncum,
                                                      u32* hist_all, DevState* st) {
@@ -166,24 +166,25 @@ __global__ void __launch_bounds__(B_NT) k_gc_adjust(const int* __restrict__ rd, 
   RSI_CTA_SETUP(c);
   __shared__ int s_k0, s_hasn;
   const int L = st->L, do_gc = st->gc_on, nn = st->n_noseq;
-  u16* col = reinterpret_cast<u16*>(smem);                          // [B_K][B_NT]
-  double* tab = reinterpret_cast<double*>(smem + (size_t)B_K * B_NT * 2);
+  u32* vh = reinterpret_cast<u32*>(smem);                          // [B_NW][B_K]
+  double* tab = reinterpret_cast<double*>(smem + (size_t)B_NW * B_K * 4);
   u8* fab = reinterpret_cast<u8*>(tab + GC_STRATA);
   u16* pre = reinterpret_cast<u16*>(fab + LD_FAB);
-  const int tid = c.tid;
-  for (int k = tid; k < B_K * B_NT; k += B_NT) col[k] = 0;
+  const int tid = c.tid, lane = tid & 31, warp = tid >> 5;
+  for (int k = tid; k < B_NW * B_K; k += B_NT) vh[k] = 0;
   for (int g = tid; g < GC_STRATA; g += B_NT) tab[g] = st->gc_tab[g];
+  u32* wh = vh + warp * B_K;
   const double mean = st->rdmean;
   const int hb = st->hist_base, s20 = st->s20, r20 = st->r20, gstar = st->gstar;
   const int q0 = s20 + r20 - GC_WIN;   // first overwritten position of the pseudo-slice (r20 >= 2)
-  u32 zeros = 0;
   int bad = 0;
+  u32 zeros = 0;
   const int ntiles = (L + LD_TILE - 1) / LD_TILE;
   for (int tile = (int)blockIdx.x; tile < ntiles; tile += (int)gridDim.x) {
     const int t0 = tile * LD_TILE, t1 = imin(t0 + LD_TILE, L);
-    int4 v[LD_TILE / 4 / B_NT];
+    int v[LD_TILE / B_NT];
 #pragma unroll
-    for (int j = 0; j < LD_TILE / 4 / B_NT; ++j) v[j] = reinterpret_cast<const int4*>(rd + t0)[j * B_NT + tid];
+    for (int j = 0; j < LD_TILE / B_NT; ++j) v[j] = rd[t0 + warp * (LD_TILE / B_NW) + j * 32 + lane];
     c.sync();
     if (tid == 0) {  // first interval that ends at or after t0
       int lo = 0, hi = nn;
@@ -195,14 +196,12 @@ __global__ void __launch_bounds__(B_NT) k_gc_adjust(const int* __restrict__ rd, 
     const int k0 = s_k0, hasn = s_hasn;
     const int shift0 = k0 < nn ? ncum[k0] : (nn ? ncum[nn - 1] + (nend[nn - 1] - nbeg[nn - 1] + 1) : 0);
 #pragma unroll
-    for (int j = 0; j < LD_TILE / 4 / B_NT; ++j) {
-      const int p0 = t0 + 4 * (j * B_NT + tid);
-      const int vv[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int p = p0 + e;
-        if (p >= t1) continue;
-        int x = vv[e];
+    for (int j = 0; j < LD_TILE / B_NT; ++j) {
+      const int p = t0 + warp * (LD_TILE / B_NW) + j * 32 + lane;
+      const bool valid = p < t1;
+      int x = v[j];
+      int key = 0x10000 + lane;      // lanes without an in-window value: a key nobody shares
+      if (valid) {
         if (do_gc && p < s20) {
           int g;
           if (r20 >= 2 && p >= q0 && p < q0 + r20) { x = rd[p + GC_WIN - r20]; g = gstar; }
@@ -211,9 +210,10 @@ __global__ void __launch_bounds__(B_NT) k_gc_adjust(const int* __restrict__ rd, 
         }
         // value histogram over every position (N bases included)
         const int w = x - hb;
-        if (x == 0) ++zeros;
-        else if ((unsigned)w < (unsigned)B_K) col[w * B_NT + tid] += 1;
-        else { if (x >= HIST_ALL_BINS || x < 0) { bad = 1; } else atomicAdd(&hist_all[x], 1u); }
+        if ((unsigned)w < (unsigned)B_K) key = w;
+        else if (x == 0) key = 0x8000;                 // zeros below the window (N stretches): merged per warp, counted in a register
+        else if (x >= HIST_ALL_BINS || x < 0) bad = 1;
+        else atomicAdd(&hist_all[x], 1u);
         // N-compacted store
         int cidx;
         if (!hasn) cidx = p - shift0;
@@ -224,21 +224,21 @@ __global__ void __launch_bounds__(B_NT) k_gc_adjust(const int* __restrict__ rd, 
         }
         if (cidx >= 0) rdc[cidx] = x;
       }
+      const unsigned m = __match_any_sync(0xffffffffu, key);
+      if (lane == __ffs((int)m) - 1) { if (key < B_K) wh[key] += (u32)__popc(m); else if (key == 0x8000) zeros += (u32)__popc(m); }
+      __syncwarp();
     }
   }
   c.sync();
   for (int w = tid; w < B_K; w += B_NT) {
     u32 s = 0;
-    for (int j = 0; j < B_NT; ++j) s += col[w * B_NT + ((j + 2 * tid) & (B_NT - 1))];
-    if (s && hb + w != 0) atomicAdd(&hist_all[hb + w], s);
-    if (s && hb + w == 0) zeros += s;
+    for (int k = 0; k < B_NW; ++k) s += vh[k * B_K + w];
+    if (s) atomicAdd(&hist_all[hb + w], s);
   }
-  zeros = c.reduce(zeros, SumOp());
   bad = c.reduce(bad, MaxOp());
-  if (tid == 0) {
-    if (zeros) atomicAdd(&hist_all[0], zeros);
-    if (bad) atomicOr(&st->err, (int)ERR_HIST_RANGE);
-  }
+  zeros = c.reduce(zeros, SumOp());
+  if (tid == 0 && zeros) atomicAdd(&hist_all[0], zeros);
+  if (tid == 0 && bad) atomicOr(&st->err, (int)ERR_HIST_RANGE);
 }
 
 // ---------------------------------------------------------------------------------------------

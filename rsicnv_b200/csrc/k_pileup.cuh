@@ -66,68 +66,94 @@ __device__ __forceinline__ u32 qual_ge4(u32 w, u32 thr4, bool all, bool none) {
 #endif
 }
 
-__global__ void __launch_bounds__(PU_NT) k_pileup_tile(ReadSoA R, int* __restrict__ rd, int L, int minq, int min_baseQ, const int* max_extent) {
-  RSI_CTA_SETUP(c);
-  __shared__ int diff[PU_T + 1 + (PU_T + 1) / 32 + 1];   // entry i lives at i + i/32: conflict-free 32-per-thread scan
-#define PU_DI(i) ((i) + ((i) >> 5))
-  __shared__ int s_r0, s_r1;
+// first / one-past-last read that can touch each position tile (reads with pos in [t0 - max_extent, t1))
+__global__ void k_tile_ranges(ReadSoA R, int L, const int* max_extent, int2* __restrict__ range) {
   const int ntiles = (L + PU_T - 1) / PU_T;
   const int ext = *max_extent;
+  for (int tile = (int)(blockIdx.x * blockDim.x + threadIdx.x); tile < ntiles; tile += (int)(gridDim.x * blockDim.x)) {
+    const int t0 = tile * PU_T, t1 = imin(t0 + PU_T, L);
+    i64 lo = 0, hi = R.n; const int want = t0 - ext;
+    while (lo < hi) { i64 mid = (lo + hi) >> 1; if (R.pos[mid] < want) lo = mid + 1; else hi = mid; }
+    const i64 r0 = lo;
+    hi = R.n;
+    while (lo < hi) { i64 mid = (lo + hi) >> 1; if (R.pos[mid] < t1) lo = mid + 1; else hi = mid; }
+    range[tile] = make_int2((int)r0, (int)lo);
+  }
+}
+
+enum { PU_QS = 32768 };   // bytes of quality strings staged in shared memory per batch of reads
+__global__ void __launch_bounds__(PU_NT) k_pileup_tile(ReadSoA R, int* __restrict__ rd, int L, int minq, int min_baseQ, const int2* __restrict__ range) {
+  RSI_CTA_SETUP(c);
+  RSI_DYN_SMEM(qs);       // PU_QS + 16 bytes
+  __shared__ int diff[PU_T + 1 + (PU_T + 1) / 32 + 1];   // entry i lives at i + i/32: conflict-free 32-per-thread scan
+#define PU_DI(i) ((i) + ((i) >> 5))
+  const int ntiles = (L + PU_T - 1) / PU_T;
   const bool q_all = min_baseQ <= 0, q_none = min_baseQ > 255;
   const u32 qthr4 = (u32)(min_baseQ & 0xff) * 0x01010101u;
   for (int tile = (int)blockIdx.x; tile < ntiles; tile += (int)gridDim.x) {
     const int t0 = tile * PU_T, t1 = imin(t0 + PU_T, L);
     c.sync();
     for (int k = c.tid; k < PU_T + 1 + (PU_T + 1) / 32 + 1; k += PU_NT) diff[k] = 0;
-    if (c.tid == 0) {  // reads with pos in [t0 - ext, t1)
-      i64 lo = 0, hi = R.n; const int want = t0 - ext;
-      while (lo < hi) { i64 mid = (lo + hi) >> 1; if (R.pos[mid] < want) lo = mid + 1; else hi = mid; }
-      s_r0 = (int)lo;
-      hi = R.n;
-      while (lo < hi) { i64 mid = (lo + hi) >> 1; if (R.pos[mid] < t1) lo = mid + 1; else hi = mid; }
-      s_r1 = (int)lo;
-    }
-    c.sync();
-    for (int r = s_r0 + c.tid; r < s_r1; r += PU_NT) {
-      const int pos = R.pos[r];
-      if (pos == 0) continue;
-      if ((int)R.mapq[r] < minq) continue;
-      const int fl = R.flag[r];
-      if (fl & (BF_SECONDARY | BF_DUP)) continue;
-      const u32 c0 = R.cigar_off[r], c1 = R.cigar_off[r + 1];
-      // reference / query coordinate at the start of each op
-      u32 k = c0, q = 0;
-      while (k < c1) { const u32 op = R.cigar[k] & 15u; if (op == 0 || op == 2 || op == 7 || op == 8) break; if (op == 1 || op == 4) q += R.cigar[k] >> 4; ++k; }
-      if (k == c1) continue;                       // no M/D/=/X op: nothing is counted
-      u32 e = (u32)pos + 1;
-      const u8* qual = R.qual + R.qual_off[r];
-      for (; k < c1; ++k) {
-        const u32 op = R.cigar[k] & 15u, l = R.cigar[k] >> 4;
-        if (op == 0 || op == 7) {
-          int p = (int)e - 1;                      // 0-based position of the op's first base
-          // maximal stretches of bases with quality >= Q, clipped to the tile and to L
-          const int jb = imax(0, t0 - p), je = imin((int)l, imin(t1, L) - p);
-          int open = -1;
-          const u8* qp = qual + q;
-          int j = jb;
-          // bytes up to the next 4-byte boundary, then whole words (four quality tests per compare), then the tail
-          while (j < je) {
-            if ((((size_t)(qp + j)) & 3) == 0 && j + 4 <= je) {
-              const u32 w = *reinterpret_cast<const u32*>(qp + j);
-              const u32 m = qual_ge4(w, qthr4, q_all, q_none);
-              if (m == 0xffffffffu) { if (open < 0) open = j; j += 4; continue; }
-              if (m == 0u) { if (open >= 0) { atomicAdd(&diff[PU_DI(p + open - t0)], 1); atomicAdd(&diff[PU_DI(p + j - t0)], -1); open = -1; } j += 4; continue; }
-            }
-            const bool ok = (int)qp[j] >= min_baseQ;
-            if (ok && open < 0) open = j;
-            if (!ok && open >= 0) { atomicAdd(&diff[PU_DI(p + open - t0)], 1); atomicAdd(&diff[PU_DI(p + j - t0)], -1); open = -1; }
-            ++j;
-          }
-          if (open >= 0) { atomicAdd(&diff[PU_DI(p + open - t0)], 1); atomicAdd(&diff[PU_DI(p + je - t0)], -1); }
-        }
-        if (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) q += l;
-        if (op == 0 || op == 2 || op == 3 || op == 4) e += l;
+    const int2 rr = range[tile];
+    int rb = rr.x;
+    while (rb < rr.y) {
+      // batch of consecutive reads whose quality strings (contiguous in HBM) fit the staging buffer:
+      // one coalesced 16-byte-vector copy HBM -> shared memory, then every thread walks its own read there
+      int nrd = imin(PU_NT, rr.y - rb);
+      const u64 q0 = R.qual_off[rb];
+      while (nrd > 1 && R.qual_off[rb + nrd] - q0 > (u64)PU_QS) nrd >>= 1;
+      const u64 q1 = R.qual_off[rb + nrd];
+      const bool staged = q1 - q0 <= (u64)PU_QS;
+      const u64 a0 = q0 & ~(u64)15;
+      c.sync();
+      if (staged) {
+        const int nvec = (int)((q1 - a0 + 15) >> 4);
+        const uint4* src = reinterpret_cast<const uint4*>(R.qual + a0);
+        uint4* dst = reinterpret_cast<uint4*>(qs);
+        for (int v = c.tid; v < nvec; v += PU_NT) dst[v] = src[v];
       }
+      c.sync();
+      const int r = rb + c.tid;
+      if (c.tid < nrd) {
+        const int pos = R.pos[r];
+        const int fl = R.flag[r];
+        const u32 c0 = R.cigar_off[r], c1 = R.cigar_off[r + 1];
+        if (pos != 0 && (int)R.mapq[r] >= minq && !(fl & (BF_SECONDARY | BF_DUP))) {
+          // reference / query coordinate at the start of each op
+          u32 k = c0, q = 0;
+          while (k < c1) { const u32 op = R.cigar[k] & 15u; if (op == 0 || op == 2 || op == 7 || op == 8) break; if (op == 1 || op == 4) q += R.cigar[k] >> 4; ++k; }
+          u32 e = (u32)pos + 1;
+          const u8* qual = staged ? (qs + (R.qual_off[r] - a0)) : (R.qual + R.qual_off[r]);
+          for (; k < c1; ++k) {      // (no M/D/=/X op: k == c1, nothing is counted)
+            const u32 op = R.cigar[k] & 15u, l = R.cigar[k] >> 4;
+            if (op == 0 || op == 7) {
+              int p = (int)e - 1;                      // 0-based position of the op's first base
+              // maximal stretches of bases with quality >= Q, clipped to the tile and to L
+              const int jb = imax(0, t0 - p), je = imin((int)l, imin(t1, L) - p);
+              int open = -1;
+              const u8* qp = qual + q;
+              int j = jb;
+              // bytes up to the next 4-byte boundary, then whole words (four quality tests per compare), then the tail
+              while (j < je) {
+                if ((((size_t)(qp + j)) & 3) == 0 && j + 4 <= je) {
+                  const u32 w = *reinterpret_cast<const u32*>(qp + j);
+                  const u32 m = qual_ge4(w, qthr4, q_all, q_none);
+                  if (m == 0xffffffffu) { if (open < 0) open = j; j += 4; continue; }
+                  if (m == 0u) { if (open >= 0) { atomicAdd(&diff[PU_DI(p + open - t0)], 1); atomicAdd(&diff[PU_DI(p + j - t0)], -1); open = -1; } j += 4; continue; }
+                }
+                const bool ok = (int)qp[j] >= min_baseQ;
+                if (ok && open < 0) open = j;
+                if (!ok && open >= 0) { atomicAdd(&diff[PU_DI(p + open - t0)], 1); atomicAdd(&diff[PU_DI(p + j - t0)], -1); open = -1; }
+                ++j;
+              }
+              if (open >= 0) { atomicAdd(&diff[PU_DI(p + open - t0)], 1); atomicAdd(&diff[PU_DI(p + je - t0)], -1); }
+            }
+            if (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) q += l;
+            if (op == 0 || op == 2 || op == 3 || op == 4) e += l;
+          }
+        }
+      }
+      rb += nrd;
     }
     c.sync();
     // difference array -> depth, PU_T / PU_NT consecutive positions per thread
@@ -265,7 +291,7 @@ __global__ void __launch_bounds__(1024) k_isize_stats(ReadSoA R, int tid_len, co
 }
 
 // One block per call: Q0 fraction and supporting read pairs.  dis[k] = the carried DIS of call k.
-__global__ void __launch_bounds__(256) k_cnv_stat(ReadSoA R, Cnv* calls, int ncalls, const int* max_extent, DevState* st) {
+__global__ void __launch_bounds__(1024) k_cnv_stat(ReadSoA R, Cnv* calls, int ncalls, const int* max_extent, DevState* st) {
   RSI_CTA_SETUP(c);
   const int im = st->isize_mean, isd = st->isize_sd;
   for (int k = (int)blockIdx.x; k < ncalls; k += (int)gridDim.x) {

@@ -101,7 +101,7 @@ struct rsigpu_ctx {
   std::vector<Cnv> h_detected, h_calls, h_dump[4];
   // reads
   DevVec<int> r_pos, r_mpos, r_isize, r_mtid; DevVec<u16> r_flag; DevVec<u8> r_mapq, r_qual; DevVec<u32> r_cigar_off, r_cigar; DevVec<u64> r_qual_off;
-  DevBuf<int> r_calend;
+  DevBuf<int> r_calend, d_tile_range;
   // accounting
   long long h_cprof[16] = {};
   int64_t launches = 0;
@@ -178,13 +178,14 @@ int set_smem_attrs() {
   static bool done = false;
   if (done) return 0;
   done = true;
-  cudaFuncSetAttribute(k_gc_table, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(GC_STRATA * A_NT * 8 + LD_FAB + (LD_PRE + 8) * 2));
-  cudaFuncSetAttribute(k_gc_adjust, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(B_K * B_NT * 2 + GC_STRATA * 8 + LD_FAB + (LD_PRE + 8) * 2));
-  cudaFuncSetAttribute(k_bins, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(C_K * C_NT * 2 + C_TP * 4));
+  cudaFuncSetAttribute(k_gc_table, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_A);
+  cudaFuncSetAttribute(k_gc_adjust, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_B);
+  cudaFuncSetAttribute(k_bins, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_C);
   cudaFuncSetAttribute(k_cand_a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CAND_SHIST * 4));
   cudaFuncSetAttribute(k_cand_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CAND_SHIST * 4));
   cudaFuncSetAttribute(k_cand_c, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CAND_SHIST * 4));
   cudaFuncSetAttribute(k_cand_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CAND_SHIST * 4));
+  cudaFuncSetAttribute(k_pileup_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PU_QS + 32));
   cudaFuncSetAttribute(k_rsi_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SCAN_SMEM);
   return 0;
 }
@@ -292,7 +293,7 @@ void rsigpu_destroy(rsigpu_ctx* c) {
   c->d_bin_med.release(); c->d_bin_nbn.release(); c->d_lut.release(); c->d_bin_medint.release(); c->d_status.release(); c->d_status1.release();
   c->d_tile.release(); c->d_nz_idx.release(); c->d_nz_val.release(); c->d_runs.release(); c->d_bin_sum.release(); c->d_pfx.release(); c->d_cprof.release(); c->d_minl_del.release(); c->d_minl_dup.release();
   c->d_lists.release(); c->d_misc.release(); c->d_ref.release(); c->d_sub.release(); c->d_pref.release(); c->d_rm.release(); c->d_chist_c.release(); c->d_spec_ref.release(); c->d_spec_pref.release(); c->d_spec_off.release(); c->d_spec_rm.release();
-  c->d_nrun_beg.release(); c->d_nrun_end.release(); c->d_scan_scratch.release(); c->r_calend.release();
+  c->d_nrun_beg.release(); c->d_nrun_end.release(); c->d_scan_scratch.release(); c->d_tile_range.release(); c->r_calend.release();
   c->r_pos.release(); c->r_mpos.release(); c->r_isize.release(); c->r_mtid.release(); c->r_flag.release(); c->r_mapq.release(); c->r_qual.release();
   c->r_cigar_off.release(); c->r_cigar.release(); c->r_qual_off.release();
   if (c->d_st) cudaFree(c->d_st);
@@ -406,7 +407,11 @@ static int run_pileup(rsigpu_ctx* c) {
     CK(c->r_calend.ensure(c->r_pos.n + 8));
     ReadSoA R = read_view(c);
     KL(k_read_ends, grid_for((int)std::min<size_t>(c->r_pos.n, 1u << 30), 256, c->n_sm * 16), 256, 0, R, mx, mx + 1);
-    KL(k_pileup_tile, grid_for(c->L, PU_T, c->n_sm * 4), PU_NT, 0, R, c->d_raw.p, c->L, c->P.minq, c->P.min_baseQ, mx);
+    const int ntile = (c->L + PU_T - 1) / PU_T;
+    CK(c->d_tile_range.ensure((size_t)ntile * 2 + 8));
+    int2* tr = reinterpret_cast<int2*>(c->d_tile_range.p);
+    KL(k_tile_ranges, grid_for(ntile, 128, c->n_sm * 8), 128, 0, R, c->L, mx, tr);
+    KL(k_pileup_tile, grid_for(c->L, PU_T, c->n_sm * 3), PU_NT, (size_t)PU_QS + 32, R, c->d_raw.p, c->L, c->P.minq, c->P.min_baseQ, tr);
   }
   c->have_depth = true;
   return RSIGPU_OK;
@@ -464,15 +469,14 @@ int rsigpu_load_finish(rsigpu_ctx* c) {
   CK(cudaMemsetAsync(c->d_misc.p, 0, 5 * 4, c->stream));
   const int* nbeg = c->d_nseq.p; const int* nend = nbeg + nn; const int* ncum = nbeg + 2 * nn;
   const int ntiles = (L + LD_TILE - 1) / LD_TILE;
-  const size_t smA = (size_t)GC_STRATA * A_NT * 8 + LD_FAB + (LD_PRE + 8) * 2;
-  const size_t smB = (size_t)B_K * B_NT * 2 + GC_STRATA * 8 + LD_FAB + (LD_PRE + 8) * 2;
-  KL(k_gc_table, std::min(ntiles, c->n_sm), A_NT, smA, c->d_raw.p, c->d_fasta.p, c->d_st);
+  const size_t smA = RSI_SMEM_A, smB = RSI_SMEM_B;
+  KL(k_gc_table, std::min(ntiles, c->n_sm * 2), A_NT, smA, c->d_raw.p, c->d_fasta.p, c->d_st);
   KL(k_gc_finalize, 1, 256, 0, c->d_fasta.p, c->d_st);
   KL(k_gc_adjust, std::min(ntiles, c->n_sm * 2), B_NT, smB, c->d_raw.p, c->d_fasta.p, c->d_rdc.p, nbeg, nend, ncum, c->d_hist_all.p, c->d_st);
   KL(k_cap_params, 1, 1024, 0, c->d_hist_all.p, c->d_st, CHIST_RCAP);
   const int bpt = std::max(1, std::min(64, C_TP / m));
   const int ntc = std::max(1, (nb + bpt - 1) / bpt);
-  KL(k_bins, std::min(ntc, c->n_sm), C_NT, (size_t)C_K * C_NT * 2 + C_TP * 4, c->d_rdc.p, c->d_bin_med.p, c->d_bin_medint.p, c->d_bin_sum.p, c->d_chist.p,
+  KL(k_bins, std::min(ntc, c->n_sm), C_NT, RSI_SMEM_C, c->d_rdc.p, c->d_bin_med.p, c->d_bin_medint.p, c->d_bin_sum.p, c->d_chist.p,
      c->d_thist.p, c->d_st, bpt);
   KL(k_chr_stats, 1, 1024, 0, c->d_chist.p, c->d_thist.p, c->d_tothist.p, c->d_st);
   CK(cudaMemcpyAsync(h, c->d_st, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
@@ -594,7 +598,7 @@ int rsigpu_cnv_stat(rsigpu_ctx* c) {
   ReadSoA R = read_view(c);
   int* mx = c->d_misc.p + 5;
   KL(k_isize_stats, 1, 1024, 0, R, c->L, mx, c->d_st);
-  KL(k_cnv_stat, std::min((int)v.size(), c->n_sm * 4), 256, 0, R, d, (int)v.size(), mx, c->d_st);
+  KL(k_cnv_stat, std::min((int)v.size(), c->n_sm * 2), 1024, 0, R, d, (int)v.size(), mx, c->d_st);
   CK(cudaMemcpyAsync(v.data(), d, sizeof(Cnv) * v.size(), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaMemcpyAsync(&c->h_st->isize_mean, field_ptr(c->d_st, &DevState::isize_mean), 8, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));

@@ -82,3 +82,8 @@ def test_chr19_full_size_properties(gpu_lib):
                     hit += 1
                     break
         assert hit >= len(ev) - 3, (hit, len(ev))
+
+
+def test_high_depth_histogram_windows(gpu_lib, oracle):
+    fa, d, _ = make_case(3_000_003, 17, mean=200.0)
+    run_depth_case(gpu_lib, oracle, fa, d)

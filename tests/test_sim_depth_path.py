@@ -52,3 +52,10 @@ def test_low_depth_gives_no_calls(sim_lib, oracle):
     fa, d, _ = make_case(300_000, 13, mean=3.0)
     calls, _ = run_depth_case(sim_lib, oracle, fa, d, check_bins=False)
     assert calls == []
+
+
+def test_high_depth_histogram_windows(sim_lib, oracle):
+    """200x depth: the value-histogram windows of passes B and C no longer start at 0 (zeros of N stretches, values
+    beyond the window and the capped range all take their side paths)"""
+    fa, d, _ = make_case(400_003, 17, mean=200.0)
+    run_depth_case(sim_lib, oracle, fa, d)
