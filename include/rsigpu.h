@@ -155,7 +155,7 @@ int rsigpu_set_profile(rsigpu_ctx* c, int on);
 int rsigpu_get_profile(const rsigpu_ctx* c, char* names, int32_t name_stride, float* ms, int32_t* launches, int32_t cap);
 
 /* test hook: filterstatus' level-0 float sum (rsi.cpp:967-974) as 0 = one sequential FADD chain,
- * 1 = the exact block-scan form (default); both must give identical bits. */
+ * 1 = the exact one-block scan form, 2 = the exact multi-block form (default); all must give identical bits. */
 int rsigpu_set_level0_mode(rsigpu_ctx* c, int mode);
 /* test hook: selected device-resident scalars of the last stage, as doubles; returns how many exist */
 int rsigpu_debug_state(const rsigpu_ctx* c, double* out, int32_t cap);

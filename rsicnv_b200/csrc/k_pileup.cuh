@@ -88,13 +88,15 @@ __global__ void __launch_bounds__(PU_NT) k_pileup_tile(ReadSoA R, int* __restric
   __shared__ int diff[PU_T + 1 + (PU_T + 1) / 32 + 1];   // entry i lives at i + i/32: conflict-free 32-per-thread scan
 #define PU_DI(i) ((i) + ((i) >> 5))
   const int ntiles = (L + PU_T - 1) / PU_T;
-  const bool q_all = min_baseQ <= 0, q_none = min_baseQ > 255;
-  const u32 qthr4 = (u32)(min_baseQ & 0xff) * 0x01010101u;
+  // quality test constants: Q <= 0 passes everything (threshold 0), Q > 255 nothing (handled by skipping the reads)
+  const int Qc = min_baseQ < 0 ? 0 : min_baseQ;
+  const bool q_none = Qc > 255, qhigh = Qc > 128;
+  const u32 qlow4 = (u32)(qhigh ? Qc - 128 : Qc) * 0x01010101u;
   for (int tile = (int)blockIdx.x; tile < ntiles; tile += (int)gridDim.x) {
     const int t0 = tile * PU_T, t1 = imin(t0 + PU_T, L);
     c.sync();
     for (int k = c.tid; k < PU_T + 1 + (PU_T + 1) / 32 + 1; k += PU_NT) diff[k] = 0;
-    const int2 rr = range[tile];
+    const int2 rr = q_none ? make_int2(0, 0) : range[tile];
     int rb = rr.x;
     while (rb < rr.y) {
       // batch of consecutive reads whose quality strings (contiguous in HBM) fit the staging buffer:
@@ -128,25 +130,59 @@ __global__ void __launch_bounds__(PU_NT) k_pileup_tile(ReadSoA R, int* __restric
             const u32 op = R.cigar[k] & 15u, l = R.cigar[k] >> 4;
             if (op == 0 || op == 7) {
               int p = (int)e - 1;                      // 0-based position of the op's first base
-              // maximal stretches of bases with quality >= Q, clipped to the tile and to L
+              // maximal stretches of bases with quality >= Q, clipped to the tile and to L.  Branch-free per chunk of
+              // 128 bases: realign the quality words (PRMT), four quality tests per __vcmpgeu4, one pass bit per base
+              // in a 128-bit mask, then run starts / ends by bit tricks -- every lane executes the same instructions.
               const int jb = imax(0, t0 - p), je = imin((int)l, imin(t1, L) - p);
-              int open = -1;
               const u8* qp = qual + q;
-              int j = jb;
-              // bytes up to the next 4-byte boundary, then whole words (four quality tests per compare), then the tail
-              while (j < je) {
-                if ((((size_t)(qp + j)) & 3) == 0 && j + 4 <= je) {
-                  const u32 w = *reinterpret_cast<const u32*>(qp + j);
-                  const u32 m = qual_ge4(w, qthr4, q_all, q_none);
-                  if (m == 0xffffffffu) { if (open < 0) open = j; j += 4; continue; }
-                  if (m == 0u) { if (open >= 0) { atomicAdd(&diff[PU_DI(p + open - t0)], 1); atomicAdd(&diff[PU_DI(p + j - t0)], -1); open = -1; } j += 4; continue; }
+              for (int cb = jb; cb < je; cb += 128) {
+                const int len = imin(128, je - cb);
+                const u8* b0 = qp + cb;
+                const u32 mis = (u32)((size_t)b0 & 3);
+                const u32* wp = reinterpret_cast<const u32*>(b0 - mis);
+                const u32 sel = 0x3210u + 0x1111u * mis;
+                const int nw = (len + 3) >> 2;
+                u32 mk[4] = {0u, 0u, 0u, 0u};
+                u32 prevw = wp[0];
+#pragma unroll
+                for (int wd = 0; wd < 4; ++wd) {
+                  if (8 * wd < nw) {
+                    u32 acc = 0u;
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) {
+                      const int k = 8 * wd + kk;
+                      if (k < nw) {
+                        const u32 nextw = wp[k + 1];               // at most one word past the op: inside the staging slack / array padding
+                        const u32 w = __byte_perm(prevw, nextw, sel);
+                        prevw = nextw;
+                        // per-byte (quality >= Q) without the video instruction: bit 7 of every byte, exact for any Q in [0, 255]
+                        const u32 t = ((w & 0x7f7f7f7fu) | 0x80808080u) - qlow4;
+                        const u32 m7 = (qhigh ? (w & t) : (w | t)) & 0x80808080u;
+                        acc += (((m7 >> 7) * 0x01020408u) >> 24) << (4 * kk);
+                      }
+                    }
+                    mk[wd] = acc;
+                  }
                 }
-                const bool ok = (int)qp[j] >= min_baseQ;
-                if (ok && open < 0) open = j;
-                if (!ok && open >= 0) { atomicAdd(&diff[PU_DI(p + open - t0)], 1); atomicAdd(&diff[PU_DI(p + j - t0)], -1); open = -1; }
-                ++j;
+                // clear the bits beyond len
+#pragma unroll
+                for (int wd = 0; wd < 4; ++wd) {
+                  const int nbits = len - 32 * wd;
+                  if (nbits <= 0) mk[wd] = 0u; else if (nbits < 32) mk[wd] &= (1u << nbits) - 1u;
+                }
+                u32 prev = 0u;
+                const int dbase = p + cb - t0;
+#pragma unroll
+                for (int wd = 0; wd < 4; ++wd) {
+                  const u32 cur = mk[wd];
+                  const u32 sh = (cur << 1) | prev;
+                  u32 st_ = cur & ~sh, en = ~cur & sh;
+                  while (st_) { const int bbit = __ffs((int)st_) - 1; atomicAdd(&diff[PU_DI(dbase + 32 * wd + bbit)], 1); st_ &= st_ - 1u; }
+                  while (en) { const int bbit = __ffs((int)en) - 1; atomicAdd(&diff[PU_DI(dbase + 32 * wd + bbit)], -1); en &= en - 1u; }
+                  prev = cur >> 31;
+                }
+                if (prev) atomicAdd(&diff[PU_DI(dbase + 128)], -1);
               }
-              if (open >= 0) { atomicAdd(&diff[PU_DI(p + open - t0)], 1); atomicAdd(&diff[PU_DI(p + je - t0)], -1); }
             }
             if (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) q += l;
             if (op == 0 || op == 2 || op == 3 || op == 4) e += l;

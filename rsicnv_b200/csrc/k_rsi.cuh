@@ -101,9 +101,9 @@ __device__ bool window_median_ok(const int* __restrict__ medint, int i1, int L, 
 // bit per centre (one __ballot_sync word per 32 centres), each thread tests the centre range of the
 // bins it owns and remembers the first (smallest) L in registers: no atomics, no per-hit loops, and the
 // result does not depend on how hits cluster.  Dynamic shared memory (NB = S_T + 2*LMAX_CAP staged bins):
-//   P[NB+1] i64 | sq[LMAX_CAP+1] f64 | SA/EA x DEL/DUP [4][S_T] i32 | cle,cge [NB+1] u16 | hit words [2][2][S_NC/32+1] u32
+//   P[NB+1] i64 | SA/EA x DEL/DUP [4][S_T] i32 | cle,cge [NB+1] u16 | hit words [2][2][S_NC/32+1] u32
 enum { S_NB = S_T + 2 * LMAX_CAP, S_NC = S_T + 2 * S_H };
-#define RSI_SCAN_SMEM ((size_t)(S_NB + 1) * 8 + (size_t)(LMAX_CAP + 1) * 8 + (size_t)4 * S_T * 4 + (size_t)2 * (S_NB + 2) * 2 + (size_t)4 * (S_NC / 32 + 2) * 4)
+#define RSI_SCAN_SMEM ((size_t)(S_NB + 1) * 8 + (size_t)4 * S_T * 4 + (size_t)2 * (S_NB + 2) * 2 + (size_t)4 * (S_NC / 32 + 2) * 4)
 
 // prev / next index with a condition, over the staged bins (block-wide max / min scans, thread-contiguous)
 __device__ void scan_prev_next(const Cta& c, const u8* cond, int N, int* prevv, int* nextv) {
@@ -135,19 +135,45 @@ __device__ void scan_prev_next(const Cta& c, const u8* cond, int N, int* prevv, 
   c.sync();
 }
 
+// The hit tests of rsistatus, (float(sum/L) - tmedian)*sqrt(L) <= -tlamda (DEL) / >= tlamda (DUP), are monotone
+// in the exact window sum (every rounding step is monotone), so for each window length they are equivalent
+// to integer thresholds on the fixed-point sum: thr[2L] = largest sum that is a DEL hit (-1: none),
+// thr[2L+1] = smallest sum that is a DUP hit (INT64_MAX: none).  One thread per length, binary search with the
+// reference's own arithmetic.
+__device__ __forceinline__ double rsi_score(i64 s, double dL, double sL, double tmed) {
+  const float mean = (float)__ddiv_rn((double)s * (1.0 / 68719476736.0), dL);
+  return __dmul_rn((double)mean - tmed, sL);
+}
+__global__ void k_rsi_thresholds(i64* __restrict__ thr, DevState* st) {
+  const int Lmax = st->Lmax;
+  const double tmed = st->tmedian, tlam = st->tlamda;
+  for (int L = 1 + (int)(blockIdx.x * blockDim.x + threadIdx.x); L <= Lmax; L += (int)(gridDim.x * blockDim.x)) {
+    const double dL = (double)L, sL = sqrt(dL);
+    const i64 smax = (i64)L * 16384ll * 68719476736ll;      // bin values are < 2^14 (checked by the scan kernel)
+    // DEL: hits form a prefix [0, S]
+    i64 lo = -1, hi = smax;                                   // invariant: lo is a hit (or -1), hi + 1 is not
+    if (!(rsi_score(smax, dL, sL, tmed) > -tlam)) lo = smax;
+    else while (lo < hi) { const i64 mid = lo + (hi - lo + 1) / 2; if (!(rsi_score(mid, dL, sL, tmed) > -tlam)) lo = mid; else hi = mid - 1; }
+    thr[2 * L] = lo;
+    // DUP: hits form a suffix [S, smax]
+    i64 a = 0, b = smax + 1;                                  // smallest hit in [a, b]; b = smax + 1 means none
+    while (a < b) { const i64 mid = a + (b - a) / 2; if (!(rsi_score(mid, dL, sL, tmed) < tlam)) b = mid; else a = mid + 1; }
+    thr[2 * L + 1] = a > smax ? 0x7fffffffffffffffll : a;
+  }
+}
+
 __global__ void __launch_bounds__(S_NT) k_rsi_scan(const float* __restrict__ t, const int* __restrict__ medint, u32* __restrict__ minl_del,
-                                                    u32* __restrict__ minl_dup, int* __restrict__ scratch, DevState* st) {
+                                                    u32* __restrict__ minl_dup, int* __restrict__ scratch, const i64* __restrict__ thr, DevState* st) {
   RSI_DYN_SMEM(smem);
   RSI_CTA_SETUP(c);
   i64* P = reinterpret_cast<i64*>(smem);
-  double* sq = reinterpret_cast<double*>(P + (S_NB + 1));
-  int* SAEA = reinterpret_cast<int*>(sq + (LMAX_CAP + 1));        // [0]=SA_del [1]=EA_del [2]=SA_dup [3]=EA_dup, S_T each
+  int* SAEA = reinterpret_cast<int*>(P + (S_NB + 1));        // [0]=SA_del [1]=EA_del [2]=SA_dup [3]=EA_dup, S_T each
   u16* cle = reinterpret_cast<u16*>(SAEA + 4 * S_T);
   u16* cge = cle + (S_NB + 2);
   u32* hw = reinterpret_cast<u32*>(cge + (S_NB + 2));              // [buf][sign][word]
   const int NW = S_NC / 32 + 2;
   const int nb = st->nb, Lmax = st->Lmax;
-  const double tmed = st->tmedian, tlam = st->tlamda, limd = st->lim_del, limu = st->lim_dup;
+  const double tmed = st->tmedian, limd = st->lim_del, limu = st->lim_dup;
   const int c0 = (int)blockIdx.x * S_T;
   const int HB = Lmax + 1;                        // staged bins: [c0 - HB, c0 + S_T + HB)
   const int base = c0 - HB;                       // smem index k <-> bin base + k
@@ -201,7 +227,6 @@ __global__ void __launch_bounds__(S_NT) k_rsi_scan(const float* __restrict__ t, 
     }
   }
   if (tid == 0) { P[N] = tots; cle[N] = (u16)totd; cge[N] = (u16)totu; }
-  for (int L = tid; L <= Lmax; L += S_NT) sq[L] = sqrt((double)L);
   // exactness of the reference's own double window sums: all partial sums need <= 53 significant bits
   tmax = c.reduce(tmax, MaxOp()); lowexp = c.reduce(lowexp, MinOp()); bad = c.reduce(bad, MaxOp());
   if (tid == 0) {
@@ -228,7 +253,7 @@ __global__ void __launch_bounds__(S_NT) k_rsi_scan(const float* __restrict__ t, 
   // ---- every window length
   for (int L = 1; L <= Lmax; ++L) {
     const int h = L / 2;
-    const double sL = sq[L], dL = (double)L;
+    const i64 sdel = thr[2 * L], sdup = thr[2 * L + 1];
     const int ilo = h + 1, ihi = nb - h - 1;        // valid centres: ilo <= i < ihi
     u32* hwd = hw + (size_t)((L & 1) * 2) * NW;     // double-buffered hit words: one barrier per length
     u32* hwu = hwd + NW;
@@ -239,9 +264,7 @@ __global__ void __launch_bounds__(S_NT) k_rsi_scan(const float* __restrict__ t, 
       if (ci < NC && i >= ilo && i < ihi) {
         const int kw = i - h - base;                // smem index of the window start
         const i64 s = P[kw + L] - P[kw];
-        const float mean = (float)__ddiv_rn((double)s * (1.0 / 68719476736.0), dL);
-        const double score = __dmul_rn((double)mean - tmed, sL);
-        hd = !(score > -tlam); hu = !(score < tlam);
+        hd = s <= sdel; hu = s >= sdup;
         if (hd) hd = window_median_ok(medint, i - h, L, (int)cle[kw + L] - (int)cle[kw], limd, -1);
         if (hu) hu = window_median_ok(medint, i - h, L, (int)cge[kw + L] - (int)cge[kw], limu, +1);
       }
@@ -486,6 +509,108 @@ __global__ void __launch_bounds__(CH_NT) k_level0_chain_scan(const float* __rest
     }
   }
   if (tid == 0) { const int l0 = -st->st_lo; st->lvl_sum[l0] = S; st->lvl_cnt[l0] = n; }
+}
+
+// Multi-block form of the same exact sum.  The array is cut into CHN_N chunks (one warp each).  A first
+// pass gives every chunk an APPROXIMATE running total (fp64), hence a guess e0 of the accumulator's binade
+// when the chain reaches it; the second pass composes the chunk's parity-step functions under the two
+// hypotheses "binade e0" and "binade e0+1".  A final one-warp pass walks the chunks in order with the EXACT
+// accumulator: when its binade matches a hypothesis and the chunk does not leave the binade, the chunk is
+// applied in O(1); otherwise (the ~20 binade crossings, or a wrong guess) the chunk is staged in shared
+// memory and added element by element with real FADDs.
+enum { CHN_N = 2048 };
+struct ChainChunk { ParStep h0, h1; int e0; int n_unmarked; };
+__device__ __forceinline__ void chain_bounds(int nb, int chunk, int* c0, int* c1) {
+  const int per = (((nb + CHN_N - 1) / CHN_N) + 31) & ~31;
+  *c0 = imin(chunk * per, nb); *c1 = imin(*c0 + per, nb);
+}
+__global__ void __launch_bounds__(256) k_chain_sums(const float* __restrict__ t, const int* __restrict__ status, double* __restrict__ csum, DevState* st) {
+  const int nb = st->nb, lane = (int)threadIdx.x & 31;
+  const int chunk = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+  if (chunk >= CHN_N) return;
+  int c0, c1; chain_bounds(nb, chunk, &c0, &c1);
+  double s = 0;
+  for (int i = c0 + lane; i < c1; i += 32) if (status[i] == 0) s += (double)t[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) csum[chunk] = s;
+}
+__global__ void __launch_bounds__(256) k_chain_compose(const float* __restrict__ t, const int* __restrict__ status, const double* __restrict__ csum,
+                                                        ChainChunk* __restrict__ cc, DevState* st) {
+  const int nb = st->nb, lane = (int)threadIdx.x & 31;
+  const int chunk = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+  if (chunk >= CHN_N) return;
+  int c0, c1; chain_bounds(nb, chunk, &c0, &c1);
+  double T0 = 0;
+  for (int k = lane; k < chunk; k += 32) T0 += csum[k];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) T0 += __shfl_xor_sync(0xffffffffu, T0, o);
+  // binade guess from the approximate total (the float chain drifts below / above the true sum by a few percent)
+  const float g = (float)(T0 * 0.9);
+  int e0 = g > 0.f ? (int)((__float_as_uint(g) >> 23) & 0xff) - 127 : -126;
+  if (e0 < -100) e0 = -100;
+  // lane-contiguous slices keep the order: lane l composes elements [a, b)
+  const int per = (c1 - c0 + 31) / 32;
+  const int a = imin(c0 + lane * per, c1), b = imin(a + per, c1);
+  ParStep h[2]; int nun = 0;
+#pragma unroll
+  for (int hyp = 0; hyp < 2; ++hyp) {
+    const int e = e0 + hyp;
+    const double u = ldexp(1.0, e - 23), inv_u = ldexp(1.0, 23 - e);
+    ParStep acc; acc.d0 = 0; acc.d1 = 0;
+    for (int i = a; i < b; ++i) if (status[i] == 0) { acc = par_compose(acc, par_elem((double)t[i], u, inv_u)); if (hyp == 0) ++nun; }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      ParStep up; up.d0 = __shfl_up_sync(0xffffffffu, acc.d0, o); up.d1 = __shfl_up_sync(0xffffffffu, acc.d1, o);
+      if (lane >= o) acc = par_compose(up, acc);
+    }
+    h[hyp] = acc;   // lane 31 holds the whole chunk
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) nun += __shfl_xor_sync(0xffffffffu, nun, o);
+  if (lane == 31) { ChainChunk r; r.h0 = h[0]; r.h1 = h[1]; r.e0 = e0; r.n_unmarked = nun; cc[chunk] = r; }
+}
+__global__ void __launch_bounds__(32) k_chain_resolve(const float* __restrict__ t, const int* __restrict__ status, const ChainChunk* __restrict__ cc, DevState* st) {
+  __shared__ float sv[4096];
+  __shared__ ChainChunk scc[32];
+  const int nb = st->nb, lane = (int)threadIdx.x;
+  float S = 0.f; u32 n = 0;
+  for (int cb = 0; cb < CHN_N; cb += 32) {
+    scc[lane] = cc[cb + lane];
+    __syncwarp();
+    for (int k = 0; k < 32; ++k) {
+      const int chunk = cb + k;
+      int c0, c1; chain_bounds(nb, chunk, &c0, &c1);
+      if (c0 >= c1) continue;                       // (uniform)
+      int need = 1;
+      if (lane == 0) {
+        const ChainChunk r = scc[k];
+        n += (u32)r.n_unmarked;
+        if (S > 0.f) {
+          const int e = (int)((__float_as_uint(S) >> 23) & 0xff) - 127;
+          if (e == r.e0 || e == r.e0 + 1) {
+            const ParStep hsel = e == r.e0 ? r.h0 : r.h1;
+            const double u = ldexp(1.0, e - 23);
+            const i64 N0 = (i64)((double)S * ldexp(1.0, 23 - e));
+            const i64 d = (N0 & 1) ? hsel.d1 : hsel.d0;
+            if (N0 + d < 16777216) { S = (float)((double)(N0 + d) * u); need = 0; }
+          }
+        }
+      }
+      need = __shfl_sync(0xffffffffu, need, 0);
+      if (!need) continue;
+      // in-order float adds for this chunk, staged through shared memory (marked bins contribute nothing)
+      for (int s0 = c0; s0 < c1; s0 += 4096) {
+        const int cnt = imin(4096, c1 - s0);
+        for (int j = lane; j < cnt; j += 32) sv[j] = status[s0 + j] == 0 ? t[s0 + j] : -1.f;   // bin values are >= 0: -1 marks "skip"
+        __syncwarp();
+        if (lane == 0) for (int j = 0; j < cnt; ++j) { const float x = sv[j]; if (x >= 0.f) S = __fadd_rn(S, x); }
+        __syncwarp();
+      }
+    }
+    __syncwarp();
+  }
+  if (lane == 0) { const int l0 = -st->st_lo; st->lvl_sum[l0] = S; st->lvl_cnt[l0] = n; }
 }
 
 // sums of the non-zero levels: one thread per level; the ordered (level, value) list of the marked

@@ -83,14 +83,15 @@ struct rsigpu_ctx {
   std::string err;
   int L = 0, Lc = 0, nb = 0, tid = 0;
   bool have_ref = false, have_depth = false, have_reads = false, loaded = false, detected = false, filtered = false;
-  int level0_mode = 1;   // 1 = block-scan chain (default), 0 = plain sequential chain (cross-check)
+  int level0_mode = 2;   // 2 = multi-block exact chain (default), 1 = one-block scan form, 0 = plain sequential FADD chain (cross-check)
+  DevBuf<double> d_csum; DevBuf<i64> d_cchunk;
   // per-base
   DevBuf<u8> d_fasta; DevBuf<int> d_raw, d_rdc, d_nseq;  // d_nseq: nbeg | nend | ncum
   std::vector<int> h_nbeg, h_nend;
   DevState* d_st = nullptr; DevState* h_st = nullptr;
   DevBuf<u32> d_hist_all, d_chist, d_thist, d_tothist, d_fq_hist;
   // bins
-  DevBuf<float> d_bin_med, d_bin_nbn, d_lut, d_nz_val; DevBuf<int> d_bin_medint, d_status, d_status1, d_tile, d_nz_idx, d_runs; DevBuf<i64> d_bin_sum, d_pfx, d_cprof;
+  DevBuf<float> d_bin_med, d_bin_nbn, d_lut, d_nz_val; DevBuf<int> d_bin_medint, d_status, d_status1, d_tile, d_nz_idx, d_runs; DevBuf<i64> d_bin_sum, d_pfx, d_cprof, d_thr;
   DevBuf<u32> d_minl_del, d_minl_dup;
   float* h_lut = nullptr; size_t h_lut_cap = 0;
   // lists
@@ -201,7 +202,8 @@ int run_rsi(rsigpu_ctx* c, int which, const float* t) {
   quantile(c, t, nullptr, 0, QM_ABSDEV, field_ptr(st, &DevState::tmedian), slot0 + 1);
   KL(k_rsi_params2, 1, 32, 0, t, st, which, c->P.threshold, slot0 + 1);
   for (int pass = 0; pass < 2; ++pass) {
-    KL(k_rsi_scan, (nb + S_T - 1) / S_T, S_NT, scan_smem, t, c->d_bin_medint.p, c->d_minl_del.p, c->d_minl_dup.p, c->d_scan_scratch.p, st);
+    KL(k_rsi_thresholds, (LMAX_CAP + 63) / 64, 64, 0, c->d_thr.p, st);
+    KL(k_rsi_scan, (nb + S_T - 1) / S_T, S_NT, scan_smem, t, c->d_bin_medint.p, c->d_minl_del.p, c->d_minl_dup.p, c->d_scan_scratch.p, c->d_thr.p, st);
     KL(k_rsi_cnt_del, gb, 256, 0, c->d_minl_del.p, st);
     KL(k_rsi_cnt_dup, gb, 256, 0, c->d_minl_del.p, c->d_minl_dup.p, st);
     int* status = pass == 0 ? c->d_status1.p : c->d_status.p;
@@ -209,7 +211,11 @@ int run_rsi(rsigpu_ctx* c, int which, const float* t) {
     if (pass == 1) break;
     // filterstatus (rsi.cpp:948-1057) on the first-pass status, in place via a second buffer
     KL(k_nz_scatter, gb, 256, 0, t, status, c->d_tile.p, c->d_nz_idx.p, c->d_nz_val.p, st);
-    if (c->level0_mode) KL(k_level0_chain_scan, 1, CH_NT, 0, t, status, st);
+    if (c->level0_mode == 2) {
+      KL(k_chain_sums, CHN_N / 8, 256, 0, t, status, c->d_csum.p, st);
+      KL(k_chain_compose, CHN_N / 8, 256, 0, t, status, c->d_csum.p, reinterpret_cast<ChainChunk*>(c->d_cchunk.p), st);
+      KL(k_chain_resolve, 1, 32, 0, t, status, reinterpret_cast<const ChainChunk*>(c->d_cchunk.p), st);
+    } else if (c->level0_mode == 1) KL(k_level0_chain_scan, 1, CH_NT, 0, t, status, st);
     else KL(k_level0_chain_seq, 1, 32, 0, t, status, st);
     KL(k_level_sums, (2 * LMAX_CAP + 3 + 127) / 128, 128, 0, c->d_nz_idx.p, c->d_nz_val.p, st);
     KL(k_filter_params, 1, 32, 0, st);
@@ -275,7 +281,8 @@ int rsigpu_create(int device, const rsigpu_params* p, rsigpu_ctx** out) {
   ok = ok && c->d_thist.ensure(CHIST_RCAP) == cudaSuccess && c->d_tothist.ensure(CHIST_RCAP) == cudaSuccess;
   ok = ok && c->d_fq_hist.ensure((size_t)FQ_BINS_CAP + 8) == cudaSuccess;
   ok = ok && c->d_lists.ensure((size_t)LIST_CAP * 10 + 8) == cudaSuccess && c->d_misc.ensure(64) == cudaSuccess;
-  ok = ok && c->d_runs.ensure((size_t)LIST_CAP * 2 + 8) == cudaSuccess && c->d_cprof.ensure(16) == cudaSuccess;
+  ok = ok && c->d_runs.ensure((size_t)LIST_CAP * 2 + 8) == cudaSuccess && c->d_cprof.ensure(16) == cudaSuccess && c->d_thr.ensure(2 * (LMAX_CAP + 2)) == cudaSuccess && c->d_csum.ensure(CHN_N + 8) == cudaSuccess
+       && c->d_cchunk.ensure((size_t)(CHN_N + 8) * sizeof(ChainChunk) / 8 + 8) == cudaSuccess;
   ok = ok && c->d_chist_c.ensure(1u << 22) == cudaSuccess && c->d_sub.ensure((size_t)p->maxchkbp * 10 + 64) == cudaSuccess;
   ok = ok && c->d_nrun_beg.ensure(1 << 20) == cudaSuccess && c->d_nrun_end.ensure(1 << 20) == cudaSuccess;
   if (ok) ok = cudaMemsetAsync(c->d_fq_hist.p, 0, ((size_t)FQ_BINS_CAP + 8) * 4, c->stream) == cudaSuccess;
@@ -291,7 +298,7 @@ void rsigpu_destroy(rsigpu_ctx* c) {
   c->d_fasta.release(); c->d_raw.release(); c->d_rdc.release(); c->d_nseq.release();
   c->d_hist_all.release(); c->d_chist.release(); c->d_thist.release(); c->d_tothist.release(); c->d_fq_hist.release();
   c->d_bin_med.release(); c->d_bin_nbn.release(); c->d_lut.release(); c->d_bin_medint.release(); c->d_status.release(); c->d_status1.release();
-  c->d_tile.release(); c->d_nz_idx.release(); c->d_nz_val.release(); c->d_runs.release(); c->d_bin_sum.release(); c->d_pfx.release(); c->d_cprof.release(); c->d_minl_del.release(); c->d_minl_dup.release();
+  c->d_tile.release(); c->d_nz_idx.release(); c->d_nz_val.release(); c->d_runs.release(); c->d_bin_sum.release(); c->d_pfx.release(); c->d_cprof.release(); c->d_thr.release(); c->d_csum.release(); c->d_cchunk.release(); c->d_minl_del.release(); c->d_minl_dup.release();
   c->d_lists.release(); c->d_misc.release(); c->d_ref.release(); c->d_sub.release(); c->d_pref.release(); c->d_rm.release(); c->d_chist_c.release(); c->d_spec_ref.release(); c->d_spec_pref.release(); c->d_spec_off.release(); c->d_spec_rm.release();
   c->d_nrun_beg.release(); c->d_nrun_end.release(); c->d_scan_scratch.release(); c->d_tile_range.release(); c->r_calend.release();
   c->r_pos.release(); c->r_mpos.release(); c->r_isize.release(); c->r_mtid.release(); c->r_flag.release(); c->r_mapq.release(); c->r_qual.release();
@@ -736,6 +743,6 @@ int rsigpu_debug_state(const rsigpu_ctx* c, double* out, int32_t cap) {
 }
 
 // test hook: 0 = sequential float chain for filterstatus' level-0 sum, 1 = block-scan form (default)
-int rsigpu_set_level0_mode(rsigpu_ctx* c, int mode) { if (!c) return RSIGPU_E_ARG; c->level0_mode = mode ? 1 : 0; return RSIGPU_OK; }
+int rsigpu_set_level0_mode(rsigpu_ctx* c, int mode) { if (!c || mode < 0 || mode > 2) return RSIGPU_E_ARG; c->level0_mode = mode; return RSIGPU_OK; }
 
 }  // extern "C"

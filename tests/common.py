@@ -35,7 +35,7 @@ def assert_calls_equal(got, want, what=""):
             assert x == y or abs(x - y) <= RTOL * max(abs(x), abs(y)), f"{what} call {i} field {f}: {x} != {y}"
 
 
-def run_depth_case(lib_path, oracle, fa, d, check_bins=True, level0_modes=(1,), **kw):
+def run_depth_case(lib_path, oracle, fa, d, check_bins=True, level0_modes=(2,), **kw):
     """the whole depth path through the C ABI vs the oracle; returns the calls"""
     oracle.set_params(**oracle_params(kw))
     ro = oracle.depth_path(d, fa, 3, want_bins=True)

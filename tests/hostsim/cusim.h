@@ -343,6 +343,16 @@ inline float __uint_as_float(unsigned i) { float f; std::memcpy(&f, &i, 4); retu
 inline long long __double_as_longlong(double d) { long long i; std::memcpy(&i, &d, 8); return i; }
 inline double __longlong_as_double(long long i) { double d; std::memcpy(&d, &i, 8); return d; }
 template <class T> inline T __ldg(const T* p) { return *p; }
+inline unsigned __byte_perm(unsigned x, unsigned y, unsigned sel) {
+  unsigned long long v = ((unsigned long long)y << 32) | x; unsigned r = 0;
+  for (int i = 0; i < 4; ++i) { unsigned n = (sel >> (4 * i)) & 7; r |= (unsigned)((v >> (8 * n)) & 0xff) << (8 * i); }
+  return r;
+}
+inline unsigned __vcmpgeu4(unsigned a, unsigned b) {
+  unsigned m = 0;
+  for (int k = 0; k < 4; ++k) if (((a >> (8 * k)) & 0xff) >= ((b >> (8 * k)) & 0xff)) m |= 0xffu << (8 * k);
+  return m;
+}
 inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
 inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
 inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }

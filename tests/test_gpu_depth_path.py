@@ -22,7 +22,7 @@ CASES = [
 @pytest.mark.parametrize("case", CASES, ids=lambda c: f"L{c['L']}-s{c['seed']}-{'-'.join(f'{k}{v}' for k, v in c.get('kw', {}).items()) or 'default'}")
 def test_depth_path_matches_oracle(case, gpu_lib, oracle):
     fa, d, _ = make_case(case["L"], case["seed"], stress=case.get("stress", False))
-    calls, launches = run_depth_case(gpu_lib, oracle, fa, d, level0_modes=(1, 0), **case.get("kw", {}))
+    calls, launches = run_depth_case(gpu_lib, oracle, fa, d, level0_modes=(2, 1, 0), **case.get("kw", {}))
     assert launches > 0
 
 
@@ -87,3 +87,20 @@ def test_chr19_full_size_properties(gpu_lib):
 def test_high_depth_histogram_windows(gpu_lib, oracle):
     fa, d, _ = make_case(3_000_003, 17, mean=200.0)
     run_depth_case(gpu_lib, oracle, fa, d)
+
+
+def test_level0_float_chain_modes_agree_at_scale(gpu_lib):
+    """MED transform at 60x over chr19: integer-valued bins push the float accumulator past 2^24 (ulp 2, 4), where exact
+    ties (round-to-even) occur on most additions -- the three implementations of the sequential float sum must agree bit for bit"""
+    L = synth.CHR19_LEN
+    fa = synth.make_fasta(L, 21)
+    d, _ = synth.make_depth(L, 21, fa, n_events=20, mean=60.0)
+    outs = []
+    with api.Context(lib=gpu_lib, trans="MED") as ctx:
+        ctx.set_reference(fa); ctx.set_depth(d)
+        for mode in (0, 1, 2):
+            ctx.set_level0_mode(mode)
+            calls = ctx.run()
+            ds = ctx.debug_state()
+            outs.append((ctx.array(api.ARR_BIN_STATUS1).tobytes(), ctx.array(api.ARR_BIN_STATUS).tobytes(), b"".join(bytes(c) for c in calls), ds["tmedian"], ds["tlamda"]))
+    assert outs[0] == outs[1] == outs[2]

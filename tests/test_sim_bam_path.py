@@ -71,3 +71,20 @@ def test_isize_sample_with_gaps_and_foreign_mates(sim_lib, oracle):
     r2["mtid"][rng.random(n) < 0.005] = -1                                      # mate unmapped: kept, not proper
     calls, st = run_bam_case(sim_lib, oracle, fa, r2, n_batches=2, min_baseQ=10, minq=0)
     assert len(calls) >= 1 and st.isize_mean > 0
+
+
+def test_pileup_quality_thresholds_full_byte_range(sim_lib, oracle):
+    """qualities over the whole 0..255 byte range against thresholds on both sides of 128 (the SWAR byte test)"""
+    from bind import oracle_pileup
+    from rsicnv_b200 import api
+    Ls = 120_000
+    fa = synth.make_fasta(Ls, 9)
+    reads, _ = synth.make_reads(Ls, 9, fa, coverage=6, n_events=0)
+    rng = np.random.default_rng(11)
+    reads["qual"] = rng.integers(0, 256, len(reads["qual"]), dtype=np.uint8)
+    for Q in (0, 1, 93, 127, 128, 129, 200, 255, 300, -5):
+        oracle.set_params(minq=0, min_baseQ=Q)
+        want = oracle_pileup(oracle, reads, Ls)
+        with api.Context(lib=sim_lib, minq=0, min_baseQ=Q) as ctx:
+            ctx.set_reference(fa); ctx.pileup_begin(); ctx.pileup_push(reads); ctx.pileup_end()
+            assert np.array_equal(ctx.array(api.ARR_RAW_DEPTH), want), Q

@@ -29,7 +29,7 @@ CASES = [
 @pytest.mark.parametrize("case", CASES, ids=lambda c: f"L{c['L']}-s{c['seed']}-{'-'.join(f'{k}{v}' for k, v in c.get('kw', {}).items()) or 'default'}")
 def test_depth_path_matches_oracle(case, sim_lib, oracle):
     fa, d, _ = make_case(case["L"], case["seed"], stress=case.get("stress", False))
-    calls, launches = run_depth_case(sim_lib, oracle, fa, d, level0_modes=(1, 0), **case.get("kw", {}))
+    calls, launches = run_depth_case(sim_lib, oracle, fa, d, level0_modes=(2, 1, 0), **case.get("kw", {}))
     assert launches > 0
 
 
@@ -40,7 +40,7 @@ def test_schedule_order_independent(order, sim_lib):
         "import sys; sys.path.insert(0, 'tests'); sys.path.insert(0, '.')\n"
         "from bind import Lib; from common import make_case, run_depth_case\n"
         "fa, d, _ = make_case(500_003, 12, stress=True)\n"
-        f"run_depth_case({sim_lib!r}, Lib('oracle'), fa, d, level0_modes=(1, 0))\n"
+        f"run_depth_case({sim_lib!r}, Lib('oracle'), fa, d, level0_modes=(2, 1, 0))\n"
         "print('ok')\n")
     env = dict(os.environ, CUSIM_ORDER=order)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
