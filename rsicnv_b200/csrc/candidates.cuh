@@ -135,7 +135,10 @@ RSI_DEVN void cta_hist_stat(const Cta& c, const CandScratch& S, const T* x, int 
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       size_t b = 0;
-      if (valid[k]) { double idx = ((double)a[k] - mn) / dy + 0.5; b = (size_t)idx; }
+      if (valid[k]) {
+        if (dy == 1.0) b = (size_t)((double)a[k] - mn + 0.5);       // integer samples: the division by dy = 1 is exact anyway
+        else { double idx = ((double)a[k] - mn) / dy + 0.5; b = (size_t)idx; }
+      }
       cta_hist_add(H, b, valid[k]);
     }
   }

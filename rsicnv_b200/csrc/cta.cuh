@@ -103,7 +103,7 @@ RSI_DEV void cta_atomic_inc(unsigned* p) { atomicAdd(p, 1u); }
 // histogram increment called by ALL threads of a warp together (valid = this lane has a sample):
 // lanes that hit the same bucket are merged into one atomic
 RSI_DEV void cta_hist_add(unsigned* h, size_t b, bool valid) {
-  const unsigned long long key = valid ? (unsigned long long)b : ~0ull;
+  const unsigned key = valid ? (unsigned)b : 0xffffffffu;     // bucket indices are far below 2^32
   const unsigned m = __match_any_sync(0xffffffffu, key);
   if (valid && (int)(threadIdx.x & 31) == __ffs((int)m) - 1) atomicAdd(&h[b], (unsigned)__popc(m));
 }

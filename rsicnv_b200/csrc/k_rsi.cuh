@@ -257,6 +257,7 @@ __global__ void __launch_bounds__(S_NT) k_rsi_scan(const float* __restrict__ t, 
     const int ilo = h + 1, ihi = nb - h - 1;        // valid centres: ilo <= i < ihi
     u32* hwd = hw + (size_t)((L & 1) * 2) * NW;     // double-buffered hit words: one barrier per length
     u32* hwu = hwd + NW;
+    int anyhit = 0;
     for (int w = warp; w < nwords; w += S_NT / 32) {
       const int ci = w * 32 + lane;                 // centre index within [0, NC)
       const int i = cbase + ci;
@@ -270,8 +271,9 @@ __global__ void __launch_bounds__(S_NT) k_rsi_scan(const float* __restrict__ t, 
       }
       const u32 bd = __ballot_sync(0xffffffffu, hd), bu = __ballot_sync(0xffffffffu, hu);
       if (lane == 0) { hwd[w] = bd; hwu[w] = bu; }
+      anyhit |= (bd | bu) != 0u;
     }
-    c.sync();
+    if (!__syncthreads_or(anyhit)) continue;        // no window of this length hits anywhere near the tile (the common case)
 #pragma unroll
     for (int r = 0; r < S_T / S_NT; ++r) {
       const int jr = tid + r * S_NT;                // owned bin, smem index HB + jr
@@ -586,14 +588,16 @@ __global__ void __launch_bounds__(32) k_chain_resolve(const float* __restrict__ 
       if (lane == 0) {
         const ChainChunk r = scc[k];
         n += (u32)r.n_unmarked;
-        if (S > 0.f) {
-          const int e = (int)((__float_as_uint(S) >> 23) & 0xff) - 127;
+        const u32 sb = __float_as_uint(S);
+        const int be = (int)((sb >> 23) & 0xff);      // biased exponent; normal positive floats only
+        if (S > 0.f && be > 0) {
+          const int e = be - 127;
           if (e == r.e0 || e == r.e0 + 1) {
             const ParStep hsel = e == r.e0 ? r.h0 : r.h1;
-            const double u = ldexp(1.0, e - 23);
-            const i64 N0 = (i64)((double)S * ldexp(1.0, 23 - e));
+            const i64 N0 = (i64)((sb & 0x7fffffu) | 0x800000u);       // S = N0 * 2^(e-23), N0 in [2^23, 2^24)
             const i64 d = (N0 & 1) ? hsel.d1 : hsel.d0;
-            if (N0 + d < 16777216) { S = (float)((double)(N0 + d) * u); need = 0; }
+            const i64 N1 = N0 + d;
+            if (N1 < 16777216) { S = __uint_as_float(((u32)be << 23) | ((u32)N1 & 0x7fffffu)); need = 0; }
           }
         }
       }
@@ -604,7 +608,17 @@ __global__ void __launch_bounds__(32) k_chain_resolve(const float* __restrict__ 
         const int cnt = imin(4096, c1 - s0);
         for (int j = lane; j < cnt; j += 32) sv[j] = status[s0 + j] == 0 ? t[s0 + j] : -1.f;   // bin values are >= 0: -1 marks "skip"
         __syncwarp();
-        if (lane == 0) for (int j = 0; j < cnt; ++j) { const float x = sv[j]; if (x >= 0.f) S = __fadd_rn(S, x); }
+        if (lane == 0) {
+          int j = 0;
+          for (; j + 8 <= cnt; j += 8) {              // loads first, then the dependent FADD chain
+            float x[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) x[q] = sv[j + q];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) if (x[q] >= 0.f) S = __fadd_rn(S, x[q]);
+          }
+          for (; j < cnt; ++j) { const float x = sv[j]; if (x >= 0.f) S = __fadd_rn(S, x); }
+        }
         __syncwarp();
       }
     }

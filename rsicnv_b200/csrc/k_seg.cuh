@@ -64,7 +64,7 @@ __global__ void k_runs_scatter(const int* __restrict__ status, const int* __rest
 struct SegBest { double v; u64 key; };
 struct SegBestOp { __device__ __forceinline__ SegBest operator()(SegBest a, SegBest b) const { return (b.v > a.v || (b.v == a.v && b.key < a.key)) ? b : a; } };
 
-__global__ void __launch_bounds__(256) k_run_argmax(const float* __restrict__ t, const int* __restrict__ status, const int* __restrict__ runs,
+__global__ void __launch_bounds__(1024) k_run_argmax(const float* __restrict__ t, const int* __restrict__ status, const int* __restrict__ runs,
                                                      i64* __restrict__ pfx, Cnv* __restrict__ segs, DevState* st) {
   RSI_CTA_SETUP(c);
   const int nruns = st->n_runs;

@@ -228,7 +228,7 @@ int run_rsi(rsigpu_ctx* c, int which, const float* t) {
   // get_rsi_segments on the second-pass status
   KL(k_runs_count, gb, 256, 0, c->d_status.p, c->d_tile.p, st);
   KL(k_runs_scatter, gb, 256, 0, c->d_status.p, c->d_tile.p, c->d_runs.p, LIST_CAP, st);
-  KL(k_run_argmax, c->n_sm * 4, 256, 0, t, c->d_status.p, c->d_runs.p, c->d_pfx.p, c->list(0), st);
+  KL(k_run_argmax, c->n_sm * 2, 1024, 0, t, c->d_status.p, c->d_runs.p, c->d_pfx.p, c->list(0), st);
   return RSIGPU_OK;
 }
 
@@ -561,7 +561,7 @@ int rsigpu_detectcnv(rsigpu_ctx* c) {
   X.cap = (long long)c->d_spec_ref.cap - 64; X.ref = c->d_spec_ref.p; X.pref = c->d_spec_pref.p; X.rm = c->d_spec_rm.p;
   CK(cudaMemsetAsync(c->d_misc.p + 12, 0, 8, c->stream));
   const int gcalls = c->n_sm;
-  KL(k_cand_a, 1, 1024, (size_t)CAND_SHIST * 4, A, X, c->d_st);
+  KL(k_cand_a, 1, 256, (size_t)CAND_SHIST * 4, A, X, c->d_st);   // bin-level arrays are tiny: fewer threads = cheaper barriers
   KL(k_cand_edge, gcalls, 1024, 0, A, X, c->d_st);
   KL(k_cand_b, 1, 1024, (size_t)CAND_SHIST * 4, A, X, c->d_st);
   KL(k_cand_final, gcalls, 1024, (size_t)CAND_SHIST * 4, A, X, c->d_st);
