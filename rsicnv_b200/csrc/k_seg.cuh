@@ -117,6 +117,8 @@ struct CandArgs {
   int list_cap;
   CandScratch S;
   int maxchkbp, merge, tid; double chklen;
+  int all_phase;      // -ALL (rsi.cpp:1852-1858): 0 = single transformation, 1 = MED half (test and park the segments), 2 = NBN half (test, append, continue)
+  Cnv* saved; int* n_saved;
 };
 
 enum { CAND_SHIST = 16384 };
@@ -149,7 +151,24 @@ __global__ void __launch_bounds__(1024) k_cand_a(CandArgs A, CandSpec X, DevStat
   }
   nl = cta_bcast(c, nl, 3);
   dump_list(c, A.segs, nl, A.d_segments, &A.n_dump[0], A.list_cap);
-  nl = cand_stage_a(c, P, A.S, st->Lc, A.medint, A.status, st->nb, A.segs, nl, A.tmp, A.ov, cand_dumps(A), 0);
+  int skip = 0;
+  if (A.all_phase) {
+    blocks_test(c, P, A.S, A.medint, A.status, st->nb, A.segs, nl, A.ov);
+    c.sync();
+    if (A.all_phase == 1) {   // park the tested MED segments; the NBN half follows
+      for (int j = c.tid; j < nl; j += c.nthr) A.saved[j] = A.segs[j];
+      if (c.tid == 0) *A.n_saved = nl;
+      return;
+    }
+    const int ns = *A.n_saved;   // concatenate: MED list first, then the NBN list (rsi.cpp:1856-1857)
+    for (int j = c.tid; j < nl; j += c.nthr) A.tmp[j] = A.segs[j];
+    c.sync();
+    for (int j = c.tid; j < ns + nl && j < A.list_cap; j += c.nthr) A.segs[j] = j < ns ? A.saved[j] : A.tmp[j - ns];
+    c.sync();
+    nl = ns + nl < A.list_cap ? ns + nl : A.list_cap;
+    skip = 1;
+  }
+  nl = cand_stage_a(c, P, A.S, st->Lc, A.medint, A.status, st->nb, A.segs, nl, A.tmp, A.ov, cand_dumps(A), skip);
   if (c.tid == 0) *X.nl = nl;
 }
 // optimize_with_derivative twice per call; calls are independent of each other

@@ -263,7 +263,7 @@ int rsigpu_create(int device, const rsigpu_params* p, rsigpu_ctx** out) {
   *out = nullptr;
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return RSIGPU_E_NODEVICE;
-  if (p->trans != RSIGPU_TRANS_NBN && p->trans != RSIGPU_TRANS_MED) return RSIGPU_E_ARG;   // -ALL: not built yet
+  if (p->trans != RSIGPU_TRANS_NBN && p->trans != RSIGPU_TRANS_MED && p->trans != RSIGPU_TRANS_ALL) return RSIGPU_E_ARG;
   rsigpu_ctx* c = new rsigpu_ctx();
   c->device = device; c->P = *p;
   if (c->P.m % 2 != 1) c->P.m += 1;   // rsi.cpp:2061-2064
@@ -280,7 +280,7 @@ int rsigpu_create(int device, const rsigpu_params* p, rsigpu_ctx** out) {
   ok = ok && c->d_hist_all.ensure(HIST_ALL_BINS) == cudaSuccess && c->d_chist.ensure((size_t)MAD_CLASSES * CHIST_RCAP) == cudaSuccess;
   ok = ok && c->d_thist.ensure(CHIST_RCAP) == cudaSuccess && c->d_tothist.ensure(CHIST_RCAP) == cudaSuccess;
   ok = ok && c->d_fq_hist.ensure((size_t)FQ_BINS_CAP + 8) == cudaSuccess;
-  ok = ok && c->d_lists.ensure((size_t)LIST_CAP * 10 + 8) == cudaSuccess && c->d_misc.ensure(64) == cudaSuccess;
+  ok = ok && c->d_lists.ensure((size_t)LIST_CAP * 11 + 8) == cudaSuccess && c->d_misc.ensure(64) == cudaSuccess;
   ok = ok && c->d_runs.ensure((size_t)LIST_CAP * 2 + 8) == cudaSuccess && c->d_cprof.ensure(16) == cudaSuccess && c->d_thr.ensure(2 * (LMAX_CAP + 2)) == cudaSuccess && c->d_csum.ensure(CHN_N + 8) == cudaSuccess
        && c->d_cchunk.ensure((size_t)(CHN_N + 8) * sizeof(ChainChunk) / 8 + 8) == cudaSuccess;
   ok = ok && c->d_chist_c.ensure(1u << 22) == cudaSuccess && c->d_sub.ensure((size_t)p->maxchkbp * 10 + 64) == cudaSuccess;
@@ -542,12 +542,14 @@ int rsigpu_detectcnv(rsigpu_ctx* c) {
     c->detected = true;
     return RSIGPU_OK;
   }
-  const int which = c->P.trans == RSIGPU_TRANS_MED ? 1 : 0;
-  int rc = run_rsi(c, which, which ? c->d_bin_med.p : c->d_bin_nbn.p);
-  if (rc) return rc;
-  CK(cudaEventRecord(c->ev[3], c->stream));
   const int nn = (int)c->h_nbeg.size();
   CandArgs A;
+  A.all_phase = 0; A.saved = c->list(10); A.n_saved = c->d_misc.p + 14;
+  const bool all = c->P.trans == RSIGPU_TRANS_ALL;
+  const int which = c->P.trans == RSIGPU_TRANS_NBN ? 0 : 1;      // MED first for -MED and -ALL (rsi.cpp:1837-1840)
+  int rc = run_rsi(c, which, which ? c->d_bin_med.p : c->d_bin_nbn.p);
+  if (rc) return rc;
+  if (!all) CK(cudaEventRecord(c->ev[3], c->stream));
   A.rdc = c->d_rdc.p; A.medint = c->d_bin_medint.p; A.status = c->d_status.p; A.nbeg = c->d_nseq.p; A.nend = c->d_nseq.p + nn;
   A.segs = c->list(0); A.tmp = c->list(1); A.ov = c->list(2);
   A.d_segments = c->list(3); A.d_blocks = c->list(4); A.d_premerge = c->list(5); A.d_merged = c->list(6); A.d_detected = c->list(7); A.d_calls = c->list(8);
@@ -561,6 +563,13 @@ int rsigpu_detectcnv(rsigpu_ctx* c) {
   X.cap = (long long)c->d_spec_ref.cap - 64; X.ref = c->d_spec_ref.p; X.pref = c->d_spec_pref.p; X.rm = c->d_spec_rm.p;
   CK(cudaMemsetAsync(c->d_misc.p + 12, 0, 8, c->stream));
   const int gcalls = c->n_sm;
+  if (all) {   // -ALL: MED segments are tested and parked, then the NBN pass is run and its segments appended
+    A.all_phase = 1;
+    KL(k_cand_a, 1, 256, (size_t)CAND_SHIST * 4, A, X, c->d_st);
+    if ((rc = run_rsi(c, 0, c->d_bin_nbn.p)) != RSIGPU_OK) return rc;
+    CK(cudaEventRecord(c->ev[3], c->stream));
+    A.all_phase = 2;
+  }
   KL(k_cand_a, 1, 256, (size_t)CAND_SHIST * 4, A, X, c->d_st);   // bin-level arrays are tiny: fewer threads = cheaper barriers
   KL(k_cand_edge, gcalls, 1024, 0, A, X, c->d_st);
   KL(k_cand_b, 1, 1024, (size_t)CAND_SHIST * 4, A, X, c->d_st);

@@ -41,7 +41,7 @@ int usage() {
           "Usage:\n  rsicnv rsi -f REF -b BAM [options]\n  rsicnv rsi -f REF -d RDFILE -c CHR [options]\n"
           "Options:\n   -o  STR  outputfile [rsiout.txt]\n   -c  STR  chromosome [1-22XY]\n   -m  INT  bin size, odd [101]\n"
           "   -q  INT  minimum mapping quality [0]\n   -Q  INT  minimum base quality [13]\n   -cap FLT cap depth at FLT x median, <=1 off [4]\n"
-          "   -NOGC    no GC adjustment\n   -MED | -NB  transformation [NB]\n   -s       save raw depth to <out>.<chr>_rd (BAM input)\n"
+          "   -NOGC    no GC adjustment\n   -MED | -NB | -ALL  transformation [NB]\n   -s       save raw depth to <out>.<chr>_rd (BAM input)\n"
           "   -gpus INT  GPUs to shard contigs over [1]   -threads INT  host inflate threads [8]\n");
   return 0;
 }
@@ -91,7 +91,6 @@ bool parse(int argc, char** argv, Opt* o) {
   if (o->outfile == o->bamfile || o->outfile == o->rdfile) { fprintf(stderr, "output file is same as input file \n"); return false; }
   if (!o->rdfile.empty() && (o->chr.empty() || o->chr == "1-22XY")) { fprintf(stderr, "readdepth file and chromosome must be specified together\n"); return false; }
   if (o->P.m % 2 != 1) { o->P.m += 1; fprintf(stderr, "m is changed to %d\n", o->P.m); }
-  if (o->P.trans == RSIGPU_TRANS_ALL) { fprintf(stderr, "-ALL is not built yet in this implementation (use -NB or -MED)\n"); return false; }
   return true;
 }
 

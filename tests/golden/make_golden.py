@@ -28,6 +28,7 @@ DEPTH_CASES = [
     dict(L=800_003, seed=7, kw=dict(m=51)), dict(L=1_500_003, seed=8, kw=dict(m=501)),
     dict(L=700_003, seed=9, stress=True), dict(L=500_003, seed=10, kw=dict(merge=False), stress=True),
     dict(L=3_000_017, seed=5), dict(L=2_000_003, seed=42),
+    dict(L=600_007, seed=6, kw=dict(trans="ALL")), dict(L=700_003, seed=9, kw=dict(trans="ALL"), stress=True), dict(L=500_003, seed=39, stress=True),
 ]
 BAM_CASE = dict(L=10_600_000, seed=3, coverage=12, n_events=6, lens=(3000, 8000, 20000), minq=0, min_baseQ=10)
 

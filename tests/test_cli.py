@@ -72,6 +72,11 @@ def test_cli_bam_two_contigs_matches_reference(cli, tmp_path):
     out = subprocess.run([cli] + common + ["-o", str(tmp_path / "ours2.txt")], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
     assert _table(str(tmp_path / "ours2.txt")) == _table(str(tmp_path / "ref2.txt"))
+    common = ["rsi", "-b", bam, "-f", fasta, "-c", "1", "-ALL", "-q", "0", "-Q", "10", "-np"]
+    subprocess.run([REF_BIN] + common + ["-o", str(tmp_path / "ref3.txt")], check=True, capture_output=True)
+    out = subprocess.run([cli] + common + ["-o", str(tmp_path / "ours3.txt")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert _table(str(tmp_path / "ours3.txt")) == _table(str(tmp_path / "ref3.txt"))
 
 
 @pytest.mark.gpu
