@@ -101,12 +101,13 @@ READ_FIELDS = ("pos", "mpos", "isize", "mtid", "flag", "mapq", "cigar_off", "cig
 
 
 # algorithmic HBM bytes of one launch of each streaming kernel (DESIGN.md "kernels"); L = contig, Lc = after N removal
-def kernel_bytes(name: str, L: int, Lc: int, reads_bytes: int = 0):
+def kernel_bytes(name: str, L: int, Lc: int, reads_bytes: int = 0, qual_bytes: int = 0):
     return {
+        "k_qual_mask": qual_bytes,        # every base quality once (the 1-bit-per-base mask it writes is overhead, not counted)
         "k_gc_table": 5 * L,          # depth 4 + FASTA 1, read once
         "k_gc_adjust": 9 * L,         # depth 4 + FASTA 1 read, adjusted depth 4 written
         "k_bins": 4 * Lc,             # compacted depth read once
-        "k_pileup_tile": reads_bytes + 4 * L,   # every read record once (core fields + CIGAR + qualities) + depth written once
+        "k_pileup_tile": reads_bytes - qual_bytes + 4 * L,   # every read record's core fields + CIGAR once + depth written once
     }.get(name, 0)
 
 
@@ -250,6 +251,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     # pinned host buffers (the e2e leg copies from these every step)
     reads_bytes = 0
+    qual_bytes = 0
     if bam:
         fa, reads, events = make_bam_inputs(19 + rank, L)
         pins = {k: torch.from_numpy(reads[k]).pin_memory() for k in READ_FIELDS}
@@ -261,6 +263,7 @@ def main():
         h2d = L + sum(int(pins[k].numel() * pins[k].element_size()) for k in READ_FIELDS)
         # bytes the pileup kernel has to read once: pos, flag, mapq, CIGAR offsets + ops, quality offsets + qualities
         reads_bytes = sum(int(pins[k].numel() * pins[k].element_size()) for k in ("pos", "flag", "mapq", "cigar_off", "cigar", "qual_off", "qual"))
+        qual_bytes = int(pins["qual"].numel())
         config["reads"] = nreads
         ctx = api.Context(device=local, minq=0, min_baseQ=10)
     else:
@@ -330,7 +333,7 @@ def main():
         value = total_bases / (dev_ms / 1e3) / 1e9
         kern = []
         for name, ms, n in prof:
-            b = kernel_bytes(name, L, st.compact_len, reads_bytes)
+            b = kernel_bytes(name, L, st.compact_len, reads_bytes, qual_bytes)
             avg = ms / max(n, 1)
             kern.append({"kernel": name, "launches_per_step": n / a.profile_steps, "avg_ms": avg, "ms_per_step": ms / a.profile_steps,
                          "algorithmic_bytes": b, "gbs": (b / 1e9) / (avg / 1e3) if b and avg > 0 else None})

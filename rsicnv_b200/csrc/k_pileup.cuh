@@ -6,11 +6,13 @@
 //   bam_rd_pr_stats (insert-size sample)  pairrd.cpp:112-260 (order of tests: SURVEY.md A.2)            k_isize_stats
 //   cnv_stat                     pairrd.cpp:622-748                                                     k_cnv_stat
 //
-// Pileup design: a block OWNS a tile of reference positions.  It binary-searches the sorted read
-// starts for the reads that can touch the tile, every thread walks the CIGAR of its reads and turns
-// each maximal stretch of M/= bases with quality >= Q into +1/-1 events in a shared-memory
-// difference array (clipped to the tile), a block-wide scan turns events into depth and the tile is
-// stored once with coalesced 16-byte stores: no global atomics, no zero-fill, no read-modify-write.
+// Pileup design: (1) k_qual_mask streams the quality bytes once and leaves one pass bit per base
+// (quality >= Q); (2) in k_pileup_tile a block OWNS a tile of reference positions: the reads that can
+// touch it come from a precomputed binary search of the sorted read starts, every thread walks the
+// CIGAR of its reads and turns each maximal stretch of passing M/= bases (bit tricks on the pass mask)
+// into +1/-1 events in a shared-memory difference array (clipped to the tile), a block-wide scan turns
+// events into depth and the tile is stored once with 16-byte stores: no global atomics, no zero-fill,
+// no read-modify-write.
 #pragma once
 #include "k_seg.cuh"
 
@@ -53,17 +55,65 @@ __global__ void k_read_ends(ReadSoA R, int* max_extent, int* sorted_bad) {
   if (bad) atomicOr(sorted_bad, 1);
 }
 
-// per-byte `quality >= Q` of four packed qualities: 0xff per passing byte
-__device__ __forceinline__ u32 qual_ge4(u32 w, u32 thr4, bool all, bool none) {
-  if (all) return 0xffffffffu;
-  if (none) return 0u;
-#if defined(RSI_SIM)
-  u32 m = 0;
-  for (int k = 0; k < 4; ++k) if (((w >> (8 * k)) & 0xff) >= ((thr4 >> (8 * k)) & 0xff)) m |= 0xffu << (8 * k);
-  return m;
-#else
-  return __vcmpgeu4(w, thr4);
-#endif
+// Base-quality filter as a pure streaming pass: one bit per quality byte (bit i of word w = byte 32w+i has
+// quality >= Q), 32 bytes per thread, SWAR byte compare (exact for any Q in [0, 255]; Q > 255 passes nothing).
+// Reads every quality byte exactly once at HBM speed and leaves an 8x smaller array for the pileup proper.
+__device__ __forceinline__ u32 qual_pass_nibble(u32 w, u32 qlow4, bool qhigh) {
+  const u32 t = ((w & 0x7f7f7f7fu) | 0x80808080u) - qlow4;
+  const u32 m7 = (qhigh ? (w & t) : (w | t)) & 0x80808080u;
+  return ((m7 >> 7) * 0x01020408u) >> 24;
+}
+__global__ void __launch_bounds__(256) k_qual_mask(const u8* __restrict__ qual, u64 nbytes, int min_baseQ, u32* __restrict__ mask) {
+  const int Qc = min_baseQ < 0 ? 0 : min_baseQ;
+  const bool q_none = Qc > 255, qhigh = Qc > 128;
+  const u32 qlow4 = (u32)(qhigh ? Qc - 128 : Qc) * 0x01010101u;
+  const u64 nwords = (nbytes + 31) >> 5;
+  for (u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += (u64)gridDim.x * blockDim.x) {
+    const uint4 a = reinterpret_cast<const uint4*>(qual)[2 * w], b = reinterpret_cast<const uint4*>(qual)[2 * w + 1];
+    u32 m = qual_pass_nibble(a.x, qlow4, qhigh) | (qual_pass_nibble(a.y, qlow4, qhigh) << 4) | (qual_pass_nibble(a.z, qlow4, qhigh) << 8) |
+            (qual_pass_nibble(a.w, qlow4, qhigh) << 12) | (qual_pass_nibble(b.x, qlow4, qhigh) << 16) | (qual_pass_nibble(b.y, qlow4, qhigh) << 20) |
+            (qual_pass_nibble(b.z, qlow4, qhigh) << 24) | (qual_pass_nibble(b.w, qlow4, qhigh) << 28);
+    mask[w] = q_none ? 0u : m;
+  }
+}
+
+#define PU_DI(i) ((i) + ((i) >> 5))
+// One M/= op: maximal stretches of passing bases among quality bytes [qb, qb + len) (global byte indices into the
+// quality array = bit indices into the pass mask) become +1 / -1 events at tile offsets dbase + j.  Chunks of 128
+// bases: five mask words, funnel shifts, then run starts / ends by bit tricks.
+__device__ __forceinline__ void pu_mask_runs(const u32* __restrict__ mask, u64 qb, int len_total, int dbase0, int* diff) {
+  for (int cb = 0; cb < len_total; cb += 128) {
+    const int len = imin(128, len_total - cb);
+    const u64 bit0 = qb + (u64)cb;
+    const u32* mw = mask + (bit0 >> 5);
+    const u32 sh = (u32)(bit0 & 31);
+    const int nwd = (len + 31) >> 5;
+    u32 mk[4];
+    u32 lo = mw[0];
+#pragma unroll
+    for (int wd = 0; wd < 4; ++wd) {
+      mk[wd] = 0u;
+      if (wd < nwd) {
+        const u32 hi = mw[wd + 1];                     // one word past the op at most: the mask array is padded
+        mk[wd] = sh ? ((lo >> sh) | (hi << (32 - sh))) : lo;
+        lo = hi;
+        const int nbits = len - 32 * wd;
+        if (nbits < 32) mk[wd] &= (1u << nbits) - 1u;
+      }
+    }
+    u32 prev = 0u;
+    const int dbase = dbase0 + cb;
+#pragma unroll
+    for (int wd = 0; wd < 4; ++wd) {
+      const u32 cur = mk[wd];
+      const u32 shf = (cur << 1) | prev;
+      u32 st_ = cur & ~shf, en = ~cur & shf;
+      while (st_) { const int bbit = __ffs((int)st_) - 1; atomicAdd(&diff[PU_DI(dbase + 32 * wd + bbit)], 1); st_ &= st_ - 1u; }
+      while (en) { const int bbit = __ffs((int)en) - 1; atomicAdd(&diff[PU_DI(dbase + 32 * wd + bbit)], -1); en &= en - 1u; }
+      prev = cur >> 31;
+    }
+    if (prev) atomicAdd(&diff[PU_DI(dbase + 128)], -1);
+  }
 }
 
 // first / one-past-last read that can touch each position tile (reads with pos in [t0 - max_extent, t1))
@@ -81,115 +131,40 @@ __global__ void k_tile_ranges(ReadSoA R, int L, const int* max_extent, int2* __r
   }
 }
 
-enum { PU_QS = 32768 };   // bytes of quality strings staged in shared memory per batch of reads
-__global__ void __launch_bounds__(PU_NT) k_pileup_tile(ReadSoA R, int* __restrict__ rd, int L, int minq, int min_baseQ, const int2* __restrict__ range) {
+__global__ void __launch_bounds__(PU_NT) k_pileup_tile(ReadSoA R, const u32* __restrict__ qmask, int* __restrict__ rd, int L, int minq,
+                                                        const int2* __restrict__ range) {
   RSI_CTA_SETUP(c);
-  RSI_DYN_SMEM(qs);       // PU_QS + 16 bytes
   __shared__ int diff[PU_T + 1 + (PU_T + 1) / 32 + 1];   // entry i lives at i + i/32: conflict-free 32-per-thread scan
-#define PU_DI(i) ((i) + ((i) >> 5))
   const int ntiles = (L + PU_T - 1) / PU_T;
-  // quality test constants: Q <= 0 passes everything (threshold 0), Q > 255 nothing (handled by skipping the reads)
-  const int Qc = min_baseQ < 0 ? 0 : min_baseQ;
-  const bool q_none = Qc > 255, qhigh = Qc > 128;
-  const u32 qlow4 = (u32)(qhigh ? Qc - 128 : Qc) * 0x01010101u;
   for (int tile = (int)blockIdx.x; tile < ntiles; tile += (int)gridDim.x) {
     const int t0 = tile * PU_T, t1 = imin(t0 + PU_T, L);
     c.sync();
     for (int k = c.tid; k < PU_T + 1 + (PU_T + 1) / 32 + 1; k += PU_NT) diff[k] = 0;
-    const int2 rr = q_none ? make_int2(0, 0) : range[tile];
-    int rb = rr.x;
-    while (rb < rr.y) {
-      // batch of consecutive reads whose quality strings (contiguous in HBM) fit the staging buffer:
-      // one coalesced 16-byte-vector copy HBM -> shared memory, then every thread walks its own read there
-      int nrd = imin(PU_NT, rr.y - rb);
-      const u64 q0 = R.qual_off[rb];
-      while (nrd > 1 && R.qual_off[rb + nrd] - q0 > (u64)PU_QS) nrd >>= 1;
-      const u64 q1 = R.qual_off[rb + nrd];
-      const bool staged = q1 - q0 <= (u64)PU_QS;
-      const u64 a0 = q0 & ~(u64)15;
-      c.sync();
-      if (staged) {
-        const int nvec = (int)((q1 - a0 + 15) >> 4);
-        const uint4* src = reinterpret_cast<const uint4*>(R.qual + a0);
-        uint4* dst = reinterpret_cast<uint4*>(qs);
-        for (int v = c.tid; v < nvec; v += PU_NT) dst[v] = src[v];
-      }
-      c.sync();
-      const int r = rb + c.tid;
-      if (c.tid < nrd) {
-        const int pos = R.pos[r];
-        const int fl = R.flag[r];
-        const u32 c0 = R.cigar_off[r], c1 = R.cigar_off[r + 1];
-        if (pos != 0 && (int)R.mapq[r] >= minq && !(fl & (BF_SECONDARY | BF_DUP))) {
-          // reference / query coordinate at the start of each op
-          u32 k = c0, q = 0;
-          while (k < c1) { const u32 op = R.cigar[k] & 15u; if (op == 0 || op == 2 || op == 7 || op == 8) break; if (op == 1 || op == 4) q += R.cigar[k] >> 4; ++k; }
-          u32 e = (u32)pos + 1;
-          const u8* qual = staged ? (qs + (R.qual_off[r] - a0)) : (R.qual + R.qual_off[r]);
-          for (; k < c1; ++k) {      // (no M/D/=/X op: k == c1, nothing is counted)
-            const u32 op = R.cigar[k] & 15u, l = R.cigar[k] >> 4;
-            if (op == 0 || op == 7) {
-              int p = (int)e - 1;                      // 0-based position of the op's first base
-              // maximal stretches of bases with quality >= Q, clipped to the tile and to L.  Branch-free per chunk of
-              // 128 bases: realign the quality words (PRMT), four quality tests per __vcmpgeu4, one pass bit per base
-              // in a 128-bit mask, then run starts / ends by bit tricks -- every lane executes the same instructions.
-              const int jb = imax(0, t0 - p), je = imin((int)l, imin(t1, L) - p);
-              const u8* qp = qual + q;
-              for (int cb = jb; cb < je; cb += 128) {
-                const int len = imin(128, je - cb);
-                const u8* b0 = qp + cb;
-                const u32 mis = (u32)((size_t)b0 & 3);
-                const u32* wp = reinterpret_cast<const u32*>(b0 - mis);
-                const u32 sel = 0x3210u + 0x1111u * mis;
-                const int nw = (len + 3) >> 2;
-                u32 mk[4] = {0u, 0u, 0u, 0u};
-                u32 prevw = wp[0];
+    const int2 rr = range[tile];
+    c.sync();
+    for (int r = rr.x + c.tid; r < rr.y; r += PU_NT) {
+      const int pos = R.pos[r], fl = R.flag[r], mq = (int)R.mapq[r];
+      const u32 c0 = R.cigar_off[r], c1 = R.cigar_off[r + 1];
+      const u64 qoff = R.qual_off[r];
+      u32 cg[3] = {0u, 0u, 0u};
 #pragma unroll
-                for (int wd = 0; wd < 4; ++wd) {
-                  if (8 * wd < nw) {
-                    u32 acc = 0u;
-#pragma unroll
-                    for (int kk = 0; kk < 8; ++kk) {
-                      const int k = 8 * wd + kk;
-                      if (k < nw) {
-                        const u32 nextw = wp[k + 1];               // at most one word past the op: inside the staging slack / array padding
-                        const u32 w = __byte_perm(prevw, nextw, sel);
-                        prevw = nextw;
-                        // per-byte (quality >= Q) without the video instruction: bit 7 of every byte, exact for any Q in [0, 255]
-                        const u32 t = ((w & 0x7f7f7f7fu) | 0x80808080u) - qlow4;
-                        const u32 m7 = (qhigh ? (w & t) : (w | t)) & 0x80808080u;
-                        acc += (((m7 >> 7) * 0x01020408u) >> 24) << (4 * kk);
-                      }
-                    }
-                    mk[wd] = acc;
-                  }
-                }
-                // clear the bits beyond len
-#pragma unroll
-                for (int wd = 0; wd < 4; ++wd) {
-                  const int nbits = len - 32 * wd;
-                  if (nbits <= 0) mk[wd] = 0u; else if (nbits < 32) mk[wd] &= (1u << nbits) - 1u;
-                }
-                u32 prev = 0u;
-                const int dbase = p + cb - t0;
-#pragma unroll
-                for (int wd = 0; wd < 4; ++wd) {
-                  const u32 cur = mk[wd];
-                  const u32 sh = (cur << 1) | prev;
-                  u32 st_ = cur & ~sh, en = ~cur & sh;
-                  while (st_) { const int bbit = __ffs((int)st_) - 1; atomicAdd(&diff[PU_DI(dbase + 32 * wd + bbit)], 1); st_ &= st_ - 1u; }
-                  while (en) { const int bbit = __ffs((int)en) - 1; atomicAdd(&diff[PU_DI(dbase + 32 * wd + bbit)], -1); en &= en - 1u; }
-                  prev = cur >> 31;
-                }
-                if (prev) atomicAdd(&diff[PU_DI(dbase + 128)], -1);
-              }
-            }
-            if (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) q += l;
-            if (op == 0 || op == 2 || op == 3 || op == 4) e += l;
-          }
+      for (int k = 0; k < 3; ++k) if (c0 + k < c1) cg[k] = R.cigar[c0 + k];
+      if (pos == 0 || mq < minq || (fl & (BF_SECONDARY | BF_DUP))) continue;
+      // reference / query coordinate at the start of each op
+      u32 k = c0, q = 0;
+      while (k < c1) { const u32 cgk = k - c0 < 3 ? cg[k - c0] : R.cigar[k]; const u32 op = cgk & 15u; if (op == 0 || op == 2 || op == 7 || op == 8) break; if (op == 1 || op == 4) q += cgk >> 4; ++k; }
+      u32 e = (u32)pos + 1;
+      for (; k < c1; ++k) {      // (no M/D/=/X op: k == c1, nothing is counted)
+        const u32 cgk = k - c0 < 3 ? cg[k - c0] : R.cigar[k];
+        const u32 op = cgk & 15u, l = cgk >> 4;
+        if (op == 0 || op == 7) {
+          const int p = (int)e - 1;                      // 0-based position of the op's first base
+          const int jb = imax(0, t0 - p), je = imin((int)l, imin(t1, L) - p);   // clipped to the tile and to L
+          if (jb < je) pu_mask_runs(qmask, qoff + q + (u32)jb, je - jb, p + jb - t0, diff);
         }
+        if (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) q += l;
+        if (op == 0 || op == 2 || op == 3 || op == 4) e += l;
       }
-      rb += nrd;
     }
     c.sync();
     // difference array -> depth, PU_T / PU_NT consecutive positions per thread
@@ -205,8 +180,8 @@ __global__ void __launch_bounds__(PU_NT) k_pileup_tile(ReadSoA R, int* __restric
       if (p < L) *reinterpret_cast<int4*>(rd + p) = make_int4(loc[j] + ex, loc[j + 1] + ex, loc[j + 2] + ex, loc[j + 3] + ex);
     }
   }
-#undef PU_DI
 }
+#undef PU_DI
 
 // ---------------------------------------------------------------------------------------------
 // Insert-size sample.  `keep`-filtered reads in file order from the first one overlapping 10 Mbp;

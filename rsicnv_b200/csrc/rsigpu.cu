@@ -102,7 +102,7 @@ struct rsigpu_ctx {
   std::vector<Cnv> h_detected, h_calls, h_dump[4];
   // reads
   DevVec<int> r_pos, r_mpos, r_isize, r_mtid; DevVec<u16> r_flag; DevVec<u8> r_mapq, r_qual; DevVec<u32> r_cigar_off, r_cigar; DevVec<u64> r_qual_off;
-  DevBuf<int> r_calend, d_tile_range;
+  DevBuf<int> r_calend, d_tile_range; DevBuf<u32> d_qmask;
   // accounting
   long long h_cprof[16] = {};
   int64_t launches = 0;
@@ -186,7 +186,6 @@ int set_smem_attrs() {
   cudaFuncSetAttribute(k_cand_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CAND_SHIST * 4));
   cudaFuncSetAttribute(k_cand_c, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CAND_SHIST * 4));
   cudaFuncSetAttribute(k_cand_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CAND_SHIST * 4));
-  cudaFuncSetAttribute(k_pileup_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PU_QS + 32));
   cudaFuncSetAttribute(k_rsi_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SCAN_SMEM);
   return 0;
 }
@@ -300,7 +299,7 @@ void rsigpu_destroy(rsigpu_ctx* c) {
   c->d_bin_med.release(); c->d_bin_nbn.release(); c->d_lut.release(); c->d_bin_medint.release(); c->d_status.release(); c->d_status1.release();
   c->d_tile.release(); c->d_nz_idx.release(); c->d_nz_val.release(); c->d_runs.release(); c->d_bin_sum.release(); c->d_pfx.release(); c->d_cprof.release(); c->d_thr.release(); c->d_csum.release(); c->d_cchunk.release(); c->d_minl_del.release(); c->d_minl_dup.release();
   c->d_lists.release(); c->d_misc.release(); c->d_ref.release(); c->d_sub.release(); c->d_pref.release(); c->d_rm.release(); c->d_chist_c.release(); c->d_spec_ref.release(); c->d_spec_pref.release(); c->d_spec_off.release(); c->d_spec_rm.release();
-  c->d_nrun_beg.release(); c->d_nrun_end.release(); c->d_scan_scratch.release(); c->d_tile_range.release(); c->r_calend.release();
+  c->d_nrun_beg.release(); c->d_nrun_end.release(); c->d_scan_scratch.release(); c->d_tile_range.release(); c->d_qmask.release(); c->r_calend.release();
   c->r_pos.release(); c->r_mpos.release(); c->r_isize.release(); c->r_mtid.release(); c->r_flag.release(); c->r_mapq.release(); c->r_qual.release();
   c->r_cigar_off.release(); c->r_cigar.release(); c->r_qual_off.release();
   if (c->d_st) cudaFree(c->d_st);
@@ -418,7 +417,10 @@ static int run_pileup(rsigpu_ctx* c) {
     CK(c->d_tile_range.ensure((size_t)ntile * 2 + 8));
     int2* tr = reinterpret_cast<int2*>(c->d_tile_range.p);
     KL(k_tile_ranges, grid_for(ntile, 128, c->n_sm * 8), 128, 0, R, c->L, mx, tr);
-    KL(k_pileup_tile, grid_for(c->L, PU_T, c->n_sm * 3), PU_NT, (size_t)PU_QS + 32, R, c->d_raw.p, c->L, c->P.minq, c->P.min_baseQ, tr);
+    const u64 nq = (u64)c->r_qual.n;
+    CK(c->d_qmask.ensure((size_t)((nq + 31) >> 5) + 16));
+    KL(k_qual_mask, c->n_sm * 16, 256, 0, c->r_qual.p, nq, c->P.min_baseQ, c->d_qmask.p);
+    KL(k_pileup_tile, grid_for(c->L, PU_T, c->n_sm * 6), PU_NT, 0, R, c->d_qmask.p, c->d_raw.p, c->L, c->P.minq, tr);
   }
   c->have_depth = true;
   return RSIGPU_OK;
