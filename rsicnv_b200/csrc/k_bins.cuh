@@ -16,8 +16,8 @@
 
 namespace rsigpu {
 
-enum { C_NT = 512, C_NW = C_NT / 32, C_K = 128, C_TP = 8192 /* max staged bases */ };
-#define RSI_SMEM_C ((size_t)C_NW * MAD_CLASSES * C_K * 2 + (size_t)C_TP * 4)
+enum { C_NT = 512, C_NW = C_NT / 32, C_K = 128, C_KP = C_K + 2 /* padded row: 65 words, lanes of a step hit 31 different banks */, C_TP = 8192 /* max staged bases */ };
+#define RSI_SMEM_C ((size_t)C_NW * MAD_CLASSES * C_KP * 2 + (size_t)C_TP * 4)
 
 __device__ __forceinline__ i64 warp_sum_i64(i64 v) {
 #pragma unroll
@@ -31,16 +31,17 @@ __global__ void __launch_bounds__(C_NT) k_bins(int* __restrict__ rdc, float* __r
                                                 i64* __restrict__ bin_sum, u32* chist, u32* thist, DevState* st, int bins_per_tile) {
   RSI_DYN_SMEM(smem);
   RSI_CTA_SETUP(c);
-  u16* ct = reinterpret_cast<u16*>(smem);                  // [C_NW][MAD_CLASSES][C_K]
-  int* vals = reinterpret_cast<int*>(smem + (size_t)C_NW * MAD_CLASSES * C_K * 2);
+  u16* ct = reinterpret_cast<u16*>(smem);                  // [C_NW][MAD_CLASSES][C_KP]
+  int* vals = reinterpret_cast<int*>(smem + (size_t)C_NW * MAD_CLASSES * C_KP * 2);
   const int tid = c.tid, lane = tid & 31, warp = tid >> 5;
   const int Lc = st->Lc, m = st->m, nb = st->nb, R = st->chist_R, cap_on = st->cap_on, capv = st->capv;
   const double thr = st->cap_thr;
   const int sub31 = MAD_CLASSES * (Lc / MAD_CLASSES);
   int wb = 0;
   if (R > C_K) { wb = (int)st->cap_median - C_K / 2; if (wb < 0) wb = 0; if (wb > R - C_K) wb = R - C_K; }
-  for (int k = tid; k < C_NW * MAD_CLASSES * C_K; k += C_NT) ct[k] = 0;
-  u16* wt = ct + (size_t)warp * MAD_CLASSES * C_K;
+  for (int k = tid; k < C_NW * MAD_CLASSES * C_KP; k += C_NT) ct[k] = 0;
+  u16* wt = ct + (size_t)warp * MAD_CLASSES * C_KP;
+  const int ithr = thr >= 2147483647.0 ? 0x7fffffff : (int)floor(thr);   // integer v: (double)v > thr  <=>  v > floor(thr)
   i64 mx = 0;
   const int ntiles = nb > 0 ? (nb + bins_per_tile - 1) / bins_per_tile : 1;
   for (int tile = (int)blockIdx.x; tile < ntiles; tile += (int)gridDim.x) {
@@ -59,7 +60,7 @@ __global__ void __launch_bounds__(C_NT) k_bins(int* __restrict__ rdc, float* __r
         for (int k = 0; k < 4; ++k) {
           const int q = qb + k * C_NT + tid;
           if (q >= nq) continue;
-          if (cap_on && (double)v[k] > thr) { v[k] = capv; rdc[B + q0 + q] = capv; }
+          if (cap_on && v[k] > ithr) { v[k] = capv; rdc[B + q0 + q] = capv; }
           vals[q] = v[k];
         }
       }
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(C_NT) k_bins(int* __restrict__ rdc, float* __r
           if (lane < 31 && q < nq) {
             const int v = vals[q], w = v - wb, cls = (Bq + q) % MAD_CLASSES;
             if (Bq + q >= sub31) { if (v >= 0 && v < R) atomicAdd(&thist[v], 1u); }
-            else if ((unsigned)w < (unsigned)C_K) wt[cls * C_K + w] += 1;
+            else if ((unsigned)w < (unsigned)C_K) wt[cls * C_KP + w] += 1;
             else if (v >= 0 && v < R) atomicAdd(&chist[cls * R + v], 1u);
           }
           __syncwarp();
@@ -81,11 +82,25 @@ __global__ void __launch_bounds__(C_NT) k_bins(int* __restrict__ rdc, float* __r
       if (q0 == 0) {
         for (int b = warp; b < nbt; b += C_NW) {
           const int* x = vals + b * m;
+          const int need = (m - 1) / 2 + 1;                    // smallest v with #{x <= v} >= need (m is odd)
+          if (m <= 128) {   // the bin lives in 4 registers per lane; one full-mask REDUX per probe
+            int r[4]; int lo = 0x7fffffff, hi = -0x7fffffff - 1, s32 = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const int j = lane + 32 * k; r[k] = j < m ? x[j] : 0x7fffffff; if (j < m) { lo = imin(lo, r[k]); hi = imax(hi, r[k]); s32 += r[k]; } }
+            lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
+            const i64 s = (i64)__reduce_add_sync(0xffffffffu, (unsigned)s32);     // < 128 * 2^24
+            while (lo < hi) {
+              const int mid = lo + ((hi - lo) >> 1);
+              const int cnt = __reduce_add_sync(0xffffffffu, (r[0] <= mid) + (r[1] <= mid) + (r[2] <= mid) + (r[3] <= mid));
+              if (cnt >= need) hi = mid; else lo = mid + 1;
+            }
+            if (lane == 0) { bin_med[b0 + b] = (float)lo; bin_medint[b0 + b] = lo; bin_sum[b0 + b] = s; mx = lmax(mx, s); }
+            continue;
+          }
           int lo = 0x7fffffff, hi = -0x7fffffff - 1; i64 s = 0;
           for (int j = lane; j < m; j += 32) { const int v = x[j]; lo = imin(lo, v); hi = imax(hi, v); s += v; }
           lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
           s = warp_sum_i64(s);
-          const int need = (m - 1) / 2 + 1;                    // smallest v with #{x <= v} >= need (m is odd)
           while (lo < hi) {
             const int mid = lo + ((hi - lo) >> 1);
             int cnt = 0;
@@ -101,7 +116,7 @@ __global__ void __launch_bounds__(C_NT) k_bins(int* __restrict__ rdc, float* __r
   for (int item = tid; item < MAD_CLASSES * C_K; item += C_NT) {
     const int cl = item / C_K, w = item % C_K;
     u32 s = 0;
-    for (int k = 0; k < C_NW; ++k) s += ct[((size_t)k * MAD_CLASSES + cl) * C_K + w];
+    for (int k = 0; k < C_NW; ++k) s += ct[((size_t)k * MAD_CLASSES + cl) * C_KP + w];
     if (s && wb + w < R) atomicAdd(&chist[cl * R + wb + w], s);
   }
   mx = c.reduce(mx, MaxOp());

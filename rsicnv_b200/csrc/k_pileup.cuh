@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(PU_NT) k_pileup_tile(ReadSoA R, const u32* __r
 // Insert-size sample.  `keep`-filtered reads in file order from the first one overlapping 10 Mbp;
 // sums run up to and including the read that trips a stop rule.
 enum { IS_K = 8 };   // consecutive reads per thread and iteration
-__global__ void __launch_bounds__(1024) k_isize_stats(ReadSoA R, int tid_len, const int* max_extent, DevState* st) {
+__global__ void __launch_bounds__(1024) k_isize_stats(ReadSoA R, int tid_len, const int* max_extent, int* __restrict__ out2) {
   RSI_CTA_SETUP(c);
   __shared__ int s_lastpos, s_segstart, s_segidx;
   const u32 beg = 10000000u, end = 349250621u;
@@ -297,14 +297,14 @@ __global__ void __launch_bounds__(1024) k_isize_stats(ReadSoA R, int tid_len, co
       const double sd = sqrt((s2 - cn * s * s) / cn);
       im = (int)s; isd = (int)sd;
     }
-    st->isize_mean = im; st->isize_sd = isd;
+    out2[0] = im; out2[1] = isd;
   }
 }
 
 // One block per call: Q0 fraction and supporting read pairs.  dis[k] = the carried DIS of call k.
-__global__ void __launch_bounds__(1024) k_cnv_stat(ReadSoA R, Cnv* calls, int ncalls, const int* max_extent, DevState* st) {
+__global__ void __launch_bounds__(1024) k_cnv_stat(ReadSoA R, Cnv* calls, int ncalls, const int* max_extent, const int* __restrict__ isz) {
   RSI_CTA_SETUP(c);
-  const int im = st->isize_mean, isd = st->isize_sd;
+  const int im = isz[0], isd = isz[1];
   for (int k = (int)blockIdx.x; k < ncalls; k += (int)gridDim.x) {
     int DIS = 1000;
     for (int j = 0; j <= k; ++j) {   // DIS is carried from call to call (pairrd.cpp:655-656)

@@ -79,7 +79,9 @@ __global__ void k_add_u64(u64* a, size_t n, u64 v) {
 struct rsigpu_ctx {
   int device = 0, n_sm = 1;
   rsigpu_params P;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr;   // stream2: work that only depends on the staged reads (insert-size sample)
+  cudaEvent_t ev_reads = nullptr, ev_isize = nullptr;
+  bool isize_pending = false;
   std::string err;
   int L = 0, Lc = 0, nb = 0, tid = 0;
   bool have_ref = false, have_depth = false, have_reads = false, loaded = false, detected = false, filtered = false;
@@ -272,7 +274,8 @@ int rsigpu_create(int device, const rsigpu_params* p, rsigpu_ctx** out) {
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return RSIGPU_E_CUDA; }
   c->n_sm = prop.multiProcessorCount;
   set_smem_attrs();
-  bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+  bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess && cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaEventCreate(&c->ev_reads) == cudaSuccess && cudaEventCreate(&c->ev_isize) == cudaSuccess;
   ok = ok && cudaMalloc((void**)&c->d_st, sizeof(DevState)) == cudaSuccess;
   ok = ok && cudaMallocHost((void**)&c->h_st, sizeof(DevState)) == cudaSuccess;
   for (int k = 0; k < 8 && ok; ++k) ok = cudaEventCreate(&c->ev[k]) == cudaSuccess;
@@ -293,6 +296,7 @@ int rsigpu_create(int device, const rsigpu_params* p, rsigpu_ctx** out) {
 void rsigpu_destroy(rsigpu_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  if (c->stream2) cudaStreamSynchronize(c->stream2);
   if (c->stream) cudaStreamSynchronize(c->stream);
   c->d_fasta.release(); c->d_raw.release(); c->d_rdc.release(); c->d_nseq.release();
   c->d_hist_all.release(); c->d_chist.release(); c->d_thist.release(); c->d_tothist.release(); c->d_fq_hist.release();
@@ -306,6 +310,9 @@ void rsigpu_destroy(rsigpu_ctx* c) {
   if (c->h_st) cudaFreeHost(c->h_st);
   if (c->h_lut) cudaFreeHost(c->h_lut);
   for (int k = 0; k < 8; ++k) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
+  if (c->ev_reads) cudaEventDestroy(c->ev_reads);
+  if (c->ev_isize) cudaEventDestroy(c->ev_isize);
+  if (c->stream2) cudaStreamDestroy(c->stream2);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -413,6 +420,16 @@ static int run_pileup(rsigpu_ctx* c) {
     CK(c->r_calend.ensure(c->r_pos.n + 8));
     ReadSoA R = read_view(c);
     KL(k_read_ends, grid_for((int)std::min<size_t>(c->r_pos.n, 1u << 30), 256, c->n_sm * 16), 256, 0, R, mx, mx + 1);
+    // the insert-size sample (bam_rd_pr_stats) needs only the reads: it runs beside the depth pipeline on a second stream
+    CK(cudaEventRecord(c->ev_reads, c->stream));
+    CK(cudaStreamWaitEvent(c->stream2, c->ev_reads, 0));
+    {
+      cudaStream_t main_s = c->stream; c->stream = c->stream2;
+      KL(k_isize_stats, 1, 1024, 0, R, c->L, mx, c->d_misc.p + 16);
+      c->stream = main_s;
+    }
+    CK(cudaEventRecord(c->ev_isize, c->stream2));
+    c->isize_pending = true;
     const int ntile = (c->L + PU_T - 1) / PU_T;
     CK(c->d_tile_range.ensure((size_t)ntile * 2 + 8));
     int2* tr = reinterpret_cast<int2*>(c->d_tile_range.p);
@@ -615,10 +632,10 @@ int rsigpu_cnv_stat(rsigpu_ctx* c) {
   if (v.empty() || c->r_pos.n == 0) return RSIGPU_OK;
   ReadSoA R = read_view(c);
   int* mx = c->d_misc.p + 5;
-  KL(k_isize_stats, 1, 1024, 0, R, c->L, mx, c->d_st);
-  KL(k_cnv_stat, std::min((int)v.size(), c->n_sm * 2), 1024, 0, R, d, (int)v.size(), mx, c->d_st);
+  if (c->isize_pending) { CK(cudaStreamWaitEvent(c->stream, c->ev_isize, 0)); c->isize_pending = false; }
+  KL(k_cnv_stat, std::min((int)v.size(), c->n_sm * 2), 1024, 0, R, d, (int)v.size(), mx, c->d_misc.p + 16);
   CK(cudaMemcpyAsync(v.data(), d, sizeof(Cnv) * v.size(), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(&c->h_st->isize_mean, field_ptr(c->d_st, &DevState::isize_mean), 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(&c->h_st->isize_mean, c->d_misc.p + 16, 8, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return RSIGPU_OK;
 }

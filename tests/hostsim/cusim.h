@@ -396,5 +396,6 @@ inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new CusimEvent(); retu
 inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return 0; }
 inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) { e->t = std::chrono::steady_clock::now(); return 0; }
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return 0; }
 inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) { *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count(); return 0; }
 template <class F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { return 0; }
