@@ -137,7 +137,14 @@ RSI_DEVN void cta_hist_stat(const Cta& c, const CandScratch& S, const T* x, int 
       size_t b = 0;
       if (valid[k]) {
         if (dy == 1.0) b = (size_t)((double)a[k] - mn + 0.5);       // integer samples: the division by dy = 1 is exact anyway
-        else { double idx = ((double)a[k] - mn) / dy + 0.5; b = (size_t)idx; }
+        else {
+          // bucket = (size_t)((x - mn) / dy + 0.5).  dy = 0.01: multiply by 100 (error << 1e-6 for < 2^22 buckets) and fall back
+          // to the exact IEEE division only when the result sits within 1e-6 of a bucket edge.
+          const double t = (double)a[k] - mn;
+          double qv = t * 100.0 + 0.5, fl = floor(qv);
+          if (dy != 0.01 || qv - fl < 1e-6 || fl + 1.0 - qv < 1e-6) { qv = t / dy + 0.5; fl = floor(qv); }
+          b = (size_t)fl;
+        }
       }
       cta_hist_add(H, b, valid[k]);
     }

@@ -62,8 +62,10 @@ __global__ void k_fq_hist(const float* __restrict__ x, const int* __restrict__ s
   for (int i = (int)(blockIdx.x * blockDim.x + threadIdx.x); i < n; i += (int)(gridDim.x * blockDim.x)) {
     if (masked && status[i] != 0) continue;
     const float v = fq_value(x, i, mode, center);
-    const double idx = __dadd_rn(__ddiv_rn((double)v - ymin, 0.01), 0.5);
-    const u64 b = (u64)idx;
+    const double tt = (double)v - ymin;
+    double qv = __dadd_rn(__dmul_rn(tt, 100.0), 0.5), fl = floor(qv);      // exact division only next to a bucket edge
+    if (qv - fl < 1e-6 || fl + 1.0 - qv < 1e-6) { qv = __dadd_rn(__ddiv_rn(tt, 0.01), 0.5); fl = floor(qv); }
+    const u64 b = (u64)fl;
     if (use_sh) atomicAdd(&sh[b], 1u); else atomicAdd(&hist[b], 1u);
   }
   if (use_sh) {

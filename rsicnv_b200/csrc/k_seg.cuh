@@ -138,10 +138,15 @@ __device__ __forceinline__ CandDumps cand_dumps(const CandArgs& A) {
 }
 
 // stage A: keep |score| >= tlamda/2 (rsi.cpp:1340-1345), areblockscnv, sort, bins -> bases
+// The bin-level stage works on a few dozen list entries with many dependent reads by the list-keeping thread:
+// the list, its sort buffer and the overlay entries live in shared memory while it runs.
+enum { CAND_A_LIST = 192 };
+#define RSI_SMEM_CAND_A ((size_t)CAND_SHIST * 4 + (size_t)(2 * CAND_A_LIST + 2) * sizeof(Cnv))
 __global__ void __launch_bounds__(1024) k_cand_a(CandArgs A, CandSpec X, DevState* st) {
   RSI_CTA_SETUP(c);
   RSI_DYN_SMEM(smem);
   A.S.shist = reinterpret_cast<unsigned*>(smem); A.S.shist_cap = CAND_SHIST;
+  Cnv* slist = reinterpret_cast<Cnv*>(smem + (size_t)CAND_SHIST * 4);
   const CandCfg P = cand_cfg(A, st);
   const int n_runs = st->n_runs;
   int nl = 0;
@@ -150,6 +155,14 @@ __global__ void __launch_bounds__(1024) k_cand_a(CandArgs A, CandSpec X, DevStat
     for (int r = 0; r < n_runs; ++r) if (!(fabs(A.segs[r].score) < half)) { if (nl != r) A.segs[nl] = A.segs[r]; ++nl; }
   }
   nl = cta_bcast(c, nl, 3);
+  Cnv* const gsegs = A.segs;
+  const int nsaved = A.all_phase == 2 ? *A.n_saved : 0;
+  const bool in_smem = nl + nsaved <= CAND_A_LIST;
+  if (in_smem) {
+    for (int j = c.tid; j < nl; j += c.nthr) slist[j] = gsegs[j];
+    c.sync();
+    A.segs = slist; A.tmp = slist + CAND_A_LIST; A.ov = slist + 2 * CAND_A_LIST;
+  }
   dump_list(c, A.segs, nl, A.d_segments, &A.n_dump[0], A.list_cap);
   int skip = 0;
   if (A.all_phase) {
@@ -169,6 +182,7 @@ __global__ void __launch_bounds__(1024) k_cand_a(CandArgs A, CandSpec X, DevStat
     skip = 1;
   }
   nl = cand_stage_a(c, P, A.S, st->Lc, A.medint, A.status, st->nb, A.segs, nl, A.tmp, A.ov, cand_dumps(A), skip);
+  if (in_smem) { c.sync(); for (int j = c.tid; j < nl; j += c.nthr) gsegs[j] = slist[j]; }
   if (c.tid == 0) *X.nl = nl;
 }
 // optimize_with_derivative twice per call; calls are independent of each other

@@ -184,7 +184,7 @@ int set_smem_attrs() {
   cudaFuncSetAttribute(k_gc_table, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_A);
   cudaFuncSetAttribute(k_gc_adjust, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_B);
   cudaFuncSetAttribute(k_bins, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_C);
-  cudaFuncSetAttribute(k_cand_a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CAND_SHIST * 4));
+  cudaFuncSetAttribute(k_cand_a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_CAND_A);
   cudaFuncSetAttribute(k_cand_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CAND_SHIST * 4));
   cudaFuncSetAttribute(k_cand_c, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CAND_SHIST * 4));
   cudaFuncSetAttribute(k_cand_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CAND_SHIST * 4));
@@ -584,12 +584,12 @@ int rsigpu_detectcnv(rsigpu_ctx* c) {
   const int gcalls = c->n_sm;
   if (all) {   // -ALL: MED segments are tested and parked, then the NBN pass is run and its segments appended
     A.all_phase = 1;
-    KL(k_cand_a, 1, 256, (size_t)CAND_SHIST * 4, A, X, c->d_st);
+    KL(k_cand_a, 1, 256, RSI_SMEM_CAND_A, A, X, c->d_st);
     if ((rc = run_rsi(c, 0, c->d_bin_nbn.p)) != RSIGPU_OK) return rc;
     CK(cudaEventRecord(c->ev[3], c->stream));
     A.all_phase = 2;
   }
-  KL(k_cand_a, 1, 256, (size_t)CAND_SHIST * 4, A, X, c->d_st);   // bin-level arrays are tiny: fewer threads = cheaper barriers
+  KL(k_cand_a, 1, 256, RSI_SMEM_CAND_A, A, X, c->d_st);   // bin-level arrays are tiny: fewer threads = cheaper barriers
   KL(k_cand_edge, gcalls, 1024, 0, A, X, c->d_st);
   KL(k_cand_b, 1, 1024, (size_t)CAND_SHIST * 4, A, X, c->d_st);
   KL(k_cand_final, gcalls, 1024, (size_t)CAND_SHIST * 4, A, X, c->d_st);
