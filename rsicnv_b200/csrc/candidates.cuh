@@ -197,7 +197,7 @@ RSI_DEVN int cta_collect(const Cta& c, const int* RD, int lo, int hi, int dir, i
   int got = 0, pos = 0;
   const int len = hi - lo + 1;
   const int lane = c.tid & 31, warp = c.tid >> 5, nw = c.nthr >> 5;
-  int* slots = reinterpret_cast<int*>(c.red);
+  unsigned char* slots = c.wslots();
   while (pos < len && got < want) {
     int sc = want - got + c.nthr;               // nearly every position is accepted
     if (sc > len - pos) sc = len - pos;
@@ -210,10 +210,10 @@ RSI_DEVN int cta_collect(const Cta& c, const int* RD, int lo, int hi, int dir, i
       cnt += __popc(__ballot_sync(0xffffffffu, ok));
     }
     c.sync();
-    if (lane == 0) slots[warp] = cnt;
+    if (lane == 0) *reinterpret_cast<int*>(slots + 16 * warp) = cnt;
     c.sync();
     int base = 0, tot = 0;
-    for (int w = 0; w < nw; ++w) { const int v = slots[w]; if (w < warp) base += v; tot += v; }
+    for (int w = 0; w < nw; ++w) { const int v = *reinterpret_cast<volatile int*>(slots + 16 * w); if (w < warp) base += v; tot += v; }
     int off = got + base;
     for (int j0 = w0; j0 < w1 && off < want; j0 += 32) {
       const int j = j0 + lane;
@@ -265,12 +265,12 @@ RSI_DEVN void cta_prefix_i32(const Cta& c, const int* ref, int n, long long* pre
   for (int j = w0 + lane; j < w1; j += 32) loc += (long long)ref[j];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) loc += __shfl_xor_sync(0xffffffffu, loc, o);
-  long long* slots = reinterpret_cast<long long*>(c.red);
+  unsigned char* slots = c.wslots();
   c.sync();
-  if (lane == 0) slots[warp] = loc;
+  if (lane == 0) *reinterpret_cast<long long*>(slots + 16 * warp) = loc;
   c.sync();
   long long carry = 0;
-  for (int w = 0; w < warp; ++w) carry += slots[w];
+  for (int w = 0; w < warp; ++w) carry += *reinterpret_cast<volatile long long*>(slots + 16 * w);
   if (c.tid == 0) pref[0] = 0;
   for (int j0 = w0; j0 < w1; j0 += 32) {
     const int j = j0 + lane;
@@ -513,12 +513,12 @@ RSI_DEVN void edge_refine(const Cta& c, const int* RD, int n, Cnv* cv) {
     for (int j = w0 + lane; j < w1; j += 32) if (j >= 1) { const int p = ns + j; loc += -(long long)RD[p - 1 - len] + 2ll * RD[p - 1] - (long long)RD[p - 1 + len]; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) loc += __shfl_xor_sync(0xffffffffu, loc, o);
-    long long* slots = reinterpret_cast<long long*>(c.red);
+    unsigned char* slots = c.wslots();
     c.sync();
-    if (lane == 0) slots[warp] = loc;
+    if (lane == 0) *reinterpret_cast<long long*>(slots + 16 * warp) = loc;
     c.sync();
     long long carry = dd0;
-    for (int w = 0; w < warp; ++w) carry += slots[w];
+    for (int w = 0; w < warp; ++w) carry += *reinterpret_cast<volatile long long*>(slots + 16 * w);
     for (int j0 = w0; j0 < w1; j0 += 32) {
       const int j = j0 + lane;
       long long inc = 0;

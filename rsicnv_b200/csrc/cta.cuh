@@ -47,32 +47,69 @@ RSI_DEV T shfl_xor_any(T v, int lane_mask) {
   return v;
 }
 
+// cluster-level plumbing (a thread-block cluster of up to 8 CTAs can act as one big cooperative group)
+#if defined(RSI_SIM)
+RSI_DEV void cluster_barrier() { cusim::cluster_sync(); }
+RSI_DEV int cluster_rank() { return (int)cusim::cluster_ctarank(); }
+RSI_DEV int cluster_size() { return (int)cusim::cluster_nctarank(); }
+#else
+RSI_DEV void cluster_barrier() { asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;\n" ::: "memory"); }
+RSI_DEV int cluster_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return (int)r; }
+RSI_DEV int cluster_size() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return (int)r; }
+#endif
+
+enum { CTA_GX_BYTES = 2 * 16 * 16 + 256 * 16 };
+// read a small value another CTA of the cluster wrote to global memory (word-wise volatile loads)
+template <class T>
+RSI_DEV T ld_xcta(const unsigned char* p) {
+  unsigned w[sizeof(T) / 4];
+#pragma unroll
+  for (int k = 0; k < (int)(sizeof(T) / 4); ++k) w[k] = reinterpret_cast<const volatile unsigned*>(p)[k];
+  T v; memcpy(&v, w, sizeof(T));
+  return v;
+}   // cluster exchange area: two generations of 16 partials + 256 warp slots
+
 struct Cta {
-  int tid, nthr;
-  unsigned char* red;  // shared scratch, >= 33 * 16 bytes
-  double* bc;          // shared broadcast area, >= 16 doubles
+  int tid, nthr;       // ids used to distribute work: block-local, or cluster-wide when nctas > 1
+  unsigned char* red;  // shared scratch of THIS block, >= 33 * 16 bytes
+  double* bc;          // broadcast area, >= 16 doubles: shared memory (one block) or global memory (cluster)
+  int ltid = -1, lnthr = 0;   // block-local ids (default: same as tid / nthr)
+  int nctas = 1, rank = 0;
+  unsigned char* gx = nullptr;   // CTA_GX_BYTES of GLOBAL memory shared by the cluster (nctas > 1)
+  mutable int xgen = 0;
 
-  RSI_DEV void sync() const { __syncthreads(); }
+  RSI_DEV int lt() const { return ltid < 0 ? tid : ltid; }
+  RSI_DEV int ln() const { return ltid < 0 ? nthr : lnthr; }
+  RSI_DEV void sync() const { if (nctas > 1) cluster_barrier(); else __syncthreads(); }
+  // per-warp slots indexed by the (cluster-wide) warp id, 16 bytes each
+  RSI_DEV unsigned char* wslots() const { return nctas > 1 ? gx + 2 * 16 * 16 : red; }
 
-  // block-wide reduction, result returned to every thread
+  // reduction over the whole group, result returned to every thread
   template <class T, class Op>
   RSI_DEV T reduce(T v, Op op) const {
     static_assert(sizeof(T) <= 16, "reduce payload");
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = op(v, shfl_xor_any(v, o));
     T* slots = reinterpret_cast<T*>(red);
-    const int warp = tid >> 5, lane = tid & 31, nw = (nthr + 31) >> 5;
+    const int t = lt(), warp = t >> 5, lane = t & 31, nw = (ln() + 31) >> 5;
     __syncthreads();
     if (lane == 0) slots[warp] = v;
     __syncthreads();
     T r = slots[0];
     for (int w = 1; w < nw; ++w) r = op(r, slots[w]);
-    return r;
+    if (nctas == 1) return r;
+    T* ex = reinterpret_cast<T*>(gx + (xgen & 1) * 256);   // 16-byte stride per rank
+    ++xgen;
+    if (t == 0) *reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(ex) + rank * 16) = r;
+    cluster_barrier();
+    T g = ld_xcta<T>(reinterpret_cast<unsigned char*>(ex));
+    for (int k = 1; k < nctas; ++k) { T pk = ld_xcta<T>(reinterpret_cast<unsigned char*>(ex) + k * 16); g = op(g, pk); }
+    return g;
   }
-  // block-wide exclusive prefix sum of one value per thread (thread order); *total to every thread
+  // exclusive prefix sum of one value per thread (thread order over the whole group); *total to every thread
   template <class T>
   RSI_DEV T scan_excl(T v, T* total) const {
-    const int warp = tid >> 5, lane = tid & 31, nw = (nthr + 31) >> 5;
+    const int t = lt(), warp = t >> 5, lane = t & 31, nw = (ln() + 31) >> 5;
     T inc = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -84,9 +121,16 @@ struct Cta {
     if (lane == 31) slots[warp] = inc;
     __syncthreads();
     T base = 0, tot = 0;
-    for (int w = 0; w < nw; ++w) { T s = slots[w]; if (w < warp) base += s; tot += s; }
-    *total = tot;
-    return base + inc - v;
+    for (int w = 0; w < nw; ++w) { T sv = slots[w]; if (w < warp) base += sv; tot += sv; }
+    if (nctas == 1) { *total = tot; return base + inc - v; }
+    unsigned char* ex = gx + (xgen & 1) * 256;
+    ++xgen;
+    if (t == 0) *reinterpret_cast<T*>(ex + rank * 16) = tot;
+    cluster_barrier();
+    T before = 0, all = 0;
+    for (int k = 0; k < nctas; ++k) { T pk = ld_xcta<T>(ex + k * 16); if (k < rank) before += pk; all += pk; }
+    *total = all;
+    return before + base + inc - v;
   }
   template <class T>
   static RSI_DEV T shfl_up_any(T v, int d) {
@@ -116,6 +160,7 @@ struct Cta {
   int tid = 0, nthr = 1;
   unsigned char* red = nullptr;
   double* bc = nullptr;
+  int nctas = 1, rank = 0;
   void sync() const {}
   template <class T, class Op> T reduce(T v, Op) const { return v; }
   template <class T> T scan_excl(T v, T* total) const { *total = v; return T(0); }

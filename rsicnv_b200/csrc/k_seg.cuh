@@ -185,13 +185,38 @@ __global__ void __launch_bounds__(1024) k_cand_a(CandArgs A, CandSpec X, DevStat
   if (in_smem) { c.sync(); for (int j = c.tid; j < nl; j += c.nthr) gsegs[j] = slist[j]; }
   if (c.tid == 0) *X.nl = nl;
 }
+// ---- per-call kernels: one thread-block CLUSTER per call.  The CTAs of a cluster act as one big cooperative group
+// (Cta with nctas > 1: cluster-wide thread ids, hardware cluster barrier, partial results exchanged through a small
+// global scratch), so the neighbourhood of a large call is processed by several SMs instead of one.
+#if defined(RSI_SIM)
+enum { CAND_CL = 4, CAND_CL_NT = 128 };     // the emulator keeps every fiber of a cluster resident: small shapes
+#else
+enum { CAND_CL = 8, CAND_CL_NT = 1024 };
+#endif
+enum { CAND_CL_HIST = 1 << 20 };            // global histogram buckets per cluster
+struct ClusterArgs { unsigned char* gx; double* gbc; unsigned* ghist; };
+__device__ __forceinline__ Cta cluster_cta(unsigned char* smem, const ClusterArgs& G, int* cid, int* ncl) {
+  Cta c;
+  const int nct = cluster_size(), rk = cluster_rank();
+  c.ltid = (int)threadIdx.x; c.lnthr = (int)blockDim.x; c.nctas = nct; c.rank = rk;
+  c.tid = rk * (int)blockDim.x + (int)threadIdx.x; c.nthr = nct * (int)blockDim.x;
+  c.red = smem;                                             // 33 * 16 bytes
+  *cid = (int)blockIdx.x / nct; *ncl = (int)gridDim.x / nct;
+  c.gx = G.gx + (size_t)*cid * CTA_GX_BYTES;
+  c.bc = nct > 1 ? G.gbc + (size_t)*cid * 32 : reinterpret_cast<double*>(smem + 33 * 16);
+  return c;
+}
+#define RSI_SMEM_CAND_CL ((size_t)33 * 16 + 32 * 8 + (size_t)CAND_SHIST * 4)
+
 // optimize_with_derivative twice per call; calls are independent of each other
-__global__ void __launch_bounds__(1024) k_cand_edge(CandArgs A, CandSpec X, DevState* st) {
-  RSI_CTA_SETUP(c);
+__global__ void __launch_bounds__(1024) k_cand_edge(CandArgs A, CandSpec X, ClusterArgs G, DevState* st) {
+  RSI_DYN_SMEM(smem);
+  int cid, ncl;
+  const Cta c = cluster_cta(smem, G, &cid, &ncl);
   const int nl = *X.nl;
   long long tm = cand_clock();
-  for (int j = (int)blockIdx.x; j < nl; j += (int)gridDim.x) { edge_refine(c, A.rdc, st->Lc, &A.segs[j]); edge_refine(c, A.rdc, st->Lc, &A.segs[j]); }
-  if (blockIdx.x == 0) cand_tick(c, A.S, 9, &tm);
+  for (int j = cid; j < nl; j += ncl) { edge_refine(c, A.rdc, st->Lc, &A.segs[j]); edge_refine(c, A.rdc, st->Lc, &A.segs[j]); }
+  if (cid == 0) cand_tick(c, A.S, 9, &tm);
 }
 __global__ void __launch_bounds__(1024) k_cand_b(CandArgs A, CandSpec X, DevState* st) {
   RSI_CTA_SETUP(c);
@@ -202,25 +227,27 @@ __global__ void __launch_bounds__(1024) k_cand_b(CandArgs A, CandSpec X, DevStat
   c.sync();
   if (c.tid == 0) *X.nl = nl;
 }
-// speculative final test, one call per block, each with its own scratch slice
-__global__ void __launch_bounds__(1024) k_cand_final(CandArgs A, CandSpec X, DevState* st) {
-  RSI_CTA_SETUP(c);
+// speculative final test, one call per cluster, each with its own scratch slice
+__global__ void __launch_bounds__(1024) k_cand_final(CandArgs A, CandSpec X, ClusterArgs G, DevState* st) {
   RSI_DYN_SMEM(smem);
+  int cid, ncl;
+  const Cta c = cluster_cta(smem, G, &cid, &ncl);
   if (!*X.on) return;
   const CandCfg P = cand_cfg(A, st);
   const int nl = *X.nl;
   long long tm = cand_clock();
-  for (int j = (int)blockIdx.x; j < nl; j += (int)gridDim.x) {
+  for (int j = cid; j < nl; j += ncl) {
     CandScratch S = A.S;
-    S.shist = reinterpret_cast<unsigned*>(smem); S.shist_cap = CAND_SHIST;
-    S.hist = nullptr; S.hist_cap = 0;                 // no shared global fallback: an overflow flags the call for the in-order pass
+    // one CTA: histogram in its shared memory; several CTAs: the cluster's slice of a global bucket array
+    if (c.nctas == 1) { S.shist = reinterpret_cast<unsigned*>(smem + 33 * 16 + 32 * 8); S.shist_cap = CAND_SHIST; S.hist = nullptr; S.hist_cap = 0; }
+    else { S.shist = nullptr; S.shist_cap = 0; S.hist = G.ghist + (size_t)cid * CAND_CL_HIST; S.hist_cap = CAND_CL_HIST; }
     S.ref = X.ref + X.off[j]; S.pref = X.pref + X.off[j] + j; S.rm = X.rm + X.off[j];
     S.ref_cap = (int)(X.off[j + 1] - X.off[j]) - 8;
-    S.prof = blockIdx.x == 0 ? A.S.prof : nullptr;
+    S.prof = cid == 0 ? A.S.prof : nullptr;
     cand_final_one(c, P, S, A.rdc, st->Lc, A.segs, nl, j, X.res);
     c.sync();
   }
-  if (blockIdx.x == 0) cand_tick(c, A.S, 6, &tm);
+  if (cid == 0) cand_tick(c, A.S, 6, &tm);
 }
 __global__ void __launch_bounds__(1024) k_cand_c(CandArgs A, CandSpec X, DevState* st) {
   RSI_CTA_SETUP(c);

@@ -86,7 +86,7 @@ struct rsigpu_ctx {
   int L = 0, Lc = 0, nb = 0, tid = 0;
   bool have_ref = false, have_depth = false, have_reads = false, loaded = false, detected = false, filtered = false;
   int level0_mode = 2;   // 2 = multi-block exact chain (default), 1 = one-block scan form, 0 = plain sequential FADD chain (cross-check)
-  DevBuf<double> d_csum; DevBuf<i64> d_cchunk;
+  DevBuf<double> d_csum, d_clbc; DevBuf<i64> d_cchunk, d_clx; DevBuf<u32> d_clhist;
   // per-base
   DevBuf<u8> d_fasta; DevBuf<int> d_raw, d_rdc, d_nseq;  // d_nseq: nbeg | nend | ncum
   std::vector<int> h_nbeg, h_nend;
@@ -145,6 +145,14 @@ struct KTimer {
     if (le_ != cudaSuccess && c->launch_err.empty()) c->launch_err = std::string(#name) + ": " + cudaGetErrorString(le_); \
   } while (0)
 
+#define KLC(name, grid, block, cluster, smem, ...)                                                \
+  do {                                                                                            \
+    KTimer kt_(c, #name);                                                                         \
+    RSI_LAUNCH_CLUSTER(name, grid, block, cluster, smem, c->stream, __VA_ARGS__);                 \
+    cudaError_t le_ = cudaGetLastError();                                                         \
+    if (le_ != cudaSuccess && c->launch_err.empty()) c->launch_err = std::string(#name) + ": " + cudaGetErrorString(le_); \
+  } while (0)
+
 template <class T> T* field_ptr(DevState* base, T DevState::*m) { return &(base->*m); }
 
 int map_dev_err(rsigpu_ctx* c, int e, int cand) {
@@ -187,7 +195,8 @@ int set_smem_attrs() {
   cudaFuncSetAttribute(k_cand_a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_CAND_A);
   cudaFuncSetAttribute(k_cand_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CAND_SHIST * 4));
   cudaFuncSetAttribute(k_cand_c, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CAND_SHIST * 4));
-  cudaFuncSetAttribute(k_cand_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CAND_SHIST * 4));
+  cudaFuncSetAttribute(k_cand_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_CAND_CL);
+  cudaFuncSetAttribute(k_cand_edge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_CAND_CL);
   cudaFuncSetAttribute(k_rsi_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SCAN_SMEM);
   return 0;
 }
@@ -284,7 +293,9 @@ int rsigpu_create(int device, const rsigpu_params* p, rsigpu_ctx** out) {
   ok = ok && c->d_fq_hist.ensure((size_t)FQ_BINS_CAP + 8) == cudaSuccess;
   ok = ok && c->d_lists.ensure((size_t)LIST_CAP * 11 + 8) == cudaSuccess && c->d_misc.ensure(64) == cudaSuccess;
   ok = ok && c->d_runs.ensure((size_t)LIST_CAP * 2 + 8) == cudaSuccess && c->d_cprof.ensure(16) == cudaSuccess && c->d_thr.ensure(2 * (LMAX_CAP + 2)) == cudaSuccess && c->d_csum.ensure(CHN_N + 8) == cudaSuccess
-       && c->d_cchunk.ensure((size_t)(CHN_N + 8) * sizeof(ChainChunk) / 8 + 8) == cudaSuccess;
+       && c->d_cchunk.ensure((size_t)(CHN_N + 8) * sizeof(ChainChunk) / 8 + 8) == cudaSuccess
+       && c->d_clx.ensure((size_t)32 * CTA_GX_BYTES / 8 + 8) == cudaSuccess && c->d_clbc.ensure(32 * 32 + 8) == cudaSuccess
+       && c->d_clhist.ensure((size_t)32 * CAND_CL_HIST + 8) == cudaSuccess;
   ok = ok && c->d_chist_c.ensure(1u << 22) == cudaSuccess && c->d_sub.ensure((size_t)p->maxchkbp * 10 + 64) == cudaSuccess;
   ok = ok && c->d_nrun_beg.ensure(1 << 20) == cudaSuccess && c->d_nrun_end.ensure(1 << 20) == cudaSuccess;
   if (ok) ok = cudaMemsetAsync(c->d_fq_hist.p, 0, ((size_t)FQ_BINS_CAP + 8) * 4, c->stream) == cudaSuccess;
@@ -301,7 +312,7 @@ void rsigpu_destroy(rsigpu_ctx* c) {
   c->d_fasta.release(); c->d_raw.release(); c->d_rdc.release(); c->d_nseq.release();
   c->d_hist_all.release(); c->d_chist.release(); c->d_thist.release(); c->d_tothist.release(); c->d_fq_hist.release();
   c->d_bin_med.release(); c->d_bin_nbn.release(); c->d_lut.release(); c->d_bin_medint.release(); c->d_status.release(); c->d_status1.release();
-  c->d_tile.release(); c->d_nz_idx.release(); c->d_nz_val.release(); c->d_runs.release(); c->d_bin_sum.release(); c->d_pfx.release(); c->d_cprof.release(); c->d_thr.release(); c->d_csum.release(); c->d_cchunk.release(); c->d_minl_del.release(); c->d_minl_dup.release();
+  c->d_tile.release(); c->d_nz_idx.release(); c->d_nz_val.release(); c->d_runs.release(); c->d_bin_sum.release(); c->d_pfx.release(); c->d_cprof.release(); c->d_thr.release(); c->d_csum.release(); c->d_cchunk.release(); c->d_clx.release(); c->d_clbc.release(); c->d_clhist.release(); c->d_minl_del.release(); c->d_minl_dup.release();
   c->d_lists.release(); c->d_misc.release(); c->d_ref.release(); c->d_sub.release(); c->d_pref.release(); c->d_rm.release(); c->d_chist_c.release(); c->d_spec_ref.release(); c->d_spec_pref.release(); c->d_spec_off.release(); c->d_spec_rm.release();
   c->d_nrun_beg.release(); c->d_nrun_end.release(); c->d_scan_scratch.release(); c->d_tile_range.release(); c->d_qmask.release(); c->r_calend.release();
   c->r_pos.release(); c->r_mpos.release(); c->r_isize.release(); c->r_mtid.release(); c->r_flag.release(); c->r_mapq.release(); c->r_qual.release();
@@ -581,7 +592,6 @@ int rsigpu_detectcnv(rsigpu_ctx* c) {
   X.off = c->d_spec_off.p; X.res = c->list(9); X.on = c->d_misc.p + 12; X.nl = c->d_misc.p + 13;
   X.cap = (long long)c->d_spec_ref.cap - 64; X.ref = c->d_spec_ref.p; X.pref = c->d_spec_pref.p; X.rm = c->d_spec_rm.p;
   CK(cudaMemsetAsync(c->d_misc.p + 12, 0, 8, c->stream));
-  const int gcalls = c->n_sm;
   if (all) {   // -ALL: MED segments are tested and parked, then the NBN pass is run and its segments appended
     A.all_phase = 1;
     KL(k_cand_a, 1, 256, RSI_SMEM_CAND_A, A, X, c->d_st);
@@ -590,9 +600,11 @@ int rsigpu_detectcnv(rsigpu_ctx* c) {
     A.all_phase = 2;
   }
   KL(k_cand_a, 1, 256, RSI_SMEM_CAND_A, A, X, c->d_st);   // bin-level arrays are tiny: fewer threads = cheaper barriers
-  KL(k_cand_edge, gcalls, 1024, 0, A, X, c->d_st);
+  ClusterArgs G; G.gx = reinterpret_cast<unsigned char*>(c->d_clx.p); G.gbc = c->d_clbc.p; G.ghist = c->d_clhist.p;
+  const int ncl = std::max(1, std::min(c->n_sm / CAND_CL, 32));
+  KLC(k_cand_edge, ncl * CAND_CL, CAND_CL_NT, CAND_CL, RSI_SMEM_CAND_CL, A, X, G, c->d_st);
   KL(k_cand_b, 1, 1024, (size_t)CAND_SHIST * 4, A, X, c->d_st);
-  KL(k_cand_final, gcalls, 1024, (size_t)CAND_SHIST * 4, A, X, c->d_st);
+  KLC(k_cand_final, ncl * CAND_CL, CAND_CL_NT, CAND_CL, RSI_SMEM_CAND_CL, A, X, G, c->d_st);
   KL(k_cand_c, 1, 1024, (size_t)CAND_SHIST * 4, A, X, c->d_st);
   CK(cudaEventRecord(c->ev[4], c->stream));
   CK(cudaMemcpyAsync(h, c->d_st, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));

@@ -8,11 +8,24 @@
 #include "cusim.h"
 #define RSI_LAUNCH(kern, grid, block, smem, stream, ...) \
   do { (void)(stream); cusim::launch(dim3(grid), dim3(block), (size_t)(smem), [=]() { kern(__VA_ARGS__); }); } while (0)
-#define RSI_DYN_SMEM(name) unsigned char* name = cusim::S().dyn_smem
+#define RSI_DYN_SMEM(name) unsigned char* name = cusim::S().dyn()
+#define RSI_LAUNCH_CLUSTER(kern, grid, block, cluster, smem, stream, ...) \
+  do { (void)(stream); cusim::launch(dim3(grid), dim3(block), (size_t)(smem), [=]() { kern(__VA_ARGS__); }, (cluster)); } while (0)
 #else
 #include <cuda_runtime.h>
 #define RSI_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<dim3(grid), dim3(block), (size_t)(smem), (stream)>>>(__VA_ARGS__)
 #define RSI_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+// launch with a thread-block cluster of `cluster` CTAs along x (grid.x must be a multiple of it)
+#define RSI_LAUNCH_CLUSTER(kern, grid, block, cluster, smem, strm_, ...)                                        \
+  do {                                                                                                          \
+    cudaLaunchConfig_t cfg_ = {};                                                                               \
+    cfg_.gridDim = dim3(grid); cfg_.blockDim = dim3(block); cfg_.dynamicSmemBytes = (size_t)(smem); cfg_.stream = (strm_); \
+    cudaLaunchAttribute at_[1];                                                                                 \
+    at_[0].id = cudaLaunchAttributeClusterDimension;                                                            \
+    at_[0].val.clusterDim.x = (cluster); at_[0].val.clusterDim.y = 1; at_[0].val.clusterDim.z = 1;              \
+    cfg_.attrs = at_; cfg_.numAttrs = 1;                                                                        \
+    cudaLaunchKernelEx(&cfg_, kern, __VA_ARGS__);                                                               \
+  } while (0)
 #endif
 
 namespace rsigpu {

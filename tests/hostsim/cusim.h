@@ -59,17 +59,26 @@ struct Fiber {
   bool done = false;
   unsigned long long bar_gen_wait = 0;
 };
-struct State {
-  std::vector<Fiber> fib;
+struct BlockCtx {     // one resident thread block (a cluster launch keeps several resident at once)
   std::vector<Warp> warps;
-  int nthreads = 0, cur = -1, live = 0;
+  int live = 0;
   unsigned long long bar_gen = 0; int bar_arrived = 0; int bar_acc_or = 0, bar_acc_and = 1, bar_acc_cnt = 0;
   int bar_res_or[2] = {0, 0}, bar_res_and[2] = {1, 1}, bar_res_cnt[2] = {0, 0};
+  unsigned char* dyn_smem = nullptr;
+  uint3 bidx{0, 0, 0};
+};
+struct State {
+  std::vector<Fiber> fib;        // [block-in-cluster][thread] flattened
+  std::vector<BlockCtx> blk;
+  int nthreads = 0, nblk = 1, cur = -1, live = 0;
+  unsigned long long cl_gen = 0; int cl_arrived = 0;   // cluster barrier
   void* sched_sp = nullptr;
   std::function<void()> body;
-  unsigned char* dyn_smem = nullptr;
   unsigned long long progress = 0;
   dim3 block_dim, grid_dim;
+  BlockCtx& cb() { return blk[cur / nthreads]; }
+  int ct() const { return cur % nthreads; }
+  unsigned char* dyn() { return cb().dyn_smem; }
 };
 inline State& S() { static State s; return s; }
 
@@ -110,22 +119,25 @@ inline void yield_to_sched() {
   Fiber& f = s.fib[s.cur];
   cusim_switch(&f.sp, s.sched_sp);
 }
+inline void release_block_barrier(BlockCtx& b) {
+  int slot = (int)(b.bar_gen & 1);
+  b.bar_res_or[slot] = b.bar_acc_or; b.bar_res_and[slot] = b.bar_acc_and; b.bar_res_cnt[slot] = b.bar_acc_cnt;
+  b.bar_acc_or = 0; b.bar_acc_and = 1; b.bar_acc_cnt = 0; b.bar_arrived = 0; b.bar_gen++;
+}
 void fiber_entry();
 #if defined(CUSIM_IMPL)
 void fiber_entry() {
   State& s = S();
   s.body();
   Fiber& f = s.fib[s.cur];
+  BlockCtx& b = s.cb();
   f.done = true;
-  s.live--;
-  s.warps[s.cur >> 5].alive &= ~(1u << (s.cur & 31));
+  s.live--; b.live--;
+  b.warps[s.ct() >> 5].alive &= ~(1u << (s.ct() & 31));
   s.progress++;
   // a thread that exits releases a barrier the others are waiting on
-  if (s.live > 0 && s.bar_arrived == s.live) {
-    int slot = (int)(s.bar_gen & 1);
-    s.bar_res_or[slot] = s.bar_acc_or; s.bar_res_and[slot] = s.bar_acc_and; s.bar_res_cnt[slot] = s.bar_acc_cnt;
-    s.bar_acc_or = 0; s.bar_acc_and = 1; s.bar_acc_cnt = 0; s.bar_arrived = 0; s.bar_gen++;
-  }
+  if (b.live > 0 && b.bar_arrived == b.live) release_block_barrier(b);
+  if (s.live > 0 && s.cl_arrived == s.live) { s.cl_arrived = 0; s.cl_gen++; }
   cusim_switch(&f.sp, s.sched_sp);
   std::abort();
 }
@@ -133,22 +145,28 @@ void fiber_entry() {
 
 static const size_t kStack = 96 * 1024;
 
-inline void set_indices(int t) {
+inline void set_indices(int f) {
   State& s = S();
+  const int t = f % s.nthreads;
   uint3& ti = tIdx();
   ti.x = t % s.block_dim.x; ti.y = (t / s.block_dim.x) % s.block_dim.y; ti.z = t / (s.block_dim.x * s.block_dim.y);
+  bIdx() = s.blk[f / s.nthreads].bidx;
 }
 
-void run_block(int order_mode);
+void run_resident(int order_mode);
 #if defined(CUSIM_IMPL)
-void run_block(int order_mode) {
+void run_resident(int order_mode) {   // runs the s.nblk resident blocks (1, or a whole cluster) to completion
   State& s = S();
-  const int n = s.nthreads;
-  s.live = n; s.bar_gen = 0; s.bar_arrived = 0; s.bar_acc_or = 0; s.bar_acc_and = 1; s.bar_acc_cnt = 0;
+  const int n = s.nthreads, nf = n * s.nblk;
+  s.live = nf; s.cl_gen = 0; s.cl_arrived = 0;
   const int nw = (n + 31) / 32;
-  s.warps.assign(nw, Warp());
-  for (int t = 0; t < n; ++t) s.warps[t >> 5].alive |= 1u << (t & 31);
-  for (int t = 0; t < n; ++t) {
+  for (int b = 0; b < s.nblk; ++b) {
+    BlockCtx& B = s.blk[b];
+    B.live = n; B.bar_gen = 0; B.bar_arrived = 0; B.bar_acc_or = 0; B.bar_acc_and = 1; B.bar_acc_cnt = 0;
+    B.warps.assign(nw, Warp());
+    for (int t = 0; t < n; ++t) B.warps[t >> 5].alive |= 1u << (t & 31);
+  }
+  for (int t = 0; t < nf; ++t) {
     Fiber& f = s.fib[t];
     f.done = false; f.bar_gen_wait = 0;
     // initial frame: six zeroed callee-saved registers, then the entry address for `ret`
@@ -162,10 +180,10 @@ void run_block(int order_mode) {
   unsigned long long rounds = 0;
   while (s.live > 0) {
     unsigned long long before = s.progress;
-    for (int k = 0; k < n; ++k) {
+    for (int k = 0; k < nf; ++k) {
       int t = k;
-      if (order_mode == 1) t = n - 1 - k;
-      else if (order_mode == 2) t = (int)((k + rounds * 7) % (unsigned long long)n);
+      if (order_mode == 1) t = nf - 1 - k;
+      else if (order_mode == 2) t = (int)((k + rounds * 7) % (unsigned long long)nf);
       Fiber& f = s.fib[t];
       if (f.done) continue;
       s.cur = t;
@@ -174,7 +192,7 @@ void run_block(int order_mode) {
     }
     ++rounds;
     if (s.progress == before) {
-      std::fprintf(stderr, "cusim: deadlock (divergent barrier / collective) in block (%u,%u,%u)\n", bIdx().x, bIdx().y, bIdx().z);
+      std::fprintf(stderr, "cusim: deadlock (divergent barrier / collective) near block (%u,%u,%u)\n", bIdx().x, bIdx().y, bIdx().z);
       std::abort();
     }
   }
@@ -187,51 +205,66 @@ inline int order_mode() {
   return m;
 }
 
-void launch(dim3 grid, dim3 block, size_t smem, std::function<void()> body);
+void launch(dim3 grid, dim3 block, size_t smem, std::function<void()> body, int cluster = 1);
 #if defined(CUSIM_IMPL)
-void launch(dim3 grid, dim3 block, size_t smem, std::function<void()> body) {
+void launch(dim3 grid, dim3 block, size_t smem, std::function<void()> body, int cluster) {
   State& s = S();
   if (s.cur >= 0 && s.live > 0) { std::fprintf(stderr, "cusim: nested launch\n"); std::abort(); }
   const int n = (int)(block.x * block.y * block.z);
   if (n <= 0 || n > 1024) { std::fprintf(stderr, "cusim: bad block size %d\n", n); std::abort(); }
-  if ((int)s.fib.size() < n) {
+  if (cluster < 1 || grid.x % (unsigned)cluster) { std::fprintf(stderr, "cusim: grid.x not a multiple of the cluster size\n"); std::abort(); }
+  const int nf = n * cluster;
+  if ((int)s.fib.size() < nf) {
     size_t old = s.fib.size();
-    s.fib.resize(n);
-    for (size_t t = old; t < (size_t)n; ++t) s.fib[t].stack = (char*)std::malloc(kStack);
+    s.fib.resize(nf);
+    for (size_t t = old; t < (size_t)nf; ++t) s.fib[t].stack = (char*)std::malloc(kStack);
   }
-  std::vector<unsigned char> dyn(smem + 64);
-  s.nthreads = n; s.block_dim = block; s.grid_dim = grid; s.body = std::move(body);
+  std::vector<std::vector<unsigned char>> dyn(cluster, std::vector<unsigned char>(smem + 64));
+  s.nthreads = n; s.nblk = cluster; s.block_dim = block; s.grid_dim = grid; s.body = std::move(body);
+  s.blk.assign(cluster, BlockCtx());
   bDim() = block; gDim() = grid;
   for (unsigned z = 0; z < grid.z; ++z)
     for (unsigned y = 0; y < grid.y; ++y)
-      for (unsigned x = 0; x < grid.x; ++x) {
-        std::memset(dyn.data(), 0xCD, dyn.size());  // shared memory is NOT zero-initialised on a GPU
-        s.dyn_smem = (unsigned char*)(((uintptr_t)dyn.data() + 15) & ~(uintptr_t)15);
-        bIdx().x = x; bIdx().y = y; bIdx().z = z;
-        run_block(order_mode());
+      for (unsigned x = 0; x < grid.x; x += (unsigned)cluster) {
+        for (int b = 0; b < cluster; ++b) {
+          std::memset(dyn[b].data(), 0xCD, dyn[b].size());  // shared memory is NOT zero-initialised on a GPU
+          s.blk[b].dyn_smem = (unsigned char*)(((uintptr_t)dyn[b].data() + 15) & ~(uintptr_t)15);
+          s.blk[b].bidx = uint3{x + (unsigned)b, y, z};
+        }
+        run_resident(order_mode());
       }
   s.cur = -1; s.live = 0;
 }
 #endif
 
+// ---- cluster: rank of the block, size, barrier over every thread of every block of the cluster
+inline unsigned cluster_ctarank() { return (unsigned)(S().cur / S().nthreads); }
+inline unsigned cluster_nctarank() { return (unsigned)S().nblk; }
+inline void cluster_sync() {
+  State& s = S();
+  const unsigned long long gen = s.cl_gen;
+  s.cl_arrived++;
+  s.progress++;
+  if (s.cl_arrived == s.live) { s.cl_arrived = 0; s.cl_gen++; }
+  else while (s.cl_gen == gen) yield_to_sched();
+}
+
 // ---- block barrier
 inline int barrier(int pred, int kind) {  // kind 0 plain, 1 or, 2 and, 3 count
   State& s = S();
+  BlockCtx& b = s.cb();
   Fiber& f = s.fib[s.cur];
-  s.bar_acc_or |= (pred != 0); s.bar_acc_and &= (pred != 0); s.bar_acc_cnt += (pred != 0);
-  const unsigned long long gen = s.bar_gen;
-  s.bar_arrived++;
+  b.bar_acc_or |= (pred != 0); b.bar_acc_and &= (pred != 0); b.bar_acc_cnt += (pred != 0);
+  const unsigned long long gen = b.bar_gen;
+  b.bar_arrived++;
   s.progress++;
-  if (s.bar_arrived == s.live) {
-    int slot = (int)(gen & 1);
-    s.bar_res_or[slot] = s.bar_acc_or; s.bar_res_and[slot] = s.bar_acc_and; s.bar_res_cnt[slot] = s.bar_acc_cnt;
-    s.bar_acc_or = 0; s.bar_acc_and = 1; s.bar_acc_cnt = 0; s.bar_arrived = 0; s.bar_gen++;
-  } else {
+  if (b.bar_arrived == b.live) release_block_barrier(b);
+  else {
     f.bar_gen_wait = gen;
-    while (s.bar_gen == gen) yield_to_sched();
+    while (b.bar_gen == gen) yield_to_sched();
   }
   int slot = (int)(gen & 1);
-  return kind == 1 ? s.bar_res_or[slot] : kind == 2 ? s.bar_res_and[slot] : kind == 3 ? s.bar_res_cnt[slot] : 0;
+  return kind == 1 ? b.bar_res_or[slot] : kind == 2 ? b.bar_res_and[slot] : kind == 3 ? b.bar_res_cnt[slot] : 0;
 }
 
 // ---- warp collective: the last lane to arrive computes every participant's result
@@ -239,8 +272,8 @@ template <class T, class R, class F>
 inline R warp_coll(unsigned mask, const T& val, F f) {
   static_assert(sizeof(T) <= 16 && sizeof(R) <= 16, "payload");
   State& s = S();
-  Warp& W = s.warps[s.cur >> 5];
-  const int lane = s.cur & 31;
+  Warp& W = s.cb().warps[s.ct() >> 5];
+  const int lane = s.ct() & 31;
   const unsigned bit = 1u << lane;
   mask &= W.alive;
   if (!(mask & bit)) { std::fprintf(stderr, "cusim: lane %d not in its own mask\n", lane); std::abort(); }
@@ -280,7 +313,7 @@ inline void __syncwarp(unsigned mask = 0xffffffffu) {
 }
 inline void __threadfence() {}
 inline void __threadfence_block() {}
-inline unsigned __activemask() { return cusim::S().warps[cusim::S().cur >> 5].alive; }
+inline unsigned __activemask() { return cusim::S().cb().warps[cusim::S().ct() >> 5].alive; }
 
 template <class T> inline T __shfl_sync(unsigned mask, T v, int src, int width = 32) {
   return cusim::warp_coll<T, T>(mask, v, [=](int l, const T* a, unsigned) { int base = l & ~(width - 1); return a[base + (src & (width - 1))]; });
