@@ -103,7 +103,9 @@ __device__ bool window_median_ok(const int* __restrict__ medint, int i1, int L, 
 // result does not depend on how hits cluster.  Dynamic shared memory (NB = S_T + 2*LMAX_CAP staged bins):
 //   P[NB+1] i64 | SA/EA x DEL/DUP [4][S_T] i32 | cle,cge [NB+1] u16 | hit words [2][2][S_NC/32+1] u32
 enum { S_NB = S_T + 2 * LMAX_CAP, S_NC = S_T + 2 * S_H };
-#define RSI_SCAN_SMEM ((size_t)(S_NB + 1) * 8 + (size_t)4 * S_T * 4 + (size_t)2 * (S_NB + 2) * 2 + (size_t)4 * (S_NC / 32 + 2) * 4)
+enum { LMAX_SMALL = 256 };        // most contigs need far fewer window lengths than LMAX_CAP: a second instantiation with a small footprint
+#define RSI_SCAN_SMEM_T(LCAP) ((size_t)(S_T + 2 * (LCAP) + 1) * 8 + (size_t)4 * S_T * 4 + (size_t)2 * (S_T + 2 * (LCAP) + 2) * 2 + (size_t)4 * ((S_T + 2 * ((LCAP) / 2 + 2)) / 32 + 2) * 4)
+#define RSI_SCAN_SMEM RSI_SCAN_SMEM_T(LMAX_CAP)
 
 // prev / next index with a condition, over the staged bins (block-wide max / min scans, thread-contiguous)
 __device__ void scan_prev_next(const Cta& c, const u8* cond, int N, int* prevv, int* nextv) {
@@ -162,17 +164,20 @@ __global__ void k_rsi_thresholds(i64* __restrict__ thr, DevState* st) {
   }
 }
 
-__global__ void __launch_bounds__(S_NT) k_rsi_scan(const float* __restrict__ t, const int* __restrict__ medint, u32* __restrict__ minl_del,
-                                                    u32* __restrict__ minl_dup, int* __restrict__ scratch, const i64* __restrict__ thr, DevState* st) {
+template <int LCAP, bool SMALL>
+__device__ __forceinline__ void rsi_scan_body(const float* __restrict__ t, const int* __restrict__ medint, u32* __restrict__ minl_del,
+                                              u32* __restrict__ minl_dup, int* __restrict__ scratch, const i64* __restrict__ thr, DevState* st) {
   RSI_DYN_SMEM(smem);
   RSI_CTA_SETUP(c);
+  constexpr int S_NBT = S_T + 2 * LCAP, S_NCT = S_T + 2 * (LCAP / 2 + 2);
   i64* P = reinterpret_cast<i64*>(smem);
-  int* SAEA = reinterpret_cast<int*>(P + (S_NB + 1));        // [0]=SA_del [1]=EA_del [2]=SA_dup [3]=EA_dup, S_T each
+  int* SAEA = reinterpret_cast<int*>(P + (S_NBT + 1));        // [0]=SA_del [1]=EA_del [2]=SA_dup [3]=EA_dup, S_T each
   u16* cle = reinterpret_cast<u16*>(SAEA + 4 * S_T);
-  u16* cge = cle + (S_NB + 2);
-  u32* hw = reinterpret_cast<u32*>(cge + (S_NB + 2));              // [buf][sign][word]
-  const int NW = S_NC / 32 + 2;
+  u16* cge = cle + (S_NBT + 2);
+  u32* hw = reinterpret_cast<u32*>(cge + (S_NBT + 2));              // [buf][sign][word]
+  const int NW = S_NCT / 32 + 2;
   const int nb = st->nb, Lmax = st->Lmax;
+  if (SMALL ? Lmax > LCAP : Lmax <= LMAX_SMALL) return;             // the other instantiation handles this contig
   const double tmed = st->tmedian, limd = st->lim_del, limu = st->lim_dup;
   const int c0 = (int)blockIdx.x * S_T;
   const int HB = Lmax + 1;                        // staged bins: [c0 - HB, c0 + S_T + HB)
@@ -309,6 +314,15 @@ __global__ void __launch_bounds__(S_NT) k_rsi_scan(const float* __restrict__ t, 
     const int j = c0 + tid + r * S_NT;
     if (j < nb) { minl_del[j] = ml_del[r]; minl_dup[j] = ml_dup[r]; }
   }
+}
+
+__global__ void __launch_bounds__(S_NT) k_rsi_scan(const float* __restrict__ t, const int* __restrict__ medint, u32* __restrict__ minl_del,
+                                                    u32* __restrict__ minl_dup, int* __restrict__ scratch, const i64* __restrict__ thr, DevState* st) {
+  rsi_scan_body<LMAX_CAP, false>(t, medint, minl_del, minl_dup, scratch, thr, st);
+}
+__global__ void __launch_bounds__(S_NT) k_rsi_scan_small(const float* __restrict__ t, const int* __restrict__ medint, u32* __restrict__ minl_del,
+                                                          u32* __restrict__ minl_dup, int* __restrict__ scratch, const i64* __restrict__ thr, DevState* st) {
+  rsi_scan_body<LMAX_SMALL, true>(t, medint, minl_del, minl_dup, scratch, thr, st);
 }
 
 // ---- the "stop once more than 20% is marked" rule (rsi.cpp:1225, 1255) from the histogram over L
@@ -520,7 +534,7 @@ __global__ void __launch_bounds__(CH_NT) k_level0_chain_scan(const float* __rest
 // accumulator: when its binade matches a hypothesis and the chunk does not leave the binade, the chunk is
 // applied in O(1); otherwise (the ~20 binade crossings, or a wrong guess) the chunk is staged in shared
 // memory and added element by element with real FADDs.
-enum { CHN_N = 2048 };
+enum { CHN_N = 512 };
 struct ChainChunk { ParStep h0, h1; int e0; int n_unmarked; };
 __device__ __forceinline__ void chain_bounds(int nb, int chunk, int* c0, int* c1) {
   const int per = (((nb + CHN_N - 1) / CHN_N) + 31) & ~31;

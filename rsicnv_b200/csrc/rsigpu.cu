@@ -198,6 +198,7 @@ int set_smem_attrs() {
   cudaFuncSetAttribute(k_cand_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_CAND_CL);
   cudaFuncSetAttribute(k_cand_edge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_CAND_CL);
   cudaFuncSetAttribute(k_rsi_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SCAN_SMEM);
+  cudaFuncSetAttribute(k_rsi_scan_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SCAN_SMEM_T(LMAX_SMALL));
   return 0;
 }
 
@@ -213,6 +214,7 @@ int run_rsi(rsigpu_ctx* c, int which, const float* t) {
   KL(k_rsi_params2, 1, 32, 0, t, st, which, c->P.threshold, slot0 + 1);
   for (int pass = 0; pass < 2; ++pass) {
     KL(k_rsi_thresholds, (LMAX_CAP + 63) / 64, 64, 0, c->d_thr.p, st);
+    KL(k_rsi_scan_small, (nb + S_T - 1) / S_T, S_NT, RSI_SCAN_SMEM_T(LMAX_SMALL), t, c->d_bin_medint.p, c->d_minl_del.p, c->d_minl_dup.p, c->d_scan_scratch.p, c->d_thr.p, st);
     KL(k_rsi_scan, (nb + S_T - 1) / S_T, S_NT, scan_smem, t, c->d_bin_medint.p, c->d_minl_del.p, c->d_minl_dup.p, c->d_scan_scratch.p, c->d_thr.p, st);
     KL(k_rsi_cnt_del, gb, 256, 0, c->d_minl_del.p, st);
     KL(k_rsi_cnt_dup, gb, 256, 0, c->d_minl_del.p, c->d_minl_dup.p, st);

@@ -23,6 +23,7 @@ CASES = [
     dict(L=700_003, seed=9, stress=True),
     dict(L=500_003, seed=10, kw=dict(merge=False), stress=True),
     dict(L=500_003, seed=39, stress=True), dict(L=500_003, seed=51, stress=True),
+    dict(L=600_007, seed=6, kw=dict(trans="MED", threshold=5.0)),   # Lmax = (4*5)^2 = 400 > 256: the large-footprint scan instantiation
     dict(L=600_007, seed=6, kw=dict(trans="ALL")), dict(L=700_003, seed=9, kw=dict(trans="ALL"), stress=True),   # a final test fails: the speculative per-call results are redone in order
 ]
 
