@@ -85,6 +85,7 @@ struct rsigpu_ctx {
   std::string err;
   int L = 0, Lc = 0, nb = 0, tid = 0;
   bool have_ref = false, have_depth = false, have_reads = false, loaded = false, detected = false, filtered = false;
+  int cand_a_threads = 256;
   int level0_mode = 2;   // 2 = multi-block exact chain (default), 1 = one-block scan form, 0 = plain sequential FADD chain (cross-check)
   DevBuf<double> d_csum, d_clbc; DevBuf<i64> d_cchunk, d_clx; DevBuf<u32> d_clhist;
   // per-base
@@ -596,12 +597,12 @@ int rsigpu_detectcnv(rsigpu_ctx* c) {
   CK(cudaMemsetAsync(c->d_misc.p + 12, 0, 8, c->stream));
   if (all) {   // -ALL: MED segments are tested and parked, then the NBN pass is run and its segments appended
     A.all_phase = 1;
-    KL(k_cand_a, 1, 256, RSI_SMEM_CAND_A, A, X, c->d_st);
+    KL(k_cand_a, 1, c->cand_a_threads, RSI_SMEM_CAND_A, A, X, c->d_st);
     if ((rc = run_rsi(c, 0, c->d_bin_nbn.p)) != RSIGPU_OK) return rc;
     CK(cudaEventRecord(c->ev[3], c->stream));
     A.all_phase = 2;
   }
-  KL(k_cand_a, 1, 256, RSI_SMEM_CAND_A, A, X, c->d_st);   // bin-level arrays are tiny: fewer threads = cheaper barriers
+  KL(k_cand_a, 1, c->cand_a_threads, RSI_SMEM_CAND_A, A, X, c->d_st);   // bin-level arrays are tiny: fewer threads = cheaper barriers
   ClusterArgs G; G.gx = reinterpret_cast<unsigned char*>(c->d_clx.p); G.gbc = c->d_clbc.p; G.ghist = c->d_clhist.p;
   const int ncl = std::max(1, std::min(c->n_sm / CAND_CL, 32));
   KLC(k_cand_edge, ncl * CAND_CL, CAND_CL_NT, CAND_CL, RSI_SMEM_CAND_CL, A, X, G, c->d_st);
@@ -785,6 +786,12 @@ int rsigpu_debug_state(const rsigpu_ctx* c, double* out, int32_t cap) {
 }
 
 // test hook: 0 = sequential float chain for filterstatus' level-0 sum, 1 = block-scan form (default)
-int rsigpu_set_level0_mode(rsigpu_ctx* c, int mode) { if (!c || mode < 0 || mode > 2) return RSIGPU_E_ARG; c->level0_mode = mode; return RSIGPU_OK; }
+int rsigpu_set_level0_mode(rsigpu_ctx* c, int mode) {
+  if (!c) return RSIGPU_E_ARG;
+  if (mode >= 100) { c->cand_a_threads = mode - 100; return RSIGPU_OK; }   // tuning hook: 100 + threads of the bin-level candidate kernel
+  if (mode < 0 || mode > 2) return RSIGPU_E_ARG;
+  c->level0_mode = mode;
+  return RSIGPU_OK;
+}
 
 }  // extern "C"
