@@ -130,7 +130,8 @@ def ref_worker(args):
 
 def ref_bam_worker(args):
     """one reference-CPU process on the BAM path: the UNMODIFIED reference CLI on its own sorted + indexed synthetic BAM"""
-    seed, L, workdir = args
+    seed, L, workdir = args[:3]
+    with_ours = len(args) > 3 and args[3]
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from bind import REF_BAMTOOL, REF_BIN
     d = os.path.join(workdir, f"s{seed}")
@@ -144,12 +145,24 @@ def ref_bam_worker(args):
                    check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     dt = time.perf_counter() - t0
     ncalls = sum(1 for ln in open(os.path.join(d, "out.txt")) if not ln.startswith("#"))
-    return dt, ncalls
+    ours = None
+    cli = os.path.join(ROOT, "rsicnv_b200", "bin", "rsicnv")
+    if with_ours and os.path.exists(cli):
+        # the same files through this repo's CLI (host BGZF/BAM decode + the CUDA path); second run = CUDA context and page cache warm
+        ts = []
+        for _ in range(2):
+            t0 = time.perf_counter()
+            subprocess.run([cli, "rsi", "-b", os.path.join(d, "t.bam"), "-f", os.path.join(d, "t.fa"), "-q", "0", "-Q", "10", "-np", "-o", os.path.join(d, "ours.txt")],
+                           check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            ts.append(time.perf_counter() - t0)
+        ours = {"first_s": ts[0], "second_s": ts[1],
+                "identical_table": open(os.path.join(d, "ours.txt"), "rb").read() == open(os.path.join(d, "out.txt"), "rb").read()}
+    return dt, ncalls, ours
 
 
 def ref_bam_port_worker(args):
     """fallback when oracle/_ref is absent: the oracle restatement of the same path on the read SoA"""
-    seed, L, _ = args
+    seed, L = args[:2]
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from bind import Lib, oracle_bam_path
     fa, reads, _ = make_bam_inputs(seed, L)
@@ -159,7 +172,7 @@ def ref_bam_port_worker(args):
     return time.perf_counter() - t0, len(res["calls"])
 
 
-def time_reference_bam(sample_len: int, procs: int, seed0: int):
+def time_reference_bam(sample_len: int, procs: int, seed0: int, with_ours: bool = False):
     import multiprocessing as mp
     import tempfile
     ctx = mp.get_context("spawn")
@@ -167,7 +180,7 @@ def time_reference_bam(sample_len: int, procs: int, seed0: int):
     if not have_ref:
         ref_kind()
     with tempfile.TemporaryDirectory() as td, ctx.Pool(procs) as pool:
-        out = pool.map(ref_bam_worker if have_ref else ref_bam_port_worker, [(seed0 + i, sample_len, td) for i in range(procs)])
+        out = pool.map(ref_bam_worker if have_ref else ref_bam_port_worker, [(seed0 + i, sample_len, td, with_ours) for i in range(procs)])
     return max(o[0] for o in out), out, ("reference" if have_ref else "port")
 
 
@@ -396,7 +409,12 @@ def main():
         if world == 1:
             sample = min(a.cpu_sample, L)
             if bam:
-                cpu, out, kind = time_reference_bam(sample, 1, 19)
+                cpu, out, kind = time_reference_bam(sample, 1, 19, with_ours=True)
+                if len(out[0]) > 2 and out[0][2]:
+                    o = out[0][2]
+                    line["cli_e2e"] = {"sample_bp": sample, "reference_cli_s": cpu, "this_cli_first_s": o["first_s"], "this_cli_second_s": o["second_s"],
+                                       "identical_table": o["identical_table"], "speedup_second": cpu / o["second_s"],
+                                       "what": "BAM + FASTA files -> CNV table through each CLI (process start, CUDA context creation, BGZF/BAM decode on the host included)"}
                 line["cpu_baseline"] = {"value": sample / cpu / 1e9, "unit": "Gbases/s", "cores": 1, "kind": kind,
                                         "sample": f"one {sample} bp 30x synthetic BAM through the unmodified `rsicnv rsi -b ... -q 0 -Q 10 -np` CLI on one host core "
                                                   f"(the reference is single-threaded; BGZF/BAM decode included, BAM in page cache)"}

@@ -126,6 +126,34 @@ int rsigpu_pileup_push(rsigpu_ctx* c, const rsigpu_read_batch* b);
 int rsigpu_pileup_end(rsigpu_ctx* c);      /* runs the pileup kernels now: the raw depth becomes readable (-s) */
 int rsigpu_pileup_commit(rsigpu_ctx* c);   /* only marks the staged batches complete; rsigpu_run runs the pileup as its first stage */
 
+/* BAM input straight from the file's bytes: BGZF inflate (samtools-0.1.18/bgzf.c:277-313 inflate_block,
+ * 258-275 check_header) and bam_read1 (bam.c:179-210, core layout bam.h:131-155) on the GPU.  The caller
+ * parses the BAM header itself (it needs the contig names anyway, bam.c:69-110) and then feeds the file from
+ * the BGZF block that holds the first alignment record:
+ *   begin(n_ref)                    n_ref = number of reference sequences in the header (record sanity bound)
+ *   feed(bytes, n, skip, ...)       `bytes` must START at a BGZF block boundary; only whole blocks are taken and
+ *                                   *consumed says how many bytes they covered (present the rest again, followed by
+ *                                   more of the file).  `skip` = decoded bytes in front of the first record (first
+ *                                   feed only).  Records are decoded into device arrays owned by the decoder and
+ *                                   reported as runs of consecutive records with the same refID, in file order; a
+ *                                   record cut by the end of the chunk is carried into the next feed.
+ *   take(c, run, dst)               appends the run's records to dst's staged reads, exactly as rsigpu_pileup_push
+ *                                   of the same records would (dst: set_reference + pileup_begin done; dst may be c
+ *                                   itself or a context on another GPU).  Runs are valid until the next feed.
+ *   end()                           fails if the file stopped inside a record.
+ * HOST pointers (pinned memory from rsigpu_pinned_alloc makes the copy asynchronous and full speed). */
+typedef struct rsigpu_bam_run { int32_t tid; int32_t reserved_; int64_t n_reads; } rsigpu_bam_run;
+int rsigpu_bam_begin(rsigpu_ctx* c, int32_t n_ref);
+int rsigpu_bam_feed(rsigpu_ctx* c, const uint8_t* bgzf, int64_t nbytes, int64_t skip, int64_t* consumed, rsigpu_bam_run* runs, int32_t cap,
+                    int32_t* n_runs);
+int rsigpu_bam_take(rsigpu_ctx* c, int32_t run, rsigpu_ctx* dst);
+int rsigpu_bam_end(rsigpu_ctx* c);
+/* one decoded field of a run copied to the host (parity tests): 0 pos, 1 mpos, 2 isize, 3 mtid (int32), 4 flag (uint16),
+ * 5 mapq (uint8), 6 cigar_off (uint32, n+1, rebased to 0), 7 cigar (uint32), 8 qual_off (uint64, n+1, rebased), 9 qual (uint8) */
+int rsigpu_bam_run_field(rsigpu_ctx* c, int32_t run, int32_t field, void* out, int64_t cap_bytes, int64_t* nbytes);
+int rsigpu_pinned_alloc(size_t nbytes, void** out);
+void rsigpu_pinned_free(void* p);
+
 /* The seams, in the order main() calls them (rsi.cpp:2197-2211).  All asynchronous on the
  * context's stream except where a result is copied to the host. */
 int rsigpu_load_finish(rsigpu_ctx* c);   /* checkgccontent + apply_cap + concatenate_data + RDmedian/RDsd: gccontent.cpp:95, loaddata.cpp:229, 48, rsi.cpp:2202 */

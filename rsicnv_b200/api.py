@@ -71,7 +71,8 @@ EXPORTS = ("rsigpu_default_params", "rsigpu_create", "rsigpu_destroy", "rsigpu_l
            "rsigpu_set_depth", "rsigpu_pileup_begin", "rsigpu_pileup_push", "rsigpu_pileup_end", "rsigpu_load_finish", "rsigpu_detectcnv",
            "rsigpu_sd_filters", "rsigpu_cnv_stat", "rsigpu_get_calls", "rsigpu_run", "rsigpu_get_chr_stats", "rsigpu_get_array",
            "rsigpu_format_row", "rsigpu_launch_count", "rsigpu_last_stage_ms", "rsigpu_set_profile", "rsigpu_get_profile",
-           "rsigpu_set_level0_mode", "rsigpu_debug_state", "rsigpu_pileup_commit")
+           "rsigpu_set_level0_mode", "rsigpu_debug_state", "rsigpu_pileup_commit", "rsigpu_bam_begin", "rsigpu_bam_feed", "rsigpu_bam_take",
+           "rsigpu_bam_end", "rsigpu_bam_run_field", "rsigpu_pinned_alloc", "rsigpu_pinned_free")
 
 _libs: dict[str, C.CDLL] = {}
 
@@ -86,6 +87,9 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.rsigpu_last_error.restype = C.c_char_p
     lib.rsigpu_launch_count.restype = C.c_int64
     lib.rsigpu_destroy.restype = None
+    lib.rsigpu_pinned_free.restype = None
+    lib.rsigpu_pinned_free.argtypes = [C.c_void_p]
+    lib.rsigpu_pinned_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
     for name in EXPORTS:
         getattr(lib, name)  # raises AttributeError if the ABI is incomplete
     _libs[path] = lib
@@ -94,6 +98,60 @@ def load_library(path: str | None = None) -> C.CDLL:
 
 def _ptr(a):
     return C.c_void_p(a.ctypes.data)
+
+
+class BamRun(C.Structure):
+    _fields_ = [("tid", C.c_int32), ("reserved_", C.c_int32), ("n_reads", C.c_int64)]
+
+
+def parse_bam_header(data) -> dict:
+    """BAM header from the first BGZF blocks of a file (bam_header_read, samtools-0.1.18/bam.c:69-110), inflated on the
+    host with zlib -- a few KiB.  Returns names, lengths and where the alignment records start: `coff` = file offset of the
+    BGZF block that holds the first record, `skip` = decoded bytes of that block in front of it."""
+    import struct
+    import zlib
+    mv = memoryview(data)
+    dec = b""; starts = []          # (file offset of block, decoded offset of its first byte)
+    off = 0
+
+    def more():
+        nonlocal off, dec
+        if off + 18 > len(mv):
+            raise ValueError("truncated BAM header")
+        h = bytes(mv[off:off + 18])
+        if h[:4] != b"\x1f\x8b\x08\x04":
+            raise ValueError("not a BGZF file")
+        bsize = struct.unpack_from("<H", h, 16)[0] + 1
+        xlen = struct.unpack_from("<H", h, 10)[0]
+        starts.append((off, len(dec)))
+        dec += zlib.decompress(bytes(mv[off + 12 + xlen:off + bsize - 8]), -15)
+        off += bsize
+
+    def need(n):
+        while len(dec) < n:
+            more()
+    need(12)
+    if dec[:4] != b"BAM\x01":
+        raise ValueError("not a BAM file")
+    l_text = struct.unpack_from("<i", dec, 4)[0]
+    need(12 + l_text)
+    n_ref = struct.unpack_from("<i", dec, 8 + l_text)[0]
+    p = 12 + l_text
+    names, lens = [], []
+    for _ in range(n_ref):
+        need(p + 4)
+        ln = struct.unpack_from("<i", dec, p)[0]
+        need(p + 8 + ln)
+        names.append(dec[p + 4:p + 4 + ln - 1].decode()); lens.append(struct.unpack_from("<i", dec, p + 4 + ln)[0])
+        p += 8 + ln
+    # the block that holds decoded offset p (the first record); if the header ends exactly at a block end, the next block
+    coff, skip = off, 0
+    for fo, do in starts:
+        if do <= p:
+            coff, skip = fo, p - do
+    if skip == len(dec) - [do for fo, do in starts if fo == coff][0] and coff != off:
+        coff, skip = off, 0
+    return {"names": names, "lens": lens, "coff": coff, "skip": skip}
 
 
 class Context:
@@ -171,6 +229,47 @@ class Context:
             setattr(b, name, keep[name].ctypes.data)
         b.n_reads = len(keep["pos"]); b.tid = tid
         self._ck(self.lib.rsigpu_pileup_push(self.h, C.byref(b)))
+
+    # ---- BAM bytes decoded on the GPU (k_bam.cuh): begin / feed / take / end
+    def bam_begin(self, n_ref: int):
+        self._ck(self.lib.rsigpu_bam_begin(self.h, C.c_int32(n_ref)))
+
+    def bam_feed(self, data, nbytes: int | None = None, skip: int = 0):
+        """data: uint8 numpy array (or an integer host address with nbytes) that starts at a BGZF block boundary.
+        Returns (bytes consumed, [(tid, n_reads), ...]) -- the runs stay valid until the next feed."""
+        if isinstance(data, int):
+            ptr, n = C.c_void_p(data), int(nbytes)
+        else:
+            data = np.ascontiguousarray(data, dtype=np.uint8)
+            self._keep = [data]
+            ptr, n = _ptr(data), (len(data) if nbytes is None else int(nbytes))
+        runs = (BamRun * 4096)()
+        consumed = C.c_int64(0); nr = C.c_int32(0)
+        self._ck(self.lib.rsigpu_bam_feed(self.h, ptr, C.c_int64(n), C.c_int64(skip), C.byref(consumed), runs, C.c_int32(4096), C.byref(nr)))
+        return int(consumed.value), [(runs[i].tid, int(runs[i].n_reads)) for i in range(min(nr.value, 4096))]
+
+    def bam_take(self, run: int, dst: "Context"):
+        rc = self.lib.rsigpu_bam_take(self.h, C.c_int32(run), dst.h)
+        if rc != 0:
+            raise RsiGpuError(rc, (self.lib.rsigpu_last_error(dst.h) or self.lib.rsigpu_last_error(self.h) or b"").decode())
+
+    def bam_end(self):
+        self._ck(self.lib.rsigpu_bam_end(self.h))
+
+    _BAM_FIELDS = (("pos", np.int32), ("mpos", np.int32), ("isize", np.int32), ("mtid", np.int32), ("flag", np.uint16), ("mapq", np.uint8),
+                   ("cigar_off", np.uint32), ("cigar", np.uint32), ("qual_off", np.uint64), ("qual", np.uint8))
+
+    def bam_run_reads(self, run: int) -> dict:
+        """the decoded records of one run as the read dict pileup_push takes (parity tests)"""
+        out = {}
+        for f, (name, dt) in enumerate(self._BAM_FIELDS):
+            nb = C.c_int64(0)
+            self._ck(self.lib.rsigpu_bam_run_field(self.h, C.c_int32(run), C.c_int32(f), None, C.c_int64(0), C.byref(nb)))
+            a = np.empty(nb.value // np.dtype(dt).itemsize, dt)
+            if nb.value:
+                self._ck(self.lib.rsigpu_bam_run_field(self.h, C.c_int32(run), C.c_int32(f), _ptr(a), C.c_int64(nb.value), C.byref(nb)))
+            out[name] = a
+        return out
 
     def pileup_end(self):
         """runs the pileup kernels now (so that the raw depth can be read back); `run()` re-runs them as its first stage"""
@@ -255,7 +354,7 @@ class Context:
                     "rdsd", "rdmad", "max_binsum", "gstar", "gc_tab80", "gc_tab90", "gc_tab100", "gc_cnt90", "tmedian", "tsigma", "tlamda", "Lmax",
                     "lbreak_del", "lbreak_dup", "n_runs", "n_nonzero", "st_lo", "st_hi", "lvl0_sum", "filt_on", "cand_redone",
                     "cp_tests", "cp_left", "cp_reverse", "cp_right", "cp_prefix", "cp_runmean", "cp_hist_ref", "cp_hist_cnv", "cp_sums", "cp_edge_refine",
-                    "cp_merge", "cp_final", "cp_blocks", "cp_sort", "cp_cnvlen_total", "cp_nref_total")
+                    "cp_merge", "cp_final", "cp_blocks", "cp_sort", "cp_cnvlen_total", "cp_nref_total", "bam_rewalked")
 
     def debug_state(self) -> dict:
         a = (C.c_double * 64)()

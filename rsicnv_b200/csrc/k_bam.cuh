@@ -1,0 +1,405 @@
+// k_bam.cuh -- BGZF inflate and BAM record decoding on the GPU: compressed file bytes in, the
+// position-sorted structure-of-arrays the pileup kernels read out (k_pileup.cuh: ReadSoA).
+//
+// Replaces, for the `rsicnv rsi -b` path (reference file:line relative to src/):
+//   BGZF block inflate       samtools-0.1.18/bgzf.c:277-313 (inflate_block: raw deflate, -15 window, no CRC check)
+//   block header             samtools-0.1.18/bgzf.c:56-70, 258-275 (check_header: gzip magic, FEXTRA, 'B','C' subfield)
+//   bam_read1 / bam1_core_t  samtools-0.1.18/bam.c:179-210, bam.h:131-155 (32-byte core, name, CIGAR, 4-bit seq, qual)
+//   the per-record fields load_data_from_bam and cnv_stat read  loaddata.cpp:312-335, pairrd.cpp:622-748
+//
+// Design.  A BGZF block (<= 64 KiB decoded) is an independent raw-deflate stream, and a chr19-sized BAM
+// holds ~60 k of them: one THREAD inflates one block, with its Huffman tables in shared memory (lane-
+// interleaved so that the 32 lanes of a warp never share a bank word for the same table index).  BAM
+// records are a linked list (each starts with its own length) and may straddle BGZF blocks, so their
+// starts are found speculatively and then proven: every block guesses its first record start with a
+// plausibility test and walks the list to the end of the block (k_bam_chain); one CTA checks that each
+// guess equals the position the previous block's walk ended at, starting from the known first record --
+// by induction every start is then exact -- and re-walks the rare block whose guess was wrong
+// (k_bam_verify).  Records are then scattered field by field into arrays (k_bam_fields, k_bam_payload).
+#pragma once
+#include "k_pileup.cuh"
+
+namespace rsigpu {
+
+enum {
+  INF_NT = 32,                     // threads per CTA: one warp, one BGZF block per thread
+  INF_FB = 9, INF_DB = 6,          // bits of the direct-lookup tables (literal/length, distance)
+  INF_LF = 0,                      // per-thread table layout, in u16 slots
+  INF_LS = INF_LF + (1 << INF_FB), // literal/length symbols ordered by code
+  INF_DF = INF_LS + 288,
+  INF_DS = INF_DF + (1 << INF_DB),
+  INF_LC = INF_DS + 32,            // code-length counts
+  INF_DC = INF_LC + 16,
+  INF_SLOTS = INF_DC + 16
+};
+#define RSI_SMEM_INFLATE ((size_t)INF_SLOTS * INF_NT * 2)
+
+enum { BAM_HEAD = 16 << 20 };      // room in front of the decoded blocks for the partial record carried from the previous chunk
+enum { BAM_NONE = -1, BAM_TAIL = 0x7fffffff };
+enum { BAM_ERR_INFLATE = 1, BAM_ERR_RECORD = 2, BAM_ERR_RUNS = 4 };
+
+struct BgzfBlock { u32 src, src_len, dst, dst_len; };   // payload offset/length in the compressed chunk, offset/length in the decoded buffer
+
+struct BitIn {
+  const u8* base; u32 pos, end;   // word-aligned base, next byte to load, one past the payload (both relative to base)
+  u64 buf; int cnt;
+};
+// byte loads until the next load is word aligned (at most 3)
+__device__ __forceinline__ void bits_align(BitIn& b) {
+  while ((b.pos & 3u) && b.cnt <= 56) { b.buf |= (u64)(b.pos < b.end + 8 ? b.base[b.pos] : 0) << b.cnt; b.cnt += 8; b.pos++; }
+}
+// at least 33 valid bits afterwards; the payload is followed by the block's 8-byte footer, so the last word load stays inside the chunk
+__device__ __forceinline__ void bits_refill(BitIn& b) {
+  if (b.cnt <= 32) {
+    const u32 w = b.pos < b.end + 8 ? *reinterpret_cast<const u32*>(b.base + b.pos) : 0u;
+    b.buf |= (u64)w << b.cnt; b.cnt += 32; b.pos += 4;
+  }
+}
+__device__ __forceinline__ u32 bits_take(BitIn& b, int n) { const u32 v = (u32)(b.buf & ((1ull << n) - 1)); b.buf >>= n; b.cnt -= n; return v; }
+
+// per-thread Huffman tables in shared memory, slot i of lane l at sm[i * 32 + l]
+#define INF_T(i) sm[(i) * INF_NT + lane]
+
+// canonical code from code lengths (count/symbol form, plus a direct table for codes of <= fb bits whose
+// entries are symbol << 4 | length).  Returns < 0 for an over-subscribed set, > 0 for an incomplete one.
+__device__ int inf_construct(u16* sm, int lane, const u8* lens, int n, int fast, int fb, int cnts, int syms) {
+  for (int l = 0; l < 16; ++l) INF_T(cnts + l) = 0;
+  for (int s = 0; s < n; ++s) INF_T(cnts + lens[s]) += 1;
+  for (int i = 0; i < (1 << fb); ++i) INF_T(fast + i) = 0;
+  if (INF_T(cnts) == n) return 0;
+  int left = 1;
+  for (int l = 1; l <= 15; ++l) { left <<= 1; left -= (int)INF_T(cnts + l); if (left < 0) return left; }
+  u16 offs[16];
+  offs[1] = 0;
+  for (int l = 1; l < 15; ++l) offs[l + 1] = (u16)(offs[l] + INF_T(cnts + l));
+  for (int s = 0; s < n; ++s) if (lens[s]) { INF_T(syms + offs[lens[s]]) = (u16)s; offs[lens[s]]++; }
+  int code = 0, index = 0;
+  for (int l = 1; l <= fb; ++l) {
+    const int cn = (int)INF_T(cnts + l);
+    for (int j = 0; j < cn; ++j) {
+      const u32 rev = __brev((u32)(code + j)) >> (32 - l);
+      const u16 e = (u16)((INF_T(syms + index + j) << 4) | l);
+      for (u32 k = rev; k < (1u << fb); k += (1u << l)) INF_T(fast + k) = e;
+    }
+    index += cn; code = (code + cn) << 1;
+  }
+  return left;
+}
+__device__ __forceinline__ int inf_decode(BitIn& b, const u16* sm, int lane, int fast, int fb, int cnts, int syms) {
+  const u32 e = INF_T(fast + (u32)(b.buf & ((1u << fb) - 1)));
+  if (e) { const int l = (int)(e & 15u); b.buf >>= l; b.cnt -= l; return (int)(e >> 4); }
+  int code = 0, first = 0, index = 0; u64 bits = b.buf;
+  for (int l = 1; l <= 15; ++l) {
+    code |= (int)(bits & 1); bits >>= 1;
+    const int cn = (int)INF_T(cnts + l);
+    if (code - cn < first) { b.buf >>= l; b.cnt -= l; return (int)INF_T(syms + index + (code - first)); }
+    index += cn; first += cn; first <<= 1; code <<= 1;
+  }
+  return -1;
+}
+
+// One raw-deflate stream -> dst[0, dst_len).  Returns 0 when the stream ends exactly at dst_len bytes.
+__device__ int inflate_one(const u8* src, u32 src_len, u8* dst, u32 dst_len, u16* sm, int lane, const u16* tab) {
+  const u16* LBASE = tab; const u16* LEXT = tab + 29; const u16* DBASE = tab + 58; const u16* DEXT = tab + 88;
+  const u32 mis = (u32)((size_t)src & 3u);
+  BitIn b; b.base = src - mis; b.pos = mis; b.end = src_len + mis; b.buf = 0; b.cnt = 0;
+  bits_align(b);
+  u32 o = 0;
+  u8 lens[320];
+  for (;;) {
+    bits_refill(b);
+    const u32 last = bits_take(b, 1), type = bits_take(b, 2);
+    if (type == 0) {   // stored
+      bits_take(b, b.cnt & 7);
+      bits_refill(b);
+      const u32 len = bits_take(b, 16); bits_refill(b); const u32 nlen = bits_take(b, 16);
+      if ((len ^ 0xffffu) != nlen) return 2;
+      if (o + len > dst_len) return 3;
+      // bytes still in the bit buffer, then straight from memory
+      u32 k = 0;
+      while (k < len && b.cnt >= 8) { dst[o + k++] = (u8)bits_take(b, 8); }
+      for (; k < len; ++k) { if (b.pos >= b.end) return 4; dst[o + k] = b.base[b.pos++]; }
+      b.buf = 0; b.cnt = 0;
+      bits_align(b);
+      o += len;
+    } else if (type == 1 || type == 2) {
+      if (type == 1) {
+        for (int s = 0; s < 144; ++s) lens[s] = 8;
+        for (int s = 144; s < 256; ++s) lens[s] = 9;
+        for (int s = 256; s < 280; ++s) lens[s] = 7;
+        for (int s = 280; s < 288; ++s) lens[s] = 8;
+        inf_construct(sm, lane, lens, 288, INF_LF, INF_FB, INF_LC, INF_LS);
+        for (int s = 0; s < 30; ++s) lens[s] = 5;
+        inf_construct(sm, lane, lens, 30, INF_DF, INF_DB, INF_DC, INF_DS);
+      } else {
+        bits_refill(b);
+        const int nlen = (int)bits_take(b, 5) + 257, ndist = (int)bits_take(b, 5) + 1, ncode = (int)bits_take(b, 4) + 4;
+        if (nlen > 286 || ndist > 30) return 5;
+        const u8 order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+        for (int i = 0; i < 19; ++i) lens[i] = 0;
+        for (int i = 0; i < ncode; ++i) { bits_refill(b); lens[order[i]] = (u8)bits_take(b, 3); }
+        if (inf_construct(sm, lane, lens, 19, INF_LF, 7, INF_LC, INF_LS) != 0) return 6;   // the code-length code must be complete
+        int idx = 0;
+        while (idx < nlen + ndist) {
+          bits_refill(b);
+          const int sym = inf_decode(b, sm, lane, INF_LF, 7, INF_LC, INF_LS);
+          if (sym < 0) return 7;
+          if (sym < 16) lens[idx++] = (u8)sym;
+          else {
+            int rep; u8 v = 0;
+            if (sym == 16) { if (idx == 0) return 8; v = lens[idx - 1]; rep = 3 + (int)bits_take(b, 2); }
+            else if (sym == 17) rep = 3 + (int)bits_take(b, 3);
+            else rep = 11 + (int)bits_take(b, 7);
+            if (idx + rep > nlen + ndist) return 9;
+            while (rep--) lens[idx++] = v;
+          }
+        }
+        if (lens[256] == 0) return 10;
+        int r = inf_construct(sm, lane, lens, nlen, INF_LF, INF_FB, INF_LC, INF_LS);
+        if (r < 0 || (r > 0 && nlen - (int)INF_T(INF_LC) != 1)) return 11;       // incomplete only allowed for a single code
+        r = inf_construct(sm, lane, lens + nlen, ndist, INF_DF, INF_DB, INF_DC, INF_DS);
+        if (r < 0 || (r > 0 && ndist - (int)INF_T(INF_DC) != 1)) return 12;
+      }
+      for (;;) {
+        bits_refill(b);
+        int sym = inf_decode(b, sm, lane, INF_LF, INF_FB, INF_LC, INF_LS);
+        if (sym < 0) return 13;
+        if (sym < 256) { if (o >= dst_len) return 3; dst[o++] = (u8)sym; continue; }
+        if (sym == 256) break;
+        sym -= 257;
+        if (sym >= 29) return 14;
+        const u32 len = (u32)LBASE[sym] + bits_take(b, (int)LEXT[sym]);
+        bits_refill(b);
+        const int ds = inf_decode(b, sm, lane, INF_DF, INF_DB, INF_DC, INF_DS);
+        if (ds < 0 || ds >= 30) return 15;
+        const u32 dist = (u32)DBASE[ds] + bits_take(b, (int)DEXT[ds]);
+        if (dist > o) return 16;
+        if (o + len > dst_len) return 3;
+        const u8* from = dst + o - dist; u8* to = dst + o;
+        for (u32 k = 0; k < len; ++k) to[k] = from[k];
+        o += len;
+      }
+    } else return 1;
+    if (last) break;
+    if (b.pos > b.end + 16) return 17;
+  }
+  return o == dst_len ? 0 : 18;
+}
+
+// inflate: one thread per BGZF block of the chunk
+__global__ void __launch_bounds__(INF_NT) k_bgzf_inflate(const u8* __restrict__ comp, const BgzfBlock* __restrict__ blk, int nblk, u8* __restrict__ U, int* __restrict__ err) {
+  RSI_DYN_SMEM(smem);
+  u16* sm = reinterpret_cast<u16*>(smem);
+  __shared__ u16 tab[120];
+  {
+    const u16 lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+    const u16 lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+    const u16 dbase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+    const u16 dext[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+    for (int i = (int)threadIdx.x; i < 29; i += INF_NT) { tab[i] = lbase[i]; tab[29 + i] = lext[i]; }
+    for (int i = (int)threadIdx.x; i < 30; i += INF_NT) { tab[58 + i] = dbase[i]; tab[88 + i] = dext[i]; }
+  }
+  __syncthreads();
+  const int lane = (int)threadIdx.x;
+  const int k = (int)blockIdx.x * INF_NT + lane;
+  if (k >= nblk) return;
+  const BgzfBlock B = blk[k];
+  if (B.dst_len == 0) return;
+  const int rc = inflate_one(comp + B.src, B.src_len, U + B.dst, B.dst_len, sm, lane, tab);
+  if (rc) { atomicOr(err, (int)BAM_ERR_INFLATE); atomicMax(err + 1, rc); }
+}
+
+// ---------------------------------------------------------------------------------------------
+// records
+__device__ __forceinline__ u32 ld32u(const u8* p) { return (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16) | ((u32)p[3] << 24); }
+
+struct BamChunk {
+  const u8* U;          // decoded stream of this chunk; valid bytes [u_begin, u_end)
+  int u_begin, u_end;   // u_begin = start of the first record (a carried partial record lies in front of BAM_HEAD)
+  const int* bound;     // nblk + 1 boundaries of the decoded BGZF blocks in U (bound[0] may be > u_begin)
+  int nblk, n_ref;
+};
+struct BamChain {       // per BGZF block
+  int* first;           // first record start inside the block (BAM_NONE: none)
+  int* endp;            // where the walk from `first` stops: first record start at or after the block's end, BAM_TAIL if the walk met the chunk's incomplete last record
+  int* tailp;           // start of that incomplete record (valid when endp == BAM_TAIL)
+  int* cnt; int* ncig; i64* nq;   // records started in the block, their CIGAR ops and quality bytes
+};
+
+// bam1_core_t sanity (bam.h:131-155): used to GUESS a record start, and as the corruption check of the walk
+__device__ bool bam_core_ok(const BamChunk& C, int p, int* next) {
+  if ((i64)p + 36 > (i64)C.u_end) return false;
+  const u8* r = C.U + p;
+  const u32 bs = ld32u(r);
+  if (bs < 32u || bs > (1u << 28)) return false;
+  const int tid = (int)ld32u(r + 4), pos = (int)ld32u(r + 8);
+  if (tid < -1 || tid >= C.n_ref || pos < -1) return false;
+  const u32 l_name = r[12], n_cig = (u32)r[16] | ((u32)r[17] << 8);
+  const int l_seq = (int)ld32u(r + 20);
+  const int mtid = (int)ld32u(r + 24), mpos = (int)ld32u(r + 28);
+  if (l_name < 1u || l_seq < 0 || mtid < -1 || mtid >= C.n_ref || mpos < -1) return false;
+  const u64 need = 32ull + l_name + 4ull * n_cig + ((u64)l_seq + 1) / 2 + (u64)l_seq;
+  if (need > (u64)bs) return false;
+  if ((i64)p + 36 + (i64)l_name <= (i64)C.u_end && r[36 + l_name - 1] != 0) return false;
+  *next = p + 4 + (int)bs;
+  return true;
+}
+
+// walk the record list from p while records START before `stop`
+__device__ void bam_walk(const BamChunk& C, int p, int stop, int k, const BamChain& H, int* err) {
+  int cnt = 0, ncig = 0; i64 nq = 0; int endp = 0, tailp = 0;
+  for (;;) {
+    if (p >= stop) { endp = p; break; }
+    if ((i64)p + 4 > (i64)C.u_end) { endp = BAM_TAIL; tailp = p; break; }
+    const u32 bs = ld32u(C.U + p);
+    if ((i64)p + 4 + (i64)bs > (i64)C.u_end) { endp = BAM_TAIL; tailp = p; break; }
+    int nx;
+    if (!bam_core_ok(C, p, &nx)) { if (err) atomicOr(err, (int)BAM_ERR_RECORD); endp = BAM_TAIL; tailp = p; break; }
+    ++cnt; ncig += (int)((u32)C.U[p + 16] | ((u32)C.U[p + 17] << 8)); nq += (i64)(int)ld32u(C.U + p + 20);
+    p = nx;
+  }
+  H.endp[k] = endp; H.tailp[k] = tailp; H.cnt[k] = cnt; H.ncig[k] = ncig; H.nq[k] = nq;
+}
+
+__global__ void k_bam_chain(BamChunk C, BamChain H) {
+  for (int k = (int)(blockIdx.x * blockDim.x + threadIdx.x); k < C.nblk; k += (int)(gridDim.x * blockDim.x)) {
+    const int ub = C.bound[k], ue = C.bound[k + 1];
+    int g = BAM_NONE;
+    if (k == 0) { if (C.u_begin < ue) g = C.u_begin; }
+    else {
+      for (int p = ub; p < ue; ++p) {
+        int nx, nx2;
+        if (!bam_core_ok(C, p, &nx)) continue;
+        if ((i64)nx + 36 <= (i64)C.u_end && !bam_core_ok(C, nx, &nx2)) continue;
+        g = p; break;
+      }
+    }
+    H.first[k] = g;
+    if (g == BAM_NONE) { H.endp[k] = BAM_NONE; H.tailp[k] = 0; H.cnt[k] = 0; H.ncig[k] = 0; H.nq[k] = 0; }
+    else bam_walk(C, g, ue, k, H, nullptr);     // a walk from a wrong guess may meet garbage: not an error
+  }
+}
+
+// info: [0] n records, [1] n cigar ops, [2..3] n quality bytes (i64), [4] tail start, [5] re-walked blocks, [6] n runs
+__global__ void __launch_bounds__(1024) k_bam_verify(BamChunk C, BamChain H, int* __restrict__ in_pos, int* __restrict__ rbase, int* __restrict__ cbase,
+                                                     i64* __restrict__ qbase, int* __restrict__ info, int* __restrict__ err) {
+  RSI_CTA_SETUP(c);
+  const int n = C.nblk;
+  const int per = (n + c.nthr - 1) / c.nthr;
+  const int k0 = imin(c.tid * per, n), k1 = imin(k0 + per, n);
+  const int lane = c.tid & 31, warp = c.tid >> 5;
+  int fixed = 0;
+  for (;;) {
+    // in_pos[k] = position the list has reached when block k begins (exclusive max-scan of the walk ends)
+    int loc = -1;
+    for (int k = k0; k < k1; ++k) if (H.first[k] != BAM_NONE) loc = imax(loc, H.endp[k]);
+    int v = loc;
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v = imax(v, u); }
+    int* slots = reinterpret_cast<int*>(c.red);
+    c.sync(); if (lane == 31) slots[warp] = v; c.sync();
+    int pre = C.u_begin; for (int w = 0; w < warp; ++w) pre = imax(pre, slots[w]);
+    const int up = __shfl_up_sync(0xffffffffu, v, 1);
+    int run = imax(pre, lane ? up : -1);
+    int bad = 0x7fffffff;
+    for (int k = k0; k < k1; ++k) {
+      in_pos[k] = run;
+      const int ue = C.bound[k + 1], g = H.first[k];
+      const bool ok = (run >= ue) ? (g == BAM_NONE) : (g == run);
+      if (!ok && bad == 0x7fffffff) bad = k;
+      if (g != BAM_NONE) run = imax(run, H.endp[k]);
+    }
+    c.sync();
+    bad = c.reduce(bad, MinOp());
+    if (bad == 0x7fffffff) break;
+    if (c.tid == 0) {      // everything before `bad` is proven: re-walk it from the true position
+      const int cur = in_pos[bad], ue = C.bound[bad + 1];
+      if (cur >= ue) { H.first[bad] = BAM_NONE; H.endp[bad] = BAM_NONE; H.cnt[bad] = 0; H.ncig[bad] = 0; H.nq[bad] = 0; }
+      else { H.first[bad] = cur; bam_walk(C, cur, ue, bad, H, nullptr); }
+    }
+    ++fixed;
+    c.sync();
+  }
+  // all starts proven: corruption inside a proven walk is a real error
+  int tail = -1, maxend = C.u_begin, e = 0;
+  for (int k = k0; k < k1; ++k) if (H.first[k] != BAM_NONE) {
+    if (H.endp[k] == BAM_TAIL) { tail = H.tailp[k]; int nx; if ((i64)tail + 36 <= (i64)C.u_end && !bam_core_ok(C, tail, &nx)) e = 1; }
+    else maxend = imax(maxend, H.endp[k]);
+  }
+  tail = c.reduce(tail, MaxOp()); maxend = c.reduce(maxend, MaxOp()); e = c.reduce(e, MaxOp());
+  // exclusive sums -> where each block's records go
+  int lc = 0, lg = 0; i64 lq = 0;
+  for (int k = k0; k < k1; ++k) { lc += H.cnt[k]; lg += H.ncig[k]; lq += H.nq[k]; }
+  int tc, tg; i64 tq;
+  int bc = c.scan_excl(lc, &tc), bg = c.scan_excl(lg, &tg); i64 bq = c.scan_excl(lq, &tq);
+  for (int k = k0; k < k1; ++k) { rbase[k] = bc; cbase[k] = bg; qbase[k] = bq; bc += H.cnt[k]; bg += H.ncig[k]; bq += H.nq[k]; }
+  if (c.tid == 0) {
+    info[0] = tc; info[1] = tg; *reinterpret_cast<i64*>(info + 2) = tq;
+    info[4] = tail >= 0 ? tail : maxend; info[5] = fixed; info[6] = 0;
+    if (e) atomicOr(err, (int)BAM_ERR_RECORD);
+    if (tail < 0 && maxend != C.u_end && !(n == 0)) atomicOr(err, (int)BAM_ERR_RECORD);
+  }
+}
+
+struct BamSoA {
+  int* rec; int* tid; int* pos; int* mpos; int* isize; int* mtid; u16* flag; u8* mapq;
+  u32* cigar_off; u32* cigar; u64* qual_off; u8* qual;
+};
+
+// fixed-size fields and offsets of every record (one thread walks the records of one BGZF block)
+__global__ void k_bam_fields(BamChunk C, BamChain H, const int* __restrict__ rbase, const int* __restrict__ cbase, const i64* __restrict__ qbase,
+                             const int* __restrict__ info, BamSoA S) {
+  for (int k = (int)(blockIdx.x * blockDim.x + threadIdx.x); k < C.nblk; k += (int)(gridDim.x * blockDim.x)) {
+    int p = H.first[k];
+    if (p == BAM_NONE) continue;
+    const int n = H.cnt[k];
+    int r = rbase[k]; u32 co = (u32)cbase[k]; u64 qo = (u64)qbase[k];
+    for (int i = 0; i < n; ++i, ++r) {
+      const u8* q = C.U + p;
+      const u32 bs = ld32u(q), bmq = ld32u(q + 12), fnc = ld32u(q + 16);
+      S.rec[r] = p; S.tid[r] = (int)ld32u(q + 4); S.pos[r] = (int)ld32u(q + 8);
+      S.mapq[r] = (u8)((bmq >> 8) & 0xffu); S.flag[r] = (u16)(fnc >> 16);
+      S.mtid[r] = (int)ld32u(q + 24); S.mpos[r] = (int)ld32u(q + 28); S.isize[r] = (int)ld32u(q + 32);
+      S.cigar_off[r] = co; S.qual_off[r] = qo;
+      co += fnc & 0xffffu; qo += (u64)ld32u(q + 20);
+      p += 4 + (int)bs;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { S.cigar_off[info[0]] = (u32)info[1]; S.qual_off[info[0]] = (u64)*reinterpret_cast<const i64*>(info + 2); }
+}
+
+// CIGAR words and quality bytes: one warp per record
+__global__ void k_bam_payload(const u8* __restrict__ U, const int* __restrict__ info, BamSoA S) {
+  const int n = info[0];
+  const int lane = (int)(threadIdx.x & 31);
+  const int wid = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), nw = (int)((gridDim.x * blockDim.x) >> 5);
+  for (int r = wid; r < n; r += nw) {
+    const u8* q = U + S.rec[r];
+    const u32 l_name = q[12], n_cig = (u32)q[16] | ((u32)q[17] << 8), l_seq = ld32u(q + 20);
+    const u8* cg = q + 36 + l_name;
+    u32* cd = S.cigar + S.cigar_off[r];
+    for (u32 j = (u32)lane; j < n_cig; j += 32) cd[j] = ld32u(cg + 4 * j);
+    const u8* qs = cg + 4 * n_cig + (l_seq + 1) / 2;
+    u8* qd = S.qual + S.qual_off[r];
+    for (u32 j = (u32)lane; j < l_seq; j += 32) qd[j] = qs[j];
+  }
+}
+
+// runs of equal refID in record order (a coordinate-sorted BAM holds each contig's records contiguously)
+__global__ void k_bam_runs(const int* __restrict__ tid, int* __restrict__ info, int* __restrict__ run_start, int cap, int* __restrict__ err) {
+  const int n = info[0];
+  for (int r = (int)(blockIdx.x * blockDim.x + threadIdx.x); r < n; r += (int)(gridDim.x * blockDim.x)) {
+    if (r == 0 || tid[r] != tid[r - 1]) {
+      const int i = atomicAdd(info + 6, 1);
+      if (i < cap) run_start[i] = r; else atomicOr(err, (int)BAM_ERR_RUNS);
+    }
+  }
+}
+// per run start r: tid, cigar offset, quality offset (for the host's run table)
+__global__ void k_bam_run_info(const int* __restrict__ run_start, int nruns, BamSoA S, i64* __restrict__ out) {
+  for (int i = (int)(blockIdx.x * blockDim.x + threadIdx.x); i < nruns; i += (int)(gridDim.x * blockDim.x)) {
+    const int r = run_start[i];
+    out[3 * i] = S.tid[r]; out[3 * i + 1] = S.cigar_off[r]; out[3 * i + 2] = (i64)S.qual_off[r];
+  }
+}
+
+}  // namespace rsigpu

@@ -15,7 +15,7 @@
 #include <vector>
 
 #include "../../include/rsigpu.h"
-#include "k_pileup.cuh"
+#include "k_bam.cuh"
 
 using namespace rsigpu;
 
@@ -55,7 +55,7 @@ struct DevVec {   // growable device array filled by appends from the host
       if (p) cudaFree(p);
       p = q; cap = ncap;
     }
-    cudaError_t e = cudaMemcpyAsync(p + n, h, cnt * sizeof(T), cudaMemcpyHostToDevice, s);
+    cudaError_t e = cudaMemcpyAsync(p + n, h, cnt * sizeof(T), cudaMemcpyDefault, s);   // host or device source
     n += cnt;
     return e;
   }
@@ -106,6 +106,13 @@ struct rsigpu_ctx {
   // reads
   DevVec<int> r_pos, r_mpos, r_isize, r_mtid; DevVec<u16> r_flag; DevVec<u8> r_mapq, r_qual; DevVec<u32> r_cigar_off, r_cigar; DevVec<u64> r_qual_off;
   DevBuf<int> r_calend, d_tile_range; DevBuf<u32> d_qmask;
+  // BAM decoder (k_bam.cuh): one chunk of BGZF blocks at a time
+  DevBuf<u8> b_comp, b_U, b_mapq, b_qual; DevBuf<BgzfBlock> b_blk; DevBuf<u16> b_flag; DevBuf<u32> b_cigoff, b_cig; DevBuf<u64> b_qoff;
+  DevBuf<int> b_bound, b_first, b_endp, b_tailp, b_cnt, b_ncig, b_in, b_rbase, b_cbase, b_info, b_runstart, b_rec, b_tid, b_pos, b_mpos, b_isize, b_mtid;
+  DevBuf<i64> b_nq, b_qbase, b_runinfo;
+  struct BamRun { int tid; i64 r0, r1, c0, c1, q0, q1; };
+  std::vector<BamRun> b_runs;
+  int b_nref = 0, b_tail_len = 0, b_rewalked = 0; bool b_active = false, b_first_feed = true;
   // accounting
   long long h_cprof[16] = {};
   int64_t launches = 0;
@@ -200,6 +207,7 @@ int set_smem_attrs() {
   cudaFuncSetAttribute(k_cand_edge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_CAND_CL);
   cudaFuncSetAttribute(k_rsi_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SCAN_SMEM);
   cudaFuncSetAttribute(k_rsi_scan_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SCAN_SMEM_T(LMAX_SMALL));
+  cudaFuncSetAttribute(k_bgzf_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_INFLATE);
   return 0;
 }
 
@@ -320,6 +328,10 @@ void rsigpu_destroy(rsigpu_ctx* c) {
   c->d_nrun_beg.release(); c->d_nrun_end.release(); c->d_scan_scratch.release(); c->d_tile_range.release(); c->d_qmask.release(); c->r_calend.release();
   c->r_pos.release(); c->r_mpos.release(); c->r_isize.release(); c->r_mtid.release(); c->r_flag.release(); c->r_mapq.release(); c->r_qual.release();
   c->r_cigar_off.release(); c->r_cigar.release(); c->r_qual_off.release();
+  c->b_comp.release(); c->b_U.release(); c->b_mapq.release(); c->b_qual.release(); c->b_blk.release(); c->b_flag.release(); c->b_cigoff.release(); c->b_cig.release(); c->b_qoff.release();
+  c->b_bound.release(); c->b_first.release(); c->b_endp.release(); c->b_tailp.release(); c->b_cnt.release(); c->b_ncig.release(); c->b_in.release(); c->b_rbase.release(); c->b_cbase.release();
+  c->b_info.release(); c->b_runstart.release(); c->b_rec.release(); c->b_tid.release(); c->b_pos.release(); c->b_mpos.release(); c->b_isize.release(); c->b_mtid.release();
+  c->b_nq.release(); c->b_qbase.release(); c->b_runinfo.release();
   if (c->d_st) cudaFree(c->d_st);
   if (c->h_st) cudaFreeHost(c->h_st);
   if (c->h_lut) cudaFreeHost(c->h_lut);
@@ -400,12 +412,11 @@ int rsigpu_pileup_begin(rsigpu_ctx* c, int32_t target_len) {
   return RSIGPU_OK;
 }
 
-int rsigpu_pileup_push(rsigpu_ctx* c, const rsigpu_read_batch* b) {
-  if (!c || !b || b->n_reads < 0) return RSIGPU_E_ARG;
-  if (b->n_reads == 0) return RSIGPU_OK;
+// append one batch to the staged reads; the batch's pointers may be host or device memory, its offset arrays start
+// at cig_first / q_first (0 for a caller's batch, the run's first offsets for records decoded on the GPU)
+static int push_impl(rsigpu_ctx* c, const rsigpu_read_batch* b, size_t nc, size_t nq, u32 cig_first, u64 q_first) {
   cudaSetDevice(c->device);
   const size_t n = (size_t)b->n_reads;
-  const size_t nc = b->cigar_off[n], nq = (size_t)b->qual_off[n];
   const size_t r0 = c->r_pos.n, c0 = c->r_cigar.n, q0 = c->r_qual.n;
   if (c0 + nc >= 0xffffffffull) { c->fail("more than 2^32 CIGAR ops in one contig"); return RSIGPU_E_RANGE; }
   CK(c->r_pos.append(b->pos, n, c->stream)); CK(c->r_mpos.append(b->mpos, n, c->stream)); CK(c->r_isize.append(b->isize, n, c->stream));
@@ -414,12 +425,185 @@ int rsigpu_pileup_push(rsigpu_ctx* c, const rsigpu_read_batch* b) {
   // offsets: entry r0 of the previous batch (its end) equals this batch's first entry after rebasing
   if (r0) { c->r_cigar_off.n = r0; c->r_qual_off.n = r0; }
   CK(c->r_cigar_off.append(b->cigar_off, n + 1, c->stream)); CK(c->r_qual_off.append(reinterpret_cast<const u64*>(b->qual_off), n + 1, c->stream));
-  if (c0) KL(k_add_u32, grid_for((int)std::min<size_t>(n + 1, 1u << 30), 1024, c->n_sm * 4), 256, 0, c->r_cigar_off.p + r0, n + 1, (u32)c0);
-  if (q0) KL(k_add_u64, grid_for((int)std::min<size_t>(n + 1, 1u << 30), 1024, c->n_sm * 4), 256, 0, c->r_qual_off.p + r0, n + 1, (u64)q0);
+  const u32 addc = (u32)c0 - cig_first; const u64 addq = (u64)q0 - q_first;
+  if (addc) KL(k_add_u32, grid_for((int)std::min<size_t>(n + 1, 1u << 30), 1024, c->n_sm * 4), 256, 0, c->r_cigar_off.p + r0, n + 1, addc);
+  if (addq) KL(k_add_u64, grid_for((int)std::min<size_t>(n + 1, 1u << 30), 1024, c->n_sm * 4), 256, 0, c->r_qual_off.p + r0, n + 1, addq);
   // the caller's buffers may be reused as soon as this returns
   CK(cudaStreamSynchronize(c->stream));
   return RSIGPU_OK;
 }
+
+int rsigpu_pileup_push(rsigpu_ctx* c, const rsigpu_read_batch* b) {
+  if (!c || !b || b->n_reads < 0) return RSIGPU_E_ARG;
+  if (b->n_reads == 0) return RSIGPU_OK;
+  const size_t n = (size_t)b->n_reads;
+  return push_impl(c, b, b->cigar_off[n], (size_t)b->qual_off[n], 0u, 0ull);
+}
+
+// ---------------------------------------------------------------------------------------------
+// BAM bytes -> staged reads on the GPU (k_bam.cuh)
+int rsigpu_bam_begin(rsigpu_ctx* c, int32_t n_ref) {
+  if (!c || n_ref < 1) return RSIGPU_E_ARG;
+  c->b_nref = n_ref; c->b_tail_len = 0; c->b_active = true; c->b_first_feed = true; c->b_runs.clear(); c->b_rewalked = 0;
+  return RSIGPU_OK;
+}
+
+int rsigpu_bam_feed(rsigpu_ctx* c, const uint8_t* bgzf, int64_t nbytes, int64_t skip, int64_t* consumed, rsigpu_bam_run* runs, int32_t cap, int32_t* n_runs) {
+  if (!c || !bgzf || nbytes < 0 || !consumed || !n_runs || skip < 0) return RSIGPU_E_ARG;
+  if (!c->b_active) { c->fail("bam_feed: call rsigpu_bam_begin first"); return RSIGPU_E_ARG; }
+  cudaSetDevice(c->device);
+  *consumed = 0; *n_runs = 0; c->b_runs.clear();
+  // BGZF block headers (bgzf.c:258-275): gzip magic, FEXTRA, the 'B','C' subfield carries the block size
+  const size_t U_MAX = (size_t)768 << 20, C_MAX = (size_t)1 << 31;
+  std::vector<BgzfBlock> blk; std::vector<int> bound;
+  size_t off = 0, utotal = 0;
+  bound.push_back((int)BAM_HEAD);
+  while (off + 18 <= (size_t)nbytes) {
+    const uint8_t* h = bgzf + off;
+    if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) { c->fail("bam_feed: not a BGZF block header"); return RSIGPU_E_ARG; }
+    const size_t xlen = (size_t)h[10] | ((size_t)h[11] << 8);
+    if (off + 12 + xlen > (size_t)nbytes) break;
+    size_t bsize = 0; bool found = false;
+    for (size_t x = 0; x + 4 <= xlen;) {
+      const uint8_t* sf = h + 12 + x; const size_t sl = (size_t)sf[2] | ((size_t)sf[3] << 8);
+      if (sf[0] == 'B' && sf[1] == 'C' && sl == 2 && x + 6 <= xlen) { bsize = ((size_t)sf[4] | ((size_t)sf[5] << 8)) + 1; found = true; break; }
+      x += 4 + sl;
+    }
+    if (!found || bsize < 12 + xlen + 8) { c->fail("bam_feed: gzip member without a BGZF size field"); return RSIGPU_E_ARG; }
+    if (off + bsize > (size_t)nbytes) break;
+    const uint8_t* foot = h + bsize - 8;
+    const size_t ulen = (size_t)foot[4] | ((size_t)foot[5] << 8) | ((size_t)foot[6] << 16) | ((size_t)foot[7] << 24);
+    if (ulen > 65536) { c->fail("bam_feed: BGZF block larger than 64 KiB"); return RSIGPU_E_ARG; }
+    if (utotal + ulen > U_MAX || off + bsize > C_MAX) break;
+    BgzfBlock B; B.src = (u32)(off + 12 + xlen); B.src_len = (u32)(bsize - 12 - xlen - 8); B.dst = (u32)(BAM_HEAD + utotal); B.dst_len = (u32)ulen;
+    blk.push_back(B);
+    utotal += ulen; off += bsize;
+    bound.push_back((int)(BAM_HEAD + utotal));
+  }
+  const int nblk = (int)blk.size();
+  if (nblk == 0) {
+    if ((size_t)nbytes >= ((size_t)1 << 17)) { c->fail("bam_feed: no whole BGZF block in 128 KiB"); return RSIGPU_E_ARG; }
+    return RSIGPU_OK;
+  }
+  if (c->b_first_feed) { if ((size_t)skip > utotal) { c->fail("bam_feed: skip beyond the decoded chunk"); return RSIGPU_E_ARG; } }
+  else if (skip != 0) { c->fail("bam_feed: skip is only meaningful on the first feed"); return RSIGPU_E_ARG; }
+  CK(c->b_comp.ensure(off + 64)); CK(c->b_U.ensure((size_t)BAM_HEAD + U_MAX + 64)); CK(c->b_blk.ensure((size_t)nblk)); CK(c->b_bound.ensure((size_t)nblk + 1));
+  CK(c->b_first.ensure(nblk)); CK(c->b_endp.ensure(nblk)); CK(c->b_tailp.ensure(nblk)); CK(c->b_cnt.ensure(nblk)); CK(c->b_ncig.ensure(nblk)); CK(c->b_nq.ensure(nblk));
+  CK(c->b_in.ensure(nblk)); CK(c->b_rbase.ensure(nblk)); CK(c->b_cbase.ensure(nblk)); CK(c->b_qbase.ensure(nblk)); CK(c->b_info.ensure(16));
+  CK(cudaMemcpyAsync(c->b_comp.p, bgzf, off, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->b_blk.p, blk.data(), (size_t)nblk * sizeof(BgzfBlock), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->b_bound.p, bound.data(), ((size_t)nblk + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemsetAsync(c->b_info.p, 0, 16 * 4, c->stream));
+  int* info = c->b_info.p; int* err = c->b_info.p + 8;
+  KL(k_bgzf_inflate, (nblk + INF_NT - 1) / INF_NT, INF_NT, RSI_SMEM_INFLATE, c->b_comp.p, c->b_blk.p, nblk, c->b_U.p, err);
+  BamChunk C; C.U = c->b_U.p; C.u_begin = c->b_first_feed ? (int)(BAM_HEAD + skip) : (int)BAM_HEAD - c->b_tail_len; C.u_end = (int)(BAM_HEAD + utotal);
+  C.bound = c->b_bound.p; C.nblk = nblk; C.n_ref = c->b_nref;
+  BamChain H; H.first = c->b_first.p; H.endp = c->b_endp.p; H.tailp = c->b_tailp.p; H.cnt = c->b_cnt.p; H.ncig = c->b_ncig.p; H.nq = c->b_nq.p;
+  KL(k_bam_chain, grid_for(nblk, 64, c->n_sm * 16), 64, 0, C, H);
+  KL(k_bam_verify, 1, 1024, 0, C, H, c->b_in.p, c->b_rbase.p, c->b_cbase.p, c->b_qbase.p, info, err);
+  int hi[16];
+  CK(cudaMemcpyAsync(hi, info, 16 * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (hi[8] & BAM_ERR_INFLATE) { c->fail("bam_feed: corrupt deflate stream in a BGZF block (code " + std::to_string(hi[9]) + ")"); return RSIGPU_E_ARG; }
+  if (hi[8] & BAM_ERR_RECORD) { c->fail("bam_feed: corrupt BAM record"); return RSIGPU_E_ARG; }
+  const size_t n = (size_t)hi[0], ncg = (size_t)hi[1]; i64 nq64; memcpy(&nq64, hi + 2, 8);
+  const int tail_start = hi[4];
+  c->b_rewalked += hi[5];
+  c->b_first_feed = false;
+  if (n) {
+    CK(c->b_rec.ensure(n)); CK(c->b_tid.ensure(n)); CK(c->b_pos.ensure(n)); CK(c->b_mpos.ensure(n)); CK(c->b_isize.ensure(n)); CK(c->b_mtid.ensure(n));
+    CK(c->b_flag.ensure(n)); CK(c->b_mapq.ensure(n)); CK(c->b_cigoff.ensure(n + 1)); CK(c->b_qoff.ensure(n + 1)); CK(c->b_cig.ensure(ncg + 1)); CK(c->b_qual.ensure((size_t)nq64 + 16));
+    CK(c->b_runstart.ensure(LIST_CAP)); CK(c->b_runinfo.ensure(3 * (size_t)LIST_CAP));
+    BamSoA S; S.rec = c->b_rec.p; S.tid = c->b_tid.p; S.pos = c->b_pos.p; S.mpos = c->b_mpos.p; S.isize = c->b_isize.p; S.mtid = c->b_mtid.p; S.flag = c->b_flag.p;
+    S.mapq = c->b_mapq.p; S.cigar_off = c->b_cigoff.p; S.cigar = c->b_cig.p; S.qual_off = c->b_qoff.p; S.qual = c->b_qual.p;
+    KL(k_bam_fields, grid_for(nblk, 64, c->n_sm * 16), 64, 0, C, H, c->b_rbase.p, c->b_cbase.p, c->b_qbase.p, info, S);
+    KL(k_bam_payload, c->n_sm * 8, 256, 0, c->b_U.p, info, S);
+    KL(k_bam_runs, grid_for((int)std::min<size_t>(n, 1u << 30), 1024, c->n_sm * 8), 256, 0, c->b_tid.p, info, c->b_runstart.p, (int)LIST_CAP, err);
+    CK(cudaMemcpyAsync(hi, info, 16 * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (hi[8] & BAM_ERR_RUNS) { c->fail("bam_feed: more than 65536 refID runs in one chunk (the BAM is not coordinate-sorted)"); return RSIGPU_E_RANGE; }
+    const int nr = hi[6];
+    std::vector<int> rs((size_t)nr);
+    CK(cudaMemcpyAsync(rs.data(), c->b_runstart.p, (size_t)nr * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    std::sort(rs.begin(), rs.end());
+    CK(cudaMemcpyAsync(c->b_runstart.p, rs.data(), (size_t)nr * 4, cudaMemcpyHostToDevice, c->stream));
+    KL(k_bam_run_info, 1, 256, 0, c->b_runstart.p, nr, S, c->b_runinfo.p);
+    std::vector<i64> ri(3 * (size_t)nr);
+    CK(cudaMemcpyAsync(ri.data(), c->b_runinfo.p, ri.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < nr; ++i) {
+      rsigpu_ctx::BamRun R; R.tid = (int)ri[3 * (size_t)i]; R.r0 = rs[(size_t)i]; R.c0 = ri[3 * (size_t)i + 1]; R.q0 = ri[3 * (size_t)i + 2];
+      R.r1 = i + 1 < nr ? rs[(size_t)i + 1] : (i64)n; R.c1 = i + 1 < nr ? ri[3 * (size_t)i + 4] : (i64)ncg; R.q1 = i + 1 < nr ? ri[3 * (size_t)i + 5] : nq64;
+      c->b_runs.push_back(R);
+    }
+  }
+  // the record cut by the end of this chunk moves in front of the next chunk's first block
+  const int tail_len = (int)(BAM_HEAD + utotal) - tail_start;
+  if (tail_len > 0) {
+    if (tail_start < (int)BAM_HEAD || tail_len > (int)BAM_HEAD) { c->fail("bam_feed: an alignment record longer than the decoder's carry buffer (16 MiB)"); return RSIGPU_E_RANGE; }
+    CK(cudaMemcpyAsync(c->b_U.p + (BAM_HEAD - tail_len), c->b_U.p + tail_start, (size_t)tail_len, cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  c->b_tail_len = tail_len > 0 ? tail_len : 0;
+  *consumed = (int64_t)off;
+  *n_runs = (int32_t)c->b_runs.size();
+  for (int i = 0; i < (int)c->b_runs.size() && i < cap && runs; ++i) { runs[i].tid = c->b_runs[(size_t)i].tid; runs[i].reserved_ = 0; runs[i].n_reads = c->b_runs[(size_t)i].r1 - c->b_runs[(size_t)i].r0; }
+  return RSIGPU_OK;
+}
+
+int rsigpu_bam_take(rsigpu_ctx* c, int32_t run, rsigpu_ctx* dst) {
+  if (!c || !dst || run < 0 || run >= (int)c->b_runs.size()) return RSIGPU_E_ARG;
+  if (!dst->have_ref) { dst->fail("bam_take: call set_reference and pileup_begin on the destination first"); return RSIGPU_E_ARG; }
+  const rsigpu_ctx::BamRun& R = c->b_runs[(size_t)run];
+  rsigpu_read_batch b; memset(&b, 0, sizeof b);
+  b.n_reads = R.r1 - R.r0; b.tid = R.tid;
+  if (b.n_reads == 0) return RSIGPU_OK;
+  b.pos = c->b_pos.p + R.r0; b.mpos = c->b_mpos.p + R.r0; b.isize = c->b_isize.p + R.r0; b.mtid = c->b_mtid.p + R.r0; b.flag = c->b_flag.p + R.r0; b.mapq = c->b_mapq.p + R.r0;
+  b.cigar_off = c->b_cigoff.p + R.r0; b.cigar = c->b_cig.p + R.c0; b.qual_off = reinterpret_cast<const uint64_t*>(c->b_qoff.p + R.r0); b.qual = c->b_qual.p + R.q0;
+  return push_impl(dst, &b, (size_t)(R.c1 - R.c0), (size_t)(R.q1 - R.q0), (u32)R.c0, (u64)R.q0);
+}
+
+int rsigpu_bam_end(rsigpu_ctx* c) {
+  if (!c) return RSIGPU_E_ARG;
+  const bool cut = c->b_active && c->b_tail_len > 0;
+  c->b_active = false; c->b_runs.clear(); c->b_tail_len = 0;
+  if (cut) { c->fail("bam_end: the BAM stream stops inside an alignment record"); return RSIGPU_E_ARG; }
+  return RSIGPU_OK;
+}
+
+int rsigpu_bam_run_field(rsigpu_ctx* c, int32_t run, int32_t field, void* out, int64_t cap_bytes, int64_t* nbytes) {
+  if (!c || !nbytes || run < 0 || run >= (int)c->b_runs.size()) return RSIGPU_E_ARG;
+  cudaSetDevice(c->device);
+  const rsigpu_ctx::BamRun& R = c->b_runs[(size_t)run];
+  const size_t n = (size_t)(R.r1 - R.r0);
+  const void* src = nullptr; size_t bytes = 0;
+  switch (field) {
+    case 0: src = c->b_pos.p + R.r0; bytes = n * 4; break;
+    case 1: src = c->b_mpos.p + R.r0; bytes = n * 4; break;
+    case 2: src = c->b_isize.p + R.r0; bytes = n * 4; break;
+    case 3: src = c->b_mtid.p + R.r0; bytes = n * 4; break;
+    case 4: src = c->b_flag.p + R.r0; bytes = n * 2; break;
+    case 5: src = c->b_mapq.p + R.r0; bytes = n; break;
+    case 6: src = c->b_cigoff.p + R.r0; bytes = (n + 1) * 4; break;
+    case 7: src = c->b_cig.p + R.c0; bytes = (size_t)(R.c1 - R.c0) * 4; break;
+    case 8: src = c->b_qoff.p + R.r0; bytes = (n + 1) * 8; break;
+    case 9: src = c->b_qual.p + R.q0; bytes = (size_t)(R.q1 - R.q0); break;
+    default: return RSIGPU_E_ARG;
+  }
+  *nbytes = (int64_t)bytes;
+  if (!out || cap_bytes < (int64_t)bytes) return RSIGPU_OK;
+  if (bytes) { CK(cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); }
+  if (field == 6) { u32* o = (u32*)out; const u32 b0 = (u32)R.c0; for (size_t i = 0; i <= n; ++i) o[i] -= b0; }
+  if (field == 8) { u64* o = (u64*)out; const u64 b0 = (u64)R.q0; for (size_t i = 0; i <= n; ++i) o[i] -= b0; }
+  return RSIGPU_OK;
+}
+
+int rsigpu_pinned_alloc(size_t nbytes, void** out) {
+  if (!out) return RSIGPU_E_ARG;
+  return cudaMallocHost(out, nbytes ? nbytes : 1) == cudaSuccess ? RSIGPU_OK : RSIGPU_E_CUDA;
+}
+void rsigpu_pinned_free(void* p) { if (p) cudaFreeHost(p); }
 
 // the pileup kernels on the staged reads -> raw depth (a5)
 static int run_pileup(rsigpu_ctx* c) {
@@ -782,7 +966,8 @@ int rsigpu_debug_state(const rsigpu_ctx* c, double* out, int32_t cap) {
   const int n = (int)(sizeof v / sizeof v[0]);
   for (int k = 0; k < n && k < cap; ++k) out[k] = v[k];
   for (int k = 0; k < 16 && n + k < cap; ++k) out[n + k] = (double)c->h_cprof[k];   // candidate-stage phase clocks (profile mode)
-  return n + 16;
+  if (n + 16 < cap) out[n + 16] = (double)c->b_rewalked;                              // BAM decoder: BGZF blocks whose speculative first record was wrong
+  return n + 17;
 }
 
 // test hook: 0 = sequential float chain for filterstatus' level-0 sum, 1 = block-scan form (default)

@@ -298,9 +298,12 @@ def make_reads(L: int, seed: int, fasta: np.ndarray | None = None, coverage: flo
     return reads, events
 
 
-def write_bam(path: str, contigs: list[tuple[str, int]], reads_by_tid: dict[int, dict], level: int = 1) -> None:
+def write_bam(path: str, contigs: list[tuple[str, int]], reads_by_tid: dict[int, dict], level: int = 1, strategy: int = 0,
+              block_size: int = 65280, random_seq: int | None = None) -> None:
     """Minimal BAM (BGZF) writer for the synthetic reads: one record per read, name 'r', sequence all 'A'
-    (the path never looks at bases), qualities as given.  Layout: SURVEY.md Appendix B."""
+    (the path never looks at bases; random_seq=SEED writes random bases instead, which makes the file compress like a
+    real one), qualities as given.  strategy: zlib strategy (zlib.Z_FIXED forces fixed-Huffman blocks), level 0 writes
+    stored blocks; records are NOT aligned to BGZF blocks.  Layout: SURVEY.md Appendix B."""
     import struct
     import zlib
     text = "@HD\tVN:1.0\tSO:coordinate\n" + "".join(f"@SQ\tSN:{n}\tLN:{l}\n" for n, l in contigs)
@@ -348,9 +351,14 @@ def write_bam(path: str, contigs: list[tuple[str, int]], reads_by_tid: dict[int,
         if nr and np.all(lq == lq[0]):
             l0 = int(lq[0]); ns0 = int(nseq[0])
             ii = (soff[:, None] + np.arange(ns0)[None, :]).ravel()
-            buf[ii] = 0x11
+            if random_seq is None:
+                buf[ii] = 0x11
+            else:
+                nib = np.array([1, 2, 4, 8], np.uint8)
+                rs = np.random.default_rng(random_seq + tid)
+                buf[ii] = (nib[rs.integers(0, 4, len(ii))] << 4) | nib[rs.integers(0, 4, len(ii))]
             if l0 % 2:
-                buf[soff + ns0 - 1] = 0x10
+                buf[soff + ns0 - 1] &= 0xf0
             qi = (soff[:, None] + ns0 + np.arange(l0)[None, :]).ravel()
             buf[qi] = R["qual"]
         else:
@@ -361,10 +369,10 @@ def write_bam(path: str, contigs: list[tuple[str, int]], reads_by_tid: dict[int,
         chunks.append(buf.tobytes())
     data = b"".join(chunks)
     with open(path, "wb") as f:
-        BS = 65280
+        BS = block_size
         for a in range(0, len(data), BS):
             blk = data[a:a + BS]
-            co = zlib.compressobj(level, zlib.DEFLATED, -15)
+            co = zlib.compressobj(level, zlib.DEFLATED, -15, 8, strategy)
             comp = co.compress(blk) + co.flush()
             f.write(b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(comp) + 25) + comp +
                     struct.pack("<II", zlib.crc32(blk) & 0xffffffff, len(blk)))

@@ -1,0 +1,192 @@
+"""BGZF inflate + BAM record decoding kernels (k_bam.cuh) in the CPU emulator: the decoded structure-of-arrays must equal
+the reads the file was written from, for every deflate block type, chunking and record/block alignment."""
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+from rsicnv_b200 import api, synth
+
+FIELDS = ("pos", "mpos", "isize", "mtid", "flag", "mapq", "cigar_off", "cigar", "qual_off", "qual")
+
+
+def concat_reads(parts):
+    out = {k: [] for k in FIELDS}
+    co = 0; qo = 0
+    for p in parts:
+        for k in ("pos", "mpos", "isize", "mtid", "flag", "mapq", "cigar", "qual"):
+            out[k].append(p[k])
+        out["cigar_off"].append(p["cigar_off"][:-1].astype(np.uint64) + co); out["qual_off"].append(p["qual_off"][:-1].astype(np.uint64) + qo)
+        co += int(p["cigar_off"][-1]); qo += int(p["qual_off"][-1])
+    res = {k: (np.concatenate(v) if v else np.zeros(0)) for k, v in out.items()}
+    res["cigar_off"] = np.concatenate((res["cigar_off"], [co])).astype(np.uint32)
+    res["qual_off"] = np.concatenate((res["qual_off"], [qo])).astype(np.uint64)
+    return res
+
+
+def decode_file(lib, path, chunk=None):
+    """feed the file in `chunk`-byte pieces (None: all at once); returns {tid: read dict}, decoder statistics"""
+    data = np.fromfile(path, np.uint8)
+    h = api.parse_bam_header(data)
+    ctx = api.Context(lib=lib)
+    ctx.bam_begin(len(h["names"]))
+    parts = {}
+    off = h["coff"]; skip = h["skip"]; pending = np.zeros(0, np.uint8)
+    step = chunk or len(data)
+    first = True
+    while off < len(data) or len(pending):
+        piece = data[off:off + step]; off += len(piece)
+        buf = np.concatenate((pending, piece))
+        consumed, runs = ctx.bam_feed(buf, skip=skip if first else 0)
+        if consumed:
+            first = False
+        for i, (tid, n) in enumerate(runs):
+            r = ctx.bam_run_reads(i)
+            assert len(r["pos"]) == n
+            parts.setdefault(tid, []).append(r)
+        pending = buf[consumed:]
+        if off >= len(data) and consumed == 0:
+            break
+    assert len(pending) == 0
+    ctx.bam_end()
+    ctx.close()
+    return {tid: concat_reads(p) for tid, p in parts.items()}, h
+
+
+def assert_same_reads(got, exp):
+    for k in FIELDS:
+        e = np.asarray(exp[k])
+        assert got[k].shape == e.shape, k
+        assert np.array_equal(got[k].astype(np.int64), e.astype(np.int64)), k
+
+
+def make_reads(L, seed, cov=6):
+    fa = synth.make_fasta(L, seed)
+    reads, _ = synth.make_reads(L, seed, fa, coverage=cov, n_events=2)
+    return fa, reads
+
+
+@pytest.mark.parametrize("level,strategy,chunk", [(1, 0, None), (6, 0, 70000), (0, 0, 150000), (9, zlib.Z_FIXED, 200000), (1, zlib.Z_HUFFMAN_ONLY, 90001)])
+def test_decode_matches_source_reads(sim_lib, tmp_path, level, strategy, chunk):
+    contigs = [("1", 60000), ("2", 5000), ("3", 90000), ("MT", 20000)]
+    rb = {0: make_reads(60000, 11)[1], 2: make_reads(90000, 12)[1], 3: make_reads(20000, 13, cov=3)[1]}
+    path = str(tmp_path / "t.bam")
+    synth.write_bam(path, contigs, rb, level=level, strategy=strategy, random_seq=5)
+    got, h = decode_file(sim_lib, path, chunk)
+    assert h["names"] == ["1", "2", "3", "MT"] and h["lens"] == [60000, 5000, 90000, 20000]
+    assert sorted(got) == [0, 2, 3]
+    for tid in got:
+        assert_same_reads(got[tid], rb[tid])
+
+
+def test_small_blocks_and_long_header(sim_lib, tmp_path):
+    """BGZF blocks far smaller than a record spacing pattern (blocks without any record start) and a header spanning several blocks"""
+    contigs = [("c%d" % i, 40000) for i in range(300)]
+    rb = {7: make_reads(40000, 21)[1], 299: make_reads(40000, 22, cov=2)[1]}
+    path = str(tmp_path / "t.bam")
+    synth.write_bam(path, contigs, rb, level=6, block_size=97)
+    got, h = decode_file(sim_lib, path, 50000)
+    assert len(h["names"]) == 300
+    for tid in (7, 299):
+        assert_same_reads(got[tid], rb[tid])
+
+
+def test_wrong_guess_is_repaired(sim_lib, tmp_path):
+    """quality bytes that look like a record header right at a BGZF block boundary: the speculative start is wrong, the proof
+    step must notice and re-walk that block"""
+    import struct
+    L = 80000
+    fa, reads = make_reads(L, 31, cov=8)
+    contigs = [("19", L)]
+    # stream offset of each record: header size, then records
+    text = "@HD\tVN:1.0\tSO:coordinate\n@SQ\tSN:19\tLN:%d\n" % L
+    hdr = 12 + len(text) + 4 + len("19") + 1 + 4
+    ncig = np.diff(reads["cigar_off"].astype(np.int64)); lq = np.diff(reads["qual_off"].astype(np.int64))
+    size = 4 + 32 + 2 + 4 * ncig + (lq + 1) // 2 + lq
+    start = hdr + np.concatenate(([0], np.cumsum(size)))[:-1]
+    qstart = start + 36 + 2 + 4 * ncig + (lq + 1) // 2
+    BS = 65280
+    fake = struct.pack("<IiiBBHHHiiii", 40, 0, 5, 1, 0, 0, 0, 0, 0, 0, 5, 0) + b"\x00" + b"\x00" * 7   # a 44-byte "record"
+    planted = 0
+    qual = reads["qual"].copy()
+    for k in range(1, int((start[-1] + size[-1]) // BS) + 1):
+        b = k * BS
+        r = int(np.searchsorted(qstart, b, side="right") - 1)
+        if r < 0 or not (qstart[r] <= b and b + 2 * len(fake) <= qstart[r] + lq[r]):
+            continue
+        o = int(reads["qual_off"][r]) + (b - int(qstart[r]))
+        qual[o:o + 2 * len(fake)] = np.frombuffer(fake + fake, np.uint8)
+        planted += 1
+    assert planted >= 1
+    reads = dict(reads); reads["qual"] = qual
+    path = str(tmp_path / "t.bam")
+    synth.write_bam(path, contigs, {0: reads}, level=1)
+    data = np.fromfile(path, np.uint8)
+    h = api.parse_bam_header(data)
+    ctx = api.Context(lib=sim_lib)
+    ctx.bam_begin(1)
+    consumed, runs = ctx.bam_feed(data[h["coff"]:], skip=h["skip"])
+    assert runs == [(0, len(reads["pos"]))]
+    assert_same_reads(ctx.bam_run_reads(0), reads)
+    assert ctx.debug_state()["bam_rewalked"] >= planted
+    ctx.bam_end(); ctx.close()
+
+
+def test_corrupt_and_truncated_input(sim_lib, tmp_path):
+    fa, reads = make_reads(30000, 41, cov=40)
+    path = str(tmp_path / "t.bam")
+    synth.write_bam(path, [("19", 30000)], {0: reads}, level=6, random_seq=1)
+    data = np.fromfile(path, np.uint8)
+    h = api.parse_bam_header(data)
+    ctx = api.Context(lib=sim_lib)
+    # an invalid deflate block type at the start of a payload (like the reference's bgzf.c, the GPU path does not check CRC32:
+    # only structural damage is detectable)
+    bad = data.copy(); bad[h["coff"] + 18] = 0x07
+    ctx.bam_begin(1)
+    with pytest.raises(api.RsiGpuError):
+        ctx.bam_feed(bad[h["coff"]:], skip=h["skip"])
+    # not a block boundary
+    ctx.bam_begin(1)
+    with pytest.raises(api.RsiGpuError):
+        ctx.bam_feed(data[h["coff"] + 1:], skip=h["skip"])
+    # file cut inside a record: the first blocks decode, end() reports the cut
+    ctx.bam_begin(1)
+    assert len(data) > 150000
+    consumed, runs = ctx.bam_feed(data[h["coff"]:h["coff"] + 100000], skip=h["skip"])
+    assert 0 < consumed <= 100000 and runs and runs[0][1] < len(reads["pos"])
+    with pytest.raises(api.RsiGpuError):
+        ctx.bam_end()
+    ctx.close()
+
+
+def test_decoded_reads_give_the_same_calls(sim_lib, tmp_path):
+    """file bytes -> GPU decode -> take -> run equals host-decoded reads -> pileup_push -> run"""
+    L = 300000
+    fa = synth.make_fasta(L, 3)
+    reads, _ = synth.make_reads(L, 3, fa, coverage=12, n_events=6, lens=(3000, 8000, 20000))
+    path = str(tmp_path / "t.bam")
+    synth.write_bam(path, [("19", L)], {0: reads}, level=1)
+    data = np.fromfile(path, np.uint8)
+    h = api.parse_bam_header(data)
+    a = api.Context(lib=sim_lib, minq=0, min_baseQ=10)
+    a.set_reference(fa); a.pileup_begin(); a.pileup_push(reads); a.have_reads()
+    want = a.run()
+    b = api.Context(lib=sim_lib, minq=0, min_baseQ=10)
+    b.set_reference(fa); b.pileup_begin()
+    b.bam_begin(1)
+    off = h["coff"]; pending = np.zeros(0, np.uint8); first = True
+    while off < len(data) or len(pending):
+        buf = np.concatenate((pending, data[off:off + 120000])); off += 120000
+        consumed, runs = b.bam_feed(buf, skip=h["skip"] if first else 0)
+        first = first and not consumed
+        for i, (tid, n) in enumerate(runs):
+            assert tid == 0
+            b.bam_take(i, b)
+        pending = buf[consumed:]
+    b.bam_end(); b.have_reads()
+    got = b.run()
+    assert len(got) == len(want) and len(want) > 0
+    for x, y in zip(got, want):
+        assert bytes(x) == bytes(y)
+    a.close(); b.close()
