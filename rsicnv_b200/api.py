@@ -146,11 +146,10 @@ def parse_bam_header(data) -> dict:
         p += 8 + ln
     # the block that holds decoded offset p (the first record); if the header ends exactly at a block end, the next block
     coff, skip = off, 0
-    for fo, do in starts:
-        if do <= p:
+    for i, (fo, do) in enumerate(starts):
+        hi = starts[i + 1][1] if i + 1 < len(starts) else len(dec)
+        if do <= p < hi:
             coff, skip = fo, p - do
-    if skip == len(dec) - [do for fo, do in starts if fo == coff][0] and coff != off:
-        coff, skip = off, 0
     return {"names": names, "lens": lens, "coff": coff, "skip": skip}
 
 

@@ -98,95 +98,110 @@ __device__ __forceinline__ int inf_decode(BitIn& b, const u16* sm, int lane, int
   return -1;
 }
 
-// One raw-deflate stream -> dst[0, dst_len).  Returns 0 when the stream ends exactly at dst_len bytes.
-__device__ int inflate_one(const u8* src, u32 src_len, u8* dst, u32 dst_len, u16* sm, int lane, const u16* tab) {
-  const u16* LBASE = tab; const u16* LEXT = tab + 29; const u16* DBASE = tab + 58; const u16* DEXT = tab + 88;
-  const u32 mis = (u32)((size_t)src & 3u);
-  BitIn b; b.base = src - mis; b.pos = mis; b.end = src_len + mis; b.buf = 0; b.cnt = 0;
-  bits_align(b);
-  u32 o = 0;
-  u8 lens[320];
-  for (;;) {
+// One raw-deflate stream -> dst[0, dst_len), as a stepper: the lanes of a warp work on 32 different streams, and a
+// free-running per-lane loop lets the hardware serialise them (one lane runs its whole stream while the others wait).
+// inf_step does ONE unit of work -- a block header with its tables, a stored block, or one literal/length symbol with
+// its match copy -- and the kernel re-converges the warp after every step.
+struct InfState {
+  BitIn b; u32 o, dst_len; u8* dst;
+  int phase;      // 0: at a block header, 1: inside a Huffman block, 2: finished (rc = 0 ok)
+  int last, rc;
+};
+enum { INF_HEADER = 0, INF_SYMS = 1, INF_DONE = 2 };
+
+__device__ __forceinline__ void inf_fail(InfState& S, int rc) { S.rc = rc; S.phase = INF_DONE; }
+
+__device__ void inf_block_header(InfState& S, u16* sm, int lane) {
+  BitIn& b = S.b;
+  bits_refill(b);
+  S.last = (int)bits_take(b, 1);
+  const u32 type = bits_take(b, 2);
+  if (type == 0) {   // stored
+    bits_take(b, b.cnt & 7);
     bits_refill(b);
-    const u32 last = bits_take(b, 1), type = bits_take(b, 2);
-    if (type == 0) {   // stored
-      bits_take(b, b.cnt & 7);
-      bits_refill(b);
-      const u32 len = bits_take(b, 16); bits_refill(b); const u32 nlen = bits_take(b, 16);
-      if ((len ^ 0xffffu) != nlen) return 2;
-      if (o + len > dst_len) return 3;
-      // bytes still in the bit buffer, then straight from memory
-      u32 k = 0;
-      while (k < len && b.cnt >= 8) { dst[o + k++] = (u8)bits_take(b, 8); }
-      for (; k < len; ++k) { if (b.pos >= b.end) return 4; dst[o + k] = b.base[b.pos++]; }
-      b.buf = 0; b.cnt = 0;
-      bits_align(b);
-      o += len;
-    } else if (type == 1 || type == 2) {
-      if (type == 1) {
-        for (int s = 0; s < 144; ++s) lens[s] = 8;
-        for (int s = 144; s < 256; ++s) lens[s] = 9;
-        for (int s = 256; s < 280; ++s) lens[s] = 7;
-        for (int s = 280; s < 288; ++s) lens[s] = 8;
-        inf_construct(sm, lane, lens, 288, INF_LF, INF_FB, INF_LC, INF_LS);
-        for (int s = 0; s < 30; ++s) lens[s] = 5;
-        inf_construct(sm, lane, lens, 30, INF_DF, INF_DB, INF_DC, INF_DS);
-      } else {
-        bits_refill(b);
-        const int nlen = (int)bits_take(b, 5) + 257, ndist = (int)bits_take(b, 5) + 1, ncode = (int)bits_take(b, 4) + 4;
-        if (nlen > 286 || ndist > 30) return 5;
-        const u8 order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
-        for (int i = 0; i < 19; ++i) lens[i] = 0;
-        for (int i = 0; i < ncode; ++i) { bits_refill(b); lens[order[i]] = (u8)bits_take(b, 3); }
-        if (inf_construct(sm, lane, lens, 19, INF_LF, 7, INF_LC, INF_LS) != 0) return 6;   // the code-length code must be complete
-        int idx = 0;
-        while (idx < nlen + ndist) {
-          bits_refill(b);
-          const int sym = inf_decode(b, sm, lane, INF_LF, 7, INF_LC, INF_LS);
-          if (sym < 0) return 7;
-          if (sym < 16) lens[idx++] = (u8)sym;
-          else {
-            int rep; u8 v = 0;
-            if (sym == 16) { if (idx == 0) return 8; v = lens[idx - 1]; rep = 3 + (int)bits_take(b, 2); }
-            else if (sym == 17) rep = 3 + (int)bits_take(b, 3);
-            else rep = 11 + (int)bits_take(b, 7);
-            if (idx + rep > nlen + ndist) return 9;
-            while (rep--) lens[idx++] = v;
-          }
-        }
-        if (lens[256] == 0) return 10;
-        int r = inf_construct(sm, lane, lens, nlen, INF_LF, INF_FB, INF_LC, INF_LS);
-        if (r < 0 || (r > 0 && nlen - (int)INF_T(INF_LC) != 1)) return 11;       // incomplete only allowed for a single code
-        r = inf_construct(sm, lane, lens + nlen, ndist, INF_DF, INF_DB, INF_DC, INF_DS);
-        if (r < 0 || (r > 0 && ndist - (int)INF_T(INF_DC) != 1)) return 12;
-      }
-      for (;;) {
-        bits_refill(b);
-        int sym = inf_decode(b, sm, lane, INF_LF, INF_FB, INF_LC, INF_LS);
-        if (sym < 0) return 13;
-        if (sym < 256) { if (o >= dst_len) return 3; dst[o++] = (u8)sym; continue; }
-        if (sym == 256) break;
-        sym -= 257;
-        if (sym >= 29) return 14;
-        const u32 len = (u32)LBASE[sym] + bits_take(b, (int)LEXT[sym]);
-        bits_refill(b);
-        const int ds = inf_decode(b, sm, lane, INF_DF, INF_DB, INF_DC, INF_DS);
-        if (ds < 0 || ds >= 30) return 15;
-        const u32 dist = (u32)DBASE[ds] + bits_take(b, (int)DEXT[ds]);
-        if (dist > o) return 16;
-        if (o + len > dst_len) return 3;
-        const u8* from = dst + o - dist; u8* to = dst + o;
-        for (u32 k = 0; k < len; ++k) to[k] = from[k];
-        o += len;
-      }
-    } else return 1;
-    if (last) break;
-    if (b.pos > b.end + 16) return 17;
+    const u32 len = bits_take(b, 16); bits_refill(b); const u32 nlen = bits_take(b, 16);
+    if ((len ^ 0xffffu) != nlen) return inf_fail(S, 2);
+    if (S.o + len > S.dst_len) return inf_fail(S, 3);
+    u32 k = 0;      // bytes still in the bit buffer, then straight from memory
+    while (k < len && b.cnt >= 8) { S.dst[S.o + k++] = (u8)bits_take(b, 8); }
+    for (; k < len; ++k) { if (b.pos >= b.end) return inf_fail(S, 4); S.dst[S.o + k] = b.base[b.pos++]; }
+    if (b.cnt == 0) bits_align(b);   // bytes were read straight from memory: get back to word loads (loaded-but-unused whole bytes stay in the buffer)
+    S.o += len;
+    if (S.last) { S.rc = S.o == S.dst_len ? 0 : 18; S.phase = INF_DONE; }
+    return;
   }
-  return o == dst_len ? 0 : 18;
+  if (type == 3) return inf_fail(S, 1);
+  u8 lens[320];
+  if (type == 1) {
+    for (int s = 0; s < 144; ++s) lens[s] = 8;
+    for (int s = 144; s < 256; ++s) lens[s] = 9;
+    for (int s = 256; s < 280; ++s) lens[s] = 7;
+    for (int s = 280; s < 288; ++s) lens[s] = 8;
+    inf_construct(sm, lane, lens, 288, INF_LF, INF_FB, INF_LC, INF_LS);
+    for (int s = 0; s < 30; ++s) lens[s] = 5;
+    inf_construct(sm, lane, lens, 30, INF_DF, INF_DB, INF_DC, INF_DS);
+  } else {
+    bits_refill(b);
+    const int nlen = (int)bits_take(b, 5) + 257, ndist = (int)bits_take(b, 5) + 1, ncode = (int)bits_take(b, 4) + 4;
+    if (nlen > 286 || ndist > 30) return inf_fail(S, 5);
+    const u8 order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    for (int i = 0; i < 19; ++i) lens[i] = 0;
+    for (int i = 0; i < ncode; ++i) { bits_refill(b); lens[order[i]] = (u8)bits_take(b, 3); }
+    if (inf_construct(sm, lane, lens, 19, INF_LF, 7, INF_LC, INF_LS) != 0) return inf_fail(S, 6);   // the code-length code must be complete
+    int idx = 0;
+    while (idx < nlen + ndist) {
+      bits_refill(b);
+      const int sym = inf_decode(b, sm, lane, INF_LF, 7, INF_LC, INF_LS);
+      if (sym < 0) return inf_fail(S, 7);
+      if (sym < 16) lens[idx++] = (u8)sym;
+      else {
+        int rep; u8 v = 0;
+        if (sym == 16) { if (idx == 0) return inf_fail(S, 8); v = lens[idx - 1]; rep = 3 + (int)bits_take(b, 2); }
+        else if (sym == 17) rep = 3 + (int)bits_take(b, 3);
+        else rep = 11 + (int)bits_take(b, 7);
+        if (idx + rep > nlen + ndist) return inf_fail(S, 9);
+        while (rep--) lens[idx++] = v;
+      }
+    }
+    if (lens[256] == 0) return inf_fail(S, 10);
+    int r = inf_construct(sm, lane, lens, nlen, INF_LF, INF_FB, INF_LC, INF_LS);
+    if (r < 0 || (r > 0 && nlen - (int)INF_T(INF_LC) != 1)) return inf_fail(S, 11);       // incomplete only allowed for a single code
+    r = inf_construct(sm, lane, lens + nlen, ndist, INF_DF, INF_DB, INF_DC, INF_DS);
+    if (r < 0 || (r > 0 && ndist - (int)INF_T(INF_DC) != 1)) return inf_fail(S, 12);
+  }
+  S.phase = INF_SYMS;
 }
 
-// inflate: one thread per BGZF block of the chunk
+__device__ __forceinline__ void inf_symbol(InfState& S, const u16* sm, int lane, const u16* tab) {
+  BitIn& b = S.b;
+  bits_refill(b);
+  int sym = inf_decode(b, sm, lane, INF_LF, INF_FB, INF_LC, INF_LS);
+  if (sym < 256) {
+    if (sym < 0) return inf_fail(S, 13);
+    if (S.o >= S.dst_len) return inf_fail(S, 3);
+    S.dst[S.o++] = (u8)sym;
+    return;
+  }
+  if (sym == 256) {
+    if (b.pos > b.end + 16) return inf_fail(S, 17);
+    if (S.last) { S.rc = S.o == S.dst_len ? 0 : 18; S.phase = INF_DONE; } else S.phase = INF_HEADER;
+    return;
+  }
+  sym -= 257;
+  if (sym >= 29) return inf_fail(S, 14);
+  const u32 len = (u32)tab[sym] + bits_take(b, (int)tab[29 + sym]);
+  bits_refill(b);
+  const int ds = inf_decode(b, sm, lane, INF_DF, INF_DB, INF_DC, INF_DS);
+  if (ds < 0 || ds >= 30) return inf_fail(S, 15);
+  const u32 dist = (u32)tab[58 + ds] + bits_take(b, (int)tab[88 + ds]);
+  if (dist > S.o) return inf_fail(S, 16);
+  if (S.o + len > S.dst_len) return inf_fail(S, 3);
+  const u8* from = S.dst + S.o - dist; u8* to = S.dst + S.o;
+  for (u32 k = 0; k < len; ++k) to[k] = from[k];
+  S.o += len;
+}
+
+// inflate: one thread per BGZF block of the chunk, the warp re-converged after every step
 __global__ void __launch_bounds__(INF_NT) k_bgzf_inflate(const u8* __restrict__ comp, const BgzfBlock* __restrict__ blk, int nblk, u8* __restrict__ U, int* __restrict__ err) {
   RSI_DYN_SMEM(smem);
   u16* sm = reinterpret_cast<u16*>(smem);
@@ -202,11 +217,28 @@ __global__ void __launch_bounds__(INF_NT) k_bgzf_inflate(const u8* __restrict__ 
   __syncthreads();
   const int lane = (int)threadIdx.x;
   const int k = (int)blockIdx.x * INF_NT + lane;
-  if (k >= nblk) return;
-  const BgzfBlock B = blk[k];
-  if (B.dst_len == 0) return;
-  const int rc = inflate_one(comp + B.src, B.src_len, U + B.dst, B.dst_len, sm, lane, tab);
-  if (rc) { atomicOr(err, (int)BAM_ERR_INFLATE); atomicMax(err + 1, rc); }
+  InfState S;
+  S.phase = INF_DONE; S.rc = 0; S.o = 0; S.dst_len = 0; S.dst = U; S.last = 0;
+  S.b.base = comp; S.b.pos = 0; S.b.end = 0; S.b.buf = 0; S.b.cnt = 0;
+  if (k < nblk) {
+    const BgzfBlock B = blk[k];
+    if (B.dst_len) {
+      const u8* src = comp + B.src;
+      const u32 mis = (u32)((size_t)src & 3u);
+      S.b.base = src - mis; S.b.pos = mis; S.b.end = B.src_len + mis;
+      bits_align(S.b);
+      S.dst = U + B.dst; S.dst_len = B.dst_len; S.phase = INF_HEADER;
+    }
+  }
+  while (__any_sync(0xffffffffu, S.phase != INF_DONE)) {
+    // lanes that need a block header (table construction: long) go first and together; the others decode one symbol
+    if (__any_sync(0xffffffffu, S.phase == INF_HEADER)) { if (S.phase == INF_HEADER) inf_block_header(S, sm, lane); }
+    else {
+#pragma unroll 1
+      for (int it = 0; it < 8; ++it) { if (S.phase == INF_SYMS) inf_symbol(S, sm, lane, tab); __syncwarp(); }
+    }
+  }
+  if (S.rc) { atomicOr(err, (int)BAM_ERR_INFLATE); atomicMax(err + 1, S.rc); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -261,18 +293,41 @@ __device__ void bam_walk(const BamChunk& C, int p, int stop, int k, const BamCha
   H.endp[k] = endp; H.tailp[k] = tailp; H.cnt[k] = cnt; H.ncig[k] = ncig; H.nq[k] = nq;
 }
 
+// extra evidence for a GUESSED start (never applied to proven records): printable read name, CIGAR op codes <= 8 whose
+// query-consuming lengths add up to l_seq (SAM spec), and the next two records pass the core check as well
+__device__ bool bam_guess_ok(const BamChunk& C, int p) {
+  int nx;
+  if (!bam_core_ok(C, p, &nx)) return false;
+  const u8* r = C.U + p;
+  const u32 l_name = r[12], n_cig = (u32)r[16] | ((u32)r[17] << 8);
+  const int l_seq = (int)ld32u(r + 20);
+  if ((i64)p + 36 + (i64)l_name + 4ll * n_cig <= (i64)C.u_end) {
+    for (u32 k = 0; k + 1 < l_name; ++k) { const u8 ch = r[36 + k]; if (ch < 33 || ch > 126) return false; }
+    if (n_cig > 0 && n_cig <= 64) {
+      i64 q = 0;
+      for (u32 k = 0; k < n_cig; ++k) {
+        const u32 c = ld32u(r + 36 + l_name + 4 * k), op = c & 15u;
+        if (op > 8u) return false;
+        if (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) q += (i64)(c >> 4);
+      }
+      if (l_seq > 0 && q != (i64)l_seq) return false;
+    }
+  }
+  int n2, n3;
+  if ((i64)nx + 36 <= (i64)C.u_end) {
+    if (!bam_core_ok(C, nx, &n2)) return false;
+    if ((i64)n2 + 36 <= (i64)C.u_end && !bam_core_ok(C, n2, &n3)) return false;
+  }
+  return true;
+}
+
 __global__ void k_bam_chain(BamChunk C, BamChain H) {
   for (int k = (int)(blockIdx.x * blockDim.x + threadIdx.x); k < C.nblk; k += (int)(gridDim.x * blockDim.x)) {
     const int ub = C.bound[k], ue = C.bound[k + 1];
     int g = BAM_NONE;
     if (k == 0) { if (C.u_begin < ue) g = C.u_begin; }
     else {
-      for (int p = ub; p < ue; ++p) {
-        int nx, nx2;
-        if (!bam_core_ok(C, p, &nx)) continue;
-        if ((i64)nx + 36 <= (i64)C.u_end && !bam_core_ok(C, nx, &nx2)) continue;
-        g = p; break;
-      }
+      for (int p = ub; p < ue; ++p) if (bam_guess_ok(C, p)) { g = p; break; }
     }
     H.first[k] = g;
     if (g == BAM_NONE) { H.endp[k] = BAM_NONE; H.tailp[k] = 0; H.cnt[k] = 0; H.ncig[k] = 0; H.nq[k] = 0; }
@@ -309,16 +364,22 @@ __global__ void __launch_bounds__(1024) k_bam_verify(BamChunk C, BamChain H, int
       if (g != BAM_NONE) run = imax(run, H.endp[k]);
     }
     c.sync();
-    bad = c.reduce(bad, MinOp());
-    if (bad == 0x7fffffff) break;
-    if (c.tid == 0) {      // everything before `bad` is proven: re-walk it from the true position
-      const int cur = in_pos[bad], ue = C.bound[bad + 1];
-      if (cur >= ue) { H.first[bad] = BAM_NONE; H.endp[bad] = BAM_NONE; H.cnt[bad] = 0; H.ncig[bad] = 0; H.nq[bad] = 0; }
-      else { H.first[bad] = cur; bam_walk(C, cur, ue, bad, H, nullptr); }
+    const int firstbad = c.reduce(bad, MinOp());
+    if (firstbad == 0x7fffffff) break;
+    // Everything before the first mismatch is proven, so ITS position is the true one.  Mismatches further on are almost
+    // always isolated wrong guesses whose incoming position is already right: every thread repairs the mismatches of its
+    // own range from in_pos; the next round proves or refutes them (at least the first one is settled per round).
+    for (int k = k0; k < k1; ++k) {
+      const int ue = C.bound[k + 1], g = H.first[k], cur = in_pos[k];
+      const bool ok = (cur >= ue) ? (g == BAM_NONE) : (g == cur);
+      if (ok) continue;
+      if (cur >= ue) { H.first[k] = BAM_NONE; H.endp[k] = BAM_NONE; H.cnt[k] = 0; H.ncig[k] = 0; H.nq[k] = 0; }
+      else { H.first[k] = cur; bam_walk(C, cur, ue, k, H, nullptr); }
+      ++fixed;
     }
-    ++fixed;
     c.sync();
   }
+  fixed = c.reduce(fixed, SumOp());
   // all starts proven: corruption inside a proven walk is a real error
   int tail = -1, maxend = C.u_begin, e = 0;
   for (int k = k0; k < k1; ++k) if (H.first[k] != BAM_NONE) {

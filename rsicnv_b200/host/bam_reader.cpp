@@ -133,4 +133,53 @@ bool BamReader::next_contig(ContigReads* out, std::string* err) {
   return out->tid >= 0;
 }
 
+bool read_bam_header(const std::string& path, BamHeader* hdr, long long* rec_coff, long long* rec_skip, std::string* err) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) { *err = "cannot open " + path; return false; }
+  std::vector<uint8_t> dec;
+  std::vector<std::pair<long long, size_t>> starts;   // (file offset, decoded offset) of every block inflated so far
+  long long foff = 0;
+  bool ok = true;
+  auto more = [&]() {
+    uint8_t h[18];
+    if (fread(h, 1, 18, f) != 18 || h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4) || rd16(h + 10) != 6 || h[12] != 'B' || h[13] != 'C') return false;
+    const size_t clen = (size_t)rd16(h + 16) + 1;
+    std::vector<uint8_t> comp(clen);
+    memcpy(comp.data(), h, 18);
+    if (clen < 26 || fread(&comp[18], 1, clen - 18, f) != clen - 18) return false;
+    const size_t ulen = rd32(&comp[clen - 4]);
+    starts.push_back(std::make_pair(foff, dec.size()));
+    const size_t at = dec.size();
+    dec.resize(at + ulen);
+    if (ulen && !inflate_block(comp.data(), clen, &dec[at], ulen)) return false;
+    foff += (long long)clen;
+    return true;
+  };
+  auto need = [&](size_t n) { while (ok && dec.size() < n) ok = more(); return ok; };
+  size_t p = 0;
+  if (!need(12) || memcmp(dec.data(), "BAM\1", 4) != 0) { *err = path + " is not a BAM file"; fclose(f); return false; }
+  const uint32_t l_text = rd32(&dec[4]);
+  if (!need(12 + (size_t)l_text)) { *err = "truncated BAM header"; fclose(f); return false; }
+  const uint32_t n_ref = rd32(&dec[8 + l_text]);
+  p = 12 + (size_t)l_text;
+  hdr->name.clear(); hdr->len.clear();
+  for (uint32_t i = 0; i < n_ref; ++i) {
+    if (!need(p + 4)) break;
+    const uint32_t l_name = rd32(&dec[p]);
+    if (!need(p + 8 + (size_t)l_name)) break;
+    hdr->name.push_back(std::string((const char*)&dec[p + 4], l_name ? l_name - 1 : 0));
+    hdr->len.push_back((int32_t)rd32(&dec[p + 4 + l_name]));
+    p += 8 + l_name;
+  }
+  fclose(f);
+  if (!ok) { *err = "truncated BAM header"; return false; }
+  // the block that holds decoded offset p; when the header ends exactly at a block end, the next block
+  *rec_coff = foff; *rec_skip = 0;
+  for (size_t i = 0; i < starts.size(); ++i) {
+    const size_t lo = starts[i].second, hi = i + 1 < starts.size() ? starts[i + 1].second : dec.size();
+    if (lo <= p && p < hi) { *rec_coff = starts[i].first; *rec_skip = (long long)(p - lo); }
+  }
+  return true;
+}
+
 }  // namespace rsihost

@@ -56,4 +56,9 @@ class BamReader {
   bool eof_ = false;
 };
 
+// Only the header (bam_header_read, bam.c:69-110), inflating block by block: names and lengths, plus where the alignment
+// records start -- rec_coff = file offset of the BGZF block that holds the first record, rec_skip = decoded bytes of that
+// block in front of it.  This is what the GPU decoder (rsigpu_bam_feed) needs from the host.
+bool read_bam_header(const std::string& path, BamHeader* hdr, long long* rec_coff, long long* rec_skip, std::string* err);
+
 }  // namespace rsihost

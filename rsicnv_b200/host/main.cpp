@@ -14,6 +14,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <fstream>
@@ -31,7 +32,7 @@ namespace {
 
 struct Opt {
   std::string function = "rsi", rdfile, bamfile, reffile, outfile = "rsiout.txt", chr = "1-22XY";
-  bool saverd = false;
+  bool saverd = false, hostdecode = false;
   int gpus = 1, threads = 8;
   rsigpu_params P;
 };
@@ -42,7 +43,7 @@ int usage() {
           "Options:\n   -o  STR  outputfile [rsiout.txt]\n   -c  STR  chromosome [1-22XY]\n   -m  INT  bin size, odd [101]\n"
           "   -q  INT  minimum mapping quality [0]\n   -Q  INT  minimum base quality [13]\n   -cap FLT cap depth at FLT x median, <=1 off [4]\n"
           "   -NOGC    no GC adjustment\n   -MED | -NB | -ALL  transformation [NB]\n   -s       save raw depth to <out>.<chr>_rd (BAM input)\n"
-          "   -gpus INT  GPUs to shard contigs over [1]   -threads INT  host inflate threads [8]\n");
+          "   -gpus INT  GPUs to shard contigs over [1]\n   -hostdecode  inflate/parse the BAM on the host (zlib, -threads INT [8]) instead of on the GPU\n");
   return 0;
 }
 
@@ -82,6 +83,7 @@ bool parse(int argc, char** argv, Opt* o) {
     if (k == "-NOGC") { o->P.gcadjust = 0; a[i] = ""; continue; }
     if (k == "-gpus") { o->gpus = atoi(val(i).c_str()); two(); continue; }
     if (k == "-threads") { o->threads = atoi(val(i).c_str()); two(); continue; }
+    if (k == "-hostdecode") { o->hostdecode = true; a[i] = ""; continue; }
   }
   bool bad = false;
   for (size_t i = 1; i < a.size(); ++i) if (!a[i].empty()) { fprintf(stderr, "unknown option %s\n", a[i].c_str()); bad = true; }
@@ -167,22 +169,22 @@ struct ContigResult {
   std::vector<rsigpu_cnv> calls; double rdmedian = 0, rdsd = 0;
 };
 
-bool run_contig(rsigpu_ctx* c, const Opt& o, const std::string& name, int tid, const std::string& fasta, const std::vector<int32_t>* depth,
-                const ContigReads* reads, ContigResult* res) {
+// set_reference + pileup_begin (BAM input) / set_depth (depth-file input)
+bool begin_contig(rsigpu_ctx* c, int tid, const std::string& fasta, const std::vector<int32_t>* depth, ContigResult* res) {
   auto fail = [&](const char* what) { res->err = std::string(what) + ": " + rsigpu_last_error(c); return false; };
   if (rsigpu_set_reference(c, (const uint8_t*)fasta.data(), (int32_t)fasta.size(), tid)) return fail("set_reference");
-  if (depth) {
-    if (rsigpu_set_depth(c, depth->data(), (int32_t)depth->size())) return fail("set_depth");
-  } else {
-    if (rsigpu_pileup_begin(c, (int32_t)fasta.size())) return fail("pileup_begin");
-    rsigpu_read_batch b; memset(&b, 0, sizeof b);
-    b.n_reads = (int64_t)reads->n(); b.tid = tid;
-    b.pos = reads->pos.data(); b.mpos = reads->mpos.data(); b.isize = reads->isize.data(); b.mtid = reads->mtid.data(); b.flag = reads->flag.data();
-    b.mapq = reads->mapq.data(); b.cigar_off = reads->cigar_off.data(); b.cigar = reads->cigar.data(); b.qual_off = reads->qual_off.data(); b.qual = reads->qual.data();
-    if (rsigpu_pileup_push(c, &b)) return fail("pileup_push");
+  if (depth) { if (rsigpu_set_depth(c, depth->data(), (int32_t)depth->size())) return fail("set_depth"); }
+  else if (rsigpu_pileup_begin(c, (int32_t)fasta.size())) return fail("pileup_begin");
+  return true;
+}
+
+// everything after the inputs are staged: the body of the chromosome loop (rsi.cpp:2197-2211)
+bool finish_contig(rsigpu_ctx* c, const Opt& o, const std::string& name, size_t fasta_len, bool bam, ContigResult* res) {
+  auto fail = [&](const char* what) { res->err = std::string(what) + ": " + rsigpu_last_error(c); return false; };
+  if (bam) {
     if (o.saverd) {
       if (rsigpu_pileup_end(c)) return fail("pileup_end");
-      std::vector<int32_t> raw(fasta.size()); int64_t cnt = 0;
+      std::vector<int32_t> raw(fasta_len); int64_t cnt = 0;
       if (rsigpu_get_array(c, RSIGPU_ARR_RAW_DEPTH, raw.data(), (int64_t)raw.size(), &cnt)) return fail("get raw depth");
       const std::string fn = o.outfile + "." + name + "_rd";   // loaddata.cpp:340-344, 464-470
       FILE* f = fopen(fn.c_str(), "w");
@@ -197,6 +199,141 @@ bool run_contig(rsigpu_ctx* c, const Opt& o, const std::string& name, int tid, c
   if (rsigpu_get_chr_stats(c, &st)) return fail("chr_stats");
   res->rdmedian = st.rdmedian; res->rdsd = st.rdsd;
   return true;
+}
+
+bool run_contig(rsigpu_ctx* c, const Opt& o, const std::string& name, int tid, const std::string& fasta, const std::vector<int32_t>* depth,
+                const ContigReads* reads, ContigResult* res) {
+  if (!begin_contig(c, tid, fasta, depth, res)) return false;
+  if (reads) {
+    rsigpu_read_batch b; memset(&b, 0, sizeof b);
+    b.n_reads = (int64_t)reads->n(); b.tid = tid;
+    b.pos = reads->pos.data(); b.mpos = reads->mpos.data(); b.isize = reads->isize.data(); b.mtid = reads->mtid.data(); b.flag = reads->flag.data();
+    b.mapq = reads->mapq.data(); b.cigar_off = reads->cigar_off.data(); b.cigar = reads->cigar.data(); b.qual_off = reads->qual_off.data(); b.qual = reads->qual.data();
+    if (rsigpu_pileup_push(c, &b)) { res->err = std::string("pileup_push: ") + rsigpu_last_error(c); return false; }
+  }
+  return finish_contig(c, o, name, fasta.size(), reads != nullptr, res);
+}
+
+double now_s() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec; }
+
+// BAM input decoded on the GPU: the file is streamed in chunks of whole BGZF blocks into rsigpu_bam_feed (inflate + record
+// decoding, k_bam.cuh); each run of records of one contig is appended to the context of the GPU that owns the contig.
+// A reader thread fills the next pinned chunk while the GPU works on the current one.
+int bam_on_gpu(const Opt& o, std::vector<rsigpu_ctx*>& ctx, std::vector<ContigResult>* results_out) {
+  const bool timing = getenv("RSICNV_TIMING") != nullptr;
+  const double t_start = now_s();
+  double t_feed = 0, t_take = 0, t_wait = 0;
+  std::string err;
+  long long coff = 0, skip = 0;
+  BamHeader h;
+  if (!read_bam_header(o.bamfile, &h, &coff, &skip, &err)) { fprintf(stderr, "%s\n", err.c_str()); return 0; }
+  std::vector<ContigResult>& results = *results_out;
+  results.resize(h.name.size());
+  for (size_t i = 0; i < h.name.size(); ++i) results[i].name = h.name[i];
+  if (o.chr != "1-22XY" && std::find(h.name.begin(), h.name.end(), o.chr) == h.name.end()) { fprintf(stderr, "BAM file doesn't have %s\n", o.chr.c_str()); return 0; }
+  const int ng = (int)ctx.size();
+  auto eligible = [&](int tid) {
+    const std::string& name = h.name[(size_t)tid];
+    if (name.find("MT") != std::string::npos || name.find(".") != std::string::npos) return false;   // rsi.cpp:2119-2120
+    return o.chr == "1-22XY" || name == o.chr;
+  };
+  // longest-processing-time assignment from the header lengths (1.038 imbalance for b37 on 8 GPUs)
+  std::vector<int> gpu_of(h.name.size(), 0);
+  {
+    std::vector<size_t> order;
+    for (size_t i = 0; i < h.name.size(); ++i) if (eligible((int)i)) order.push_back(i);
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return h.len[a] > h.len[b]; });
+    std::vector<long long> load((size_t)ng, 0);
+    for (size_t i : order) { const int g = (int)(std::min_element(load.begin(), load.end()) - load.begin()); gpu_of[i] = g; load[(size_t)g] += h.len[i]; }
+  }
+  rsigpu_ctx* dec = nullptr;
+  if (rsigpu_create(0, &o.P, &dec)) { fprintf(stderr, "cannot create the decoder context\n"); return 2; }
+  if (rsigpu_bam_begin(dec, (int32_t)h.name.size())) { fprintf(stderr, "%s\n", rsigpu_last_error(dec)); return 2; }
+  FILE* f = fopen(o.bamfile.c_str(), "rb");
+  if (!f || fseeko(f, (off_t)coff, SEEK_SET) != 0) { fprintf(stderr, "cannot open %s\n", o.bamfile.c_str()); return 0; }
+  const size_t CHUNK = (size_t)64 << 20, CARRY = (size_t)192 << 20;   // a chunk the decoder takes only partly (very compressible data) is presented again
+  uint8_t* buf[2] = {nullptr, nullptr};
+  for (int k = 0; k < 2; ++k) if (rsigpu_pinned_alloc(CARRY + CHUNK, (void**)&buf[k])) { fprintf(stderr, "cannot allocate pinned staging memory\n"); return 2; }
+  std::vector<std::thread> workers((size_t)ng);
+  std::mutex mu;
+  int cur = -1; bool cur_ok = false; std::string cur_fasta_err;
+  size_t cur_len = 0;
+  auto finish_cur = [&]() {
+    if (cur < 0 || !cur_ok) { cur = -1; return; }
+    const int tid = cur, g = gpu_of[(size_t)tid]; const size_t flen = cur_len;
+    workers[(size_t)g] = std::thread([&, tid, g, flen]() {
+      ContigResult& r = results[(size_t)tid];
+      r.done = finish_contig(ctx[(size_t)g], o, r.name, flen, true, &r);
+      if (!r.done) { std::lock_guard<std::mutex> lk(mu); fprintf(stderr, "%s: %s\n", r.name.c_str(), r.err.c_str()); }
+    });
+    cur = -1;
+  };
+  auto start = [&](int tid, long long nfirst) {
+    cur = tid; cur_ok = false;
+    if (!eligible(tid)) return;
+    const int g = gpu_of[(size_t)tid];
+    const double t0 = now_s();
+    if (workers[(size_t)g].joinable()) workers[(size_t)g].join();
+    t_wait += now_s() - t0;
+    ContigResult& r = results[(size_t)tid];
+    fprintf(stderr, "#processing %s on GPU %d\n", r.name.c_str(), g);
+    (void)nfirst;
+    std::string fasta, e2;
+    if (!read_fasta(o.reffile, r.name, &fasta, &e2)) { r.err = e2; fprintf(stderr, "%s: %s\n", r.name.c_str(), e2.c_str()); return; }
+    if ((int)fasta.size() != h.len[(size_t)tid]) fprintf(stderr, "reference and target not same size %zu\t%d\n", fasta.size(), h.len[(size_t)tid]);
+    cur_len = fasta.size();
+    if (!begin_contig(ctx[(size_t)g], tid, fasta, nullptr, &r)) { fprintf(stderr, "%s: %s\n", r.name.c_str(), r.err.c_str()); return; }
+    cur_ok = true;
+  };
+  size_t have = 0;          // bytes in buf[cb] not yet consumed
+  int cb = 0; bool eof = false, first = true, stop = false;
+  // the first chunk synchronously, then always one read ahead
+  have = fread(buf[cb], 1, CHUNK, f);
+  if (have < CHUNK) eof = true;
+  std::thread reader; size_t next_got = 0;
+  std::vector<rsigpu_bam_run> runs(4096);
+  const double t_loop = now_s();
+  while (have > 0 && !stop) {
+    const int nb = cb ^ 1;
+    if (!eof) reader = std::thread([&, nb]() { next_got = fread(buf[nb] + CARRY, 1, CHUNK, f); });
+    int64_t consumed = 0; int32_t nr = 0;
+    double t0 = now_s();
+    const int rc = rsigpu_bam_feed(dec, buf[cb], (int64_t)have, first ? skip : 0, &consumed, runs.data(), (int32_t)runs.size(), &nr);
+    t_feed += now_s() - t0;
+    if (rc) { fprintf(stderr, "%s\n", rsigpu_last_error(dec)); if (reader.joinable()) reader.join(); break; }
+    if (consumed) first = false;
+    t0 = now_s();
+    for (int i = 0; i < nr && i < (int)runs.size() && !stop; ++i) {
+      if (runs[(size_t)i].tid < 0) { stop = true; break; }           // unplaced reads come last in a sorted BAM
+      if (runs[(size_t)i].tid != cur) { finish_cur(); start(runs[(size_t)i].tid, runs[(size_t)i].n_reads); }
+      if (cur_ok && rsigpu_bam_take(dec, i, ctx[(size_t)gpu_of[(size_t)cur]])) {
+        fprintf(stderr, "%s: %s\n", results[(size_t)cur].name.c_str(), rsigpu_last_error(ctx[(size_t)gpu_of[(size_t)cur]])); cur_ok = false;
+      }
+    }
+    t_take += now_s() - t0;
+    const size_t rest = have - (size_t)consumed;
+    if (reader.joinable()) reader.join();
+    if (eof) {
+      if (consumed == 0) { if (rest) fprintf(stderr, "truncated BGZF block at the end of %s\n", o.bamfile.c_str()); break; }
+      memmove(buf[cb], buf[cb] + consumed, rest); have = rest;
+    } else {
+      if (rest > CARRY) { fprintf(stderr, "internal: carry buffer too small\n"); break; }
+      memcpy(buf[nb] + CARRY - rest, buf[cb] + consumed, rest);
+      // the next buffer's valid bytes start at CARRY - rest
+      if (next_got < CHUNK) eof = true;
+      have = rest + next_got;
+      if (CARRY - rest) memmove(buf[nb], buf[nb] + CARRY - rest, have);
+      cb = nb;
+    }
+  }
+  finish_cur();
+  if (!stop && rsigpu_bam_end(dec)) fprintf(stderr, "%s\n", rsigpu_last_error(dec));
+  for (auto& w : workers) if (w.joinable()) w.join();
+  fclose(f);
+  for (int k = 0; k < 2; ++k) rsigpu_pinned_free(buf[k]);
+  rsigpu_destroy(dec);
+  if (timing) fprintf(stderr, "#timing: setup %.3f s, decode loop %.3f s (bam_feed %.3f, take+fasta+begin %.3f of which waiting for the GPU %.3f)\n", t_loop - t_start, now_s() - t_loop, t_feed, t_take, t_wait);
+  return 0;
 }
 
 void write_table(const Opt& o, const std::vector<ContigResult>& all) {
@@ -261,6 +398,9 @@ int main(int argc, char** argv) {
     fprintf(stderr, "#processing %s\n", o.chr.c_str());
     results[0].done = run_contig(ctx[0], o, o.chr, 0, fasta, &rd, nullptr, &results[0]);
     if (!results[0].done) fprintf(stderr, "%s\n", results[0].err.c_str());
+  } else if (!o.hostdecode) {
+    const int rc = bam_on_gpu(o, ctx, &results);
+    if (rc) return rc;
   } else {
     BamReader br(o.threads);
     if (!br.open(o.bamfile, &err)) { fprintf(stderr, "%s\n", err.c_str()); return 0; }

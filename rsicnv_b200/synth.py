@@ -298,84 +298,110 @@ def make_reads(L: int, seed: int, fasta: np.ndarray | None = None, coverage: flo
     return reads, events
 
 
+def _bam_records(R: dict, tid: int, lo: int, hi: int, random_seq):
+    """records lo..hi of one contig's reads as BAM bytes (bam1_core_t layout, bam.h:131-155)"""
+    nr = hi - lo
+    co_all = R["cigar_off"].astype(np.int64); qo_all = R["qual_off"].astype(np.int64)
+    co = co_all[lo:hi]; ncig = co_all[lo + 1:hi + 1] - co; qo = qo_all[lo:hi]; lq = qo_all[lo + 1:hi + 1] - qo
+    lname = 2  # "r\0"
+    size = 32 + lname + 4 * ncig + (lq + 1) // 2 + lq   # block_size payload (without the 4-byte length)
+    offs = np.concatenate(([0], np.cumsum(size + 4)))
+    buf = np.zeros(int(offs[-1]), np.uint8)
+    o = offs[:-1]
+
+    def put32(off, val):
+        v = np.ascontiguousarray(np.asarray(val).astype("<u4")).view(np.uint8).reshape(-1, 4)
+        for k in range(4):
+            buf[o + off + k] = v[:, k]
+    pos = R["pos"][lo:hi].astype(np.int64)
+    # reg2bin needs the alignment end: sum of M/D/N lengths
+    cig = R["cigar"][int(co_all[lo]):int(co_all[hi])]
+    cl = (cig >> 4).astype(np.int64); cop = cig & 15
+    refl = np.where((cop == 0) | (cop == 2) | (cop == 3), cl, 0)
+    csum = np.concatenate(([0], np.cumsum(refl)))
+    c0 = co - co_all[lo]
+    end = pos + (csum[c0 + ncig] - csum[c0])
+    b = _reg2bin(pos, np.maximum(end, pos + 1))
+    put32(0, size)
+    put32(4, np.full(nr, tid)); put32(8, R["pos"][lo:hi])
+    put32(12, (b.astype(np.uint32) << 16) | (R["mapq"][lo:hi].astype(np.uint32) << 8) | lname)
+    put32(16, (R["flag"][lo:hi].astype(np.uint32) << 16) | ncig.astype(np.uint32))
+    put32(20, lq); put32(24, R["mtid"][lo:hi]); put32(28, R["mpos"][lo:hi]); put32(32, R["isize"][lo:hi])
+    buf[o + 36] = ord("r")
+    for k in range(int(ncig.max()) if nr else 0):
+        sel = np.flatnonzero(ncig > k)
+        v = np.ascontiguousarray(cig[c0[sel] + k].astype("<u4")).view(np.uint8).reshape(-1, 4)
+        for bb in range(4):
+            buf[o[sel] + 38 + 4 * k + bb] = v[:, bb]
+    # packed sequence (all 'A' = 1, or random bases) and qualities
+    soff = o + 38 + 4 * ncig
+    nseq = (lq + 1) // 2
+    nib = np.array([1, 2, 4, 8], np.uint8)
+    rs = np.random.default_rng([random_seq, tid, lo]) if random_seq is not None else None
+    qual = R["qual"][int(qo_all[lo]):int(qo_all[hi])]
+    if nr and np.all(lq == lq[0]):
+        l0 = int(lq[0]); ns0 = int(nseq[0])
+        ii = (soff[:, None] + np.arange(ns0)[None, :]).ravel()
+        if rs is None:
+            buf[ii] = 0x11
+        else:
+            buf[ii] = (nib[rs.integers(0, 4, len(ii))] << 4) | nib[rs.integers(0, 4, len(ii))]
+        if l0 % 2:
+            buf[soff + ns0 - 1] &= 0xf0
+        qi = (soff[:, None] + ns0 + np.arange(l0)[None, :]).ravel()
+        buf[qi] = qual
+    else:
+        q0 = qo - qo_all[lo]
+        for r in range(nr):
+            if rs is None:
+                buf[soff[r]:soff[r] + nseq[r]] = 0x11
+            else:
+                buf[soff[r]:soff[r] + nseq[r]] = (nib[rs.integers(0, 4, int(nseq[r]))] << 4) | nib[rs.integers(0, 4, int(nseq[r]))]
+            if lq[r] % 2:
+                buf[soff[r] + nseq[r] - 1] &= 0xf0
+            buf[soff[r] + nseq[r]:soff[r] + nseq[r] + lq[r]] = qual[q0[r]:q0[r] + lq[r]]
+    return buf.tobytes()
+
+
 def write_bam(path: str, contigs: list[tuple[str, int]], reads_by_tid: dict[int, dict], level: int = 1, strategy: int = 0,
-              block_size: int = 65280, random_seq: int | None = None) -> None:
+              block_size: int = 65280, random_seq: int | None = None, threads: int = 8) -> None:
     """Minimal BAM (BGZF) writer for the synthetic reads: one record per read, name 'r', sequence all 'A'
     (the path never looks at bases; random_seq=SEED writes random bases instead, which makes the file compress like a
     real one), qualities as given.  strategy: zlib strategy (zlib.Z_FIXED forces fixed-Huffman blocks), level 0 writes
-    stored blocks; records are NOT aligned to BGZF blocks.  Layout: SURVEY.md Appendix B."""
+    stored blocks; records are NOT aligned to BGZF blocks.  Reads are serialised in slabs and the blocks compressed on a
+    thread pool, so a chr19-sized file takes about a minute.  Layout: SURVEY.md Appendix B."""
     import struct
     import zlib
+    from concurrent.futures import ThreadPoolExecutor
     text = "@HD\tVN:1.0\tSO:coordinate\n" + "".join(f"@SQ\tSN:{n}\tLN:{l}\n" for n, l in contigs)
     hdr = bytearray(b"BAM\x01") + struct.pack("<i", len(text)) + text.encode() + struct.pack("<i", len(contigs))
     for n, l in contigs:
         hdr += struct.pack("<i", len(n) + 1) + n.encode() + b"\x00" + struct.pack("<i", l)
-    chunks = [bytes(hdr)]
-    for tid in sorted(reads_by_tid):
-        R = reads_by_tid[tid]
-        nr = len(R["pos"])
-        ncig = np.diff(R["cigar_off"].astype(np.int64)); lq = np.diff(R["qual_off"].astype(np.int64))
-        lname = 2  # "r\0"
-        size = 32 + lname + 4 * ncig + (lq + 1) // 2 + lq   # block_size payload (without the 4-byte length)
-        offs = np.concatenate(([0], np.cumsum(size + 4)))
-        buf = np.zeros(int(offs[-1]), np.uint8)
-        o = offs[:-1]
 
-        def put32(off, val):
-            v = np.ascontiguousarray(np.asarray(val).astype("<u4")).view(np.uint8).reshape(-1, 4)
-            for k in range(4):
-                buf[o + off + k] = v[:, k]
-        pos = R["pos"].astype(np.int64)
-        # reg2bin needs the alignment end: sum of M/D/N lengths
-        cl = (R["cigar"] >> 4).astype(np.int64); cop = R["cigar"] & 15
-        refl = np.where((cop == 0) | (cop == 2) | (cop == 3), cl, 0)
-        csum = np.concatenate(([0], np.cumsum(refl)))
-        end = pos + (csum[R["cigar_off"][1:].astype(np.int64)] - csum[R["cigar_off"][:-1].astype(np.int64)])
-        b = _reg2bin(pos, np.maximum(end, pos + 1))
-        put32(0, size)
-        put32(4, np.full(nr, tid)); put32(8, R["pos"])
-        put32(12, (b.astype(np.uint32) << 16) | (R["mapq"].astype(np.uint32) << 8) | lname)
-        put32(16, (R["flag"].astype(np.uint32) << 16) | ncig.astype(np.uint32))
-        put32(20, lq); put32(24, R["mtid"]); put32(28, R["mpos"]); put32(32, R["isize"])
-        buf[o + 36] = ord("r")
-        # cigar ops
-        co = R["cigar_off"].astype(np.int64)
-        for k in range(int(ncig.max()) if nr else 0):
-            sel = np.flatnonzero(ncig > k)
-            v = np.ascontiguousarray(R["cigar"][co[sel] + k].astype("<u4")).view(np.uint8).reshape(-1, 4)
-            for bb in range(4):
-                buf[o[sel] + 38 + 4 * k + bb] = v[:, bb]
-        # packed sequence (all 'A' = 1) and qualities
-        soff = o + 38 + 4 * ncig
-        nseq = (lq + 1) // 2
-        if nr and np.all(lq == lq[0]):
-            l0 = int(lq[0]); ns0 = int(nseq[0])
-            ii = (soff[:, None] + np.arange(ns0)[None, :]).ravel()
-            if random_seq is None:
-                buf[ii] = 0x11
-            else:
-                nib = np.array([1, 2, 4, 8], np.uint8)
-                rs = np.random.default_rng(random_seq + tid)
-                buf[ii] = (nib[rs.integers(0, 4, len(ii))] << 4) | nib[rs.integers(0, 4, len(ii))]
-            if l0 % 2:
-                buf[soff + ns0 - 1] &= 0xf0
-            qi = (soff[:, None] + ns0 + np.arange(l0)[None, :]).ravel()
-            buf[qi] = R["qual"]
-        else:
-            qo = R["qual_off"].astype(np.int64)
-            for r in range(nr):
-                buf[soff[r]:soff[r] + nseq[r]] = 0x11
-                buf[soff[r] + nseq[r]:soff[r] + nseq[r] + lq[r]] = R["qual"][qo[r]:qo[r + 1]]
-        chunks.append(buf.tobytes())
-    data = b"".join(chunks)
-    with open(path, "wb") as f:
-        BS = block_size
-        for a in range(0, len(data), BS):
-            blk = data[a:a + BS]
-            co = zlib.compressobj(level, zlib.DEFLATED, -15, 8, strategy)
-            comp = co.compress(blk) + co.flush()
-            f.write(b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(comp) + 25) + comp +
-                    struct.pack("<II", zlib.crc32(blk) & 0xffffffff, len(blk)))
+    def pieces():
+        yield bytes(hdr)
+        for tid in sorted(reads_by_tid):
+            R = reads_by_tid[tid]
+            nr = len(R["pos"])
+            for lo in range(0, nr, 1 << 19):
+                yield _bam_records(R, tid, lo, min(nr, lo + (1 << 19)), random_seq)
+
+    def bgzf(blk: bytes) -> bytes:
+        co = zlib.compressobj(level, zlib.DEFLATED, -15, 8, strategy)
+        comp = co.compress(blk) + co.flush()
+        return (b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(comp) + 25) + comp +
+                struct.pack("<II", zlib.crc32(blk) & 0xffffffff, len(blk)))
+    BS = block_size
+    with open(path, "wb") as f, ThreadPoolExecutor(threads) as pool:
+        carry = b""
+        for piece in pieces():
+            data = carry + piece
+            nfull = len(data) // BS * BS
+            for out in pool.map(bgzf, (data[a:a + BS] for a in range(0, nfull, BS))):
+                f.write(out)
+            carry = data[nfull:]
+        if carry:
+            f.write(bgzf(carry))
         f.write(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
 
 

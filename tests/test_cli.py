@@ -66,6 +66,10 @@ def test_cli_bam_two_contigs_matches_reference(cli, tmp_path):
     assert out.returncode == 0, out.stderr
     assert _table(str(tmp_path / "ours.txt")) == _table(str(tmp_path / "ref.txt"))
     assert len(_table(str(tmp_path / "ours.txt"))) > 6
+    # the host decoder (zlib on threads) instead of the GPU one: same table
+    out = subprocess.run([cli] + common + ["-hostdecode", "-o", str(tmp_path / "ours_h.txt")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert _table(str(tmp_path / "ours_h.txt")) == _table(str(tmp_path / "ref.txt"))
     # one chromosome only, other knobs
     common = ["rsi", "-b", bam, "-f", fasta, "-c", "2", "-m", "51", "-NOGC", "-MED", "-np"]
     subprocess.run([REF_BIN] + common + ["-o", str(tmp_path / "ref2.txt")], check=True, capture_output=True)

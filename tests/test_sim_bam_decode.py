@@ -190,3 +190,41 @@ def test_decoded_reads_give_the_same_calls(sim_lib, tmp_path):
     for x, y in zip(got, want):
         assert bytes(x) == bytes(y)
     a.close(); b.close()
+
+
+def _rebgzf(src, dst, compress_block, bs=60000):
+    """re-block a BGZF file: same decoded stream, each block's deflate stream produced by compress_block(bytes)"""
+    import struct
+    data = open(src, "rb").read()
+    dec = b""; off = 0
+    while off < len(data):
+        bsize = struct.unpack_from("<H", data, off + 16)[0] + 1
+        dec += zlib.decompress(data[off + 18:off + bsize - 8], -15)
+        off += bsize
+    with open(dst, "wb") as f:
+        for a in range(0, len(dec), bs):
+            blk = dec[a:a + bs]
+            comp = compress_block(blk)
+            f.write(b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(comp) + 25) + comp +
+                    struct.pack("<II", zlib.crc32(blk) & 0xffffffff, len(blk)))
+        f.write(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
+
+
+def test_mixed_block_types_inside_one_stream(sim_lib, tmp_path):
+    """deflate streams that switch between dynamic, stored (also empty, from a flush) and fixed blocks inside one BGZF block"""
+    fa, reads = make_reads(50000, 51, cov=10)
+    src = str(tmp_path / "a.bam"); dst = str(tmp_path / "b.bam")
+    synth.write_bam(src, [("19", 50000)], {0: reads}, level=6, random_seq=2)
+
+    def comp(blk):
+        out = b""
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        n = len(blk)
+        out += co.compress(blk[:n // 5]) + co.flush(zlib.Z_FULL_FLUSH)       # dynamic block + empty stored block
+        out += co.compress(blk[n // 5:n // 3]) + co.flush(zlib.Z_SYNC_FLUSH)
+        out += co.compress(blk[n // 3:n // 3 + 7]) + co.flush(zlib.Z_FULL_FLUSH)   # a tiny (fixed-Huffman) block
+        out += co.compress(blk[n // 3 + 7:]) + co.flush()
+        return out
+    _rebgzf(src, dst, comp)
+    got, h = decode_file(sim_lib, dst, 100000)
+    assert_same_reads(got[0], reads)
