@@ -22,23 +22,24 @@
 namespace rsigpu {
 
 enum {
-  INF_NT = 32,                     // threads per CTA: one warp, one BGZF block per thread
-  INF_FB = 9, INF_DB = 6,          // bits of the direct-lookup tables (literal/length, distance)
-  INF_LF = 0,                      // per-thread table layout, in u16 slots
+  INF_NT = 128,                    // threads per CTA, one BGZF block per thread
+  INF_FB = 10, INF_DB = 7,         // bits of the direct-lookup tables (literal/length, distance)
+  INF_LF = 0,                      // per-thread table layout in GLOBAL memory, in u16 slots
   INF_LS = INF_LF + (1 << INF_FB), // literal/length symbols ordered by code
   INF_DF = INF_LS + 288,
   INF_DS = INF_DF + (1 << INF_DB),
-  INF_LC = INF_DS + 32,            // code-length counts
-  INF_DC = INF_LC + 16,
-  INF_SLOTS = INF_DC + 16
+  INF_GSLOTS = INF_DS + 32,
+  INF_LC = 0, INF_DC = 16          // code-length counts: shared memory, 32 u16 per thread
 };
-#define RSI_SMEM_INFLATE ((size_t)INF_SLOTS * INF_NT * 2)
+// table scratch for n BGZF blocks (whole warps)
+#define RSI_INFLATE_TAB_BYTES(nblk) ((size_t)(((nblk) + 31) / 32) * 32 * INF_GSLOTS * 2)
 
 enum { BAM_HEAD = 16 << 20 };      // room in front of the decoded blocks for the partial record carried from the previous chunk
-enum { BAM_NONE = -1, BAM_TAIL = 0x7fffffff };
+#define BAM_NONE (-1ll)
+#define BAM_TAIL 0x7fffffffffffffffll
 enum { BAM_ERR_INFLATE = 1, BAM_ERR_RECORD = 2, BAM_ERR_RUNS = 4 };
 
-struct BgzfBlock { u32 src, src_len, dst, dst_len; };   // payload offset/length in the compressed chunk, offset/length in the decoded buffer
+struct BgzfBlock { u64 dst; u32 src, src_len, dst_len, pad_; };   // payload offset/length in the compressed chunk, offset/length in the decoded buffer
 
 struct BitIn {
   const u8* base; u32 pos, end;   // word-aligned base, next byte to load, one past the payload (both relative to base)
@@ -57,42 +58,47 @@ __device__ __forceinline__ void bits_refill(BitIn& b) {
 }
 __device__ __forceinline__ u32 bits_take(BitIn& b, int n) { const u32 v = (u32)(b.buf & ((1ull << n) - 1)); b.buf >>= n; b.cnt -= n; return v; }
 
-// per-thread Huffman tables in shared memory, slot i of lane l at sm[i * 32 + l]
-#define INF_T(i) sm[(i) * INF_NT + lane]
+// Per-thread Huffman tables.  The big ones (direct-lookup tables, symbols by code) live in global memory and stay in L2:
+// at 2.7 KB per thread, shared memory would hold three warps per SM, and one thread's decode loop is a chain of dependent
+// loads that only many resident warps can hide.  Slot i of lane l is at g[i * 32 + l] (a warp's tables are interleaved, so
+// the construction loops -- same i in every lane -- are coalesced).  The 2 x 16 code-length counts sit in shared memory.
+struct InfTabs { u16* g; u16* s; int lane, stid; };
+#define INF_G(i) T.g[(size_t)(i) * 32 + T.lane]
+#define INF_C(i) T.s[(i) * INF_NT + T.stid]
 
 // canonical code from code lengths (count/symbol form, plus a direct table for codes of <= fb bits whose
 // entries are symbol << 4 | length).  Returns < 0 for an over-subscribed set, > 0 for an incomplete one.
-__device__ int inf_construct(u16* sm, int lane, const u8* lens, int n, int fast, int fb, int cnts, int syms) {
-  for (int l = 0; l < 16; ++l) INF_T(cnts + l) = 0;
-  for (int s = 0; s < n; ++s) INF_T(cnts + lens[s]) += 1;
-  for (int i = 0; i < (1 << fb); ++i) INF_T(fast + i) = 0;
-  if (INF_T(cnts) == n) return 0;
+__device__ int inf_construct(const InfTabs& T, const u8* lens, int n, int fast, int fb, int cnts, int syms) {
+  for (int l = 0; l < 16; ++l) INF_C(cnts + l) = 0;
+  for (int s = 0; s < n; ++s) INF_C(cnts + lens[s]) += 1;
+  for (int i = 0; i < (1 << fb); ++i) INF_G(fast + i) = 0;
+  if (INF_C(cnts) == n) return 0;
   int left = 1;
-  for (int l = 1; l <= 15; ++l) { left <<= 1; left -= (int)INF_T(cnts + l); if (left < 0) return left; }
+  for (int l = 1; l <= 15; ++l) { left <<= 1; left -= (int)INF_C(cnts + l); if (left < 0) return left; }
   u16 offs[16];
   offs[1] = 0;
-  for (int l = 1; l < 15; ++l) offs[l + 1] = (u16)(offs[l] + INF_T(cnts + l));
-  for (int s = 0; s < n; ++s) if (lens[s]) { INF_T(syms + offs[lens[s]]) = (u16)s; offs[lens[s]]++; }
+  for (int l = 1; l < 15; ++l) offs[l + 1] = (u16)(offs[l] + INF_C(cnts + l));
+  for (int s = 0; s < n; ++s) if (lens[s]) { INF_G(syms + offs[lens[s]]) = (u16)s; offs[lens[s]]++; }
   int code = 0, index = 0;
   for (int l = 1; l <= fb; ++l) {
-    const int cn = (int)INF_T(cnts + l);
+    const int cn = (int)INF_C(cnts + l);
     for (int j = 0; j < cn; ++j) {
       const u32 rev = __brev((u32)(code + j)) >> (32 - l);
-      const u16 e = (u16)((INF_T(syms + index + j) << 4) | l);
-      for (u32 k = rev; k < (1u << fb); k += (1u << l)) INF_T(fast + k) = e;
+      const u16 e = (u16)((INF_G(syms + index + j) << 4) | l);
+      for (u32 k = rev; k < (1u << fb); k += (1u << l)) INF_G(fast + k) = e;
     }
     index += cn; code = (code + cn) << 1;
   }
   return left;
 }
-__device__ __forceinline__ int inf_decode(BitIn& b, const u16* sm, int lane, int fast, int fb, int cnts, int syms) {
-  const u32 e = INF_T(fast + (u32)(b.buf & ((1u << fb) - 1)));
+__device__ __forceinline__ int inf_decode(BitIn& b, const InfTabs& T, int fast, int fb, int cnts, int syms) {
+  const u32 e = INF_G(fast + (u32)(b.buf & ((1u << fb) - 1)));
   if (e) { const int l = (int)(e & 15u); b.buf >>= l; b.cnt -= l; return (int)(e >> 4); }
   int code = 0, first = 0, index = 0; u64 bits = b.buf;
   for (int l = 1; l <= 15; ++l) {
     code |= (int)(bits & 1); bits >>= 1;
-    const int cn = (int)INF_T(cnts + l);
-    if (code - cn < first) { b.buf >>= l; b.cnt -= l; return (int)INF_T(syms + index + (code - first)); }
+    const int cn = (int)INF_C(cnts + l);
+    if (code - cn < first) { b.buf >>= l; b.cnt -= l; return (int)INF_G(syms + index + (code - first)); }
     index += cn; first += cn; first <<= 1; code <<= 1;
   }
   return -1;
@@ -111,7 +117,7 @@ enum { INF_HEADER = 0, INF_SYMS = 1, INF_DONE = 2 };
 
 __device__ __forceinline__ void inf_fail(InfState& S, int rc) { S.rc = rc; S.phase = INF_DONE; }
 
-__device__ void inf_block_header(InfState& S, u16* sm, int lane) {
+__device__ void inf_block_header(InfState& S, const InfTabs& T) {
   BitIn& b = S.b;
   bits_refill(b);
   S.last = (int)bits_take(b, 1);
@@ -137,9 +143,9 @@ __device__ void inf_block_header(InfState& S, u16* sm, int lane) {
     for (int s = 144; s < 256; ++s) lens[s] = 9;
     for (int s = 256; s < 280; ++s) lens[s] = 7;
     for (int s = 280; s < 288; ++s) lens[s] = 8;
-    inf_construct(sm, lane, lens, 288, INF_LF, INF_FB, INF_LC, INF_LS);
+    inf_construct(T, lens, 288, INF_LF, INF_FB, INF_LC, INF_LS);
     for (int s = 0; s < 30; ++s) lens[s] = 5;
-    inf_construct(sm, lane, lens, 30, INF_DF, INF_DB, INF_DC, INF_DS);
+    inf_construct(T, lens, 30, INF_DF, INF_DB, INF_DC, INF_DS);
   } else {
     bits_refill(b);
     const int nlen = (int)bits_take(b, 5) + 257, ndist = (int)bits_take(b, 5) + 1, ncode = (int)bits_take(b, 4) + 4;
@@ -147,11 +153,11 @@ __device__ void inf_block_header(InfState& S, u16* sm, int lane) {
     const u8 order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
     for (int i = 0; i < 19; ++i) lens[i] = 0;
     for (int i = 0; i < ncode; ++i) { bits_refill(b); lens[order[i]] = (u8)bits_take(b, 3); }
-    if (inf_construct(sm, lane, lens, 19, INF_LF, 7, INF_LC, INF_LS) != 0) return inf_fail(S, 6);   // the code-length code must be complete
+    if (inf_construct(T, lens, 19, INF_LF, 7, INF_LC, INF_LS) != 0) return inf_fail(S, 6);   // the code-length code must be complete
     int idx = 0;
     while (idx < nlen + ndist) {
       bits_refill(b);
-      const int sym = inf_decode(b, sm, lane, INF_LF, 7, INF_LC, INF_LS);
+      const int sym = inf_decode(b, T, INF_LF, 7, INF_LC, INF_LS);
       if (sym < 0) return inf_fail(S, 7);
       if (sym < 16) lens[idx++] = (u8)sym;
       else {
@@ -164,18 +170,18 @@ __device__ void inf_block_header(InfState& S, u16* sm, int lane) {
       }
     }
     if (lens[256] == 0) return inf_fail(S, 10);
-    int r = inf_construct(sm, lane, lens, nlen, INF_LF, INF_FB, INF_LC, INF_LS);
-    if (r < 0 || (r > 0 && nlen - (int)INF_T(INF_LC) != 1)) return inf_fail(S, 11);       // incomplete only allowed for a single code
-    r = inf_construct(sm, lane, lens + nlen, ndist, INF_DF, INF_DB, INF_DC, INF_DS);
-    if (r < 0 || (r > 0 && ndist - (int)INF_T(INF_DC) != 1)) return inf_fail(S, 12);
+    int r = inf_construct(T, lens, nlen, INF_LF, INF_FB, INF_LC, INF_LS);
+    if (r < 0 || (r > 0 && nlen - (int)INF_C(INF_LC) != 1)) return inf_fail(S, 11);       // incomplete only allowed for a single code
+    r = inf_construct(T, lens + nlen, ndist, INF_DF, INF_DB, INF_DC, INF_DS);
+    if (r < 0 || (r > 0 && ndist - (int)INF_C(INF_DC) != 1)) return inf_fail(S, 12);
   }
   S.phase = INF_SYMS;
 }
 
-__device__ __forceinline__ void inf_symbol(InfState& S, const u16* sm, int lane, const u16* tab) {
+__device__ __forceinline__ void inf_symbol(InfState& S, const InfTabs& T, const u16* tab) {
   BitIn& b = S.b;
   bits_refill(b);
-  int sym = inf_decode(b, sm, lane, INF_LF, INF_FB, INF_LC, INF_LS);
+  int sym = inf_decode(b, T, INF_LF, INF_FB, INF_LC, INF_LS);
   if (sym < 256) {
     if (sym < 0) return inf_fail(S, 13);
     if (S.o >= S.dst_len) return inf_fail(S, 3);
@@ -191,7 +197,7 @@ __device__ __forceinline__ void inf_symbol(InfState& S, const u16* sm, int lane,
   if (sym >= 29) return inf_fail(S, 14);
   const u32 len = (u32)tab[sym] + bits_take(b, (int)tab[29 + sym]);
   bits_refill(b);
-  const int ds = inf_decode(b, sm, lane, INF_DF, INF_DB, INF_DC, INF_DS);
+  const int ds = inf_decode(b, T, INF_DF, INF_DB, INF_DC, INF_DS);
   if (ds < 0 || ds >= 30) return inf_fail(S, 15);
   const u32 dist = (u32)tab[58 + ds] + bits_take(b, (int)tab[88 + ds]);
   if (dist > S.o) return inf_fail(S, 16);
@@ -202,10 +208,10 @@ __device__ __forceinline__ void inf_symbol(InfState& S, const u16* sm, int lane,
 }
 
 // inflate: one thread per BGZF block of the chunk, the warp re-converged after every step
-__global__ void __launch_bounds__(INF_NT) k_bgzf_inflate(const u8* __restrict__ comp, const BgzfBlock* __restrict__ blk, int nblk, u8* __restrict__ U, int* __restrict__ err) {
-  RSI_DYN_SMEM(smem);
-  u16* sm = reinterpret_cast<u16*>(smem);
+__global__ void __launch_bounds__(INF_NT) k_bgzf_inflate(const u8* __restrict__ comp, const BgzfBlock* __restrict__ blk, int nblk, u8* __restrict__ U,
+                                                         u16* __restrict__ tabs, int* __restrict__ err) {
   __shared__ u16 tab[120];
+  __shared__ u16 cnts[32 * INF_NT];
   {
     const u16 lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
     const u16 lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
@@ -215,8 +221,9 @@ __global__ void __launch_bounds__(INF_NT) k_bgzf_inflate(const u8* __restrict__ 
     for (int i = (int)threadIdx.x; i < 30; i += INF_NT) { tab[58 + i] = dbase[i]; tab[88 + i] = dext[i]; }
   }
   __syncthreads();
-  const int lane = (int)threadIdx.x;
-  const int k = (int)blockIdx.x * INF_NT + lane;
+  const int k = (int)blockIdx.x * INF_NT + (int)threadIdx.x;
+  InfTabs T; T.lane = (int)(threadIdx.x & 31); T.stid = (int)threadIdx.x; T.s = cnts;
+  T.g = tabs + (size_t)(k >> 5) * 32 * INF_GSLOTS;
   InfState S;
   S.phase = INF_DONE; S.rc = 0; S.o = 0; S.dst_len = 0; S.dst = U; S.last = 0;
   S.b.base = comp; S.b.pos = 0; S.b.end = 0; S.b.buf = 0; S.b.cnt = 0;
@@ -231,14 +238,14 @@ __global__ void __launch_bounds__(INF_NT) k_bgzf_inflate(const u8* __restrict__ 
     }
   }
   while (__any_sync(0xffffffffu, S.phase != INF_DONE)) {
-    // lanes that need a block header (table construction: long) go first and together; the others decode one symbol
-    if (__any_sync(0xffffffffu, S.phase == INF_HEADER)) { if (S.phase == INF_HEADER) inf_block_header(S, sm, lane); }
+    // lanes that need a block header (table construction: long) go first and together; the others decode symbols
+    if (__any_sync(0xffffffffu, S.phase == INF_HEADER)) { if (S.phase == INF_HEADER) inf_block_header(S, T); }
     else {
 #pragma unroll 1
-      for (int it = 0; it < 8; ++it) { if (S.phase == INF_SYMS) inf_symbol(S, sm, lane, tab); __syncwarp(); }
+      for (int it = 0; it < 8; ++it) { if (S.phase == INF_SYMS) inf_symbol(S, T, tab); __syncwarp(); }
     }
   }
-  if (S.rc) { atomicOr(err, (int)BAM_ERR_INFLATE); atomicMax(err + 1, S.rc); }
+  if (S.rc) { atomicOr(err + 1, (int)BAM_ERR_INFLATE); atomicMax(err + 2, S.rc); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -247,20 +254,20 @@ __device__ __forceinline__ u32 ld32u(const u8* p) { return (u32)p[0] | ((u32)p[1
 
 struct BamChunk {
   const u8* U;          // decoded stream of this chunk; valid bytes [u_begin, u_end)
-  int u_begin, u_end;   // u_begin = start of the first record (a carried partial record lies in front of BAM_HEAD)
-  const int* bound;     // nblk + 1 boundaries of the decoded BGZF blocks in U (bound[0] may be > u_begin)
+  i64 u_begin, u_end;   // u_begin = start of the first record (a carried partial record lies in front of BAM_HEAD)
+  const i64* bound;     // nblk + 1 boundaries of the decoded BGZF blocks in U (bound[0] may be > u_begin)
   int nblk, n_ref;
 };
 struct BamChain {       // per BGZF block
-  int* first;           // first record start inside the block (BAM_NONE: none)
-  int* endp;            // where the walk from `first` stops: first record start at or after the block's end, BAM_TAIL if the walk met the chunk's incomplete last record
-  int* tailp;           // start of that incomplete record (valid when endp == BAM_TAIL)
+  i64* first;           // first record start inside the block (BAM_NONE: none)
+  i64* endp;            // where the walk from `first` stops: first record start at or after the block's end, BAM_TAIL if the walk met the chunk's incomplete last record
+  i64* tailp;           // start of that incomplete record (valid when endp == BAM_TAIL)
   int* cnt; int* ncig; i64* nq;   // records started in the block, their CIGAR ops and quality bytes
 };
 
 // bam1_core_t sanity (bam.h:131-155): used to GUESS a record start, and as the corruption check of the walk
-__device__ bool bam_core_ok(const BamChunk& C, int p, int* next) {
-  if ((i64)p + 36 > (i64)C.u_end) return false;
+__device__ bool bam_core_ok(const BamChunk& C, i64 p, i64* next) {
+  if (p + 36 > C.u_end) return false;
   const u8* r = C.U + p;
   const u32 bs = ld32u(r);
   if (bs < 32u || bs > (1u << 28)) return false;
@@ -272,72 +279,56 @@ __device__ bool bam_core_ok(const BamChunk& C, int p, int* next) {
   if (l_name < 1u || l_seq < 0 || mtid < -1 || mtid >= C.n_ref || mpos < -1) return false;
   const u64 need = 32ull + l_name + 4ull * n_cig + ((u64)l_seq + 1) / 2 + (u64)l_seq;
   if (need > (u64)bs) return false;
-  if ((i64)p + 36 + (i64)l_name <= (i64)C.u_end && r[36 + l_name - 1] != 0) return false;
-  *next = p + 4 + (int)bs;
+  if (p + 36 + (i64)l_name <= C.u_end && r[36 + l_name - 1] != 0) return false;
+  *next = p + 4 + (i64)bs;
   return true;
 }
 
-// walk the record list from p while records START before `stop`
-__device__ void bam_walk(const BamChunk& C, int p, int stop, int k, const BamChain& H, int* err) {
-  int cnt = 0, ncig = 0; i64 nq = 0; int endp = 0, tailp = 0;
+// walk the record list from p while records START before `stop`; false if a record fails the core check (a wrong start,
+// or a corrupt file).  The per-block results are written either way.
+__device__ bool bam_walk(const BamChunk& C, i64 p, i64 stop, int k, const BamChain& H) {
+  int cnt = 0, ncig = 0; i64 nq = 0, endp = 0, tailp = 0; bool clean = true;
   for (;;) {
     if (p >= stop) { endp = p; break; }
-    if ((i64)p + 4 > (i64)C.u_end) { endp = BAM_TAIL; tailp = p; break; }
-    const u32 bs = ld32u(C.U + p);
-    if ((i64)p + 4 + (i64)bs > (i64)C.u_end) { endp = BAM_TAIL; tailp = p; break; }
-    int nx;
-    if (!bam_core_ok(C, p, &nx)) { if (err) atomicOr(err, (int)BAM_ERR_RECORD); endp = BAM_TAIL; tailp = p; break; }
+    if (p + 4 > C.u_end) { endp = BAM_TAIL; tailp = p; break; }                       // the chunk ends inside the length field
+    if (p + 36 > C.u_end) {                                                           // ... inside the fixed-size core
+      const u32 bs = ld32u(C.U + p);
+      clean = bs >= 32u && bs <= (1u << 28);
+      endp = BAM_TAIL; tailp = p; break;
+    }
+    i64 nx;
+    if (!bam_core_ok(C, p, &nx)) { clean = false; endp = BAM_TAIL; tailp = p; break; }
+    if (nx > C.u_end) { endp = BAM_TAIL; tailp = p; break; }                          // ... inside the record: carried to the next chunk
     ++cnt; ncig += (int)((u32)C.U[p + 16] | ((u32)C.U[p + 17] << 8)); nq += (i64)(int)ld32u(C.U + p + 20);
     p = nx;
   }
   H.endp[k] = endp; H.tailp[k] = tailp; H.cnt[k] = cnt; H.ncig[k] = ncig; H.nq[k] = nq;
+  return clean;
 }
+__device__ __forceinline__ void bam_no_start(int k, const BamChain& H) { H.first[k] = BAM_NONE; H.endp[k] = BAM_NONE; H.tailp[k] = 0; H.cnt[k] = 0; H.ncig[k] = 0; H.nq[k] = 0; }
 
-// extra evidence for a GUESSED start (never applied to proven records): printable read name, CIGAR op codes <= 8 whose
-// query-consuming lengths add up to l_seq (SAM spec), and the next two records pass the core check as well
-__device__ bool bam_guess_ok(const BamChunk& C, int p) {
-  int nx;
-  if (!bam_core_ok(C, p, &nx)) return false;
-  const u8* r = C.U + p;
-  const u32 l_name = r[12], n_cig = (u32)r[16] | ((u32)r[17] << 8);
-  const int l_seq = (int)ld32u(r + 20);
-  if ((i64)p + 36 + (i64)l_name + 4ll * n_cig <= (i64)C.u_end) {
-    for (u32 k = 0; k + 1 < l_name; ++k) { const u8 ch = r[36 + k]; if (ch < 33 || ch > 126) return false; }
-    if (n_cig > 0 && n_cig <= 64) {
-      i64 q = 0;
-      for (u32 k = 0; k < n_cig; ++k) {
-        const u32 c = ld32u(r + 36 + l_name + 4 * k), op = c & 15u;
-        if (op > 8u) return false;
-        if (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) q += (i64)(c >> 4);
-      }
-      if (l_seq > 0 && q != (i64)l_seq) return false;
-    }
-  }
-  int n2, n3;
-  if ((i64)nx + 36 <= (i64)C.u_end) {
-    if (!bam_core_ok(C, nx, &n2)) return false;
-    if ((i64)n2 + 36 <= (i64)C.u_end && !bam_core_ok(C, n2, &n3)) return false;
-  }
-  return true;
-}
-
+// Guess: the first position of the block that passes the core check AND from which the list walks cleanly to the end of
+// the block (a few hundred records) -- wrong guesses that survive this are practically impossible, and k_bam_verify does
+// not depend on it.
 __global__ void k_bam_chain(BamChunk C, BamChain H) {
   for (int k = (int)(blockIdx.x * blockDim.x + threadIdx.x); k < C.nblk; k += (int)(gridDim.x * blockDim.x)) {
-    const int ub = C.bound[k], ue = C.bound[k + 1];
-    int g = BAM_NONE;
-    if (k == 0) { if (C.u_begin < ue) g = C.u_begin; }
+    const i64 ub = C.bound[k], ue = C.bound[k + 1];
+    bool found = false;
+    if (k == 0) { if (C.u_begin < ue) { H.first[k] = C.u_begin; bam_walk(C, C.u_begin, ue, k, H); found = true; } }
     else {
-      for (int p = ub; p < ue; ++p) if (bam_guess_ok(C, p)) { g = p; break; }
+      for (i64 p = ub; p < ue && !found; ++p) {
+        i64 nx;
+        if (!bam_core_ok(C, p, &nx)) continue;
+        if (bam_walk(C, p, ue, k, H)) { H.first[k] = p; found = true; }
+      }
     }
-    H.first[k] = g;
-    if (g == BAM_NONE) { H.endp[k] = BAM_NONE; H.tailp[k] = 0; H.cnt[k] = 0; H.ncig[k] = 0; H.nq[k] = 0; }
-    else bam_walk(C, g, ue, k, H, nullptr);     // a walk from a wrong guess may meet garbage: not an error
+    if (!found) bam_no_start(k, H);
   }
 }
 
-// info: [0] n records, [1] n cigar ops, [2..3] n quality bytes (i64), [4] tail start, [5] re-walked blocks, [6] n runs
-__global__ void __launch_bounds__(1024) k_bam_verify(BamChunk C, BamChain H, int* __restrict__ in_pos, int* __restrict__ rbase, int* __restrict__ cbase,
-                                                     i64* __restrict__ qbase, int* __restrict__ info, int* __restrict__ err) {
+// info (i64): [0] n records, [1] n cigar ops, [2] n quality bytes, [3] tail start, [4] repaired blocks.  cnt32: [0] n runs, [1] error bits, [2] inflate code
+__global__ void __launch_bounds__(1024) k_bam_verify(BamChunk C, BamChain H, i64* __restrict__ in_pos, int* __restrict__ rbase, int* __restrict__ cbase,
+                                                     i64* __restrict__ qbase, i64* __restrict__ info, int* __restrict__ err) {
   RSI_CTA_SETUP(c);
   const int n = C.nblk;
   const int per = (n + c.nthr - 1) / c.nthr;
@@ -346,45 +337,49 @@ __global__ void __launch_bounds__(1024) k_bam_verify(BamChunk C, BamChain H, int
   int fixed = 0;
   for (;;) {
     // in_pos[k] = position the list has reached when block k begins (exclusive max-scan of the walk ends)
-    int loc = -1;
-    for (int k = k0; k < k1; ++k) if (H.first[k] != BAM_NONE) loc = imax(loc, H.endp[k]);
-    int v = loc;
-    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v = imax(v, u); }
-    int* slots = reinterpret_cast<int*>(c.red);
+    i64 loc = -1;
+    for (int k = k0; k < k1; ++k) if (H.first[k] != BAM_NONE) loc = lmax(loc, H.endp[k]);
+    i64 v = loc;
+    for (int o = 1; o < 32; o <<= 1) { const i64 u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v = lmax(v, u); }
+    i64* slots = reinterpret_cast<i64*>(c.red);
     c.sync(); if (lane == 31) slots[warp] = v; c.sync();
-    int pre = C.u_begin; for (int w = 0; w < warp; ++w) pre = imax(pre, slots[w]);
-    const int up = __shfl_up_sync(0xffffffffu, v, 1);
-    int run = imax(pre, lane ? up : -1);
-    int bad = 0x7fffffff;
+    i64 pre = C.u_begin; for (int w = 0; w < warp; ++w) pre = lmax(pre, slots[w]);
+    const i64 up = __shfl_up_sync(0xffffffffu, v, 1);
+    i64 run = lmax(pre, lane ? up : -1);
+    int bad = 0;
     for (int k = k0; k < k1; ++k) {
       in_pos[k] = run;
-      const int ue = C.bound[k + 1], g = H.first[k];
+      const i64 ue = C.bound[k + 1], g = H.first[k];
       const bool ok = (run >= ue) ? (g == BAM_NONE) : (g == run);
-      if (!ok && bad == 0x7fffffff) bad = k;
-      if (g != BAM_NONE) run = imax(run, H.endp[k]);
+      if (!ok) bad = 1;
+      if (g != BAM_NONE) run = lmax(run, H.endp[k]);
     }
     c.sync();
-    const int firstbad = c.reduce(bad, MinOp());
-    if (firstbad == 0x7fffffff) break;
-    // Everything before the first mismatch is proven, so ITS position is the true one.  Mismatches further on are almost
-    // always isolated wrong guesses whose incoming position is already right: every thread repairs the mismatches of its
-    // own range from in_pos; the next round proves or refutes them (at least the first one is settled per round).
+    if (!c.reduce(bad, MaxOp())) break;
+    // Everything before the first mismatch is proven, so ITS incoming position is the true one.  Mismatches further on are
+    // almost always isolated (the guess skipped a record the core check rejects, the walks merge again): every thread
+    // repairs the mismatches of its own range from in_pos; the next round proves or refutes them, and at least the first
+    // one is settled per round.
     for (int k = k0; k < k1; ++k) {
-      const int ue = C.bound[k + 1], g = H.first[k], cur = in_pos[k];
+      const i64 ue = C.bound[k + 1], g = H.first[k], cur = in_pos[k];
       const bool ok = (cur >= ue) ? (g == BAM_NONE) : (g == cur);
       if (ok) continue;
-      if (cur >= ue) { H.first[k] = BAM_NONE; H.endp[k] = BAM_NONE; H.cnt[k] = 0; H.ncig[k] = 0; H.nq[k] = 0; }
-      else { H.first[k] = cur; bam_walk(C, cur, ue, k, H, nullptr); }
+      if (cur >= ue) bam_no_start(k, H);
+      else { H.first[k] = cur; bam_walk(C, cur, ue, k, H); }
       ++fixed;
     }
     c.sync();
   }
   fixed = c.reduce(fixed, SumOp());
-  // all starts proven: corruption inside a proven walk is a real error
-  int tail = -1, maxend = C.u_begin, e = 0;
+  // all starts proven: a record that fails the core check inside a proven walk is a corrupt file
+  i64 tail = -1, maxend = C.u_begin; int e = 0;
   for (int k = k0; k < k1; ++k) if (H.first[k] != BAM_NONE) {
-    if (H.endp[k] == BAM_TAIL) { tail = H.tailp[k]; int nx; if ((i64)tail + 36 <= (i64)C.u_end && !bam_core_ok(C, tail, &nx)) e = 1; }
-    else maxend = imax(maxend, H.endp[k]);
+    if (H.endp[k] == BAM_TAIL) {
+      tail = H.tailp[k];
+      i64 nx;
+      if (tail + 36 <= C.u_end) { if (!bam_core_ok(C, tail, &nx) || nx <= C.u_end) e = 1; }      // complete but invalid: the walk stopped on it
+      else if (tail + 4 <= C.u_end) { const u32 bs = ld32u(C.U + tail); if (bs < 32u || bs > (1u << 28)) e = 1; }
+    } else maxend = lmax(maxend, H.endp[k]);
   }
   tail = c.reduce(tail, MaxOp()); maxend = c.reduce(maxend, MaxOp()); e = c.reduce(e, MaxOp());
   // exclusive sums -> where each block's records go
@@ -394,23 +389,23 @@ __global__ void __launch_bounds__(1024) k_bam_verify(BamChunk C, BamChain H, int
   int bc = c.scan_excl(lc, &tc), bg = c.scan_excl(lg, &tg); i64 bq = c.scan_excl(lq, &tq);
   for (int k = k0; k < k1; ++k) { rbase[k] = bc; cbase[k] = bg; qbase[k] = bq; bc += H.cnt[k]; bg += H.ncig[k]; bq += H.nq[k]; }
   if (c.tid == 0) {
-    info[0] = tc; info[1] = tg; *reinterpret_cast<i64*>(info + 2) = tq;
-    info[4] = tail >= 0 ? tail : maxend; info[5] = fixed; info[6] = 0;
-    if (e) atomicOr(err, (int)BAM_ERR_RECORD);
-    if (tail < 0 && maxend != C.u_end && !(n == 0)) atomicOr(err, (int)BAM_ERR_RECORD);
+    info[0] = tc; info[1] = tg; info[2] = tq;
+    info[3] = tail >= 0 ? tail : maxend; info[4] = fixed;
+    if (e) atomicOr(err + 1, (int)BAM_ERR_RECORD);
+    if (tail < 0 && maxend != C.u_end && n != 0) atomicOr(err + 1, (int)BAM_ERR_RECORD);
   }
 }
 
 struct BamSoA {
-  int* rec; int* tid; int* pos; int* mpos; int* isize; int* mtid; u16* flag; u8* mapq;
+  i64* rec; int* tid; int* pos; int* mpos; int* isize; int* mtid; u16* flag; u8* mapq;
   u32* cigar_off; u32* cigar; u64* qual_off; u8* qual;
 };
 
 // fixed-size fields and offsets of every record (one thread walks the records of one BGZF block)
 __global__ void k_bam_fields(BamChunk C, BamChain H, const int* __restrict__ rbase, const int* __restrict__ cbase, const i64* __restrict__ qbase,
-                             const int* __restrict__ info, BamSoA S) {
+                             const i64* __restrict__ info, BamSoA S) {
   for (int k = (int)(blockIdx.x * blockDim.x + threadIdx.x); k < C.nblk; k += (int)(gridDim.x * blockDim.x)) {
-    int p = H.first[k];
+    i64 p = H.first[k];
     if (p == BAM_NONE) continue;
     const int n = H.cnt[k];
     int r = rbase[k]; u32 co = (u32)cbase[k]; u64 qo = (u64)qbase[k];
@@ -422,15 +417,15 @@ __global__ void k_bam_fields(BamChunk C, BamChain H, const int* __restrict__ rba
       S.mtid[r] = (int)ld32u(q + 24); S.mpos[r] = (int)ld32u(q + 28); S.isize[r] = (int)ld32u(q + 32);
       S.cigar_off[r] = co; S.qual_off[r] = qo;
       co += fnc & 0xffffu; qo += (u64)ld32u(q + 20);
-      p += 4 + (int)bs;
+      p += 4 + (i64)bs;
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) { S.cigar_off[info[0]] = (u32)info[1]; S.qual_off[info[0]] = (u64)*reinterpret_cast<const i64*>(info + 2); }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { S.cigar_off[info[0]] = (u32)info[1]; S.qual_off[info[0]] = (u64)info[2]; }
 }
 
 // CIGAR words and quality bytes: one warp per record
-__global__ void k_bam_payload(const u8* __restrict__ U, const int* __restrict__ info, BamSoA S) {
-  const int n = info[0];
+__global__ void k_bam_payload(const u8* __restrict__ U, const i64* __restrict__ info, BamSoA S) {
+  const int n = (int)info[0];
   const int lane = (int)(threadIdx.x & 31);
   const int wid = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), nw = (int)((gridDim.x * blockDim.x) >> 5);
   for (int r = wid; r < n; r += nw) {
@@ -446,12 +441,12 @@ __global__ void k_bam_payload(const u8* __restrict__ U, const int* __restrict__ 
 }
 
 // runs of equal refID in record order (a coordinate-sorted BAM holds each contig's records contiguously)
-__global__ void k_bam_runs(const int* __restrict__ tid, int* __restrict__ info, int* __restrict__ run_start, int cap, int* __restrict__ err) {
-  const int n = info[0];
+__global__ void k_bam_runs(const int* __restrict__ tid, const i64* __restrict__ info, int* __restrict__ run_start, int cap, int* __restrict__ err) {
+  const int n = (int)info[0];
   for (int r = (int)(blockIdx.x * blockDim.x + threadIdx.x); r < n; r += (int)(gridDim.x * blockDim.x)) {
     if (r == 0 || tid[r] != tid[r - 1]) {
-      const int i = atomicAdd(info + 6, 1);
-      if (i < cap) run_start[i] = r; else atomicOr(err, (int)BAM_ERR_RUNS);
+      const int i = atomicAdd(err, 1);
+      if (i < cap) run_start[i] = r; else atomicOr(err + 1, (int)BAM_ERR_RUNS);
     }
   }
 }

@@ -107,9 +107,9 @@ struct rsigpu_ctx {
   DevVec<int> r_pos, r_mpos, r_isize, r_mtid; DevVec<u16> r_flag; DevVec<u8> r_mapq, r_qual; DevVec<u32> r_cigar_off, r_cigar; DevVec<u64> r_qual_off;
   DevBuf<int> r_calend, d_tile_range; DevBuf<u32> d_qmask;
   // BAM decoder (k_bam.cuh): one chunk of BGZF blocks at a time
-  DevBuf<u8> b_comp, b_U, b_mapq, b_qual; DevBuf<BgzfBlock> b_blk; DevBuf<u16> b_flag; DevBuf<u32> b_cigoff, b_cig; DevBuf<u64> b_qoff;
-  DevBuf<int> b_bound, b_first, b_endp, b_tailp, b_cnt, b_ncig, b_in, b_rbase, b_cbase, b_info, b_runstart, b_rec, b_tid, b_pos, b_mpos, b_isize, b_mtid;
-  DevBuf<i64> b_nq, b_qbase, b_runinfo;
+  DevBuf<u8> b_comp, b_U, b_carry, b_mapq, b_qual; DevBuf<BgzfBlock> b_blk; DevBuf<u16> b_flag, b_tabs; DevBuf<u32> b_cigoff, b_cig; DevBuf<u64> b_qoff;
+  DevBuf<int> b_cnt, b_ncig, b_rbase, b_cbase, b_cnt32, b_runstart, b_tid, b_pos, b_mpos, b_isize, b_mtid;
+  DevBuf<i64> b_bound, b_first, b_endp, b_tailp, b_in, b_info, b_rec, b_nq, b_qbase, b_runinfo;
   struct BamRun { int tid; i64 r0, r1, c0, c1, q0, q1; };
   std::vector<BamRun> b_runs;
   int b_nref = 0, b_tail_len = 0, b_rewalked = 0; bool b_active = false, b_first_feed = true;
@@ -207,7 +207,6 @@ int set_smem_attrs() {
   cudaFuncSetAttribute(k_cand_edge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_CAND_CL);
   cudaFuncSetAttribute(k_rsi_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SCAN_SMEM);
   cudaFuncSetAttribute(k_rsi_scan_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SCAN_SMEM_T(LMAX_SMALL));
-  cudaFuncSetAttribute(k_bgzf_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_INFLATE);
   return 0;
 }
 
@@ -328,6 +327,7 @@ void rsigpu_destroy(rsigpu_ctx* c) {
   c->d_nrun_beg.release(); c->d_nrun_end.release(); c->d_scan_scratch.release(); c->d_tile_range.release(); c->d_qmask.release(); c->r_calend.release();
   c->r_pos.release(); c->r_mpos.release(); c->r_isize.release(); c->r_mtid.release(); c->r_flag.release(); c->r_mapq.release(); c->r_qual.release();
   c->r_cigar_off.release(); c->r_cigar.release(); c->r_qual_off.release();
+  c->b_carry.release(); c->b_tabs.release(); c->b_cnt32.release();
   c->b_comp.release(); c->b_U.release(); c->b_mapq.release(); c->b_qual.release(); c->b_blk.release(); c->b_flag.release(); c->b_cigoff.release(); c->b_cig.release(); c->b_qoff.release();
   c->b_bound.release(); c->b_first.release(); c->b_endp.release(); c->b_tailp.release(); c->b_cnt.release(); c->b_ncig.release(); c->b_in.release(); c->b_rbase.release(); c->b_cbase.release();
   c->b_info.release(); c->b_runstart.release(); c->b_rec.release(); c->b_tid.release(); c->b_pos.release(); c->b_mpos.release(); c->b_isize.release(); c->b_mtid.release();
@@ -454,10 +454,10 @@ int rsigpu_bam_feed(rsigpu_ctx* c, const uint8_t* bgzf, int64_t nbytes, int64_t 
   cudaSetDevice(c->device);
   *consumed = 0; *n_runs = 0; c->b_runs.clear();
   // BGZF block headers (bgzf.c:258-275): gzip magic, FEXTRA, the 'B','C' subfield carries the block size
-  const size_t U_MAX = (size_t)768 << 20, C_MAX = (size_t)1 << 31;
-  std::vector<BgzfBlock> blk; std::vector<int> bound;
+  const size_t U_MAX = (size_t)5 << 30, C_MAX = (size_t)1 << 31;
+  std::vector<BgzfBlock> blk; std::vector<i64> bound;
   size_t off = 0, utotal = 0;
-  bound.push_back((int)BAM_HEAD);
+  bound.push_back((i64)BAM_HEAD);
   while (off + 18 <= (size_t)nbytes) {
     const uint8_t* h = bgzf + off;
     if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) { c->fail("bam_feed: not a BGZF block header"); return RSIGPU_E_ARG; }
@@ -475,10 +475,10 @@ int rsigpu_bam_feed(rsigpu_ctx* c, const uint8_t* bgzf, int64_t nbytes, int64_t 
     const size_t ulen = (size_t)foot[4] | ((size_t)foot[5] << 8) | ((size_t)foot[6] << 16) | ((size_t)foot[7] << 24);
     if (ulen > 65536) { c->fail("bam_feed: BGZF block larger than 64 KiB"); return RSIGPU_E_ARG; }
     if (utotal + ulen > U_MAX || off + bsize > C_MAX) break;
-    BgzfBlock B; B.src = (u32)(off + 12 + xlen); B.src_len = (u32)(bsize - 12 - xlen - 8); B.dst = (u32)(BAM_HEAD + utotal); B.dst_len = (u32)ulen;
+    BgzfBlock B; B.src = (u32)(off + 12 + xlen); B.src_len = (u32)(bsize - 12 - xlen - 8); B.dst = (u64)BAM_HEAD + utotal; B.dst_len = (u32)ulen; B.pad_ = 0;
     blk.push_back(B);
     utotal += ulen; off += bsize;
-    bound.push_back((int)(BAM_HEAD + utotal));
+    bound.push_back((i64)(BAM_HEAD + utotal));
   }
   const int nblk = (int)blk.size();
   if (nblk == 0) {
@@ -487,28 +487,31 @@ int rsigpu_bam_feed(rsigpu_ctx* c, const uint8_t* bgzf, int64_t nbytes, int64_t 
   }
   if (c->b_first_feed) { if ((size_t)skip > utotal) { c->fail("bam_feed: skip beyond the decoded chunk"); return RSIGPU_E_ARG; } }
   else if (skip != 0) { c->fail("bam_feed: skip is only meaningful on the first feed"); return RSIGPU_E_ARG; }
-  CK(c->b_comp.ensure(off + 64)); CK(c->b_U.ensure((size_t)BAM_HEAD + U_MAX + 64)); CK(c->b_blk.ensure((size_t)nblk)); CK(c->b_bound.ensure((size_t)nblk + 1));
+  CK(c->b_comp.ensure(off + 64)); CK(c->b_U.ensure((size_t)BAM_HEAD + utotal + 64)); CK(c->b_blk.ensure((size_t)nblk)); CK(c->b_bound.ensure((size_t)nblk + 1));
+  CK(c->b_tabs.ensure(RSI_INFLATE_TAB_BYTES(nblk) / 2));
   CK(c->b_first.ensure(nblk)); CK(c->b_endp.ensure(nblk)); CK(c->b_tailp.ensure(nblk)); CK(c->b_cnt.ensure(nblk)); CK(c->b_ncig.ensure(nblk)); CK(c->b_nq.ensure(nblk));
-  CK(c->b_in.ensure(nblk)); CK(c->b_rbase.ensure(nblk)); CK(c->b_cbase.ensure(nblk)); CK(c->b_qbase.ensure(nblk)); CK(c->b_info.ensure(16));
+  CK(c->b_in.ensure(nblk)); CK(c->b_rbase.ensure(nblk)); CK(c->b_cbase.ensure(nblk)); CK(c->b_qbase.ensure(nblk)); CK(c->b_info.ensure(8)); CK(c->b_cnt32.ensure(4));
   CK(cudaMemcpyAsync(c->b_comp.p, bgzf, off, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->b_blk.p, blk.data(), (size_t)nblk * sizeof(BgzfBlock), cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->b_bound.p, bound.data(), ((size_t)nblk + 1) * 4, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemsetAsync(c->b_info.p, 0, 16 * 4, c->stream));
-  int* info = c->b_info.p; int* err = c->b_info.p + 8;
-  KL(k_bgzf_inflate, (nblk + INF_NT - 1) / INF_NT, INF_NT, RSI_SMEM_INFLATE, c->b_comp.p, c->b_blk.p, nblk, c->b_U.p, err);
-  BamChunk C; C.U = c->b_U.p; C.u_begin = c->b_first_feed ? (int)(BAM_HEAD + skip) : (int)BAM_HEAD - c->b_tail_len; C.u_end = (int)(BAM_HEAD + utotal);
+  CK(cudaMemcpyAsync(c->b_bound.p, bound.data(), ((size_t)nblk + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemsetAsync(c->b_info.p, 0, 8 * 8, c->stream)); CK(cudaMemsetAsync(c->b_cnt32.p, 0, 4 * 4, c->stream));
+  if (c->b_tail_len) CK(cudaMemcpyAsync(c->b_U.p + (BAM_HEAD - c->b_tail_len), c->b_carry.p, (size_t)c->b_tail_len, cudaMemcpyDeviceToDevice, c->stream));
+  i64* info = c->b_info.p; int* err = c->b_cnt32.p;
+  KL(k_bgzf_inflate, (nblk + INF_NT - 1) / INF_NT, INF_NT, 0, c->b_comp.p, c->b_blk.p, nblk, c->b_U.p, c->b_tabs.p, err);
+  BamChunk C; C.U = c->b_U.p; C.u_begin = c->b_first_feed ? (i64)BAM_HEAD + skip : (i64)BAM_HEAD - c->b_tail_len; C.u_end = (i64)(BAM_HEAD + utotal);
   C.bound = c->b_bound.p; C.nblk = nblk; C.n_ref = c->b_nref;
   BamChain H; H.first = c->b_first.p; H.endp = c->b_endp.p; H.tailp = c->b_tailp.p; H.cnt = c->b_cnt.p; H.ncig = c->b_ncig.p; H.nq = c->b_nq.p;
-  KL(k_bam_chain, grid_for(nblk, 64, c->n_sm * 16), 64, 0, C, H);
+  KL(k_bam_chain, grid_for(nblk, 64, c->n_sm * 32), 64, 0, C, H);
   KL(k_bam_verify, 1, 1024, 0, C, H, c->b_in.p, c->b_rbase.p, c->b_cbase.p, c->b_qbase.p, info, err);
-  int hi[16];
-  CK(cudaMemcpyAsync(hi, info, 16 * 4, cudaMemcpyDeviceToHost, c->stream));
+  i64 hi[8]; int he[4];
+  CK(cudaMemcpyAsync(hi, info, 8 * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(he, err, 4 * 4, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  if (hi[8] & BAM_ERR_INFLATE) { c->fail("bam_feed: corrupt deflate stream in a BGZF block (code " + std::to_string(hi[9]) + ")"); return RSIGPU_E_ARG; }
-  if (hi[8] & BAM_ERR_RECORD) { c->fail("bam_feed: corrupt BAM record"); return RSIGPU_E_ARG; }
-  const size_t n = (size_t)hi[0], ncg = (size_t)hi[1]; i64 nq64; memcpy(&nq64, hi + 2, 8);
-  const int tail_start = hi[4];
-  c->b_rewalked += hi[5];
+  if (he[1] & BAM_ERR_INFLATE) { c->fail("bam_feed: corrupt deflate stream in a BGZF block (code " + std::to_string(he[2]) + ")"); return RSIGPU_E_ARG; }
+  if (he[1] & BAM_ERR_RECORD) { c->fail("bam_feed: corrupt BAM record"); return RSIGPU_E_ARG; }
+  const size_t n = (size_t)hi[0], ncg = (size_t)hi[1]; const i64 nq64 = hi[2];
+  const i64 tail_start = hi[3];
+  c->b_rewalked += (int)hi[4];
   c->b_first_feed = false;
   if (n) {
     CK(c->b_rec.ensure(n)); CK(c->b_tid.ensure(n)); CK(c->b_pos.ensure(n)); CK(c->b_mpos.ensure(n)); CK(c->b_isize.ensure(n)); CK(c->b_mtid.ensure(n));
@@ -516,13 +519,13 @@ int rsigpu_bam_feed(rsigpu_ctx* c, const uint8_t* bgzf, int64_t nbytes, int64_t 
     CK(c->b_runstart.ensure(LIST_CAP)); CK(c->b_runinfo.ensure(3 * (size_t)LIST_CAP));
     BamSoA S; S.rec = c->b_rec.p; S.tid = c->b_tid.p; S.pos = c->b_pos.p; S.mpos = c->b_mpos.p; S.isize = c->b_isize.p; S.mtid = c->b_mtid.p; S.flag = c->b_flag.p;
     S.mapq = c->b_mapq.p; S.cigar_off = c->b_cigoff.p; S.cigar = c->b_cig.p; S.qual_off = c->b_qoff.p; S.qual = c->b_qual.p;
-    KL(k_bam_fields, grid_for(nblk, 64, c->n_sm * 16), 64, 0, C, H, c->b_rbase.p, c->b_cbase.p, c->b_qbase.p, info, S);
+    KL(k_bam_fields, grid_for(nblk, 64, c->n_sm * 32), 64, 0, C, H, c->b_rbase.p, c->b_cbase.p, c->b_qbase.p, info, S);
     KL(k_bam_payload, c->n_sm * 8, 256, 0, c->b_U.p, info, S);
     KL(k_bam_runs, grid_for((int)std::min<size_t>(n, 1u << 30), 1024, c->n_sm * 8), 256, 0, c->b_tid.p, info, c->b_runstart.p, (int)LIST_CAP, err);
-    CK(cudaMemcpyAsync(hi, info, 16 * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(he, err, 4 * 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    if (hi[8] & BAM_ERR_RUNS) { c->fail("bam_feed: more than 65536 refID runs in one chunk (the BAM is not coordinate-sorted)"); return RSIGPU_E_RANGE; }
-    const int nr = hi[6];
+    if (he[1] & BAM_ERR_RUNS) { c->fail("bam_feed: more than 65536 refID runs in one chunk (the BAM is not coordinate-sorted)"); return RSIGPU_E_RANGE; }
+    const int nr = he[0];
     std::vector<int> rs((size_t)nr);
     CK(cudaMemcpyAsync(rs.data(), c->b_runstart.p, (size_t)nr * 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -538,14 +541,15 @@ int rsigpu_bam_feed(rsigpu_ctx* c, const uint8_t* bgzf, int64_t nbytes, int64_t 
       c->b_runs.push_back(R);
     }
   }
-  // the record cut by the end of this chunk moves in front of the next chunk's first block
-  const int tail_len = (int)(BAM_HEAD + utotal) - tail_start;
+  // the record cut by the end of this chunk is kept for the next feed (it goes in front of that chunk's first block)
+  const i64 tail_len = (i64)(BAM_HEAD + utotal) - tail_start;
   if (tail_len > 0) {
-    if (tail_start < (int)BAM_HEAD || tail_len > (int)BAM_HEAD) { c->fail("bam_feed: an alignment record longer than the decoder's carry buffer (16 MiB)"); return RSIGPU_E_RANGE; }
-    CK(cudaMemcpyAsync(c->b_U.p + (BAM_HEAD - tail_len), c->b_U.p + tail_start, (size_t)tail_len, cudaMemcpyDeviceToDevice, c->stream));
+    if (tail_start < (i64)BAM_HEAD || tail_len > (i64)BAM_HEAD) { c->fail("bam_feed: an alignment record longer than the decoder's carry buffer (16 MiB)"); return RSIGPU_E_RANGE; }
+    CK(c->b_carry.ensure((size_t)BAM_HEAD));
+    CK(cudaMemcpyAsync(c->b_carry.p, c->b_U.p + tail_start, (size_t)tail_len, cudaMemcpyDeviceToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
   }
-  c->b_tail_len = tail_len > 0 ? tail_len : 0;
+  c->b_tail_len = tail_len > 0 ? (int)tail_len : 0;
   *consumed = (int64_t)off;
   *n_runs = (int32_t)c->b_runs.size();
   for (int i = 0; i < (int)c->b_runs.size() && i < cap && runs; ++i) { runs[i].tid = c->b_runs[(size_t)i].tid; runs[i].reserved_ = 0; runs[i].n_reads = c->b_runs[(size_t)i].r1 - c->b_runs[(size_t)i].r0; }

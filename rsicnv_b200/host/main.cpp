@@ -251,7 +251,12 @@ int bam_on_gpu(const Opt& o, std::vector<rsigpu_ctx*>& ctx, std::vector<ContigRe
   if (rsigpu_bam_begin(dec, (int32_t)h.name.size())) { fprintf(stderr, "%s\n", rsigpu_last_error(dec)); return 2; }
   FILE* f = fopen(o.bamfile.c_str(), "rb");
   if (!f || fseeko(f, (off_t)coff, SEEK_SET) != 0) { fprintf(stderr, "cannot open %s\n", o.bamfile.c_str()); return 0; }
-  const size_t CHUNK = (size_t)64 << 20, CARRY = (size_t)192 << 20;   // a chunk the decoder takes only partly (very compressible data) is presented again
+  // chunk = what one rsigpu_bam_feed sees: large enough that its ~20 k BGZF blocks fill the GPU (one thread inflates one block);
+  // whatever the decoder does not take (it stops at whole blocks, or at its decoded-size limit) is presented again
+  fseeko(f, 0, SEEK_END);
+  const size_t fsize = (size_t)ftello(f) - (size_t)coff;
+  fseeko(f, (off_t)coff, SEEK_SET);
+  const size_t CHUNK = std::max<size_t>(std::min<size_t>((size_t)256 << 20, fsize + 1), (size_t)1 << 20), CARRY = CHUNK;
   uint8_t* buf[2] = {nullptr, nullptr};
   for (int k = 0; k < 2; ++k) if (rsigpu_pinned_alloc(CARRY + CHUNK, (void**)&buf[k])) { fprintf(stderr, "cannot allocate pinned staging memory\n"); return 2; }
   std::vector<std::thread> workers((size_t)ng);

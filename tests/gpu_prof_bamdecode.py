@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 from rsicnv_b200 import api, synth
 L = int(sys.argv[1]) if len(sys.argv) > 1 else synth.CHR19_LEN
-chunk = (int(sys.argv[2]) if len(sys.argv) > 2 else 64) << 20
+chunk = (int(sys.argv[2]) if len(sys.argv) > 2 else 4096) << 20
 fa = synth.make_fasta(L, 19)
 reads, _ = synth.make_reads(L, 19, fa, coverage=30, n_events=20)
 path = "/tmp/prof.bam"
