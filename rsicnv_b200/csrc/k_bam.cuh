@@ -289,7 +289,11 @@ __device__ bool bam_core_ok(const BamChunk& C, i64 p, i64* next) {
 __device__ bool bam_walk(const BamChunk& C, i64 p, i64 stop, int k, const BamChain& H) {
   int cnt = 0, ncig = 0; i64 nq = 0, endp = 0, tailp = 0; bool clean = true;
   for (;;) {
-    if (p >= stop) { endp = p; break; }
+    if (p >= stop) {                                                                  // the landing position must look like a record too
+      i64 q = p, n2;
+      for (int hop = 0; hop < 3 && clean && q + 36 <= C.u_end; ++hop) { if (!bam_core_ok(C, q, &n2)) clean = false; q = n2; }
+      endp = p; break;
+    }
     if (p + 4 > C.u_end) { endp = BAM_TAIL; tailp = p; break; }                       // the chunk ends inside the length field
     if (p + 36 > C.u_end) {                                                           // ... inside the fixed-size core
       const u32 bs = ld32u(C.U + p);
@@ -319,6 +323,11 @@ __global__ void k_bam_chain(BamChunk C, BamChain H) {
       for (i64 p = ub; p < ue && !found; ++p) {
         i64 nx;
         if (!bam_core_ok(C, p, &nx)) continue;
+        {   // a guess (only a guess) must not carry megabytes of optional fields: block_size close to what the core implies
+          const u8* r = C.U + p;
+          const u64 need = 32ull + r[12] + 4ull * ((u32)r[16] | ((u32)r[17] << 8)) + ((u64)ld32u(r + 20) + 1) / 2 + (u64)ld32u(r + 20);
+          if ((u64)ld32u(r) - need > 65536ull) continue;
+        }
         if (bam_walk(C, p, ue, k, H)) { H.first[k] = p; found = true; }
       }
     }
@@ -346,25 +355,27 @@ __global__ void __launch_bounds__(1024) k_bam_verify(BamChunk C, BamChain H, i64
     i64 pre = C.u_begin; for (int w = 0; w < warp; ++w) pre = lmax(pre, slots[w]);
     const i64 up = __shfl_up_sync(0xffffffffu, v, 1);
     i64 run = lmax(pre, lane ? up : -1);
-    int bad = 0;
+    int bad = 0x7fffffff;
     for (int k = k0; k < k1; ++k) {
       in_pos[k] = run;
       const i64 ue = C.bound[k + 1], g = H.first[k];
       const bool ok = (run >= ue) ? (g == BAM_NONE) : (g == run);
-      if (!ok) bad = 1;
+      if (!ok && bad == 0x7fffffff) bad = k;
       if (g != BAM_NONE) run = lmax(run, H.endp[k]);
     }
     c.sync();
-    if (!c.reduce(bad, MaxOp())) break;
-    // Everything before the first mismatch is proven, so ITS incoming position is the true one.  Mismatches further on are
-    // almost always isolated (the guess skipped a record the core check rejects, the walks merge again): every thread
-    // repairs the mismatches of its own range from in_pos; the next round proves or refutes them, and at least the first
-    // one is settled per round.
+    const int firstbad = c.reduce(bad, MinOp());
+    if (firstbad == 0x7fffffff) break;
+    // Everything before the first mismatch is proven, so ITS incoming position is the true one and it is repaired whatever
+    // it says.  A mismatch further on is usually an isolated wrong guess whose incoming position is already right, but it
+    // can also be the shadow of an earlier wrong walk (the max-scan carries a wrong, far end over every later block): so
+    // later blocks are only re-walked when the incoming position lies inside them, never emptied.  Each round settles at
+    // least the first mismatch; the loop ends when every block matches, which is the proof.
     for (int k = k0; k < k1; ++k) {
       const i64 ue = C.bound[k + 1], g = H.first[k], cur = in_pos[k];
       const bool ok = (cur >= ue) ? (g == BAM_NONE) : (g == cur);
       if (ok) continue;
-      if (cur >= ue) bam_no_start(k, H);
+      if (cur >= ue) { if (k != firstbad) continue; bam_no_start(k, H); }
       else { H.first[k] = cur; bam_walk(C, cur, ue, k, H); }
       ++fixed;
     }
