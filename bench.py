@@ -149,13 +149,14 @@ def ref_bam_worker(args):
     cli = os.path.join(ROOT, "rsicnv_b200", "bin", "rsicnv")
     if with_ours and os.path.exists(cli):
         # the same files through this repo's CLI (host BGZF/BAM decode + the CUDA path); second run = CUDA context and page cache warm
-        ts = []
-        for _ in range(2):
+        ts = []; notes = []
+        for extra in ([], [], ["-hostdecode"]):
             t0 = time.perf_counter()
-            subprocess.run([cli, "rsi", "-b", os.path.join(d, "t.bam"), "-f", os.path.join(d, "t.fa"), "-q", "0", "-Q", "10", "-np", "-o", os.path.join(d, "ours.txt")],
-                           check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            r = subprocess.run([cli, "rsi", "-b", os.path.join(d, "t.bam"), "-f", os.path.join(d, "t.fa"), "-q", "0", "-Q", "10", "-np", "-o", os.path.join(d, "ours.txt")] + extra,
+                               check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, env=dict(os.environ, RSICNV_TIMING="1"))
             ts.append(time.perf_counter() - t0)
-        ours = {"first_s": ts[0], "second_s": ts[1],
+            notes += [ln for ln in r.stderr.splitlines() if ln.startswith("#timing")]
+        ours = {"first_s": ts[0], "second_s": ts[1], "hostdecode_s": ts[2], "timing": notes,
                 "identical_table": open(os.path.join(d, "ours.txt"), "rb").read() == open(os.path.join(d, "out.txt"), "rb").read()}
     return dt, ncalls, ours
 
@@ -288,6 +289,16 @@ def main():
         qual_bytes = int(pins["qual"].numel())
         config["reads"] = nreads
         ctxs = [api.Context(device=local, minq=0, min_baseQ=10) for _ in range(K)]
+        # the same reads as a BAM FILE image (BGZF level 1, random bases so that it compresses like a real one): the
+        # end-to-end leg starts from these bytes, as the reference does (samtools bgzf/bam readers, BAM in page cache)
+        import tempfile
+        with tempfile.TemporaryDirectory() as td:
+            t0 = time.perf_counter()
+            synth.write_bam(os.path.join(td, "t.bam"), [("19", L)], {0: reads}, level=1, random_seq=7 + rank, threads=min(32, os.cpu_count() or 8))
+            bam_np = np.fromfile(os.path.join(td, "t.bam"), np.uint8)
+        bam_hdr = api.parse_bam_header(bam_np)
+        bam_pin = torch.from_numpy(bam_np).pin_memory()
+        config["bam_file_bytes"] = int(bam_np.size); config["bam_write_s"] = round(time.perf_counter() - t0, 1)
     else:
         fa, depth, events = make_inputs(19 + rank, L)
         dp_pin = torch.from_numpy(depth).pin_memory()
@@ -322,6 +333,27 @@ def main():
             stage_one(kb[0])
             return kb[0].run_count(kb[1], 65536)
         return list(pool.map(one, zip(ctxs, bufs)))
+
+    def file_one(kb):
+        """BAM file bytes (pinned host memory) -> BGZF inflate + record decode on the GPU -> pileup -> ... -> calls on the host"""
+        cx, out = kb
+        cx.set_reference_ptr(fa_pin.data_ptr(), L)
+        cx.pileup_begin()
+        cx.bam_begin(len(bam_hdr["names"]))
+        off = bam_hdr["coff"]; first = True; n = int(bam_np.size)
+        while off < n:
+            consumed, runs = cx.bam_feed(bam_pin.data_ptr() + off, n - off, skip=bam_hdr["skip"] if first else 0)
+            for i, (tid, nr) in enumerate(runs):
+                if tid == 0:
+                    cx.bam_take(i, cx)
+            if consumed == 0:
+                break
+            first = False; off += consumed
+        cx.bam_end(); cx.have_reads()
+        return cx.run_count(out, 65536)
+
+    def file_all():
+        return list(pool.map(file_one, zip(ctxs, bufs)))
 
     def barrier():
         torch.cuda.synchronize()
@@ -360,17 +392,33 @@ def main():
         ne = e2e_all()[0]
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - t0)
+    file_ms = None
+    if bam:
+        nf = file_all()[0]
+        assert nf == ne, "decoded-on-GPU path disagrees with the staged-reads path"
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            nf = file_all()[0]
+        barrier()
+        file_ms = 1e3 * (time.perf_counter() - t0)
     # ---- per-kernel device times (extra profiled steps, CUDA events around every launch on the context's stream)
     ctx.set_profile(True)
     for _ in range(a.profile_steps):
         ctx.run_count(buf, 65536)
     prof = ctx.profile()
     ctx.set_profile(False)
+    dprof = []
+    if bam:
+        ctx.set_profile(True)
+        file_one((ctx, buf))
+        dprof = [(nm, ms, n) for nm, ms, n in ctx.profile() if nm.startswith("k_bgzf") or nm.startswith("k_bam")]
+        ctx.set_profile(False)
 
-    t = torch.tensor([dev_ms, wall_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, wall_ms, e2e_ms, file_ms or 0.0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, wall_ms, e2e_ms = [float(x) for x in t.tolist()]
+    dev_ms, wall_ms, e2e_ms, file_ms = [float(x) for x in t.tolist()]
     if rank == 0:
         peak, peak_src = peaks()
         total_bases = world * K * L * a.steps
@@ -399,20 +447,35 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "Gbases/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": dev_ms / a.steps, "wall_ms_per_step": wall_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8 qualities -> int32 depth / f64 statistics", "data": "synthetic", "config": config, "clocks": clocks,
-                "e2e": {"value": total_bases / (e2e_ms / 1e3) / 1e9, "unit": "Gbases/s", "h2d_bytes_per_step": int(h2d) * K, "d2h_bytes_per_step": int(ne * 128 + 53000) * K,
-                        "ms_per_step": e2e_ms / a.steps},
+                "e2e": None,
                 "gpu_launches": int(launches), "calls_per_contig": int(ncalls), "roofline": roof,
                 "single_contig_stage_ms": {k: v / a.steps for k, v in (stages or {}).items()},
                 "timing": "value: wall time of each step bracketed by torch.cuda.synchronize (K contexts on K streams overlap, per-context CUDA-event "
                           "times are in single_contig_stage_ms); kernels: CUDA events around every launch of one context in extra profiled steps",
                 "kernels": kern[:12]}
+        soa = {"value": total_bases / (e2e_ms / 1e3) / 1e9, "unit": "Gbases/s", "h2d_bytes_per_step": int(h2d) * K,
+               "d2h_bytes_per_step": int(ne * 128 + 53000) * K, "ms_per_step": e2e_ms / a.steps}
+        if bam:
+            # headline: from the BAM FILE's bytes, like the reference arm (BGZF inflate + BAM record decoding inside the timed region, on the GPU)
+            line["e2e"] = {"value": total_bases / (file_ms / 1e3) / 1e9, "unit": "Gbases/s", "h2d_bytes_per_step": (int(bam_np.size) + L) * K,
+                           "d2h_bytes_per_step": int(ne * 128 + 53000) * K, "ms_per_step": file_ms / a.steps,
+                           "input": "BAM file image (BGZF) + FASTA contig in pinned host memory -> rsigpu_bam_feed/take -> rsigpu_run -> calls on the host"}
+            soa["input"] = "already-decoded reads (structure of arrays, rsigpu_pileup_push) + FASTA contig in pinned host memory"
+            line["e2e_decoded_reads"] = soa
+        else:
+            line["e2e"] = soa
+        if dprof:
+            dec_bytes = int(sum(np.diff(reads["qual_off"].astype(np.int64)) * 3 // 2 + 38 + 4 * np.diff(reads["cigar_off"].astype(np.int64))))
+            line["decode_kernels"] = [{"kernel": nm, "launches": n, "ms": ms,
+                                       **({"compressed_bytes": int(bam_np.size), "decoded_bytes": dec_bytes, "decoded_gbs": dec_bytes / 1e9 / (ms / 1e3)} if nm == "k_bgzf_inflate" else {})}
+                                      for nm, ms, n in sorted(dprof, key=lambda x: -x[1])]
         if world == 1:
             sample = min(a.cpu_sample, L)
             if bam:
                 cpu, out, kind = time_reference_bam(sample, 1, 19, with_ours=True)
                 if len(out[0]) > 2 and out[0][2]:
                     o = out[0][2]
-                    line["cli_e2e"] = {"sample_bp": sample, "reference_cli_s": cpu, "this_cli_first_s": o["first_s"], "this_cli_second_s": o["second_s"],
+                    line["cli_e2e"] = {"sample_bp": sample, "reference_cli_s": cpu, "this_cli_first_s": o["first_s"], "this_cli_second_s": o["second_s"], "this_cli_hostdecode_s": o["hostdecode_s"], "this_cli_timing": o["timing"],
                                        "identical_table": o["identical_table"], "speedup_second": cpu / o["second_s"],
                                        "what": "BAM + FASTA files -> CNV table through each CLI (process start, CUDA context creation, BGZF/BAM decode on the host included)"}
                 line["cpu_baseline"] = {"value": sample / cpu / 1e9, "unit": "Gbases/s", "cores": 1, "kind": kind,

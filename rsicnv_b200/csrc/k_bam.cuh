@@ -203,7 +203,26 @@ __device__ __forceinline__ void inf_symbol(InfState& S, const InfTabs& T, const 
   if (dist > S.o) return inf_fail(S, 16);
   if (S.o + len > S.dst_len) return inf_fail(S, 3);
   const u8* from = S.dst + S.o - dist; u8* to = S.dst + S.o;
-  for (u32 k = 0; k < len; ++k) to[k] = from[k];
+  // The source is this thread's own recent output (L2, not L1): a byte-by-byte copy is a chain of load -> store -> load
+  // round trips.  Loads are issued in groups that cannot depend on the stores of the same group.
+  if (dist == 1) { const u8 v = from[0]; for (u32 k = 0; k < len; ++k) to[k] = v; }
+  else if (dist < 8) {                      // periodic pattern of `dist` bytes: keep it in a register
+    u64 pat = 0;
+    for (u32 k = 0; k < dist; ++k) pat |= (u64)from[k] << (8 * k);
+    u32 j = 0;
+    for (u32 k = 0; k < len; ++k) { to[k] = (u8)(pat >> (8 * j)); if (++j == dist) j = 0; }
+  } else {
+    u32 k = 0;
+    for (; k + 8 <= len; k += 8) {
+      const u8 b0 = from[k], b1 = from[k + 1], b2 = from[k + 2], b3 = from[k + 3], b4 = from[k + 4], b5 = from[k + 5], b6 = from[k + 6], b7 = from[k + 7];
+      to[k] = b0; to[k + 1] = b1; to[k + 2] = b2; to[k + 3] = b3; to[k + 4] = b4; to[k + 5] = b5; to[k + 6] = b6; to[k + 7] = b7;
+    }
+    u8 t[8]; const u32 rem = len - k;
+#pragma unroll
+    for (u32 i = 0; i < 8; ++i) if (i < rem) t[i] = from[k + i];
+#pragma unroll
+    for (u32 i = 0; i < 8; ++i) if (i < rem) to[k + i] = t[i];
+  }
   S.o += len;
 }
 
@@ -312,26 +331,50 @@ __device__ bool bam_walk(const BamChunk& C, i64 p, i64 stop, int k, const BamCha
 __device__ __forceinline__ void bam_no_start(int k, const BamChain& H) { H.first[k] = BAM_NONE; H.endp[k] = BAM_NONE; H.tailp[k] = 0; H.cnt[k] = 0; H.ncig[k] = 0; H.nq[k] = 0; }
 
 // Guess: the first position of the block that passes the core check AND from which the list walks cleanly to the end of
-// the block (a few hundred records) -- wrong guesses that survive this are practically impossible, and k_bam_verify does
-// not depend on it.
+// the block (a few hundred records) and lands on something that looks like a record -- wrong guesses that survive this are
+// practically impossible, and k_bam_verify does not depend on it.  One thread per BGZF block; scanning and walking are
+// written as a state machine advanced one unit per iteration of a warp-uniform loop, so that the 32 lanes (32 different
+// blocks) stay converged instead of running their walks one after the other.
 __global__ void k_bam_chain(BamChunk C, BamChain H) {
-  for (int k = (int)(blockIdx.x * blockDim.x + threadIdx.x); k < C.nblk; k += (int)(gridDim.x * blockDim.x)) {
-    const i64 ub = C.bound[k], ue = C.bound[k + 1];
-    bool found = false;
-    if (k == 0) { if (C.u_begin < ue) { H.first[k] = C.u_begin; bam_walk(C, C.u_begin, ue, k, H); found = true; } }
-    else {
-      for (i64 p = ub; p < ue && !found; ++p) {
-        i64 nx;
-        if (!bam_core_ok(C, p, &nx)) continue;
-        {   // a guess (only a guess) must not carry megabytes of optional fields: block_size close to what the core implies
-          const u8* r = C.U + p;
+  const int k = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  enum { SCAN = 0, WALK = 1, DONE = 2 };
+  int phase = DONE;
+  i64 ub = 0, ue = 0, cand = 0, p = 0, nq = 0; int cnt = 0, ncig = 0;
+  if (k < C.nblk) {
+    ub = C.bound[k]; ue = C.bound[k + 1];
+    if (k == 0) { if (C.u_begin < ue) { H.first[k] = C.u_begin; bam_walk(C, C.u_begin, ue, k, H); } else bam_no_start(k, H); }
+    else { phase = SCAN; cand = ub; }
+  }
+  while (__any_sync(0xffffffffu, phase != DONE)) {
+    if (phase == SCAN) {
+      if (cand >= ue) { bam_no_start(k, H); phase = DONE; }
+      else {
+        i64 nx; bool ok = bam_core_ok(C, cand, &nx);
+        if (ok) {   // a guess (only a guess) must not carry megabytes of optional fields: block_size close to what the core implies
+          const u8* r = C.U + cand;
           const u64 need = 32ull + r[12] + 4ull * ((u32)r[16] | ((u32)r[17] << 8)) + ((u64)ld32u(r + 20) + 1) / 2 + (u64)ld32u(r + 20);
-          if ((u64)ld32u(r) - need > 65536ull) continue;
+          ok = (u64)ld32u(r) - need <= 65536ull;
         }
-        if (bam_walk(C, p, ue, k, H)) { H.first[k] = p; found = true; }
+        if (ok) { phase = WALK; p = cand; cnt = 0; ncig = 0; nq = 0; } else ++cand;
       }
+    } else if (phase == WALK) {
+      // one record per iteration: the same rules as bam_walk
+      bool fail = false, fin = false; i64 endp = 0, tailp = 0;
+      if (p >= ue) {
+        i64 q = p, n2;
+        for (int hop = 0; hop < 3 && !fail && q + 36 <= C.u_end; ++hop) { if (!bam_core_ok(C, q, &n2)) fail = true; q = n2; }
+        endp = p; fin = true;
+      } else if (p + 4 > C.u_end) { endp = BAM_TAIL; tailp = p; fin = true; }
+      else if (p + 36 > C.u_end) { const u32 bs = ld32u(C.U + p); fail = !(bs >= 32u && bs <= (1u << 28)); endp = BAM_TAIL; tailp = p; fin = true; }
+      else {
+        i64 nx;
+        if (!bam_core_ok(C, p, &nx)) fail = true;
+        else if (nx > C.u_end) { endp = BAM_TAIL; tailp = p; fin = true; }
+        else { ++cnt; ncig += (int)((u32)C.U[p + 16] | ((u32)C.U[p + 17] << 8)); nq += (i64)(int)ld32u(C.U + p + 20); p = nx; }
+      }
+      if (fail) { phase = SCAN; ++cand; }
+      else if (fin) { H.first[k] = cand; H.endp[k] = endp; H.tailp[k] = tailp; H.cnt[k] = cnt; H.ncig[k] = ncig; H.nq[k] = nq; phase = DONE; }
     }
-    if (!found) bam_no_start(k, H);
   }
 }
 
@@ -415,12 +458,12 @@ struct BamSoA {
 // fixed-size fields and offsets of every record (one thread walks the records of one BGZF block)
 __global__ void k_bam_fields(BamChunk C, BamChain H, const int* __restrict__ rbase, const int* __restrict__ cbase, const i64* __restrict__ qbase,
                              const i64* __restrict__ info, BamSoA S) {
-  for (int k = (int)(blockIdx.x * blockDim.x + threadIdx.x); k < C.nblk; k += (int)(gridDim.x * blockDim.x)) {
-    i64 p = H.first[k];
-    if (p == BAM_NONE) continue;
-    const int n = H.cnt[k];
-    int r = rbase[k]; u32 co = (u32)cbase[k]; u64 qo = (u64)qbase[k];
-    for (int i = 0; i < n; ++i, ++r) {
+  const int k = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  i64 p = k < C.nblk ? H.first[k] : BAM_NONE;
+  const int n = p == BAM_NONE ? 0 : H.cnt[k];
+  int r = n ? rbase[k] : 0; u32 co = n ? (u32)cbase[k] : 0u; u64 qo = n ? (u64)qbase[k] : 0ull;
+  for (int i = 0; __any_sync(0xffffffffu, i < n); ++i) {      // warp-uniform trip count: the lanes walk 32 different blocks in step
+    if (i < n) {
       const u8* q = C.U + p;
       const u32 bs = ld32u(q), bmq = ld32u(q + 12), fnc = ld32u(q + 16);
       S.rec[r] = p; S.tid[r] = (int)ld32u(q + 4); S.pos[r] = (int)ld32u(q + 8);
@@ -428,7 +471,7 @@ __global__ void k_bam_fields(BamChunk C, BamChain H, const int* __restrict__ rba
       S.mtid[r] = (int)ld32u(q + 24); S.mpos[r] = (int)ld32u(q + 28); S.isize[r] = (int)ld32u(q + 32);
       S.cigar_off[r] = co; S.qual_off[r] = qo;
       co += fnc & 0xffffu; qo += (u64)ld32u(q + 20);
-      p += 4 + (i64)bs;
+      p += 4 + (i64)bs; ++r;
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) { S.cigar_off[info[0]] = (u32)info[1]; S.qual_off[info[0]] = (u64)info[2]; }

@@ -501,7 +501,7 @@ int rsigpu_bam_feed(rsigpu_ctx* c, const uint8_t* bgzf, int64_t nbytes, int64_t 
   BamChunk C; C.U = c->b_U.p; C.u_begin = c->b_first_feed ? (i64)BAM_HEAD + skip : (i64)BAM_HEAD - c->b_tail_len; C.u_end = (i64)(BAM_HEAD + utotal);
   C.bound = c->b_bound.p; C.nblk = nblk; C.n_ref = c->b_nref;
   BamChain H; H.first = c->b_first.p; H.endp = c->b_endp.p; H.tailp = c->b_tailp.p; H.cnt = c->b_cnt.p; H.ncig = c->b_ncig.p; H.nq = c->b_nq.p;
-  KL(k_bam_chain, grid_for(nblk, 64, c->n_sm * 32), 64, 0, C, H);
+  KL(k_bam_chain, (nblk + 127) / 128, 128, 0, C, H);
   KL(k_bam_verify, 1, 1024, 0, C, H, c->b_in.p, c->b_rbase.p, c->b_cbase.p, c->b_qbase.p, info, err);
   i64 hi[8]; int he[4];
   CK(cudaMemcpyAsync(hi, info, 8 * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -519,7 +519,7 @@ int rsigpu_bam_feed(rsigpu_ctx* c, const uint8_t* bgzf, int64_t nbytes, int64_t 
     CK(c->b_runstart.ensure(LIST_CAP)); CK(c->b_runinfo.ensure(3 * (size_t)LIST_CAP));
     BamSoA S; S.rec = c->b_rec.p; S.tid = c->b_tid.p; S.pos = c->b_pos.p; S.mpos = c->b_mpos.p; S.isize = c->b_isize.p; S.mtid = c->b_mtid.p; S.flag = c->b_flag.p;
     S.mapq = c->b_mapq.p; S.cigar_off = c->b_cigoff.p; S.cigar = c->b_cig.p; S.qual_off = c->b_qoff.p; S.qual = c->b_qual.p;
-    KL(k_bam_fields, grid_for(nblk, 64, c->n_sm * 32), 64, 0, C, H, c->b_rbase.p, c->b_cbase.p, c->b_qbase.p, info, S);
+    KL(k_bam_fields, (nblk + 127) / 128, 128, 0, C, H, c->b_rbase.p, c->b_cbase.p, c->b_qbase.p, info, S);
     KL(k_bam_payload, c->n_sm * 8, 256, 0, c->b_U.p, info, S);
     KL(k_bam_runs, grid_for((int)std::min<size_t>(n, 1u << 30), 1024, c->n_sm * 8), 256, 0, c->b_tid.p, info, c->b_runstart.p, (int)LIST_CAP, err);
     CK(cudaMemcpyAsync(he, err, 4 * 4, cudaMemcpyDeviceToHost, c->stream));

@@ -389,11 +389,13 @@ int main(int argc, char** argv) {
   Opt o;
   if (!parse(argc, argv, &o)) return usage();
   if (o.function == "decode") return do_decode(o);
+  const double t_main = now_s();
   const int ndev = rsigpu_num_devices();
   if (ndev <= 0) { fprintf(stderr, "no CUDA device: this implementation has no CPU path\n"); return 2; }
   const int ng = std::max(1, std::min(o.gpus, ndev));
   std::vector<rsigpu_ctx*> ctx((size_t)ng, nullptr);
   for (int g = 0; g < ng; ++g) if (rsigpu_create(g, &o.P, &ctx[(size_t)g])) { fprintf(stderr, "cannot create a context on GPU %d\n", g); return 2; }
+  if (getenv("RSICNV_TIMING")) fprintf(stderr, "#timing: CUDA start-up + contexts %.3f s\n", now_s() - t_main);
   std::vector<ContigResult> results;
   std::string err;
   if (!o.rdfile.empty()) {   // depth-file input: one contig (rsi.cpp:2133-2136, 2192-2195)
@@ -453,6 +455,7 @@ int main(int argc, char** argv) {
     if (!err.empty()) fprintf(stderr, "%s\n", err.c_str());
   }
   write_table(o, results);
+  if (getenv("RSICNV_TIMING")) fprintf(stderr, "#timing: total %.3f s\n", now_s() - t_main);
   fprintf(stderr, "output written to %s\n", o.outfile.c_str());
   for (rsigpu_ctx* c : ctx) rsigpu_destroy(c);
   return 0;
