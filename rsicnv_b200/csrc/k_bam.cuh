@@ -112,6 +112,7 @@ struct InfState {
   BitIn b; u32 o, dst_len; u8* dst;
   int phase;      // 0: at a block header, 1: inside a Huffman block, 2: finished (rc = 0 ok)
   int last, rc;
+  u32 m_len, m_dist;   // match decoded by the last inf_symbol, not yet copied
 };
 enum { INF_HEADER = 0, INF_SYMS = 1, INF_DONE = 2 };
 
@@ -202,28 +203,41 @@ __device__ __forceinline__ void inf_symbol(InfState& S, const InfTabs& T, const 
   const u32 dist = (u32)tab[58 + ds] + bits_take(b, (int)tab[88 + ds]);
   if (dist > S.o) return inf_fail(S, 16);
   if (S.o + len > S.dst_len) return inf_fail(S, 3);
-  const u8* from = S.dst + S.o - dist; u8* to = S.dst + S.o;
-  // The source is this thread's own recent output (L2, not L1): a byte-by-byte copy is a chain of load -> store -> load
-  // round trips.  Loads are issued in groups that cannot depend on the stores of the same group.
-  if (dist == 1) { const u8 v = from[0]; for (u32 k = 0; k < len; ++k) to[k] = v; }
-  else if (dist < 8) {                      // periodic pattern of `dist` bytes: keep it in a register
-    u64 pat = 0;
-    for (u32 k = 0; k < dist; ++k) pat |= (u64)from[k] << (8 * k);
-    u32 j = 0;
-    for (u32 k = 0; k < len; ++k) { to[k] = (u8)(pat >> (8 * j)); if (++j == dist) j = 0; }
-  } else {
-    u32 k = 0;
-    for (; k + 8 <= len; k += 8) {
-      const u8 b0 = from[k], b1 = from[k + 1], b2 = from[k + 2], b3 = from[k + 3], b4 = from[k + 4], b5 = from[k + 5], b6 = from[k + 6], b7 = from[k + 7];
-      to[k] = b0; to[k + 1] = b1; to[k + 2] = b2; to[k + 3] = b3; to[k + 4] = b4; to[k + 5] = b5; to[k + 6] = b6; to[k + 7] = b7;
+  S.m_len = len; S.m_dist = dist;      // copied by the whole warp (inf_warp_copy) before the next symbol
+}
+
+// The pending matches of all 32 lanes, copied by the whole warp.  A match byte i comes from i - dist, which for i >= dist is
+// a byte of the same match: the source is periodic, out[i] = src[i mod dist], so every byte can be read from data that was
+// complete before the copy began -- no byte depends on another one of this round.  The bytes of all lanes' matches are laid
+// end to end and dealt to the lanes 32 at a time (the owner of a byte is found by a search over the warp's prefix sums):
+// all loads of a round are independent and consecutive lanes touch consecutive addresses, instead of one lane copying
+// byte by byte (a load -> store -> load chain through L2) while 31 wait.
+__device__ __forceinline__ void inf_warp_copy(InfState& S, int lane) {
+  const u32 len = S.m_len;
+  u32 incl = len;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const u32 up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += up; }
+  const u32 total = __shfl_sync(0xffffffffu, incl, 31);
+  if (total == 0) return;
+  u8* const to = S.dst + S.o;
+  const u64 to_bits = (u64)(size_t)to;
+  const u32 to_lo = (u32)to_bits, to_hi = (u32)(to_bits >> 32);
+  for (u32 t0 = 0; t0 < total; t0 += 32) {
+    const u32 t = t0 + (u32)lane;
+    int lo = 0, hi = 31;
+#pragma unroll
+    for (int it = 0; it < 5; ++it) { const int mid = (lo + hi) >> 1; const u32 v = __shfl_sync(0xffffffffu, incl, mid); if (v > t) hi = mid; else lo = mid + 1; }
+    const int j = lo > 31 ? 31 : lo;
+    const u32 end_j = __shfl_sync(0xffffffffu, incl, j), len_j = __shfl_sync(0xffffffffu, len, j), dist_j = __shfl_sync(0xffffffffu, S.m_dist, j);
+    const u32 plo = __shfl_sync(0xffffffffu, to_lo, j), phi = __shfl_sync(0xffffffffu, to_hi, j);
+    if (t < total) {
+      u8* tj = reinterpret_cast<u8*>((size_t)(((u64)phi << 32) | plo));
+      const u32 i = t - (end_j - len_j);
+      const u32 si = i < dist_j ? i : i % dist_j;
+      tj[i] = (tj - dist_j)[si];
     }
-    u8 t[8]; const u32 rem = len - k;
-#pragma unroll
-    for (u32 i = 0; i < 8; ++i) if (i < rem) t[i] = from[k + i];
-#pragma unroll
-    for (u32 i = 0; i < 8; ++i) if (i < rem) to[k + i] = t[i];
   }
-  S.o += len;
+  S.o += len; S.m_len = 0;
 }
 
 // inflate: one thread per BGZF block of the chunk, the warp re-converged after every step
@@ -244,7 +258,7 @@ __global__ void __launch_bounds__(INF_NT) k_bgzf_inflate(const u8* __restrict__ 
   InfTabs T; T.lane = (int)(threadIdx.x & 31); T.stid = (int)threadIdx.x; T.s = cnts;
   T.g = tabs + (size_t)(k >> 5) * 32 * INF_GSLOTS;
   InfState S;
-  S.phase = INF_DONE; S.rc = 0; S.o = 0; S.dst_len = 0; S.dst = U; S.last = 0;
+  S.phase = INF_DONE; S.rc = 0; S.o = 0; S.dst_len = 0; S.dst = U; S.last = 0; S.m_len = 0; S.m_dist = 1;
   S.b.base = comp; S.b.pos = 0; S.b.end = 0; S.b.buf = 0; S.b.cnt = 0;
   if (k < nblk) {
     const BgzfBlock B = blk[k];
@@ -261,7 +275,7 @@ __global__ void __launch_bounds__(INF_NT) k_bgzf_inflate(const u8* __restrict__ 
     if (__any_sync(0xffffffffu, S.phase == INF_HEADER)) { if (S.phase == INF_HEADER) inf_block_header(S, T); }
     else {
 #pragma unroll 1
-      for (int it = 0; it < 8; ++it) { if (S.phase == INF_SYMS) inf_symbol(S, T, tab); __syncwarp(); }
+      for (int it = 0; it < 8; ++it) { if (S.phase == INF_SYMS) inf_symbol(S, T, tab); __syncwarp(); inf_warp_copy(S, T.lane); }
     }
   }
   if (S.rc) { atomicOr(err + 1, (int)BAM_ERR_INFLATE); atomicMax(err + 2, S.rc); }
