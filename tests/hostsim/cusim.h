@@ -315,8 +315,12 @@ inline void __threadfence() {}
 inline void __threadfence_block() {}
 inline unsigned __activemask() { return cusim::S().cb().warps[cusim::S().ct() >> 5].alive; }
 
+// every lane may name a different source lane: the source index travels with the value
+template <class T> struct CusimShflArg { T v; int src; };
 template <class T> inline T __shfl_sync(unsigned mask, T v, int src, int width = 32) {
-  return cusim::warp_coll<T, T>(mask, v, [=](int l, const T* a, unsigned) { int base = l & ~(width - 1); return a[base + (src & (width - 1))]; });
+  static_assert(sizeof(T) <= 8, "shfl payload");
+  CusimShflArg<T> arg; arg.v = v; arg.src = src;
+  return cusim::warp_coll<CusimShflArg<T>, T>(mask, arg, [=](int l, const CusimShflArg<T>* a, unsigned) { int base = l & ~(width - 1); return a[base + (a[l].src & (width - 1))].v; });
 }
 template <class T> inline T __shfl_xor_sync(unsigned mask, T v, int lm, int width = 32) {
   return cusim::warp_coll<T, T>(mask, v, [=](int l, const T* a, unsigned) { int o = l ^ lm; return (o / width == l / width && o < 32) ? a[o] : a[l]; });
