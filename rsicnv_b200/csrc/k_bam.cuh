@@ -212,30 +212,50 @@ __device__ __forceinline__ void inf_symbol(InfState& S, const InfTabs& T, const 
 // end to end and dealt to the lanes 32 at a time (the owner of a byte is found by a search over the warp's prefix sums):
 // all loads of a round are independent and consecutive lanes touch consecutive addresses, instead of one lane copying
 // byte by byte (a load -> store -> load chain through L2) while 31 wait.
-__device__ __forceinline__ void inf_warp_copy(InfState& S, int lane) {
+struct InfPending { u8* a0; u8* a1; u32 v0, v1; };   // bytes loaded by the last round of inf_warp_copy, stored by the next call (a == nullptr: none)
+
+__device__ __forceinline__ void inf_flush(InfPending& P) {
+  if (P.a0) { *P.a0 = (u8)P.v0; P.a0 = nullptr; }
+  if (P.a1) { *P.a1 = (u8)P.v1; P.a1 = nullptr; }
+}
+// owner of flattened byte t among the warp's matches: lane j (smallest j with incl_j > t), and the byte's source / destination
+__device__ __forceinline__ void inf_copy_assign(u32 t, u32 total, u32 incl, u32 len, u32 dist, u32 to_lo, u32 to_hi, u8** dstp, const u8** srcp) {
+  int lo = 0, hi = 31;
+#pragma unroll
+  for (int it = 0; it < 5; ++it) { const int mid = (lo + hi) >> 1; const u32 v = __shfl_sync(0xffffffffu, incl, mid); if (v > t) hi = mid; else lo = mid + 1; }
+  const int j = lo > 31 ? 31 : lo;
+  const u32 end_j = __shfl_sync(0xffffffffu, incl, j), len_j = __shfl_sync(0xffffffffu, len, j), dist_j = __shfl_sync(0xffffffffu, dist, j);
+  const u32 plo = __shfl_sync(0xffffffffu, to_lo, j), phi = __shfl_sync(0xffffffffu, to_hi, j);
+  *dstp = nullptr; *srcp = nullptr;
+  if (t < total) {
+    u8* tj = reinterpret_cast<u8*>((size_t)(((u64)phi << 32) | plo));
+    const u32 i = t - (end_j - len_j);
+    const u32 si = i < dist_j ? i : i % dist_j;
+    *dstp = tj + i; *srcp = tj - dist_j + si;
+  }
+}
+// 64 bytes per round (two per lane).  The loads of the LAST round are left in flight: their stores are issued by the next
+// call (or by inf_flush), after the next symbol has been decoded, so the L2 round trip of the copy overlaps the table
+// look-ups of the decode instead of adding to them.  Stores of a call are issued before its loads, with a warp barrier in
+// between (memory ordering among the lanes), because a match may read what the previous one wrote.
+__device__ __forceinline__ void inf_warp_copy(InfState& S, int lane, InfPending& P) {
   const u32 len = S.m_len;
+  if (!__any_sync(0xffffffffu, len != 0)) return;
   u32 incl = len;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { const u32 up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += up; }
   const u32 total = __shfl_sync(0xffffffffu, incl, 31);
-  if (total == 0) return;
   u8* const to = S.dst + S.o;
   const u64 to_bits = (u64)(size_t)to;
   const u32 to_lo = (u32)to_bits, to_hi = (u32)(to_bits >> 32);
-  for (u32 t0 = 0; t0 < total; t0 += 32) {
-    const u32 t = t0 + (u32)lane;
-    int lo = 0, hi = 31;
-#pragma unroll
-    for (int it = 0; it < 5; ++it) { const int mid = (lo + hi) >> 1; const u32 v = __shfl_sync(0xffffffffu, incl, mid); if (v > t) hi = mid; else lo = mid + 1; }
-    const int j = lo > 31 ? 31 : lo;
-    const u32 end_j = __shfl_sync(0xffffffffu, incl, j), len_j = __shfl_sync(0xffffffffu, len, j), dist_j = __shfl_sync(0xffffffffu, S.m_dist, j);
-    const u32 plo = __shfl_sync(0xffffffffu, to_lo, j), phi = __shfl_sync(0xffffffffu, to_hi, j);
-    if (t < total) {
-      u8* tj = reinterpret_cast<u8*>((size_t)(((u64)phi << 32) | plo));
-      const u32 i = t - (end_j - len_j);
-      const u32 si = i < dist_j ? i : i % dist_j;
-      tj[i] = (tj - dist_j)[si];
-    }
+  for (u32 t0 = 0; t0 < total; t0 += 64) {
+    u8* d0; u8* d1; const u8* s0; const u8* s1;
+    inf_copy_assign(t0 + (u32)lane, total, incl, len, S.m_dist, to_lo, to_hi, &d0, &s0);
+    inf_copy_assign(t0 + 32 + (u32)lane, total, incl, len, S.m_dist, to_lo, to_hi, &d1, &s1);
+    inf_flush(P);
+    __syncwarp();
+    if (s0) { P.v0 = *s0; P.a0 = d0; }
+    if (s1) { P.v1 = *s1; P.a1 = d1; }
   }
   S.o += len; S.m_len = 0;
 }
@@ -270,14 +290,16 @@ __global__ void __launch_bounds__(INF_NT) k_bgzf_inflate(const u8* __restrict__ 
       S.dst = U + B.dst; S.dst_len = B.dst_len; S.phase = INF_HEADER;
     }
   }
+  InfPending P; P.a0 = nullptr; P.a1 = nullptr; P.v0 = 0; P.v1 = 0;
   while (__any_sync(0xffffffffu, S.phase != INF_DONE)) {
     // lanes that need a block header (table construction: long) go first and together; the others decode symbols
     if (__any_sync(0xffffffffu, S.phase == INF_HEADER)) { if (S.phase == INF_HEADER) inf_block_header(S, T); }
     else {
 #pragma unroll 1
-      for (int it = 0; it < 8; ++it) { if (S.phase == INF_SYMS) inf_symbol(S, T, tab); __syncwarp(); inf_warp_copy(S, T.lane); }
+      for (int it = 0; it < 8; ++it) { if (S.phase == INF_SYMS) inf_symbol(S, T, tab); __syncwarp(); inf_warp_copy(S, T.lane, P); }
     }
   }
+  inf_flush(P);
   if (S.rc) { atomicOr(err + 1, (int)BAM_ERR_INFLATE); atomicMax(err + 2, S.rc); }
 }
 
