@@ -261,7 +261,10 @@ __device__ __forceinline__ void inf_warp_copy(InfState& S, int lane, InfPending&
 }
 
 // inflate: one thread per BGZF block of the chunk, the warp re-converged after every step
-__global__ void __launch_bounds__(INF_NT) k_bgzf_inflate(const u8* __restrict__ comp, const BgzfBlock* __restrict__ blk, int nblk, u8* __restrict__ U,
+#ifndef INF_MINB
+#define INF_MINB 1
+#endif
+__global__ void __launch_bounds__(INF_NT, INF_MINB) k_bgzf_inflate(const u8* __restrict__ comp, const BgzfBlock* __restrict__ blk, int nblk, u8* __restrict__ U,
                                                          u16* __restrict__ tabs, int* __restrict__ err) {
   __shared__ u16 tab[120];
   __shared__ u16 cnts[32 * INF_NT];
