@@ -298,13 +298,31 @@ def make_reads(L: int, seed: int, fasta: np.ndarray | None = None, coverage: flo
     return reads, events
 
 
-def _bam_records(R: dict, tid: int, lo: int, hi: int, random_seq):
-    """records lo..hi of one contig's reads as BAM bytes (bam1_core_t layout, bam.h:131-155)"""
+def _fill_var(buf, starts, lens, values):
+    """buf[starts[r] + k] = values[...] for k < lens[r], all records at once"""
+    lens = np.asarray(lens, np.int64)
+    tot = int(lens.sum())
+    if tot == 0:
+        return
+    idx = np.repeat(np.asarray(starts, np.int64), lens) + (np.arange(tot) - np.repeat(np.cumsum(lens) - lens, lens))
+    buf[idx] = values
+
+
+def _bam_records(R: dict, tid: int, lo: int, hi: int, random_seq, rich=None):
+    """records lo..hi of one contig's reads as BAM bytes (bam1_core_t layout, bam.h:131-155).  rich=SEED: what real files
+    carry and the path must skip -- read names of varying length, random bases, optional fields after the qualities."""
     nr = hi - lo
     co_all = R["cigar_off"].astype(np.int64); qo_all = R["qual_off"].astype(np.int64)
     co = co_all[lo:hi]; ncig = co_all[lo + 1:hi + 1] - co; qo = qo_all[lo:hi]; lq = qo_all[lo + 1:hi + 1] - qo
-    lname = 2  # "r\0"
-    size = 32 + lname + 4 * ncig + (lq + 1) // 2 + lq   # block_size payload (without the 4-byte length)
+    rs = np.random.default_rng([rich if rich is not None else (random_seq or 0), tid, lo])
+    if rich is not None:
+        lname = rs.integers(2, 25, nr).astype(np.int64)          # incl. the NUL
+        laux = np.where(rs.random(nr) < 0.7, rs.integers(4, 64, nr), 0).astype(np.int64)
+    else:
+        lname = np.full(nr, 2, np.int64)  # "r\0"
+        laux = np.zeros(nr, np.int64)
+    nseq = (lq + 1) // 2
+    size = 32 + lname + 4 * ncig + nseq + lq + laux   # block_size payload (without the 4-byte length)
     offs = np.concatenate(([0], np.cumsum(size + 4)))
     buf = np.zeros(int(offs[-1]), np.uint8)
     o = offs[:-1]
@@ -324,52 +342,47 @@ def _bam_records(R: dict, tid: int, lo: int, hi: int, random_seq):
     b = _reg2bin(pos, np.maximum(end, pos + 1))
     put32(0, size)
     put32(4, np.full(nr, tid)); put32(8, R["pos"][lo:hi])
-    put32(12, (b.astype(np.uint32) << 16) | (R["mapq"][lo:hi].astype(np.uint32) << 8) | lname)
+    put32(12, (b.astype(np.uint32) << 16) | (R["mapq"][lo:hi].astype(np.uint32) << 8) | lname.astype(np.uint32))
     put32(16, (R["flag"][lo:hi].astype(np.uint32) << 16) | ncig.astype(np.uint32))
     put32(20, lq); put32(24, R["mtid"][lo:hi]); put32(28, R["mpos"][lo:hi]); put32(32, R["isize"][lo:hi])
-    buf[o + 36] = ord("r")
-    for k in range(int(ncig.max()) if nr else 0):
-        sel = np.flatnonzero(ncig > k)
-        v = np.ascontiguousarray(cig[c0[sel] + k].astype("<u4")).view(np.uint8).reshape(-1, 4)
-        for bb in range(4):
-            buf[o[sel] + 38 + 4 * k + bb] = v[:, bb]
-    # packed sequence (all 'A' = 1, or random bases) and qualities
-    soff = o + 38 + 4 * ncig
-    nseq = (lq + 1) // 2
-    nib = np.array([1, 2, 4, 8], np.uint8)
-    rs = np.random.default_rng([random_seq, tid, lo]) if random_seq is not None else None
-    qual = R["qual"][int(qo_all[lo]):int(qo_all[hi])]
-    if nr and np.all(lq == lq[0]):
-        l0 = int(lq[0]); ns0 = int(nseq[0])
-        ii = (soff[:, None] + np.arange(ns0)[None, :]).ravel()
-        if rs is None:
-            buf[ii] = 0x11
-        else:
-            buf[ii] = (nib[rs.integers(0, 4, len(ii))] << 4) | nib[rs.integers(0, 4, len(ii))]
-        if l0 % 2:
-            buf[soff + ns0 - 1] &= 0xf0
-        qi = (soff[:, None] + ns0 + np.arange(l0)[None, :]).ravel()
-        buf[qi] = qual
+    # read name: printable characters, NUL-terminated
+    if rich is not None:
+        _fill_var(buf, o + 36, lname - 1, rs.integers(33, 127, int((lname - 1).sum())).astype(np.uint8))
     else:
-        q0 = qo - qo_all[lo]
-        for r in range(nr):
-            if rs is None:
-                buf[soff[r]:soff[r] + nseq[r]] = 0x11
-            else:
-                buf[soff[r]:soff[r] + nseq[r]] = (nib[rs.integers(0, 4, int(nseq[r]))] << 4) | nib[rs.integers(0, 4, int(nseq[r]))]
-            if lq[r] % 2:
-                buf[soff[r] + nseq[r] - 1] &= 0xf0
-            buf[soff[r] + nseq[r]:soff[r] + nseq[r] + lq[r]] = qual[q0[r]:q0[r] + lq[r]]
+        buf[o + 36] = ord("r")
+    # CIGAR words
+    _fill_var(buf, o + 36 + lname, 4 * ncig, np.ascontiguousarray(cig.astype("<u4")).view(np.uint8))
+    # packed sequence (all 'A' = 1, or random bases) and qualities
+    soff = o + 36 + lname + 4 * ncig
+    nib = np.array([1, 2, 4, 8], np.uint8)
+    nst = int(nseq.sum())
+    if random_seq is None and rich is None:
+        seqb = np.full(nst, 0x11, np.uint8)
+    else:
+        seqb = ((nib[rs.integers(0, 4, nst)] << 4) | nib[rs.integers(0, 4, nst)]).astype(np.uint8)
+    _fill_var(buf, soff, nseq, seqb)
+    odd = np.flatnonzero(lq % 2 == 1)
+    buf[soff[odd] + nseq[odd] - 1] &= 0xf0
+    _fill_var(buf, soff + nseq, lq, R["qual"][int(qo_all[lo]):int(qo_all[hi])])
+    # optional fields: "XA:Z:<text>\0"-shaped bytes (never parsed on this path)
+    if rich is not None and int(laux.sum()):
+        aux = rs.integers(33, 127, int(laux.sum())).astype(np.uint8)
+        _fill_var(buf, soff + nseq + lq, laux, aux)
+        has = np.flatnonzero(laux > 0)
+        a0 = (soff + nseq + lq)[has]
+        buf[a0] = ord("X"); buf[a0 + 1] = ord("A"); buf[a0 + 2] = ord("Z"); buf[a0 + laux[has] - 1] = 0
     return buf.tobytes()
 
 
 def write_bam(path: str, contigs: list[tuple[str, int]], reads_by_tid: dict[int, dict], level: int = 1, strategy: int = 0,
-              block_size: int = 65280, random_seq: int | None = None, threads: int = 8) -> None:
+              block_size: int = 65280, random_seq: int | None = None, threads: int = 8, rich: int | None = None,
+              unmapped_tail: int = 0) -> None:
     """Minimal BAM (BGZF) writer for the synthetic reads: one record per read, name 'r', sequence all 'A'
     (the path never looks at bases; random_seq=SEED writes random bases instead, which makes the file compress like a
     real one), qualities as given.  strategy: zlib strategy (zlib.Z_FIXED forces fixed-Huffman blocks), level 0 writes
     stored blocks; records are NOT aligned to BGZF blocks.  Reads are serialised in slabs and the blocks compressed on a
-    thread pool, so a chr19-sized file takes about a minute.  Layout: SURVEY.md Appendix B."""
+    thread pool, so a chr19-sized file takes about a minute.  rich=SEED writes real-looking records (names, bases, optional
+    fields); unmapped_tail appends that many refID -1 records.  Layout: SURVEY.md Appendix B."""
     import struct
     import zlib
     from concurrent.futures import ThreadPoolExecutor
@@ -384,7 +397,11 @@ def write_bam(path: str, contigs: list[tuple[str, int]], reads_by_tid: dict[int,
             R = reads_by_tid[tid]
             nr = len(R["pos"])
             for lo in range(0, nr, 1 << 19):
-                yield _bam_records(R, tid, lo, min(nr, lo + (1 << 19)), random_seq)
+                yield _bam_records(R, tid, lo, min(nr, lo + (1 << 19)), random_seq, rich)
+        for u in range(unmapped_tail):    # unplaced, unmapped reads: refID -1, pos -1, flag 4, no CIGAR
+            name = b"unm%d\x00" % u
+            body = struct.pack("<iiIIiiii", -1, -1, (4680 << 16) | len(name), (4 << 16), 10, -1, -1, 0) + name + b"\x11" * 5 + b"\x1e" * 10
+            yield struct.pack("<I", len(body)) + body
 
     def bgzf(blk: bytes) -> bytes:
         co = zlib.compressobj(level, zlib.DEFLATED, -15, 8, strategy)

@@ -100,3 +100,36 @@ def test_cli_depth_file_matches_reference(cli, tmp_path):
     out = subprocess.run([cli] + common + ["-o", str(tmp_path / "ours.txt")], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
     assert open(str(tmp_path / "ours.txt")).read() == open(str(tmp_path / "ref.txt")).read()
+
+
+def test_host_decoder_real_looking_records(cli, tmp_path):
+    """the zlib reader on records with names, bases, optional fields and an unmapped tail"""
+    r1, _ = synth.make_reads(120_000, 5, None, coverage=6, n_events=0, tid=0)
+    bam = str(tmp_path / "t.bam")
+    synth.write_bam(bam, [("1", 120_000)], {0: r1}, level=6, rich=3, unmapped_tail=10)
+    out = subprocess.run([cli, "decode", "-b", bam, "-c", "1", "-o", str(tmp_path / "d")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    for f, dt in FIELDS:
+        assert np.array_equal(np.fromfile(str(tmp_path / ("d." + f)), dtype=dt), r1[f]), f
+
+
+@pytest.mark.gpu
+def test_cli_real_looking_bam_matches_reference(cli, tmp_path):
+    """records as real files carry them (names, bases, optional fields, unmapped reads at the end): GPU decode, host decode and
+    the unmodified reference CLI give the same table"""
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    L = 10_400_000
+    fa = synth.make_fasta(L, 6)
+    r, _ = synth.make_reads(L, 6, fa, coverage=12, n_events=5, lens=(3000, 8000, 20000), tid=0)
+    bam = str(tmp_path / "t.bam"); fasta = str(tmp_path / "t.fa")
+    synth.write_bam(bam, [("7", L), ("MT", 16569)], {0: r}, level=6, rich=11, unmapped_tail=100)
+    synth.write_fasta_multi(fasta, [("7", fa)])
+    subprocess.run([REF_BAMTOOL, "index", bam], check=True)
+    common = ["rsi", "-b", bam, "-f", fasta, "-q", "0", "-Q", "10", "-np"]
+    subprocess.run([REF_BIN] + common + ["-o", str(tmp_path / "ref.txt")], check=True, capture_output=True)
+    for extra, name in (([], "gpu.txt"), (["-hostdecode"], "host.txt")):
+        out = subprocess.run([cli] + common + extra + ["-o", str(tmp_path / name)], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        assert _table(str(tmp_path / name)) == _table(str(tmp_path / "ref.txt")), name
+    assert len(_table(str(tmp_path / "ref.txt"))) > 3

@@ -32,6 +32,10 @@ def test_decoded_reads_give_the_same_calls(gpu_lib, tmp_path):
     T.test_decoded_reads_give_the_same_calls(gpu_lib, tmp_path)
 
 
+def test_real_looking_records(gpu_lib, tmp_path):
+    T.test_real_looking_records(gpu_lib, tmp_path)
+
+
 def test_large_file_all_fields(gpu_lib, tmp_path):
     """12 Mbp at 30x (3.6 M records, ~13 k BGZF blocks), fed in 32 MiB pieces"""
     L = 12_000_000

@@ -231,3 +231,16 @@ def test_mixed_block_types_inside_one_stream(sim_lib, tmp_path):
     _rebgzf(src, dst, comp)
     got, h = decode_file(sim_lib, dst, 100000)
     assert_same_reads(got[0], reads)
+
+
+def test_real_looking_records(sim_lib, tmp_path):
+    """read names of varying length, random bases, optional fields after the qualities, unmapped reads (refID -1) at the end"""
+    contigs = [("1", 70000), ("2", 50000)]
+    rb = {0: make_reads(70000, 61, cov=8)[1], 1: make_reads(50000, 62, cov=5)[1]}
+    path = str(tmp_path / "t.bam")
+    synth.write_bam(path, contigs, rb, level=6, rich=9, unmapped_tail=25)
+    got, h = decode_file(sim_lib, path, 64000)
+    assert sorted(got) == [-1, 0, 1]
+    assert len(got[-1]["pos"]) == 25 and np.all(got[-1]["pos"] == -1)
+    for tid in (0, 1):
+        assert_same_reads(got[tid], rb[tid])
