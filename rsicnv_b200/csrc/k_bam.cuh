@@ -21,15 +21,23 @@
 
 namespace rsigpu {
 
+#ifndef INF_FB_BITS
+#define INF_FB_BITS 9
+#endif
+#ifndef INF_DB_BITS
+#define INF_DB_BITS 6
+#endif
 enum {
   INF_NT = 128,                    // threads per CTA, one BGZF block per thread
-  INF_FB = 10, INF_DB = 7,         // bits of the direct-lookup tables (literal/length, distance)
+  INF_FB = INF_FB_BITS, INF_DB = INF_DB_BITS,   // bits of the direct-lookup tables (literal/length, distance)
   INF_LF = 0,                      // per-thread table layout in GLOBAL memory, in u16 slots
   INF_LS = INF_LF + (1 << INF_FB), // literal/length symbols ordered by code
   INF_DF = INF_LS + 288,
   INF_DS = INF_DF + (1 << INF_DB),
   INF_GSLOTS = INF_DS + 32,
-  INF_LC = 0, INF_DC = 16          // code-length counts: shared memory, 32 u16 per thread
+  INF_LC = 0, INF_DC = 16,         // code-length counts: shared memory, 16 u16 each per thread
+  INF_NC = 32,                     // next code per length while a table is built (shared, 16 u16 per thread)
+  INF_SSLOTS = 48                  // u16 slots of shared memory per thread; plus 128 bytes for the code-length code's direct table
 };
 // table scratch for n BGZF blocks (whole warps)
 #define RSI_INFLATE_TAB_BYTES(nblk) ((size_t)(((nblk) + 31) / 32) * 32 * INF_GSLOTS * 2)
@@ -44,16 +52,19 @@ struct BgzfBlock { u64 dst; u32 src, src_len, dst_len, pad_; };   // payload off
 struct BitIn {
   const u8* base; u32 pos, end;   // word-aligned base, next byte to load, one past the payload (both relative to base)
   u64 buf; int cnt;
+  u32 nextw;                      // the word at `pos`, loaded one refill ahead so that a refill never waits for memory
 };
-// byte loads until the next load is word aligned (at most 3)
+__device__ __forceinline__ u32 bits_word(const BitIn& b, u32 pos) { return pos < b.end + 8 ? *reinterpret_cast<const u32*>(b.base + pos) : 0u; }
+// byte loads until the next load is word aligned (at most 3), then prime the look-ahead word
 __device__ __forceinline__ void bits_align(BitIn& b) {
   while ((b.pos & 3u) && b.cnt <= 56) { b.buf |= (u64)(b.pos < b.end + 8 ? b.base[b.pos] : 0) << b.cnt; b.cnt += 8; b.pos++; }
+  b.nextw = bits_word(b, b.pos);
 }
 // at least 33 valid bits afterwards; the payload is followed by the block's 8-byte footer, so the last word load stays inside the chunk
 __device__ __forceinline__ void bits_refill(BitIn& b) {
   if (b.cnt <= 32) {
-    const u32 w = b.pos < b.end + 8 ? *reinterpret_cast<const u32*>(b.base + b.pos) : 0u;
-    b.buf |= (u64)w << b.cnt; b.cnt += 32; b.pos += 4;
+    b.buf |= (u64)b.nextw << b.cnt; b.cnt += 32; b.pos += 4;
+    b.nextw = bits_word(b, b.pos);
   }
 }
 __device__ __forceinline__ u32 bits_take(BitIn& b, int n) { const u32 v = (u32)(b.buf & ((1ull << n) - 1)); b.buf >>= n; b.cnt -= n; return v; }
@@ -62,12 +73,15 @@ __device__ __forceinline__ u32 bits_take(BitIn& b, int n) { const u32 v = (u32)(
 // at 2.7 KB per thread, shared memory would hold three warps per SM, and one thread's decode loop is a chain of dependent
 // loads that only many resident warps can hide.  Slot i of lane l is at g[i * 32 + l] (a warp's tables are interleaved, so
 // the construction loops -- same i in every lane -- are coalesced).  The 2 x 16 code-length counts sit in shared memory.
-struct InfTabs { u16* g; u16* s; int lane, stid; };
+struct InfTabs { u16* g; u16* s; u8* cl; int lane, stid; };
 #define INF_G(i) T.g[(size_t)(i) * 32 + T.lane]
 #define INF_C(i) T.s[(i) * INF_NT + T.stid]
+#define INF_CL(i) T.cl[(i) * INF_NT + T.stid]
 
 // canonical code from code lengths (count/symbol form, plus a direct table for codes of <= fb bits whose
 // entries are symbol << 4 | length).  Returns < 0 for an over-subscribed set, > 0 for an incomplete one.
+// One pass over the symbols: codes are handed out in symbol order per length (next-code counters in shared memory), so the
+// direct table is filled without reading back anything that was just written to global memory.
 __device__ int inf_construct(const InfTabs& T, const u8* lens, int n, int fast, int fb, int cnts, int syms) {
   for (int l = 0; l < 16; ++l) INF_C(cnts + l) = 0;
   for (int s = 0; s < n; ++s) INF_C(cnts + lens[s]) += 1;
@@ -78,16 +92,17 @@ __device__ int inf_construct(const InfTabs& T, const u8* lens, int n, int fast, 
   u16 offs[16];
   offs[1] = 0;
   for (int l = 1; l < 15; ++l) offs[l + 1] = (u16)(offs[l] + INF_C(cnts + l));
-  for (int s = 0; s < n; ++s) if (lens[s]) { INF_G(syms + offs[lens[s]]) = (u16)s; offs[lens[s]]++; }
-  int code = 0, index = 0;
-  for (int l = 1; l <= fb; ++l) {
-    const int cn = (int)INF_C(cnts + l);
-    for (int j = 0; j < cn; ++j) {
-      const u32 rev = __brev((u32)(code + j)) >> (32 - l);
-      const u16 e = (u16)((INF_G(syms + index + j) << 4) | l);
+  { int code = 0; for (int l = 1; l <= 15; ++l) { INF_C(INF_NC + l) = (u16)code; code = (code + (int)INF_C(cnts + l)) << 1; } }
+  for (int s = 0; s < n; ++s) {
+    const int l = lens[s];
+    if (!l) continue;
+    INF_G(syms + offs[l]) = (u16)s; offs[l]++;
+    const u32 code = INF_C(INF_NC + l); INF_C(INF_NC + l) = (u16)(code + 1);
+    if (l <= fb) {
+      const u32 rev = __brev(code) >> (32 - l);
+      const u16 e = (u16)((s << 4) | l);
       for (u32 k = rev; k < (1u << fb); k += (1u << l)) INF_G(fast + k) = e;
     }
-    index += cn; code = (code + cn) << 1;
   }
   return left;
 }
@@ -102,6 +117,30 @@ __device__ __forceinline__ int inf_decode(BitIn& b, const InfTabs& T, int fast, 
     index += cn; first += cn; first <<= 1; code <<= 1;
   }
   return -1;
+}
+// the code-length code (19 symbols, codes of <= 7 bits): a 128-entry direct table in shared memory, entry = symbol << 3 | length
+__device__ int inf_construct_cl(const InfTabs& T, const u8* lens) {
+  for (int l = 0; l < 8; ++l) INF_C(INF_LC + l) = 0;
+  for (int s = 0; s < 19; ++s) INF_C(INF_LC + (lens[s] & 7)) += 1;
+  for (int i = 0; i < 128; ++i) INF_CL(i) = 0;
+  int left = 1, code = 0;
+  for (int l = 1; l < 8; ++l) { left <<= 1; left -= (int)INF_C(INF_LC + l); INF_C(INF_NC + l) = (u16)code; code = (code + (int)INF_C(INF_LC + l)) << 1; }
+  if (left != 0) return left < 0 ? -1 : 1;
+  for (int s = 0; s < 19; ++s) {
+    const int l = lens[s];
+    if (!l) continue;
+    const u32 c = INF_C(INF_NC + l); INF_C(INF_NC + l) = (u16)(c + 1);
+    const u32 rev = __brev(c) >> (32 - l);
+    const u8 e = (u8)((s << 3) | l);
+    for (u32 k = rev; k < 128u; k += (1u << l)) INF_CL(k) = e;
+  }
+  return 0;
+}
+__device__ __forceinline__ int inf_decode_cl(BitIn& b, const InfTabs& T) {
+  const u32 e = INF_CL((u32)(b.buf & 127u));
+  if (!e) return -1;
+  const int l = (int)(e & 7u); b.buf >>= l; b.cnt -= l;
+  return (int)(e >> 3);
 }
 
 // One raw-deflate stream -> dst[0, dst_len), as a stepper: the lanes of a warp work on 32 different streams, and a
@@ -118,7 +157,7 @@ enum { INF_HEADER = 0, INF_SYMS = 1, INF_DONE = 2 };
 
 __device__ __forceinline__ void inf_fail(InfState& S, int rc) { S.rc = rc; S.phase = INF_DONE; }
 
-__device__ void inf_block_header(InfState& S, const InfTabs& T) {
+__device__ __noinline__ void inf_block_header(InfState& S, const InfTabs& T) {
   BitIn& b = S.b;
   bits_refill(b);
   S.last = (int)bits_take(b, 1);
@@ -154,11 +193,11 @@ __device__ void inf_block_header(InfState& S, const InfTabs& T) {
     const u8 order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
     for (int i = 0; i < 19; ++i) lens[i] = 0;
     for (int i = 0; i < ncode; ++i) { bits_refill(b); lens[order[i]] = (u8)bits_take(b, 3); }
-    if (inf_construct(T, lens, 19, INF_LF, 7, INF_LC, INF_LS) != 0) return inf_fail(S, 6);   // the code-length code must be complete
+    if (inf_construct_cl(T, lens) != 0) return inf_fail(S, 6);   // the code-length code must be complete
     int idx = 0;
     while (idx < nlen + ndist) {
       bits_refill(b);
-      const int sym = inf_decode(b, T, INF_LF, 7, INF_LC, INF_LS);
+      const int sym = inf_decode_cl(b, T);
       if (sym < 0) return inf_fail(S, 7);
       if (sym < 16) lens[idx++] = (u8)sym;
       else {
@@ -267,7 +306,8 @@ __device__ __forceinline__ void inf_warp_copy(InfState& S, int lane, InfPending&
 __global__ void __launch_bounds__(INF_NT, INF_MINB) k_bgzf_inflate(const u8* __restrict__ comp, const BgzfBlock* __restrict__ blk, int nblk, u8* __restrict__ U,
                                                          u16* __restrict__ tabs, int* __restrict__ err) {
   __shared__ u16 tab[120];
-  __shared__ u16 cnts[32 * INF_NT];
+  __shared__ u16 cnts[INF_SSLOTS * INF_NT];
+  __shared__ u8 cltab[128 * INF_NT];
   {
     const u16 lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
     const u16 lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
@@ -278,7 +318,7 @@ __global__ void __launch_bounds__(INF_NT, INF_MINB) k_bgzf_inflate(const u8* __r
   }
   __syncthreads();
   const int k = (int)blockIdx.x * INF_NT + (int)threadIdx.x;
-  InfTabs T; T.lane = (int)(threadIdx.x & 31); T.stid = (int)threadIdx.x; T.s = cnts;
+  InfTabs T; T.lane = (int)(threadIdx.x & 31); T.stid = (int)threadIdx.x; T.s = cnts; T.cl = cltab;
   T.g = tabs + (size_t)(k >> 5) * 32 * INF_GSLOTS;
   InfState S;
   S.phase = INF_DONE; S.rc = 0; S.o = 0; S.dst_len = 0; S.dst = U; S.last = 0; S.m_len = 0; S.m_dist = 1;
