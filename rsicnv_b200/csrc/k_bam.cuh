@@ -37,7 +37,8 @@ enum {
   INF_GSLOTS = INF_DS + 32,
   INF_LC = 0, INF_DC = 16,         // code-length counts: shared memory, 16 u16 each per thread
   INF_NC = 32,                     // next code per length while a table is built (shared, 16 u16 per thread)
-  INF_SSLOTS = 48                  // u16 slots of shared memory per thread; plus 128 bytes for the code-length code's direct table
+  INF_LX = 48, INF_DX = 50,        // canonical-decode state after the direct table's bits: first, index (2 u16 per table)
+  INF_SSLOTS = 52                  // u16 slots of shared memory per thread; plus 128 bytes for the code-length code's direct table
 };
 // table scratch for n BGZF blocks (whole warps)
 #define RSI_INFLATE_TAB_BYTES(nblk) ((size_t)(((nblk) + 31) / 32) * 32 * INF_GSLOTS * 2)
@@ -82,7 +83,7 @@ struct InfTabs { u16* g; u16* s; u8* cl; int lane, stid; };
 // entries are symbol << 4 | length).  Returns < 0 for an over-subscribed set, > 0 for an incomplete one.
 // One pass over the symbols: codes are handed out in symbol order per length (next-code counters in shared memory), so the
 // direct table is filled without reading back anything that was just written to global memory.
-__device__ int inf_construct(const InfTabs& T, const u8* lens, int n, int fast, int fb, int cnts, int syms) {
+__device__ int inf_construct(const InfTabs& T, const u8* lens, int n, int fast, int fb, int cnts, int syms, int xs) {
   for (int l = 0; l < 16; ++l) INF_C(cnts + l) = 0;
   for (int s = 0; s < n; ++s) INF_C(cnts + lens[s]) += 1;
   for (int i = 0; i < (1 << fb); ++i) INF_G(fast + i) = 0;
@@ -93,6 +94,7 @@ __device__ int inf_construct(const InfTabs& T, const u8* lens, int n, int fast, 
   offs[1] = 0;
   for (int l = 1; l < 15; ++l) offs[l + 1] = (u16)(offs[l] + INF_C(cnts + l));
   { int code = 0; for (int l = 1; l <= 15; ++l) { INF_C(INF_NC + l) = (u16)code; code = (code + (int)INF_C(cnts + l)) << 1; } }
+  { int first = 0, index = 0; for (int l = 1; l <= fb; ++l) { const int cn = (int)INF_C(cnts + l); index += cn; first += cn; first <<= 1; } INF_C(xs) = (u16)first; INF_C(xs + 1) = (u16)index; }
   for (int s = 0; s < n; ++s) {
     const int l = lens[s];
     if (!l) continue;
@@ -106,11 +108,14 @@ __device__ int inf_construct(const InfTabs& T, const u8* lens, int n, int fast, 
   }
   return left;
 }
-__device__ __forceinline__ int inf_decode(BitIn& b, const InfTabs& T, int fast, int fb, int cnts, int syms) {
-  const u32 e = INF_G(fast + (u32)(b.buf & ((1u << fb) - 1)));
+__device__ __forceinline__ int inf_decode(BitIn& b, const InfTabs& T, int fast, int fb, int cnts, int syms, int xs) {
+  const u32 low = (u32)(b.buf & ((1u << fb) - 1));
+  const u32 e = INF_G(fast + low);
   if (e) { const int l = (int)(e & 15u); b.buf >>= l; b.cnt -= l; return (int)(e >> 4); }
-  int code = 0, first = 0, index = 0; u64 bits = b.buf;
-  for (int l = 1; l <= 15; ++l) {
+  // longer than fb bits: canonical walk (count / first / index per length), resumed after the fb bits already seen
+  int code = (int)((__brev(low) >> (32 - fb)) << 1), first = (int)INF_C(xs), index = (int)INF_C(xs + 1);
+  u64 bits = b.buf >> fb;
+  for (int l = fb + 1; l <= 15; ++l) {
     code |= (int)(bits & 1); bits >>= 1;
     const int cn = (int)INF_C(cnts + l);
     if (code - cn < first) { b.buf >>= l; b.cnt -= l; return (int)INF_G(syms + index + (code - first)); }
@@ -183,9 +188,9 @@ __device__ __noinline__ void inf_block_header(InfState& S, const InfTabs& T) {
     for (int s = 144; s < 256; ++s) lens[s] = 9;
     for (int s = 256; s < 280; ++s) lens[s] = 7;
     for (int s = 280; s < 288; ++s) lens[s] = 8;
-    inf_construct(T, lens, 288, INF_LF, INF_FB, INF_LC, INF_LS);
+    inf_construct(T, lens, 288, INF_LF, INF_FB, INF_LC, INF_LS, INF_LX);
     for (int s = 0; s < 30; ++s) lens[s] = 5;
-    inf_construct(T, lens, 30, INF_DF, INF_DB, INF_DC, INF_DS);
+    inf_construct(T, lens, 30, INF_DF, INF_DB, INF_DC, INF_DS, INF_DX);
   } else {
     bits_refill(b);
     const int nlen = (int)bits_take(b, 5) + 257, ndist = (int)bits_take(b, 5) + 1, ncode = (int)bits_take(b, 4) + 4;
@@ -210,9 +215,9 @@ __device__ __noinline__ void inf_block_header(InfState& S, const InfTabs& T) {
       }
     }
     if (lens[256] == 0) return inf_fail(S, 10);
-    int r = inf_construct(T, lens, nlen, INF_LF, INF_FB, INF_LC, INF_LS);
+    int r = inf_construct(T, lens, nlen, INF_LF, INF_FB, INF_LC, INF_LS, INF_LX);
     if (r < 0 || (r > 0 && nlen - (int)INF_C(INF_LC) != 1)) return inf_fail(S, 11);       // incomplete only allowed for a single code
-    r = inf_construct(T, lens + nlen, ndist, INF_DF, INF_DB, INF_DC, INF_DS);
+    r = inf_construct(T, lens + nlen, ndist, INF_DF, INF_DB, INF_DC, INF_DS, INF_DX);
     if (r < 0 || (r > 0 && ndist - (int)INF_C(INF_DC) != 1)) return inf_fail(S, 12);
   }
   S.phase = INF_SYMS;
@@ -221,7 +226,7 @@ __device__ __noinline__ void inf_block_header(InfState& S, const InfTabs& T) {
 __device__ __forceinline__ void inf_symbol(InfState& S, const InfTabs& T, const u16* tab) {
   BitIn& b = S.b;
   bits_refill(b);
-  int sym = inf_decode(b, T, INF_LF, INF_FB, INF_LC, INF_LS);
+  int sym = inf_decode(b, T, INF_LF, INF_FB, INF_LC, INF_LS, INF_LX);
   if (sym < 256) {
     if (sym < 0) return inf_fail(S, 13);
     if (S.o >= S.dst_len) return inf_fail(S, 3);
@@ -237,7 +242,7 @@ __device__ __forceinline__ void inf_symbol(InfState& S, const InfTabs& T, const 
   if (sym >= 29) return inf_fail(S, 14);
   const u32 len = (u32)tab[sym] + bits_take(b, (int)tab[29 + sym]);
   bits_refill(b);
-  const int ds = inf_decode(b, T, INF_DF, INF_DB, INF_DC, INF_DS);
+  const int ds = inf_decode(b, T, INF_DF, INF_DB, INF_DC, INF_DS, INF_DX);
   if (ds < 0 || ds >= 30) return inf_fail(S, 15);
   const u32 dist = (u32)tab[58 + ds] + bits_take(b, (int)tab[88 + ds]);
   if (dist > S.o) return inf_fail(S, 16);
@@ -251,50 +256,46 @@ __device__ __forceinline__ void inf_symbol(InfState& S, const InfTabs& T, const 
 // end to end and dealt to the lanes 32 at a time (the owner of a byte is found by a search over the warp's prefix sums):
 // all loads of a round are independent and consecutive lanes touch consecutive addresses, instead of one lane copying
 // byte by byte (a load -> store -> load chain through L2) while 31 wait.
-struct InfPending { u8* a0; u8* a1; u32 v0, v1; };   // bytes loaded by the last round of inf_warp_copy, stored by the next call (a == nullptr: none)
+struct InfPending { u8* a0; u8* a1; u32 v0, v1; };   // bytes loaded by inf_warp_copy whose stores are still to be issued (a == nullptr: none)
 
 __device__ __forceinline__ void inf_flush(InfPending& P) {
   if (P.a0) { *P.a0 = (u8)P.v0; P.a0 = nullptr; }
   if (P.a1) { *P.a1 = (u8)P.v1; P.a1 = nullptr; }
 }
-// owner of flattened byte t among the warp's matches: lane j (smallest j with incl_j > t), and the byte's source / destination
-__device__ __forceinline__ void inf_copy_assign(u32 t, u32 total, u32 incl, u32 len, u32 dist, u32 to_lo, u32 to_hi, u8** dstp, const u8** srcp) {
-  int lo = 0, hi = 31;
-#pragma unroll
-  for (int it = 0; it < 5; ++it) { const int mid = (lo + hi) >> 1; const u32 v = __shfl_sync(0xffffffffu, incl, mid); if (v > t) hi = mid; else lo = mid + 1; }
-  const int j = lo > 31 ? 31 : lo;
-  const u32 end_j = __shfl_sync(0xffffffffu, incl, j), len_j = __shfl_sync(0xffffffffu, len, j), dist_j = __shfl_sync(0xffffffffu, dist, j);
-  const u32 plo = __shfl_sync(0xffffffffu, to_lo, j), phi = __shfl_sync(0xffffffffu, to_hi, j);
-  *dstp = nullptr; *srcp = nullptr;
-  if (t < total) {
-    u8* tj = reinterpret_cast<u8*>((size_t)(((u64)phi << 32) | plo));
-    const u32 i = t - (end_j - len_j);
-    const u32 si = i < dist_j ? i : i % dist_j;
-    *dstp = tj + i; *srcp = tj - dist_j + si;
-  }
+// One match, 32 bytes at a time (a "unit": at most one byte per lane).  Units of one call never depend on each other, so a
+// lane keeps up to two loaded bytes in flight: a unit first stores what its slot still holds, then loads.
+__device__ __forceinline__ void inf_copy_unit(u8*& pa, u32& pv, u8* tj, u32 i, u32 len_j, u32 dist_j) {
+  if (pa) { *pa = (u8)pv; pa = nullptr; }
+  if (i < len_j) { const u32 si = i < dist_j ? i : i % dist_j; pv = (tj - dist_j)[si]; pa = tj + i; }
 }
-// 64 bytes per round (two per lane).  The loads of the LAST round are left in flight: their stores are issued by the next
-// call (or by inf_flush), after the next symbol has been decoded, so the L2 round trip of the copy overlaps the table
-// look-ups of the decode instead of adding to them.  Stores of a call are issued before its loads, with a warp barrier in
-// between (memory ordering among the lanes), because a match may read what the previous one wrote.
+// The pending matches of all 32 lanes, copied by the whole warp.  A match byte i comes from i - dist, which for i >= dist is
+// a byte of the same match: the source is periodic, out[i] = src[i mod dist], so every byte is read from data that was
+// complete before the copy began.  The matches are taken one after the other (ballot), their parameters broadcast, and the
+// lanes copy 32 consecutive bytes per step -- coalesced, all loads independent -- instead of one lane copying byte by byte
+// (a load -> store -> load chain through L2) while 31 wait.  The last loads stay in flight: their stores are issued by the
+// next call (after the next symbol has been decoded) or by inf_flush, so the L2 round trip overlaps the table look-ups.
+// Stores of the previous call are issued before any load of this one, with a warp barrier in between (memory ordering
+// among the lanes), because a match may read what the previous one wrote.
 __device__ __forceinline__ void inf_warp_copy(InfState& S, int lane, InfPending& P) {
   const u32 len = S.m_len;
-  if (!__any_sync(0xffffffffu, len != 0)) return;
-  u32 incl = len;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { const u32 up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += up; }
-  const u32 total = __shfl_sync(0xffffffffu, incl, 31);
-  u8* const to = S.dst + S.o;
-  const u64 to_bits = (u64)(size_t)to;
+  u32 mask = __ballot_sync(0xffffffffu, len != 0);
+  if (!mask) return;
+  inf_flush(P);
+  __syncwarp();
+  const u32 ld = len | (S.m_dist << 9);                 // len <= 258 (9 bits), dist <= 32768
+  const u64 to_bits = (u64)(size_t)(S.dst + S.o);
   const u32 to_lo = (u32)to_bits, to_hi = (u32)(to_bits >> 32);
-  for (u32 t0 = 0; t0 < total; t0 += 64) {
-    u8* d0; u8* d1; const u8* s0; const u8* s1;
-    inf_copy_assign(t0 + (u32)lane, total, incl, len, S.m_dist, to_lo, to_hi, &d0, &s0);
-    inf_copy_assign(t0 + 32 + (u32)lane, total, incl, len, S.m_dist, to_lo, to_hi, &d1, &s1);
-    inf_flush(P);
-    __syncwarp();
-    if (s0) { P.v0 = *s0; P.a0 = d0; }
-    if (s1) { P.v1 = *s1; P.a1 = d1; }
+  int slot = 0;
+  while (mask) {
+    const int j = __ffs((int)mask) - 1; mask &= mask - 1;
+    const u32 ldj = __shfl_sync(0xffffffffu, ld, j), plo = __shfl_sync(0xffffffffu, to_lo, j), phi = __shfl_sync(0xffffffffu, to_hi, j);
+    const u32 len_j = ldj & 511u, dist_j = ldj >> 9;
+    u8* tj = reinterpret_cast<u8*>((size_t)(((u64)phi << 32) | plo));
+    for (u32 c = 0; c < len_j; c += 32) {
+      if (slot == 0) inf_copy_unit(P.a0, P.v0, tj, c + (u32)lane, len_j, dist_j);
+      else inf_copy_unit(P.a1, P.v1, tj, c + (u32)lane, len_j, dist_j);
+      slot ^= 1;
+    }
   }
   S.o += len; S.m_len = 0;
 }
@@ -336,7 +337,7 @@ __global__ void __launch_bounds__(INF_NT, INF_MINB) k_bgzf_inflate(const u8* __r
   InfPending P; P.a0 = nullptr; P.a1 = nullptr; P.v0 = 0; P.v1 = 0;
   while (__any_sync(0xffffffffu, S.phase != INF_DONE)) {
     // lanes that need a block header (table construction: long) go first and together; the others decode symbols
-    if (__any_sync(0xffffffffu, S.phase == INF_HEADER)) { if (S.phase == INF_HEADER) inf_block_header(S, T); }
+    if (__any_sync(0xffffffffu, S.phase == INF_HEADER)) { if (S.phase == INF_HEADER) { InfState H = S; inf_block_header(H, T); S = H; } }   // out of line: a copy keeps S in registers
     else {
 #pragma unroll 1
       for (int it = 0; it < 8; ++it) { if (S.phase == INF_SYMS) inf_symbol(S, T, tab); __syncwarp(); inf_warp_copy(S, T.lane, P); }
