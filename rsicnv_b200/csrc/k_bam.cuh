@@ -256,46 +256,50 @@ __device__ __forceinline__ void inf_symbol(InfState& S, const InfTabs& T, const 
 // end to end and dealt to the lanes 32 at a time (the owner of a byte is found by a search over the warp's prefix sums):
 // all loads of a round are independent and consecutive lanes touch consecutive addresses, instead of one lane copying
 // byte by byte (a load -> store -> load chain through L2) while 31 wait.
-struct InfPending { u8* a0; u8* a1; u32 v0, v1; };   // bytes loaded by inf_warp_copy whose stores are still to be issued (a == nullptr: none)
+struct InfPending { u8* a0; u8* a1; u32 v0, v1; };   // bytes loaded by the last round of inf_warp_copy, stored by the next call (a == nullptr: none)
 
 __device__ __forceinline__ void inf_flush(InfPending& P) {
   if (P.a0) { *P.a0 = (u8)P.v0; P.a0 = nullptr; }
   if (P.a1) { *P.a1 = (u8)P.v1; P.a1 = nullptr; }
 }
-// One match, 32 bytes at a time (a "unit": at most one byte per lane).  Units of one call never depend on each other, so a
-// lane keeps up to two loaded bytes in flight: a unit first stores what its slot still holds, then loads.
-__device__ __forceinline__ void inf_copy_unit(u8*& pa, u32& pv, u8* tj, u32 i, u32 len_j, u32 dist_j) {
-  if (pa) { *pa = (u8)pv; pa = nullptr; }
-  if (i < len_j) { const u32 si = i < dist_j ? i : i % dist_j; pv = (tj - dist_j)[si]; pa = tj + i; }
+// owner of flattened byte t among the warp's matches: lane j (smallest j with incl_j > t), and the byte's source / destination
+__device__ __forceinline__ void inf_copy_assign(u32 t, u32 total, u32 incl, u32 len, u32 dist, u32 to_lo, u32 to_hi, u8** dstp, const u8** srcp) {
+  int lo = 0, hi = 31;
+#pragma unroll
+  for (int it = 0; it < 5; ++it) { const int mid = (lo + hi) >> 1; const u32 v = __shfl_sync(0xffffffffu, incl, mid); if (v > t) hi = mid; else lo = mid + 1; }
+  const int j = lo > 31 ? 31 : lo;
+  const u32 end_j = __shfl_sync(0xffffffffu, incl, j), len_j = __shfl_sync(0xffffffffu, len, j), dist_j = __shfl_sync(0xffffffffu, dist, j);
+  const u32 plo = __shfl_sync(0xffffffffu, to_lo, j), phi = __shfl_sync(0xffffffffu, to_hi, j);
+  *dstp = nullptr; *srcp = nullptr;
+  if (t < total) {
+    u8* tj = reinterpret_cast<u8*>((size_t)(((u64)phi << 32) | plo));
+    const u32 i = t - (end_j - len_j);
+    const u32 si = i < dist_j ? i : i % dist_j;
+    *dstp = tj + i; *srcp = tj - dist_j + si;
+  }
 }
-// The pending matches of all 32 lanes, copied by the whole warp.  A match byte i comes from i - dist, which for i >= dist is
-// a byte of the same match: the source is periodic, out[i] = src[i mod dist], so every byte is read from data that was
-// complete before the copy began.  The matches are taken one after the other (ballot), their parameters broadcast, and the
-// lanes copy 32 consecutive bytes per step -- coalesced, all loads independent -- instead of one lane copying byte by byte
-// (a load -> store -> load chain through L2) while 31 wait.  The last loads stay in flight: their stores are issued by the
-// next call (after the next symbol has been decoded) or by inf_flush, so the L2 round trip overlaps the table look-ups.
-// Stores of the previous call are issued before any load of this one, with a warp barrier in between (memory ordering
-// among the lanes), because a match may read what the previous one wrote.
+// 64 bytes per round (two per lane).  The loads of the LAST round are left in flight: their stores are issued by the next
+// call (or by inf_flush), after the next symbol has been decoded, so the L2 round trip of the copy overlaps the table
+// look-ups of the decode instead of adding to them.  Stores of a call are issued before its loads, with a warp barrier in
+// between (memory ordering among the lanes), because a match may read what the previous one wrote.
 __device__ __forceinline__ void inf_warp_copy(InfState& S, int lane, InfPending& P) {
   const u32 len = S.m_len;
-  u32 mask = __ballot_sync(0xffffffffu, len != 0);
-  if (!mask) return;
-  inf_flush(P);
-  __syncwarp();
-  const u32 ld = len | (S.m_dist << 9);                 // len <= 258 (9 bits), dist <= 32768
-  const u64 to_bits = (u64)(size_t)(S.dst + S.o);
+  if (!__any_sync(0xffffffffu, len != 0)) return;
+  u32 incl = len;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const u32 up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += up; }
+  const u32 total = __shfl_sync(0xffffffffu, incl, 31);
+  u8* const to = S.dst + S.o;
+  const u64 to_bits = (u64)(size_t)to;
   const u32 to_lo = (u32)to_bits, to_hi = (u32)(to_bits >> 32);
-  int slot = 0;
-  while (mask) {
-    const int j = __ffs((int)mask) - 1; mask &= mask - 1;
-    const u32 ldj = __shfl_sync(0xffffffffu, ld, j), plo = __shfl_sync(0xffffffffu, to_lo, j), phi = __shfl_sync(0xffffffffu, to_hi, j);
-    const u32 len_j = ldj & 511u, dist_j = ldj >> 9;
-    u8* tj = reinterpret_cast<u8*>((size_t)(((u64)phi << 32) | plo));
-    for (u32 c = 0; c < len_j; c += 32) {
-      if (slot == 0) inf_copy_unit(P.a0, P.v0, tj, c + (u32)lane, len_j, dist_j);
-      else inf_copy_unit(P.a1, P.v1, tj, c + (u32)lane, len_j, dist_j);
-      slot ^= 1;
-    }
+  for (u32 t0 = 0; t0 < total; t0 += 64) {
+    u8* d0; u8* d1; const u8* s0; const u8* s1;
+    inf_copy_assign(t0 + (u32)lane, total, incl, len, S.m_dist, to_lo, to_hi, &d0, &s0);
+    inf_copy_assign(t0 + 32 + (u32)lane, total, incl, len, S.m_dist, to_lo, to_hi, &d1, &s1);
+    inf_flush(P);
+    __syncwarp();
+    if (s0) { P.v0 = *s0; P.a0 = d0; }
+    if (s1) { P.v1 = *s1; P.a1 = d1; }
   }
   S.o += len; S.m_len = 0;
 }
