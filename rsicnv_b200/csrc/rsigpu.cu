@@ -44,7 +44,8 @@ struct DevBuf {
 template <class T>
 struct DevVec {   // growable device array filled by appends from the host
   T* p = nullptr; size_t n = 0, cap = 0;
-  cudaError_t append(const T* h, size_t cnt, cudaStream_t s) {
+  // h: host memory, memory of the current device, or (src_dev >= 0) memory of another device
+  cudaError_t append(const T* h, size_t cnt, cudaStream_t s, int src_dev = -1, int dst_dev = -1) {
     if (n + cnt > cap) {
       size_t ncap = std::max(n + cnt, cap * 2);
       T* q = nullptr;
@@ -55,7 +56,8 @@ struct DevVec {   // growable device array filled by appends from the host
       if (p) cudaFree(p);
       p = q; cap = ncap;
     }
-    cudaError_t e = cudaMemcpyAsync(p + n, h, cnt * sizeof(T), cudaMemcpyDefault, s);   // host or device source
+    cudaError_t e = (src_dev >= 0 && src_dev != dst_dev) ? cudaMemcpyPeerAsync(p + n, dst_dev, h, src_dev, cnt * sizeof(T), s)
+                                                         : cudaMemcpyAsync(p + n, h, cnt * sizeof(T), cudaMemcpyDefault, s);   // host or device source
     n += cnt;
     return e;
   }
@@ -414,17 +416,18 @@ int rsigpu_pileup_begin(rsigpu_ctx* c, int32_t target_len) {
 
 // append one batch to the staged reads; the batch's pointers may be host or device memory, its offset arrays start
 // at cig_first / q_first (0 for a caller's batch, the run's first offsets for records decoded on the GPU)
-static int push_impl(rsigpu_ctx* c, const rsigpu_read_batch* b, size_t nc, size_t nq, u32 cig_first, u64 q_first) {
+static int push_impl(rsigpu_ctx* c, const rsigpu_read_batch* b, size_t nc, size_t nq, u32 cig_first, u64 q_first, int src_dev = -1) {
   cudaSetDevice(c->device);
   const size_t n = (size_t)b->n_reads;
   const size_t r0 = c->r_pos.n, c0 = c->r_cigar.n, q0 = c->r_qual.n;
+  const int sd = src_dev, dd = c->device;
   if (c0 + nc >= 0xffffffffull) { c->fail("more than 2^32 CIGAR ops in one contig"); return RSIGPU_E_RANGE; }
-  CK(c->r_pos.append(b->pos, n, c->stream)); CK(c->r_mpos.append(b->mpos, n, c->stream)); CK(c->r_isize.append(b->isize, n, c->stream));
-  CK(c->r_mtid.append(b->mtid, n, c->stream)); CK(c->r_flag.append(b->flag, n, c->stream)); CK(c->r_mapq.append(b->mapq, n, c->stream));
-  CK(c->r_cigar.append(b->cigar, nc, c->stream)); CK(c->r_qual.append(b->qual, nq, c->stream));
+  CK(c->r_pos.append(b->pos, n, c->stream, sd, dd)); CK(c->r_mpos.append(b->mpos, n, c->stream, sd, dd)); CK(c->r_isize.append(b->isize, n, c->stream, sd, dd));
+  CK(c->r_mtid.append(b->mtid, n, c->stream, sd, dd)); CK(c->r_flag.append(b->flag, n, c->stream, sd, dd)); CK(c->r_mapq.append(b->mapq, n, c->stream, sd, dd));
+  CK(c->r_cigar.append(b->cigar, nc, c->stream, sd, dd)); CK(c->r_qual.append(b->qual, nq, c->stream, sd, dd));
   // offsets: entry r0 of the previous batch (its end) equals this batch's first entry after rebasing
   if (r0) { c->r_cigar_off.n = r0; c->r_qual_off.n = r0; }
-  CK(c->r_cigar_off.append(b->cigar_off, n + 1, c->stream)); CK(c->r_qual_off.append(reinterpret_cast<const u64*>(b->qual_off), n + 1, c->stream));
+  CK(c->r_cigar_off.append(b->cigar_off, n + 1, c->stream, sd, dd)); CK(c->r_qual_off.append(reinterpret_cast<const u64*>(b->qual_off), n + 1, c->stream, sd, dd));
   const u32 addc = (u32)c0 - cig_first; const u64 addq = (u64)q0 - q_first;
   if (addc) KL(k_add_u32, grid_for((int)std::min<size_t>(n + 1, 1u << 30), 1024, c->n_sm * 4), 256, 0, c->r_cigar_off.p + r0, n + 1, addc);
   if (addq) KL(k_add_u64, grid_for((int)std::min<size_t>(n + 1, 1u << 30), 1024, c->n_sm * 4), 256, 0, c->r_qual_off.p + r0, n + 1, addq);
@@ -565,7 +568,7 @@ int rsigpu_bam_take(rsigpu_ctx* c, int32_t run, rsigpu_ctx* dst) {
   if (b.n_reads == 0) return RSIGPU_OK;
   b.pos = c->b_pos.p + R.r0; b.mpos = c->b_mpos.p + R.r0; b.isize = c->b_isize.p + R.r0; b.mtid = c->b_mtid.p + R.r0; b.flag = c->b_flag.p + R.r0; b.mapq = c->b_mapq.p + R.r0;
   b.cigar_off = c->b_cigoff.p + R.r0; b.cigar = c->b_cig.p + R.c0; b.qual_off = reinterpret_cast<const uint64_t*>(c->b_qoff.p + R.r0); b.qual = c->b_qual.p + R.q0;
-  return push_impl(dst, &b, (size_t)(R.c1 - R.c0), (size_t)(R.q1 - R.q0), (u32)R.c0, (u64)R.q0);
+  return push_impl(dst, &b, (size_t)(R.c1 - R.c0), (size_t)(R.q1 - R.q0), (u32)R.c0, (u64)R.q0, c->device);
 }
 
 int rsigpu_bam_end(rsigpu_ctx* c) {

@@ -64,7 +64,7 @@ def test_cli_bam_two_contigs_matches_reference(cli, tmp_path):
     subprocess.run([REF_BIN] + common + ["-o", str(tmp_path / "ref.txt")], check=True, capture_output=True)
     out = subprocess.run([cli] + common + ["-gpus", "2", "-o", str(tmp_path / "ours.txt")], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
-    assert _table(str(tmp_path / "ours.txt")) == _table(str(tmp_path / "ref.txt"))
+    assert _table(str(tmp_path / "ours.txt")) == _table(str(tmp_path / "ref.txt")), out.stderr
     assert len(_table(str(tmp_path / "ours.txt"))) > 6
     # the host decoder (zlib on threads) instead of the GPU one: same table
     out = subprocess.run([cli] + common + ["-hostdecode", "-o", str(tmp_path / "ours_h.txt")], capture_output=True, text=True)
