@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -195,10 +196,13 @@ void quantile(rsigpu_ctx* c, const float* x, const int* status, int masked, int 
   KL(k_fq_pick, 1, 1024, 0, c->d_fq_hist.p, c->d_st, slot);
 }
 
-int set_smem_attrs() {
-  static bool done = false;
-  if (done) return 0;
-  done = true;
+// cudaFuncSetAttribute is per device: once for every device a context is created on (the current device is the context's)
+int set_smem_attrs(int device) {
+  static bool done[64] = {};
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  if (device < 0 || device >= 64 || done[device]) return 0;
+  done[device] = true;
   cudaFuncSetAttribute(k_gc_table, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_A);
   cudaFuncSetAttribute(k_gc_adjust, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_B);
   cudaFuncSetAttribute(k_bins, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_C);
@@ -294,7 +298,7 @@ int rsigpu_create(int device, const rsigpu_params* p, rsigpu_ctx** out) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return RSIGPU_E_CUDA; }
   c->n_sm = prop.multiProcessorCount;
-  set_smem_attrs();
+  set_smem_attrs(device);
   bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess && cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaEventCreate(&c->ev_reads) == cudaSuccess && cudaEventCreate(&c->ev_isize) == cudaSuccess;
   ok = ok && cudaMalloc((void**)&c->d_st, sizeof(DevState)) == cudaSuccess;
