@@ -271,6 +271,7 @@ def main():
         return 2
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"   # NCCL's version banner goes to stdout at VERSION/INFO level; stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     # pinned host buffers (the e2e leg copies from these every step)
     reads_bytes = 0
