@@ -24,6 +24,7 @@ using namespace std;
 #include "loaddata.h"
 #include "readref.h"
 #include "alglibinterface.h"
+#include "bam.h"
 
 // reference functions defined in rsi.cpp / loaddata.cpp without a header (file:line = definition)
 void isitcnv(Array<int>& RDref, Array<int>& RDcnv, cnv_st& icnv);                          // rsi.cpp:101
@@ -289,6 +290,34 @@ int ref_format_row(const ref_cnv* c, const char* chrom, double rdmedian, double 
   string s = cnv_format1(x);
   strncpy(buf, s.c_str(), cap - 1); buf[cap - 1] = 0;
   return (int)s.size();
+}
+
+// every alignment record of one refID as the reference's own samtools returns it (bam_read1, bam.c:179-210), in file order:
+// the fields the path reads (bam1_core_t, bam1_cigar, bam1_qual).  Returns the number of records, or -1 - needed when a
+// capacity is too small; *n_cig / *n_qual = totals.
+long ref_bam_records(const char* path, int tid, long cap_reads, long cap_cig, long cap_qual, int* pos, int* mpos, int* isize, int* mtid,
+                     unsigned short* flag, unsigned char* mapq, unsigned* cigar_off, unsigned* cigar, unsigned long long* qual_off,
+                     unsigned char* qual, long* n_cig, long* n_qual) {
+  bamFile fp = bam_open(path, "r");
+  if (!fp) return -1;
+  bam_header_t* h = bam_header_read(fp);
+  bam1_t* b = bam_init1();
+  long n = 0, nc = 0, nq = 0;
+  bool over = false;
+  while (bam_read1(fp, b) >= 0) {
+    if (b->core.tid != tid) continue;
+    if (n < cap_reads && nc + b->core.n_cigar <= cap_cig && nq + b->core.l_qseq <= cap_qual) {
+      pos[n] = b->core.pos; mpos[n] = b->core.mpos; isize[n] = b->core.isize; mtid[n] = b->core.mtid; flag[n] = b->core.flag; mapq[n] = b->core.qual;
+      cigar_off[n] = (unsigned)nc; qual_off[n] = (unsigned long long)nq;
+      memcpy(cigar + nc, bam1_cigar(b), 4 * (size_t)b->core.n_cigar);
+      memcpy(qual + nq, bam1_qual(b), (size_t)b->core.l_qseq);
+    } else over = true;
+    ++n; nc += b->core.n_cigar; nq += b->core.l_qseq;
+  }
+  if (!over && n <= cap_reads) { cigar_off[n] = (unsigned)nc; qual_off[n] = (unsigned long long)nq; }
+  bam_destroy1(b); bam_header_destroy(h); bam_close(fp);
+  *n_cig = nc; *n_qual = nq;
+  return over ? -1 - n : n;
 }
 
 }  // extern "C"

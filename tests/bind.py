@@ -315,3 +315,34 @@ def oracle_bam_path(o: "Lib", reads: dict, fasta, **params):
 
 def have_ref() -> bool:
     return os.path.exists(REF_SO)
+
+
+# ---- BAM records as the reference's samtools returns them (ref_harness.cpp::ref_bam_records) / as oracle/bam_decode.py restates them
+BAM_FIELDS = (("pos", np.int32), ("mpos", np.int32), ("isize", np.int32), ("mtid", np.int32), ("flag", np.uint16), ("mapq", np.uint8),
+              ("cigar_off", np.uint32), ("cigar", np.uint32), ("qual_off", np.uint64), ("qual", np.uint8))
+
+
+def ref_bam_records(path: str, tid: int) -> dict:
+    lib = C.CDLL(REF_SO)
+    lib.ref_bam_records.restype = C.c_long
+    cap_r, cap_c, cap_q = 1 << 16, 1 << 18, 1 << 22
+    while True:
+        a = {"pos": np.zeros(cap_r, np.int32), "mpos": np.zeros(cap_r, np.int32), "isize": np.zeros(cap_r, np.int32), "mtid": np.zeros(cap_r, np.int32),
+             "flag": np.zeros(cap_r, np.uint16), "mapq": np.zeros(cap_r, np.uint8), "cigar_off": np.zeros(cap_r + 1, np.uint32), "cigar": np.zeros(cap_c, np.uint32),
+             "qual_off": np.zeros(cap_r + 1, np.uint64), "qual": np.zeros(cap_q, np.uint8)}
+        nc = C.c_long(0); nq = C.c_long(0)
+        n = lib.ref_bam_records(C.c_char_p(path.encode()), C.c_int(tid), C.c_long(cap_r), C.c_long(cap_c), C.c_long(cap_q),
+                                *[C.c_void_p(a[k].ctypes.data) for k, _ in BAM_FIELDS], C.byref(nc), C.byref(nq))
+        if n >= 0:
+            break
+        cap_r = max(cap_r, -1 - n + 1); cap_c = max(cap_c, nc.value + 1); cap_q = max(cap_q, nq.value + 1)
+    return {"pos": a["pos"][:n], "mpos": a["mpos"][:n], "isize": a["isize"][:n], "mtid": a["mtid"][:n], "flag": a["flag"][:n], "mapq": a["mapq"][:n],
+            "cigar_off": a["cigar_off"][:n + 1], "cigar": a["cigar"][:nc.value], "qual_off": a["qual_off"][:n + 1], "qual": a["qual"][:nq.value]}
+
+
+def oracle_bam_decode(data) -> dict:
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("rsi_oracle_bam_decode", os.path.join(ROOT, "oracle", "bam_decode.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.decode(data)

@@ -101,3 +101,23 @@ def test_depth_path_live(case, oracle, ref):
     a, b = oracle.depth_path(d, fa, 3), ref.depth_path(d, fa, 3)
     assert np.array_equal(a["depth"], b["depth"]) and a["stats"] == b["stats"]
     assert [x.as_dict() for x in a["calls"]] == [x.as_dict() for x in b["calls"]]
+
+
+def test_bam_decode_matches_reference_samtools(tmp_path):
+    """oracle/bam_decode.py (BGZF + bam_read1 restated) against the reference's own samtools on a real-looking file"""
+    from bind import BAM_FIELDS, have_ref, oracle_bam_decode, ref_bam_records
+    from rsicnv_b200 import synth
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    r0, _ = synth.make_reads(150_000, 71, None, coverage=8, n_events=0, tid=0, frac_indel=0.3)
+    r1, _ = synth.make_reads(90_000, 72, None, coverage=6, n_events=0, tid=1)
+    path = str(tmp_path / "t.bam")
+    synth.write_bam(path, [("1", 150_000), ("2", 90_000)], {0: r0, 1: r1}, level=6, rich=5, unmapped_tail=11)
+    d = oracle_bam_decode(np.fromfile(path, np.uint8))
+    assert d["order"] == [0, 1, -1]
+    for tid, src in ((0, r0), (1, r1), (-1, None)):
+        R = ref_bam_records(path, tid)
+        for k, dt in BAM_FIELDS:
+            assert np.array_equal(R[k], d["reads"][tid][k]), (tid, k)
+            if src is not None:
+                assert np.array_equal(R[k].astype(np.int64), np.asarray(src[k]).astype(np.int64)), (tid, k)
