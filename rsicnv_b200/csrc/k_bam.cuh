@@ -575,16 +575,7 @@ __global__ void k_bam_payload(const u8* __restrict__ U, const i64* __restrict__ 
     for (u32 j = (u32)lane; j < n_cig; j += 32) cd[j] = ld32u(cg + 4 * j);
     const u8* qs = cg + 4 * n_cig + (l_seq + 1) / 2;
     u8* qd = S.qual + S.qual_off[r];
-    // destination words where the destination is 4-byte aligned (source bytes are at any alignment), bytes otherwise
-    const u32 head = (u32)((4u - ((u32)(size_t)qd & 3u)) & 3u);
-    const u32 h = head < l_seq ? head : l_seq;
-    const u32 nw = (l_seq - h) >> 2;
-    if ((u32)lane < h) qd[lane] = qs[lane];
-    for (u32 w = (u32)lane; w < nw; w += 32) {
-      const u8* p = qs + h + 4 * w;
-      *reinterpret_cast<u32*>(qd + h + 4 * w) = (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16) | ((u32)p[3] << 24);
-    }
-    for (u32 j = h + 4 * nw + (u32)lane; j < l_seq; j += 32) qd[j] = qs[j];
+    for (u32 j = (u32)lane; j < l_seq; j += 32) qd[j] = qs[j];
   }
 }
 
