@@ -28,7 +28,8 @@ namespace rsigpu {
 #define INF_DB_BITS 6
 #endif
 enum {
-  INF_NT = 128,                    // threads per CTA, one BGZF block per thread
+  INF_NT = 64,                     // threads per CTA, one BGZF block per thread
+  INF_SB = 7,                      // bits of the literal/length code's FIRST-level direct table, in shared memory (256 B per thread)
   INF_FB = INF_FB_BITS, INF_DB = INF_DB_BITS,   // bits of the direct-lookup tables (literal/length, distance)
   INF_LF = 0,                      // per-thread table layout in GLOBAL memory, in u16 slots
   INF_LS = INF_LF + (1 << INF_FB), // literal/length symbols ordered by code
@@ -74,19 +75,21 @@ __device__ __forceinline__ u32 bits_take(BitIn& b, int n) { const u32 v = (u32)(
 // at 2.7 KB per thread, shared memory would hold three warps per SM, and one thread's decode loop is a chain of dependent
 // loads that only many resident warps can hide.  Slot i of lane l is at g[i * 32 + l] (a warp's tables are interleaved, so
 // the construction loops -- same i in every lane -- are coalesced).  The 2 x 16 code-length counts sit in shared memory.
-struct InfTabs { u16* g; u16* s; u8* cl; int lane, stid; };
+struct InfTabs { u16* g; u16* s; u16* sf; u8* cl; int lane, stid; };
 #define INF_G(i) T.g[(size_t)(i) * 32 + T.lane]
 #define INF_C(i) T.s[(i) * INF_NT + T.stid]
-#define INF_CL(i) T.cl[(i) * INF_NT + T.stid]
+#define INF_CL(i) T.sf[(i) * INF_NT + T.stid]   /* the code-length code's table lives in the thread's own first-level slots while a header is parsed */
+#define INF_SF(i) T.sf[(i) * INF_NT + T.stid]
 
 // canonical code from code lengths (count/symbol form, plus a direct table for codes of <= fb bits whose
 // entries are symbol << 4 | length).  Returns < 0 for an over-subscribed set, > 0 for an incomplete one.
 // One pass over the symbols: codes are handed out in symbol order per length (next-code counters in shared memory), so the
 // direct table is filled without reading back anything that was just written to global memory.
-__device__ int inf_construct(const InfTabs& T, const u8* lens, int n, int fast, int fb, int cnts, int syms, int xs) {
+__device__ int inf_construct(const InfTabs& T, const u8* lens, int n, int fast, int fb, int cnts, int syms, int xs, int sfb) {
   for (int l = 0; l < 16; ++l) INF_C(cnts + l) = 0;
   for (int s = 0; s < n; ++s) INF_C(cnts + lens[s]) += 1;
   for (int i = 0; i < (1 << fb); ++i) INF_G(fast + i) = 0;
+  for (int i = 0; i < (sfb ? (1 << sfb) : 0); ++i) INF_SF(i) = 0;
   if (INF_C(cnts) == n) return 0;
   int left = 1;
   for (int l = 1; l <= 15; ++l) { left <<= 1; left -= (int)INF_C(cnts + l); if (left < 0) return left; }
@@ -104,12 +107,17 @@ __device__ int inf_construct(const InfTabs& T, const u8* lens, int n, int fast, 
       const u32 rev = __brev(code) >> (32 - l);
       const u16 e = (u16)((s << 4) | l);
       for (u32 k = rev; k < (1u << fb); k += (1u << l)) INF_G(fast + k) = e;
+      if (l <= sfb) for (u32 k = rev; k < (1u << sfb); k += (1u << l)) INF_SF(k) = e;
     }
   }
   return left;
 }
-__device__ __forceinline__ int inf_decode(BitIn& b, const InfTabs& T, int fast, int fb, int cnts, int syms, int xs) {
+__device__ __forceinline__ int inf_decode(BitIn& b, const InfTabs& T, int fast, int fb, int cnts, int syms, int xs, int sfb) {
   const u32 low = (u32)(b.buf & ((1u << fb) - 1));
+  if (sfb) {   // codes of <= sfb bits (the frequent symbols): one shared-memory look-up, no trip to L1/L2
+    const u32 e0 = INF_SF(low & ((1u << sfb) - 1));
+    if (e0) { const int l = (int)(e0 & 15u); b.buf >>= l; b.cnt -= l; return (int)(e0 >> 4); }
+  }
   const u32 e = INF_G(fast + low);
   if (e) { const int l = (int)(e & 15u); b.buf >>= l; b.cnt -= l; return (int)(e >> 4); }
   // longer than fb bits: canonical walk (count / first / index per length), resumed after the fb bits already seen
@@ -136,7 +144,7 @@ __device__ int inf_construct_cl(const InfTabs& T, const u8* lens) {
     if (!l) continue;
     const u32 c = INF_C(INF_NC + l); INF_C(INF_NC + l) = (u16)(c + 1);
     const u32 rev = __brev(c) >> (32 - l);
-    const u8 e = (u8)((s << 3) | l);
+    const u16 e = (u16)((s << 3) | l);
     for (u32 k = rev; k < 128u; k += (1u << l)) INF_CL(k) = e;
   }
   return 0;
@@ -188,9 +196,9 @@ __device__ __noinline__ void inf_block_header(InfState& S, const InfTabs& T) {
     for (int s = 144; s < 256; ++s) lens[s] = 9;
     for (int s = 256; s < 280; ++s) lens[s] = 7;
     for (int s = 280; s < 288; ++s) lens[s] = 8;
-    inf_construct(T, lens, 288, INF_LF, INF_FB, INF_LC, INF_LS, INF_LX);
+    inf_construct(T, lens, 288, INF_LF, INF_FB, INF_LC, INF_LS, INF_LX, INF_SB);
     for (int s = 0; s < 30; ++s) lens[s] = 5;
-    inf_construct(T, lens, 30, INF_DF, INF_DB, INF_DC, INF_DS, INF_DX);
+    inf_construct(T, lens, 30, INF_DF, INF_DB, INF_DC, INF_DS, INF_DX, 0);
   } else {
     bits_refill(b);
     const int nlen = (int)bits_take(b, 5) + 257, ndist = (int)bits_take(b, 5) + 1, ncode = (int)bits_take(b, 4) + 4;
@@ -215,9 +223,9 @@ __device__ __noinline__ void inf_block_header(InfState& S, const InfTabs& T) {
       }
     }
     if (lens[256] == 0) return inf_fail(S, 10);
-    int r = inf_construct(T, lens, nlen, INF_LF, INF_FB, INF_LC, INF_LS, INF_LX);
+    int r = inf_construct(T, lens, nlen, INF_LF, INF_FB, INF_LC, INF_LS, INF_LX, INF_SB);
     if (r < 0 || (r > 0 && nlen - (int)INF_C(INF_LC) != 1)) return inf_fail(S, 11);       // incomplete only allowed for a single code
-    r = inf_construct(T, lens + nlen, ndist, INF_DF, INF_DB, INF_DC, INF_DS, INF_DX);
+    r = inf_construct(T, lens + nlen, ndist, INF_DF, INF_DB, INF_DC, INF_DS, INF_DX, 0);
     if (r < 0 || (r > 0 && ndist - (int)INF_C(INF_DC) != 1)) return inf_fail(S, 12);
   }
   S.phase = INF_SYMS;
@@ -226,7 +234,7 @@ __device__ __noinline__ void inf_block_header(InfState& S, const InfTabs& T) {
 __device__ __forceinline__ void inf_symbol(InfState& S, const InfTabs& T, const u16* tab) {
   BitIn& b = S.b;
   bits_refill(b);
-  int sym = inf_decode(b, T, INF_LF, INF_FB, INF_LC, INF_LS, INF_LX);
+  int sym = inf_decode(b, T, INF_LF, INF_FB, INF_LC, INF_LS, INF_LX, INF_SB);
   if (sym < 256) {
     if (sym < 0) return inf_fail(S, 13);
     if (S.o >= S.dst_len) return inf_fail(S, 3);
@@ -242,7 +250,7 @@ __device__ __forceinline__ void inf_symbol(InfState& S, const InfTabs& T, const 
   if (sym >= 29) return inf_fail(S, 14);
   const u32 len = (u32)tab[sym] + bits_take(b, (int)tab[29 + sym]);
   bits_refill(b);
-  const int ds = inf_decode(b, T, INF_DF, INF_DB, INF_DC, INF_DS, INF_DX);
+  const int ds = inf_decode(b, T, INF_DF, INF_DB, INF_DC, INF_DS, INF_DX, 0);
   if (ds < 0 || ds >= 30) return inf_fail(S, 15);
   const u32 dist = (u32)tab[58 + ds] + bits_take(b, (int)tab[88 + ds]);
   if (dist > S.o) return inf_fail(S, 16);
@@ -313,7 +321,7 @@ __global__ void __launch_bounds__(INF_NT, INF_MINB) k_bgzf_inflate(const u8* __r
                                                          u16* __restrict__ tabs, int* __restrict__ err) {
   __shared__ u16 tab[120];
   __shared__ u16 cnts[INF_SSLOTS * INF_NT];
-  __shared__ u8 cltab[128 * INF_NT];
+  __shared__ u16 sfast[(1 << INF_SB) * INF_NT];   // first-level literal/length table; doubles as the code-length code's table while a header is parsed
   {
     const u16 lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
     const u16 lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
@@ -324,7 +332,7 @@ __global__ void __launch_bounds__(INF_NT, INF_MINB) k_bgzf_inflate(const u8* __r
   }
   __syncthreads();
   const int k = (int)blockIdx.x * INF_NT + (int)threadIdx.x;
-  InfTabs T; T.lane = (int)(threadIdx.x & 31); T.stid = (int)threadIdx.x; T.s = cnts; T.cl = cltab;
+  InfTabs T; T.lane = (int)(threadIdx.x & 31); T.stid = (int)threadIdx.x; T.s = cnts; T.sf = sfast; T.cl = nullptr;
   T.g = tabs + (size_t)(k >> 5) * 32 * INF_GSLOTS;
   InfState S;
   S.phase = INF_DONE; S.rc = 0; S.o = 0; S.dst_len = 0; S.dst = U; S.last = 0; S.m_len = 0; S.m_dist = 1;
