@@ -8,6 +8,8 @@
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
+#include <time.h>
 
 #include <algorithm>
 #include <map>
@@ -181,6 +183,10 @@ int map_dev_err(rsigpu_ctx* c, int e, int cand) {
   c->fail(m);
   return RSIGPU_E_RANGE;
 }
+
+static double trace_now() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (double)t.tv_sec * 1e3 + 1e-6 * (double)t.tv_nsec; }
+static bool trace_on() { static int on = -1; if (on < 0) on = getenv("RSIGPU_TRACE") ? 1 : 0; return on == 1; }
+#define TRACE(c, what) do { if (trace_on()) fprintf(stderr, "[trace %p] %-28s %.3f ms\n", (void*)(c), what, trace_now()); } while (0)
 
 int grid_for(int n_items, int per_block, int cap) { int g = (n_items + per_block - 1) / per_block; if (g < 1) g = 1; return g > cap ? cap : g; }
 
@@ -498,12 +504,14 @@ int rsigpu_bam_feed(rsigpu_ctx* c, const uint8_t* bgzf, int64_t nbytes, int64_t 
   CK(c->b_tabs.ensure(RSI_INFLATE_TAB_BYTES(nblk) / 2));
   CK(c->b_first.ensure(nblk)); CK(c->b_endp.ensure(nblk)); CK(c->b_tailp.ensure(nblk)); CK(c->b_cnt.ensure(nblk)); CK(c->b_ncig.ensure(nblk)); CK(c->b_nq.ensure(nblk));
   CK(c->b_in.ensure(nblk)); CK(c->b_rbase.ensure(nblk)); CK(c->b_cbase.ensure(nblk)); CK(c->b_qbase.ensure(nblk)); CK(c->b_info.ensure(8)); CK(c->b_cnt32.ensure(4));
+  TRACE(c, "feed: start");
   CK(cudaMemcpyAsync(c->b_comp.p, bgzf, off, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->b_blk.p, blk.data(), (size_t)nblk * sizeof(BgzfBlock), cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->b_bound.p, bound.data(), ((size_t)nblk + 1) * 8, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemsetAsync(c->b_info.p, 0, 8 * 8, c->stream)); CK(cudaMemsetAsync(c->b_cnt32.p, 0, 4 * 4, c->stream));
   if (c->b_tail_len) CK(cudaMemcpyAsync(c->b_U.p + (BAM_HEAD - c->b_tail_len), c->b_carry.p, (size_t)c->b_tail_len, cudaMemcpyDeviceToDevice, c->stream));
   i64* info = c->b_info.p; int* err = c->b_cnt32.p;
+  if (trace_on()) { cudaStreamSynchronize(c->stream); TRACE(c, "feed: H2D done"); }
   KL(k_bgzf_inflate, (nblk + INF_NT - 1) / INF_NT, INF_NT, 0, c->b_comp.p, c->b_blk.p, nblk, c->b_U.p, c->b_tabs.p, err);
   BamChunk C; C.U = c->b_U.p; C.u_begin = c->b_first_feed ? (i64)BAM_HEAD + skip : (i64)BAM_HEAD - c->b_tail_len; C.u_end = (i64)(BAM_HEAD + utotal);
   C.bound = c->b_bound.p; C.nblk = nblk; C.n_ref = c->b_nref;
@@ -511,6 +519,7 @@ int rsigpu_bam_feed(rsigpu_ctx* c, const uint8_t* bgzf, int64_t nbytes, int64_t 
   KL(k_bam_chain, (nblk + 127) / 128, 128, 0, C, H);
   KL(k_bam_verify, 1, 1024, 0, C, H, c->b_in.p, c->b_rbase.p, c->b_cbase.p, c->b_qbase.p, info, err);
   i64 hi[8]; int he[4];
+  if (trace_on()) { cudaStreamSynchronize(c->stream); TRACE(c, "feed: inflate+chain done"); }
   CK(cudaMemcpyAsync(hi, info, 8 * 8, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaMemcpyAsync(he, err, 4 * 4, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
@@ -557,6 +566,7 @@ int rsigpu_bam_feed(rsigpu_ctx* c, const uint8_t* bgzf, int64_t nbytes, int64_t 
     CK(cudaStreamSynchronize(c->stream));
   }
   c->b_tail_len = tail_len > 0 ? (int)tail_len : 0;
+  TRACE(c, "feed: end");
   *consumed = (int64_t)off;
   *n_runs = (int32_t)c->b_runs.size();
   for (int i = 0; i < (int)c->b_runs.size() && i < cap && runs; ++i) { runs[i].tid = c->b_runs[(size_t)i].tid; runs[i].reserved_ = 0; runs[i].n_reads = c->b_runs[(size_t)i].r1 - c->b_runs[(size_t)i].r0; }
@@ -864,6 +874,7 @@ int rsigpu_run(rsigpu_ctx* c, rsigpu_cnv* out, int32_t cap, int32_t* n) {
   if (!c) return RSIGPU_E_ARG;
   cudaSetDevice(c->device);
   int rc;
+  TRACE(c, "run: start");
   CK(cudaEventRecord(c->ev[0], c->stream));
   if (c->have_reads && (rc = run_pileup(c)) != RSIGPU_OK) return rc;   // BAM input: the pileup is the first stage of the path
   if ((rc = rsigpu_load_finish(c)) != RSIGPU_OK) return rc;
@@ -872,6 +883,7 @@ int rsigpu_run(rsigpu_ctx* c, rsigpu_cnv* out, int32_t cap, int32_t* n) {
   if (c->have_reads && (rc = rsigpu_cnv_stat(c)) != RSIGPU_OK) return rc;
   CK(cudaEventRecord(c->ev[5], c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  TRACE(c, "run: end");
   float ms = 0;
   cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->stage_ms[0] = ms;
   cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); c->stage_ms[1] = ms;
