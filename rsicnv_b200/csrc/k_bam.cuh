@@ -24,12 +24,15 @@ namespace rsigpu {
 #ifndef INF_FB_BITS
 #define INF_FB_BITS 9
 #endif
+#ifndef INF_SB_BITS
+#define INF_SB_BITS 6
+#endif
 #ifndef INF_DB_BITS
 #define INF_DB_BITS 6
 #endif
 enum {
   INF_NT = 64,                     // threads per CTA, one BGZF block per thread
-  INF_SB = 7,                      // bits of the literal/length code's FIRST-level direct table, in shared memory (256 B per thread)
+  INF_SB = INF_SB_BITS,            // bits of the literal/length code's FIRST-level direct table, in shared memory (2^SB u16 per thread; >= 6)
   INF_FB = INF_FB_BITS, INF_DB = INF_DB_BITS,   // bits of the direct-lookup tables (literal/length, distance)
   INF_LF = 0,                      // per-thread table layout in GLOBAL memory, in u16 slots
   INF_LS = INF_LF + (1 << INF_FB), // literal/length symbols ordered by code
@@ -78,7 +81,7 @@ __device__ __forceinline__ u32 bits_take(BitIn& b, int n) { const u32 v = (u32)(
 struct InfTabs { u16* g; u16* s; u16* sf; u8* cl; int lane, stid; };
 #define INF_G(i) T.g[(size_t)(i) * 32 + T.lane]
 #define INF_C(i) T.s[(i) * INF_NT + T.stid]
-#define INF_CL(i) T.sf[(i) * INF_NT + T.stid]   /* the code-length code's table lives in the thread's own first-level slots while a header is parsed */
+#define INF_CL(i) reinterpret_cast<u8*>(&T.sf[((i) >> 1) * INF_NT + T.stid])[(i) & 1]   /* the code-length code's 128 one-byte entries live in 64 of the thread's own first-level slots while a header is parsed */
 #define INF_SF(i) T.sf[(i) * INF_NT + T.stid]
 
 // canonical code from code lengths (count/symbol form, plus a direct table for codes of <= fb bits whose
@@ -144,7 +147,7 @@ __device__ int inf_construct_cl(const InfTabs& T, const u8* lens) {
     if (!l) continue;
     const u32 c = INF_C(INF_NC + l); INF_C(INF_NC + l) = (u16)(c + 1);
     const u32 rev = __brev(c) >> (32 - l);
-    const u16 e = (u16)((s << 3) | l);
+    const u8 e = (u8)((s << 3) | l);
     for (u32 k = rev; k < 128u; k += (1u << l)) INF_CL(k) = e;
   }
   return 0;
