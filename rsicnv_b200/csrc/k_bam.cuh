@@ -78,7 +78,7 @@ __device__ __forceinline__ u32 bits_take(BitIn& b, int n) { const u32 v = (u32)(
 // at 2.7 KB per thread, shared memory would hold three warps per SM, and one thread's decode loop is a chain of dependent
 // loads that only many resident warps can hide.  Slot i of lane l is at g[i * 32 + l] (a warp's tables are interleaved, so
 // the construction loops -- same i in every lane -- are coalesced).  The 2 x 16 code-length counts sit in shared memory.
-struct InfTabs { u16* g; u16* s; u16* sf; u8* cl; int lane, stid; };
+struct InfTabs { u16* g; u16* s; u16* sf; int lane, stid; };
 #define INF_G(i) T.g[(size_t)(i) * 32 + T.lane]
 #define INF_C(i) T.s[(i) * INF_NT + T.stid]
 #define INF_CL(i) reinterpret_cast<u8*>(&T.sf[((i) >> 1) * INF_NT + T.stid])[(i) & 1]   /* the code-length code's 128 one-byte entries live in 64 of the thread's own first-level slots while a header is parsed */
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(INF_NT, INF_MINB) k_bgzf_inflate(const u8* __r
   }
   __syncthreads();
   const int k = (int)blockIdx.x * INF_NT + (int)threadIdx.x;
-  InfTabs T; T.lane = (int)(threadIdx.x & 31); T.stid = (int)threadIdx.x; T.s = cnts; T.sf = sfast; T.cl = nullptr;
+  InfTabs T; T.lane = (int)(threadIdx.x & 31); T.stid = (int)threadIdx.x; T.s = cnts; T.sf = sfast;
   T.g = tabs + (size_t)(k >> 5) * 32 * INF_GSLOTS;
   InfState S;
   S.phase = INF_DONE; S.rc = 0; S.o = 0; S.dst_len = 0; S.dst = U; S.last = 0; S.m_len = 0; S.m_dist = 1;
