@@ -8,9 +8,12 @@
 //   the per-record fields load_data_from_bam and cnv_stat read  loaddata.cpp:312-335, pairrd.cpp:622-748
 //
 // Design.  A BGZF block (<= 64 KiB decoded) is an independent raw-deflate stream, and a chr19-sized BAM
-// holds ~60 k of them: one THREAD inflates one block, with its Huffman tables in shared memory (lane-
-// interleaved so that the 32 lanes of a warp never share a bank word for the same table index).  BAM
-// records are a linked list (each starts with its own length) and may straddle BGZF blocks, so their
+// holds ~65 k of them: one THREAD inflates one block.  Its Huffman decode has three levels: a 6-bit direct
+// table in shared memory (the frequent literal/length codes), 9/6-bit direct tables in global memory
+// (per thread, warp-interleaved, L1/L2 resident) and the canonical count/symbol walk for longer codes.
+// The 32 lanes of a warp (32 different streams) are kept converged -- one symbol per lane per step, table
+// construction as a separate phase -- and the LZ77 matches of all lanes are copied by the whole warp.
+// BAM records are a linked list (each starts with its own length) and may straddle BGZF blocks, so their
 // starts are found speculatively and then proven: every block guesses its first record start with a
 // plausibility test and walks the list to the end of the block (k_bam_chain); one CTA checks that each
 // guess equals the position the previous block's walk ended at, starting from the known first record --
