@@ -133,3 +133,28 @@ def test_cli_real_looking_bam_matches_reference(cli, tmp_path):
         assert out.returncode == 0, out.stderr
         assert _table(str(tmp_path / name)) == _table(str(tmp_path / "ref.txt")), name
     assert len(_table(str(tmp_path / "ref.txt"))) > 3
+
+
+@pytest.mark.gpu
+def test_cli_six_contigs_streamed(cli, tmp_path):
+    """a small 'whole genome': six contigs of different lengths plus MT and an unplaced scaffold, decoded on the GPU in
+    chunks that cut through contigs, dealt to the GPUs longest first; rows must come out in header order, equal to the reference's"""
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    lens = [10_900_000, 10_300_000, 10_700_000, 10_250_000, 10_500_000, 10_400_000]
+    names = ["1", "2", "3", "4", "X", "Y"]
+    fas = [synth.make_fasta(L, 30 + i) for i, L in enumerate(lens)]
+    reads = {}
+    for i, L in enumerate(lens):
+        reads[i], _ = synth.make_reads(L, 30 + i, fas[i], coverage=6, n_events=3, lens=(4000, 9000, 20000), tid=i)
+    bam = str(tmp_path / "t.bam"); fasta = str(tmp_path / "t.fa")
+    synth.write_bam(bam, [(n, L) for n, L in zip(names, lens)] + [("MT", 16569), ("GL000192.1", 547496)], reads, level=1, rich=23, unmapped_tail=50)
+    synth.write_fasta_multi(fasta, list(zip(names, fas)))
+    subprocess.run([REF_BAMTOOL, "index", bam], check=True)
+    common = ["rsi", "-b", bam, "-f", fasta, "-q", "0", "-Q", "10", "-np"]
+    subprocess.run([REF_BIN] + common + ["-o", str(tmp_path / "ref.txt")], check=True, capture_output=True)
+    out = subprocess.run([cli] + common + ["-gpus", "8", "-o", str(tmp_path / "ours.txt")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    ours, ref = _table(str(tmp_path / "ours.txt")), _table(str(tmp_path / "ref.txt"))
+    assert ours == ref, out.stderr
+    assert len({ln.split("\t")[0] for ln in ref if not ln.startswith("#")}) >= 4
