@@ -363,6 +363,10 @@ void write_table(const Opt& o, const std::vector<ContigResult>& all) {
 
 int do_decode(const Opt& o) {
   BamReader br(o.threads); std::string err;
+  {   // what the GPU decoder is given: where the alignment records start
+    BamHeader h; long long coff = 0, skip = 0;
+    if (read_bam_header(o.bamfile, &h, &coff, &skip, &err)) printf("records start at file offset %lld + %lld decoded bytes, %zu references\n", coff, skip, h.name.size());
+  }
   if (!br.open(o.bamfile, &err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
   ContigReads cr;
   while (br.next_contig(&cr, &err)) {

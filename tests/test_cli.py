@@ -158,3 +158,19 @@ def test_cli_six_contigs_streamed(cli, tmp_path):
     ours, ref = _table(str(tmp_path / "ours.txt")), _table(str(tmp_path / "ref.txt"))
     assert ours == ref, out.stderr
     assert len({ln.split("\t")[0] for ln in ref if not ln.startswith("#")}) >= 4
+
+
+def test_header_reader_agrees_with_the_python_one(cli, tmp_path):
+    """read_bam_header (what the CLI hands to the GPU decoder) vs api.parse_bam_header: ordinary file, header ending exactly at a
+    block boundary, header spanning many blocks"""
+    from rsicnv_b200 import api
+    r1, _ = synth.make_reads(60_000, 7, None, coverage=3, n_events=0, tid=0)
+    text = "@HD\tVN:1.0\tSO:coordinate\n@SQ\tSN:19\tLN:60000\n"
+    hdr_len = 12 + len(text) + 4 + len("19") + 1 + 4
+    for k, (contigs, bs) in enumerate(([[("19", 60_000)], 65280], [[("19", 60_000)], hdr_len], [[("19", 60_000)] + [("c%d" % i, 1000) for i in range(400)], 211])):
+        bam = str(tmp_path / ("t%d.bam" % k))
+        synth.write_bam(bam, contigs, {0: r1}, level=6, block_size=bs)
+        h = api.parse_bam_header(np.fromfile(bam, np.uint8))
+        out = subprocess.run([cli, "decode", "-b", bam, "-c", "19", "-o", str(tmp_path / "d")], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        assert "records start at file offset %d + %d decoded bytes, %d references" % (h["coff"], h["skip"], len(contigs)) in out.stdout, out.stdout

@@ -244,3 +244,17 @@ def test_real_looking_records(sim_lib, tmp_path):
     assert len(got[-1]["pos"]) == 25 and np.all(got[-1]["pos"] == -1)
     for tid in (0, 1):
         assert_same_reads(got[tid], rb[tid])
+
+
+def test_header_ending_exactly_at_a_block_boundary(sim_lib, tmp_path):
+    """first alignment record at the very start of a BGZF block (skip = 0, the feed starts at the second block)"""
+    contigs = [("19", 50000)]
+    text = "@HD\tVN:1.0\tSO:coordinate\n@SQ\tSN:19\tLN:50000\n"
+    hdr_len = 12 + len(text) + 4 + len("19") + 1 + 4
+    fa, reads = make_reads(50000, 81, cov=4)
+    path = str(tmp_path / "t.bam")
+    synth.write_bam(path, contigs, {0: reads}, level=6, block_size=hdr_len)
+    h = api.parse_bam_header(np.fromfile(path, np.uint8))
+    assert h["skip"] == 0 and h["coff"] > 0
+    got, _ = decode_file(sim_lib, path, 30000)
+    assert_same_reads(got[0], reads)
