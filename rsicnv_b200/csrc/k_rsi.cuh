@@ -101,10 +101,10 @@ __device__ bool window_median_ok(const int* __restrict__ medint, int i1, int L, 
 // bit per centre (one __ballot_sync word per 32 centres), each thread tests the centre range of the
 // bins it owns and remembers the first (smallest) L in registers: no atomics, no per-hit loops, and the
 // result does not depend on how hits cluster.  Dynamic shared memory (NB = S_T + 2*LMAX_CAP staged bins):
-//   P[NB+1] i64 | SA/EA x DEL/DUP [4][S_T] i32 | cle,cge [NB+1] u16 | hit words [2][2][S_NC/32+1] u32
+//   P[NB+1] i64 | SA/EA x DEL/DUP [4][S_T] i32 | cle,cge [NB+1] u16 | hit words [2 buffers][2 lengths][2 signs][S_NC/32+1] u32
 enum { S_NB = S_T + 2 * LMAX_CAP, S_NC = S_T + 2 * S_H };
 enum { LMAX_SMALL = 256 };        // most contigs need far fewer window lengths than LMAX_CAP: a second instantiation with a small footprint
-#define RSI_SCAN_SMEM_T(LCAP) ((size_t)(S_T + 2 * (LCAP) + 1) * 8 + (size_t)4 * S_T * 4 + (size_t)2 * (S_T + 2 * (LCAP) + 2) * 2 + (size_t)4 * ((S_T + 2 * ((LCAP) / 2 + 2)) / 32 + 2) * 4)
+#define RSI_SCAN_SMEM_T(LCAP) ((size_t)(S_T + 2 * (LCAP) + 1) * 8 + (size_t)4 * S_T * 4 + (size_t)2 * (S_T + 2 * (LCAP) + 2) * 2 + (size_t)8 * ((S_T + 2 * ((LCAP) / 2 + 2)) / 32 + 2) * 4)
 #define RSI_SCAN_SMEM RSI_SCAN_SMEM_T(LMAX_CAP)
 
 // prev / next index with a condition, over the staged bins (block-wide max / min scans, thread-contiguous)
@@ -255,57 +255,74 @@ __device__ __forceinline__ void rsi_scan_body(const float* __restrict__ t, const
 #pragma unroll
   for (int r = 0; r < S_T / S_NT; ++r) { ml_del[r] = MINL_INF; ml_dup[r] = MINL_INF; }
   const int nwords = (NC + 31) / 32;
-  // ---- every window length
-  for (int L = 1; L <= Lmax; ++L) {
-    const int h = L / 2;
-    const i64 sdel = thr[2 * L], sdup = thr[2 * L + 1];
+  // ---- every window length.  Lengths 2k and 2k+1 have the same half-width k (same centres, same window start), so they are
+  // taken together: three prefix loads give both sums, and there is one barrier per PAIR.  L = 1 goes alone.
+  int pbuf = 0;
+  for (int L0 = 1; L0 <= Lmax; L0 += (L0 == 1 ? 1 : 2)) {
+    const int nL = (L0 == 1 || L0 + 1 > Lmax) ? 1 : 2;
+    const int h = L0 / 2;
+    const i64 sdel0 = thr[2 * L0], sdup0 = thr[2 * L0 + 1];
+    const i64 sdel1 = nL == 2 ? thr[2 * L0 + 2] : -1, sdup1 = nL == 2 ? thr[2 * L0 + 3] : 0x7fffffffffffffffll;
     const int ilo = h + 1, ihi = nb - h - 1;        // valid centres: ilo <= i < ihi
-    u32* hwd = hw + (size_t)((L & 1) * 2) * NW;     // double-buffered hit words: one barrier per length
-    u32* hwu = hwd + NW;
+    u32* hwb = hw + (size_t)(pbuf * 4) * NW;        // double-buffered hit words [length][sign][word]: one barrier per pair
+    pbuf ^= 1;
     int anyhit = 0;
     for (int w = warp; w < nwords; w += S_NT / 32) {
       const int ci = w * 32 + lane;                 // centre index within [0, NC)
       const int i = cbase + ci;
-      bool hd = false, hu = false;
+      bool hd0 = false, hu0 = false, hd1 = false, hu1 = false;
       if (ci < NC && i >= ilo && i < ihi) {
         const int kw = i - h - base;                // smem index of the window start
-        const i64 s = P[kw + L] - P[kw];
-        hd = s <= sdel; hu = s >= sdup;
-        if (hd) hd = window_median_ok(medint, i - h, L, (int)cle[kw + L] - (int)cle[kw], limd, -1);
-        if (hu) hu = window_median_ok(medint, i - h, L, (int)cge[kw + L] - (int)cge[kw], limu, +1);
-      }
-      const u32 bd = __ballot_sync(0xffffffffu, hd), bu = __ballot_sync(0xffffffffu, hu);
-      if (lane == 0) { hwd[w] = bd; hwu[w] = bu; }
-      anyhit |= (bd | bu) != 0u;
-    }
-    if (!__syncthreads_or(anyhit)) continue;        // no window of this length hits anywhere near the tile (the common case)
-#pragma unroll
-    for (int r = 0; r < S_T / S_NT; ++r) {
-      const int jr = tid + r * S_NT;                // owned bin, smem index HB + jr
-      const int j = c0 + jr;
-      if (j >= nb) continue;
-#pragma unroll
-      for (int sgn = 0; sgn < 2; ++sgn) {
-        if ((sgn ? ml_dup[r] : ml_del[r]) != MINL_INF) continue;
-        const int sa = SAEA[(2 * sgn) * S_T + jr], ea = SAEA[(2 * sgn + 1) * S_T + jr];
-        if (sa < 0 || ea == 0x7fffffff) continue;
-        // windows [s, e] (smem indices) with s <= sa, e = s + L - 1 >= ea; centre smem index = s + h
-        int slo = ea - (L - 1), shi = sa;
-        if (slo > shi) continue;
-        // to centre indices within [0, NC): centre bin = base + s + h  =>  ci = s + h + base - cbase
-        int clo = slo + h + (base - cbase), chi = shi + h + (base - cbase);
-        if (clo < 0) clo = 0;
-        if (chi > NC - 1) chi = NC - 1;
-        if (clo > chi) continue;
-        const u32* hwp = sgn ? hwu : hwd;
-        bool any = false;
-        for (int w = clo >> 5; w <= (chi >> 5) && !any; ++w) {
-          u32 m = hwp[w];
-          if (w == (clo >> 5)) m &= 0xffffffffu << (clo & 31);
-          if (w == (chi >> 5)) m &= 0xffffffffu >> (31 - (chi & 31));
-          any = m != 0;
+        const i64 p0 = P[kw];
+        const i64 s0 = P[kw + L0] - p0;
+        hd0 = s0 <= sdel0; hu0 = s0 >= sdup0;
+        if (hd0) hd0 = window_median_ok(medint, i - h, L0, (int)cle[kw + L0] - (int)cle[kw], limd, -1);
+        if (hu0) hu0 = window_median_ok(medint, i - h, L0, (int)cge[kw + L0] - (int)cge[kw], limu, +1);
+        if (nL == 2) {
+          const i64 s1 = P[kw + L0 + 1] - p0;
+          hd1 = s1 <= sdel1; hu1 = s1 >= sdup1;
+          if (hd1) hd1 = window_median_ok(medint, i - h, L0 + 1, (int)cle[kw + L0 + 1] - (int)cle[kw], limd, -1);
+          if (hu1) hu1 = window_median_ok(medint, i - h, L0 + 1, (int)cge[kw + L0 + 1] - (int)cge[kw], limu, +1);
         }
-        if (any) { if (sgn) ml_dup[r] = (u32)L; else ml_del[r] = (u32)L; }
+      }
+      const u32 bd0 = __ballot_sync(0xffffffffu, hd0), bu0 = __ballot_sync(0xffffffffu, hu0);
+      const u32 bd1 = __ballot_sync(0xffffffffu, hd1), bu1 = __ballot_sync(0xffffffffu, hu1);
+      if (lane == 0) { hwb[w] = bd0; hwb[NW + w] = bu0; hwb[2 * NW + w] = bd1; hwb[3 * NW + w] = bu1; }
+      anyhit |= (bd0 | bu0 | bd1 | bu1) != 0u;
+    }
+    if (!__syncthreads_or(anyhit)) continue;        // no window of these lengths hits anywhere near the tile (the common case)
+    for (int q = 0; q < nL; ++q) {                  // increasing length: the smallest L wins
+      const int L = L0 + q;
+      const u32* hwd = hwb + (size_t)(2 * q) * NW;
+      const u32* hwu = hwd + NW;
+#pragma unroll
+      for (int r = 0; r < S_T / S_NT; ++r) {
+        const int jr = tid + r * S_NT;                // owned bin, smem index HB + jr
+        const int j = c0 + jr;
+        if (j >= nb) continue;
+#pragma unroll
+        for (int sgn = 0; sgn < 2; ++sgn) {
+          if ((sgn ? ml_dup[r] : ml_del[r]) != MINL_INF) continue;
+          const int sa = SAEA[(2 * sgn) * S_T + jr], ea = SAEA[(2 * sgn + 1) * S_T + jr];
+          if (sa < 0 || ea == 0x7fffffff) continue;
+          // windows [s, e] (smem indices) with s <= sa, e = s + L - 1 >= ea; centre smem index = s + h
+          int slo = ea - (L - 1), shi = sa;
+          if (slo > shi) continue;
+          // to centre indices within [0, NC): centre bin = base + s + h  =>  ci = s + h + base - cbase
+          int clo = slo + h + (base - cbase), chi = shi + h + (base - cbase);
+          if (clo < 0) clo = 0;
+          if (chi > NC - 1) chi = NC - 1;
+          if (clo > chi) continue;
+          const u32* hwp = sgn ? hwu : hwd;
+          bool any = false;
+          for (int w = clo >> 5; w <= (chi >> 5) && !any; ++w) {
+            u32 m = hwp[w];
+            if (w == (clo >> 5)) m &= 0xffffffffu << (clo & 31);
+            if (w == (chi >> 5)) m &= 0xffffffffu >> (31 - (chi & 31));
+            any = m != 0;
+          }
+          if (any) { if (sgn) ml_dup[r] = (u32)L; else ml_del[r] = (u32)L; }
+        }
       }
     }
   }
