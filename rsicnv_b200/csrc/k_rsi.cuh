@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(S_NT) k_rsi_scan(const float* __restrict__ t, 
                                                     u32* __restrict__ minl_dup, int* __restrict__ scratch, const i64* __restrict__ thr, DevState* st) {
   rsi_scan_body<LMAX_CAP, false>(t, medint, minl_del, minl_dup, scratch, thr, st);
 }
-__global__ void __launch_bounds__(S_NT) k_rsi_scan_small(const float* __restrict__ t, const int* __restrict__ medint, u32* __restrict__ minl_del,
+__global__ void __launch_bounds__(S_NT, 4) k_rsi_scan_small(const float* __restrict__ t, const int* __restrict__ medint, u32* __restrict__ minl_del,
                                                           u32* __restrict__ minl_dup, int* __restrict__ scratch, const i64* __restrict__ thr, DevState* st) {
   rsi_scan_body<LMAX_SMALL, true>(t, medint, minl_del, minl_dup, scratch, thr, st);
 }

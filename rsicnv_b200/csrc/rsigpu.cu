@@ -219,6 +219,9 @@ int set_smem_attrs(int device) {
   cudaFuncSetAttribute(k_cand_edge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_CAND_CL);
   cudaFuncSetAttribute(k_rsi_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SCAN_SMEM);
   cudaFuncSetAttribute(k_rsi_scan_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SCAN_SMEM_T(LMAX_SMALL));
+  // occupancy of these two is set by shared memory: ask for the largest shared-memory carve-out
+  cudaFuncSetAttribute(k_rsi_scan_small, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(k_bgzf_inflate, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   return 0;
 }
 

@@ -436,4 +436,5 @@ inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) { e->t
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
 inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return 0; }
 inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) { *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count(); return 0; }
+enum { cudaFuncAttributePreferredSharedMemoryCarveout = 9 };
 template <class F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { return 0; }
