@@ -474,6 +474,13 @@ def main():
                                        **({"compressed_bytes": int(bam_np.size), "decoded_bytes": dec_bytes, "decoded_gbs": dec_bytes / 1e9 / (ms / 1e3)} if nm == "k_bgzf_inflate" else {})}
                                       for nm, ms, n in sorted(dprof, key=lambda x: -x[1])]
         if world == 1:
+            # release this process's device memory and pinned buffers before other processes (the CLIs) are timed
+            for cx in ctxs:
+                cx.close()
+            if bam:
+                del pins, bam_pin
+            del fa_pin
+            torch.cuda.empty_cache()
             sample = min(a.cpu_sample, L)
             if bam:
                 cpu, out, kind = time_reference_bam(sample, 1, 19, with_ours=True)
