@@ -133,6 +133,12 @@ def test_cli_real_looking_bam_matches_reference(cli, tmp_path):
         assert out.returncode == 0, out.stderr
         assert _table(str(tmp_path / name)) == _table(str(tmp_path / "ref.txt")), name
     assert len(_table(str(tmp_path / "ref.txt"))) > 3
+    # -s: the per-base depth dump <out>.<chr>_rd (write_rd_to_file, loaddata.cpp:464-470) is byte-identical, and so is the table
+    subprocess.run([REF_BIN] + common + ["-s", "-o", str(tmp_path / "refs.txt")], check=True, capture_output=True)
+    out = subprocess.run([cli] + common + ["-s", "-o", str(tmp_path / "gpus.txt")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert open(str(tmp_path / "gpus.txt.7_rd"), "rb").read() == open(str(tmp_path / "refs.txt.7_rd"), "rb").read()
+    assert _table(str(tmp_path / "gpus.txt")) == _table(str(tmp_path / "refs.txt"))
 
 
 @pytest.mark.gpu
