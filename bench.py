@@ -295,7 +295,7 @@ def main():
         import tempfile
         with tempfile.TemporaryDirectory() as td:
             t0 = time.perf_counter()
-            synth.write_bam(os.path.join(td, "t.bam"), [("19", L)], {0: reads}, level=1, random_seq=7 + rank, threads=min(32, os.cpu_count() or 8))
+            synth.write_bam(os.path.join(td, "t.bam"), [("19", L)], {0: reads}, level=1, random_seq=7 + rank, threads=max(4, min(32, (os.cpu_count() or 8) // world)))
             bam_np = np.fromfile(os.path.join(td, "t.bam"), np.uint8)
         bam_hdr = api.parse_bam_header(bam_np)
         bam_pin = torch.from_numpy(bam_np).pin_memory()
