@@ -118,6 +118,7 @@ struct rsigpu_ctx {
   struct BamRun { int tid; i64 r0, r1, c0, c1, q0, q1; };
   std::vector<BamRun> b_runs;
   int b_nref = 0, b_tail_len = 0, b_rewalked = 0; bool b_active = false, b_first_feed = true;
+  size_t b_umax = (size_t)5 << 30;   // decoded bytes one feed may produce (test hook: rsigpu_set_level0_mode(1000000 + bytes))
   // accounting
   long long h_cprof[16] = {};
   int64_t launches = 0;
@@ -470,7 +471,7 @@ int rsigpu_bam_feed(rsigpu_ctx* c, const uint8_t* bgzf, int64_t nbytes, int64_t 
   cudaSetDevice(c->device);
   *consumed = 0; *n_runs = 0; c->b_runs.clear();
   // BGZF block headers (bgzf.c:258-275): gzip magic, FEXTRA, the 'B','C' subfield carries the block size
-  const size_t U_MAX = (size_t)5 << 30, C_MAX = (size_t)1 << 31;
+  const size_t U_MAX = c->b_umax, C_MAX = (size_t)1 << 31;
   std::vector<BgzfBlock> blk; std::vector<i64> bound;
   size_t off = 0, utotal = 0;
   bound.push_back((i64)BAM_HEAD);
@@ -999,6 +1000,7 @@ int rsigpu_debug_state(const rsigpu_ctx* c, double* out, int32_t cap) {
 // test hook: 0 = sequential float chain for filterstatus' level-0 sum, 1 = block-scan form (default)
 int rsigpu_set_level0_mode(rsigpu_ctx* c, int mode) {
   if (!c) return RSIGPU_E_ARG;
+  if (mode >= 1000000) { c->b_umax = (size_t)(mode - 1000000); return RSIGPU_OK; }   // test hook: decoded-size limit of one rsigpu_bam_feed
   if (mode >= 100) { c->cand_a_threads = mode - 100; return RSIGPU_OK; }   // tuning hook: 100 + threads of the bin-level candidate kernel
   if (mode < 0 || mode > 2) return RSIGPU_E_ARG;
   c->level0_mode = mode;

@@ -258,3 +258,26 @@ def test_header_ending_exactly_at_a_block_boundary(sim_lib, tmp_path):
     assert h["skip"] == 0 and h["coff"] > 0
     got, _ = decode_file(sim_lib, path, 30000)
     assert_same_reads(got[0], reads)
+
+
+def test_feed_stops_at_its_decoded_size_limit(sim_lib, tmp_path):
+    """one feed may only produce so many decoded bytes (5 GiB in the product; lowered here through the test hook): it must take
+    a prefix of whole blocks, report what it consumed, and carry the cut record into the next feed"""
+    fa, reads = make_reads(120000, 91, cov=10)
+    path = str(tmp_path / "t.bam")
+    synth.write_bam(path, [("19", 120000)], {0: reads}, level=6, block_size=20000, random_seq=4)
+    data = np.fromfile(path, np.uint8)
+    h = api.parse_bam_header(data)
+    ctx = api.Context(lib=sim_lib)
+    ctx.set_level0_mode(1000000 + 70000)          # at most three 20000-byte blocks per feed
+    ctx.bam_begin(1)
+    parts = []; off = h["coff"]; first = True; feeds = 0
+    while off < len(data):
+        consumed, runs = ctx.bam_feed(data[off:], skip=h["skip"] if first else 0)
+        assert consumed > 0
+        for i, (tid, n) in enumerate(runs):
+            parts.append(ctx.bam_run_reads(i))
+        first = False; off += consumed; feeds += 1
+    ctx.bam_end(); ctx.close()
+    assert feeds > 5
+    assert_same_reads(concat_reads(parts), reads)
