@@ -77,9 +77,9 @@ __device__ __forceinline__ void bits_refill(BitIn& b) {
 }
 __device__ __forceinline__ u32 bits_take(BitIn& b, int n) { const u32 v = (u32)(b.buf & ((1ull << n) - 1)); b.buf >>= n; b.cnt -= n; return v; }
 
-// Per-thread Huffman tables.  The big ones (direct-lookup tables, symbols by code) live in global memory and stay in L2:
-// at 2.7 KB per thread, shared memory would hold three warps per SM, and one thread's decode loop is a chain of dependent
-// loads that only many resident warps can hide.  Slot i of lane l is at g[i * 32 + l] (a warp's tables are interleaved, so
+// Per-thread Huffman tables.  The big ones (9/6-bit direct tables, symbols by code) live in global memory and stay in L2:
+// at 1.8 KB per thread, shared memory would hold a few warps per SM, and one thread's decode loop is a chain of dependent
+// loads that only many resident warps can hide.  A 6-bit first level for the literal/length code (sf) is in shared memory.  Slot i of lane l is at g[i * 32 + l] (a warp's tables are interleaved, so
 // the construction loops -- same i in every lane -- are coalesced).  The 2 x 16 code-length counts sit in shared memory.
 struct InfTabs { u16* g; u16* s; u16* sf; int lane, stid; };
 #define INF_G(i) T.g[(size_t)(i) * 32 + T.lane]

@@ -997,7 +997,7 @@ int rsigpu_debug_state(const rsigpu_ctx* c, double* out, int32_t cap) {
   return n + 17;
 }
 
-// test hook: 0 = sequential float chain for filterstatus' level-0 sum, 1 = block-scan form (default)
+// test hooks (see include/rsigpu.h): 0/1/2 = form of filterstatus' level-0 float sum (2 = multi-block, default)
 int rsigpu_set_level0_mode(rsigpu_ctx* c, int mode) {
   if (!c) return RSIGPU_E_ARG;
   if (mode >= 1000000) { c->b_umax = (size_t)(mode - 1000000); return RSIGPU_OK; }   // test hook: decoded-size limit of one rsigpu_bam_feed
