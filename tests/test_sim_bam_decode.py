@@ -281,3 +281,42 @@ def test_feed_stops_at_its_decoded_size_limit(sim_lib, tmp_path):
     ctx.bam_end(); ctx.close()
     assert feeds > 5
     assert_same_reads(concat_reads(parts), reads)
+
+
+def test_separate_decoder_and_two_destinations(sim_lib, tmp_path):
+    """the CLI's arrangement: one decoder context, the runs of each contig appended to that contig's own context"""
+    L0, L1 = 260000, 220000
+    fa0 = synth.make_fasta(L0, 3); fa1 = synth.make_fasta(L1, 4)
+    r0, _ = synth.make_reads(L0, 3, fa0, coverage=10, n_events=4, lens=(3000, 8000, 20000), tid=0)
+    r1, _ = synth.make_reads(L1, 4, fa1, coverage=10, n_events=3, lens=(3000, 8000, 20000), tid=1)
+    path = str(tmp_path / "t.bam")
+    synth.write_bam(path, [("1", L0), ("2", L1)], {0: r0, 1: r1}, level=1, rich=2)
+    want = []
+    for fa, r in ((fa0, r0), (fa1, r1)):
+        c = api.Context(lib=sim_lib, minq=0, min_baseQ=10)
+        c.set_reference(fa); c.pileup_begin(); c.pileup_push(r); c.have_reads()
+        want.append(c.run()); c.close()
+    data = np.fromfile(path, np.uint8)
+    h = api.parse_bam_header(data)
+    dec = api.Context(lib=sim_lib)
+    dst = [api.Context(lib=sim_lib, minq=0, min_baseQ=10) for _ in range(2)]
+    for c, fa in zip(dst, (fa0, fa1)):
+        c.set_reference(fa); c.pileup_begin()
+    dec.bam_begin(2)
+    off = h["coff"]; pending = np.zeros(0, np.uint8); first = True
+    while off < len(data) or len(pending):
+        buf = np.concatenate((pending, data[off:off + 150000])); off += 150000
+        consumed, runs = dec.bam_feed(buf, skip=h["skip"] if first else 0)
+        first = first and not consumed
+        for i, (tid, n) in enumerate(runs):
+            dec.bam_take(i, dst[tid])
+        pending = buf[consumed:]
+        if off >= len(data) and consumed == 0:
+            break
+    dec.bam_end()
+    for c, w in zip(dst, want):
+        c.have_reads()
+        got = c.run()
+        assert len(got) == len(w) and all(bytes(x) == bytes(y) for x, y in zip(got, w))
+        c.close()
+    dec.close()
