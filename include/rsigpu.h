@@ -183,10 +183,12 @@ int rsigpu_set_profile(rsigpu_ctx* c, int on);
 int rsigpu_get_profile(const rsigpu_ctx* c, char* names, int32_t name_stride, float* ms, int32_t* launches, int32_t cap);
 
 /* test hook: filterstatus' level-0 float sum (rsi.cpp:967-974) as 0 = one sequential FADD chain,
- * 1 = the exact one-block scan form, 2 = the exact multi-block form (default); all must give identical bits.
- * Two more hooks share the entry point: 100 + n = threads of the bin-level candidate kernel (tuning),
- * 1000000 + n = decoded bytes one rsigpu_bam_feed may produce (tests of the partial-consumption path; 5 GiB by default). */
+ * 1 = the exact one-block scan form, 2 = the exact multi-block form (default); all must give identical bits. */
 int rsigpu_set_level0_mode(rsigpu_ctx* c, int mode);
+/* test hook: decoded bytes one rsigpu_bam_feed may produce (tests of the partial-consumption path; 5 GiB by default, >= 64 KiB) */
+int rsigpu_set_feed_limit(rsigpu_ctx* c, int64_t decoded_bytes);
+/* tuning hook: threads of the bin-level candidate kernel (multiple of 32, 32..1024) */
+int rsigpu_set_cand_threads(rsigpu_ctx* c, int threads);
 /* test hook: selected device-resident scalars of the last stage, as doubles; returns how many exist */
 int rsigpu_debug_state(const rsigpu_ctx* c, double* out, int32_t cap);
 

@@ -103,6 +103,8 @@ void ref_set_params(int m, int minq, int min_baseQ, double cap, int gcadjust, co
   rsi::tid = 0; rsi::target_name.clear(); rsi::target_name.push_back("chr"); rsi::plot = false;
   rsi::chklen = 2.5; rsi::maxchkbp = 100000; rsi::minmlen = 3.01; rsi::buffer = 0.05; rsi::p = 0.05;
 }
+// the undocumented knobs -reflen / -maxchkbp (rsi.cpp:2024-2026); call after ref_set_params
+void ref_set_knobs(double chklen, int maxchkbp) { rsi::chklen = chklen; rsi::maxchkbp = maxchkbp; }
 void ref_set_state(double RDmedian, double RDsd, int start, int end, int Lmax, double factor) {
   rsi::RDmedian = RDmedian; rsi::RDsd = RDsd; rsi::start = start; rsi::end = end; rsi::Lmax = Lmax;
   rsi::factor = factor;

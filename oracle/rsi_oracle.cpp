@@ -715,6 +715,10 @@ void sd_filters(std::vector<ocl_cnv>& list) {
 
 // L3: detectcnv, rsi.cpp:1795-1945.  Optionally exports the bin-level intermediates.
 struct BinDump { std::vector<float> med, nbn; std::vector<int> medint, status; };
+// the intermediate call lists of the last detectcnv (parity of RSIGPU_ARR_SEGMENTS/BLOCKS/PREMERGE/MERGED):
+// [0] segments leaving rsicnvnbn/rsicnvmed (the last transformation run), [1] after areblockscnv, [2] after
+// bins->bases + 2x optimize + sort, [3] after mergesegments + sort
+std::vector<ocl_cnv> g_lists[4];
 void detectcnv(const int* RD, int n, std::vector<ocl_cnv>& out, BinDump* dump) {
   out.clear();
   if (G.RDmedian < 5) return;
@@ -730,13 +734,15 @@ void detectcnv(const int* RD, int n, std::vector<ocl_cnv>& out, BinDump* dump) {
   G.Lmax = std::max(10000 / m, 20);
   std::vector<int> st_med(nb, 0), st_nbn(nb, 0);
   std::vector<ocl_cnv> segs;
-  if (G.trans != 0) { rsicnv(1, med.data(), medint.data(), nb, st_med.data(), segs); areblockscnv(medint.data(), st_med.data(), nb, segs); }
-  if (G.trans == 0) { rsicnv(0, nbn.data(), medint.data(), nb, st_nbn.data(), segs); areblockscnv(medint.data(), st_nbn.data(), nb, segs); }
+  for (auto& l : g_lists) l.clear();
+  if (G.trans != 0) { rsicnv(1, med.data(), medint.data(), nb, st_med.data(), segs); g_lists[0] = segs; areblockscnv(medint.data(), st_med.data(), nb, segs); }
+  if (G.trans == 0) { rsicnv(0, nbn.data(), medint.data(), nb, st_nbn.data(), segs); g_lists[0] = segs; areblockscnv(medint.data(), st_nbn.data(), nb, segs); }
   if (G.trans == 2) {
     std::vector<ocl_cnv> s2;
-    rsicnv(0, nbn.data(), medint.data(), nb, st_nbn.data(), s2); areblockscnv(medint.data(), st_nbn.data(), nb, s2);
+    rsicnv(0, nbn.data(), medint.data(), nb, st_nbn.data(), s2); g_lists[0] = s2; areblockscnv(medint.data(), st_nbn.data(), nb, s2);
     segs.insert(segs.end(), s2.begin(), s2.end());
   }
+  g_lists[1] = segs;
   if (dump) { dump->med = med; dump->nbn = nbn; dump->medint = medint; dump->status = G.trans == 1 ? st_med : st_nbn; }
   sort_by_start(segs);
   std::vector<ocl_cnv> list;
@@ -753,8 +759,10 @@ void detectcnv(const int* RD, int n, std::vector<ocl_cnv>& out, BinDump* dump) {
   for (auto& c : list) c.tid = G.tid;
   for (int rep = 0; rep < 2; ++rep) for (auto& c : list) optimize_one(RD, n, c);
   sort_by_start(list);
+  g_lists[2] = list;
   mergesegments(RD, n, list);
   sort_by_start(list);
+  g_lists[3] = list;
   for (int i = 0; i < (int)list.size(); ++i) {
     double len = double(list[i].end - list[i].start + 1) / double(m);
     isitcnvwrap(RD, n, list, i);
@@ -928,6 +936,8 @@ void ocl_set_params(int m, int minq, int min_baseQ, double cap, int gcadjust, in
   G.m = m; G.minq = minq; G.min_baseQ = min_baseQ; G.cap = cap; G.gcadjust = gcadjust != 0; G.trans = trans;
   G.merge = merge != 0; G.threshold = threshold; G.epsilon = epsilon;
 }
+// the undocumented knobs -reflen / -maxchkbp (rsi.cpp:2024-2026); call after ocl_set_params
+void ocl_set_knobs(double chklen, int maxchkbp) { G.chklen = chklen; G.maxchkbp = maxchkbp; }
 void ocl_set_state(double RDmedian, double RDsd, int start, int end, int Lmax, double factor) {
   G.RDmedian = RDmedian; G.RDsd = RDsd; G.start = start; G.end = end; G.Lmax = Lmax; G.factor = factor;
 }
@@ -995,6 +1005,10 @@ int ocl_mergesegments(const int* rd, int n, ocl_cnv* list, int nlist) {
 }
 int ocl_sd_filters(ocl_cnv* list, int nlist) { std::vector<ocl_cnv> v(list, list + nlist); sd_filters(v); return list_out(v, list, nlist); }
 int ocl_expand_coordinate(int p) { return expand_coordinate(p); }
+int ocl_last_list(int which, ocl_cnv* out, int cap) {
+  if (which < 0 || which > 3) return -1;
+  return list_out(g_lists[which], out, cap);
+}
 int ocl_detectcnv(const int* rd, int n, ocl_cnv* out, int cap) {
   std::vector<ocl_cnv> v; detectcnv(rd, n, v, nullptr); return list_out(v, out, cap);
 }

@@ -90,6 +90,7 @@ struct rsigpu_ctx {
   std::string err;
   int L = 0, Lc = 0, nb = 0, tid = 0;
   bool have_ref = false, have_depth = false, have_reads = false, loaded = false, detected = false, filtered = false;
+  bool pileup_fresh = false;   // rsigpu_pileup_end has just produced the depth of the staged reads: the next rsigpu_run does not redo it
   int cand_a_threads = 256;
   int level0_mode = 2;   // 2 = multi-block exact chain (default), 1 = one-block scan form, 0 = plain sequential FADD chain (cross-check)
   DevBuf<double> d_csum, d_clbc; DevBuf<i64> d_cchunk, d_clx; DevBuf<u32> d_clhist;
@@ -118,7 +119,7 @@ struct rsigpu_ctx {
   struct BamRun { int tid; i64 r0, r1, c0, c1, q0, q1; };
   std::vector<BamRun> b_runs;
   int b_nref = 0, b_tail_len = 0, b_rewalked = 0; bool b_active = false, b_first_feed = true;
-  size_t b_umax = (size_t)5 << 30;   // decoded bytes one feed may produce (test hook: rsigpu_set_level0_mode(1000000 + bytes))
+  size_t b_umax = (size_t)5 << 30;   // decoded bytes one feed may produce (test hook: rsigpu_set_feed_limit)
   // accounting
   long long h_cprof[16] = {};
   int64_t launches = 0;
@@ -636,6 +637,8 @@ static int run_pileup(rsigpu_ctx* c) {
   const size_t padded = ((size_t)c->L + LD_TILE - 1) / LD_TILE * LD_TILE + 64;
   CK(c->d_raw.ensure(padded));
   int* mx = c->d_misc.p + 5;   // max_extent, sorted_bad
+  // a previous insert-size sample (second stream) may still be reading max_extent
+  if (c->isize_pending) { CK(cudaStreamWaitEvent(c->stream, c->ev_isize, 0)); c->isize_pending = false; }
   CK(cudaMemsetAsync(mx, 0, 8, c->stream));
   if (c->r_pos.n == 0) {
     CK(cudaMemsetAsync(c->d_raw.p, 0, padded * 4, c->stream));
@@ -676,6 +679,7 @@ int rsigpu_pileup_end(rsigpu_ctx* c) {
   CK(cudaStreamSynchronize(c->stream));
   if (h[1]) { c->fail("read batch is not sorted by position"); return RSIGPU_E_ARG; }
   c->have_reads = true; c->loaded = false; c->detected = false; c->filtered = false;
+  c->pileup_fresh = true;
   return RSIGPU_OK;
 }
 
@@ -880,7 +884,9 @@ int rsigpu_run(rsigpu_ctx* c, rsigpu_cnv* out, int32_t cap, int32_t* n) {
   int rc;
   TRACE(c, "run: start");
   CK(cudaEventRecord(c->ev[0], c->stream));
-  if (c->have_reads && (rc = run_pileup(c)) != RSIGPU_OK) return rc;   // BAM input: the pileup is the first stage of the path
+  // BAM input: the pileup is the first stage of the path (already done when rsigpu_pileup_end has just run it, the -s path)
+  if (c->have_reads && !(c->pileup_fresh && c->have_depth) && (rc = run_pileup(c)) != RSIGPU_OK) return rc;
+  c->pileup_fresh = false;
   if ((rc = rsigpu_load_finish(c)) != RSIGPU_OK) return rc;
   if ((rc = rsigpu_detectcnv(c)) != RSIGPU_OK) return rc;
   if ((rc = rsigpu_sd_filters(c)) != RSIGPU_OK) return rc;
@@ -999,11 +1005,20 @@ int rsigpu_debug_state(const rsigpu_ctx* c, double* out, int32_t cap) {
 
 // test hooks (see include/rsigpu.h): 0/1/2 = form of filterstatus' level-0 float sum (2 = multi-block, default)
 int rsigpu_set_level0_mode(rsigpu_ctx* c, int mode) {
-  if (!c) return RSIGPU_E_ARG;
-  if (mode >= 1000000) { c->b_umax = (size_t)(mode - 1000000); return RSIGPU_OK; }   // test hook: decoded-size limit of one rsigpu_bam_feed
-  if (mode >= 100) { c->cand_a_threads = mode - 100; return RSIGPU_OK; }   // tuning hook: 100 + threads of the bin-level candidate kernel
-  if (mode < 0 || mode > 2) return RSIGPU_E_ARG;
+  if (!c || mode < 0 || mode > 2) return RSIGPU_E_ARG;
   c->level0_mode = mode;
+  return RSIGPU_OK;
+}
+// test hook: decoded bytes one rsigpu_bam_feed may produce (partial-consumption path)
+int rsigpu_set_feed_limit(rsigpu_ctx* c, int64_t decoded_bytes) {
+  if (!c || decoded_bytes < 65536) return RSIGPU_E_ARG;
+  c->b_umax = (size_t)decoded_bytes;
+  return RSIGPU_OK;
+}
+// tuning hook: threads of the bin-level candidate kernel
+int rsigpu_set_cand_threads(rsigpu_ctx* c, int threads) {
+  if (!c || threads < 32 || threads > 1024 || threads % 32) return RSIGPU_E_ARG;
+  c->cand_a_threads = threads;
   return RSIGPU_OK;
 }
 

@@ -159,6 +159,34 @@ def write_depth_file(path: str, depth: np.ndarray, chunk: int = 4_000_000) -> No
             f.write(b"\n")
 
 
+def write_depth_file_fast(path: str, depth: np.ndarray, chunk: int = 8_000_000) -> None:
+    """the same `pos<TAB>depth` file written with vectorised digit arithmetic (a chr19-sized file in seconds); the depth column is
+    zero-padded to the width of the largest value -- `istream >> int` (loaddata.cpp:509) reads "030" as 30"""
+    depth = np.asarray(depth)
+    wd = max(1, len(str(int(depth.max(initial=0)))))
+    assert depth.min(initial=0) >= 0
+    with open(path, "wb") as f:
+        L = len(depth)
+        a = 0
+        while a < L:
+            # positions a+1 .. with the same number of digits
+            p0 = a + 1
+            wp = len(str(p0))
+            b = min(L, a + chunk, 10 ** wp - 1)
+            n = b - a
+            pos = np.arange(p0, p0 + n, dtype=np.int64)
+            d = depth[a:b].astype(np.int64)
+            line = np.empty((n, wp + 1 + wd + 1), np.uint8)
+            for k in range(wp):
+                line[:, wp - 1 - k] = 48 + (pos // 10 ** k) % 10
+            line[:, wp] = 9
+            for k in range(wd):
+                line[:, wp + wd - k] = 48 + (d // 10 ** k) % 10
+            line[:, -1] = 10
+            f.write(line.tobytes())
+            a = b
+
+
 def stress_events(L: int, seed: int, n_blocks) -> list[tuple[int, int, float]]:
     """Adversarial event layout for the candidate stage: same-type neighbours separated by short gaps
     (merge paths), nested copy-number levels (multi-level RSI status -> multisegments), weak events

@@ -67,12 +67,14 @@ class Lib:
         return getattr(self.lib, self.pre + name)
 
     # ---- state
-    def set_params(self, m=101, minq=0, min_baseQ=13, cap=4.0, gcadjust=1, trans="NBN", merge=1, threshold=-1.0, epsilon=1.5):
+    def set_params(self, m=101, minq=0, min_baseQ=13, cap=4.0, gcadjust=1, trans="NBN", merge=1, threshold=-1.0, epsilon=1.5,
+                   chklen=2.5, maxchkbp=100000):
         t = C.c_int(TRANS[trans]) if self.kind == "oracle" else C.c_char_p(trans.encode())
         if self.kind == "ref" and m % 2 != 1:
             m += 1
         self.fn("set_params")(C.c_int(m), C.c_int(minq), C.c_int(min_baseQ), C.c_double(cap), C.c_int(gcadjust), t,
                               C.c_int(merge), C.c_double(threshold), C.c_double(epsilon))
+        self.fn("set_knobs")(C.c_double(chklen), C.c_int(maxchkbp))   # -reflen / -maxchkbp (rsi.cpp:2024-2026)
 
     def set_state(self, RDmedian, RDsd, start, end, Lmax=-1, factor=6.6):
         self.fn("set_state")(C.c_double(RDmedian), C.c_double(RDsd), C.c_int(start), C.c_int(end), C.c_int(Lmax), C.c_double(factor))
@@ -241,6 +243,12 @@ class Lib:
     def detectcnv(self, rd):
         rd = i32(rd); out = self._list()
         n = self.fn("detectcnv")(_p(rd, C.c_int), C.c_int(len(rd)), out, C.c_int(len(out)))
+        return self._copy(out, n)
+
+    def last_list(self, which):
+        """intermediate call lists of the last detectcnv (oracle only): 0 segments, 1 blocks, 2 premerge, 3 merged"""
+        out = self._list(65536)
+        n = self.fn("last_list")(C.c_int(which), out, C.c_int(len(out)))
         return self._copy(out, n)
 
     def depth_path(self, depth, fasta, stage=3, want_bins=False):

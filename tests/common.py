@@ -39,6 +39,7 @@ def run_depth_case(lib_path, oracle, fa, d, check_bins=True, level0_modes=(2,), 
     """the whole depth path through the C ABI vs the oracle; returns the calls"""
     oracle.set_params(**oracle_params(kw))
     ro = oracle.depth_path(d, fa, 3, want_bins=True)
+    ro_lists = [oracle.last_list(k) for k in range(4)]
     ro1 = None
     ctx = api.Context(lib=lib_path, **kw)
     try:
@@ -62,6 +63,9 @@ def run_depth_case(lib_path, oracle, fa, d, check_bins=True, level0_modes=(2,), 
                 assert np.array_equal(ctx.array(api.ARR_BIN_NBN), bn[:nb]), "negative_binomial_transfer"
                 assert np.array_equal(ctx.array(api.ARR_BIN_STATUS), bs[:nb]), "RSI status"
             assert_calls_equal(calls, ro["calls"], f"level0_mode={mode}")
+            # the intermediate lists: segments leaving rsicnv*, after areblockscnv, before / after mergesegments
+            for k, name in enumerate(("segments", "blocks", "premerge", "merged")):
+                assert_calls_equal(ctx.array(api.ARR_SEGMENTS + k), ro_lists[k], f"{name} list, level0_mode={mode}")
         return calls, ctx.launch_count()
     finally:
         ctx.close()

@@ -92,8 +92,10 @@ def test_gc_cap_compact_live(L, oracle, ref):
     assert np.array_equal(nb_o, nb_r) and np.array_equal(ne_o, ne_r)
 
 
-@pytest.mark.parametrize("case", [dict(L=500_003, seed=12, stress=True), dict(L=900_001, seed=14, kw=dict(trans="MED")), dict(L=700_001, seed=15, kw=dict(m=51))],
-                         ids=lambda c: f"L{c['L']}-s{c['seed']}")
+@pytest.mark.parametrize("case", [dict(L=500_003, seed=12, stress=True), dict(L=900_001, seed=14, kw=dict(trans="MED")), dict(L=700_001, seed=15, kw=dict(m=51)),
+                                  dict(L=700_003, seed=9, stress=True, kw=dict(epsilon=0.5)), dict(L=500_003, seed=39, stress=True, kw=dict(chklen=1.5)),
+                                  dict(L=700_003, seed=9, stress=True, kw=dict(maxchkbp=500)), dict(L=600_007, seed=5, kw=dict(epsilon=3.0, chklen=4.0, maxchkbp=2000))],
+                         ids=lambda c: f"L{c['L']}-s{c['seed']}-{'-'.join(f'{k}{v}' for k, v in c.get('kw', {}).items()) or 'default'}")
 def test_depth_path_live(case, oracle, ref):
     fa, d, _ = make_case(case["L"], case["seed"], stress=case.get("stress", False))
     kw = oracle_params(case.get("kw", {}))

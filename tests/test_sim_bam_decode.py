@@ -269,7 +269,7 @@ def test_feed_stops_at_its_decoded_size_limit(sim_lib, tmp_path):
     data = np.fromfile(path, np.uint8)
     h = api.parse_bam_header(data)
     ctx = api.Context(lib=sim_lib)
-    ctx.set_level0_mode(1000000 + 70000)          # at most three 20000-byte blocks per feed
+    ctx.set_feed_limit(70000)          # at most three 20000-byte blocks per feed
     ctx.bam_begin(1)
     parts = []; off = h["coff"]; first = True; feeds = 0
     while off < len(data):

@@ -24,6 +24,9 @@ CASES = [
     dict(L=500_003, seed=10, kw=dict(merge=False), stress=True),
     dict(L=500_003, seed=39, stress=True), dict(L=500_003, seed=51, stress=True),
     dict(L=600_007, seed=6, kw=dict(trans="MED", threshold=5.0)),   # Lmax = (4*5)^2 = 400 > 256: the large-footprint scan instantiation
+    # the undocumented knobs (rsi.cpp:2020-2026): -e (RSI factor), -reflen (neighbourhood length), -maxchkbp (sub-sampling of long neighbourhoods)
+    dict(L=700_003, seed=9, kw=dict(epsilon=0.5), stress=True), dict(L=500_003, seed=39, kw=dict(chklen=1.5), stress=True),
+    dict(L=700_003, seed=9, kw=dict(maxchkbp=500), stress=True), dict(L=600_007, seed=5, kw=dict(epsilon=3.0, chklen=4.0, maxchkbp=2000)),
     dict(L=600_007, seed=6, kw=dict(trans="ALL")), dict(L=700_003, seed=9, kw=dict(trans="ALL"), stress=True),   # a final test fails: the speculative per-call results are redone in order
 ]
 

@@ -7,7 +7,7 @@ L = synth.CHR19_LEN
 fa, d, _ = make_case(L, 23, n_events=20, lens=(2000, 5000, 10000, 30000, 100000))
 ctx = api.Context(); ctx.set_reference(fa); ctx.set_depth(d)
 for nt in (32, 64, 128, 256, 512):
-    ctx.set_level0_mode(100 + nt)
+    ctx.set_cand_threads(nt)
     ctx.run(); ctx.run()
     ctx.set_profile(True); calls = ctx.run()
     pr = {k: v for k, v, n in ctx.profile()}
