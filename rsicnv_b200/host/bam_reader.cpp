@@ -182,4 +182,49 @@ bool read_bam_header(const std::string& path, BamHeader* hdr, long long* rec_cof
   return true;
 }
 
+// BAI layout (SAM spec 5.2; written by bam_index_save, bam_index.c:262-319): magic "BAI\1", n_ref, then per reference
+// n_bin x {bin, n_chunk, n_chunk x (beg, end)}, n_intv, n_intv x ioffset.  Bin 37450 is samtools' pseudo-bin (file range of
+// the reference + mapped/unmapped counts), not a chunk list.
+bool read_bai(const std::string& bam_path, size_t n_ref, std::vector<BaiRef>* out) {
+  FILE* f = fopen((bam_path + ".bai").c_str(), "rb");
+  if (!f) {
+    std::string alt = bam_path;
+    if (alt.size() > 4 && alt.compare(alt.size() - 4, 4, ".bam") == 0) { alt.replace(alt.size() - 4, 4, ".bai"); f = fopen(alt.c_str(), "rb"); }
+    if (!f) return false;
+  }
+  std::vector<uint8_t> d;
+  uint8_t tmp[1 << 16];
+  size_t got;
+  while ((got = fread(tmp, 1, sizeof tmp, f)) > 0) d.insert(d.end(), tmp, tmp + got);
+  fclose(f);
+  size_t p = 0;
+  auto u32 = [&](uint32_t* v) { if (p + 4 > d.size()) return false; *v = rd32(&d[p]); p += 4; return true; };
+  auto u64 = [&](uint64_t* v) { if (p + 8 > d.size()) return false; *v = (uint64_t)rd32(&d[p]) | ((uint64_t)rd32(&d[p + 4]) << 32); p += 8; return true; };
+  uint32_t nref = 0;
+  if (d.size() < 8 || memcmp(d.data(), "BAI\1", 4) != 0) return false;
+  p = 4;
+  if (!u32(&nref) || nref != n_ref) return false;
+  out->assign(n_ref, BaiRef());
+  for (uint32_t r = 0; r < nref; ++r) {
+    uint32_t nbin = 0;
+    if (!u32(&nbin)) return false;
+    uint64_t first = ~0ull;
+    for (uint32_t b = 0; b < nbin; ++b) {
+      uint32_t bin = 0, nchunk = 0;
+      if (!u32(&bin) || !u32(&nchunk)) return false;
+      for (uint32_t k = 0; k < nchunk; ++k) {
+        uint64_t beg = 0, end = 0;
+        if (!u64(&beg) || !u64(&end)) return false;
+        if (bin != 37450 && beg < first) first = beg;
+      }
+    }
+    uint32_t nintv = 0;
+    if (!u32(&nintv)) return false;
+    if (p + 8 * (size_t)nintv > d.size()) return false;
+    p += 8 * (size_t)nintv;
+    if (first != ~0ull) { (*out)[r].has_reads = true; (*out)[r].first_voff = first; }
+  }
+  return true;
+}
+
 }  // namespace rsihost

@@ -61,4 +61,11 @@ class BamReader {
 // block in front of it.  This is what the GPU decoder (rsigpu_bam_feed) needs from the host.
 bool read_bam_header(const std::string& path, BamHeader* hdr, long long* rec_coff, long long* rec_skip, std::string* err);
 
+// The BAI index next to the BAM (bam_index.c:321-465 loads it; the reference REQUIRES it: rsi.cpp:2112-2113).  Only what the
+// chromosome-sharded GPU path needs: for every reference sequence whether it has records (the reference's "populated" test,
+// rsi.cpp:2121-2126) and the virtual file offset (BGZF block offset << 16 | offset inside the decoded block) of its first
+// record, so that every GPU can start decoding ITS contigs in the middle of the file.  false if the file is absent or malformed.
+struct BaiRef { bool has_reads = false; uint64_t first_voff = 0; };
+bool read_bai(const std::string& bam_path, size_t n_ref, std::vector<BaiRef>* out);
+
 }  // namespace rsihost

@@ -16,7 +16,12 @@
 #include <string.h>
 #include <time.h>
 
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <algorithm>
+#include <atomic>
 #include <fstream>
 #include <mutex>
 #include <string>
@@ -216,129 +221,275 @@ bool run_contig(rsigpu_ctx* c, const Opt& o, const std::string& name, int tid, c
 
 double now_s() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec; }
 
-// BAM input decoded on the GPU: the file is streamed in chunks of whole BGZF blocks into rsigpu_bam_feed (inflate + record
-// decoding, k_bam.cuh); each run of records of one contig is appended to the context of the GPU that owns the contig.
-// A reader thread fills the next pinned chunk while the GPU works on the current one.
-int bam_on_gpu(const Opt& o, std::vector<rsigpu_ctx*>& ctx, std::vector<ContigResult>* results_out) {
+// which contigs of the header are processed (rsi.cpp:2116-2143): by default every contig whose name contains neither "MT"
+// nor "." (and that has reads); with -c exactly the named one, whatever its name
+bool eligible(const Opt& o, const std::string& name) {
+  if (o.chr != "1-22XY") return name == o.chr;
+  return name.find("MT") == std::string::npos && name.find(".") == std::string::npos;
+}
+
+// longest-processing-time assignment from the header lengths (1.038 imbalance for b37 on 8 GPUs)
+std::vector<int> lpt_assign(const Opt& o, const BamHeader& h, int ng, const std::vector<BaiRef>* bai) {
+  std::vector<int> gpu_of(h.name.size(), -1);
+  std::vector<size_t> order;
+  for (size_t i = 0; i < h.name.size(); ++i) if (eligible(o, h.name[i]) && (!bai || (*bai)[i].has_reads)) order.push_back(i);
+  std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return h.len[a] > h.len[b]; });
+  std::vector<long long> load((size_t)ng, 0);
+  for (size_t i : order) { const int g = (int)(std::min_element(load.begin(), load.end()) - load.begin()); gpu_of[i] = g; load[(size_t)g] += h.len[i]; }
+  return gpu_of;
+}
+
+// page-cache -> buffer with several threads (one memcpy stream of pread() tops out near 3 GB/s)
+size_t parallel_pread(int fd, uint8_t* dst, size_t n, long long off, int nthreads = 4) {
+  if (n < ((size_t)8 << 20)) nthreads = 1;
+  std::vector<std::thread> th; std::vector<size_t> got((size_t)nthreads, 0);
+  const size_t per = (n + (size_t)nthreads - 1) / (size_t)nthreads;
+  for (int t = 0; t < nthreads; ++t)
+    th.emplace_back([&, t]() {
+      size_t a = (size_t)t * per, e = std::min(n, a + per), done = 0;
+      while (a + done < e) {
+        const ssize_t r = pread(fd, dst + a + done, e - a - done, (off_t)(off + (long long)(a + done)));
+        if (r <= 0) break;
+        done += (size_t)r;
+      }
+      got[(size_t)t] = done;
+    });
+  for (auto& x : th) x.join();
+  size_t total = 0;
+  for (int t = 0; t < nthreads; ++t) { total += got[(size_t)t]; if (got[(size_t)t] < std::min(n, ((size_t)t + 1) * per) - std::min(n, (size_t)t * per)) break; }
+  return total;
+}
+
+// FASTA of the next contig read while the current one is being decoded
+struct FastaPrefetch {
+  std::string ref; std::thread th; std::string name, fasta, err; bool ok = false, busy = false;
+  explicit FastaPrefetch(const std::string& r) : ref(r) {}
+  ~FastaPrefetch() { if (th.joinable()) th.join(); }
+  void request(const std::string& n) {
+    if (th.joinable()) th.join();
+    name = n; busy = true;
+    th = std::thread([this]() { fasta.clear(); err.clear(); ok = read_fasta(ref, name, &fasta, &err); });
+  }
+  bool take(const std::string& n, std::string* out, std::string* e) {
+    if (!busy || name != n) request(n);
+    th.join(); busy = false;
+    if (!ok) { *e = err; return false; }
+    out->swap(fasta);
+    return true;
+  }
+};
+
+struct DecodeTiming { double feed = 0, take = 0, wait = 0, read = 0; };
+
+// Streams a BAM file from file offset `coff` (a BGZF block boundary; `skip` decoded bytes of that block precede the first
+// wanted record) through the decoder context `dec` in chunks of whole BGZF blocks read one chunk ahead.  on_run(i, run) is
+// called for every run of records with one refID, in file order: 0 = go on, 1 = stop (the caller has what it wanted),
+// < 0 = error.  Returns 0 (end of file or stopped), 1 on any error (message on stderr): the caller must NOT use the partial data.
+template <class F>
+int stream_bam(const std::string& path, long long coff, long long skip, rsigpu_ctx* dec, size_t chunk_bytes, F&& on_run, DecodeTiming* tm) {
+  const int fd = open(path.c_str(), O_RDONLY);
+  if (fd < 0) { fprintf(stderr, "cannot open %s\n", path.c_str()); return 1; }
+  struct stat sb;
+  if (fstat(fd, &sb) != 0 || (long long)sb.st_size < coff) { fprintf(stderr, "cannot read %s\n", path.c_str()); close(fd); return 1; }
+  const size_t remaining = (size_t)((long long)sb.st_size - coff);
+  const size_t CARRY = (size_t)1 << 20;
+  const size_t CHUNK = std::max<size_t>(std::min(chunk_bytes, remaining + 1), (size_t)1 << 20);
+  const bool two = remaining > CHUNK;
+  uint8_t* buf[2] = {nullptr, nullptr};
+  for (int k = 0; k < (two ? 2 : 1); ++k)
+    if (rsigpu_pinned_alloc(CARRY + CHUNK, (void**)&buf[k])) { fprintf(stderr, "cannot allocate pinned staging memory\n"); close(fd); for (int j = 0; j < k; ++j) rsigpu_pinned_free(buf[j]); return 1; }
+  auto cleanup = [&]() { for (int k = 0; k < 2; ++k) rsigpu_pinned_free(buf[k]); close(fd); };
+  long long foff = coff;
+  double t0 = now_s();
+  size_t have = parallel_pread(fd, buf[0] + CARRY, std::min(CHUNK, remaining), foff);
+  tm->read += now_s() - t0;
+  foff += (long long)have;
+  uint8_t* cur = buf[0] + CARRY;      // valid bytes: [cur, cur + have)
+  int cb = 0; bool eof = (size_t)(foff - coff) >= remaining, first = true;
+  std::vector<rsigpu_bam_run> runs(65536);          // the decoder's own limit of runs per feed
+  std::thread reader; size_t next_got = 0;
+  int status = 0; bool stop = false;
+  while (have > 0 && !stop && !status) {
+    const int nb = cb ^ 1;
+    if (!eof) {
+      const size_t want = std::min(CHUNK, remaining - (size_t)(foff - coff));
+      reader = std::thread([&, nb, want]() { next_got = parallel_pread(fd, buf[nb] + CARRY, want, foff); });
+    }
+    size_t pos = 0;
+    for (;;) {          // the decoder takes whole blocks up to its own limits: present the rest again until (less than) one block is left
+      int64_t consumed = 0; int32_t nr = 0;
+      t0 = now_s();
+      const int rc = rsigpu_bam_feed(dec, cur + pos, (int64_t)(have - pos), first ? skip : 0, &consumed, runs.data(), (int32_t)runs.size(), &nr);
+      tm->feed += now_s() - t0;
+      if (rc) { fprintf(stderr, "%s\n", rsigpu_last_error(dec)); status = 1; break; }
+      if (nr > (int32_t)runs.size()) { fprintf(stderr, "more than %zu reference runs in one chunk of %s\n", runs.size(), path.c_str()); status = 1; break; }
+      if (consumed) first = false;
+      t0 = now_s();
+      for (int i = 0; i < nr && !stop && !status; ++i) {
+        const int r = on_run(i, runs[(size_t)i]);
+        if (r > 0) stop = true; else if (r < 0) status = 1;
+      }
+      tm->take += now_s() - t0;
+      pos += (size_t)consumed;
+      if (stop || status || consumed == 0 || have - pos < ((size_t)1 << 17)) break;
+    }
+    const size_t rest = have - pos;
+    if (reader.joinable()) reader.join();
+    if (stop || status) break;
+    if (eof) {
+      if (rest) { fprintf(stderr, "truncated BGZF block at the end of %s\n", path.c_str()); status = 1; }
+      break;
+    }
+    if (rest > CARRY) { fprintf(stderr, "%s: a BGZF block sequence the decoder cannot take (%zu bytes left over)\n", path.c_str(), rest); status = 1; break; }
+    memcpy(buf[nb] + CARRY - rest, cur + pos, rest);
+    cur = buf[nb] + CARRY - rest; have = rest + next_got;
+    foff += (long long)next_got;
+    if ((size_t)(foff - coff) >= remaining || next_got == 0) eof = true;
+    cb = nb;
+  }
+  if (reader.joinable()) reader.join();
+  if (!status && !stop && rsigpu_bam_end(dec)) { fprintf(stderr, "%s\n", rsigpu_last_error(dec)); status = 1; }
+  cleanup();
+  return status;
+}
+
+// BAM input decoded on the GPU (rsigpu_bam_feed: BGZF inflate + record decoding, k_bam.cuh).
+//   With the .bai index (which the reference requires, rsi.cpp:2112-2113): every GPU owns the contigs LPT gives it, seeks to the
+//   first record of each (virtual offset from the index) and runs its OWN decoder -- reading, decoding and the hot path of
+//   different GPUs never meet.  Per GPU two contig contexts alternate: contig k+1 is decoded while contig k is in the hot path,
+//   and the FASTA of contig k+1 is read while contig k is decoded.
+//   Without an index: one pass over the file with the decoder on GPU 0; each run of records is appended to the context of the
+//   owning GPU (device-to-device, rsigpu_bam_take).
+// Any decoder error fails the contig being decoded: its rows are not written and the exit status is non-zero.
+int bam_on_gpu(const Opt& o, const std::vector<std::vector<rsigpu_ctx*>>& ctx, std::vector<ContigResult>* results_out) {
   const bool timing = getenv("RSICNV_TIMING") != nullptr;
   const double t_start = now_s();
-  double t_feed = 0, t_take = 0, t_wait = 0;
   std::string err;
   long long coff = 0, skip = 0;
   BamHeader h;
-  if (!read_bam_header(o.bamfile, &h, &coff, &skip, &err)) { fprintf(stderr, "%s\n", err.c_str()); return 0; }
+  if (!read_bam_header(o.bamfile, &h, &coff, &skip, &err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
   std::vector<ContigResult>& results = *results_out;
   results.resize(h.name.size());
   for (size_t i = 0; i < h.name.size(); ++i) results[i].name = h.name[i];
   if (o.chr != "1-22XY" && std::find(h.name.begin(), h.name.end(), o.chr) == h.name.end()) { fprintf(stderr, "BAM file doesn't have %s\n", o.chr.c_str()); return 0; }
-  const int ng = (int)ctx.size();
-  auto eligible = [&](int tid) {
-    const std::string& name = h.name[(size_t)tid];
-    if (name.find("MT") != std::string::npos || name.find(".") != std::string::npos) return false;   // rsi.cpp:2119-2120
-    return o.chr == "1-22XY" || name == o.chr;
-  };
-  // longest-processing-time assignment from the header lengths (1.038 imbalance for b37 on 8 GPUs)
-  std::vector<int> gpu_of(h.name.size(), 0);
-  {
-    std::vector<size_t> order;
-    for (size_t i = 0; i < h.name.size(); ++i) if (eligible((int)i)) order.push_back(i);
-    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return h.len[a] > h.len[b]; });
-    std::vector<long long> load((size_t)ng, 0);
-    for (size_t i : order) { const int g = (int)(std::min_element(load.begin(), load.end()) - load.begin()); gpu_of[i] = g; load[(size_t)g] += h.len[i]; }
-  }
-  rsigpu_ctx* dec = nullptr;
-  if (rsigpu_create(0, &o.P, &dec)) { fprintf(stderr, "cannot create the decoder context\n"); return 2; }
-  if (rsigpu_bam_begin(dec, (int32_t)h.name.size())) { fprintf(stderr, "%s\n", rsigpu_last_error(dec)); return 2; }
-  FILE* f = fopen(o.bamfile.c_str(), "rb");
-  if (!f || fseeko(f, (off_t)coff, SEEK_SET) != 0) { fprintf(stderr, "cannot open %s\n", o.bamfile.c_str()); return 0; }
-  // chunk = what one rsigpu_bam_feed sees: large enough that its ~20 k BGZF blocks fill the GPU (one thread inflates one block);
-  // whatever the decoder does not take (it stops at whole blocks, or at its decoded-size limit) is presented again
-  fseeko(f, 0, SEEK_END);
-  const size_t fsize = (size_t)ftello(f) - (size_t)coff;
-  fseeko(f, (off_t)coff, SEEK_SET);
-  const size_t CHUNK = std::max<size_t>(std::min<size_t>((size_t)256 << 20, fsize + 1), (size_t)1 << 20), CARRY = CHUNK;
-  uint8_t* buf[2] = {nullptr, nullptr};
-  for (int k = 0; k < 2; ++k) if (rsigpu_pinned_alloc(CARRY + CHUNK, (void**)&buf[k])) { fprintf(stderr, "cannot allocate pinned staging memory\n"); return 2; }
-  std::vector<std::thread> workers((size_t)ng);
+  const int ng = (int)ctx.size(), n_ref = (int)h.name.size();
+  std::vector<BaiRef> bai;
+  const bool indexed = !getenv("RSICNV_NO_INDEX") && read_bai(o.bamfile, h.name.size(), &bai);
+  const std::vector<int> gpu_of = lpt_assign(o, h, ng, indexed ? &bai : nullptr);
   std::mutex mu;
-  int cur = -1; bool cur_ok = false; std::string cur_fasta_err;
-  size_t cur_len = 0;
-  auto finish_cur = [&]() {
-    if (cur < 0 || !cur_ok) { cur = -1; return; }
-    const int tid = cur, g = gpu_of[(size_t)tid]; const size_t flen = cur_len;
-    workers[(size_t)g] = std::thread([&, tid, g, flen]() {
+  std::atomic<int> failed(0);
+  const size_t CHUNK = (size_t)1 << 30;
+  auto fail_contig = [&](int tid, const std::string& what) {
+    std::lock_guard<std::mutex> lk(mu);
+    results[(size_t)tid].err = what; results[(size_t)tid].done = false;
+    fprintf(stderr, "%s: %s\n", results[(size_t)tid].name.c_str(), what.c_str());
+    failed++;
+  };
+  auto finish_async = [&](std::thread* slot, rsigpu_ctx* c, int tid, size_t flen) {
+    *slot = std::thread([&, c, tid, flen]() {
       ContigResult& r = results[(size_t)tid];
-      r.done = finish_contig(ctx[(size_t)g], o, r.name, flen, true, &r);
-      if (!r.done) { std::lock_guard<std::mutex> lk(mu); fprintf(stderr, "%s: %s\n", r.name.c_str(), r.err.c_str()); }
+      r.done = finish_contig(c, o, r.name, flen, true, &r);
+      if (!r.done) { std::lock_guard<std::mutex> lk(mu); fprintf(stderr, "%s: %s\n", r.name.c_str(), r.err.c_str()); failed++; }
     });
-    cur = -1;
   };
-  auto start = [&](int tid, long long nfirst) {
-    cur = tid; cur_ok = false;
-    if (!eligible(tid)) return;
-    const int g = gpu_of[(size_t)tid];
-    const double t0 = now_s();
-    if (workers[(size_t)g].joinable()) workers[(size_t)g].join();
-    t_wait += now_s() - t0;
-    ContigResult& r = results[(size_t)tid];
-    fprintf(stderr, "#processing %s on GPU %d\n", r.name.c_str(), g);
-    (void)nfirst;
-    std::string fasta, e2;
-    if (!read_fasta(o.reffile, r.name, &fasta, &e2)) { r.err = e2; fprintf(stderr, "%s: %s\n", r.name.c_str(), e2.c_str()); return; }
-    if ((int)fasta.size() != h.len[(size_t)tid]) fprintf(stderr, "reference and target not same size %zu\t%d\n", fasta.size(), h.len[(size_t)tid]);
-    cur_len = fasta.size();
-    if (!begin_contig(ctx[(size_t)g], tid, fasta, nullptr, &r)) { fprintf(stderr, "%s: %s\n", r.name.c_str(), r.err.c_str()); return; }
-    cur_ok = true;
-  };
-  size_t have = 0;          // bytes in buf[cb] not yet consumed
-  int cb = 0; bool eof = false, first = true, stop = false;
-  // the first chunk synchronously, then always one read ahead
-  have = fread(buf[cb], 1, CHUNK, f);
-  if (have < CHUNK) eof = true;
-  std::thread reader; size_t next_got = 0;
-  std::vector<rsigpu_bam_run> runs(4096);
-  const double t_loop = now_s();
-  while (have > 0 && !stop) {
-    const int nb = cb ^ 1;
-    if (!eof) reader = std::thread([&, nb]() { next_got = fread(buf[nb] + CARRY, 1, CHUNK, f); });
-    int64_t consumed = 0; int32_t nr = 0;
-    double t0 = now_s();
-    const int rc = rsigpu_bam_feed(dec, buf[cb], (int64_t)have, first ? skip : 0, &consumed, runs.data(), (int32_t)runs.size(), &nr);
-    t_feed += now_s() - t0;
-    if (rc) { fprintf(stderr, "%s\n", rsigpu_last_error(dec)); if (reader.joinable()) reader.join(); break; }
-    if (consumed) first = false;
-    t0 = now_s();
-    for (int i = 0; i < nr && i < (int)runs.size() && !stop; ++i) {
-      if (runs[(size_t)i].tid < 0) { stop = true; break; }           // unplaced reads come last in a sorted BAM
-      if (runs[(size_t)i].tid != cur) { finish_cur(); start(runs[(size_t)i].tid, runs[(size_t)i].n_reads); }
-      if (cur_ok && rsigpu_bam_take(dec, i, ctx[(size_t)gpu_of[(size_t)cur]])) {
-        fprintf(stderr, "%s: %s\n", results[(size_t)cur].name.c_str(), rsigpu_last_error(ctx[(size_t)gpu_of[(size_t)cur]])); cur_ok = false;
+  std::vector<DecodeTiming> tms((size_t)ng);
+  if (indexed) {
+    std::vector<std::thread> lanes;
+    for (int g = 0; g < ng; ++g)
+      lanes.emplace_back([&, g]() {
+        std::vector<int> tids;
+        for (int t = 0; t < n_ref; ++t) if (gpu_of[(size_t)t] == g) tids.push_back(t);
+        if (tids.empty()) return;
+        rsigpu_ctx* dec = nullptr;
+        if (rsigpu_create(g, &o.P, &dec)) { for (int t : tids) fail_contig(t, "cannot create the decoder context"); return; }
+        FastaPrefetch fp(o.reffile);
+        fp.request(h.name[(size_t)tids[0]]);
+        std::thread fin[2];
+        for (size_t k = 0; k < tids.size(); ++k) {
+          const int tid = tids[k]; const size_t slot = k % ctx[(size_t)g].size();
+          rsigpu_ctx* c = ctx[(size_t)g][slot];
+          double t0 = now_s();
+          if (fin[slot & 1].joinable()) fin[slot & 1].join();
+          tms[(size_t)g].wait += now_s() - t0;
+          ContigResult& r = results[(size_t)tid];
+          { std::lock_guard<std::mutex> lk(mu); fprintf(stderr, "#processing %s on GPU %d\n", r.name.c_str(), g); }
+          std::string fasta, e2;
+          const bool got = fp.take(r.name, &fasta, &e2);
+          if (k + 1 < tids.size()) fp.request(h.name[(size_t)tids[k + 1]]);
+          if (!got) { fail_contig(tid, e2); continue; }
+          if ((int)fasta.size() != h.len[(size_t)tid]) fprintf(stderr, "reference and target not same size %zu\t%d\n", fasta.size(), h.len[(size_t)tid]);
+          if (!begin_contig(c, tid, fasta, nullptr, &r)) { fail_contig(tid, r.err); continue; }
+          if (rsigpu_bam_begin(dec, (int32_t)n_ref)) { fail_contig(tid, rsigpu_last_error(dec)); continue; }
+          const uint64_t v = bai[(size_t)tid].first_voff;
+          bool take_err = false;
+          const int rc = stream_bam(o.bamfile, (long long)(v >> 16), (long long)(v & 0xffff), dec, CHUNK, [&](int i, const rsigpu_bam_run& run) {
+            if (run.tid != tid) return 1;                         // the next contig (or the unplaced reads) begins: done
+            if (rsigpu_bam_take(dec, i, c)) { take_err = true; return -1; }
+            return 0;
+          }, &tms[(size_t)g]);
+          if (rc || take_err) { fail_contig(tid, take_err ? std::string("bam_take: ") + rsigpu_last_error(c) : "BAM decoding failed"); continue; }
+          finish_async(&fin[slot & 1], c, tid, fasta.size());
+        }
+        for (auto& f : fin) if (f.joinable()) f.join();
+        rsigpu_destroy(dec);
+      });
+    for (auto& l : lanes) l.join();
+  } else {
+    rsigpu_ctx* dec = nullptr;
+    if (rsigpu_create(0, &o.P, &dec)) { fprintf(stderr, "cannot create the decoder context\n"); return 2; }
+    if (rsigpu_bam_begin(dec, (int32_t)n_ref)) { fprintf(stderr, "%s\n", rsigpu_last_error(dec)); return 2; }
+    std::vector<std::vector<std::thread>> fin((size_t)ng);
+    for (int g = 0; g < ng; ++g) fin[(size_t)g].resize(ctx[(size_t)g].size());
+    std::vector<size_t> next_slot((size_t)ng, 0);
+    FastaPrefetch fp(o.reffile);
+    int cur = -1; bool cur_ok = false; size_t cur_len = 0, cur_slot = 0;
+    auto finish_cur = [&]() {
+      if (cur >= 0 && cur_ok) { const int g = gpu_of[(size_t)cur]; finish_async(&fin[(size_t)g][cur_slot], ctx[(size_t)g][cur_slot], cur, cur_len); }
+      cur = -1; cur_ok = false;
+    };
+    auto start = [&](int tid) {
+      cur = tid; cur_ok = false;
+      if (gpu_of[(size_t)tid] < 0) return;
+      const int g = gpu_of[(size_t)tid];
+      cur_slot = next_slot[(size_t)g]++ % ctx[(size_t)g].size();
+      double t0 = now_s();
+      if (fin[(size_t)g][cur_slot].joinable()) fin[(size_t)g][cur_slot].join();
+      tms[0].wait += now_s() - t0;
+      ContigResult& r = results[(size_t)tid];
+      fprintf(stderr, "#processing %s on GPU %d\n", r.name.c_str(), g);
+      std::string fasta, e2;
+      const bool got = fp.take(r.name, &fasta, &e2);
+      for (int t = tid + 1; t < n_ref; ++t) if (gpu_of[(size_t)t] >= 0) { fp.request(h.name[(size_t)t]); break; }   // the next eligible contig, in header order
+      if (!got) { fail_contig(tid, e2); return; }
+      if ((int)fasta.size() != h.len[(size_t)tid]) fprintf(stderr, "reference and target not same size %zu\t%d\n", fasta.size(), h.len[(size_t)tid]);
+      cur_len = fasta.size();
+      if (!begin_contig(ctx[(size_t)g][cur_slot], tid, fasta, nullptr, &r)) { fail_contig(tid, r.err); return; }
+      cur_ok = true;
+    };
+    const int rc = stream_bam(o.bamfile, coff, skip, dec, CHUNK, [&](int i, const rsigpu_bam_run& run) {
+      if (run.tid < 0) return 1;                                 // unplaced reads come last in a sorted BAM
+      if (run.tid != cur) { finish_cur(); start(run.tid); }
+      if (cur_ok && rsigpu_bam_take(dec, i, ctx[(size_t)gpu_of[(size_t)cur]][cur_slot])) {
+        fail_contig(cur, std::string("bam_take: ") + rsigpu_last_error(ctx[(size_t)gpu_of[(size_t)cur]][cur_slot])); cur_ok = false;
       }
+      return 0;
+    }, &tms[0]);
+    if (rc) {   // the contig being decoded is incomplete: never turn partial depth into calls
+      if (cur >= 0 && cur_ok) fail_contig(cur, "BAM decoding failed inside this contig");
+      else failed++;
+      cur = -1; cur_ok = false;
     }
-    t_take += now_s() - t0;
-    const size_t rest = have - (size_t)consumed;
-    if (reader.joinable()) reader.join();
-    if (eof) {
-      if (consumed == 0) { if (rest) fprintf(stderr, "truncated BGZF block at the end of %s\n", o.bamfile.c_str()); break; }
-      memmove(buf[cb], buf[cb] + consumed, rest); have = rest;
-    } else {
-      if (rest > CARRY) { fprintf(stderr, "internal: carry buffer too small\n"); break; }
-      memcpy(buf[nb] + CARRY - rest, buf[cb] + consumed, rest);
-      // the next buffer's valid bytes start at CARRY - rest
-      if (next_got < CHUNK) eof = true;
-      have = rest + next_got;
-      if (CARRY - rest) memmove(buf[nb], buf[nb] + CARRY - rest, have);
-      cb = nb;
-    }
+    finish_cur();
+    for (auto& v : fin) for (auto& f : v) if (f.joinable()) f.join();
+    rsigpu_destroy(dec);
   }
-  finish_cur();
-  if (!stop && rsigpu_bam_end(dec)) fprintf(stderr, "%s\n", rsigpu_last_error(dec));
-  for (auto& w : workers) if (w.joinable()) w.join();
-  fclose(f);
-  for (int k = 0; k < 2; ++k) rsigpu_pinned_free(buf[k]);
-  rsigpu_destroy(dec);
-  if (timing) fprintf(stderr, "#timing: setup %.3f s, decode loop %.3f s (bam_feed %.3f, take+fasta+begin %.3f of which waiting for the GPU %.3f)\n", t_loop - t_start, now_s() - t_loop, t_feed, t_take, t_wait);
-  return 0;
+  if (timing) {
+    DecodeTiming t;
+    for (const DecodeTiming& x : tms) { t.feed += x.feed; t.take += x.take; t.wait += x.wait; t.read += x.read; }
+    fprintf(stderr, "#timing: %s decode, header+index %.3f s, decode loop %.3f s (first read %.3f, bam_feed %.3f, take %.3f, waiting for the GPU %.3f; summed over %d lanes)\n",
+            indexed ? "indexed per-GPU" : "sequential", 0.0, now_s() - t_start, t.read, t.feed, t.take, t.wait, indexed ? ng : 1);
+  }
+  return failed.load() ? 1 : 0;
 }
 
 void write_table(const Opt& o, const std::vector<ContigResult>& all) {
@@ -397,21 +548,32 @@ int main(int argc, char** argv) {
   const int ndev = rsigpu_num_devices();
   if (ndev <= 0) { fprintf(stderr, "no CUDA device: this implementation has no CPU path\n"); return 2; }
   const int ng = std::max(1, std::min(o.gpus, ndev));
-  std::vector<rsigpu_ctx*> ctx((size_t)ng, nullptr);
-  for (int g = 0; g < ng; ++g) if (rsigpu_create(g, &o.P, &ctx[(size_t)g])) { fprintf(stderr, "cannot create a context on GPU %d\n", g); return 2; }
+  // per GPU: two contig contexts for BAM input decoded on the GPU (one is decoded into while the other runs the hot path), else one
+  const int per_gpu = (!o.bamfile.empty() && !o.hostdecode) ? 2 : 1;
+  std::vector<std::vector<rsigpu_ctx*>> ctx((size_t)ng);
+  {
+    std::vector<std::thread> th; std::atomic<int> bad(0);
+    for (int g = 0; g < ng; ++g)
+      th.emplace_back([&, g]() {
+        for (int k = 0; k < per_gpu; ++k) { rsigpu_ctx* c = nullptr; if (rsigpu_create(g, &o.P, &c)) { bad++; return; } ctx[(size_t)g].push_back(c); }
+      });
+    for (auto& t : th) t.join();
+    if (bad.load()) { fprintf(stderr, "cannot create a context on every GPU\n"); return 2; }
+  }
   if (getenv("RSICNV_TIMING")) fprintf(stderr, "#timing: CUDA start-up + contexts %.3f s\n", now_s() - t_main);
   std::vector<ContigResult> results;
   std::string err;
+  int rc_all = 0;
   if (!o.rdfile.empty()) {   // depth-file input: one contig (rsi.cpp:2133-2136, 2192-2195)
     results.resize(1); results[0].name = o.chr;
     std::string fasta; std::vector<int32_t> rd;
     if (!read_fasta(o.reffile, o.chr, &fasta, &err) || !parse_depth_text(o.rdfile, (int)fasta.size(), &rd, &err)) { fprintf(stderr, "%s\n", err.c_str()); return 0; }
     fprintf(stderr, "#processing %s\n", o.chr.c_str());
-    results[0].done = run_contig(ctx[0], o, o.chr, 0, fasta, &rd, nullptr, &results[0]);
-    if (!results[0].done) fprintf(stderr, "%s\n", results[0].err.c_str());
+    results[0].done = run_contig(ctx[0][0], o, o.chr, 0, fasta, &rd, nullptr, &results[0]);
+    if (!results[0].done) { fprintf(stderr, "%s\n", results[0].err.c_str()); rc_all = 1; }
   } else if (!o.hostdecode) {
-    const int rc = bam_on_gpu(o, ctx, &results);
-    if (rc) return rc;
+    rc_all = bam_on_gpu(o, ctx, &results);
+    if (rc_all == 2) return 2;
   } else {
     BamReader br(o.threads);
     if (!br.open(o.bamfile, &err)) { fprintf(stderr, "%s\n", err.c_str()); return 0; }
@@ -423,20 +585,11 @@ int main(int argc, char** argv) {
     std::mutex mu;
     std::vector<std::thread> workers((size_t)ng);
     ContigReads cr;
-    // longest-processing-time assignment from the header lengths (1.038 imbalance for b37 on 8 GPUs)
-    std::vector<int> gpu_of(h.name.size(), 0);
-    {
-      std::vector<size_t> order;
-      for (size_t i = 0; i < h.name.size(); ++i)
-        if (h.name[i].find("MT") == std::string::npos && h.name[i].find(".") == std::string::npos && (o.chr == "1-22XY" || h.name[i] == o.chr)) order.push_back(i);
-      std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return h.len[a] > h.len[b]; });
-      std::vector<long long> load((size_t)ng, 0);
-      for (size_t i : order) { const int g = (int)(std::min_element(load.begin(), load.end()) - load.begin()); gpu_of[i] = g; load[(size_t)g] += h.len[i]; }
-    }
+    const std::vector<int> gpu_of = lpt_assign(o, h, ng, nullptr);
+    std::atomic<int> failed(0);
     while (br.next_contig(&cr, &err)) {
       const std::string& name = h.name[(size_t)cr.tid];
-      if (name.find("MT") != std::string::npos || name.find(".") != std::string::npos) continue;   // rsi.cpp:2119-2120
-      if (o.chr != "1-22XY" && name != o.chr) continue;
+      if (!eligible(o, name)) continue;                       // rsi.cpp:2119-2120, 2137-2143
       const int g = gpu_of[(size_t)cr.tid];
       if (workers[(size_t)g].joinable()) workers[(size_t)g].join();
       fprintf(stderr, "#processing %s (%zu reads) on GPU %d\n", name.c_str(), cr.n(), g);
@@ -449,18 +602,19 @@ int main(int argc, char** argv) {
         if (!read_fasta(o.reffile, r.name, &fasta, &e2)) r.err = e2;
         else {
           if ((int)fasta.size() != h.len[(size_t)tid]) fprintf(stderr, "reference and target not same size %zu\t%d\n", fasta.size(), h.len[(size_t)tid]);
-          r.done = run_contig(ctx[(size_t)g], o, r.name, tid, fasta, nullptr, mine, &r);
+          r.done = run_contig(ctx[(size_t)g][0], o, r.name, tid, fasta, nullptr, mine, &r);
         }
-        if (!r.done) { std::lock_guard<std::mutex> lk(mu); fprintf(stderr, "%s: %s\n", r.name.c_str(), r.err.c_str()); }
+        if (!r.done) { std::lock_guard<std::mutex> lk(mu); fprintf(stderr, "%s: %s\n", r.name.c_str(), r.err.c_str()); failed++; }
         delete mine;
       });
     }
     for (auto& w : workers) if (w.joinable()) w.join();
-    if (!err.empty()) fprintf(stderr, "%s\n", err.c_str());
+    if (!err.empty()) { fprintf(stderr, "%s\n", err.c_str()); failed++; }   // the reader stopped on a corrupt block: the contig it was in is not reported
+    if (failed.load()) rc_all = 1;
   }
   write_table(o, results);
   if (getenv("RSICNV_TIMING")) fprintf(stderr, "#timing: total %.3f s\n", now_s() - t_main);
   fprintf(stderr, "output written to %s\n", o.outfile.c_str());
-  for (rsigpu_ctx* c : ctx) rsigpu_destroy(c);
-  return 0;
+  for (auto& v : ctx) for (rsigpu_ctx* c : v) rsigpu_destroy(c);
+  return rc_all;
 }

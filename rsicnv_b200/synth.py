@@ -336,7 +336,7 @@ def _fill_var(buf, starts, lens, values):
     buf[idx] = values
 
 
-def _bam_records(R: dict, tid: int, lo: int, hi: int, random_seq, rich=None):
+def _bam_records(R: dict, tid: int, lo: int, hi: int, random_seq, rich=None, want_offsets: bool = False):
     """records lo..hi of one contig's reads as BAM bytes (bam1_core_t layout, bam.h:131-155).  rich=SEED: what real files
     carry and the path must skip -- read names of varying length, random bases, optional fields after the qualities."""
     nr = hi - lo
@@ -399,6 +399,8 @@ def _bam_records(R: dict, tid: int, lo: int, hi: int, random_seq, rich=None):
         has = np.flatnonzero(laux > 0)
         a0 = (soff + nseq + lq)[has]
         buf[a0] = ord("X"); buf[a0 + 1] = ord("A"); buf[a0 + 2] = ord("Z"); buf[a0 + laux[has] - 1] = 0
+    if want_offsets:
+        return buf.tobytes(), offs
     return buf.tobytes()
 
 
@@ -448,6 +450,46 @@ def write_bam(path: str, contigs: list[tuple[str, int]], reads_by_tid: dict[int,
         if carry:
             f.write(bgzf(carry))
         f.write(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
+
+
+def write_bam_aligned(path: str, name: str, L: int, reads: dict, level: int = 1, random_seq: int | None = None, threads: int = 8,
+                      block_size: int = 65280):
+    """One-contig BAM whose BGZF blocks END AT RECORD BOUNDARIES (valid BGZF/BAM: writers may flush anywhere), the header in
+    blocks of its own.  Any prefix of the record blocks is then itself a complete record stream, so the byte range
+    [rec_off, blk_end[k]) of this ONE image is the BAM of the contig truncated after record blk_rec_end[k] -- what bench.py's
+    whole-genome workload uses to present 24 per-chromosome files without compressing 24 images.
+    Returns dict(rec_off=file offset of the first record block, blk_end=int64[nblk] file offset after each record block,
+    blk_rec_end=int64[nblk] number of records in blocks 0..k)."""
+    import struct
+    import zlib
+    from concurrent.futures import ThreadPoolExecutor
+    text = "@HD\tVN:1.0\tSO:coordinate\n" + f"@SQ\tSN:{name}\tLN:{L}\n"
+    hdr = bytearray(b"BAM\x01") + struct.pack("<i", len(text)) + text.encode() + struct.pack("<i", 1)
+    hdr += struct.pack("<i", len(name) + 1) + name.encode() + b"\x00" + struct.pack("<i", L)
+
+    def bgzf(blk: bytes) -> bytes:
+        co = zlib.compressobj(level, zlib.DEFLATED, -15, 8, 0)
+        comp = co.compress(blk) + co.flush()
+        return (b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(comp) + 25) + comp +
+                struct.pack("<II", zlib.crc32(blk) & 0xffffffff, len(blk)))
+    nr = len(reads["pos"])
+    blk_end, blk_rec_end = [], []
+    with open(path, "wb") as f, ThreadPoolExecutor(threads) as pool:
+        f.write(bgzf(bytes(hdr)))
+        rec_off = foff = f.tell()
+        for lo in range(0, nr, 1 << 19):
+            hi = min(nr, lo + (1 << 19))
+            data, offs = _bam_records(reads, 0, lo, hi, random_seq, None, want_offsets=True)
+            cuts = [0]                       # indices into offs: greedy blocks of whole records
+            while cuts[-1] < hi - lo:
+                k = int(np.searchsorted(offs, offs[cuts[-1]] + block_size, side="right")) - 1
+                cuts.append(max(k, cuts[-1] + 1))
+            for a, b, out in zip(cuts[:-1], cuts[1:], pool.map(bgzf, (data[int(offs[a]):int(offs[b])] for a, b in zip(cuts[:-1], cuts[1:])))):
+                f.write(out)
+                foff += len(out)
+                blk_end.append(foff); blk_rec_end.append(lo + b)
+        f.write(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
+    return dict(rec_off=rec_off, blk_end=np.asarray(blk_end, np.int64), blk_rec_end=np.asarray(blk_rec_end, np.int64))
 
 
 def _reg2bin(beg, end):

@@ -257,7 +257,7 @@ class Lib:
         nc = C.c_int(0); stats = np.zeros(2); out = self._list()
         res = {}
         if self.kind == "oracle":
-            nbmax = len(depth) + 1
+            nbmax = len(depth) // 3 + 8      # bins of at least 3 bases (m is odd, >= 3)
             bm = np.zeros(nbmax, np.float32) if want_bins else None
             bn = np.zeros(nbmax, np.float32) if want_bins else None
             bi = np.zeros(nbmax, np.int32) if want_bins else None

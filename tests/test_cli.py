@@ -166,6 +166,62 @@ def test_cli_six_contigs_streamed(cli, tmp_path):
     assert len({ln.split("\t")[0] for ln in ref if not ln.startswith("#")}) >= 4
 
 
+@pytest.mark.gpu
+def test_cli_explicit_contig_and_decode_paths(cli, tmp_path):
+    """-c with a name the default list would skip ("MT", a name with a dot) is processed like any other (rsi.cpp:2137-2143 resets
+    the list to the named target); the default run skips both (rsi.cpp:2119-2120).  Every decode route gives the same table:
+    per-GPU decoders started from the .bai offsets (default), one sequential pass without the index, host zlib."""
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    lens = [10_350_000, 10_450_000, 10_550_000]
+    names = ["1", "MT", "GL000207.1"]
+    fas = [synth.make_fasta(L, 60 + i) for i, L in enumerate(lens)]
+    reads = {i: synth.make_reads(L, 60 + i, fas[i], coverage=8, n_events=4, lens=(4000, 9000, 20000), tid=i)[0] for i, L in enumerate(lens)}
+    bam = str(tmp_path / "t.bam"); fasta = str(tmp_path / "t.fa")
+    synth.write_bam(bam, list(zip(names, lens)), reads, level=1, rich=29, unmapped_tail=20)
+    synth.write_fasta_multi(fasta, list(zip(names, fas)))
+    subprocess.run([REF_BAMTOOL, "index", bam], check=True)
+    for k, sel in enumerate((["-c", "MT"], ["-c", "GL000207.1"], [])):
+        common = ["rsi", "-b", bam, "-f", fasta, "-q", "0", "-Q", "10", "-np"] + sel
+        subprocess.run([REF_BIN] + common + ["-o", str(tmp_path / f"ref{k}.txt")], check=True, capture_output=True)
+        ref = _table(str(tmp_path / f"ref{k}.txt"))
+        for extra, env in (([], {}), ([], {"RSICNV_NO_INDEX": "1"}), (["-hostdecode"], {}), (["-gpus", "2"], {})):
+            out = subprocess.run([cli] + common + extra + ["-o", str(tmp_path / "ours.txt")], capture_output=True, text=True, env=dict(os.environ, **env))
+            assert out.returncode == 0, out.stderr
+            assert _table(str(tmp_path / "ours.txt")) == ref, (sel, extra, env, out.stderr)
+        chroms = {ln.split("\t")[0] for ln in ref if not ln.startswith("#")}
+        assert chroms == ({"MT"}, {"GL000207.1"}, {"1"})[k], chroms
+
+
+@pytest.mark.gpu
+def test_cli_corrupt_bam_is_an_error_not_a_table(cli, tmp_path):
+    """a deflate stream damaged in the middle of the second contig: the first contig's rows are written, the damaged contig's are NOT
+    (no calls from partial depth) and the exit status is non-zero -- on every decode route"""
+    lens = [10_300_000, 10_400_000]
+    fas = [synth.make_fasta(L, 70 + i) for i, L in enumerate(lens)]
+    reads = {i: synth.make_reads(L, 70 + i, fas[i], coverage=8, n_events=4, lens=(4000, 9000, 20000), tid=i)[0] for i, L in enumerate(lens)}
+    bam = str(tmp_path / "t.bam"); fasta = str(tmp_path / "t.fa")
+    synth.write_bam(bam, [("1", lens[0]), ("2", lens[1])], reads, level=1, random_seq=5)
+    synth.write_fasta_multi(fasta, [("1", fas[0]), ("2", fas[1])])
+    if have_ref():
+        subprocess.run([REF_BAMTOOL, "index", bam], check=True)
+    good = subprocess.run([cli, "rsi", "-b", bam, "-f", fasta, "-q", "0", "-Q", "10", "-np", "-o", str(tmp_path / "good.txt")], capture_output=True, text=True)
+    assert good.returncode == 0, good.stderr
+    rows = [ln for ln in _table(str(tmp_path / "good.txt")) if not ln.startswith("#")]
+    assert {ln.split("\t")[0] for ln in rows} == {"1", "2"}
+    data = bytearray(open(bam, "rb").read())
+    at = int(len(data) * 0.8)                    # well inside contig 2
+    for k in range(64):
+        data[at + k] ^= 0x5a
+    open(bam, "wb").write(bytes(data))
+    for extra, env in (([], {}), ([], {"RSICNV_NO_INDEX": "1"}), (["-hostdecode"], {})):
+        out = subprocess.run([cli, "rsi", "-b", bam, "-f", fasta, "-q", "0", "-Q", "10", "-np", "-o", str(tmp_path / "bad.txt")] + extra,
+                             capture_output=True, text=True, env=dict(os.environ, **env))
+        assert out.returncode != 0, (extra, env, out.stderr)
+        bad = [ln for ln in _table(str(tmp_path / "bad.txt")) if not ln.startswith("#")]
+        assert bad == [ln for ln in rows if ln.split("\t")[0] == "1"], (extra, env, out.stderr)
+
+
 def test_header_reader_agrees_with_the_python_one(cli, tmp_path):
     """read_bam_header (what the CLI hands to the GPU decoder) vs api.parse_bam_header: ordinary file, header ending exactly at a
     block boundary, header spanning many blocks"""
