@@ -721,6 +721,7 @@ struct BinDump { std::vector<float> med, nbn; std::vector<int> medint, status; }
 std::vector<ocl_cnv> g_lists[4];
 void detectcnv(const int* RD, int n, std::vector<ocl_cnv>& out, BinDump* dump) {
   out.clear();
+  for (auto& l : g_lists) l.clear();
   if (G.RDmedian < 5) return;
   const int m = G.m;
   std::vector<float> med, nbn;
@@ -734,7 +735,6 @@ void detectcnv(const int* RD, int n, std::vector<ocl_cnv>& out, BinDump* dump) {
   G.Lmax = std::max(10000 / m, 20);
   std::vector<int> st_med(nb, 0), st_nbn(nb, 0);
   std::vector<ocl_cnv> segs;
-  for (auto& l : g_lists) l.clear();
   if (G.trans != 0) { rsicnv(1, med.data(), medint.data(), nb, st_med.data(), segs); g_lists[0] = segs; areblockscnv(medint.data(), st_med.data(), nb, segs); }
   if (G.trans == 0) { rsicnv(0, nbn.data(), medint.data(), nb, st_nbn.data(), segs); g_lists[0] = segs; areblockscnv(medint.data(), st_nbn.data(), nb, segs); }
   if (G.trans == 2) {

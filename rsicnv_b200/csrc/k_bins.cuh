@@ -16,8 +16,10 @@
 
 namespace rsigpu {
 
-enum { C_NT = 512, C_NW = C_NT / 32, C_K = 128, C_KP = C_K + 2 /* padded row: 65 words, lanes of a step hit 31 different banks */, C_TP = 8192 /* max staged bases */ };
-#define RSI_SMEM_C ((size_t)C_NW * MAD_CLASSES * C_KP * 2 + (size_t)C_TP * 4)
+enum { C_NT = 256, C_NW = C_NT / 32, C_K = 128, C_KP = C_K + 2 /* padded row: 65 words, lanes of a step hit 31 different banks */,
+       C_TP = 8192 /* largest bin size */, C_CAP = 13312 /* words of one staged tile (52 KB) */, C_BINS = 128 /* bins per tile at most */ };
+// dynamic shared memory: 2 staged tiles | ct[C_NW][MAD_CLASSES][C_KP] u16
+#define RSI_SMEM_C (2 * ((size_t)C_CAP * 4 + 16) + (size_t)C_NW * MAD_CLASSES * C_KP * 2)
 
 __device__ __forceinline__ i64 warp_sum_i64(i64 v) {
 #pragma unroll
@@ -25,14 +27,42 @@ __device__ __forceinline__ i64 warp_sum_i64(i64 v) {
   return v;
 }
 
+// tile `t` of pass C: bins [b0, b0 + nbt) and their bases [B, B + np); the pseudo-tile after the last bin tile owns the
+// < m bases beyond nb*m (they count for the chromosome statistics only)
+struct CTile { int b0, nbt, B, np; };
+__device__ __forceinline__ CTile c_tile(int t, int nbin_tiles, int bpt, int nb, int m, int Lc) {
+  CTile T;
+  if (t < nbin_tiles) { T.b0 = t * bpt; T.nbt = imin(bpt, nb - T.b0); T.B = T.b0 * m; T.np = T.nbt * m; }
+  else { T.b0 = nb; T.nbt = 0; T.B = nb * m; T.np = Lc - nb * m; }
+  return T;
+}
+// one thread: bulk copy of the tile's words, from the 16-byte aligned address at or below its first base
+__device__ __forceinline__ void c_issue(int* dst, u64* bar, const int* __restrict__ rdc, const CTile& T) {
+  const int skew = T.B & 3;
+  const u32 bytes = (u32)(((T.np + skew) * 4 + 15) & ~15);
+  fence_proxy_async();
+  mbar_expect_tx(bar, bytes);
+  bulk_g2s(dst, rdc + (T.B - skew), bytes, bar);
+}
+
 // chist[c * R + v]: #bases of class c (compacted index mod 31, index < 31*floor(Lc/31)) with capped
-// value v; thist[v]: the < 31 bases beyond.  bins_per_tile * m <= C_TP.
+// value v; thist[v]: the < 31 bases beyond.  (bins_per_tile + 1) * m <= C_CAP - 4.
+// One pass over the compacted depth (4 B/base).  Tiles of whole bins arrive by bulk copy into a two-stage ring.  Per tile:
+//   phase 1 (all warps): cap clamp + the 31 strided class histograms -- a warp counts 31 CONSECUTIVE bases per step, which
+//           fall into 31 different classes, so the plain read-modify-writes of its lanes never collide; the class of a
+//           lane is fixed for the whole tile (steps advance by multiples of 31);
+//   phase 2: bin medians and sums.  m <= 127: a PAIR of lanes owns a bin, each lane keeps its half of the values in
+//           registers as bytes relative to the value window (4 per register) and counts "value <= probe" for 4 values with
+//           one subtract (no lane ever waits for another: one shuffle per probe joins the two halves).  Larger m, or a bin
+//           with a value outside the window: one warp per bin with ballots.
 __global__ void __launch_bounds__(C_NT) k_bins(int* __restrict__ rdc, float* __restrict__ bin_med, int* __restrict__ bin_medint,
                                                 i64* __restrict__ bin_sum, u32* chist, u32* thist, DevState* st, int bins_per_tile) {
   RSI_DYN_SMEM(smem);
   RSI_CTA_SETUP(c);
-  u16* ct = reinterpret_cast<u16*>(smem);                  // [C_NW][MAD_CLASSES][C_KP]
-  int* vals = reinterpret_cast<int*>(smem + (size_t)C_NW * MAD_CLASSES * C_KP * 2);
+  __shared__ __align__(8) u64 s_bar[2];
+  __shared__ int s_slow[C_BINS + 1];
+  int* stage[2] = {reinterpret_cast<int*>(smem), reinterpret_cast<int*>(smem + (size_t)C_CAP * 4 + 16)};
+  u16* ct = reinterpret_cast<u16*>(smem + 2 * ((size_t)C_CAP * 4 + 16));   // [C_NW][MAD_CLASSES][C_KP]
   const int tid = c.tid, lane = tid & 31, warp = tid >> 5;
   const int Lc = st->Lc, m = st->m, nb = st->nb, R = st->chist_R, cap_on = st->cap_on, capv = st->capv;
   const double thr = st->cap_thr;
@@ -43,81 +73,117 @@ __global__ void __launch_bounds__(C_NT) k_bins(int* __restrict__ rdc, float* __r
   u16* wt = ct + (size_t)warp * MAD_CLASSES * C_KP;
   const int ithr = thr >= 2147483647.0 ? 0x7fffffff : (int)floor(thr);   // integer v: (double)v > thr  <=>  v > floor(thr)
   i64 mx = 0;
-  const int ntiles = nb > 0 ? (nb + bins_per_tile - 1) / bins_per_tile : 1;
-  for (int tile = (int)blockIdx.x; tile < ntiles; tile += (int)gridDim.x) {
-    const int b0 = tile * bins_per_tile, nbt = imin(bins_per_tile, nb - b0);
-    const int B = b0 * m;
-    const int np = (tile == ntiles - 1) ? Lc - B : nbt * m;   // the last tile also owns the tail beyond nb*m
-    c.sync();
-    for (int q0 = 0; q0 < np; q0 += C_TP) {                    // (only the tail of a tiny contig can exceed C_TP)
-      const int nq = imin(C_TP, np - q0);
-      if (q0) c.sync();
-      for (int qb = 0; qb < nq; qb += C_NT * 4) {   // 4 independent loads in flight per thread before any (aliasing) store
-        int v[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { const int q = qb + k * C_NT + tid; v[k] = q < nq ? rdc[B + q0 + q] : 0; }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int q = qb + k * C_NT + tid;
-          if (q >= nq) continue;
-          if (cap_on && v[k] > ithr) { v[k] = capv; rdc[B + q0 + q] = capv; }
-          vals[q] = v[k];
-        }
-      }
-      c.sync();
-      {
-        const int Bq = B + q0;
-        // warp-steps of 31 consecutive bases: 31 distinct classes, lane 31 idles
-        for (int s0 = warp * 31; s0 < nq; s0 += C_NW * 31) {
-          const int q = s0 + lane;
-          if (lane < 31 && q < nq) {
-            const int v = vals[q], w = v - wb, cls = (Bq + q) % MAD_CLASSES;
-            if (Bq + q >= sub31) { if (v >= 0 && v < R) atomicAdd(&thist[v], 1u); }
-            else if ((unsigned)w < (unsigned)C_K) wt[cls * C_KP + w] += 1;
-            else if (v >= 0 && v < R) atomicAdd(&chist[cls * R + v], 1u);
-          }
-          __syncwarp();
-        }
-      }
-      if (q0 == 0) {
-        for (int b = warp; b < nbt; b += C_NW) {
-          const int* x = vals + b * m;
-          const int need = (m - 1) / 2 + 1;                    // smallest v with #{x <= v} >= need (m is odd)
-          if (m <= 128) {   // the bin lives in 4 registers per lane; one full-mask REDUX per probe
-            int r[4]; int lo = 0x7fffffff, hi = -0x7fffffff - 1, s32 = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { const int j = lane + 32 * k; r[k] = j < m ? x[j] : 0x7fffffff; if (j < m) { lo = imin(lo, r[k]); hi = imax(hi, r[k]); s32 += r[k]; } }
-            lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
-            const i64 s = (i64)__reduce_add_sync(0xffffffffu, (unsigned)s32);     // < 128 * 2^24
-            while (lo < hi) {
-              const int mid = lo + ((hi - lo) >> 1);
-              const int cnt = __reduce_add_sync(0xffffffffu, (r[0] <= mid) + (r[1] <= mid) + (r[2] <= mid) + (r[3] <= mid));
-              if (cnt >= need) hi = mid; else lo = mid + 1;
-            }
-            if (lane == 0) { bin_med[b0 + b] = (float)lo; bin_medint[b0 + b] = lo; bin_sum[b0 + b] = s; mx = lmax(mx, s); }
-            continue;
-          }
-          int lo = 0x7fffffff, hi = -0x7fffffff - 1; i64 s = 0;
-          for (int j = lane; j < m; j += 32) { const int v = x[j]; lo = imin(lo, v); hi = imax(hi, v); s += v; }
-          lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
-          s = warp_sum_i64(s);
-          while (lo < hi) {
-            const int mid = lo + ((hi - lo) >> 1);
-            int cnt = 0;
-            for (int j0 = 0; j0 < m; j0 += 32) { const int j = j0 + lane; cnt += __popc(__ballot_sync(0xffffffffu, j < m && x[j] <= mid)); }
-            if (cnt >= need) hi = mid; else lo = mid + 1;
-          }
-          if (lane == 0) { bin_med[b0 + b] = (float)lo; bin_medint[b0 + b] = lo; bin_sum[b0 + b] = s; mx = lmax(mx, s); }
+  const int bpt = bins_per_tile;
+  const int nbin_tiles = nb > 0 ? (nb + bpt - 1) / bpt : 0;
+  const int ntiles = nbin_tiles + (Lc - nb * m > 0 ? 1 : 0);
+  if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
+  c.sync();
+  if (tid == 0)
+    for (int s = 0; s < 2; ++s) { const int t = (int)blockIdx.x + s * (int)gridDim.x; if (t < ntiles) c_issue(stage[s], &s_bar[s], rdc, c_tile(t, nbin_tiles, bpt, nb, m, Lc)); }
+  const int need = (m - 1) / 2 + 1;                    // median = smallest v with #{x <= v} >= need (m is odd)
+  int it = 0;
+  for (int tile = (int)blockIdx.x; tile < ntiles; tile += (int)gridDim.x, ++it) {
+    const int s = it & 1;
+    const CTile T = c_tile(tile, nbin_tiles, bpt, nb, m, Lc);
+    mbar_wait(&s_bar[s], (u32)(it >> 1) & 1u);
+#ifdef RSI_SIM_DEBUG
+    if (tid == 0 || tid == 255) fprintf(stderr, "k_bins blk %d tid %d tile %d it %d nbt %d np %d m %d\n", (int)blockIdx.x, tid, tile, it, T.nbt, T.np, m);
+#endif
+    int* vals = stage[s] + (T.B & 3);
+    if (tid <= C_BINS) s_slow[tid] = 0;
+    // ---- phase 1: clamp + class histograms
+    {
+      const int cls0 = T.B % MAD_CLASSES;
+      int cls = cls0 + lane; if (cls >= MAD_CLASSES) cls -= MAD_CLASSES;       // class of this lane's bases in every step of this tile
+      u16* row = wt + cls * C_KP;
+      u32* grow = chist + (size_t)cls * R;
+      // no two lanes of a warp ever share a row, whatever their relative progress: no warp barrier in the loop
+      for (int q = warp * 31 + lane; q < T.np; q += C_NW * 31) {
+        if (lane < 31) {
+          int v = vals[q];
+          if (cap_on && v > ithr) { v = capv; vals[q] = capv; rdc[T.B + q] = capv; }
+          const unsigned w = (unsigned)(v - wb);
+          if (T.B + q >= sub31) { if (v >= 0 && v < R) atomicAdd(&thist[v], 1u); }
+          else if (w < (unsigned)C_K) row[w] += 1;
+          else if (v >= 0 && v < R) atomicAdd(&grow[v], 1u);
         }
       }
     }
+    c.sync();
+    // ---- phase 2: medians and sums
+    if (m <= 127) {
+      const int nreg = (m + 7) / 8;                   // packed registers per lane: ceil(ceil(m/2) / 4)
+      for (int bb = 0; bb < T.nbt; bb += C_NT / 2) {
+        const int b = bb + (tid >> 1), par = tid & 1;
+        const bool act = b < T.nbt;
+        const int* x = vals + (act ? b : 0) * m;
+        u32 pk[16];
+        int s32 = 0; u32 out = 0;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          u32 w4 = 0;
+          if (r < nreg) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int j = 2 * (r * 4 + k) + par;
+              u32 u = 0x7fu;                            // padding: never <= a probe below 127, and a real 127 makes the bin take the slow path
+              if (act && j < m) { const int v = x[j]; s32 += v; const unsigned d = (unsigned)(v - wb); out |= d; u = d & 0x7fu; }
+              w4 |= u << (8 * k);
+            }
+          }
+          pk[r] = w4;
+        }
+        // values of the bin must lie in [wb, wb + 126]
+        const bool slow = (out >= 127u);
+        const i64 sum = (i64)s32 + (i64)__shfl_xor_sync(0xffffffffu, s32, 1);      // < 127 * 2^24
+        const int oslow = __shfl_xor_sync(0xffffffffu, (int)slow, 1);               // (no short-circuit around a warp collective)
+        const bool pslow = slow || oslow != 0;
+        int lo = 0, hi = 126;
+#pragma unroll 1
+        for (int itb = 0; itb < 7; ++itb) {          // every lane runs the 7 probes (idle pairs on padding): the shuffles stay converged
+          const int mid = (lo + hi) >> 1;
+          const u32 probe = 0x80808080u | ((u32)mid * 0x01010101u);
+          u32 acc = 0;
+#pragma unroll
+          for (int r = 0; r < 16; ++r) if (r < nreg) acc += ((probe - pk[r]) >> 7) & 0x01010101u;    // per byte: 1 iff value <= mid
+          int cnt = (int)((acc * 0x01010101u) >> 24);
+          cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
+          if (cnt >= need) hi = mid; else lo = mid + 1;
+        }
+        if (act && par == 0) {
+          if (pslow) s_slow[b] = 1;
+          else { const int med = wb + lo; bin_med[T.b0 + b] = (float)med; bin_medint[T.b0 + b] = med; bin_sum[T.b0 + b] = sum; mx = lmax(mx, sum); }
+        }
+      }
+      c.sync();
+    } else if (tid == 0) { for (int b = 0; b < T.nbt; ++b) s_slow[b] = 1; }
+    if (m > 127) c.sync();
+    // bins left for the warp-per-bin path (large m, or a value outside the window)
+    for (int b = warp; b < T.nbt; b += C_NW) {
+      if (!s_slow[b]) continue;
+      const int* x = vals + b * m;
+      int lo = 0x7fffffff, hi = -0x7fffffff - 1; i64 sm = 0;
+      for (int j = lane; j < m; j += 32) { const int v = x[j]; lo = imin(lo, v); hi = imax(hi, v); sm += v; }
+      lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
+      sm = warp_sum_i64(sm);
+      while (lo < hi) {
+        const int mid = lo + ((hi - lo) >> 1);
+        int cnt = 0;
+        for (int j0 = 0; j0 < m; j0 += 32) { const int j = j0 + lane; cnt += __popc(__ballot_sync(0xffffffffu, j < m && x[j] <= mid)); }
+        if (cnt >= need) hi = mid; else lo = mid + 1;
+      }
+      if (lane == 0) { bin_med[T.b0 + b] = (float)lo; bin_medint[T.b0 + b] = lo; bin_sum[T.b0 + b] = sm; mx = lmax(mx, sm); }
+    }
+    c.sync();                                          // everybody is done with stage s
+    const int t2 = tile + 2 * (int)gridDim.x;
+    if (tid == 0 && t2 < ntiles) c_issue(stage[s], &s_bar[s], rdc, c_tile(t2, nbin_tiles, bpt, nb, m, Lc));
   }
   c.sync();
   for (int item = tid; item < MAD_CLASSES * C_K; item += C_NT) {
     const int cl = item / C_K, w = item % C_K;
-    u32 s = 0;
-    for (int k = 0; k < C_NW; ++k) s += ct[((size_t)k * MAD_CLASSES + cl) * C_KP + w];
-    if (s && wb + w < R) atomicAdd(&chist[cl * R + wb + w], s);
+    u32 sum = 0;
+    for (int k = 0; k < C_NW; ++k) sum += ct[((size_t)k * MAD_CLASSES + cl) * C_KP + w];
+    if (sum && wb + w < R) atomicAdd(&chist[cl * R + wb + w], sum);
   }
   mx = c.reduce(mx, MaxOp());
   if (tid == 0 && mx > 0) atomicMax(reinterpret_cast<u64*>(&st->max_binsum), (u64)mx);

@@ -88,7 +88,7 @@ struct rsigpu_ctx {
   cudaEvent_t ev_reads = nullptr, ev_isize = nullptr;
   bool isize_pending = false;
   std::string err;
-  int L = 0, Lc = 0, nb = 0, tid = 0;
+  int L = 0, Lc = 0, nb = 0, tid = 0, gc_base = 0;
   bool have_ref = false, have_depth = false, have_reads = false, loaded = false, detected = false, filtered = false;
   bool pileup_fresh = false;   // rsigpu_pileup_end has just produced the depth of the staged reads: the next rsigpu_run does not redo it
   int cand_a_threads = 256;
@@ -369,16 +369,16 @@ int rsigpu_set_reference(rsigpu_ctx* c, const uint8_t* fasta, int32_t len, int32
   cudaSetDevice(c->device);
   c->L = len; c->tid = tid;
   c->have_ref = true; c->have_depth = false; c->have_reads = false; c->loaded = false; c->detected = false; c->filtered = false;
-  const size_t padded = ((size_t)len + 15) / 16 * 16 + 512;
+  const size_t padded = ((size_t)len + 15) / 16 * 16 + LD_T + 512;   // a whole tile beyond the last base is staged by the bulk copies
   CK(c->d_fasta.ensure(padded));
   CK(cudaMemsetAsync(c->d_fasta.p + len, 0, padded - (size_t)len, c->stream));
   CK(cudaMemcpyAsync(c->d_fasta.p, fasta, (size_t)len, cudaMemcpyHostToDevice, c->stream));
-  int* n2 = c->d_misc.p + 8;
-  CK(cudaMemsetAsync(n2, 0, 8, c->stream));
+  int* n2 = c->d_misc.p + 8;     // n_begN | n_endN | (u64) number of G/C bases
+  CK(cudaMemsetAsync(n2, 0, 16, c->stream));
   const int cap = 1 << 20;
-  KL(k_n_runs, grid_for(len, 256 * 16, c->n_sm * 8), 256, 0, c->d_fasta.p, len, c->d_nrun_beg.p, c->d_nrun_end.p, n2, n2 + 1, cap);
-  int hn[2];
-  CK(cudaMemcpyAsync(hn, n2, 8, cudaMemcpyDeviceToHost, c->stream));
+  KL(k_n_runs, grid_for(len, 256 * 16, c->n_sm * 8), 256, 0, c->d_fasta.p, len, c->d_nrun_beg.p, c->d_nrun_end.p, n2, n2 + 1, cap, reinterpret_cast<u64*>(n2 + 2));
+  int hn[4];
+  CK(cudaMemcpyAsync(hn, n2, 16, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   if (hn[0] != hn[1] || hn[0] > cap) { c->fail("more than 2^20 N runs"); return RSIGPU_E_RANGE; }
   std::vector<int> b(hn[0]), e(hn[0]);
@@ -404,6 +404,13 @@ int rsigpu_set_reference(rsigpu_ctx* c, const uint8_t* fasta, int32_t len, int32
   CK(cudaMemcpyAsync(c->d_nseq.p, pack.data(), (3 * (size_t)nn + 4) * 4, cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   c->Lc = len - removed;
+  {   // mean G/C count of a 201-base window of sequence: centre of the strata pass A keeps in its private tables
+    u64 ngc; memcpy(&ngc, hn + 2, 8);
+    long long nseq = 0; for (int k = 0; k < hn[0]; ++k) nseq += e[k] - b[k] + 1;
+    nseq = (long long)len - nseq;
+    const int centre = nseq > 0 ? (int)((double)GC_WIN * (double)ngc / (double)nseq + 0.5) : GC_WIN / 2;
+    c->gc_base = std::max(0, std::min(centre - LD_ROWS / 2, (int)GC_STRATA - LD_ROWS));
+  }
   c->nb = c->Lc / c->P.m;
   if (c->nb < 64) { c->fail("fewer than 64 bins after N removal"); return RSIGPU_E_RANGE; }
   return RSIGPU_OK;
@@ -709,6 +716,7 @@ int rsigpu_load_finish(rsigpu_ctx* c) {
   DevState* h = c->h_st;
   memset(h, 0, sizeof(DevState));
   h->L = L; h->Lc = c->Lc; h->nb = nb; h->m = m; h->n_noseq = nn; h->gc_on = c->P.gcadjust ? 1 : 0; h->cap_on = c->P.cap > 1 ? 1 : 0;
+  h->gc_base = c->gc_base;
   h->trans = c->P.trans; h->cap = c->P.cap; h->rd_min = 0x7fffffff; h->rd_max = -0x7fffffff - 1;
   h->nb_tmin_ord = 0xffffffffu;
   h->factor = sqrt(2.0 * (1.0 + c->P.epsilon) * log(3.1E9));   // rsi.cpp:1829
@@ -723,12 +731,12 @@ int rsigpu_load_finish(rsigpu_ctx* c) {
   const int* nbeg = c->d_nseq.p; const int* nend = nbeg + nn; const int* ncum = nbeg + 2 * nn;
   const int ntiles = (L + LD_TILE - 1) / LD_TILE;
   const size_t smA = RSI_SMEM_A, smB = RSI_SMEM_B;
-  KL(k_gc_table, std::min(ntiles, c->n_sm * 2), A_NT, smA, c->d_raw.p, c->d_fasta.p, c->d_st);
+  KL(k_gc_table, std::min(ntiles, c->n_sm), LD_NT, smA, c->d_raw.p, c->d_fasta.p, c->d_st);
   KL(k_gc_finalize, 1, 256, 0, c->d_fasta.p, c->d_st);
-  KL(k_gc_adjust, std::min(ntiles, c->n_sm * 2), B_NT, smB, c->d_raw.p, c->d_fasta.p, c->d_rdc.p, nbeg, nend, ncum, c->d_hist_all.p, c->d_st);
+  KL(k_gc_adjust, std::min(ntiles, c->n_sm), LD_NT, smB, c->d_raw.p, c->d_fasta.p, c->d_rdc.p, nbeg, nend, ncum, c->d_hist_all.p, c->d_st);
   KL(k_cap_params, 1, 1024, 0, c->d_hist_all.p, c->d_st, CHIST_RCAP);
-  const int bpt = std::max(1, std::min(64, C_TP / m));
-  const int ntc = std::max(1, (nb + bpt - 1) / bpt);
+  const int bpt = std::max(1, std::min((int)C_BINS, (C_CAP - 4) / m));     // bpt * m + 3 words fit a stage
+  const int ntc = std::max(1, (nb + bpt - 1) / bpt + 1);
   KL(k_bins, std::min(ntc, c->n_sm), C_NT, RSI_SMEM_C, c->d_rdc.p, c->d_bin_med.p, c->d_bin_medint.p, c->d_bin_sum.p, c->d_chist.p,
      c->d_thist.p, c->d_st, bpt);
   KL(k_chr_stats, 1, 1024, 0, c->d_chist.p, c->d_thist.p, c->d_tothist.p, c->d_st);

@@ -54,6 +54,7 @@ struct DevState {
   u64 gc_sum[GC_STRATA], gc_cnt[GC_STRATA];
   double gc_tab[GC_STRATA];
   int gstar;                   // #GC in [L-201, L-1]: the recount at the 21st pseudo-slice
+  int gc_base, pad_gc_;        // first stratum of pass A's private per-warp tables (set by the host from the contig's GC fraction)
   int s20, r20;                // 20*floor(L/20), L - 20*floor(L/20)
   // ---- cap (apply_cap, loaddata.cpp:229-240)
   double cap_median, cap_thr;

@@ -208,7 +208,7 @@ bool read_bai(const std::string& bam_path, size_t n_ref, std::vector<BaiRef>* ou
   for (uint32_t r = 0; r < nref; ++r) {
     uint32_t nbin = 0;
     if (!u32(&nbin)) return false;
-    uint64_t first = ~0ull;
+    uint64_t first = ~0ull, last = 0;
     for (uint32_t b = 0; b < nbin; ++b) {
       uint32_t bin = 0, nchunk = 0;
       if (!u32(&bin) || !u32(&nchunk)) return false;
@@ -216,13 +216,14 @@ bool read_bai(const std::string& bam_path, size_t n_ref, std::vector<BaiRef>* ou
         uint64_t beg = 0, end = 0;
         if (!u64(&beg) || !u64(&end)) return false;
         if (bin != 37450 && beg < first) first = beg;
+        if (bin == 37450 && k == 0) last = end;          // (ref_beg, ref_end) of the pseudo-bin
       }
     }
     uint32_t nintv = 0;
     if (!u32(&nintv)) return false;
     if (p + 8 * (size_t)nintv > d.size()) return false;
     p += 8 * (size_t)nintv;
-    if (first != ~0ull) { (*out)[r].has_reads = true; (*out)[r].first_voff = first; }
+    if (first != ~0ull) { (*out)[r].has_reads = true; (*out)[r].first_voff = first; (*out)[r].end_voff = last >= first ? last : 0; }
   }
   return true;
 }

@@ -65,7 +65,7 @@ bool read_bam_header(const std::string& path, BamHeader* hdr, long long* rec_cof
 // chromosome-sharded GPU path needs: for every reference sequence whether it has records (the reference's "populated" test,
 // rsi.cpp:2121-2126) and the virtual file offset (BGZF block offset << 16 | offset inside the decoded block) of its first
 // record, so that every GPU can start decoding ITS contigs in the middle of the file.  false if the file is absent or malformed.
-struct BaiRef { bool has_reads = false; uint64_t first_voff = 0; };
+struct BaiRef { bool has_reads = false; uint64_t first_voff = 0, end_voff = 0; };   // end_voff: where the last record ends (samtools' pseudo-bin), 0 = unknown
 bool read_bai(const std::string& bam_path, size_t n_ref, std::vector<BaiRef>* out);
 
 }  // namespace rsihost

@@ -286,12 +286,20 @@ struct DecodeTiming { double feed = 0, take = 0, wait = 0, read = 0; };
 // called for every run of records with one refID, in file order: 0 = go on, 1 = stop (the caller has what it wanted),
 // < 0 = error.  Returns 0 (end of file or stopped), 1 on any error (message on stderr): the caller must NOT use the partial data.
 template <class F>
-int stream_bam(const std::string& path, long long coff, long long skip, rsigpu_ctx* dec, size_t chunk_bytes, F&& on_run, DecodeTiming* tm) {
+int stream_bam(const std::string& path, long long coff, long long skip, long long end_off, rsigpu_ctx* dec, size_t chunk_bytes, F&& on_run, DecodeTiming* tm) {
   const int fd = open(path.c_str(), O_RDONLY);
   if (fd < 0) { fprintf(stderr, "cannot open %s\n", path.c_str()); return 1; }
   struct stat sb;
   if (fstat(fd, &sb) != 0 || (long long)sb.st_size < coff) { fprintf(stderr, "cannot read %s\n", path.c_str()); close(fd); return 1; }
-  const size_t remaining = (size_t)((long long)sb.st_size - coff);
+  // end_off > 0: the BGZF block that starts there is the last one wanted (the contig's records end inside it)
+  long long stop_at = (long long)sb.st_size;
+  if (end_off > 0 && end_off + 18 <= (long long)sb.st_size) {
+    uint8_t hb[18];
+    if (pread(fd, hb, 18, (off_t)end_off) == 18 && hb[0] == 0x1f && hb[1] == 0x8b && hb[12] == 'B' && hb[13] == 'C')
+      stop_at = std::min<long long>(stop_at, end_off + (long long)((unsigned)hb[16] | ((unsigned)hb[17] << 8)) + 1);
+  }
+  if (stop_at <= coff) stop_at = (long long)sb.st_size;
+  const size_t remaining = (size_t)(stop_at - coff);
   const size_t CARRY = (size_t)1 << 20;
   const size_t CHUNK = std::max<size_t>(std::min(chunk_bytes, remaining + 1), (size_t)1 << 20);
   const bool two = remaining > CHUNK;
@@ -348,7 +356,8 @@ int stream_bam(const std::string& path, long long coff, long long skip, rsigpu_c
     cb = nb;
   }
   if (reader.joinable()) reader.join();
-  if (!status && !stop && rsigpu_bam_end(dec)) { fprintf(stderr, "%s\n", rsigpu_last_error(dec)); status = 1; }
+  // the whole FILE was consumed without being stopped: it must not end inside a record (a bounded range ends where the index says)
+  if (!status && !stop && stop_at == (long long)sb.st_size && rsigpu_bam_end(dec)) { fprintf(stderr, "%s\n", rsigpu_last_error(dec)); status = 1; }
   cleanup();
   return status;
 }
@@ -421,8 +430,11 @@ int bam_on_gpu(const Opt& o, const std::vector<std::vector<rsigpu_ctx*>>& ctx, s
           if (!begin_contig(c, tid, fasta, nullptr, &r)) { fail_contig(tid, r.err); continue; }
           if (rsigpu_bam_begin(dec, (int32_t)n_ref)) { fail_contig(tid, rsigpu_last_error(dec)); continue; }
           const uint64_t v = bai[(size_t)tid].first_voff;
+          // the contig's byte range: up to the block where its last record ends (pseudo-bin), else where the next contig with reads starts
+          uint64_t ve = bai[(size_t)tid].end_voff;
+          if (!ve) for (int t = tid + 1; t < n_ref; ++t) if (bai[(size_t)t].has_reads) { ve = bai[(size_t)t].first_voff; break; }
           bool take_err = false;
-          const int rc = stream_bam(o.bamfile, (long long)(v >> 16), (long long)(v & 0xffff), dec, CHUNK, [&](int i, const rsigpu_bam_run& run) {
+          const int rc = stream_bam(o.bamfile, (long long)(v >> 16), (long long)(v & 0xffff), ve ? (long long)(ve >> 16) : 0, dec, CHUNK, [&](int i, const rsigpu_bam_run& run) {
             if (run.tid != tid) return 1;                         // the next contig (or the unplaced reads) begins: done
             if (rsigpu_bam_take(dec, i, c)) { take_err = true; return -1; }
             return 0;
@@ -466,7 +478,7 @@ int bam_on_gpu(const Opt& o, const std::vector<std::vector<rsigpu_ctx*>>& ctx, s
       if (!begin_contig(ctx[(size_t)g][cur_slot], tid, fasta, nullptr, &r)) { fail_contig(tid, r.err); return; }
       cur_ok = true;
     };
-    const int rc = stream_bam(o.bamfile, coff, skip, dec, CHUNK, [&](int i, const rsigpu_bam_run& run) {
+    const int rc = stream_bam(o.bamfile, coff, skip, 0, dec, (size_t)256 << 20, [&](int i, const rsigpu_bam_run& run) {
       if (run.tid < 0) return 1;                                 // unplaced reads come last in a sorted BAM
       if (run.tid != cur) { finish_cur(); start(run.tid); }
       if (cur_ok && rsigpu_bam_take(dec, i, ctx[(size_t)gpu_of[(size_t)cur]][cur_slot])) {

@@ -211,6 +211,9 @@ void launch(dim3 grid, dim3 block, size_t smem, std::function<void()> body, int 
   State& s = S();
   if (s.cur >= 0 && s.live > 0) { std::fprintf(stderr, "cusim: nested launch\n"); std::abort(); }
   const int n = (int)(block.x * block.y * block.z);
+  static int trace = -1, seq = 0;
+  if (trace < 0) trace = std::getenv("CUSIM_TRACE") ? 1 : 0;
+  if (trace) std::fprintf(stderr, "cusim: launch #%d grid %u block %d smem %zu cluster %d\n", seq++, grid.x, n, smem, cluster);
   if (n <= 0 || n > 1024) { std::fprintf(stderr, "cusim: bad block size %d\n", n); std::abort(); }
   if (cluster < 1 || grid.x % (unsigned)cluster) { std::fprintf(stderr, "cusim: grid.x not a multiple of the cluster size\n"); std::abort(); }
   const int nf = n * cluster;

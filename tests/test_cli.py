@@ -219,7 +219,11 @@ def test_cli_corrupt_bam_is_an_error_not_a_table(cli, tmp_path):
                              capture_output=True, text=True, env=dict(os.environ, **env))
         assert out.returncode != 0, (extra, env, out.stderr)
         bad = [ln for ln in _table(str(tmp_path / "bad.txt")) if not ln.startswith("#")]
-        assert bad == [ln for ln in rows if ln.split("\t")[0] == "1"], (extra, env, out.stderr)
+        first = [ln for ln in rows if ln.split("\t")[0] == "1"]
+        if env:      # one sequential pass: the chunk that holds the damage may also hold the end of contig 1, which then fails as well
+            assert bad in ([], first), (extra, env, out.stderr)
+        else:        # per-contig byte ranges from the index / host reader: contig 1 is untouched by the damage
+            assert bad == first, (extra, env, out.stderr)
 
 
 def test_header_reader_agrees_with_the_python_one(cli, tmp_path):
