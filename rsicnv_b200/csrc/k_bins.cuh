@@ -189,6 +189,132 @@ __global__ void __launch_bounds__(C_NT) k_bins(int* __restrict__ rdc, float* __r
   if (tid == 0 && mx > 0) atomicMax(reinterpret_cast<u64*>(&st->max_binsum), (u64)mx);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pass C for bins of m <= 127 bases (the default 101 and every smaller bin): the same work as k_bins with every WARP as an
+// independent pipeline, like the per-base passes -- its own warp-tiles of CW_BINS whole bins, its own two-stage bulk-copy
+// ring, its own class-histogram table; no block barrier in the loop.  The pseudo-tile after the last bin tile owns the
+// < m bases beyond nb*m.
+enum { CW_NW = 8, CW_NT = CW_NW * 32, CW_BINS = 16 /* one bin per lane pair */, CW_CAP = 2048 /* words per stage >= 16 * 127 + 3 */ };
+#define RSI_CW_WARP_BYTES ((size_t)2 * CW_CAP * 4 + (size_t)MAD_CLASSES * C_KP * 2 + 4)
+#define RSI_SMEM_CW ((size_t)CW_NW * RSI_CW_WARP_BYTES)
+__global__ void __launch_bounds__(CW_NT) k_bins_warp(int* __restrict__ rdc, float* __restrict__ bin_med, int* __restrict__ bin_medint,
+                                                      i64* __restrict__ bin_sum, u32* chist, u32* thist, DevState* st) {
+  RSI_DYN_SMEM(smem);
+  RSI_CTA_SETUP(c);
+  __shared__ __align__(8) u64 s_bar[CW_NW * 2];
+  const int tid = c.tid, lane = tid & 31, warp = tid >> 5;
+  unsigned char* wsm = smem + (size_t)warp * RSI_CW_WARP_BYTES;
+  u16* wt_ = reinterpret_cast<u16*>(wsm + 2 * CW_CAP * 4);     // [MAD_CLASSES][C_KP]
+  u64* bar = s_bar + warp * 2;
+  const int Lc = st->Lc, m = st->m, nb = st->nb, R = st->chist_R, cap_on = st->cap_on, capv = st->capv;
+  const double thr = st->cap_thr;
+  const int sub31 = MAD_CLASSES * (Lc / MAD_CLASSES);
+  int wb = 0;
+  if (R > C_K) { wb = (int)st->cap_median - C_K / 2; if (wb < 0) wb = 0; if (wb > R - C_K) wb = R - C_K; }
+  for (int k = lane; k < MAD_CLASSES * C_KP; k += 32) wt_[k] = 0;
+  const int ithr = thr >= 2147483647.0 ? 0x7fffffff : (int)floor(thr);   // integer v: (double)v > thr  <=>  v > floor(thr)
+  i64 mx = 0;
+  const int nbin_tiles = nb > 0 ? (nb + CW_BINS - 1) / CW_BINS : 0;
+  const int ntiles = nbin_tiles + (Lc - nb * m > 0 ? 1 : 0);
+  if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
+  c.sync();
+  const int gw = (int)blockIdx.x * CW_NW + warp, GW = (int)gridDim.x * CW_NW;
+  if (lane == 0)
+    for (int s = 0; s < 2; ++s) { const int t = gw + s * GW; if (t < ntiles) c_issue(reinterpret_cast<int*>(wsm + (size_t)s * CW_CAP * 4), &bar[s], rdc, c_tile(t, nbin_tiles, CW_BINS, nb, m, Lc)); }
+  const int need = (m - 1) / 2 + 1;                    // median = smallest v with #{x <= v} >= need (m is odd)
+  const int nreg = (m + 7) / 8;                        // packed registers per lane: ceil(ceil(m/2) / 4)
+  int it = 0;
+  for (int tile = gw; tile < ntiles; tile += GW, ++it) {
+    const int s = it & 1;
+    const CTile T = c_tile(tile, nbin_tiles, CW_BINS, nb, m, Lc);
+    int* stage = reinterpret_cast<int*>(wsm + (size_t)s * CW_CAP * 4);
+    mbar_wait(&bar[s], (u32)(it >> 1) & 1u);
+    int* vals = stage + (T.B & 3);
+    // ---- phase 1: cap clamp + class histograms: 31 consecutive bases per step, 31 different classes, a lane's class is fixed for the tile
+    if (lane < 31) {
+      int cls = T.B % MAD_CLASSES + lane; if (cls >= MAD_CLASSES) cls -= MAD_CLASSES;
+      u16* row = wt_ + cls * C_KP;
+      u32* grow = chist + (size_t)cls * R;
+      for (int q = lane; q < T.np; q += 31) {
+        int v = vals[q];
+        if (cap_on && v > ithr) { v = capv; vals[q] = capv; rdc[T.B + q] = capv; }
+        const unsigned w = (unsigned)(v - wb);
+        if (T.B + q >= sub31) { if (v >= 0 && v < R) atomicAdd(&thist[v], 1u); }
+        else if (w < (unsigned)C_K) row[w] += 1;
+        else if (v >= 0 && v < R) atomicAdd(&grow[v], 1u);
+      }
+    }
+    __syncwarp();
+    // ---- phase 2: a lane pair per bin; values as bytes relative to the window, 4 per register
+    {
+      const int b = lane >> 1, par = lane & 1;
+      const bool act = b < T.nbt;
+      const int* x = vals + (act ? b : 0) * m;
+      u32 pk[16];
+      int s32 = 0; u32 out = 0;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        u32 w4 = 0;
+        if (r < nreg) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int j = 2 * (r * 4 + k) + par;
+            u32 u = 0x7fu;                            // padding: never <= a probe below 127, and a real 127 makes the bin take the slow path
+            if (act && j < m) { const int v = x[j]; s32 += v; const unsigned d = (unsigned)(v - wb); out |= d; u = d & 0x7fu; }
+            w4 |= u << (8 * k);
+          }
+        }
+        pk[r] = w4;
+      }
+      const bool slow = (out >= 127u);                // values of the bin must lie in [wb, wb + 126]
+      const i64 sum = (i64)s32 + (i64)__shfl_xor_sync(0xffffffffu, s32, 1);      // < 127 * 2^24
+      const int oslow = __shfl_xor_sync(0xffffffffu, (int)slow, 1);
+      const bool pslow = slow || oslow != 0;
+      int lo = 0, hi = 126;
+#pragma unroll 1
+      for (int itb = 0; itb < 7; ++itb) {            // every lane runs the 7 probes (idle pairs on padding): the shuffles stay converged
+        const int mid = (lo + hi) >> 1;
+        const u32 probe = 0x80808080u | ((u32)mid * 0x01010101u);
+        u32 acc = 0;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) if (r < nreg) acc += ((probe - pk[r]) >> 7) & 0x01010101u;    // per byte: 1 iff value <= mid
+        int cnt = (int)((acc * 0x01010101u) >> 24);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
+        if (cnt >= need) hi = mid; else lo = mid + 1;
+      }
+      if (act && par == 0 && !pslow) { const int med = wb + lo; bin_med[T.b0 + b] = (float)med; bin_medint[T.b0 + b] = med; bin_sum[T.b0 + b] = sum; mx = lmax(mx, sum); }
+      // bins with a value outside the window: the whole warp, one bin after the other (rare)
+      unsigned todo = __ballot_sync(0xffffffffu, act && par == 0 && pslow);
+      while (todo) {
+        const int bb = (__ffs((int)todo) - 1) >> 1; todo &= todo - 1;
+        const int* xb = vals + bb * m;
+        int l2 = 0x7fffffff, h2 = -0x7fffffff - 1; i64 sm = 0;
+        for (int j = lane; j < m; j += 32) { const int v = xb[j]; l2 = imin(l2, v); h2 = imax(h2, v); sm += v; }
+        l2 = __reduce_min_sync(0xffffffffu, l2); h2 = __reduce_max_sync(0xffffffffu, h2);
+        sm = warp_sum_i64(sm);
+        while (l2 < h2) {
+          const int mid = l2 + ((h2 - l2) >> 1);
+          int cnt = 0;
+          for (int j0 = 0; j0 < m; j0 += 32) { const int j = j0 + lane; cnt += __popc(__ballot_sync(0xffffffffu, j < m && xb[j] <= mid)); }
+          if (cnt >= need) h2 = mid; else l2 = mid + 1;
+        }
+        if (lane == 0) { bin_med[T.b0 + bb] = (float)l2; bin_medint[T.b0 + bb] = l2; bin_sum[T.b0 + bb] = sm; mx = lmax(mx, sm); }
+      }
+    }
+    __syncwarp();                                      // every lane is done with stage s
+    const int t2 = tile + 2 * GW;
+    if (lane == 0 && t2 < ntiles) c_issue(stage, &bar[s], rdc, c_tile(t2, nbin_tiles, CW_BINS, nb, m, Lc));
+  }
+  __syncwarp();
+  for (int item = lane; item < MAD_CLASSES * C_K; item += 32) {
+    const int cl = item / C_K, w = item % C_K;
+    const u32 sum = wt_[cl * C_KP + w];
+    if (sum && wb + w < R) atomicAdd(&chist[cl * R + wb + w], sum);
+  }
+  mx = c.reduce(mx, MaxOp());
+  if (tid == 0 && mx > 0) atomicMax(reinterpret_cast<u64*>(&st->max_binsum), (u64)mx);
+}
+
 // RDmedian, RDsd (rsi.cpp:2202-2203) and negative_binomial_transfer's MAD (rsi.cpp:1128-1140) from the
 // class histograms.  One block; thread c < 31 walks class c.
 __global__ void __launch_bounds__(1024) k_chr_stats(const u32* chist, const u32* thist, u32* tot_hist, DevState* st) {

@@ -26,18 +26,22 @@ namespace rsigpu {
   c.tid = (int)threadIdx.x; c.nthr = (int)blockDim.x; c.red = cta_red_; c.bc = cta_bc_;
 
 // ---------------------------------------------------------------------------------------------
-// Tile geometry of the two per-base passes.  A block of LD_NT threads owns LD_T consecutive bases per iteration; thread t
-// owns the LD_CH consecutive bases [t*LD_CH, (t+1)*LD_CH) of the tile (so the GC count of its window moves by at most one
-// per base and is tracked incrementally), which it reads from the staged tile with 16-byte shared-memory loads -- LD_CH is
-// 4 * odd, so the 8 lanes of a quarter-warp hit 8 different 16-byte bank groups.  Tiles (depth words + FASTA bytes incl. the
-// 100-base window halo on both sides) arrive by bulk copy into a two-stage ring (rt.cuh).
-enum { LD_NT = 256, LD_NW = LD_NT / 32, LD_CH = 28, LD_T = LD_NT * LD_CH /* 7168 bases */,
-       LD_FPAD = 208 /* FASTA bytes staged in front of the tile: the window of the contig's last bases starts up to 201 before them */,
-       LD_FR = 112 /* ... and behind it: the window reaches 100 past a base; both multiples of 16 */,
-       LD_FA = LD_T + LD_FPAD + LD_FR /* FASTA bytes per tile */, LD_GW = LD_FA / 32 /* GC bit words */, LD_ROWS = 64 /* GC strata in a warp's private table */ };
-enum { B_K = 128 };        // value window of pass B's private histogram
-enum { LD_TILE = LD_T };   // depth arrays are padded to a multiple of this (rsigpu.cu)
-static_assert(LD_FA % 32 == 0 && (LD_CH % 8) == 4, "tile geometry");
+// Geometry of the two per-base passes.  Every WARP is an independent pipeline: it owns the warp-tiles gw, gw + GW, ... (W_T
+// consecutive bases each; gw = global warp id), its own two-stage ring in shared memory that bulk copies (cp.async.bulk,
+// rt.cuh) fill with the tile's depth words and FASTA bytes (incl. the window halo), its own mbarriers and its own private
+// tables -- no block barrier anywhere in the loop, so a slow warp never stalls the other warps of the SM.  Lane l owns the
+// W_CH consecutive bases [l*W_CH, (l+1)*W_CH) of the tile: the GC count of its 201-base window moves by at most one per
+// base, so it is one popcount of the window at the chunk start plus prefix popcounts of the in/out bits.  W_CH is 4 * odd:
+// the 16-byte shared-memory loads of the 8 lanes of a quarter-warp hit 8 different bank groups.
+enum { W_CH = 28, W_T = 32 * W_CH /* 896 bases */,
+       W_FL = 208 /* FASTA bytes staged in front of the tile: the window of the contig's last bases starts up to 201 before them */,
+       W_FR = 112 /* ... and behind it: the window reaches 100 past a base; both multiples of 16 */,
+       W_FA = W_T + W_FL + W_FR /* 1216 FASTA bytes per tile */, W_GW = W_FA / 32 /* 38 GC bit words */,
+       W_STAGE = W_T * 4 + W_FA /* 4800 bytes */, W_BITS = (W_GW + 2) * 4 };
+enum { LD_T = 8 * W_T, LD_TILE = LD_T };   // depth arrays are padded to a multiple of this (rsigpu.cu)
+enum { A_NW = 8, A_NT = A_NW * 32, A_ROWS = 64 /* GC strata in a warp's private table */ };
+enum { B_NW = 10, B_NT = B_NW * 32, B_K = 128 /* value window of pass B's private histogram */, B_NCACHE = 256 /* N intervals cached in shared memory */ };
+static_assert(W_FA % 32 == 0 && (W_CH % 8) == 4 && W_STAGE % 16 == 0, "tile geometry");
 
 // ---------------------------------------------------------------------------------------------
 // N runs of the contig (uppercase 'N' only): run starts and run ends are appended (unordered) to two
@@ -62,53 +66,44 @@ __global__ void k_n_runs(const u8* __restrict__ fa, int L, int* beg, int* end, i
 // edge never takes the last base" quirk).
 __device__ __forceinline__ int gc_lo(int i, int L) { return iclamp(i - GC_WIN / 2, 0, L - GC_WIN - 1); }
 
-struct LdStage { int* rd; u8* fa; };
-struct LdRing {   // dynamic shared memory: 2 x (depth tile | FASTA tile) | GC bit words
-  LdStage st[2]; u32* gcb; u64* bar;
-};
-__device__ __forceinline__ LdRing ld_ring(unsigned char* smem, u64* bars) {
-  LdRing R;
-  R.st[0].rd = reinterpret_cast<int*>(smem); R.st[0].fa = smem + (size_t)LD_T * 4;
-  R.st[1].rd = reinterpret_cast<int*>(smem + (size_t)LD_T * 4 + LD_FA); R.st[1].fa = smem + (size_t)LD_T * 8 + LD_FA;
-  R.gcb = reinterpret_cast<u32*>(smem + 2 * ((size_t)LD_T * 4 + LD_FA));
-  R.bar = bars;
-  return R;
-}
-#define RSI_LD_RING_BYTES (2 * ((size_t)LD_T * 4 + LD_FA) + (size_t)(LD_GW + 4) * 4)
-// one thread: arm the stage's barrier and issue the two copies of tile `tile` (depth words; FASTA bytes [t0-LD_FPAD, t0+LD_T+LD_FR))
-__device__ __forceinline__ void ld_issue(const LdRing& R, int s, int tile, const int* __restrict__ rd, const u8* __restrict__ fa, int do_gc) {
-  const size_t t0 = (size_t)tile * LD_T;
-  const u32 fskip = tile == 0 ? LD_FPAD : 0;     // nothing in front of base 0
-  const u32 fbytes = do_gc ? LD_FA - fskip : 0;
+// one lane: arm the stage's barrier and issue the copies of warp-tile `wt` (depth words; FASTA bytes [w0 - W_FL, w0 + W_T + W_FR))
+__device__ __forceinline__ void w_issue(unsigned char* stage, u64* bar, int wt, const int* __restrict__ rd, const u8* __restrict__ fa, int do_gc) {
+  const size_t w0 = (size_t)wt * W_T;
+  const u32 fskip = wt == 0 ? W_FL : 0;     // nothing in front of base 0
+  const u32 fbytes = do_gc ? W_FA - fskip : 0;
   fence_proxy_async();
-  mbar_expect_tx(&R.bar[s], (u32)LD_T * 4 + fbytes);
-  bulk_g2s(R.st[s].rd, rd + t0, (u32)LD_T * 4, &R.bar[s]);
-  if (fbytes) bulk_g2s(R.st[s].fa + fskip, fa + t0 - LD_FPAD + fskip, fbytes, &R.bar[s]);
+  mbar_expect_tx(bar, (u32)W_T * 4 + fbytes);
+  bulk_g2s(stage, rd + w0, (u32)W_T * 4, bar);
+  if (fbytes) bulk_g2s(stage + (size_t)W_T * 4 + fskip, fa + w0 - W_FL + fskip, fbytes, bar);
 }
-// GC flags of the staged FASTA tile as a bit string: bit k of gcb <-> base t0 - LD_FPAD + k.  32 bytes -> one word per thread.
-__device__ __forceinline__ void ld_gc_bits(const LdRing& R, int s, int tile, int tid) {
-  const uint4* f = reinterpret_cast<const uint4*>(R.st[s].fa);
-  for (int w = tid; w < LD_GW; w += LD_NT) {
-    u32 word = 0;
-    if (!(tile == 0 && w * 32 < LD_FPAD)) {      // bytes in front of base 0 were never copied (and are never used)
+// GC flags of the staged FASTA bytes as a bit string: bit k of gcb <-> base w0 - W_FL + k.  One word per lane (32 bytes), twice.
+__device__ __forceinline__ void w_gc_bits(const unsigned char* stage_fa, u32* gcb, int wt, int lane) {
+  const uint4* f = reinterpret_cast<const uint4*>(stage_fa);
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const uint4 v = f[w * 2 + h];
-        const u32 x[4] = {v.x, v.y, v.z, v.w};
+  for (int r = 0; r < 2; ++r) {
+    const int w = r * 32 + lane;
+    if (w < W_GW) {
+      u32 word = 0;
+      if (!(wt == 0 && w * 32 < W_FL)) {      // bytes in front of base 0 were never copied (and are never used)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const u32 y = (x[k] | 0x04040404u) ^ 0x47474747u;                      // zero byte <=> 'G' or 'C' (uppercase only)
-          const u32 z = ~(((y & 0x7f7f7f7fu) + 0x7f7f7f7fu) | y | 0x7f7f7f7fu);   // 0x80 in every zero byte
-          word |= ((((z >> 7) * 0x00204081u) >> 21) & 0xfu) << (h * 16 + k * 4);
+        for (int h = 0; h < 2; ++h) {
+          const uint4 v = f[w * 2 + h];
+          const u32 x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const u32 y = (x[k] | 0x04040404u) ^ 0x47474747u;                      // zero byte <=> 'G' or 'C' (uppercase only)
+            const u32 z = ~(((y & 0x7f7f7f7fu) + 0x7f7f7f7fu) | y | 0x7f7f7f7fu);   // 0x80 in every zero byte
+            word |= ((((z >> 7) * 0x00204081u) >> 21) & 0xfu) << (h * 16 + k * 4);
+          }
         }
       }
+      gcb[w] = word;
     }
-    R.gcb[w] = word;
   }
-  if (tid < 4) R.gcb[LD_GW + tid] = 0;
+  if (lane < 2) gcb[W_GW + lane] = 0;
 }
 // number of G/C among the 201 bases that start at bit a of the tile's bit string
-__device__ __forceinline__ int ld_gc_count(const u32* gcb, int a) {
+__device__ __forceinline__ int w_gc_count(const u32* gcb, int a) {
   const int w0 = a >> 5, sh = a & 31;
   int n = 0;
   u32 cur = gcb[w0];
@@ -121,104 +116,142 @@ __device__ __forceinline__ int ld_gc_count(const u32* gcb, int a) {
   }
   return n;
 }
-__device__ __forceinline__ u32 ld_bits32(const u32* gcb, int a) {
+__device__ __forceinline__ u32 w_bits32(const u32* gcb, int a) {
   const int w0 = a >> 5;
   return (u32)((((u64)gcb[w0 + 1] << 32) | gcb[w0]) >> (a & 31));
 }
+// is every base of the warp-tile an interior position of the contig (window unclamped, whole tile inside the contig)?
+__device__ __forceinline__ bool w_interior(int w0, int L) { return w0 >= GC_WIN / 2 && w0 + W_T - 1 <= L - GC_WIN / 2 - 2; }
 
 // ---------------------------------------------------------------------------------------------
 // Pass A: mean of the positive depths and the per-stratum depth sums / counts (5 B/base read; checkgccontent's table,
-// gccontent.cpp:95-150).  Every warp has a PRIVATE table wtab[LD_ROWS][32 lanes] of packed (count << 40 | sum) words: lane l
-// only ever touches column l, so the per-base update is a plain conflict-free 8-byte read-modify-write -- no atomics, no
-// warp votes.  Rows cover the strata [gc_base, gc_base + LD_ROWS) around the contig's mean GC count; a base outside that
-// window goes to a small block table with shared-memory atomics.  A lane adds < 2^16 bases of depth < 2^24 to one word.
-// Dynamic shared memory: ring | wtab[LD_NW][LD_ROWS][32] u64 | osum[GC_STRATA] u64 | ocnt[GC_STRATA] u32
-#define RSI_SMEM_A (RSI_LD_RING_BYTES + (size_t)LD_NW * LD_ROWS * 32 * 8 + (size_t)GC_STRATA * 12 + 16)
-__global__ void __launch_bounds__(LD_NT) k_gc_table(const int* __restrict__ rd, const u8* __restrict__ fa, DevState* st) {
+// gccontent.cpp:95-150).  Every warp has a PRIVATE table wtab[A_ROWS + 1][32 lanes] of packed (count << 40 | sum) words: lane
+// l only ever touches column l, so the per-base update is a plain conflict-free 8-byte read-modify-write -- no atomics, no
+// warp votes.  Rows cover the strata [gc_base, gc_base + A_ROWS) around the contig's mean GC count; a base outside goes to
+// the spare row (never read) and is redone afterwards through a block table with shared-memory atomics.  The update is
+// branch-free and software-pipelined: the next base's word is loaded BEFORE the current one is stored, and forwarded in
+// registers when both are the same row (every second base), so a lane's chain of updates never waits for shared memory.
+// A lane adds < 2^16 bases of depth < 2^24 to one word.
+// Dynamic shared memory per warp: 2 stages | bit string | wtab;  per block: osum[GC_STRATA] u64 | ocnt[GC_STRATA] u32
+#define RSI_A_WARP_BYTES ((size_t)2 * W_STAGE + W_BITS + (size_t)(A_ROWS + 1) * 256)
+#define RSI_SMEM_A ((size_t)A_NW * RSI_A_WARP_BYTES + (size_t)GC_STRATA * 12 + 16)
+__global__ void __launch_bounds__(A_NT) k_gc_table(const int* __restrict__ rd, const u8* __restrict__ fa, DevState* st) {
   RSI_DYN_SMEM(smem);
   RSI_CTA_SETUP(c);
-  __shared__ __align__(8) u64 s_bar[2];
+  __shared__ __align__(8) u64 s_bar[A_NW * 2];
   const int L = st->L, do_gc = st->gc_on, gbase = st->gc_base;
-  const LdRing R = ld_ring(smem, s_bar);
-  u64* wtab_all = reinterpret_cast<u64*>(smem + ((RSI_LD_RING_BYTES + 15) & ~(size_t)15));
-  u64* osum = wtab_all + (size_t)LD_NW * LD_ROWS * 32;
-  u32* ocnt = reinterpret_cast<u32*>(osum + GC_STRATA);
   const int tid = c.tid, lane = tid & 31, warp = tid >> 5;
+  unsigned char* wsm = smem + (size_t)warp * RSI_A_WARP_BYTES;
+  u32* gcb = reinterpret_cast<u32*>(wsm + 2 * W_STAGE);
+  u64* wtab = reinterpret_cast<u64*>(wsm + 2 * W_STAGE + W_BITS);
+  u64* osum = reinterpret_cast<u64*>(smem + (size_t)A_NW * RSI_A_WARP_BYTES);
+  u32* ocnt = reinterpret_cast<u32*>(osum + GC_STRATA);
+  u64* bar = s_bar + warp * 2;
   if (do_gc) {
-    for (int k = tid; k < LD_NW * LD_ROWS * 32; k += LD_NT) wtab_all[k] = 0ull;
-    for (int k = tid; k < GC_STRATA; k += LD_NT) { osum[k] = 0ull; ocnt[k] = 0u; }
+    for (int k = lane; k < (A_ROWS + 1) * 32; k += 32) wtab[k] = 0ull;
+    for (int k = tid; k < GC_STRATA; k += A_NT) { osum[k] = 0ull; ocnt[k] = 0u; }
   }
-  u64* col = wtab_all + (size_t)warp * LD_ROWS * 32 + lane;
-  const int ntiles = (L + LD_T - 1) / LD_T;
-  if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
+  if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
   c.sync();
-  if (tid == 0)
-    for (int s = 0; s < 2; ++s) { const int t = (int)blockIdx.x + s * (int)gridDim.x; if (t < ntiles) ld_issue(R, s, t, rd, fa, do_gc); }
+  u64* col = wtab + lane;
+  const int nwt = (L + W_T - 1) / W_T;
+  const int gw = (int)blockIdx.x * A_NW + warp, GW = (int)gridDim.x * A_NW;
+  if (lane == 0)
+    for (int s = 0; s < 2; ++s) { const int t = gw + s * GW; if (t < nwt) w_issue(wsm + s * W_STAGE, &bar[s], t, rd, fa, do_gc); }
   u64 psum = 0, pcnt = 0;
   int vmin = 0x7fffffff, vmax = -0x7fffffff - 1;
   int it = 0;
-  for (int tile = (int)blockIdx.x; tile < ntiles; tile += (int)gridDim.x, ++it) {
+  for (int wt = gw; wt < nwt; wt += GW, ++it) {
     const int s = it & 1;
-    mbar_wait(&R.bar[s], (u32)(it >> 1) & 1u);
-    const int t0 = tile * LD_T;
-    if (do_gc) { ld_gc_bits(R, s, tile, tid); c.sync(); }
-    const int* x4 = R.st[s].rd + tid * LD_CH;
-    const int p0 = t0 + tid * LD_CH;
+    unsigned char* stage = wsm + s * W_STAGE;
+    mbar_wait(&bar[s], (u32)(it >> 1) & 1u);
+    const int w0 = wt * W_T;
+    if (do_gc) { w_gc_bits(stage + (size_t)W_T * 4, gcb, wt, lane); __syncwarp(); }
+    const int* x4 = reinterpret_cast<const int*>(stage) + lane * W_CH;
+    const int p0 = w0 + lane * W_CH;
     u32 tsum = 0, tcnt = 0;
-    auto add = [&](int x, int g) {
-      vmin = imin(vmin, x); vmax = imax(vmax, x);
-      if (x > 0) { tsum += (u32)x; tcnt += 1; }
-      if (do_gc) {
-        const unsigned row = (unsigned)(g - gbase);
-        const u64 e = (1ull << 40) | (u64)((u32)x & 0xffffffu);
-        if (row < (unsigned)LD_ROWS) col[row * 32] += e;
-        else { atomicAdd(&osum[g], (u64)((u32)x & 0xffffffu)); atomicAdd(&ocnt[g], 1u); }
-      }
-    };
-    if (p0 + LD_CH <= L && (!do_gc || (p0 >= GC_WIN / 2 && p0 + LD_CH - 1 <= L - GC_WIN / 2 - 2))) {
-      // interior chunk: the window slides by one base per step, g += bit(p+101) - bit(p-100)
-      int g = 0; u32 inw = 0, outw = 0;
-      if (do_gc) {
-        const int q = tid * LD_CH;               // p - t0; bit index of base p is q + LD_FPAD
-        g = ld_gc_count(R.gcb, q + LD_FPAD - GC_WIN / 2);
-        inw = ld_bits32(R.gcb, q + LD_FPAD + GC_WIN / 2 + 1); outw = ld_bits32(R.gcb, q + LD_FPAD - GC_WIN / 2);
-      }
+    if (w_interior(w0, L) || (!do_gc && w0 + W_T <= L)) {
+      // ---- fast path: 28 interior bases, straight-line code
+      int xs[W_CH];
 #pragma unroll
-      for (int j4 = 0; j4 < LD_CH / 4; ++j4) {
+      for (int j4 = 0; j4 < W_CH / 4; ++j4) {
         const int4 v = *reinterpret_cast<const int4*>(x4 + j4 * 4);
-        const int xs[4] = {v.x, v.y, v.z, v.w};
+        xs[j4 * 4] = v.x; xs[j4 * 4 + 1] = v.y; xs[j4 * 4 + 2] = v.z; xs[j4 * 4 + 3] = v.w;
+      }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int j = j4 * 4 + k;
-          add(xs[k], g);
-          g += (int)((inw >> j) & 1u) - (int)((outw >> j) & 1u);
+      for (int j = 0; j < W_CH; ++j) {
+        const int x = xs[j];
+        vmin = imin(vmin, x); vmax = imax(vmax, x);
+        tsum += (u32)imax(x, 0); tcnt += x > 0 ? 1u : 0u;
+      }
+      if (do_gc) {
+        const int q = lane * W_CH;               // p - w0; bit index of base p is q + W_FL
+        const int g0 = w_gc_count(gcb, q + W_FL - GC_WIN / 2) - gbase;
+        const u32 inw = w_bits32(gcb, q + W_FL + GC_WIN / 2 + 1), outw = w_bits32(gcb, q + W_FL - GC_WIN / 2);
+        const u32 plus = inw & ~outw, minus = outw & ~inw;      // the window count moves by bit(p+101) - bit(p-100) per base
+        u32 ovf = 0;
+        unsigned row = (unsigned)g0;
+        unsigned re = row < (unsigned)A_ROWS ? row : (unsigned)A_ROWS;
+        ovf |= row < (unsigned)A_ROWS ? 0u : 1u;
+        u64 e = col[re * 32];
+#pragma unroll
+        for (int j = 0; j < W_CH; ++j) {
+          u64 en = 0; unsigned rn = re;
+          if (j + 1 < W_CH) {
+            const u32 mk = (2u << j) - 1u;
+            const unsigned nrow = (unsigned)(g0 + __popc(plus & mk) - __popc(minus & mk));
+            rn = nrow < (unsigned)A_ROWS ? nrow : (unsigned)A_ROWS;
+            ovf |= nrow < (unsigned)A_ROWS ? 0u : (2u << j);
+            en = col[rn * 32];                     // issued before the store below
+          }
+          e += (1ull << 40) | (u64)((u32)xs[j] & 0xffffffu);
+          col[re * 32] = e;
+          e = rn == re ? e : en;
+          re = rn;
+        }
+        if (ovf) {                                 // rare: strata outside the private window
+          for (u32 m = ovf; m; m &= m - 1) {
+            const int j = __ffs((int)m) - 1;
+            const u32 mk = (1u << j) - 1u;
+            const int g = g0 + gbase + __popc(plus & mk) - __popc(minus & mk);
+            atomicAdd(&osum[g], (u64)((u32)x4[j] & 0xffffffu)); atomicAdd(&ocnt[g], 1u);      // (from the stage: a dynamic index would push xs[] to local memory)
+          }
         }
       }
     } else {
-      for (int j = 0; j < LD_CH && p0 + j < L; ++j) {
-        const int p = p0 + j;
-        const int g = do_gc ? ld_gc_count(R.gcb, gc_lo(p, L) - t0 + LD_FPAD) : 0;
-        add(x4[j], g);
+      // ---- contig ends: clamped windows, partial tile
+      for (int j = 0; j < W_CH && p0 + j < L; ++j) {
+        const int p = p0 + j, x = x4[j];
+        vmin = imin(vmin, x); vmax = imax(vmax, x);
+        if (x > 0) { tsum += (u32)x; tcnt += 1; }
+        if (do_gc) {
+          const int g = w_gc_count(gcb, gc_lo(p, L) - w0 + W_FL);
+          const unsigned row = (unsigned)(g - gbase);
+          if (row < (unsigned)A_ROWS) col[row * 32] += (1ull << 40) | (u64)((u32)x & 0xffffffu);
+          else { atomicAdd(&osum[g], (u64)((u32)x & 0xffffffu)); atomicAdd(&ocnt[g], 1u); }
+        }
       }
     }
     psum += tsum; pcnt += tcnt;
-    c.sync();                                     // everybody is done with stage s (and with the bit string)
-    const int t2 = tile + 2 * (int)gridDim.x;
-    if (tid == 0 && t2 < ntiles) ld_issue(R, s, t2, rd, fa, do_gc);
+    __syncwarp();                                  // every lane is done with stage s and with the bit string
+    const int t2 = wt + 2 * GW;
+    if (lane == 0 && t2 < nwt) w_issue(stage, &bar[s], t2, rd, fa, do_gc);
   }
   c.sync();
   if (do_gc) {
-    // column sums of the private tables: thread (row, part) adds 2 warps x 32 lanes of its row into the block table
+    // column sums of the private tables: thread (row, part) adds A_NW / 4 warps x 32 lanes of its row into the block table
     {
-      const int row = tid & (LD_ROWS - 1), part = tid / LD_ROWS;          // LD_NT / LD_ROWS = 4 parts
+      const int row = tid & (A_ROWS - 1), part = tid / A_ROWS;          // A_NT / A_ROWS = 4 parts
       u64 sum = 0, cnt = 0;
-      for (int w = part * (LD_NW / 4); w < (part + 1) * (LD_NW / 4); ++w)
-        for (int l = 0; l < 32; ++l) { const u64 e = wtab_all[((size_t)w * LD_ROWS + row) * 32 + ((l + tid) & 31)]; sum += e & ((1ull << 40) - 1); cnt += e >> 40; }
+      for (int w = part * (A_NW / 4); w < (part + 1) * (A_NW / 4); ++w) {
+        const u64* t = reinterpret_cast<const u64*>(smem + (size_t)w * RSI_A_WARP_BYTES + 2 * W_STAGE + W_BITS);
+        for (int l = 0; l < 32; ++l) { const u64 e = t[(size_t)row * 32 + ((l + tid) & 31)]; sum += e & ((1ull << 40) - 1); cnt += e >> 40; }
+      }
       const int g = gbase + row;
       if (cnt && g < GC_STRATA) { atomicAdd(&osum[g], sum); atomicAdd(&ocnt[g], (u32)cnt); }
     }
     c.sync();
-    for (int g = tid; g < GC_STRATA; g += LD_NT)
+    for (int g = tid; g < GC_STRATA; g += A_NT)
       if (ocnt[g]) { atomicAdd(&st->gc_sum[g], osum[g]); atomicAdd(&st->gc_cnt[g], (u64)ocnt[g]); }
   }
   psum = c.reduce(psum, SumOp()); pcnt = c.reduce(pcnt, SumOp());
@@ -260,126 +293,165 @@ __global__ void k_gc_finalize(const u8* __restrict__ fa, DevState* st) {
 // Pass B: GC adjust (out-of-place map + the 21st pseudo-slice quirk), value histogram of
 // ALL positions for apply_cap's median, and the N-compacted store (9 B/base: 4+1 read, 4 written).
 // noseq intervals: nbeg/nend (0-based inclusive), ncum[k] = bases removed by intervals 0..k-1.
-// Same tile ring and incremental GC count as pass A.  The adjusted value goes back into the staged tile in place
-// (a thread only touches its own chunk) and the block then writes the tile out with coalesced 16-byte stores.  The value
-// histogram uses one private column per lane again: vh[warp][B_K][32] u16 (a lane adds < 2^16 bases to one counter).
-// Dynamic shared memory: ring | vh[LD_NW][B_K][32] u16 | tab[GC_STRATA][16] f64
-#define RSI_SMEM_B (RSI_LD_RING_BYTES + 16 + (size_t)LD_NW * B_K * 32 * 2 + (size_t)GC_STRATA * 16 * 8)
-__global__ void __launch_bounds__(LD_NT) k_gc_adjust(const int* __restrict__ rd, const u8* __restrict__ fa, int* __restrict__ rdc,
-                                                      const int* __restrict__ nbeg, const int* __restrict__ nend, const int* __restrict__ ncum,
-                                                      u32* hist_all, DevState* st) {
+// Same warp-private rings and GC counts as pass A.  The adjusted value goes back into the staged tile in place (a lane only
+// touches its own chunk) and the warp then writes its tile out with coalesced stores, 16 bytes per lane where the
+// destination allows.  The value histogram uses one private column per lane again: vh[B_K][32] u16 per warp (a lane adds
+// < 2^16 bases to one counter), updated branch-free; values outside the window are redone after the chunk.
+// Dynamic shared memory per warp: 2 stages | bit string | vh;  per block: tab[GC_STRATA][16] f64 | N intervals (beg, end, cum)
+#define RSI_B_WARP_BYTES ((size_t)2 * W_STAGE + W_BITS + (size_t)(B_K + 1) * 64)
+#define RSI_SMEM_B ((size_t)B_NW * RSI_B_WARP_BYTES + (size_t)GC_STRATA * 16 * 8 + (size_t)B_NCACHE * 12 + 16)
+__global__ void __launch_bounds__(B_NT) k_gc_adjust(const int* __restrict__ rd, const u8* __restrict__ fa, int* __restrict__ rdc,
+                                                     const int* __restrict__ nbeg, const int* __restrict__ nend, const int* __restrict__ ncum,
+                                                     u32* hist_all, DevState* st) {
   RSI_DYN_SMEM(smem);
   RSI_CTA_SETUP(c);
-  __shared__ __align__(8) u64 s_bar[2];
-  __shared__ int s_k0, s_hasn;
+  __shared__ __align__(8) u64 s_bar[B_NW * 2];
   const int L = st->L, do_gc = st->gc_on, nn = st->n_noseq;
-  const LdRing R = ld_ring(smem, s_bar);
-  u16* vh = reinterpret_cast<u16*>(smem + ((RSI_LD_RING_BYTES + 15) & ~(size_t)15));
-  double* tab = reinterpret_cast<double*>(vh + (size_t)LD_NW * B_K * 32);
   const int tid = c.tid, lane = tid & 31, warp = tid >> 5;
-  for (int k = tid; k < LD_NW * B_K * 32 / 2; k += LD_NT) reinterpret_cast<u32*>(vh)[k] = 0u;
-  if (do_gc) for (int k = tid; k < GC_STRATA * 16; k += LD_NT) tab[k] = st->gc_tab[k >> 4];   // 16 copies: the lanes of a half-warp read 16 different banks pairs
-  u16* vcol = vh + (size_t)warp * B_K * 32 + lane;
+  unsigned char* wsm = smem + (size_t)warp * RSI_B_WARP_BYTES;
+  u32* gcb = reinterpret_cast<u32*>(wsm + 2 * W_STAGE);
+  u16* vh = reinterpret_cast<u16*>(wsm + 2 * W_STAGE + W_BITS);       // [B_K][32]
+  double* tab = reinterpret_cast<double*>(smem + (size_t)B_NW * RSI_B_WARP_BYTES);
+  int* nc = reinterpret_cast<int*>(tab + GC_STRATA * 16);               // beg[B_NCACHE] | end[B_NCACHE] | cum[B_NCACHE]
+  u64* bar = s_bar + warp * 2;
+  for (int k = lane; k < B_K * 16; k += 32) reinterpret_cast<u32*>(vh)[k] = 0u;
+  if (do_gc) for (int k = tid; k < GC_STRATA * 16; k += B_NT) tab[k] = st->gc_tab[k >> 4];   // 16 copies: the lanes of a half-warp read 16 different bank pairs
+  const bool ncached = nn <= B_NCACHE;
+  if (ncached) for (int k = tid; k < nn; k += B_NT) { nc[k] = nbeg[k]; nc[B_NCACHE + k] = nend[k]; nc[2 * B_NCACHE + k] = ncum[k]; }
+  const int* nb_ = ncached ? nc : nbeg; const int* ne_ = ncached ? nc + B_NCACHE : nend; const int* nm_ = ncached ? nc + 2 * B_NCACHE : ncum;
+  if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
+  c.sync();
+  u16* vcol = vh + lane;
   const double* tcol = tab + (lane & 15);
   const double mean = st->rdmean;
   const int hb = st->hist_base, s20 = st->s20, r20 = st->r20, gstar = st->gstar;
   const int q0 = s20 + r20 - GC_WIN;   // first overwritten position of the pseudo-slice (r20 >= 2)
+  const int removed_all = nn ? nm_[nn - 1] + (ne_[nn - 1] - nb_[nn - 1] + 1) : 0;
   int bad = 0;
   u32 zeros = 0;
-  const int ntiles = (L + LD_T - 1) / LD_T;
-  if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
-  c.sync();
-  if (tid == 0)
-    for (int s = 0; s < 2; ++s) { const int t = (int)blockIdx.x + s * (int)gridDim.x; if (t < ntiles) ld_issue(R, s, t, rd, fa, do_gc); }
+  int kn = 0;                          // first N interval that ends at or after the current warp-tile (tiles are visited in increasing order)
+  const int nwt = (L + W_T - 1) / W_T;
+  const int gw = (int)blockIdx.x * B_NW + warp, GW = (int)gridDim.x * B_NW;
+  if (lane == 0)
+    for (int s = 0; s < 2; ++s) { const int t = gw + s * GW; if (t < nwt) w_issue(wsm + s * W_STAGE, &bar[s], t, rd, fa, do_gc); }
+  auto count_slow = [&](int x) {       // value histogram, general form
+    const unsigned w = (unsigned)(x - hb);
+    if (w < (unsigned)B_K) vcol[w * 32] += 1;
+    else if (x == 0) zeros += 1;                       // zeros below the window (N stretches): counted in a register
+    else if (x >= HIST_ALL_BINS || x < 0) bad = 1;
+    else atomicAdd(&hist_all[x], 1u);
+  };
   int it = 0;
-  for (int tile = (int)blockIdx.x; tile < ntiles; tile += (int)gridDim.x, ++it) {
+  for (int wt = gw; wt < nwt; wt += GW, ++it) {
     const int s = it & 1;
-    mbar_wait(&R.bar[s], (u32)(it >> 1) & 1u);
-    const int t0 = tile * LD_T, t1 = imin(t0 + LD_T, L);
-    if (tid == 0) {  // first interval that ends at or after t0
-      int lo = 0, hi = nn;
-      while (lo < hi) { int mid = (lo + hi) >> 1; if (nend[mid] < t0) lo = mid + 1; else hi = mid; }
-      s_k0 = lo; s_hasn = (lo < nn && nbeg[lo] < t1) ? 1 : 0;
-    }
-    if (do_gc) ld_gc_bits(R, s, tile, tid);
-    c.sync();
-    int* x4 = R.st[s].rd + tid * LD_CH;
-    const int p0 = t0 + tid * LD_CH;
-    auto count = [&](int x) {     // value histogram over every position (N bases included)
-      const unsigned w = (unsigned)(x - hb);
-      if (w < (unsigned)B_K) vcol[w * 32] += 1;
-      else if (x == 0) zeros += 1;                       // zeros below the window (N stretches): counted in a register
-      else if (x >= HIST_ALL_BINS || x < 0) bad = 1;
-      else atomicAdd(&hist_all[x], 1u);
-    };
-    if (!do_gc) {
-      for (int j = 0; j < LD_CH && p0 + j < L; ++j) count(x4[j]);
-    } else if (p0 + LD_CH <= s20 && p0 >= GC_WIN / 2 && p0 + LD_CH - 1 <= L - GC_WIN / 2 - 2 && !(r20 >= 2 && p0 + LD_CH > q0 && p0 < q0 + r20)) {
-      const int q = tid * LD_CH;
-      int g = ld_gc_count(R.gcb, q + LD_FPAD - GC_WIN / 2);
-      const u32 inw = ld_bits32(R.gcb, q + LD_FPAD + GC_WIN / 2 + 1), outw = ld_bits32(R.gcb, q + LD_FPAD - GC_WIN / 2);
+    unsigned char* stage = wsm + s * W_STAGE;
+    mbar_wait(&bar[s], (u32)(it >> 1) & 1u);
+    const int w0 = wt * W_T, w1 = imin(w0 + W_T, L);
+    if (do_gc) { w_gc_bits(stage + (size_t)W_T * 4, gcb, wt, lane); __syncwarp(); }
+    int* x4 = reinterpret_cast<int*>(stage) + lane * W_CH;
+    const int p0 = w0 + lane * W_CH;
+    const bool quirk = r20 >= 2 && w0 + W_T > q0 && w0 < q0 + r20;
+    if (w0 + W_T <= L && (!do_gc || (w_interior(w0, L) && w0 + W_T <= s20 && !quirk))) {
+      // ---- fast path: straight-line code for 28 bases
+      int xs[W_CH];
 #pragma unroll
-      for (int j4 = 0; j4 < LD_CH / 4; ++j4) {
-        int4 v = *reinterpret_cast<const int4*>(x4 + j4 * 4);
-        int xs[4] = {v.x, v.y, v.z, v.w};
+      for (int j4 = 0; j4 < W_CH / 4; ++j4) {
+        const int4 v = *reinterpret_cast<const int4*>(x4 + j4 * 4);
+        xs[j4 * 4] = v.x; xs[j4 * 4 + 1] = v.y; xs[j4 * 4 + 2] = v.z; xs[j4 * 4 + 3] = v.w;
+      }
+      if (do_gc) {
+        const int q = lane * W_CH;
+        const int g0 = w_gc_count(gcb, q + W_FL - GC_WIN / 2);
+        const u32 inw = w_bits32(gcb, q + W_FL + GC_WIN / 2 + 1), outw = w_bits32(gcb, q + W_FL - GC_WIN / 2);
+        const u32 plus = inw & ~outw, minus = outw & ~inw;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int j = j4 * 4 + k;
-          xs[k] = (int)(__dadd_rn(__ddiv_rn(__dmul_rn((double)xs[k], mean), tcol[g * 16]), 0.5));
-          count(xs[k]);
-          g += (int)((inw >> j) & 1u) - (int)((outw >> j) & 1u);
+        for (int j = 0; j < W_CH; ++j) {
+          const u32 mk = (1u << j) - 1u;
+          const int g = g0 + __popc(plus & mk) - __popc(minus & mk);
+          xs[j] = (int)(__dadd_rn(__ddiv_rn(__dmul_rn((double)xs[j], mean), tcol[g * 16]), 0.5));
         }
-        *reinterpret_cast<int4*>(x4 + j4 * 4) = make_int4(xs[0], xs[1], xs[2], xs[3]);
+#pragma unroll
+        for (int j4 = 0; j4 < W_CH / 4; ++j4) *reinterpret_cast<int4*>(x4 + j4 * 4) = make_int4(xs[j4 * 4], xs[j4 * 4 + 1], xs[j4 * 4 + 2], xs[j4 * 4 + 3]);
+      }
+      // value histogram: branch-free pipelined updates of the lane's column (the spare slot B_K * 32 takes what is outside the window)
+      u32 ovf = 0;
+      unsigned wv = (unsigned)(xs[0] - hb);
+      unsigned re = wv < (unsigned)B_K ? wv : (unsigned)B_K;
+      ovf |= wv < (unsigned)B_K ? 0u : 1u;
+      u32 e = vcol[re * 32];
+#pragma unroll
+      for (int j = 0; j < W_CH; ++j) {
+        u32 en = 0; unsigned rn = re;
+        if (j + 1 < W_CH) {
+          const unsigned nw_ = (unsigned)(xs[j + 1] - hb);
+          rn = nw_ < (unsigned)B_K ? nw_ : (unsigned)B_K;
+          ovf |= nw_ < (unsigned)B_K ? 0u : (2u << j);
+          en = vcol[rn * 32];
+        }
+        e += 1;
+        vcol[re * 32] = (u16)e;
+        e = rn == re ? e : en;
+        re = rn;
+      }
+      if (ovf) {
+        for (u32 m = ovf; m; m &= m - 1) {
+          const int x = x4[__ffs((int)m) - 1];      // (from the stage, which holds the adjusted values)
+          if (x == 0) zeros += 1;
+          else if (x >= HIST_ALL_BINS || x < 0) bad = 1;
+          else atomicAdd(&hist_all[x], 1u);
+        }
       }
     } else {
-      for (int j = 0; j < LD_CH && p0 + j < L; ++j) {
+      for (int j = 0; j < W_CH && p0 + j < L; ++j) {
         const int p = p0 + j;
         int x = x4[j];
-        if (p < s20) {
+        if (do_gc && p < s20) {
           int g;
           if (r20 >= 2 && p >= q0 && p < q0 + r20) { x = rd[p + GC_WIN - r20]; g = gstar; }
-          else g = ld_gc_count(R.gcb, gc_lo(p, L) - t0 + LD_FPAD);
+          else g = w_gc_count(gcb, gc_lo(p, L) - w0 + W_FL);
           x = (int)(__dadd_rn(__ddiv_rn(__dmul_rn((double)x, mean), tcol[g * 16]), 0.5));
           x4[j] = x;
         }
-        count(x);
+        count_slow(x);
       }
     }
-    c.sync();
-    // N-compacted store of the tile: coalesced, 16 bytes per thread where the tile has no N interval
+    __syncwarp();
+    // ---- N-compacted store of the warp-tile, coalesced
     {
-      const int* tile_rd = R.st[s].rd;
-      const int k0 = s_k0, hasn = s_hasn, np = t1 - t0;
-      const int shift0 = k0 < nn ? ncum[k0] : (nn ? ncum[nn - 1] + (nend[nn - 1] - nbeg[nn - 1] + 1) : 0);
+      const int* tile_rd = reinterpret_cast<const int*>(stage);
+      while (kn < nn && ne_[kn] < w0) ++kn;
+      const bool hasn = kn < nn && nb_[kn] < w1;
+      const int shift0 = kn < nn ? nm_[kn] : removed_all;
+      const int np = w1 - w0;
       if (!hasn) {
-        int* dst = rdc + (t0 - shift0);
-        const int a = (int)((4 - ((size_t)(t0 - shift0) & 3)) & 3);      // elements up to the first 16-byte aligned destination
+        int* dst = rdc + (w0 - shift0);
+        const int a = (int)((4 - ((size_t)(w0 - shift0) & 3)) & 3);      // elements up to the first 16-byte aligned destination
         const int nv = np > a ? (np - a) >> 2 : 0;
-        if (tid < a && tid < np) dst[tid] = tile_rd[tid];
-        for (int v = tid; v < nv; v += LD_NT) {
+        if (lane < a && lane < np) dst[lane] = tile_rd[lane];
+        for (int v = lane; v < nv; v += 32) {
           const int q = a + v * 4;
           *reinterpret_cast<int4*>(dst + q) = make_int4(tile_rd[q], tile_rd[q + 1], tile_rd[q + 2], tile_rd[q + 3]);
         }
-        for (int q = a + nv * 4 + tid; q < np; q += LD_NT) dst[q] = tile_rd[q];
+        for (int q = a + nv * 4 + lane; q < np; q += 32) dst[q] = tile_rd[q];
       } else {
-        for (int q = tid; q < np; q += LD_NT) {
-          const int p = t0 + q;
-          int k = k0, sh = shift0;
-          while (k < nn && nend[k] < p) { sh += nend[k] - nbeg[k] + 1; ++k; }
-          if (!(k < nn && p >= nbeg[k])) rdc[p - sh] = tile_rd[q];
+        for (int q = lane; q < np; q += 32) {
+          const int p = w0 + q;
+          int k = kn, sh = shift0;
+          while (k < nn && ne_[k] < p) { sh += ne_[k] - nb_[k] + 1; ++k; }
+          if (!(k < nn && p >= nb_[k])) rdc[p - sh] = tile_rd[q];
         }
       }
     }
-    c.sync();
-    const int t2 = tile + 2 * (int)gridDim.x;
-    if (tid == 0 && t2 < ntiles) ld_issue(R, s, t2, rd, fa, do_gc);
+    __syncwarp();
+    const int t2 = wt + 2 * GW;
+    if (lane == 0 && t2 < nwt) w_issue(stage, &bar[s], t2, rd, fa, do_gc);
   }
-  c.sync();
-  for (int w = tid; w < B_K; w += LD_NT) {
+  __syncwarp();
+  // flush the warp's private histogram: lane w sums row w over the 32 columns
+  for (int w = lane; w < B_K; w += 32) {
     u32 sum = 0;
-    for (int k = 0; k < LD_NW; ++k)
-      for (int l = 0; l < 32; ++l) sum += vh[((size_t)k * B_K + w) * 32 + ((l + tid) & 31)];
-    if (sum) atomicAdd(&hist_all[hb + w], sum);
+    for (int l = 0; l < 32; ++l) sum += vh[(size_t)w * 32 + ((l + lane) & 31)];
+    if (sum) { if (hb + w < HIST_ALL_BINS) atomicAdd(&hist_all[hb + w], sum); else bad = 1; }
   }
   bad = c.reduce(bad, MaxOp());
   zeros = c.reduce(zeros, SumOp());

@@ -242,6 +242,7 @@ __global__ void __launch_bounds__(1024) k_cand_final(CandArgs A, CandSpec X, Clu
     if (c.nctas == 1) { S.shist = reinterpret_cast<unsigned*>(smem + 33 * 16 + 32 * 8); S.shist_cap = CAND_SHIST; S.hist = nullptr; S.hist_cap = 0; }
     else { S.shist = nullptr; S.shist_cap = 0; S.hist = G.ghist + (size_t)cid * CAND_CL_HIST; S.hist_cap = CAND_CL_HIST; }
     S.ref = X.ref + X.off[j]; S.pref = X.pref + X.off[j] + j; S.rm = X.rm + X.off[j];
+    S.sub = A.S.sub + (size_t)(1 + cid) * A.S.sub_cap;      // concurrent calls must not share the sub-sampling buffer
     S.ref_cap = (int)(X.off[j + 1] - X.off[j]) - 8;
     S.prof = cid == 0 ? A.S.prof : nullptr;
     cand_final_one(c, P, S, A.rdc, st->Lc, A.segs, nl, j, X.res);

@@ -214,6 +214,7 @@ int set_smem_attrs(int device) {
   cudaFuncSetAttribute(k_gc_table, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_A);
   cudaFuncSetAttribute(k_gc_adjust, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_B);
   cudaFuncSetAttribute(k_bins, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_C);
+  cudaFuncSetAttribute(k_bins_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_CW);
   cudaFuncSetAttribute(k_cand_a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_CAND_A);
   cudaFuncSetAttribute(k_cand_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CAND_SHIST * 4));
   cudaFuncSetAttribute(k_cand_c, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CAND_SHIST * 4));
@@ -323,7 +324,7 @@ int rsigpu_create(int device, const rsigpu_params* p, rsigpu_ctx** out) {
        && c->d_cchunk.ensure((size_t)(CHN_N + 8) * sizeof(ChainChunk) / 8 + 8) == cudaSuccess
        && c->d_clx.ensure((size_t)32 * CTA_GX_BYTES / 8 + 8) == cudaSuccess && c->d_clbc.ensure(32 * 32 + 8) == cudaSuccess
        && c->d_clhist.ensure((size_t)32 * CAND_CL_HIST + 8) == cudaSuccess;
-  ok = ok && c->d_chist_c.ensure(1u << 22) == cudaSuccess && c->d_sub.ensure((size_t)p->maxchkbp * 10 + 64) == cudaSuccess;
+  ok = ok && c->d_chist_c.ensure(1u << 22) == cudaSuccess && c->d_sub.ensure(((size_t)p->maxchkbp * 10 + 64) * 33) == cudaSuccess;
   ok = ok && c->d_nrun_beg.ensure(1 << 20) == cudaSuccess && c->d_nrun_end.ensure(1 << 20) == cudaSuccess;
   if (ok) ok = cudaMemsetAsync(c->d_fq_hist.p, 0, ((size_t)FQ_BINS_CAP + 8) * 4, c->stream) == cudaSuccess;
   if (!ok) { rsigpu_destroy(c); return RSIGPU_E_CUDA; }
@@ -409,7 +410,7 @@ int rsigpu_set_reference(rsigpu_ctx* c, const uint8_t* fasta, int32_t len, int32
     long long nseq = 0; for (int k = 0; k < hn[0]; ++k) nseq += e[k] - b[k] + 1;
     nseq = (long long)len - nseq;
     const int centre = nseq > 0 ? (int)((double)GC_WIN * (double)ngc / (double)nseq + 0.5) : GC_WIN / 2;
-    c->gc_base = std::max(0, std::min(centre - LD_ROWS / 2, (int)GC_STRATA - LD_ROWS));
+    c->gc_base = std::max(0, std::min(centre - A_ROWS / 2, (int)GC_STRATA - A_ROWS));
   }
   c->nb = c->Lc / c->P.m;
   if (c->nb < 64) { c->fail("fewer than 64 bins after N removal"); return RSIGPU_E_RANGE; }
@@ -729,16 +730,22 @@ int rsigpu_load_finish(rsigpu_ctx* c) {
   CK(cudaMemsetAsync(c->d_thist.p, 0, (size_t)CHIST_RCAP * 4, c->stream));
   CK(cudaMemsetAsync(c->d_misc.p, 0, 5 * 4, c->stream));
   const int* nbeg = c->d_nseq.p; const int* nend = nbeg + nn; const int* ncum = nbeg + 2 * nn;
-  const int ntiles = (L + LD_TILE - 1) / LD_TILE;
   const size_t smA = RSI_SMEM_A, smB = RSI_SMEM_B;
-  KL(k_gc_table, std::min(ntiles, c->n_sm), LD_NT, smA, c->d_raw.p, c->d_fasta.p, c->d_st);
+  const int nwt = (L + W_T - 1) / W_T;     // warp-tiles: every warp of the two per-base passes is its own pipeline
+  KL(k_gc_table, std::min((nwt + A_NW - 1) / A_NW, c->n_sm), A_NT, smA, c->d_raw.p, c->d_fasta.p, c->d_st);
   KL(k_gc_finalize, 1, 256, 0, c->d_fasta.p, c->d_st);
-  KL(k_gc_adjust, std::min(ntiles, c->n_sm), LD_NT, smB, c->d_raw.p, c->d_fasta.p, c->d_rdc.p, nbeg, nend, ncum, c->d_hist_all.p, c->d_st);
+  KL(k_gc_adjust, std::min((nwt + B_NW - 1) / B_NW, c->n_sm), B_NT, smB, c->d_raw.p, c->d_fasta.p, c->d_rdc.p, nbeg, nend, ncum, c->d_hist_all.p, c->d_st);
   KL(k_cap_params, 1, 1024, 0, c->d_hist_all.p, c->d_st, CHIST_RCAP);
   const int bpt = std::max(1, std::min((int)C_BINS, (C_CAP - 4) / m));     // bpt * m + 3 words fit a stage
   const int ntc = std::max(1, (nb + bpt - 1) / bpt + 1);
-  KL(k_bins, std::min(ntc, c->n_sm), C_NT, RSI_SMEM_C, c->d_rdc.p, c->d_bin_med.p, c->d_bin_medint.p, c->d_bin_sum.p, c->d_chist.p,
-     c->d_thist.p, c->d_st, bpt);
+  if (m <= 127) {   // every warp its own pipeline: warp-tiles of CW_BINS bins
+    const int nwtc = (nb + CW_BINS - 1) / CW_BINS + 1;
+    KL(k_bins_warp, std::min((nwtc + CW_NW - 1) / CW_NW, c->n_sm), CW_NT, RSI_SMEM_CW, c->d_rdc.p, c->d_bin_med.p, c->d_bin_medint.p, c->d_bin_sum.p, c->d_chist.p,
+       c->d_thist.p, c->d_st);
+  } else {
+    KL(k_bins, std::min(ntc, c->n_sm), C_NT, RSI_SMEM_C, c->d_rdc.p, c->d_bin_med.p, c->d_bin_medint.p, c->d_bin_sum.p, c->d_chist.p,
+       c->d_thist.p, c->d_st, bpt);
+  }
   KL(k_chr_stats, 1, 1024, 0, c->d_chist.p, c->d_thist.p, c->d_tothist.p, c->d_st);
   CK(cudaMemcpyAsync(h, c->d_st, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
@@ -808,7 +815,7 @@ int rsigpu_detectcnv(rsigpu_ctx* c) {
   A.segs = c->list(0); A.tmp = c->list(1); A.ov = c->list(2);
   A.d_segments = c->list(3); A.d_blocks = c->list(4); A.d_premerge = c->list(5); A.d_merged = c->list(6); A.d_detected = c->list(7); A.d_calls = c->list(8);
   A.n_dump = c->d_misc.p; A.list_cap = LIST_CAP;
-  A.S.ref = c->d_ref.p; A.S.ref_cap = (int)std::min<size_t>(c->d_ref.cap, 0x7fffffff); A.S.sub = c->d_sub.p; A.S.sub_cap = (int)c->d_sub.cap;
+  A.S.ref = c->d_ref.p; A.S.ref_cap = (int)std::min<size_t>(c->d_ref.cap, 0x7fffffff); A.S.sub = c->d_sub.p; A.S.sub_cap = c->P.maxchkbp * 10 + 64;   // slice 0; the per-call cluster kernels use slice 1 + cluster id
   A.S.pref = c->d_pref.p; A.S.rm = c->d_rm.p; A.S.hist = c->d_chist_c.p; A.S.hist_cap = (int)c->d_chist_c.cap; A.S.err = c->d_misc.p + 4; A.S.prof = c->profile ? c->d_cprof.p : nullptr;
   if (c->profile) CK(cudaMemsetAsync(c->d_cprof.p, 0, 16 * 8, c->stream));
   A.maxchkbp = c->P.maxchkbp; A.merge = c->P.merge; A.tid = c->tid; A.chklen = c->P.chklen;
