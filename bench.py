@@ -106,6 +106,9 @@ def genome_contigs(scale: float):
 
 # algorithmic HBM bytes of one launch of each streaming kernel; L = contig, Lc = after N removal
 def kernel_bytes(name: str, L: int, Lc: int, reads_bytes: int = 0, qual_bytes: int = 0):
+    name = name.split("<")[0]
+    if name == "k_bins_warp":
+        name = "k_bins"           # the warp-pipelined form of pass C (bins of <= 127 bases)
     return {
         "k_qual_mask": qual_bytes,        # every base quality once (the 1-bit-per-base mask it writes is overhead, not counted)
         "k_gc_table": 5 * L,          # depth 4 + FASTA 1, read once

@@ -237,16 +237,25 @@ __device__ __noinline__ void inf_block_header(InfState& S, const InfTabs& T) {
   S.phase = INF_SYMS;
 }
 
+// One step of a lane: up to INF_LITS literals (most symbols of BAM data are literals: bases, names, fields), ended early by
+// a length symbol -- whose match is then copied by the whole warp -- or by the end of the deflate block.  Several literals
+// per step amortise the per-step costs of the warp (re-convergence, the search for pending matches, the copy rounds).
+#ifndef INF_LITS
+#define INF_LITS 4
+#endif
 __device__ __forceinline__ void inf_symbol(InfState& S, const InfTabs& T, const u16* tab) {
   BitIn& b = S.b;
-  bits_refill(b);
-  int sym = inf_decode(b, T, INF_LF, INF_FB, INF_LC, INF_LS, INF_LX, INF_SB);
-  if (sym < 256) {
+  int sym = 0;
+#pragma unroll 1
+  for (int rep = 0; rep < INF_LITS; ++rep) {
+    bits_refill(b);
+    sym = inf_decode(b, T, INF_LF, INF_FB, INF_LC, INF_LS, INF_LX, INF_SB);
+    if (sym >= 256) break;
     if (sym < 0) return inf_fail(S, 13);
     if (S.o >= S.dst_len) return inf_fail(S, 3);
     S.dst[S.o++] = (u8)sym;
-    return;
   }
+  if (sym < 256) return;
   if (sym == 256) {
     if (b.pos > b.end + 16) return inf_fail(S, 17);
     if (S.last) { S.rc = S.o == S.dst_len ? 0 : 18; S.phase = INF_DONE; } else S.phase = INF_HEADER;

@@ -197,6 +197,8 @@ __global__ void __launch_bounds__(C_NT) k_bins(int* __restrict__ rdc, float* __r
 enum { CW_NW = 8, CW_NT = CW_NW * 32, CW_BINS = 16 /* one bin per lane pair */, CW_CAP = 2048 /* words per stage >= 16 * 127 + 3 */ };
 #define RSI_CW_WARP_BYTES ((size_t)2 * CW_CAP * 4 + (size_t)MAD_CLASSES * C_KP * 2 + 4)
 #define RSI_SMEM_CW ((size_t)CW_NW * RSI_CW_WARP_BYTES)
+// M: the bin size as a compile-time constant (101 = the default, 51), or 0 = read it from the state (any odd m <= 127)
+template <int M>
 __global__ void __launch_bounds__(CW_NT) k_bins_warp(int* __restrict__ rdc, float* __restrict__ bin_med, int* __restrict__ bin_medint,
                                                       i64* __restrict__ bin_sum, u32* chist, u32* thist, DevState* st) {
   RSI_DYN_SMEM(smem);
@@ -206,7 +208,7 @@ __global__ void __launch_bounds__(CW_NT) k_bins_warp(int* __restrict__ rdc, floa
   unsigned char* wsm = smem + (size_t)warp * RSI_CW_WARP_BYTES;
   u16* wt_ = reinterpret_cast<u16*>(wsm + 2 * CW_CAP * 4);     // [MAD_CLASSES][C_KP]
   u64* bar = s_bar + warp * 2;
-  const int Lc = st->Lc, m = st->m, nb = st->nb, R = st->chist_R, cap_on = st->cap_on, capv = st->capv;
+  const int Lc = st->Lc, m = M ? M : st->m, nb = st->nb, R = st->chist_R, cap_on = st->cap_on, capv = st->capv;
   const double thr = st->cap_thr;
   const int sub31 = MAD_CLASSES * (Lc / MAD_CLASSES);
   int wb = 0;
@@ -235,13 +237,25 @@ __global__ void __launch_bounds__(CW_NT) k_bins_warp(int* __restrict__ rdc, floa
       int cls = T.B % MAD_CLASSES + lane; if (cls >= MAD_CLASSES) cls -= MAD_CLASSES;
       u16* row = wt_ + cls * C_KP;
       u32* grow = chist + (size_t)cls * R;
-      for (int q = lane; q < T.np; q += 31) {
-        int v = vals[q];
-        if (cap_on && v > ithr) { v = capv; vals[q] = capv; rdc[T.B + q] = capv; }
-        const unsigned w = (unsigned)(v - wb);
-        if (T.B + q >= sub31) { if (v >= 0 && v < R) atomicAdd(&thist[v], 1u); }
-        else if (w < (unsigned)C_K) row[w] += 1;
-        else if (v >= 0 && v < R) atomicAdd(&grow[v], 1u);
+      const int icap = cap_on ? ithr : 0x7fffffff;
+      if (T.B + T.np <= sub31) {            // every tile but the contig's last ones
+#pragma unroll 4
+        for (int q = lane; q < T.np; q += 31) {
+          int v = vals[q];
+          if (v > icap) { v = capv; vals[q] = capv; rdc[T.B + q] = capv; }
+          const unsigned w = (unsigned)(v - wb);
+          if (w < (unsigned)C_K) row[w] += 1;
+          else if (v >= 0 && v < R) atomicAdd(&grow[v], 1u);
+        }
+      } else {
+        for (int q = lane; q < T.np; q += 31) {
+          int v = vals[q];
+          if (v > icap) { v = capv; vals[q] = capv; rdc[T.B + q] = capv; }
+          const unsigned w = (unsigned)(v - wb);
+          if (T.B + q >= sub31) { if (v >= 0 && v < R) atomicAdd(&thist[v], 1u); }
+          else if (w < (unsigned)C_K) row[w] += 1;
+          else if (v >= 0 && v < R) atomicAdd(&grow[v], 1u);
+        }
       }
     }
     __syncwarp();

@@ -159,6 +159,7 @@ __global__ void __launch_bounds__(A_NT) k_gc_table(const int* __restrict__ rd, c
   if (lane == 0)
     for (int s = 0; s < 2; ++s) { const int t = gw + s * GW; if (t < nwt) w_issue(wsm + s * W_STAGE, &bar[s], t, rd, fa, do_gc); }
   u64 psum = 0, pcnt = 0;
+  u64 zsum = 0; u32 zcnt = 0;          // stratum 0 (windows without any G/C: the N stretches) is kept in registers
   int vmin = 0x7fffffff, vmax = -0x7fffffff - 1;
   int it = 0;
   for (int wt = gw; wt < nwt; wt += GW, ++it) {
@@ -209,12 +210,18 @@ __global__ void __launch_bounds__(A_NT) k_gc_table(const int* __restrict__ rd, c
           e = rn == re ? e : en;
           re = rn;
         }
-        if (ovf) {                                 // rare: strata outside the private window
-          for (u32 m = ovf; m; m &= m - 1) {
-            const int j = __ffs((int)m) - 1;
-            const u32 mk = (1u << j) - 1u;
-            const int g = g0 + gbase + __popc(plus & mk) - __popc(minus & mk);
-            atomicAdd(&osum[g], (u64)((u32)x4[j] & 0xffffffu)); atomicAdd(&ocnt[g], 1u);      // (from the stage: a dynamic index would push xs[] to local memory)
+        if (ovf) {                                 // strata outside the private window
+          if (gbase > 0 && g0 + gbase == 0 && plus == 0u) {      // a chunk inside an N stretch: every window is empty
+            zsum += tsum; zcnt += W_CH;                           // (tsum: depths are >= 0 or the contig is rejected)
+          } else {
+            for (u32 m = ovf; m; m &= m - 1) {
+              const int j = __ffs((int)m) - 1;
+              const u32 mk = (1u << j) - 1u;
+              const int g = g0 + gbase + __popc(plus & mk) - __popc(minus & mk);
+              const u32 xv = (u32)x4[j] & 0xffffffu;     // (from the stage: a dynamic index would push xs[] to local memory)
+              if (g == 0) { zsum += xv; zcnt += 1; }
+              else { atomicAdd(&osum[g], (u64)xv); atomicAdd(&ocnt[g], 1u); }
+            }
           }
         }
       }
@@ -228,6 +235,7 @@ __global__ void __launch_bounds__(A_NT) k_gc_table(const int* __restrict__ rd, c
           const int g = w_gc_count(gcb, gc_lo(p, L) - w0 + W_FL);
           const unsigned row = (unsigned)(g - gbase);
           if (row < (unsigned)A_ROWS) col[row * 32] += (1ull << 40) | (u64)((u32)x & 0xffffffu);
+          else if (g == 0) { zsum += (u32)x & 0xffffffu; zcnt += 1; }
           else { atomicAdd(&osum[g], (u64)((u32)x & 0xffffffu)); atomicAdd(&ocnt[g], 1u); }
         }
       }
@@ -239,6 +247,8 @@ __global__ void __launch_bounds__(A_NT) k_gc_table(const int* __restrict__ rd, c
   }
   c.sync();
   if (do_gc) {
+    zsum = c.reduce(zsum, SumOp()); zcnt = c.reduce(zcnt, SumOp());
+    if (tid == 0 && zcnt) { atomicAdd(&osum[0], zsum); atomicAdd(&ocnt[0], zcnt); }
     // column sums of the private tables: thread (row, part) adds A_NW / 4 warps x 32 lanes of its row into the block table
     {
       const int row = tid & (A_ROWS - 1), part = tid / A_ROWS;          // A_NT / A_ROWS = 4 parts

@@ -214,7 +214,9 @@ int set_smem_attrs(int device) {
   cudaFuncSetAttribute(k_gc_table, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_A);
   cudaFuncSetAttribute(k_gc_adjust, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_B);
   cudaFuncSetAttribute(k_bins, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_C);
-  cudaFuncSetAttribute(k_bins_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_CW);
+  cudaFuncSetAttribute(k_bins_warp<101>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_CW);
+  cudaFuncSetAttribute(k_bins_warp<51>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_CW);
+  cudaFuncSetAttribute(k_bins_warp<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_CW);
   cudaFuncSetAttribute(k_cand_a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_CAND_A);
   cudaFuncSetAttribute(k_cand_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CAND_SHIST * 4));
   cudaFuncSetAttribute(k_cand_c, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CAND_SHIST * 4));
@@ -740,8 +742,10 @@ int rsigpu_load_finish(rsigpu_ctx* c) {
   const int ntc = std::max(1, (nb + bpt - 1) / bpt + 1);
   if (m <= 127) {   // every warp its own pipeline: warp-tiles of CW_BINS bins
     const int nwtc = (nb + CW_BINS - 1) / CW_BINS + 1;
-    KL(k_bins_warp, std::min((nwtc + CW_NW - 1) / CW_NW, c->n_sm), CW_NT, RSI_SMEM_CW, c->d_rdc.p, c->d_bin_med.p, c->d_bin_medint.p, c->d_bin_sum.p, c->d_chist.p,
-       c->d_thist.p, c->d_st);
+    const int gcw = std::min((nwtc + CW_NW - 1) / CW_NW, c->n_sm);
+    if (m == 101) KL(k_bins_warp<101>, gcw, CW_NT, RSI_SMEM_CW, c->d_rdc.p, c->d_bin_med.p, c->d_bin_medint.p, c->d_bin_sum.p, c->d_chist.p, c->d_thist.p, c->d_st);
+    else if (m == 51) KL(k_bins_warp<51>, gcw, CW_NT, RSI_SMEM_CW, c->d_rdc.p, c->d_bin_med.p, c->d_bin_medint.p, c->d_bin_sum.p, c->d_chist.p, c->d_thist.p, c->d_st);
+    else KL(k_bins_warp<0>, gcw, CW_NT, RSI_SMEM_CW, c->d_rdc.p, c->d_bin_med.p, c->d_bin_medint.p, c->d_bin_sum.p, c->d_chist.p, c->d_thist.p, c->d_st);
   } else {
     KL(k_bins, std::min(ntc, c->n_sm), C_NT, RSI_SMEM_C, c->d_rdc.p, c->d_bin_med.p, c->d_bin_medint.p, c->d_bin_sum.p, c->d_chist.p,
        c->d_thist.p, c->d_st, bpt);
