@@ -179,36 +179,55 @@ __global__ void __launch_bounds__(A_NT) k_gc_table(const int* __restrict__ rd, c
         const int4 v = *reinterpret_cast<const int4*>(x4 + j4 * 4);
         xs[j4 * 4] = v.x; xs[j4 * 4 + 1] = v.y; xs[j4 * 4 + 2] = v.z; xs[j4 * 4 + 3] = v.w;
       }
+      // depth statistics: a depth outside [0, 2^24) rejects the contig, so the OR of the words is enough as a range check
+      // (any negative word sets the sign bit, any word >= 2^24 a bit above 23) and the sums may assume x >= 0
+      int orx = 0;
 #pragma unroll
-      for (int j = 0; j < W_CH; ++j) {
-        const int x = xs[j];
-        vmin = imin(vmin, x); vmax = imax(vmax, x);
-        tsum += (u32)imax(x, 0); tcnt += x > 0 ? 1u : 0u;
-      }
+      for (int j = 0; j < W_CH; ++j) { const int x = xs[j]; orx |= x; tsum += (u32)x; tcnt += (u32)imin(x, 1); }
+      vmin = imin(vmin, orx < 0 ? -1 : 0); vmax = imax(vmax, orx < 0 ? 0x7fffffff : orx);
       if (do_gc) {
         const int q = lane * W_CH;               // p - w0; bit index of base p is q + W_FL
         const int g0 = w_gc_count(gcb, q + W_FL - GC_WIN / 2) - gbase;
         const u32 inw = w_bits32(gcb, q + W_FL + GC_WIN / 2 + 1), outw = w_bits32(gcb, q + W_FL - GC_WIN / 2);
         const u32 plus = inw & ~outw, minus = outw & ~inw;      // the window count moves by bit(p+101) - bit(p-100) per base
         u32 ovf = 0;
-        unsigned row = (unsigned)g0;
-        unsigned re = row < (unsigned)A_ROWS ? row : (unsigned)A_ROWS;
-        ovf |= row < (unsigned)A_ROWS ? 0u : 1u;
-        u64 e = col[re * 32];
+        if (g0 - __popc(minus) >= 0 && g0 + __popc(plus) < A_ROWS) {
+          // the whole chunk stays inside the private window (the count moves at most popc(minus) down, popc(plus) up): no clamping
+          unsigned re = (unsigned)g0;
+          u64 e = col[re * 32];
 #pragma unroll
-        for (int j = 0; j < W_CH; ++j) {
-          u64 en = 0; unsigned rn = re;
-          if (j + 1 < W_CH) {
-            const u32 mk = (2u << j) - 1u;
-            const unsigned nrow = (unsigned)(g0 + __popc(plus & mk) - __popc(minus & mk));
-            rn = nrow < (unsigned)A_ROWS ? nrow : (unsigned)A_ROWS;
-            ovf |= nrow < (unsigned)A_ROWS ? 0u : (2u << j);
-            en = col[rn * 32];                     // issued before the store below
+          for (int j = 0; j < W_CH; ++j) {
+            u64 en = 0; unsigned rn = re;
+            if (j + 1 < W_CH) {
+              const u32 mk = (2u << j) - 1u;
+              rn = (unsigned)(g0 + __popc(plus & mk) - __popc(minus & mk));
+              en = col[rn * 32];                     // issued before the store below
+            }
+            e += (1ull << 40) | (u64)(u32)xs[j];
+            col[re * 32] = e;
+            e = rn == re ? e : en;
+            re = rn;
           }
-          e += (1ull << 40) | (u64)((u32)xs[j] & 0xffffffu);
-          col[re * 32] = e;
-          e = rn == re ? e : en;
-          re = rn;
+        } else {
+          unsigned row = (unsigned)g0;
+          unsigned re = row < (unsigned)A_ROWS ? row : (unsigned)A_ROWS;
+          ovf |= row < (unsigned)A_ROWS ? 0u : 1u;
+          u64 e = col[re * 32];
+#pragma unroll
+          for (int j = 0; j < W_CH; ++j) {
+            u64 en = 0; unsigned rn = re;
+            if (j + 1 < W_CH) {
+              const u32 mk = (2u << j) - 1u;
+              const unsigned nrow = (unsigned)(g0 + __popc(plus & mk) - __popc(minus & mk));
+              rn = nrow < (unsigned)A_ROWS ? nrow : (unsigned)A_ROWS;
+              ovf |= nrow < (unsigned)A_ROWS ? 0u : (2u << j);
+              en = col[rn * 32];
+            }
+            e += (1ull << 40) | (u64)((u32)xs[j] & 0xffffffu);
+            col[re * 32] = e;
+            e = rn == re ? e : en;
+            re = rn;
+          }
         }
         if (ovf) {                                 // strata outside the private window
           if (gbase > 0 && g0 + gbase == 0 && plus == 0u) {      // a chunk inside an N stretch: every window is empty
