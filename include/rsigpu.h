@@ -162,6 +162,14 @@ int rsigpu_sd_filters(rsigpu_ctx* c);    /* sd_filters, rsi.cpp:1753-1792 */
 int rsigpu_cnv_stat(rsigpu_ctx* c);      /* cnv_stat + bam_rd_pr_stats, pairrd.cpp:622-748, 112-260 (BAM input only) */
 int rsigpu_get_calls(rsigpu_ctx* c, rsigpu_cnv* out, int32_t cap, int32_t* n);  /* rows write_cnv_to_file would print */
 
+/* `rsicnv stat` (rsi.cpp:2235-2249): RP / Q0 of calls that come from a file instead of detectcnv.
+ *   reads_begin(tid, len)    stage reads of contig `tid` WITHOUT a reference (then rsigpu_pileup_push / rsigpu_bam_take as usual)
+ *   stat_calls(list, n)      cnv_stat + bam_rd_pr_stats (pairrd.cpp:622-748, 112-260) on the staged reads for the entries of
+ *                            `list` whose tid is this contig's; the list must be the WHOLE file's list in file order, because
+ *                            the search distance DIS is carried from call to call (pairrd.cpp:655-656).  rp / q0 are filled in place. */
+int rsigpu_reads_begin(rsigpu_ctx* c, int32_t tid, int32_t target_len);
+int rsigpu_stat_calls(rsigpu_ctx* c, rsigpu_cnv* list, int32_t n);
+
 /* Everything above on the staged inputs, one host synchronisation at the end. */
 int rsigpu_run(rsigpu_ctx* c, rsigpu_cnv* out, int32_t cap, int32_t* n);
 

@@ -71,7 +71,7 @@ EXPORTS = ("rsigpu_default_params", "rsigpu_create", "rsigpu_destroy", "rsigpu_l
            "rsigpu_set_depth", "rsigpu_pileup_begin", "rsigpu_pileup_push", "rsigpu_pileup_end", "rsigpu_load_finish", "rsigpu_detectcnv",
            "rsigpu_sd_filters", "rsigpu_cnv_stat", "rsigpu_get_calls", "rsigpu_run", "rsigpu_get_chr_stats", "rsigpu_get_array",
            "rsigpu_format_row", "rsigpu_launch_count", "rsigpu_last_stage_ms", "rsigpu_set_profile", "rsigpu_get_profile",
-           "rsigpu_set_level0_mode", "rsigpu_set_feed_limit", "rsigpu_set_cand_threads", "rsigpu_debug_state", "rsigpu_pileup_commit", "rsigpu_bam_begin", "rsigpu_bam_feed", "rsigpu_bam_take",
+           "rsigpu_reads_begin", "rsigpu_stat_calls", "rsigpu_set_level0_mode", "rsigpu_set_feed_limit", "rsigpu_set_cand_threads", "rsigpu_debug_state", "rsigpu_pileup_commit", "rsigpu_bam_begin", "rsigpu_bam_feed", "rsigpu_bam_take",
            "rsigpu_bam_end", "rsigpu_bam_run_field", "rsigpu_pinned_alloc", "rsigpu_pinned_free")
 
 _libs: dict[str, C.CDLL] = {}
@@ -269,6 +269,19 @@ class Context:
                 self._ck(self.lib.rsigpu_bam_run_field(self.h, C.c_int32(run), C.c_int32(f), _ptr(a), C.c_int64(nb.value), C.byref(nb)))
             out[name] = a
         return out
+
+    def reads_begin(self, tid: int, target_len: int):
+        """`stat`: stage reads of one contig without a reference (then pileup_push / bam_take)"""
+        self._ck(self.lib.rsigpu_reads_begin(self.h, C.c_int32(tid), C.c_int32(target_len)))
+        self.L = target_len
+
+    def stat_calls(self, calls: list) -> list:
+        """RP / Q0 (cnv_stat, pairrd.cpp:622-748) for a list of calls (the whole file's list, in order); returns the annotated copies"""
+        buf = (Cnv * max(len(calls), 1))()
+        for i, c in enumerate(calls):
+            C.memmove(C.byref(buf[i]), C.byref(c), C.sizeof(Cnv))
+        self._ck(self.lib.rsigpu_stat_calls(self.h, buf, C.c_int32(len(calls))))
+        return [_copy_cnv(buf[i]) for i in range(len(calls))]
 
     def pileup_end(self):
         """runs the pileup kernels now (so that the raw depth can be read back); `run()` re-runs them as its first stage"""

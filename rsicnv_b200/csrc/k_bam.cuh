@@ -81,7 +81,11 @@ __device__ __forceinline__ u32 bits_take(BitIn& b, int n) { const u32 v = (u32)(
 // at 1.8 KB per thread, shared memory would hold a few warps per SM, and one thread's decode loop is a chain of dependent
 // loads that only many resident warps can hide.  A 6-bit first level for the literal/length code (sf) is in shared memory.  Slot i of lane l is at g[i * 32 + l] (a warp's tables are interleaved, so
 // the construction loops -- same i in every lane -- are coalesced).  The 2 x 16 code-length counts sit in shared memory.
-struct InfTabs { u16* g; u16* s; u16* sf; int lane, stid; };
+struct InfTabs { u16* g; u16* s; u16* sf; u16* sd; int lane, stid; };   // sd: the distance code's first-level table in shared memory (INF_DSH bits, 0 = none)
+#ifndef INF_DSH
+#define INF_DSH 0
+#endif
+#define INF_SH(sh, i) (sh)[(i) * INF_NT + T.stid]
 #define INF_G(i) T.g[(size_t)(i) * 32 + T.lane]
 #define INF_C(i) T.s[(i) * INF_NT + T.stid]
 #define INF_CL(i) reinterpret_cast<u8*>(&T.sf[((i) >> 1) * INF_NT + T.stid])[(i) & 1]   /* the code-length code's 128 one-byte entries live in 64 of the thread's own first-level slots while a header is parsed */
@@ -91,11 +95,11 @@ struct InfTabs { u16* g; u16* s; u16* sf; int lane, stid; };
 // entries are symbol << 4 | length).  Returns < 0 for an over-subscribed set, > 0 for an incomplete one.
 // One pass over the symbols: codes are handed out in symbol order per length (next-code counters in shared memory), so the
 // direct table is filled without reading back anything that was just written to global memory.
-__device__ int inf_construct(const InfTabs& T, const u8* lens, int n, int fast, int fb, int cnts, int syms, int xs, int sfb) {
+__device__ int inf_construct(const InfTabs& T, const u8* lens, int n, int fast, int fb, int cnts, int syms, int xs, int sfb, u16* sh) {
   for (int l = 0; l < 16; ++l) INF_C(cnts + l) = 0;
   for (int s = 0; s < n; ++s) INF_C(cnts + lens[s]) += 1;
   for (int i = 0; i < (1 << fb); ++i) INF_G(fast + i) = 0;
-  for (int i = 0; i < (sfb ? (1 << sfb) : 0); ++i) INF_SF(i) = 0;
+  for (int i = 0; i < (sfb ? (1 << sfb) : 0); ++i) INF_SH(sh, i) = 0;
   if (INF_C(cnts) == n) return 0;
   int left = 1;
   for (int l = 1; l <= 15; ++l) { left <<= 1; left -= (int)INF_C(cnts + l); if (left < 0) return left; }
@@ -113,15 +117,15 @@ __device__ int inf_construct(const InfTabs& T, const u8* lens, int n, int fast, 
       const u32 rev = __brev(code) >> (32 - l);
       const u16 e = (u16)((s << 4) | l);
       for (u32 k = rev; k < (1u << fb); k += (1u << l)) INF_G(fast + k) = e;
-      if (l <= sfb) for (u32 k = rev; k < (1u << sfb); k += (1u << l)) INF_SF(k) = e;
+      if (l <= sfb) for (u32 k = rev; k < (1u << sfb); k += (1u << l)) INF_SH(sh, k) = e;
     }
   }
   return left;
 }
-__device__ __forceinline__ int inf_decode(BitIn& b, const InfTabs& T, int fast, int fb, int cnts, int syms, int xs, int sfb) {
+__device__ __forceinline__ int inf_decode(BitIn& b, const InfTabs& T, int fast, int fb, int cnts, int syms, int xs, int sfb, const u16* sh) {
   const u32 low = (u32)(b.buf & ((1u << fb) - 1));
   if (sfb) {   // codes of <= sfb bits (the frequent symbols): one shared-memory look-up, no trip to L1/L2
-    const u32 e0 = INF_SF(low & ((1u << sfb) - 1));
+    const u32 e0 = INF_SH(sh, low & ((1u << sfb) - 1));
     if (e0) { const int l = (int)(e0 & 15u); b.buf >>= l; b.cnt -= l; return (int)(e0 >> 4); }
   }
   const u32 e = INF_G(fast + low);
@@ -202,9 +206,9 @@ __device__ __noinline__ void inf_block_header(InfState& S, const InfTabs& T) {
     for (int s = 144; s < 256; ++s) lens[s] = 9;
     for (int s = 256; s < 280; ++s) lens[s] = 7;
     for (int s = 280; s < 288; ++s) lens[s] = 8;
-    inf_construct(T, lens, 288, INF_LF, INF_FB, INF_LC, INF_LS, INF_LX, INF_SB);
+    inf_construct(T, lens, 288, INF_LF, INF_FB, INF_LC, INF_LS, INF_LX, INF_SB, T.sf);
     for (int s = 0; s < 30; ++s) lens[s] = 5;
-    inf_construct(T, lens, 30, INF_DF, INF_DB, INF_DC, INF_DS, INF_DX, 0);
+    inf_construct(T, lens, 30, INF_DF, INF_DB, INF_DC, INF_DS, INF_DX, INF_DSH, T.sd);
   } else {
     bits_refill(b);
     const int nlen = (int)bits_take(b, 5) + 257, ndist = (int)bits_take(b, 5) + 1, ncode = (int)bits_take(b, 4) + 4;
@@ -229,9 +233,9 @@ __device__ __noinline__ void inf_block_header(InfState& S, const InfTabs& T) {
       }
     }
     if (lens[256] == 0) return inf_fail(S, 10);
-    int r = inf_construct(T, lens, nlen, INF_LF, INF_FB, INF_LC, INF_LS, INF_LX, INF_SB);
+    int r = inf_construct(T, lens, nlen, INF_LF, INF_FB, INF_LC, INF_LS, INF_LX, INF_SB, T.sf);
     if (r < 0 || (r > 0 && nlen - (int)INF_C(INF_LC) != 1)) return inf_fail(S, 11);       // incomplete only allowed for a single code
-    r = inf_construct(T, lens + nlen, ndist, INF_DF, INF_DB, INF_DC, INF_DS, INF_DX, 0);
+    r = inf_construct(T, lens + nlen, ndist, INF_DF, INF_DB, INF_DC, INF_DS, INF_DX, INF_DSH, T.sd);
     if (r < 0 || (r > 0 && ndist - (int)INF_C(INF_DC) != 1)) return inf_fail(S, 12);
   }
   S.phase = INF_SYMS;
@@ -249,7 +253,7 @@ __device__ __forceinline__ void inf_symbol(InfState& S, const InfTabs& T, const 
 #pragma unroll 1
   for (int rep = 0; rep < INF_LITS; ++rep) {
     bits_refill(b);
-    sym = inf_decode(b, T, INF_LF, INF_FB, INF_LC, INF_LS, INF_LX, INF_SB);
+    sym = inf_decode(b, T, INF_LF, INF_FB, INF_LC, INF_LS, INF_LX, INF_SB, T.sf);
     if (sym >= 256) break;
     if (sym < 0) return inf_fail(S, 13);
     if (S.o >= S.dst_len) return inf_fail(S, 3);
@@ -265,7 +269,7 @@ __device__ __forceinline__ void inf_symbol(InfState& S, const InfTabs& T, const 
   if (sym >= 29) return inf_fail(S, 14);
   const u32 len = (u32)tab[sym] + bits_take(b, (int)tab[29 + sym]);
   bits_refill(b);
-  const int ds = inf_decode(b, T, INF_DF, INF_DB, INF_DC, INF_DS, INF_DX, 0);
+  const int ds = inf_decode(b, T, INF_DF, INF_DB, INF_DC, INF_DS, INF_DX, INF_DSH, T.sd);
   if (ds < 0 || ds >= 30) return inf_fail(S, 15);
   const u32 dist = (u32)tab[58 + ds] + bits_take(b, (int)tab[88 + ds]);
   if (dist > S.o) return inf_fail(S, 16);
@@ -337,6 +341,7 @@ __global__ void __launch_bounds__(INF_NT, INF_MINB) k_bgzf_inflate(const u8* __r
   __shared__ u16 tab[120];
   __shared__ u16 cnts[INF_SSLOTS * INF_NT];
   __shared__ u16 sfast[(1 << INF_SB) * INF_NT];   // first-level literal/length table; doubles as the code-length code's table while a header is parsed
+  __shared__ u16 sdist[(INF_DSH ? (1 << INF_DSH) : 1) * INF_NT];   // first-level distance table (optional; measured: 46.9 vs 48.0 ms with 6 bits, not worth the occupancy)
   {
     const u16 lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
     const u16 lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
@@ -347,7 +352,7 @@ __global__ void __launch_bounds__(INF_NT, INF_MINB) k_bgzf_inflate(const u8* __r
   }
   __syncthreads();
   const int k = (int)blockIdx.x * INF_NT + (int)threadIdx.x;
-  InfTabs T; T.lane = (int)(threadIdx.x & 31); T.stid = (int)threadIdx.x; T.s = cnts; T.sf = sfast;
+  InfTabs T; T.lane = (int)(threadIdx.x & 31); T.stid = (int)threadIdx.x; T.s = cnts; T.sf = sfast; T.sd = sdist;
   T.g = tabs + (size_t)(k >> 5) * 32 * INF_GSLOTS;
   InfState S;
   S.phase = INF_DONE; S.rc = 0; S.o = 0; S.dst_len = 0; S.dst = U; S.last = 0; S.m_len = 0; S.m_dist = 1;

@@ -306,6 +306,7 @@ __global__ void __launch_bounds__(1024) k_cnv_stat(ReadSoA R, Cnv* calls, int nc
   RSI_CTA_SETUP(c);
   const int im = isz[0], isd = isz[1];
   for (int k = (int)blockIdx.x; k < ncalls; k += (int)gridDim.x) {
+    if (calls[k].tid != R.tid) continue;      // `stat` hands over the calls of every contig: DIS below runs over the whole list
     int DIS = 1000;
     for (int j = 0; j <= k; ++j) {   // DIS is carried from call to call (pairrd.cpp:655-656)
       int b = calls[j].start, e = calls[j].end; if (b > e) { int t = b; b = e; e = t; }

@@ -887,6 +887,40 @@ int rsigpu_cnv_stat(rsigpu_ctx* c) {
   return RSIGPU_OK;
 }
 
+// `stat`: reads of one contig without a reference, then RP / Q0 for calls from a file
+int rsigpu_reads_begin(rsigpu_ctx* c, int32_t tid, int32_t target_len) {
+  if (!c || target_len < 1) return RSIGPU_E_ARG;
+  c->L = target_len; c->tid = tid;
+  c->have_ref = true;           // staging reads needs only the contig's length and id
+  c->have_depth = false; c->have_reads = false; c->loaded = false; c->detected = false; c->filtered = false;
+  return rsigpu_pileup_begin(c, target_len);
+}
+
+int rsigpu_stat_calls(rsigpu_ctx* c, rsigpu_cnv* list, int32_t n) {
+  if (!c || !list || n < 0) return RSIGPU_E_ARG;
+  if (n == 0 || c->r_pos.n == 0) return RSIGPU_OK;
+  if (n > LIST_CAP * 8) { c->fail("stat_calls: more than 524288 calls"); return RSIGPU_E_RANGE; }
+  cudaSetDevice(c->device);
+  CK(c->r_calend.ensure(c->r_pos.n + 8));
+  ReadSoA R = read_view(c);
+  int* mx = c->d_misc.p + 5;
+  if (c->isize_pending) { CK(cudaStreamWaitEvent(c->stream, c->ev_isize, 0)); c->isize_pending = false; }
+  CK(cudaMemsetAsync(mx, 0, 8, c->stream));
+  KL(k_read_ends, grid_for((int)std::min<size_t>(c->r_pos.n, 1u << 30), 256, c->n_sm * 16), 256, 0, R, mx, mx + 1);
+  KL(k_isize_stats, 1, 1024, 0, R, c->L, mx, c->d_misc.p + 16);
+  Cnv* d = c->list(0);          // lists 0..7 are contiguous: room for 8 * LIST_CAP entries
+  CK(cudaMemcpyAsync(d, list, sizeof(Cnv) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  KL(k_cnv_stat, std::min((int)n, c->n_sm * 2), 1024, 0, R, d, (int)n, mx, c->d_misc.p + 16);
+  std::vector<Cnv> out((size_t)n);
+  int sb = 0;
+  CK(cudaMemcpyAsync(out.data(), d, sizeof(Cnv) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(&sb, mx + 1, 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (sb) { c->fail("read batch is not sorted by position"); return RSIGPU_E_ARG; }
+  for (int32_t k = 0; k < n; ++k) if (list[k].tid == c->tid) { list[k].rp = out[(size_t)k].rp; list[k].q0 = out[(size_t)k].q0; }
+  return RSIGPU_OK;
+}
+
 int rsigpu_get_calls(rsigpu_ctx* c, rsigpu_cnv* out, int32_t cap, int32_t* n) {
   if (!c || !n) return RSIGPU_E_ARG;
   if (!c->detected) { c->fail("get_calls: call detectcnv first"); return RSIGPU_E_ARG; }

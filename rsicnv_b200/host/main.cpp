@@ -36,7 +36,7 @@ using namespace rsihost;
 namespace {
 
 struct Opt {
-  std::string function = "rsi", rdfile, bamfile, reffile, outfile = "rsiout.txt", chr = "1-22XY";
+  std::string function = "rsi", rdfile, bamfile, reffile, cnvfile, outfile = "rsiout.txt", chr = "1-22XY";
   bool saverd = false, hostdecode = false;
   int gpus = 1, threads = 8;
   rsigpu_params P;
@@ -58,7 +58,7 @@ bool parse(int argc, char** argv, Opt* o) {
   if (a.size() < 2) return false;
   if (a[1][0] != '-') {
     o->function = a[1]; a[1] = "";
-    if (o->function != "rsi" && o->function != "decode") { fprintf(stderr, "no such function %s (this build implements `rsi`)\n", o->function.c_str()); return false; }
+    if (o->function != "rsi" && o->function != "decode" && o->function != "stat") { fprintf(stderr, "no such function %s (this build implements `rsi` and `stat`)\n", o->function.c_str()); return false; }
   }
   auto val = [&](size_t i) { return i + 1 < a.size() ? a[i + 1] : std::string(); };
   for (size_t i = 1; i < a.size(); ++i) {
@@ -67,7 +67,7 @@ bool parse(int argc, char** argv, Opt* o) {
     if (k == "-d") { o->rdfile = val(i); two(); continue; }
     if (k == "-b") { o->bamfile = val(i); two(); continue; }
     if (k == "-f") { o->reffile = val(i); two(); continue; }
-    if (k == "-v") { two(); continue; }
+    if (k == "-v") { o->cnvfile = val(i); two(); continue; }
     if (k == "-o") { o->outfile = val(i); two(); continue; }
     if (k == "-c") { o->chr = val(i); two(); continue; }
     if (k == "-s") { o->saverd = true; a[i] = ""; continue; }
@@ -95,6 +95,7 @@ bool parse(int argc, char** argv, Opt* o) {
   if (bad) return false;
   if (o->rdfile.empty() && o->bamfile.empty()) { fprintf(stderr, "need input file \n"); return false; }
   if (o->reffile.empty() && o->function == "rsi") { fprintf(stderr, "need reference file \n"); return false; }
+  if (o->function == "stat" && (o->bamfile.empty() || o->cnvfile.empty())) { fprintf(stderr, "stat needs -b BAM and -v CNVFILE\n"); return false; }
   if (o->outfile == o->bamfile || o->outfile == o->rdfile) { fprintf(stderr, "output file is same as input file \n"); return false; }
   if (!o->rdfile.empty() && (o->chr.empty() || o->chr == "1-22XY")) { fprintf(stderr, "readdepth file and chromosome must be specified together\n"); return false; }
   if (o->P.m % 2 != 1) { o->P.m += 1; fprintf(stderr, "m is changed to %d\n", o->P.m); }
@@ -504,6 +505,91 @@ int bam_on_gpu(const Opt& o, const std::vector<std::vector<rsigpu_ctx*>>& ctx, s
   return failed.load() ? 1 : 0;
 }
 
+// `rsicnv stat -b BAM -v CNVFILE -o OUT` (rsi.cpp:2235-2249): every line of CNVFILE that names a call (read_cnvlist,
+// loaddata.cpp:606-673: >= 5 characters, not a comment, >= 4 fields RNAME START END TYPE) is written back followed by
+// RP=<supporting read pairs>;Q0=<fraction of mapq-0 reads> (cnv_stat, pairrd.cpp:622-748).  The reads of every contig that
+// has calls are decoded on the GPU (from the .bai offset of the contig, or in one pass over the file without an index).
+bool ci_has(const std::string& hay, const char* needle) {
+  std::string h = hay; for (char& ch : h) ch = (char)tolower((unsigned char)ch);
+  return h.find(needle) != std::string::npos;
+}
+int do_stat(const Opt& o, rsigpu_ctx* c) {
+  std::string err; long long coff = 0, skip = 0;
+  BamHeader h;
+  if (!read_bam_header(o.bamfile, &h, &coff, &skip, &err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+  std::ifstream in(o.cnvfile.c_str());
+  if (!in) { fprintf(stderr, "File %s not exist\n", o.cnvfile.c_str()); return 0; }
+  std::vector<rsigpu_cnv> list; std::vector<std::string> lines;
+  std::string ln;
+  while (std::getline(in, ln)) {
+    if (ln.size() < 5 || ln[0] == '#') continue;
+    std::vector<std::string> cell; { size_t p = 0; while (p < ln.size()) { while (p < ln.size() && isspace((unsigned char)ln[p])) ++p; size_t q = p; while (q < ln.size() && !isspace((unsigned char)ln[q])) ++q; if (q > p) cell.push_back(ln.substr(p, q - p)); p = q; } }
+    if (cell.size() < 4) { fprintf(stderr, "skipping lines with less than 4 fields\nexpecting RNAME cnv_begin_pos cnv_end_pos cnv_type in each line\n"); continue; }
+    rsigpu_cnv x; memset(&x, 0, sizeof x);
+    x.tid = -1; x.type = RSIGPU_TYPE_UNKNOWN; x.p1 = x.p2 = 1.0; x.q0 = -1.0; x.rp = -1;
+    for (size_t t = 0; t < h.name.size(); ++t) if (h.name[t] == cell[0]) { x.tid = (int32_t)t; break; }
+    x.start = atoi(cell[1].c_str()); x.end = atoi(cell[2].c_str());
+    if (ci_has(cell[3], "del")) x.type = RSIGPU_TYPE_DEL;
+    if (ci_has(cell[3], "loss")) x.type = RSIGPU_TYPE_DEL;
+    if (ci_has(cell[3], "dup")) x.type = RSIGPU_TYPE_DUP;
+    if (ci_has(cell[3], "gain")) x.type = RSIGPU_TYPE_DUP;
+    if (ci_has(cell[3], "add")) x.type = RSIGPU_TYPE_DUP;
+    list.push_back(x); lines.push_back(ln);
+  }
+  if (list.empty()) { fprintf(stderr, "I can't find any CNV from %s\n", o.cnvfile.c_str()); return 0; }
+  const int n_ref = (int)h.name.size();
+  std::vector<char> wanted((size_t)n_ref, 0);
+  for (const rsigpu_cnv& x : list) if (x.tid >= 0) wanted[(size_t)x.tid] = 1;
+  rsigpu_ctx* dec = nullptr;
+  if (rsigpu_create(0, &o.P, &dec)) { fprintf(stderr, "cannot create the decoder context\n"); return 2; }
+  std::vector<BaiRef> bai;
+  const bool indexed = !getenv("RSICNV_NO_INDEX") && read_bai(o.bamfile, h.name.size(), &bai);
+  DecodeTiming tm;
+  int failed = 0;
+  auto stat_contig = [&](int tid) {
+    if (rsigpu_stat_calls(c, list.data(), (int32_t)list.size())) { fprintf(stderr, "%s: %s\n", h.name[(size_t)tid].c_str(), rsigpu_last_error(c)); ++failed; }
+  };
+  if (indexed) {
+    for (int tid = 0; tid < n_ref; ++tid) {
+      if (!wanted[(size_t)tid] || !bai[(size_t)tid].has_reads) continue;
+      fprintf(stderr, "#sampling %s\n", h.name[(size_t)tid].c_str());
+      if (rsigpu_reads_begin(c, tid, h.len[(size_t)tid]) || rsigpu_bam_begin(dec, (int32_t)n_ref)) { fprintf(stderr, "%s\n", rsigpu_last_error(c)); ++failed; continue; }
+      const uint64_t v = bai[(size_t)tid].first_voff;
+      uint64_t ve = bai[(size_t)tid].end_voff;
+      if (!ve) for (int t = tid + 1; t < n_ref; ++t) if (bai[(size_t)t].has_reads) { ve = bai[(size_t)t].first_voff; break; }
+      bool take_err = false;
+      const int rc = stream_bam(o.bamfile, (long long)(v >> 16), (long long)(v & 0xffff), ve ? (long long)(ve >> 16) : 0, dec, (size_t)1 << 30, [&](int i, const rsigpu_bam_run& run) {
+        if (run.tid != tid) return 1;
+        if (rsigpu_bam_take(dec, i, c)) { take_err = true; return -1; }
+        return 0;
+      }, &tm);
+      if (rc || take_err) { fprintf(stderr, "%s: BAM decoding failed\n", h.name[(size_t)tid].c_str()); ++failed; continue; }
+      stat_contig(tid);
+    }
+  } else {
+    if (rsigpu_bam_begin(dec, (int32_t)n_ref)) { fprintf(stderr, "%s\n", rsigpu_last_error(dec)); return 2; }
+    int cur = -1; bool cur_ok = false;
+    const int rc = stream_bam(o.bamfile, coff, skip, 0, dec, (size_t)256 << 20, [&](int i, const rsigpu_bam_run& run) {
+      if (run.tid < 0) return 1;
+      if (run.tid != cur) {
+        if (cur >= 0 && cur_ok) stat_contig(cur);
+        cur = run.tid; cur_ok = false;
+        if (wanted[(size_t)cur]) { fprintf(stderr, "#sampling %s\n", h.name[(size_t)cur].c_str()); cur_ok = rsigpu_reads_begin(c, cur, h.len[(size_t)cur]) == 0; }
+      }
+      if (cur_ok && rsigpu_bam_take(dec, i, c)) { fprintf(stderr, "%s: %s\n", h.name[(size_t)cur].c_str(), rsigpu_last_error(c)); cur_ok = false; ++failed; }
+      return 0;
+    }, &tm);
+    if (rc) ++failed;
+    else if (cur >= 0 && cur_ok) stat_contig(cur);
+  }
+  rsigpu_destroy(dec);
+  FILE* f = fopen(o.outfile.c_str(), "w");
+  if (!f) { fprintf(stderr, "cannot write %s\n", o.outfile.c_str()); return 1; }
+  for (size_t i = 0; i < list.size(); ++i) fprintf(f, "%s\tRP=%d;Q0=%g\n", lines[i].c_str(), list[i].rp, list[i].q0);
+  fclose(f);
+  return failed ? 1 : 0;
+}
+
 void write_table(const Opt& o, const std::vector<ContigResult>& all) {
   FILE* f = fopen(o.outfile.c_str(), "w");
   if (!f) { fprintf(stderr, "cannot write %s\n", o.outfile.c_str()); return; }
@@ -573,6 +659,11 @@ int main(int argc, char** argv) {
     if (bad.load()) { fprintf(stderr, "cannot create a context on every GPU\n"); return 2; }
   }
   if (getenv("RSICNV_TIMING")) fprintf(stderr, "#timing: CUDA start-up + contexts %.3f s\n", now_s() - t_main);
+  if (o.function == "stat") {
+    const int rc = do_stat(o, ctx[0][0]);
+    for (auto& v : ctx) for (rsigpu_ctx* c : v) rsigpu_destroy(c);
+    return rc;
+  }
   std::vector<ContigResult> results;
   std::string err;
   int rc_all = 0;

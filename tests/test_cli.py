@@ -240,3 +240,30 @@ def test_header_reader_agrees_with_the_python_one(cli, tmp_path):
         out = subprocess.run([cli, "decode", "-b", bam, "-c", "19", "-o", str(tmp_path / "d")], capture_output=True, text=True)
         assert out.returncode == 0, out.stderr
         assert "records start at file offset %d + %d decoded bytes, %d references" % (h["coff"], h["skip"], len(contigs)) in out.stdout, out.stdout
+
+
+@pytest.mark.gpu
+def test_cli_stat_matches_reference(cli, tmp_path):
+    """`rsicnv stat -b BAM -v CALLS -o OUT` (rsi.cpp:2235-2249): the reference's own table goes in, every call line comes back with
+    RP= / Q0= appended; also lines the reader skips (comments, short lines, < 4 fields), and the route without the index"""
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    lens = [10_600_000, 10_450_000]
+    fas = [synth.make_fasta(L, 40 + i) for i, L in enumerate(lens)]
+    reads = {i: synth.make_reads(L, 40 + i, fas[i], coverage=10, n_events=5, lens=(3000, 8000, 20000), tid=i)[0] for i, L in enumerate(lens)}
+    bam = str(tmp_path / "t.bam"); fasta = str(tmp_path / "t.fa")
+    synth.write_bam(bam, [("1", lens[0]), ("2", lens[1])], reads, level=1, rich=17, unmapped_tail=10)
+    synth.write_fasta_multi(fasta, [("1", fas[0]), ("2", fas[1])])
+    subprocess.run([REF_BAMTOOL, "index", bam], check=True)
+    subprocess.run([REF_BIN, "rsi", "-b", bam, "-f", fasta, "-q", "0", "-Q", "10", "-np", "-o", str(tmp_path / "calls.txt")], check=True, capture_output=True)
+    calls = str(tmp_path / "calls.txt")
+    with open(calls, "a") as f:
+        f.write("# comment\n1 2\n2\t5000000\t5003000\tgain\textra\n1\t7000000\t6990000\tloss\n2 x y\n")
+    subprocess.run([REF_BIN, "stat", "-b", bam, "-v", calls, "-o", str(tmp_path / "ref_stat.txt")], check=True, capture_output=True)
+    ref = open(str(tmp_path / "ref_stat.txt")).read().splitlines()
+    assert len(ref) > 8
+    for env in ({}, {"RSICNV_NO_INDEX": "1"}):
+        out = subprocess.run([cli, "stat", "-b", bam, "-v", calls, "-o", str(tmp_path / "our_stat.txt")], capture_output=True, text=True, env=dict(os.environ, **env))
+        assert out.returncode == 0, out.stderr
+        ours = open(str(tmp_path / "our_stat.txt")).read().splitlines()
+        assert ours == ref, (env, out.stderr)

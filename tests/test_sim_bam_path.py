@@ -88,3 +88,31 @@ def test_pileup_quality_thresholds_full_byte_range(sim_lib, oracle):
         with api.Context(lib=sim_lib, minq=0, min_baseQ=Q) as ctx:
             ctx.set_reference(fa); ctx.pileup_begin(); ctx.pileup_push(reads); ctx.pileup_end()
             assert np.array_equal(ctx.array(api.ARR_RAW_DEPTH), want), Q
+
+
+def test_stat_calls_matches_oracle(case, sim_lib, oracle):
+    """`rsicnv stat` (rsi.cpp:2235-2249): RP / Q0 for calls that come from a file -- any coordinates, several contigs in one list
+    (entries of other contigs are left alone, but the search distance DIS is carried across them, pairrd.cpp:655-656)"""
+    from bind import new_cnv, oracle_cnv_stat
+    from rsicnv_b200 import api
+    fa, reads, ev = case
+    lst = []
+    for k, (s, e, f) in enumerate(ev):
+        lst.append(new_cnv(start=s, end=e, type=0 if f < 1 else 1, tid=0))
+        lst.append(new_cnv(start=s + 700 * k, end=e + 2100, type=1 if f < 1 else 0, tid=0))      # shifted, wrong type
+    lst.insert(1, new_cnv(start=5_000_000, end=5_004_000, type=0, tid=1))                           # another contig: DIS grows to 4001 for what follows
+    lst.append(new_cnv(start=9_000_000, end=8_990_000, type=2, tid=0))                              # reversed, unknown type
+    oracle.set_params(minq=0, min_baseQ=10)
+    mine = [c for c in lst if c.tid == 0]
+    # the oracle works on one contig's list: hand it the same DIS history by keeping the foreign entry's length in the list
+    want_all = oracle_cnv_stat(oracle, reads, L, lst)
+    with api.Context(lib=sim_lib, minq=0, min_baseQ=10) as ctx:
+        ctx.reads_begin(0, L)
+        ctx.pileup_push(reads)
+        got = ctx.stat_calls(lst)
+    for i, (g, w, src) in enumerate(zip(got, want_all, lst)):
+        if src.tid == 0:
+            assert g.rp == w.rp and (g.q0 == w.q0 or abs(g.q0 - w.q0) <= 1e-9 * abs(w.q0)), (i, g.rp, w.rp, g.q0, w.q0)
+        else:
+            assert g.rp == -1 and g.q0 == -1.0
+    assert any(g.rp > 0 for g in got) and len(mine) == len(lst) - 1
