@@ -147,6 +147,8 @@ int rsigpu_bam_begin(rsigpu_ctx* c, int32_t n_ref);
 int rsigpu_bam_feed(rsigpu_ctx* c, const uint8_t* bgzf, int64_t nbytes, int64_t skip, int64_t* consumed, rsigpu_bam_run* runs, int32_t cap,
                     int32_t* n_runs);
 int rsigpu_bam_take(rsigpu_ctx* c, int32_t run, rsigpu_ctx* dst);
+/* only the records of the run with pos in [pos_lo, pos_hi) (a part of a contig split over several GPUs, rsigpu_split_run) */
+int rsigpu_bam_take_range(rsigpu_ctx* c, int32_t run, rsigpu_ctx* dst, int32_t pos_lo, int32_t pos_hi);
 int rsigpu_bam_end(rsigpu_ctx* c);
 /* one decoded field of a run copied to the host (parity tests): 0 pos, 1 mpos, 2 isize, 3 mtid (int32), 4 flag (uint16),
  * 5 mapq (uint8), 6 cigar_off (uint32, n+1, rebased to 0), 7 cigar (uint32), 8 qual_off (uint64, n+1, rebased), 9 qual (uint8) */
@@ -172,6 +174,17 @@ int rsigpu_stat_calls(rsigpu_ctx* c, rsigpu_cnv* list, int32_t n);
 
 /* Everything above on the staged inputs, one host synchronisation at the end. */
 int rsigpu_run(rsigpu_ctx* c, rsigpu_cnv* out, int32_t cap, int32_t* n);
+
+/* One contig over several GPUs (config 5; the reference is one thread on one array, rsi.cpp:2189-2217: there is nothing to
+ * mirror, the result must simply be identical).  parts[0] is the lead (it ends up with the calls, the arrays and the stats);
+ * every part context -- one per GPU -- gets the WHOLE reference (rsigpu_set_reference) and then either the whole depth array
+ * (rsigpu_set_depth) or, for BAM input, only the reads with pos in [beg - read_halo, end) of ITS range as rsigpu_split_range
+ * reports it (rsigpu_pileup_begin / push / commit or rsigpu_bam_take as usual).  rsigpu_split_run then does what rsigpu_run does:
+ * pileup and the three per-base passes on each part's own range, the parts' integer tables added on the lead over peer-to-peer
+ * copies, the bin-level and candidate stages on the lead.  rsigpu_split_p2p_bytes: bytes that crossed between devices. */
+int rsigpu_split_range(int32_t target_len, int32_t n_parts, int32_t part, int32_t* beg, int32_t* end, int32_t* read_halo);
+int rsigpu_split_run(rsigpu_ctx** parts, int32_t n_parts, rsigpu_cnv* out, int32_t cap, int32_t* n);
+long long rsigpu_split_p2p_bytes(const rsigpu_ctx* lead);
 
 int rsigpu_get_chr_stats(rsigpu_ctx* c, rsigpu_chr_stats* out);
 /* copies min(count, cap) elements of the selected device array to `out`, *count = elements available */

@@ -71,7 +71,7 @@ EXPORTS = ("rsigpu_default_params", "rsigpu_create", "rsigpu_destroy", "rsigpu_l
            "rsigpu_set_depth", "rsigpu_pileup_begin", "rsigpu_pileup_push", "rsigpu_pileup_end", "rsigpu_load_finish", "rsigpu_detectcnv",
            "rsigpu_sd_filters", "rsigpu_cnv_stat", "rsigpu_get_calls", "rsigpu_run", "rsigpu_get_chr_stats", "rsigpu_get_array",
            "rsigpu_format_row", "rsigpu_launch_count", "rsigpu_last_stage_ms", "rsigpu_set_profile", "rsigpu_get_profile",
-           "rsigpu_reads_begin", "rsigpu_stat_calls", "rsigpu_set_level0_mode", "rsigpu_set_feed_limit", "rsigpu_set_cand_threads", "rsigpu_debug_state", "rsigpu_pileup_commit", "rsigpu_bam_begin", "rsigpu_bam_feed", "rsigpu_bam_take",
+           "rsigpu_reads_begin", "rsigpu_stat_calls", "rsigpu_bam_take_range", "rsigpu_split_range", "rsigpu_split_run", "rsigpu_split_p2p_bytes", "rsigpu_set_level0_mode", "rsigpu_set_feed_limit", "rsigpu_set_cand_threads", "rsigpu_debug_state", "rsigpu_pileup_commit", "rsigpu_bam_begin", "rsigpu_bam_feed", "rsigpu_bam_take",
            "rsigpu_bam_end", "rsigpu_bam_run_field", "rsigpu_pinned_alloc", "rsigpu_pinned_free")
 
 _libs: dict[str, C.CDLL] = {}
@@ -86,6 +86,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib = C.CDLL(path)
     lib.rsigpu_last_error.restype = C.c_char_p
     lib.rsigpu_launch_count.restype = C.c_int64
+    lib.rsigpu_split_p2p_bytes.restype = C.c_longlong
     lib.rsigpu_destroy.restype = None
     lib.rsigpu_pinned_free.restype = None
     lib.rsigpu_pinned_free.argtypes = [C.c_void_p]
@@ -252,6 +253,11 @@ class Context:
         if rc != 0:
             raise RsiGpuError(rc, (self.lib.rsigpu_last_error(dst.h) or self.lib.rsigpu_last_error(self.h) or b"").decode())
 
+    def bam_take_range(self, run: int, dst: "Context", pos_lo: int, pos_hi: int):
+        rc = self.lib.rsigpu_bam_take_range(self.h, C.c_int32(run), dst.h, C.c_int32(pos_lo), C.c_int32(pos_hi))
+        if rc != 0:
+            raise RsiGpuError(rc, (self.lib.rsigpu_last_error(dst.h) or self.lib.rsigpu_last_error(self.h) or b"").decode())
+
     def bam_end(self):
         self._ck(self.lib.rsigpu_bam_end(self.h))
 
@@ -382,6 +388,37 @@ class Context:
 
     def set_cand_threads(self, threads: int):
         self._ck(self.lib.rsigpu_set_cand_threads(self.h, C.c_int(threads)))
+
+
+def split_range(lib: C.CDLL, target_len: int, n_parts: int, part: int):
+    """(beg, end, read_halo) of one part of a contig split over several GPUs (rsigpu_split_range)"""
+    b = C.c_int32(0); e = C.c_int32(0); h = C.c_int32(0)
+    rc = lib.rsigpu_split_range(C.c_int32(target_len), C.c_int32(n_parts), C.c_int32(part), C.byref(b), C.byref(e), C.byref(h))
+    if rc != 0:
+        raise RsiGpuError(rc, "split_range")
+    return b.value, e.value, h.value
+
+
+def split_reads(reads: dict, beg: int, end: int, halo: int) -> dict:
+    """the reads a part of a split contig stages: pos in [beg - halo, end), offsets rebased (position-sorted SoA in, SoA out)"""
+    pos = reads["pos"]
+    lo = int(np.searchsorted(pos, beg - halo, side="left")); hi = int(np.searchsorted(pos, end, side="left"))
+    co = reads["cigar_off"].astype(np.int64); qo = reads["qual_off"].astype(np.int64)
+    d = {k: reads[k][lo:hi] for k in ("pos", "mpos", "isize", "mtid", "flag", "mapq")}
+    d["cigar_off"] = (co[lo:hi + 1] - co[lo]).astype(np.uint32); d["cigar"] = reads["cigar"][co[lo]:co[hi]]
+    d["qual_off"] = (qo[lo:hi + 1] - qo[lo]).astype(np.uint64); d["qual"] = reads["qual"][qo[lo]:qo[hi]]
+    return d
+
+
+def split_run(parts: list, cap: int = 65536) -> list:
+    """rsigpu_split_run: parts[0] is the lead; returns the calls"""
+    arr = (C.c_void_p * len(parts))(*[p.h for p in parts])
+    n = C.c_int32(0)
+    buf = (Cnv * cap)()
+    rc = parts[0].lib.rsigpu_split_run(arr, C.c_int32(len(parts)), buf, C.c_int32(cap), C.byref(n))
+    if rc != 0:
+        raise RsiGpuError(rc, (parts[0].lib.rsigpu_last_error(parts[0].h) or b"").decode())
+    return [_copy_cnv(buf[i]) for i in range(n.value)]
 
 
 def _copy_cnv(src: Cnv) -> Cnv:

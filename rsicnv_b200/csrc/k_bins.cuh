@@ -55,8 +55,10 @@ __device__ __forceinline__ void c_issue(int* dst, u64* bar, const int* __restric
 //           registers as bytes relative to the value window (4 per register) and counts "value <= probe" for 4 values with
 //           one subtract (no lane ever waits for another: one shuffle per probe joins the two halves).  Larger m, or a bin
 //           with a value outside the window: one warp per bin with ballots.
+// tile0 .. tile1: the tiles this launch covers (all of them, or one part of a contig split over several GPUs; the tail
+// pseudo-tile has index nbin_tiles and belongs to the last part)
 __global__ void __launch_bounds__(C_NT) k_bins(int* __restrict__ rdc, float* __restrict__ bin_med, int* __restrict__ bin_medint,
-                                                i64* __restrict__ bin_sum, u32* chist, u32* thist, DevState* st, int bins_per_tile) {
+                                                i64* __restrict__ bin_sum, u32* chist, u32* thist, DevState* st, int bins_per_tile, int tile0, int tile1) {
   RSI_DYN_SMEM(smem);
   RSI_CTA_SETUP(c);
   __shared__ __align__(8) u64 s_bar[2];
@@ -75,14 +77,14 @@ __global__ void __launch_bounds__(C_NT) k_bins(int* __restrict__ rdc, float* __r
   i64 mx = 0;
   const int bpt = bins_per_tile;
   const int nbin_tiles = nb > 0 ? (nb + bpt - 1) / bpt : 0;
-  const int ntiles = nbin_tiles + (Lc - nb * m > 0 ? 1 : 0);
+  const int ntiles = imin(nbin_tiles + (Lc - nb * m > 0 ? 1 : 0), tile1);
   if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
   c.sync();
   if (tid == 0)
-    for (int s = 0; s < 2; ++s) { const int t = (int)blockIdx.x + s * (int)gridDim.x; if (t < ntiles) c_issue(stage[s], &s_bar[s], rdc, c_tile(t, nbin_tiles, bpt, nb, m, Lc)); }
+    for (int s = 0; s < 2; ++s) { const int t = tile0 + (int)blockIdx.x + s * (int)gridDim.x; if (t < ntiles) c_issue(stage[s], &s_bar[s], rdc, c_tile(t, nbin_tiles, bpt, nb, m, Lc)); }
   const int need = (m - 1) / 2 + 1;                    // median = smallest v with #{x <= v} >= need (m is odd)
   int it = 0;
-  for (int tile = (int)blockIdx.x; tile < ntiles; tile += (int)gridDim.x, ++it) {
+  for (int tile = tile0 + (int)blockIdx.x; tile < ntiles; tile += (int)gridDim.x, ++it) {
     const int s = it & 1;
     const CTile T = c_tile(tile, nbin_tiles, bpt, nb, m, Lc);
     mbar_wait(&s_bar[s], (u32)(it >> 1) & 1u);
@@ -194,15 +196,21 @@ __global__ void __launch_bounds__(C_NT) k_bins(int* __restrict__ rdc, float* __r
 // independent pipeline, like the per-base passes -- its own warp-tiles of CW_BINS whole bins, its own two-stage bulk-copy
 // ring, its own class-histogram table; no block barrier in the loop.  The pseudo-tile after the last bin tile owns the
 // < m bases beyond nb*m.
-enum { CW_NW = 8, CW_NT = CW_NW * 32, CW_BINS = 16 /* one bin per lane pair */, CW_CAP = 2048 /* words per stage >= 16 * 127 + 3 */ };
-#define RSI_CW_WARP_BYTES ((size_t)2 * CW_CAP * 4 + (size_t)MAD_CLASSES * C_KP * 2 + 4)
-#define RSI_SMEM_CW ((size_t)CW_NW * RSI_CW_WARP_BYTES)
+enum { CW_BINS = 16 /* one bin per lane pair */ };
+// words of one stage: CW_BINS bins + the skew to the 16-byte aligned source, rounded to 16 bytes (M = 0: any m <= 127)
+__host__ __device__ constexpr int cw_cap(int M) { return M ? ((CW_BINS * M + 3 + 3) & ~3) : 2048; }
+__host__ __device__ constexpr size_t cw_warp_bytes(int M) { return (size_t)2 * cw_cap(M) * 4 + (((size_t)MAD_CLASSES * C_KP * 2 + 15) & ~(size_t)15); }
+// warps per block: as many as the shared memory of an SM holds (a warp's smaller stages leave room for more warps, and more
+// warps are what hides the latency of the dependent shared-memory updates)
+__host__ __device__ constexpr int cw_nw(int M) { return (int)((size_t)220 * 1024 / cw_warp_bytes(M)) > 16 ? 16 : (int)((size_t)220 * 1024 / cw_warp_bytes(M)); }
 // M: the bin size as a compile-time constant (101 = the default, 51), or 0 = read it from the state (any odd m <= 127)
 template <int M>
-__global__ void __launch_bounds__(CW_NT) k_bins_warp(int* __restrict__ rdc, float* __restrict__ bin_med, int* __restrict__ bin_medint,
-                                                      i64* __restrict__ bin_sum, u32* chist, u32* thist, DevState* st) {
+__global__ void __launch_bounds__(cw_nw(M) * 32) k_bins_warp(int* __restrict__ rdc, float* __restrict__ bin_med, int* __restrict__ bin_medint,
+                                                      i64* __restrict__ bin_sum, u32* chist, u32* thist, DevState* st, int tile0, int tile1) {
   RSI_DYN_SMEM(smem);
   RSI_CTA_SETUP(c);
+  constexpr int CW_NW = cw_nw(M), CW_CAP = cw_cap(M);
+  constexpr size_t RSI_CW_WARP_BYTES = cw_warp_bytes(M);
   __shared__ __align__(8) u64 s_bar[CW_NW * 2];
   const int tid = c.tid, lane = tid & 31, warp = tid >> 5;
   unsigned char* wsm = smem + (size_t)warp * RSI_CW_WARP_BYTES;
@@ -217,10 +225,10 @@ __global__ void __launch_bounds__(CW_NT) k_bins_warp(int* __restrict__ rdc, floa
   const int ithr = thr >= 2147483647.0 ? 0x7fffffff : (int)floor(thr);   // integer v: (double)v > thr  <=>  v > floor(thr)
   i64 mx = 0;
   const int nbin_tiles = nb > 0 ? (nb + CW_BINS - 1) / CW_BINS : 0;
-  const int ntiles = nbin_tiles + (Lc - nb * m > 0 ? 1 : 0);
+  const int ntiles = imin(nbin_tiles + (Lc - nb * m > 0 ? 1 : 0), tile1);
   if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
   c.sync();
-  const int gw = (int)blockIdx.x * CW_NW + warp, GW = (int)gridDim.x * CW_NW;
+  const int gw = tile0 + (int)blockIdx.x * CW_NW + warp, GW = (int)gridDim.x * CW_NW;
   if (lane == 0)
     for (int s = 0; s < 2; ++s) { const int t = gw + s * GW; if (t < ntiles) c_issue(reinterpret_cast<int*>(wsm + (size_t)s * CW_CAP * 4), &bar[s], rdc, c_tile(t, nbin_tiles, CW_BINS, nb, m, Lc)); }
   const int need = (m - 1) / 2 + 1;                    // median = smallest v with #{x <= v} >= need (m is odd)

@@ -135,7 +135,8 @@ __device__ __forceinline__ bool w_interior(int w0, int L) { return w0 >= GC_WIN 
 // Dynamic shared memory per warp: 2 stages | bit string | wtab;  per block: osum[GC_STRATA] u64 | ocnt[GC_STRATA] u32
 #define RSI_A_WARP_BYTES ((size_t)2 * W_STAGE + W_BITS + (size_t)(A_ROWS + 1) * 256)
 #define RSI_SMEM_A ((size_t)A_NW * RSI_A_WARP_BYTES + (size_t)GC_STRATA * 12 + 16)
-__global__ void __launch_bounds__(A_NT) k_gc_table(const int* __restrict__ rd, const u8* __restrict__ fa, DevState* st) {
+// wt0 .. wt1: the warp-tiles this launch covers (the whole contig, or one part of a contig split over several GPUs)
+__global__ void __launch_bounds__(A_NT) k_gc_table(const int* __restrict__ rd, const u8* __restrict__ fa, DevState* st, int wt0, int wt1) {
   RSI_DYN_SMEM(smem);
   RSI_CTA_SETUP(c);
   __shared__ __align__(8) u64 s_bar[A_NW * 2];
@@ -154,8 +155,8 @@ __global__ void __launch_bounds__(A_NT) k_gc_table(const int* __restrict__ rd, c
   if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
   c.sync();
   u64* col = wtab + lane;
-  const int nwt = (L + W_T - 1) / W_T;
-  const int gw = (int)blockIdx.x * A_NW + warp, GW = (int)gridDim.x * A_NW;
+  const int nwt = imin((L + W_T - 1) / W_T, wt1);
+  const int gw = wt0 + (int)blockIdx.x * A_NW + warp, GW = (int)gridDim.x * A_NW;
   if (lane == 0)
     for (int s = 0; s < 2; ++s) { const int t = gw + s * GW; if (t < nwt) w_issue(wsm + s * W_STAGE, &bar[s], t, rd, fa, do_gc); }
   u64 psum = 0, pcnt = 0;
@@ -331,7 +332,7 @@ __global__ void k_gc_finalize(const u8* __restrict__ fa, DevState* st) {
 #define RSI_SMEM_B ((size_t)B_NW * RSI_B_WARP_BYTES + (size_t)GC_STRATA * 16 * 8 + (size_t)B_NCACHE * 12 + 16)
 __global__ void __launch_bounds__(B_NT) k_gc_adjust(const int* __restrict__ rd, const u8* __restrict__ fa, int* __restrict__ rdc,
                                                      const int* __restrict__ nbeg, const int* __restrict__ nend, const int* __restrict__ ncum,
-                                                     u32* hist_all, DevState* st) {
+                                                     u32* hist_all, DevState* st, int wt0, int wt1) {
   RSI_DYN_SMEM(smem);
   RSI_CTA_SETUP(c);
   __shared__ __align__(8) u64 s_bar[B_NW * 2];
@@ -359,8 +360,8 @@ __global__ void __launch_bounds__(B_NT) k_gc_adjust(const int* __restrict__ rd, 
   int bad = 0;
   u32 zeros = 0;
   int kn = 0;                          // first N interval that ends at or after the current warp-tile (tiles are visited in increasing order)
-  const int nwt = (L + W_T - 1) / W_T;
-  const int gw = (int)blockIdx.x * B_NW + warp, GW = (int)gridDim.x * B_NW;
+  const int nwt = imin((L + W_T - 1) / W_T, wt1);
+  const int gw = wt0 + (int)blockIdx.x * B_NW + warp, GW = (int)gridDim.x * B_NW;
   if (lane == 0)
     for (int s = 0; s < 2; ++s) { const int t = gw + s * GW; if (t < nwt) w_issue(wsm + s * W_STAGE, &bar[s], t, rd, fa, do_gc); }
   auto count_slow = [&](int x) {       // value histogram, general form

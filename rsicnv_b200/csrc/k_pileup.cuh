@@ -26,7 +26,10 @@ struct ReadSoA {
   const u32* cigar_off; const u32* cigar;
   const u64* qual_off; const u8* qual;
   int* calend;   // bam_calend per read (pos + 1 for reads without CIGAR)
+  u16* ncig;     // n_cigar per read (clamped to 65535), written by k_read_ends; when cigar_off is null (the read summaries of a
+                 // split contig, rsigpu_split_run) the kernels that only need the NUMBER of ops read it from here
 };
+__device__ __forceinline__ int read_ncig(const ReadSoA& R, i64 r) { return R.cigar_off ? (int)(R.cigar_off[r + 1] - R.cigar_off[r]) : (int)R.ncig[r]; }
 enum { BF_PROPER = 2, BF_REV = 16, BF_MREV = 32, BF_SECONDARY = 256, BF_DUP = 1024 };
 enum { PU_T = 8192, PU_NT = 256 };
 
@@ -48,6 +51,7 @@ __global__ void k_read_ends(ReadSoA R, int* max_extent, int* sorted_bad) {
     for (u32 k = c0; k < c1; ++k) { const u32 op = R.cigar[k] & 15u, l = R.cigar[k] >> 4; if (op == 7 && l > eqmax) eqmax = l; }
     ext += eqmax;
     R.calend[r] = c1 > c0 ? (int)end : R.pos[r] + 1;
+    R.ncig[r] = (u16)(c1 - c0 > 65535u ? 65535u : c1 - c0);
     mx = imax(mx, (int)ext);
     if (r > 0 && R.pos[r] < R.pos[r - 1]) bad = 1;
   }
@@ -131,12 +135,13 @@ __global__ void k_tile_ranges(ReadSoA R, int L, const int* max_extent, int2* __r
   }
 }
 
+// tile0 .. tile1: the position tiles this launch covers (all of them, or one part of a contig split over several GPUs)
 __global__ void __launch_bounds__(PU_NT) k_pileup_tile(ReadSoA R, const u32* __restrict__ qmask, int* __restrict__ rd, int L, int minq,
-                                                        const int2* __restrict__ range) {
+                                                        const int2* __restrict__ range, int tile0, int tile1) {
   RSI_CTA_SETUP(c);
   __shared__ int diff[PU_T + 1 + (PU_T + 1) / 32 + 1];   // entry i lives at i + i/32: conflict-free 32-per-thread scan
-  const int ntiles = (L + PU_T - 1) / PU_T;
-  for (int tile = (int)blockIdx.x; tile < ntiles; tile += (int)gridDim.x) {
+  const int ntiles = imin((L + PU_T - 1) / PU_T, tile1);
+  for (int tile = tile0 + (int)blockIdx.x; tile < ntiles; tile += (int)gridDim.x) {
     const int t0 = tile * PU_T, t1 = imin(t0 + PU_T, L);
     c.sync();
     for (int k = c.tid; k < PU_T + 1 + (PU_T + 1) / 32 + 1; k += PU_NT) diff[k] = 0;
@@ -215,7 +220,7 @@ __global__ void __launch_bounds__(1024) k_isize_stats(ReadSoA R, int tid_len, co
         kept[k] = overl && !(mt != R.tid && mt > 0) && !(fl & BF_SECONDARY) && !(fl & BF_DUP);
         prop[k] = kept[k] && (fl & BF_PROPER) && mt == R.tid;
         isz[k] = R.isize[r];
-        const int rpe = (R.cigar_off[r + 1] > R.cigar_off[r]) ? (int)re : pos[k];   // bam_calend proper
+        const int rpe = read_ncig(R, r) > 0 ? (int)re : pos[k];   // bam_calend proper
         stopA[k] = kept[k] && (pos[k] >= tid_len || rpe >= tid_len);
         past[k] = (u32)pos[k] >= end;          // the iterator stops at the first read with pos >= end
         if (kept[k]) { ++nkept; lastkept = pos[k]; }
@@ -325,7 +330,7 @@ __global__ void __launch_bounds__(1024) k_cnv_stat(ReadSoA R, Cnv* calls, int nc
     const i64 rb = lo;
     u32 qall = 0, q0 = 0, rp = 0;
     for (i64 r = ra + c.tid; r < rb; r += c.nthr) {
-      const int nc = (int)(R.cigar_off[r + 1] - R.cigar_off[r]);
+      const int nc = read_ncig(R, r);
       const int rbeg = R.pos[r], rend = R.calend[r];
       if (!((u32)rend > (u32)p1e && (u32)rbeg < (u32)p2e)) continue;
       if (nc <= 1) continue;

@@ -79,6 +79,33 @@ __global__ void k_add_u64(u64* a, size_t n, u64 v) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) a[i] += v;
 }
 
+// ---- a contig split over several GPUs: partial tables of the parts are added on the lead
+__global__ void k_vec_add_u32(u32* __restrict__ dst, const u32* __restrict__ src, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] += src[i];
+}
+// phase 0: after pass A (sums of positive depths, stratum tables, depth range); 1: after pass B; 2: after pass C (largest bin sum)
+__global__ void k_split_reduce_state(DevState* lead, const DevState* parts, int nparts, int phase) {
+  for (int g = 0; g < nparts; ++g) {
+    const DevState* p = parts + g;
+    if (phase == 0) {
+      for (int k = (int)threadIdx.x; k < GC_STRATA; k += (int)blockDim.x) { lead->gc_sum[k] += p->gc_sum[k]; lead->gc_cnt[k] += p->gc_cnt[k]; }
+      if (threadIdx.x == 0) {
+        lead->pos_sum += p->pos_sum; lead->pos_cnt += p->pos_cnt;
+        if (p->rd_min < lead->rd_min) lead->rd_min = p->rd_min;
+        if (p->rd_max > lead->rd_max) lead->rd_max = p->rd_max;
+      }
+    }
+    if (phase == 2 && threadIdx.x == 0 && p->max_binsum > lead->max_binsum) lead->max_binsum = p->max_binsum;
+    if (threadIdx.x == 0) lead->err |= p->err;
+  }
+}
+// number of reads that start before `key` (the reads a part shares with its left neighbour)
+__global__ void k_count_before(const int* __restrict__ pos, long long n, int key, long long* out) {
+  long long lo = 0, hi = n;
+  while (lo < hi) { const long long mid = (lo + hi) >> 1; if (pos[mid] < key) lo = mid + 1; else hi = mid; }
+  *out = lo;
+}
+
 }  // namespace
 
 struct rsigpu_ctx {
@@ -111,7 +138,14 @@ struct rsigpu_ctx {
   std::vector<Cnv> h_detected, h_calls, h_dump[4];
   // reads
   DevVec<int> r_pos, r_mpos, r_isize, r_mtid; DevVec<u16> r_flag; DevVec<u8> r_mapq, r_qual; DevVec<u32> r_cigar_off, r_cigar; DevVec<u64> r_qual_off;
-  DevBuf<int> r_calend, d_tile_range; DevBuf<u32> d_qmask;
+  DevBuf<int> r_calend, d_tile_range; DevBuf<u32> d_qmask; DevBuf<u16> r_ncig;
+  // a contig split over several GPUs (rsigpu_split_run): on the lead, the read summaries of every part in position order
+  // (what the insert-size sample and cnv_stat read), and staging space for the parts' partial tables
+  DevBuf<int> s_pos, s_mpos, s_isize, s_mtid, s_calend; DevBuf<u16> s_flag; DevBuf<u8> s_mapq; DevBuf<u32> s_cigar_off;
+  size_t s_n = 0; bool use_summary = false;
+  DevBuf<DevState> d_part_st; DevBuf<u32> d_part_u32;
+  cudaEvent_t ev_part = nullptr, ev_lead = nullptr;
+  long long split_p2p_bytes = 0;
   // BAM decoder (k_bam.cuh): one chunk of BGZF blocks at a time
   DevBuf<u8> b_comp, b_U, b_carry, b_mapq, b_qual; DevBuf<BgzfBlock> b_blk; DevBuf<u16> b_flag, b_tabs; DevBuf<u32> b_cigoff, b_cig; DevBuf<u64> b_qoff;
   DevBuf<int> b_cnt, b_ncig, b_rbase, b_cbase, b_cnt32, b_runstart, b_tid, b_pos, b_mpos, b_isize, b_mtid;
@@ -214,9 +248,9 @@ int set_smem_attrs(int device) {
   cudaFuncSetAttribute(k_gc_table, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_A);
   cudaFuncSetAttribute(k_gc_adjust, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_B);
   cudaFuncSetAttribute(k_bins, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_C);
-  cudaFuncSetAttribute(k_bins_warp<101>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_CW);
-  cudaFuncSetAttribute(k_bins_warp<51>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_CW);
-  cudaFuncSetAttribute(k_bins_warp<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_CW);
+  cudaFuncSetAttribute(k_bins_warp<101>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(cw_nw(101) * cw_warp_bytes(101)));
+  cudaFuncSetAttribute(k_bins_warp<51>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(cw_nw(51) * cw_warp_bytes(51)));
+  cudaFuncSetAttribute(k_bins_warp<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(cw_nw(0) * cw_warp_bytes(0)));
   cudaFuncSetAttribute(k_cand_a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RSI_SMEM_CAND_A);
   cudaFuncSetAttribute(k_cand_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CAND_SHIST * 4));
   cudaFuncSetAttribute(k_cand_c, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CAND_SHIST * 4));
@@ -274,9 +308,17 @@ int run_rsi(rsigpu_ctx* c, int which, const float* t) {
 
 ReadSoA read_view(rsigpu_ctx* c) {
   ReadSoA R;
+  if (c->use_summary) {   // the lead of a split contig: summaries of all parts (no CIGAR ops, no qualities: the pileup is done)
+    R.n = (i64)c->s_n; R.tid = c->tid;
+    R.pos = c->s_pos.p; R.mpos = c->s_mpos.p; R.isize = c->s_isize.p; R.mtid = c->s_mtid.p; R.flag = c->s_flag.p; R.mapq = c->s_mapq.p;
+    R.cigar_off = nullptr; R.cigar = nullptr; R.qual_off = nullptr; R.qual = nullptr; R.calend = c->s_calend.p;
+    R.ncig = reinterpret_cast<u16*>(c->s_cigar_off.p);
+    return R;
+  }
   R.n = (i64)c->r_pos.n; R.tid = c->tid;
   R.pos = c->r_pos.p; R.mpos = c->r_mpos.p; R.isize = c->r_isize.p; R.mtid = c->r_mtid.p; R.flag = c->r_flag.p; R.mapq = c->r_mapq.p;
   R.cigar_off = c->r_cigar_off.p; R.cigar = c->r_cigar.p; R.qual_off = c->r_qual_off.p; R.qual = c->r_qual.p; R.calend = c->r_calend.p;
+  R.ncig = c->r_ncig.p;
   return R;
 }
 
@@ -315,6 +357,7 @@ int rsigpu_create(int device, const rsigpu_params* p, rsigpu_ctx** out) {
   set_smem_attrs(device);
   bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess && cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaEventCreate(&c->ev_reads) == cudaSuccess && cudaEventCreate(&c->ev_isize) == cudaSuccess;
+  ok = ok && cudaEventCreate(&c->ev_part) == cudaSuccess && cudaEventCreate(&c->ev_lead) == cudaSuccess;
   ok = ok && cudaMalloc((void**)&c->d_st, sizeof(DevState)) == cudaSuccess;
   ok = ok && cudaMallocHost((void**)&c->h_st, sizeof(DevState)) == cudaSuccess;
   for (int k = 0; k < 8 && ok; ++k) ok = cudaEventCreate(&c->ev[k]) == cudaSuccess;
@@ -344,7 +387,7 @@ void rsigpu_destroy(rsigpu_ctx* c) {
   c->d_bin_med.release(); c->d_bin_nbn.release(); c->d_lut.release(); c->d_bin_medint.release(); c->d_status.release(); c->d_status1.release();
   c->d_tile.release(); c->d_nz_idx.release(); c->d_nz_val.release(); c->d_runs.release(); c->d_bin_sum.release(); c->d_pfx.release(); c->d_cprof.release(); c->d_thr.release(); c->d_csum.release(); c->d_cchunk.release(); c->d_clx.release(); c->d_clbc.release(); c->d_clhist.release(); c->d_minl_del.release(); c->d_minl_dup.release();
   c->d_lists.release(); c->d_misc.release(); c->d_ref.release(); c->d_sub.release(); c->d_pref.release(); c->d_rm.release(); c->d_chist_c.release(); c->d_spec_ref.release(); c->d_spec_pref.release(); c->d_spec_off.release(); c->d_spec_rm.release();
-  c->d_nrun_beg.release(); c->d_nrun_end.release(); c->d_scan_scratch.release(); c->d_tile_range.release(); c->d_qmask.release(); c->r_calend.release();
+  c->d_nrun_beg.release(); c->d_nrun_end.release(); c->d_scan_scratch.release(); c->d_tile_range.release(); c->d_qmask.release(); c->r_calend.release(); c->r_ncig.release();
   c->r_pos.release(); c->r_mpos.release(); c->r_isize.release(); c->r_mtid.release(); c->r_flag.release(); c->r_mapq.release(); c->r_qual.release();
   c->r_cigar_off.release(); c->r_cigar.release(); c->r_qual_off.release();
   c->b_carry.release(); c->b_tabs.release(); c->b_cnt32.release();
@@ -358,6 +401,10 @@ void rsigpu_destroy(rsigpu_ctx* c) {
   for (int k = 0; k < 8; ++k) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
   if (c->ev_reads) cudaEventDestroy(c->ev_reads);
   if (c->ev_isize) cudaEventDestroy(c->ev_isize);
+  if (c->ev_part) cudaEventDestroy(c->ev_part);
+  if (c->ev_lead) cudaEventDestroy(c->ev_lead);
+  c->s_pos.release(); c->s_mpos.release(); c->s_isize.release(); c->s_mtid.release(); c->s_calend.release(); c->s_flag.release(); c->s_mapq.release(); c->s_cigar_off.release();
+  c->d_part_st.release(); c->d_part_u32.release();
   if (c->stream2) cudaStreamDestroy(c->stream2);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -372,6 +419,7 @@ int rsigpu_set_reference(rsigpu_ctx* c, const uint8_t* fasta, int32_t len, int32
   cudaSetDevice(c->device);
   c->L = len; c->tid = tid;
   c->have_ref = true; c->have_depth = false; c->have_reads = false; c->loaded = false; c->detected = false; c->filtered = false;
+  c->use_summary = false;
   const size_t padded = ((size_t)len + 15) / 16 * 16 + LD_T + 512;   // a whole tile beyond the last base is staged by the bulk copies
   CK(c->d_fasta.ensure(padded));
   CK(cudaMemsetAsync(c->d_fasta.p + len, 0, padded - (size_t)len, c->stream));
@@ -600,6 +648,36 @@ int rsigpu_bam_take(rsigpu_ctx* c, int32_t run, rsigpu_ctx* dst) {
   return push_impl(dst, &b, (size_t)(R.c1 - R.c0), (size_t)(R.q1 - R.q0), (u32)R.c0, (u64)R.q0, c->device);
 }
 
+// the records of a run whose pos lies in [pos_lo, pos_hi): what one part of a contig split over several GPUs stages
+int rsigpu_bam_take_range(rsigpu_ctx* c, int32_t run, rsigpu_ctx* dst, int32_t pos_lo, int32_t pos_hi) {
+  if (!c || !dst || run < 0 || run >= (int)c->b_runs.size()) return RSIGPU_E_ARG;
+  if (!dst->have_ref) { dst->fail("bam_take: call set_reference and pileup_begin on the destination first"); return RSIGPU_E_ARG; }
+  const rsigpu_ctx::BamRun& R = c->b_runs[(size_t)run];
+  const long long n = R.r1 - R.r0;
+  if (n == 0 || pos_hi <= pos_lo) return RSIGPU_OK;
+  cudaSetDevice(c->device);
+  long long* dcount = reinterpret_cast<long long*>(c->d_cprof.p);     // 16 x 8 bytes of scratch
+  KL(k_count_before, 1, 1, 0, c->b_pos.p + R.r0, n, pos_lo, dcount);
+  KL(k_count_before, 1, 1, 0, c->b_pos.p + R.r0, n, pos_hi, dcount + 1);
+  long long h[2] = {0, 0};
+  CK(cudaMemcpyAsync(h, dcount, 16, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  const long long i0 = h[0], i1 = h[1];
+  if (i1 <= i0) return RSIGPU_OK;
+  u32 co[2]; u64 qo[2];
+  CK(cudaMemcpyAsync(&co[0], c->b_cigoff.p + R.r0 + i0, 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(&co[1], c->b_cigoff.p + R.r0 + i1, 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(&qo[0], c->b_qoff.p + R.r0 + i0, 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(&qo[1], c->b_qoff.p + R.r0 + i1, 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  rsigpu_read_batch b; memset(&b, 0, sizeof b);
+  const long long a = R.r0 + i0;
+  b.n_reads = i1 - i0; b.tid = R.tid;
+  b.pos = c->b_pos.p + a; b.mpos = c->b_mpos.p + a; b.isize = c->b_isize.p + a; b.mtid = c->b_mtid.p + a; b.flag = c->b_flag.p + a; b.mapq = c->b_mapq.p + a;
+  b.cigar_off = c->b_cigoff.p + a; b.cigar = c->b_cig.p + co[0]; b.qual_off = reinterpret_cast<const uint64_t*>(c->b_qoff.p + a); b.qual = c->b_qual.p + qo[0];
+  return push_impl(dst, &b, (size_t)(co[1] - co[0]), (size_t)(qo[1] - qo[0]), co[0], qo[0], c->device);
+}
+
 int rsigpu_bam_end(rsigpu_ctx* c) {
   if (!c) return RSIGPU_E_ARG;
   const bool cut = c->b_active && c->b_tail_len > 0;
@@ -642,7 +720,7 @@ int rsigpu_pinned_alloc(size_t nbytes, void** out) {
 void rsigpu_pinned_free(void* p) { if (p) cudaFreeHost(p); }
 
 // the pileup kernels on the staged reads -> raw depth (a5)
-static int run_pileup(rsigpu_ctx* c) {
+static int run_pileup(rsigpu_ctx* c, int pt0 = 0, int pt1 = 0x7fffffff, bool with_isize = true) {
   cudaSetDevice(c->device);
   const size_t padded = ((size_t)c->L + LD_TILE - 1) / LD_TILE * LD_TILE + 64;
   CK(c->d_raw.ensure(padded));
@@ -653,19 +731,21 @@ static int run_pileup(rsigpu_ctx* c) {
   if (c->r_pos.n == 0) {
     CK(cudaMemsetAsync(c->d_raw.p, 0, padded * 4, c->stream));
   } else {
-    CK(c->r_calend.ensure(c->r_pos.n + 8));
+    CK(c->r_calend.ensure(c->r_pos.n + 8)); CK(c->r_ncig.ensure(c->r_pos.n + 8));
     ReadSoA R = read_view(c);
     KL(k_read_ends, grid_for((int)std::min<size_t>(c->r_pos.n, 1u << 30), 256, c->n_sm * 16), 256, 0, R, mx, mx + 1);
     // the insert-size sample (bam_rd_pr_stats) needs only the reads: it runs beside the depth pipeline on a second stream
-    CK(cudaEventRecord(c->ev_reads, c->stream));
-    CK(cudaStreamWaitEvent(c->stream2, c->ev_reads, 0));
-    {
-      cudaStream_t main_s = c->stream; c->stream = c->stream2;
-      KL(k_isize_stats, 1, 1024, 0, R, c->L, mx, c->d_misc.p + 16);
-      c->stream = main_s;
+    if (with_isize) {
+      CK(cudaEventRecord(c->ev_reads, c->stream));
+      CK(cudaStreamWaitEvent(c->stream2, c->ev_reads, 0));
+      {
+        cudaStream_t main_s = c->stream; c->stream = c->stream2;
+        KL(k_isize_stats, 1, 1024, 0, R, c->L, mx, c->d_misc.p + 16);
+        c->stream = main_s;
+      }
+      CK(cudaEventRecord(c->ev_isize, c->stream2));
+      c->isize_pending = true;
     }
-    CK(cudaEventRecord(c->ev_isize, c->stream2));
-    c->isize_pending = true;
     const int ntile = (c->L + PU_T - 1) / PU_T;
     CK(c->d_tile_range.ensure((size_t)ntile * 2 + 8));
     int2* tr = reinterpret_cast<int2*>(c->d_tile_range.p);
@@ -673,7 +753,8 @@ static int run_pileup(rsigpu_ctx* c) {
     const u64 nq = (u64)c->r_qual.n;
     CK(c->d_qmask.ensure((size_t)((nq + 31) >> 5) + 16));
     KL(k_qual_mask, c->n_sm * 16, 256, 0, c->r_qual.p, nq, c->P.min_baseQ, c->d_qmask.p);
-    KL(k_pileup_tile, grid_for(c->L, PU_T, c->n_sm * 6), PU_NT, 0, R, c->d_qmask.p, c->d_raw.p, c->L, c->P.minq, tr);
+    const int npt = std::min(ntile, pt1) - pt0;
+    if (npt > 0) KL(k_pileup_tile, std::min(npt, c->n_sm * 6), PU_NT, 0, R, c->d_qmask.p, c->d_raw.p, c->L, c->P.minq, tr, pt0, pt1);
   }
   c->have_depth = true;
   return RSIGPU_OK;
@@ -700,22 +781,15 @@ int rsigpu_pileup_commit(rsigpu_ctx* c) {
   return RSIGPU_OK;
 }
 
-// a7 + a8 + a9 + chromosome statistics + bin arrays (median_transfer, negative_binomial_transfer)
-int rsigpu_load_finish(rsigpu_ctx* c) {
-  if (!c) return RSIGPU_E_ARG;
-  if (c->have_ref && c->have_reads && !c->have_depth) { int rc = run_pileup(c); if (rc) return rc; }
-  if (!c->have_ref || !c->have_depth) { c->fail("load_finish: no reference or depth staged"); return RSIGPU_E_ARG; }
-  cudaSetDevice(c->device);
+// a7 + a8 + a9 + chromosome statistics + bin arrays (median_transfer, negative_binomial_transfer), in phases: the per-base
+// passes take a range so that one contig can be spread over several GPUs (rsigpu_split_run); rsigpu_load_finish is all
+// phases over the whole contig on one context.
+static int lf_prepare(rsigpu_ctx* c) {
   const int L = c->L, nb = c->nb, nn = (int)c->h_nbeg.size(), m = c->P.m;
-  // buffers
   CK(c->d_rdc.ensure((size_t)c->Lc + 64));
   CK(c->d_bin_med.ensure(nb + 8)); CK(c->d_bin_nbn.ensure(nb + 8)); CK(c->d_bin_medint.ensure(nb + 8)); CK(c->d_bin_sum.ensure(nb + 8));
   CK(c->d_status.ensure(nb + 8)); CK(c->d_status1.ensure(nb + 8)); CK(c->d_nz_idx.ensure(nb + 8)); CK(c->d_nz_val.ensure(nb + 8)); CK(c->d_tile.ensure(nb / 1024 + 8));
   CK(c->d_scan_scratch.ensure((size_t)((nb + S_T - 1) / S_T) * 10 * S_NB + 64)); CK(c->d_minl_del.ensure(nb + 8)); CK(c->d_minl_dup.ensure(nb + 8)); CK(c->d_pfx.ensure((size_t)nb + LIST_CAP + 8));
-  CK(c->d_ref.ensure((size_t)c->Lc + 64)); CK(c->d_pref.ensure((size_t)c->Lc + 64)); CK(c->d_rm.ensure((size_t)c->Lc + 64));
-  CK(c->d_spec_ref.ensure(2 * (size_t)c->Lc + 128)); CK(c->d_spec_pref.ensure(2 * (size_t)c->Lc + LIST_CAP + 128)); CK(c->d_spec_rm.ensure(2 * (size_t)c->Lc + 128));
-  CK(c->d_spec_off.ensure(LIST_CAP + 8));
-  // device state
   DevState* h = c->h_st;
   memset(h, 0, sizeof(DevState));
   h->L = L; h->Lc = c->Lc; h->nb = nb; h->m = m; h->n_noseq = nn; h->gc_on = c->P.gcadjust ? 1 : 0; h->cap_on = c->P.cap > 1 ? 1 : 0;
@@ -731,29 +805,56 @@ int rsigpu_load_finish(rsigpu_ctx* c) {
   CK(cudaMemsetAsync(c->d_chist.p, 0, (size_t)MAD_CLASSES * CHIST_RCAP * 4, c->stream));
   CK(cudaMemsetAsync(c->d_thist.p, 0, (size_t)CHIST_RCAP * 4, c->stream));
   CK(cudaMemsetAsync(c->d_misc.p, 0, 5 * 4, c->stream));
+  return RSIGPU_OK;
+}
+static int lf_candidate_scratch(rsigpu_ctx* c) {   // what only the context that runs the candidate stage needs
+  CK(c->d_ref.ensure((size_t)c->Lc + 64)); CK(c->d_pref.ensure((size_t)c->Lc + 64)); CK(c->d_rm.ensure((size_t)c->Lc + 64));
+  CK(c->d_spec_ref.ensure(2 * (size_t)c->Lc + 128)); CK(c->d_spec_pref.ensure(2 * (size_t)c->Lc + LIST_CAP + 128)); CK(c->d_spec_rm.ensure(2 * (size_t)c->Lc + 128));
+  CK(c->d_spec_off.ensure(LIST_CAP + 8));
+  return RSIGPU_OK;
+}
+static int lf_pass_a(rsigpu_ctx* c, int wt0, int wt1) {
+  const int nw = std::min((c->L + W_T - 1) / W_T, wt1) - wt0;
+  if (nw > 0) KL(k_gc_table, std::min((nw + A_NW - 1) / A_NW, c->n_sm), A_NT, RSI_SMEM_A, c->d_raw.p, c->d_fasta.p, c->d_st, wt0, wt1);
+  return RSIGPU_OK;
+}
+static int lf_finalize_a(rsigpu_ctx* c) { KL(k_gc_finalize, 1, 256, 0, c->d_fasta.p, c->d_st); return RSIGPU_OK; }
+static int lf_pass_b(rsigpu_ctx* c, int wt0, int wt1) {
+  const int nn = (int)c->h_nbeg.size();
   const int* nbeg = c->d_nseq.p; const int* nend = nbeg + nn; const int* ncum = nbeg + 2 * nn;
-  const size_t smA = RSI_SMEM_A, smB = RSI_SMEM_B;
-  const int nwt = (L + W_T - 1) / W_T;     // warp-tiles: every warp of the two per-base passes is its own pipeline
-  KL(k_gc_table, std::min((nwt + A_NW - 1) / A_NW, c->n_sm), A_NT, smA, c->d_raw.p, c->d_fasta.p, c->d_st);
-  KL(k_gc_finalize, 1, 256, 0, c->d_fasta.p, c->d_st);
-  KL(k_gc_adjust, std::min((nwt + B_NW - 1) / B_NW, c->n_sm), B_NT, smB, c->d_raw.p, c->d_fasta.p, c->d_rdc.p, nbeg, nend, ncum, c->d_hist_all.p, c->d_st);
-  KL(k_cap_params, 1, 1024, 0, c->d_hist_all.p, c->d_st, CHIST_RCAP);
-  const int bpt = std::max(1, std::min((int)C_BINS, (C_CAP - 4) / m));     // bpt * m + 3 words fit a stage
-  const int ntc = std::max(1, (nb + bpt - 1) / bpt + 1);
+  const int nw = std::min((c->L + W_T - 1) / W_T, wt1) - wt0;
+  if (nw > 0) KL(k_gc_adjust, std::min((nw + B_NW - 1) / B_NW, c->n_sm), B_NT, RSI_SMEM_B, c->d_raw.p, c->d_fasta.p, c->d_rdc.p, nbeg, nend, ncum, c->d_hist_all.p, c->d_st, wt0, wt1);
+  return RSIGPU_OK;
+}
+static int lf_cap(rsigpu_ctx* c) { KL(k_cap_params, 1, 1024, 0, c->d_hist_all.p, c->d_st, CHIST_RCAP); return RSIGPU_OK; }
+// pass C works on tiles of `unit` bins (lf_c_unit); the pseudo-tile after the last bin tile owns the bases beyond nb * m
+static int lf_c_unit(const rsigpu_ctx* c) { return c->P.m <= 127 ? (int)CW_BINS : std::max(1, std::min((int)C_BINS, (C_CAP - 4) / c->P.m)); }
+static int lf_c_tiles(const rsigpu_ctx* c) { const int u = lf_c_unit(c); return (c->nb + u - 1) / u + 1; }
+static int lf_pass_c(rsigpu_ctx* c, int t0, int t1) {
+  const int m = c->P.m, unit = lf_c_unit(c);
+  const int nt = std::min(lf_c_tiles(c), t1) - t0;
+  if (nt <= 0) return RSIGPU_OK;
   if (m <= 127) {   // every warp its own pipeline: warp-tiles of CW_BINS bins
-    const int nwtc = (nb + CW_BINS - 1) / CW_BINS + 1;
-    const int gcw = std::min((nwtc + CW_NW - 1) / CW_NW, c->n_sm);
-    if (m == 101) KL(k_bins_warp<101>, gcw, CW_NT, RSI_SMEM_CW, c->d_rdc.p, c->d_bin_med.p, c->d_bin_medint.p, c->d_bin_sum.p, c->d_chist.p, c->d_thist.p, c->d_st);
-    else if (m == 51) KL(k_bins_warp<51>, gcw, CW_NT, RSI_SMEM_CW, c->d_rdc.p, c->d_bin_med.p, c->d_bin_medint.p, c->d_bin_sum.p, c->d_chist.p, c->d_thist.p, c->d_st);
-    else KL(k_bins_warp<0>, gcw, CW_NT, RSI_SMEM_CW, c->d_rdc.p, c->d_bin_med.p, c->d_bin_medint.p, c->d_bin_sum.p, c->d_chist.p, c->d_thist.p, c->d_st);
+#define RSI_BINS_WARP(M)                                                                                                                     \
+  KL(k_bins_warp<M>, std::min((nt + cw_nw(M) - 1) / cw_nw(M), c->n_sm), cw_nw(M) * 32, cw_nw(M) * cw_warp_bytes(M), c->d_rdc.p, c->d_bin_med.p, \
+     c->d_bin_medint.p, c->d_bin_sum.p, c->d_chist.p, c->d_thist.p, c->d_st, t0, t1)
+    if (m == 101) RSI_BINS_WARP(101);
+    else if (m == 51) RSI_BINS_WARP(51);
+    else RSI_BINS_WARP(0);
+#undef RSI_BINS_WARP
   } else {
-    KL(k_bins, std::min(ntc, c->n_sm), C_NT, RSI_SMEM_C, c->d_rdc.p, c->d_bin_med.p, c->d_bin_medint.p, c->d_bin_sum.p, c->d_chist.p,
-       c->d_thist.p, c->d_st, bpt);
+    KL(k_bins, std::min(nt, c->n_sm), C_NT, RSI_SMEM_C, c->d_rdc.p, c->d_bin_med.p, c->d_bin_medint.p, c->d_bin_sum.p, c->d_chist.p,
+       c->d_thist.p, c->d_st, unit, t0, t1);
   }
+  return RSIGPU_OK;
+}
+static int lf_finish(rsigpu_ctx* c) {
+  DevState* h = c->h_st;
+  const int nb = c->nb, m = c->P.m;
   KL(k_chr_stats, 1, 1024, 0, c->d_chist.p, c->d_thist.p, c->d_tothist.p, c->d_st);
   CK(cudaMemcpyAsync(h, c->d_st, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  if (c->have_reads) {
+  if (c->have_reads && !c->use_summary) {
     int sb = 0;
     CK(cudaMemcpyAsync(&sb, c->d_misc.p + 6, 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -792,6 +893,17 @@ int rsigpu_load_finish(rsigpu_ctx* c) {
   CK(cudaEventRecord(c->ev[2], c->stream));
   c->loaded = true; c->detected = false; c->filtered = false;
   return RSIGPU_OK;
+}
+
+int rsigpu_load_finish(rsigpu_ctx* c) {
+  if (!c) return RSIGPU_E_ARG;
+  if (c->have_ref && c->have_reads && !c->have_depth) { int rc = run_pileup(c); if (rc) return rc; }
+  if (!c->have_ref || !c->have_depth) { c->fail("load_finish: no reference or depth staged"); return RSIGPU_E_ARG; }
+  cudaSetDevice(c->device);
+  int rc;
+  if ((rc = lf_prepare(c)) || (rc = lf_candidate_scratch(c))) return rc;
+  if ((rc = lf_pass_a(c, 0, 0x7fffffff)) || (rc = lf_finalize_a(c)) || (rc = lf_pass_b(c, 0, 0x7fffffff)) || (rc = lf_cap(c)) || (rc = lf_pass_c(c, 0, 0x7fffffff))) return rc;
+  return lf_finish(c);
 }
 
 // detectcnv (rsi.cpp:1795-1945) incl. the list that sd_filters would keep
@@ -876,7 +988,7 @@ int rsigpu_cnv_stat(rsigpu_ctx* c) {
   cudaSetDevice(c->device);
   std::vector<Cnv>& v = c->filtered ? c->h_calls : c->h_detected;
   Cnv* d = c->filtered ? c->list(8) : c->list(7);
-  if (v.empty() || c->r_pos.n == 0) return RSIGPU_OK;
+  if (v.empty() || (c->use_summary ? c->s_n : c->r_pos.n) == 0) return RSIGPU_OK;
   ReadSoA R = read_view(c);
   int* mx = c->d_misc.p + 5;
   if (c->isize_pending) { CK(cudaStreamWaitEvent(c->stream, c->ev_isize, 0)); c->isize_pending = false; }
@@ -901,7 +1013,7 @@ int rsigpu_stat_calls(rsigpu_ctx* c, rsigpu_cnv* list, int32_t n) {
   if (n == 0 || c->r_pos.n == 0) return RSIGPU_OK;
   if (n > LIST_CAP * 8) { c->fail("stat_calls: more than 524288 calls"); return RSIGPU_E_RANGE; }
   cudaSetDevice(c->device);
-  CK(c->r_calend.ensure(c->r_pos.n + 8));
+  CK(c->r_calend.ensure(c->r_pos.n + 8)); CK(c->r_ncig.ensure(c->r_pos.n + 8));
   ReadSoA R = read_view(c);
   int* mx = c->d_misc.p + 5;
   if (c->isize_pending) { CK(cudaStreamWaitEvent(c->stream, c->ev_isize, 0)); c->isize_pending = false; }
@@ -956,6 +1068,231 @@ int rsigpu_run(rsigpu_ctx* c, rsigpu_cnv* out, int32_t cap, int32_t* n) {
   cudaEventElapsedTime(&ms, c->ev[0], c->ev[5]); c->stage_ms[5] = ms;
   return rsigpu_get_calls(c, out, cap, n);
 }
+
+// ---------------------------------------------------------------------------------------------
+// One contig over several GPUs (north_star: "chromosomes larger than one shard are split with halo exchange ... over NVLink
+// P2P").  Every part context holds the whole FASTA and full-length arrays but STAGES only the reads (or uses only the depth)
+// of its own base range, and runs the per-base work -- pileup, passes A, B, C -- on that range.  What the passes accumulate
+// is integer (sums and counts per GC stratum, the value histograms, bin sums): the parts' partial tables are copied to the
+// lead over peer-to-peer and added there, which is exact, the lead derives the few scalars (stratum table, cap, medians) and
+// sends the state back.  Halo: pass C works on whole bins of the N-compacted array, so a part needs the first few hundred
+// compacted values of its right neighbour (the bins that straddle the cut).  After pass C the lead gathers the compacted
+// depth, the bin arrays and the read summaries and runs the bin-level and candidate stages exactly as for an unsplit contig:
+// the result is bit-identical.  Cuts are multiples of 57344 bases (whole pileup tiles and whole warp-tiles).
+enum { SPLIT_ALIGN = 57344, SPLIT_HALO = 65536 };
+static int split_point(int L, int n, int g) {
+  if (g <= 0) return 0;
+  if (g >= n) return L;
+  const long long s = ((long long)L * g / n + SPLIT_ALIGN / 2) / SPLIT_ALIGN * SPLIT_ALIGN;
+  return (int)std::min<long long>(s, (long long)L);
+}
+int rsigpu_split_range(int32_t L, int32_t n_parts, int32_t part, int32_t* beg, int32_t* end, int32_t* read_halo) {
+  if (n_parts < 1 || part < 0 || part >= n_parts || L < 1 || !beg || !end) return RSIGPU_E_ARG;
+  if ((long long)L < 2ll * SPLIT_ALIGN * n_parts) return RSIGPU_E_RANGE;
+  *beg = split_point(L, n_parts, part); *end = split_point(L, n_parts, part + 1);
+  if (read_halo) *read_halo = SPLIT_HALO;
+  return RSIGPU_OK;
+}
+
+namespace {
+// `dst`'s stream waits for everything queued so far on `src`'s stream (the two may sit on different devices)
+int split_dep(rsigpu_ctx* src, rsigpu_ctx* dst) {
+  rsigpu_ctx* c = src;
+  cudaSetDevice(src->device);
+  CK(cudaEventRecord(src->ev_part, src->stream));
+  cudaSetDevice(dst->device);
+  CK(cudaStreamWaitEvent(dst->stream, src->ev_part, 0));
+  return RSIGPU_OK;
+}
+int split_copy(rsigpu_ctx* lead, rsigpu_ctx* dst, void* d, rsigpu_ctx* src, const void* s_, size_t bytes) {
+  rsigpu_ctx* c = dst;
+  if (!bytes) return RSIGPU_OK;
+  cudaSetDevice(dst->device);
+  CK(cudaMemcpyPeerAsync(d, dst->device, s_, src->device, bytes, dst->stream));
+  if (dst->device != src->device) lead->split_p2p_bytes += (long long)bytes;
+  return RSIGPU_OK;
+}
+// lead += the parts' DevState fields of `phase`, then every part gets the lead's state
+int split_reduce_state(rsigpu_ctx** parts, int n, int phase, bool finalize_a, bool cap) {
+  rsigpu_ctx* lead = parts[0]; rsigpu_ctx* c = lead;
+  int rc;
+  for (int g = 1; g < n; ++g) {
+    if ((rc = split_dep(parts[g], lead))) return rc;
+    if ((rc = split_copy(lead, lead, lead->d_part_st.p + (g - 1), parts[g], parts[g]->d_st, sizeof(DevState)))) return rc;
+  }
+  cudaSetDevice(lead->device);
+  KL(k_split_reduce_state, 1, 256, 0, lead->d_st, lead->d_part_st.p, n - 1, phase);
+  if (finalize_a && (rc = lf_finalize_a(lead))) return rc;
+  if (cap && (rc = lf_cap(lead))) return rc;
+  for (int g = 1; g < n; ++g) {
+    if ((rc = split_dep(lead, parts[g]))) return rc;
+    if ((rc = split_copy(lead, parts[g], parts[g]->d_st, lead, lead->d_st, sizeof(DevState)))) return rc;
+  }
+  return RSIGPU_OK;
+}
+int split_add_u32(rsigpu_ctx* lead, rsigpu_ctx* part, u32* dst, const u32* src, size_t n) {   // dst (lead) += src (part); the dependency is already in place
+  rsigpu_ctx* c = lead;
+  int rc;
+  if ((rc = split_copy(lead, lead, lead->d_part_u32.p, part, src, n * 4))) return rc;
+  cudaSetDevice(lead->device);
+  KL(k_vec_add_u32, grid_for((int)n, 1024, lead->n_sm * 4), 256, 0, dst, lead->d_part_u32.p, n);
+  return RSIGPU_OK;
+}
+long long compact_index(const rsigpu_ctx* c, int s) {   // number of non-N positions before s
+  long long removed = 0;
+  for (size_t k = 0; k < c->h_nbeg.size(); ++k) {
+    if (c->h_nbeg[k] >= s) break;
+    removed += (long long)std::min(c->h_nend[k], s - 1) - c->h_nbeg[k] + 1;
+  }
+  return (long long)s - removed;
+}
+}  // namespace
+
+int rsigpu_split_run(rsigpu_ctx** parts, int32_t n, rsigpu_cnv* out, int32_t cap, int32_t* n_out) {
+  if (!parts || n < 1 || !parts[0]) return RSIGPU_E_ARG;
+  if (n == 1) return rsigpu_run(parts[0], out, cap, n_out);
+  rsigpu_ctx* lead = parts[0]; rsigpu_ctx* c = lead;
+  const int L = lead->L;
+  for (int g = 0; g < n; ++g) {
+    rsigpu_ctx* p = parts[g];
+    if (!p || !p->have_ref || p->L != L || p->Lc != lead->Lc || p->P.m != lead->P.m) { lead->fail("split_run: every part needs the same reference and parameters"); return RSIGPU_E_ARG; }
+    if (p->have_reads != lead->have_reads || (!p->have_reads && !p->have_depth)) { lead->fail("split_run: every part needs its reads (or the depth) staged"); return RSIGPU_E_ARG; }
+    for (int q = 0; q < g; ++q) if (parts[q] == p) { lead->fail("split_run: a context appears twice"); return RSIGPU_E_ARG; }
+  }
+  if ((long long)L < 2ll * SPLIT_ALIGN * n) { lead->fail("split_run: contig too short for this many parts"); return RSIGPU_E_RANGE; }
+  const bool reads = lead->have_reads;
+  int rc;
+  TRACE(lead, "split_run: start");
+  // peer access (direct NVLink copies; without it the peer copies are staged through the host)
+  for (int g = 0; g < n; ++g) for (int q = 0; q < n; ++q) if (parts[g]->device != parts[q]->device) {
+    cudaSetDevice(parts[g]->device);
+    int can = 0; cudaDeviceCanAccessPeer(&can, parts[g]->device, parts[q]->device);
+    if (can) { cudaError_t e = cudaDeviceEnablePeerAccess(parts[q]->device, 0); if (e != cudaSuccess) cudaGetLastError(); }
+  }
+  cudaSetDevice(lead->device);
+  lead->split_p2p_bytes = 0; lead->use_summary = false;
+  CK(lead->d_part_st.ensure((size_t)n)); CK(lead->d_part_u32.ensure((size_t)MAD_CLASSES * CHIST_RCAP + 8));
+  CK(cudaEventRecord(lead->ev[0], lead->stream));
+  std::vector<int> cut((size_t)n + 1);
+  for (int g = 0; g <= n; ++g) cut[(size_t)g] = split_point(L, n, g);
+  // ---- pileup + pass A on every part's own range
+  for (int g = 0; g < n; ++g) {
+    rsigpu_ctx* p = parts[g]; c = p;
+    cudaSetDevice(p->device);
+    p->use_summary = false; p->pileup_fresh = false;
+    if (reads && (rc = run_pileup(p, cut[(size_t)g] / PU_T, g + 1 < n ? cut[(size_t)g + 1] / PU_T : 0x7fffffff, false))) { if (p != lead) lead->fail(p->err); return rc; }
+    if ((rc = lf_prepare(p)) || (rc = lf_pass_a(p, cut[(size_t)g] / W_T, g + 1 < n ? cut[(size_t)g + 1] / W_T : 0x7fffffff))) { if (p != lead) lead->fail(p->err); return rc; }
+  }
+  c = lead;
+  if ((rc = split_reduce_state(parts, n, 0, true, false))) return rc;
+  // ---- pass B
+  for (int g = 0; g < n; ++g) {
+    cudaSetDevice(parts[g]->device);
+    if ((rc = lf_pass_b(parts[g], cut[(size_t)g] / W_T, g + 1 < n ? cut[(size_t)g + 1] / W_T : 0x7fffffff))) { if (parts[g] != lead) lead->fail(parts[g]->err); return rc; }
+  }
+  for (int g = 1; g < n; ++g) {
+    if ((rc = split_dep(parts[g], lead))) return rc;
+    if ((rc = split_add_u32(lead, parts[g], lead->d_hist_all.p, parts[g]->d_hist_all.p, (size_t)HIST_ALL_BINS))) return rc;
+  }
+  if ((rc = split_reduce_state(parts, n, 1, false, true))) return rc;
+  // ---- pass C on whole tiles of bins; the bins that straddle a cut need the right neighbour's first compacted values
+  const int unit = lf_c_unit(lead), ntile_c = lf_c_tiles(lead), m = lead->P.m;
+  std::vector<int> ct((size_t)n + 1); std::vector<long long> cc((size_t)n + 1);
+  for (int g = 0; g <= n; ++g) cc[(size_t)g] = g == n ? (long long)lead->Lc : compact_index(lead, cut[(size_t)g]);
+  ct[0] = 0; ct[(size_t)n] = ntile_c;
+  for (int g = 1; g < n; ++g) ct[(size_t)g] = (int)std::min<long long>((cc[(size_t)g] + (long long)unit * m - 1) / ((long long)unit * m), (long long)ntile_c - 1);
+  for (int g = 0; g + 1 < n; ++g) {
+    const long long a = cc[(size_t)g + 1], b = std::min<long long>((long long)ct[(size_t)g + 1] * unit * m, (long long)lead->Lc);
+    if (b > cc[(size_t)g + 2]) { lead->fail("split_run: parts too small for the bin size"); return RSIGPU_E_RANGE; }
+    if (b > a) {
+      if ((rc = split_dep(parts[g + 1], parts[g]))) return rc;
+      if ((rc = split_copy(lead, parts[g], parts[g]->d_rdc.p + a, parts[g + 1], parts[g + 1]->d_rdc.p + a, (size_t)(b - a) * 4))) return rc;
+      // the neighbour must not start capping (pass C writes the capped values back) before its uncapped values have been copied
+      if ((rc = split_dep(parts[g], parts[g + 1]))) return rc;
+    }
+  }
+  for (int g = 0; g < n; ++g) {
+    cudaSetDevice(parts[g]->device);
+    if ((rc = lf_pass_c(parts[g], ct[(size_t)g], ct[(size_t)g + 1]))) { if (parts[g] != lead) lead->fail(parts[g]->err); return rc; }
+  }
+  // ---- gather on the lead: compacted depth, bin arrays, class histograms
+  for (int g = 1; g < n; ++g) {
+    rsigpu_ctx* p = parts[g];
+    if ((rc = split_dep(p, lead))) return rc;
+    const long long a = std::min<long long>((long long)ct[(size_t)g] * unit * m, (long long)lead->Lc), b = g + 1 < n ? std::min<long long>((long long)ct[(size_t)g + 1] * unit * m, (long long)lead->Lc) : (long long)lead->Lc;
+    if ((rc = split_copy(lead, lead, lead->d_rdc.p + a, p, p->d_rdc.p + a, (size_t)std::max<long long>(b - a, 0) * 4))) return rc;
+    const long long b0 = std::min<long long>((long long)ct[(size_t)g] * unit, (long long)lead->nb), b1 = std::min<long long>((long long)ct[(size_t)g + 1] * unit, (long long)lead->nb);
+    if (b1 > b0) {
+      if ((rc = split_copy(lead, lead, lead->d_bin_med.p + b0, p, p->d_bin_med.p + b0, (size_t)(b1 - b0) * 4))) return rc;
+      if ((rc = split_copy(lead, lead, lead->d_bin_medint.p + b0, p, p->d_bin_medint.p + b0, (size_t)(b1 - b0) * 4))) return rc;
+      if ((rc = split_copy(lead, lead, lead->d_bin_sum.p + b0, p, p->d_bin_sum.p + b0, (size_t)(b1 - b0) * 8))) return rc;
+    }
+    if ((rc = split_add_u32(lead, p, lead->d_chist.p, p->d_chist.p, (size_t)MAD_CLASSES * CHIST_RCAP))) return rc;
+    if ((rc = split_add_u32(lead, p, lead->d_thist.p, p->d_thist.p, (size_t)CHIST_RCAP))) return rc;
+  }
+  if ((rc = split_reduce_state(parts, n, 2, false, false))) return rc;
+  // ---- read summaries of the whole contig on the lead (insert-size sample, RP / Q0): a part owns the reads that start in its range
+  cudaSetDevice(lead->device);
+  if (reads) {
+    std::vector<long long> skip((size_t)n, 0), cnt((size_t)n, 0);
+    long long total = 0; int mxe[2] = {0, 0};
+    for (int g = 0; g < n; ++g) {
+      rsigpu_ctx* p = parts[g]; c = p;
+      cudaSetDevice(p->device);
+      long long h = 0; int pm[2] = {0, 0};
+      if (p->r_pos.n) {
+        if (g > 0) {
+          long long* dcount = reinterpret_cast<long long*>(p->d_cprof.p);
+          KL(k_count_before, 1, 1, 0, p->r_pos.p, (long long)p->r_pos.n, cut[(size_t)g], dcount);
+          CK(cudaMemcpyAsync(&h, dcount, 8, cudaMemcpyDeviceToHost, p->stream));
+        }
+        CK(cudaMemcpyAsync(pm, p->d_misc.p + 5, 8, cudaMemcpyDeviceToHost, p->stream));
+        CK(cudaStreamSynchronize(p->stream));
+      }
+      if (pm[1]) { lead->fail("read batch is not sorted by position"); return RSIGPU_E_ARG; }
+      if (pm[0] > SPLIT_HALO) { lead->fail("split_run: a read reaches further than the halo of 65536 bases"); return RSIGPU_E_RANGE; }
+      mxe[0] = std::max(mxe[0], pm[0]);
+      skip[(size_t)g] = h; cnt[(size_t)g] = (long long)p->r_pos.n - h; total += cnt[(size_t)g];
+    }
+    c = lead;
+    cudaSetDevice(lead->device);
+    const size_t tn = (size_t)total;
+    CK(lead->s_pos.ensure(tn + 8)); CK(lead->s_mpos.ensure(tn + 8)); CK(lead->s_isize.ensure(tn + 8)); CK(lead->s_mtid.ensure(tn + 8)); CK(lead->s_calend.ensure(tn + 8));
+    CK(lead->s_flag.ensure(tn + 8)); CK(lead->s_mapq.ensure(tn + 8)); CK(lead->s_cigar_off.ensure(tn / 2 + 8));   // (holds the u16 n_cigar of every read)
+    long long o = 0;
+    for (int g = 0; g < n; ++g) {
+      rsigpu_ctx* p = parts[g]; const size_t h = (size_t)skip[(size_t)g], k = (size_t)cnt[(size_t)g];
+      if (p != lead && (rc = split_dep(p, lead))) return rc;
+      if ((rc = split_copy(lead, lead, lead->s_pos.p + o, p, p->r_pos.p + h, k * 4)) || (rc = split_copy(lead, lead, lead->s_mpos.p + o, p, p->r_mpos.p + h, k * 4)) ||
+          (rc = split_copy(lead, lead, lead->s_isize.p + o, p, p->r_isize.p + h, k * 4)) || (rc = split_copy(lead, lead, lead->s_mtid.p + o, p, p->r_mtid.p + h, k * 4)) ||
+          (rc = split_copy(lead, lead, lead->s_calend.p + o, p, p->r_calend.p + h, k * 4)) || (rc = split_copy(lead, lead, lead->s_flag.p + o, p, p->r_flag.p + h, k * 2)) ||
+          (rc = split_copy(lead, lead, lead->s_mapq.p + o, p, p->r_mapq.p + h, k)) ||
+          (rc = split_copy(lead, lead, reinterpret_cast<u16*>(lead->s_cigar_off.p) + o, p, p->r_ncig.p + h, k * 2))) return rc;
+      o += (long long)k;
+    }
+    lead->s_n = tn; lead->use_summary = true;
+    CK(cudaMemcpyAsync(lead->d_misc.p + 5, mxe, 8, cudaMemcpyHostToDevice, lead->stream));
+    CK(cudaStreamSynchronize(lead->stream));     // (mxe is a stack array)
+    if (tn) {
+      ReadSoA R = read_view(lead);
+      KL(k_isize_stats, 1, 1024, 0, R, lead->L, lead->d_misc.p + 5, lead->d_misc.p + 16);
+    }
+  }
+  // ---- from here on the lead alone, exactly as for an unsplit contig
+  if ((rc = lf_candidate_scratch(lead)) || (rc = lf_finish(lead))) return rc;
+  if ((rc = rsigpu_detectcnv(lead)) != RSIGPU_OK) return rc;
+  if ((rc = rsigpu_sd_filters(lead)) != RSIGPU_OK) return rc;
+  if (reads && (rc = rsigpu_cnv_stat(lead)) != RSIGPU_OK) return rc;
+  CK(cudaEventRecord(lead->ev[5], lead->stream));
+  CK(cudaStreamSynchronize(lead->stream));
+  for (int g = 1; g < n; ++g) { cudaSetDevice(parts[g]->device); cudaStreamSynchronize(parts[g]->stream); }
+  cudaSetDevice(lead->device);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, lead->ev[0], lead->ev[5]); lead->stage_ms[5] = ms;
+  TRACE(lead, "split_run: end");
+  return rsigpu_get_calls(lead, out, cap, n_out);
+}
+long long rsigpu_split_p2p_bytes(const rsigpu_ctx* lead) { return lead ? lead->split_p2p_bytes : 0; }
 
 int rsigpu_get_chr_stats(rsigpu_ctx* c, rsigpu_chr_stats* o) {
   if (!c || !o) return RSIGPU_E_ARG;

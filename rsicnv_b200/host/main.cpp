@@ -38,7 +38,7 @@ namespace {
 struct Opt {
   std::string function = "rsi", rdfile, bamfile, reffile, cnvfile, outfile = "rsiout.txt", chr = "1-22XY";
   bool saverd = false, hostdecode = false;
-  int gpus = 1, threads = 8;
+  int gpus = 1, threads = 8, split = 1;
   rsigpu_params P;
 };
 
@@ -48,7 +48,7 @@ int usage() {
           "Options:\n   -o  STR  outputfile [rsiout.txt]\n   -c  STR  chromosome [1-22XY]\n   -m  INT  bin size, odd [101]\n"
           "   -q  INT  minimum mapping quality [0]\n   -Q  INT  minimum base quality [13]\n   -cap FLT cap depth at FLT x median, <=1 off [4]\n"
           "   -NOGC    no GC adjustment\n   -MED | -NB | -ALL  transformation [NB]\n   -s       save raw depth to <out>.<chr>_rd (BAM input)\n"
-          "   -gpus INT  GPUs to shard contigs over [1]\n   -hostdecode  inflate/parse the BAM on the host (zlib, -threads INT [8]) instead of on the GPU\n");
+          "   -gpus INT  GPUs to shard contigs over [1]\n   -split INT  spread EVERY contig over INT GPUs instead (base ranges + halos, identical table) [1]\n   -hostdecode  inflate/parse the BAM on the host (zlib, -threads INT [8]) instead of on the GPU\n");
   return 0;
 }
 
@@ -87,6 +87,7 @@ bool parse(int argc, char** argv, Opt* o) {
     if (k == "-nomerge") { o->P.merge = 0; a[i] = ""; continue; }
     if (k == "-NOGC") { o->P.gcadjust = 0; a[i] = ""; continue; }
     if (k == "-gpus") { o->gpus = atoi(val(i).c_str()); two(); continue; }
+    if (k == "-split") { o->split = atoi(val(i).c_str()); two(); continue; }
     if (k == "-threads") { o->threads = atoi(val(i).c_str()); two(); continue; }
     if (k == "-hostdecode") { o->hostdecode = true; a[i] = ""; continue; }
   }
@@ -361,6 +362,92 @@ int stream_bam(const std::string& path, long long coff, long long skip, long lon
   if (!status && !stop && stop_at == (long long)sb.st_size && rsigpu_bam_end(dec)) { fprintf(stderr, "%s\n", rsigpu_last_error(dec)); status = 1; }
   cleanup();
   return status;
+}
+
+// `-split N`: one contig over N GPUs (rsigpu_split_run).  parts[g] = the context on GPU g; every part gets the whole FASTA and
+// the reads of its own base range (+ halo); the lead (GPU 0) ends up with the calls.
+bool split_finish(const Opt& o, std::vector<rsigpu_ctx*>& parts, const std::string& name, bool bam, ContigResult* res) {
+  auto fail = [&](const char* what) { res->err = std::string(what) + ": " + rsigpu_last_error(parts[0]); return false; };
+  if (bam) for (rsigpu_ctx* p : parts) if (rsigpu_pileup_commit(p)) return fail("pileup_commit");
+  int32_t n = 0;
+  res->calls.resize(65536);
+  if (rsigpu_split_run(parts.data(), (int32_t)parts.size(), res->calls.data(), (int32_t)res->calls.size(), &n)) return fail("split_run");
+  res->calls.resize((size_t)n);
+  rsigpu_chr_stats st;
+  if (rsigpu_get_chr_stats(parts[0], &st)) return fail("chr_stats");
+  res->rdmedian = st.rdmedian; res->rdsd = st.rdsd;
+  if (getenv("RSICNV_TIMING")) fprintf(stderr, "#timing: %s split over %zu GPUs, %lld bytes crossed between devices\n", name.c_str(), parts.size(), rsigpu_split_p2p_bytes(parts[0]));
+  return true;
+}
+int bam_split_on_gpu(const Opt& o, std::vector<rsigpu_ctx*>& parts, std::vector<ContigResult>* results_out) {
+  std::string err; long long coff = 0, skip = 0;
+  BamHeader h;
+  if (!read_bam_header(o.bamfile, &h, &coff, &skip, &err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+  std::vector<ContigResult>& results = *results_out;
+  results.resize(h.name.size());
+  for (size_t i = 0; i < h.name.size(); ++i) results[i].name = h.name[i];
+  if (o.chr != "1-22XY" && std::find(h.name.begin(), h.name.end(), o.chr) == h.name.end()) { fprintf(stderr, "BAM file doesn't have %s\n", o.chr.c_str()); return 0; }
+  const int n_ref = (int)h.name.size(), np = (int)parts.size();
+  std::vector<BaiRef> bai;
+  const bool indexed = !getenv("RSICNV_NO_INDEX") && read_bai(o.bamfile, h.name.size(), &bai);
+  rsigpu_ctx* dec = nullptr;
+  if (rsigpu_create(0, &o.P, &dec)) { fprintf(stderr, "cannot create the decoder context\n"); return 2; }
+  DecodeTiming tm; int failed = 0;
+  std::vector<int32_t> pbeg((size_t)np), pend((size_t)np); int32_t halo = 0;
+  auto start = [&](int tid) -> bool {      // FASTA to every part, read staging opened
+    ContigResult& r = results[(size_t)tid];
+    fprintf(stderr, "#processing %s on %d GPUs\n", r.name.c_str(), np);
+    std::string fasta, e2;
+    if (!read_fasta(o.reffile, r.name, &fasta, &e2)) { r.err = e2; fprintf(stderr, "%s: %s\n", r.name.c_str(), e2.c_str()); ++failed; return false; }
+    for (int g = 0; g < np; ++g) {
+      if (rsigpu_split_range((int32_t)fasta.size(), np, g, &pbeg[(size_t)g], &pend[(size_t)g], &halo)) { fprintf(stderr, "%s: too short to be split over %d GPUs\n", r.name.c_str(), np); ++failed; return false; }
+      if (!begin_contig(parts[(size_t)g], tid, fasta, nullptr, &r)) { fprintf(stderr, "%s: %s\n", r.name.c_str(), r.err.c_str()); ++failed; return false; }
+    }
+    return true;
+  };
+  auto take = [&](int i, int tid) -> bool {
+    for (int g = 0; g < np; ++g)
+      if (rsigpu_bam_take_range(dec, i, parts[(size_t)g], pbeg[(size_t)g] - halo, pend[(size_t)g])) { fprintf(stderr, "%s: %s\n", results[(size_t)tid].name.c_str(), rsigpu_last_error(parts[(size_t)g])); return false; }
+    return true;
+  };
+  auto finish = [&](int tid) {
+    ContigResult& r = results[(size_t)tid];
+    r.done = split_finish(o, parts, r.name, true, &r);
+    if (!r.done) { fprintf(stderr, "%s: %s\n", r.name.c_str(), r.err.c_str()); ++failed; }
+  };
+  if (indexed) {
+    for (int tid = 0; tid < n_ref; ++tid) {
+      if (!eligible(o, h.name[(size_t)tid]) || !bai[(size_t)tid].has_reads) continue;
+      if (!start(tid) || rsigpu_bam_begin(dec, (int32_t)n_ref)) continue;
+      const uint64_t v = bai[(size_t)tid].first_voff;
+      uint64_t ve = bai[(size_t)tid].end_voff;
+      if (!ve) for (int t = tid + 1; t < n_ref; ++t) if (bai[(size_t)t].has_reads) { ve = bai[(size_t)t].first_voff; break; }
+      bool bad = false;
+      const int rc = stream_bam(o.bamfile, (long long)(v >> 16), (long long)(v & 0xffff), ve ? (long long)(ve >> 16) : 0, dec, (size_t)1 << 30, [&](int i, const rsigpu_bam_run& run) {
+        if (run.tid != tid) return 1;
+        if (!take(i, tid)) { bad = true; return -1; }
+        return 0;
+      }, &tm);
+      if (rc || bad) { fprintf(stderr, "%s: BAM decoding failed\n", h.name[(size_t)tid].c_str()); ++failed; continue; }
+      finish(tid);
+    }
+  } else {
+    if (rsigpu_bam_begin(dec, (int32_t)n_ref)) { fprintf(stderr, "%s\n", rsigpu_last_error(dec)); return 2; }
+    int cur = -1; bool cur_ok = false;
+    const int rc = stream_bam(o.bamfile, coff, skip, 0, dec, (size_t)256 << 20, [&](int i, const rsigpu_bam_run& run) {
+      if (run.tid < 0) return 1;
+      if (run.tid != cur) {
+        if (cur >= 0 && cur_ok) finish(cur);
+        cur = run.tid; cur_ok = eligible(o, h.name[(size_t)cur]) && start(cur);
+      }
+      if (cur_ok && !take(i, cur)) { cur_ok = false; ++failed; }
+      return 0;
+    }, &tm);
+    if (rc) ++failed;
+    else if (cur >= 0 && cur_ok) finish(cur);
+  }
+  rsigpu_destroy(dec);
+  return failed ? 1 : 0;
 }
 
 // BAM input decoded on the GPU (rsigpu_bam_feed: BGZF inflate + record decoding, k_bam.cuh).
@@ -645,9 +732,14 @@ int main(int argc, char** argv) {
   const double t_main = now_s();
   const int ndev = rsigpu_num_devices();
   if (ndev <= 0) { fprintf(stderr, "no CUDA device: this implementation has no CPU path\n"); return 2; }
+  if (o.split > 1) {
+    if (o.split > ndev) { fprintf(stderr, "-split %d: only %d GPUs\n", o.split, ndev); return 2; }
+    if (o.hostdecode || o.saverd) { fprintf(stderr, "-split works with the GPU decoder and without -s\n"); return 2; }
+    o.gpus = o.split;
+  }
   const int ng = std::max(1, std::min(o.gpus, ndev));
   // per GPU: two contig contexts for BAM input decoded on the GPU (one is decoded into while the other runs the hot path), else one
-  const int per_gpu = (!o.bamfile.empty() && !o.hostdecode) ? 2 : 1;
+  const int per_gpu = (!o.bamfile.empty() && !o.hostdecode && o.split <= 1) ? 2 : 1;
   std::vector<std::vector<rsigpu_ctx*>> ctx((size_t)ng);
   {
     std::vector<std::thread> th; std::atomic<int> bad(0);
@@ -672,8 +764,18 @@ int main(int argc, char** argv) {
     std::string fasta; std::vector<int32_t> rd;
     if (!read_fasta(o.reffile, o.chr, &fasta, &err) || !parse_depth_text(o.rdfile, (int)fasta.size(), &rd, &err)) { fprintf(stderr, "%s\n", err.c_str()); return 0; }
     fprintf(stderr, "#processing %s\n", o.chr.c_str());
-    results[0].done = run_contig(ctx[0][0], o, o.chr, 0, fasta, &rd, nullptr, &results[0]);
+    if (o.split > 1) {
+      std::vector<rsigpu_ctx*> parts;
+      bool ok = true;
+      for (int g = 0; g < ng && ok; ++g) { parts.push_back(ctx[(size_t)g][0]); ok = begin_contig(parts.back(), 0, fasta, &rd, &results[0]); }
+      results[0].done = ok && split_finish(o, parts, o.chr, false, &results[0]);
+    } else results[0].done = run_contig(ctx[0][0], o, o.chr, 0, fasta, &rd, nullptr, &results[0]);
     if (!results[0].done) { fprintf(stderr, "%s\n", results[0].err.c_str()); rc_all = 1; }
+  } else if (o.split > 1) {
+    std::vector<rsigpu_ctx*> parts;
+    for (int g = 0; g < ng; ++g) parts.push_back(ctx[(size_t)g][0]);
+    rc_all = bam_split_on_gpu(o, parts, &results);
+    if (rc_all == 2) return 2;
   } else if (!o.hostdecode) {
     rc_all = bam_on_gpu(o, ctx, &results);
     if (rc_all == 2) return 2;

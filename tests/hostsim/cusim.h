@@ -425,6 +425,8 @@ template <class T> inline cudaError_t cudaMallocHost(T** p, size_t n) { return c
 inline cudaError_t cudaFreeHost(void* p) { std::free(p); return 0; }
 inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memcpy(d, s, n); return 0; }
 inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { std::memcpy(d, s, n); return 0; }
+inline cudaError_t cudaDeviceCanAccessPeer(int* can, int, int) { *can = 0; return 0; }
+inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return 0; }
 inline cudaError_t cudaMemcpyPeerAsync(void* d, int, const void* s, int, size_t n, cudaStream_t = nullptr) { std::memcpy(d, s, n); return 0; }
 inline cudaError_t cudaMemset(void* d, int v, size_t n) { std::memset(d, v, n); return 0; }
 inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { std::memset(d, v, n); return 0; }

@@ -104,3 +104,74 @@ def test_bench_whole_genome_two_ranks_same_table(two_gpus, tmp_path):
     j2 = json.loads([ln for ln in r2.stdout.splitlines() if ln.startswith("{")][-1])
     assert j1["table_sha1"] == j2["table_sha1"] and j1["calls"] == j2["calls"] and j1["calls"] > 0
     assert j2["n_gpus"] == 2 and j2["scaling"] == "strong"
+
+
+def _snap(ctx, calls):
+    st = ctx.chr_stats()
+    return dict(calls=[bytes(c) for c in calls], depth=ctx.array(api.ARR_DEPTH).tobytes(), nbn=ctx.array(api.ARR_BIN_NBN).tobytes(),
+                status=ctx.array(api.ARR_BIN_STATUS).tobytes(), stats=(st.rdmedian, st.rdsd, st.rdmad, st.isize_mean, st.isize_sd, st.nbins, st.compact_len))
+
+
+def test_split_chr1_sized_contig_two_gpus_equals_one(two_gpus, gpu_lib):
+    """config 5's building block: a chr1-sized contig (249,250,621 bp) split over two GPUs by base range -- per-base passes on each
+    half, integer tables added on the lead over NVLink peer copies, halo of the bins that straddle the cut -- gives the one-GPU
+    result bit for bit"""
+    L = synth.B37_LENS["1"]
+    fa = synth.make_fasta(L, 1)
+    d, _ = synth.make_depth(L, 1, fa, n_events=40, lens=(2000, 5000, 10000, 30000, 100000))
+    with api.Context(device=0, lib=gpu_lib) as c0:
+        c0.set_reference(fa); c0.set_depth(d)
+        want = _snap(c0, c0.run())
+        one_ms = c0.stage_ms()["total"]
+    parts = [api.Context(device=g, lib=gpu_lib) for g in range(2)]
+    try:
+        for p in parts:
+            p.set_reference(fa); p.set_depth(d)
+        api.split_run(parts)                       # warm-up (allocations)
+        got = _snap(parts[0], api.split_run(parts))
+        split_ms = parts[0].stage_ms()["total"]
+        p2p = parts[0].lib.rsigpu_split_p2p_bytes(parts[0].h)
+    finally:
+        for p in parts:
+            p.close()
+    assert got == want and len(want["calls"]) >= 20
+    assert p2p > 0.4 * 4 * L          # about half of the compacted depth crosses to the lead, plus tables and bins
+    print(f"chr1-sized contig: one GPU {one_ms:.2f} ms, split over two {split_ms:.2f} ms, {p2p / 1e6:.1f} MB peer-to-peer")
+
+
+def test_split_bam_contig_two_gpus_and_cli(two_gpus, gpu_lib, tmp_path):
+    L = 10_600_000
+    fa = synth.make_fasta(L, 83)
+    reads, _ = synth.make_reads(L, 83, fa, coverage=12, n_events=6, lens=(3000, 8000, 20000))
+    kw = dict(minq=0, min_baseQ=10)
+    with api.Context(device=0, lib=gpu_lib, **kw) as c0:
+        c0.set_reference(fa); c0.pileup_begin(); c0.pileup_push(reads); c0.have_reads()
+        want = _snap(c0, c0.run())
+    parts = [api.Context(device=g, lib=gpu_lib, **kw) for g in range(2)]
+    try:
+        for g, p in enumerate(parts):
+            b, e, halo = api.split_range(p.lib, L, 2, g)
+            p.set_reference(fa); p.pileup_begin(); p.pileup_push(api.split_reads(reads, b, e, halo)); p.have_reads()
+        got = _snap(parts[0], api.split_run(parts))
+    finally:
+        for p in parts:
+            p.close()
+    assert got == want and len(want["calls"]) >= 3 and any(api.Cnv.from_buffer_copy(c).rp > 0 for c in want["calls"])
+    # the CLI: -split 2 against one GPU, BAM and depth-file input
+    if not os.path.exists(CLI):
+        subprocess.run(["make", "-s", "cli"], cwd=ROOT, check=True)
+    bam = str(tmp_path / "t.bam"); fasta = str(tmp_path / "t.fa"); rd = str(tmp_path / "t.rd")
+    synth.write_bam(bam, [("7", L)], {0: reads}, level=1, random_seq=9)
+    synth.write_fasta(fasta, "7", fa)
+    if have_ref():
+        subprocess.run([REF_BAMTOOL, "index", bam], check=True)
+    depth, _ = synth.make_depth(L, 83, fa, n_events=6, lens=(3000, 8000, 20000))
+    synth.write_depth_file_fast(rd, depth)
+    for common in (["rsi", "-b", bam, "-f", fasta, "-q", "0", "-Q", "10", "-np"], ["rsi", "-d", rd, "-c", "7", "-f", fasta, "-np"]):
+        outs = []
+        for extra, env in (([], {}), (["-split", "2"], {}), (["-split", "2"], {"RSICNV_NO_INDEX": "1"})):
+            o = str(tmp_path / f"o{len(outs)}.txt")
+            r = subprocess.run([CLI] + common + extra + ["-o", o], capture_output=True, text=True, env=dict(os.environ, **env))
+            assert r.returncode == 0, r.stderr
+            outs.append(_table(o))
+        assert outs[0] == outs[1] == outs[2] and len(outs[0]) > 3
