@@ -121,6 +121,7 @@ def test_split_chr1_sized_contig_two_gpus_equals_one(two_gpus, gpu_lib):
     d, _ = synth.make_depth(L, 1, fa, n_events=40, lens=(2000, 5000, 10000, 30000, 100000))
     with api.Context(device=0, lib=gpu_lib) as c0:
         c0.set_reference(fa); c0.set_depth(d)
+        c0.run()                                   # warm-up (allocations)
         want = _snap(c0, c0.run())
         one_ms = c0.stage_ms()["total"]
     parts = [api.Context(device=g, lib=gpu_lib) for g in range(2)]
