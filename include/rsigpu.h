@@ -193,6 +193,13 @@ int rsigpu_get_array(rsigpu_ctx* c, int32_t which, void* out, int64_t cap, int64
 /* cnv_format1 (rsi.cpp:581-631): one table row, or the column header when cnv == NULL. */
 int rsigpu_format_row(const rsigpu_cnv* cnv, const char* chrom, double rdmedian, double rdsd, char* buf, int32_t cap);
 
+/* The deterministic part of <out>.log for the contig just processed (what rsi::dout receives between "#processing <chr>" and
+ * "output written to": N regions, depth means before / after GC adjust and cap, the transformation parameters of both passes,
+ * the per-length DEL-/DUP+ lines of rsistatus, filterstatus' level table, segment counts; rsi.cpp:1221-1224, 1251-1254, 1291-1298,
+ * 1884, 1939-1942, loaddata.cpp:260-265, 349-356).  text_input: 1 for a depth file (load_data_from_text prints a third mean).
+ * Call with buf == NULL to get the size. */
+int rsigpu_get_log(rsigpu_ctx* c, const char* chrom, int32_t text_input, char* buf, int64_t cap, int64_t* nbytes);
+
 /* timing / accounting for bench.py: kernels launched by this context since creation, and the
  * device time (ms, CUDA events on the context's stream) of the last rsigpu_run by stage:
  * [0]=pileup [1]=load_finish [2]=detect bins+scan [3]=candidates [4]=sd_filters+cnv_stat [5]=total */

@@ -71,7 +71,7 @@ EXPORTS = ("rsigpu_default_params", "rsigpu_create", "rsigpu_destroy", "rsigpu_l
            "rsigpu_set_depth", "rsigpu_pileup_begin", "rsigpu_pileup_push", "rsigpu_pileup_end", "rsigpu_load_finish", "rsigpu_detectcnv",
            "rsigpu_sd_filters", "rsigpu_cnv_stat", "rsigpu_get_calls", "rsigpu_run", "rsigpu_get_chr_stats", "rsigpu_get_array",
            "rsigpu_format_row", "rsigpu_launch_count", "rsigpu_last_stage_ms", "rsigpu_set_profile", "rsigpu_get_profile",
-           "rsigpu_reads_begin", "rsigpu_stat_calls", "rsigpu_bam_take_range", "rsigpu_split_range", "rsigpu_split_run", "rsigpu_split_p2p_bytes", "rsigpu_set_level0_mode", "rsigpu_set_feed_limit", "rsigpu_set_cand_threads", "rsigpu_debug_state", "rsigpu_pileup_commit", "rsigpu_bam_begin", "rsigpu_bam_feed", "rsigpu_bam_take",
+           "rsigpu_get_log", "rsigpu_reads_begin", "rsigpu_stat_calls", "rsigpu_bam_take_range", "rsigpu_split_range", "rsigpu_split_run", "rsigpu_split_p2p_bytes", "rsigpu_set_level0_mode", "rsigpu_set_feed_limit", "rsigpu_set_cand_threads", "rsigpu_debug_state", "rsigpu_pileup_commit", "rsigpu_bam_begin", "rsigpu_bam_feed", "rsigpu_bam_take",
            "rsigpu_bam_end", "rsigpu_bam_run_field", "rsigpu_pinned_alloc", "rsigpu_pinned_free")
 
 _libs: dict[str, C.CDLL] = {}
@@ -345,6 +345,14 @@ class Context:
         out = np.zeros(max(n, 1), _ARR_DTYPE[which])
         self._ck(self.lib.rsigpu_get_array(self.h, C.c_int32(which), _ptr(out), C.c_int64(n), C.byref(cnt)))
         return out[:n]
+
+    def log_text(self, chrom: str, text_input: bool) -> str:
+        """the deterministic part of <out>.log for the contig just processed (rsigpu_get_log)"""
+        n = C.c_int64(0)
+        self._ck(self.lib.rsigpu_get_log(self.h, C.c_char_p(chrom.encode()), C.c_int32(1 if text_input else 0), None, C.c_int64(0), C.byref(n)))
+        buf = C.create_string_buffer(n.value + 1)
+        self._ck(self.lib.rsigpu_get_log(self.h, C.c_char_p(chrom.encode()), C.c_int32(1 if text_input else 0), buf, C.c_int64(n.value), C.byref(n)))
+        return buf.raw[:n.value].decode()
 
     def launch_count(self) -> int:
         return int(self.lib.rsigpu_launch_count(self.h))

@@ -522,6 +522,18 @@ __global__ void __launch_bounds__(1024) k_cap_params(const u32* hist_all, DevSta
   const u64 n = (u64)st->L;
   int pick[3], fnz, lnz;
   cta_hist_pick(c, hist_all, (int)HIST_ALL_BINS, n / 4, n / 2, n * 3 / 4, pick, &fnz, &lnz);
+  {   // for <out>.log: the mean of the adjusted depth before and after the cap (loaddata.cpp:353-356, 531-536) and of its positive part
+    const double medl = (fnz == lnz || pick[1] < 0) ? (double)fnz : (double)pick[1];
+    const double thr = medl * st->cap; const int capv = (int)(medl * st->cap), cap_on = st->cap_on;
+    u64 s1 = 0, s2 = 0, np = 0;
+    for (int v = c.tid; v < (int)HIST_ALL_BINS; v += c.nthr) {
+      const u64 h = hist_all[v];
+      s1 += h * (u64)v; s2 += h * (u64)((cap_on && (double)v > thr) ? capv : v);
+      if (v > 0) np += h;
+    }
+    s1 = c.reduce(s1, SumOp()); s2 = c.reduce(s2, SumOp()); np = c.reduce(np, SumOp());
+    if (c.tid == 0) { st->adj_sum = (double)s1; st->cap_sum = (double)s2; st->adj_pos = np; }
+  }
   if (c.tid == 0) {
     double med = (fnz == lnz || pick[1] < 0) ? (double)fnz : (double)pick[1];  // all equal -> the mean, i.e. that value
     st->cap_median = med;

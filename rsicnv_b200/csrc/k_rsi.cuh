@@ -52,12 +52,13 @@ __global__ void k_rsi_params2(const float* __restrict__ t, DevState* st, int whi
   if (Lmax < calmax) Lmax = calmax;
   if (Lmax > LMAX_CAP) { st->err |= ERR_LMAX; Lmax = LMAX_CAP; }
   st->tsigma = tsigma; st->tlamda = tlamda; st->target = target; st->dev = dev; st->Lmax = Lmax;
+  { RsiLogT& g = st->rlog[which]; g.tmedian1 = tmedian; g.tsigma1 = tsigma; g.tlamda1 = tlamda; g.target = target; g.calmax = calmax; g.lmax = Lmax; g.used = 1; g.filt_on = -1; }
   for (int L = 0; L < LMAX_CAP + 2; ++L) { st->cnt_del[L] = 0; st->cnt_dup[L] = 0; }
   for (int l = 0; l < 2 * LMAX_CAP + 3; ++l) { st->lvl_sum[l] = 0.f; st->lvl_cnt[l] = 0; }
   st->st_lo = 0; st->st_hi = 0; st->last_run_start = -1; st->n_nonzero = 0;
 }
 // re-estimation on the unmarked bins after filterstatus (rsi.cpp:1307-1318 / 1457-1468)
-__global__ void k_rsi_params3(DevState* st, int slot_med, int slot_sig) {
+__global__ void k_rsi_params3(DevState* st, int slot_med, int slot_sig, int which) {
   if (threadIdx.x || blockIdx.x) return;
   const u32 k = st->qj[slot_med].n;
   st->n_unmarked = k;
@@ -68,6 +69,7 @@ __global__ void k_rsi_params3(DevState* st, int slot_med, int slot_sig) {
     st->tlamda = tl > st->target ? tl : st->target;
   }
   st->out_tmedian = st->tmedian; st->out_tlamda = st->tlamda;
+  { RsiLogT& g = st->rlog[which]; g.tmedian2 = st->tmedian; g.tsigma2 = st->tsigma; g.tlamda2 = st->tlamda; }
   for (int L = 0; L < LMAX_CAP + 2; ++L) { st->cnt_del[L] = 0; st->cnt_dup[L] = 0; }
   st->st_lo = 0; st->st_hi = 0; st->last_run_start = -1; st->n_nonzero = 0;
 }
@@ -677,7 +679,7 @@ __global__ void __launch_bounds__(128) k_level_sums(const int* __restrict__ nz_l
   if (lvl <= hi && lvl != 0) { st->lvl_sum[lvl - lo] = s; st->lvl_cnt[lvl - lo] = n; }
 }
 
-__global__ void k_filter_params(DevState* st) {
+__global__ void k_filter_params(DevState* st, int which) {
   if (threadIdx.x || blockIdx.x) return;
   const int lo = st->st_lo, hi = st->st_hi, nl = hi - lo + 1;
   const double dev = st->dev;
@@ -687,9 +689,22 @@ __global__ void k_filter_params(DevState* st) {
   int ldel = lo, ladd = hi;
   for (int l = 0; l < nl; ++l) if ((double)st->lvl_sum[l] < (double)m0 - dev) { ldel = l + lo; break; }
   for (int l = nl - 1; l >= 0; --l) if ((double)st->lvl_sum[l] > (double)m0 + dev) { ladd = l + lo; break; }
+  {   // the level table as filterstatus prints it (rsi.cpp:991-997)
+    RsiLogT& g = st->rlog[which];
+    g.st_lo = lo; g.st_hi = hi; g.leveldel = ldel; g.leveladd = ladd;
+    for (int l = 0; l < nl; ++l) { g.lvl_mean[l] = st->lvl_sum[l]; g.lvl_cnt[l] = st->lvl_cnt[l]; }
+    g.filt_on = (ldel > 0 || ladd < 0 || ldel > ladd) ? 0 : 1;
+  }
   if (ldel > 0 || ladd < 0 || ldel > ladd) return;
   st->filt_tdel = (double)m0 - dev; st->filt_tadd = (double)m0 + dev;
   st->filt_on = 1;
+}
+
+// the per-length counts and break levels of one rsistatus pass, kept for <out>.log (rsi.cpp:1221-1224, 1251-1254)
+__global__ void k_rsi_log_pass(DevState* st, int which, int pass) {
+  RsiLogT& g = st->rlog[which];
+  for (int L = (int)threadIdx.x; L < LMAX_CAP + 2; L += (int)blockDim.x) { g.cnt[pass][0][L] = st->cnt_del[L]; g.cnt[pass][1][L] = st->cnt_dup[L]; }
+  if (threadIdx.x == 0) { g.lbreak_del[pass] = st->lbreak_del; g.lbreak_dup[pass] = st->lbreak_dup; }
 }
 
 // trim both edges of every run but the last (rsi.cpp:1027-1046); one thread per run start

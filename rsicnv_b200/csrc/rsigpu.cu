@@ -10,6 +10,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include <time.h>
+#include <stdarg.h>
 
 #include <algorithm>
 #include <map>
@@ -282,6 +283,7 @@ int run_rsi(rsigpu_ctx* c, int which, const float* t) {
     KL(k_rsi_cnt_dup, gb, 256, 0, c->d_minl_del.p, c->d_minl_dup.p, st);
     int* status = pass == 0 ? c->d_status1.p : c->d_status.p;
     KL(k_rsi_status, gb, 256, 0, c->d_minl_del.p, c->d_minl_dup.p, status, c->d_tile.p, st);
+    KL(k_rsi_log_pass, 1, 256, 0, st, which, pass);
     if (pass == 1) break;
     // filterstatus (rsi.cpp:948-1057) on the first-pass status, in place via a second buffer
     KL(k_nz_scatter, gb, 256, 0, t, status, c->d_tile.p, c->d_nz_idx.p, c->d_nz_val.p, st);
@@ -292,12 +294,12 @@ int run_rsi(rsigpu_ctx* c, int which, const float* t) {
     } else if (c->level0_mode == 1) KL(k_level0_chain_scan, 1, CH_NT, 0, t, status, st);
     else KL(k_level0_chain_seq, 1, 32, 0, t, status, st);
     KL(k_level_sums, (2 * LMAX_CAP + 3 + 127) / 128, 128, 0, c->d_nz_idx.p, c->d_nz_val.p, st);
-    KL(k_filter_params, 1, 32, 0, st);
+    KL(k_filter_params, 1, 32, 0, st, which);
     CK(cudaMemcpyAsync(c->d_status.p, status, (size_t)nb * 4, cudaMemcpyDeviceToDevice, c->stream));
     KL(k_filter_trim, gb, 256, 0, t, c->d_status.p, status, st);
     quantile(c, t, status, 1, QM_ID, nullptr, slot0 + 2);
     quantile(c, t, status, 1, QM_ABSDEV, &(st->qj[slot0 + 2].q[1]), slot0 + 3);
-    KL(k_rsi_params3, 1, 32, 0, st, slot0 + 2, slot0 + 3);
+    KL(k_rsi_params3, 1, 32, 0, st, slot0 + 2, slot0 + 3, which);
   }
   // get_rsi_segments on the second-pass status
   KL(k_runs_count, gb, 256, 0, c->d_status.p, c->d_tile.p, st);
@@ -1349,6 +1351,93 @@ int rsigpu_format_row(const rsigpu_cnv* cnv, const char* chrom, double rdmedian,
   int k = snprintf(buf, (size_t)cap, "%s\t%d\t%d\t%s\t%d\t%d\t%g(%g);%g(%g);%g(%g)\tRP=%d;Q0=%g\trsi", chrom ? chrom : "", cnv->start, cnv->end, T[ty],
                    (int)q1, cnv->end - cnv->start + 1, cnv->cnvmed, cnv->cnviqr / 1.349, cnv->refmed, cnv->refiqr / 1.349, rdmedian, rdsd, cnv->rp, cnv->q0);
   return k < cap ? RSIGPU_OK : RSIGPU_E_CAPACITY;
+}
+
+// The deterministic part of what the reference writes to <out>.log for one contig (rsi::dout tees to stderr and the log,
+// rsi.cpp:86, 2079-2080), from "#Noseq regions excluded" to "Found n CNVs": loaddata.cpp:260-265, 315, 338, 349-356, 522-536,
+// 234-236; gccontent.cpp:154, 181; rsi.cpp:1804-1813, 1140-1141, 1291-1298 / 1436-1448, 1221-1224, 1251-1254, 991-1002,
+// 1320-1326 / 1472-1478, 1884, 1939-1942.  Doubles go through the default ostream formatting (= %g).
+namespace {
+struct LogBuf {
+  std::string s;
+  void add(const char* fmt, ...) {
+    char tmp[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(tmp, sizeof tmp, fmt, ap); va_end(ap);
+    s += tmp;
+  }
+};
+void log_pass(LogBuf& o, const RsiLogT& g, int pass, int nb) {
+  for (int sgn = 0; sgn < 2; ++sgn) {
+    const int lb = sgn ? g.lbreak_dup[pass] : g.lbreak_del[pass];
+    unsigned long long cum = 0;
+    for (int L = 1; L <= g.lmax; ++L) {
+      cum += g.cnt[pass][sgn][L];
+      const double portion = (double)cum / (double)nb;
+      o.add("%s\t%d\t%llu\t%d\t%g\n", sgn ? "DUP+" : "DEL-", L, cum, nb, portion);
+      if (portion > 0.2 || L == lb) { if (portion > 0.2) break; }
+    }
+  }
+}
+void log_trans(LogBuf& o, const DevState* h, int which, int nb) {
+  const RsiLogT& g = h->rlog[which];
+  const char* name = which == 0 ? "Negative binormial transformation : " : "local median transformation : ";
+  o.add("%s\n\tmedian of transformations : %g\n\tsigma : %g\n\tmedian/sigma : %g\n\trsifactor: %g\n\tlamda : %g\n\ttarget_tlamda : %g\n\tMax L needed  : %d\n",
+        name, g.tmedian1, g.tsigma1, g.tmedian1 / g.tsigma1, h->factor, g.tlamda1, g.target, g.calmax);
+  if (which == 1) {
+    if (g.tlamda1 < g.tmedian1 * sqrt(2.5)) o.add("Warning : lamda might be low\n");
+    if (g.tlamda1 > g.tmedian1 * sqrt(3.0)) o.add("Warning : lamda might be too large\n");
+  }
+  log_pass(o, g, 0, nb);
+  const int nl = g.st_hi - g.st_lo + 1;
+  for (int l = 0; l < nl; ++l) if (g.lvl_cnt[l]) o.add("%d\t%u\t%g\n", l + g.st_lo, g.lvl_cnt[l], (double)g.lvl_mean[l]);
+  o.add("%d\t%g\n%d\t%g\n", g.leveldel, (double)g.lvl_mean[g.leveldel - g.st_lo], g.leveladd, (double)g.lvl_mean[g.leveladd - g.st_lo]);
+  if (!g.filt_on) o.add("warning level error, status not filtered\n%d\t%d\nfilterstatus()\n", g.leveldel, g.leveladd);
+  o.add("second pass\n%s\n\tmedian of transformations : %g\n\tsigma : %g\n\tmedian/sigma : %g\n\tlamda : %g\n\target_tlamda : %g\n",
+        name, g.tmedian2, g.tsigma2, g.tmedian2 / g.tsigma2, g.tlamda2, g.target);
+  log_pass(o, g, 1, nb);
+}
+}  // namespace
+
+int rsigpu_get_log(rsigpu_ctx* c, const char* chrom, int32_t text_input, char* buf, int64_t cap, int64_t* nbytes) {
+  if (!c || !nbytes) return RSIGPU_E_ARG;
+  if (!c->loaded) { c->fail("get_log: call load_finish / run first"); return RSIGPU_E_ARG; }
+  const DevState* h = c->h_st;
+  const char* name = chrom ? chrom : "";
+  LogBuf o;
+  o.add("#Noseq regions excluded\n");
+  for (size_t k = 0; k < c->h_nbeg.size(); ++k) o.add("%s\t%d\t%d\n", name, c->h_nbeg[k], c->h_nend[k]);
+  const double L = (double)c->L;
+  if (c->have_reads) {   // load_data_from_bam's progress marks (one per million records, carriage returns, one newline)
+    const size_t nr = c->use_summary ? c->s_n : c->r_pos.n;
+    for (size_t k = 1; k <= nr / 1000000; ++k) o.add("#processed %zuM reads\r", k);
+    o.add("\n");
+  }
+  o.add("%d\t%g\n", c->L, (double)h->pos_sum / L);
+  if (c->P.gcadjust) {
+    o.add("RD mean before GC adjust = %g\n", h->rdmean);
+    o.add("RD mean after GC adjust = %g\n", h->adj_sum / (double)h->adj_pos);
+  }
+  o.add("%d\t%g\n", c->L, h->adj_sum / L);
+  if (c->P.cap > 1) o.add("applying cap %g times of mean %g\ncap = %g\n", c->P.cap, h->cap_median, c->P.cap * h->cap_median);
+  if (text_input) o.add("%d\t%g\n", c->L, h->cap_sum / L);
+  o.add("region  : %s:%d-%d\nmedian  : %g\nrs::m   : %d\nrs::cap : %g\n", name, 1, c->Lc, h->rdmedian, c->P.m, c->P.cap);
+  if (h->rdmedian < 5) o.add("Read depths too low, cannot call\n");
+  else {
+    if (h->rdmedian < 10) o.add("Read depths low, not reliable\n");
+    o.add("RD median : %g\nRD median absolute deviation : %g\n", h->rdmedian, h->rdmad);
+    if (c->detected) {
+      if (c->P.trans != RSIGPU_TRANS_NBN) log_trans(o, h, 1, c->nb);
+      if (c->P.trans != RSIGPU_TRANS_MED) log_trans(o, h, 0, c->nb);
+      int ndel = 0, nadd = 0;
+      for (const Cnv& x : c->h_detected) { if (x.type == RSIGPU_TYPE_DUP) ++nadd; if (x.type == RSIGPU_TYPE_DEL) ++ndel; }
+      o.add("Selected %zu segments for testing\n", c->h_dump[2].size());
+      o.add("Done checking overlaps, after merging, %zu segments left\nFound %d CNVs : %d DEL + %d DUP\n", c->h_detected.size(), ndel + nadd, ndel, nadd);
+    }
+  }
+  *nbytes = (int64_t)o.s.size();
+  if (!buf || cap < (int64_t)o.s.size()) return buf ? RSIGPU_E_CAPACITY : RSIGPU_OK;
+  memcpy(buf, o.s.data(), o.s.size());
+  return RSIGPU_OK;
 }
 
 int64_t rsigpu_launch_count(const rsigpu_ctx* c) { return c ? c->launches : 0; }

@@ -37,6 +37,15 @@ struct QuantJob {   // one histogram-quantile evaluation (partition_stat_tp, wuf
   double q[3];      // lower quartile, median, upper quartile (mean when the range is below dy)
 };
 
+// What <out>.log prints of one transformation (rsicnvnbn / rsicnvmed, rsi.cpp:1262-1515): the first-pass values and tables
+// are overwritten by the second pass, so they are saved here as they are produced.
+struct RsiLogT {
+  double tmedian1, tsigma1, tlamda1, target, tmedian2, tsigma2, tlamda2;
+  int calmax, lmax, lbreak_del[2], lbreak_dup[2], st_lo, st_hi, leveldel, leveladd, filt_on, used;
+  u32 cnt[2][2][LMAX_CAP + 2];                       // [pass][DEL, DUP][L]: bins whose smallest covering window has length L
+  float lvl_mean[2 * LMAX_CAP + 3]; u32 lvl_cnt[2 * LMAX_CAP + 3];   // filterstatus' per-level means / counts (index = level - st_lo)
+};
+
 struct DevState {
   int err, cand_err;
   // ---- inputs
@@ -95,6 +104,9 @@ struct DevState {
   int isize_mean, isize_sd;
   // ---- scratch for the quantile jobs
   QuantJob qj[8];
+  // ---- for <out>.log: sums of the adjusted / capped depth over all L positions, and the per-transformation record
+  double adj_sum, cap_sum; u64 adj_pos;
+  RsiLogT rlog[2];             // [0] = NBN, [1] = MED
 };
 
 }  // namespace rsigpu

@@ -174,7 +174,32 @@ bool parse_depth_text(const std::string& path, int L, std::vector<int32_t>* rd, 
 struct ContigResult {
   std::string name; bool done = false; std::string err;
   std::vector<rsigpu_cnv> calls; double rdmedian = 0, rdsd = 0;
+  std::string log;      // what the reference's <out>.log holds for this contig (rsigpu_get_log)
 };
+
+// <out>.log: the reference tees everything it says to stderr into it (rsi::dout, rsi.cpp:86, 2079-2098).  Reproduced: the parameter
+// echo, the BAM header check, and per contig the deterministic lines of the loaders and the detector; not reproduced: the Vm*
+// lines of /proc/<pid>/status.
+std::string param_echo(const Opt& o, const std::string& command) {
+  char tmp[64];
+  std::string s = "#command:   " + command + "\n#bamfile:   " + o.bamfile + "\n#rdfile:    " + o.rdfile + "\n#reffile:   " + o.reffile + "\n#cnvfile:   " + o.cnvfile + "\n#chrom:     " + o.chr + "\n";
+  snprintf(tmp, sizeof tmp, "#min_mapq:  %d\n#min_baseQ: %d\n#binsize:   %d\n#adjustGC:  %d\n", o.P.minq, o.P.min_baseQ, o.P.m, o.P.gcadjust ? 1 : 0); s += tmp;
+  s += "#plots:     cnv_plots\n#output:    " + o.outfile + "\n";
+  return s;
+}
+void contig_log(rsigpu_ctx* c, const Opt& o, const std::string& name, bool text_input, ContigResult* res) {
+  int64_t n = 0;
+  if (rsigpu_get_log(c, name.c_str(), text_input ? 1 : 0, nullptr, 0, &n) || n <= 0) return;
+  std::string t((size_t)n, '\0');
+  if (rsigpu_get_log(c, name.c_str(), text_input ? 1 : 0, &t[0], n, &n)) return;
+  if (o.saverd && !text_input) {   // "RD of <chr> is saved to <file>" follows the progress line of the read loop (loaddata.cpp:338-342)
+    size_t p = t.find('\n') + 1;                                  // after "#Noseq regions excluded"
+    while (p < t.size() && t.compare(p, name.size() + 1, name + "\t") == 0) p = t.find('\n', p) + 1;
+    p = t.find('\n', p) + 1;                                     // after the progress line
+    t.insert(p, "RD of " + name + " is saved to " + o.outfile + "." + name + "_rd\n");
+  }
+  res->log = "#processing " + name + "\n" + t + "output written to " + o.outfile + "\n";
+}
 
 // set_reference + pileup_begin (BAM input) / set_depth (depth-file input)
 bool begin_contig(rsigpu_ctx* c, int tid, const std::string& fasta, const std::vector<int32_t>* depth, ContigResult* res) {
@@ -205,6 +230,7 @@ bool finish_contig(rsigpu_ctx* c, const Opt& o, const std::string& name, size_t 
   rsigpu_chr_stats st;
   if (rsigpu_get_chr_stats(c, &st)) return fail("chr_stats");
   res->rdmedian = st.rdmedian; res->rdsd = st.rdsd;
+  contig_log(c, o, name, !bam, res);
   return true;
 }
 
@@ -376,6 +402,7 @@ bool split_finish(const Opt& o, std::vector<rsigpu_ctx*>& parts, const std::stri
   rsigpu_chr_stats st;
   if (rsigpu_get_chr_stats(parts[0], &st)) return fail("chr_stats");
   res->rdmedian = st.rdmedian; res->rdsd = st.rdsd;
+  contig_log(parts[0], o, name, !bam, res);
   if (getenv("RSICNV_TIMING")) fprintf(stderr, "#timing: %s split over %zu GPUs, %lld bytes crossed between devices\n", name.c_str(), parts.size(), rsigpu_split_p2p_bytes(parts[0]));
   return true;
 }
@@ -697,6 +724,18 @@ void write_table(const Opt& o, const std::vector<ContigResult>& all) {
   fclose(f);
 }
 
+void write_log(const Opt& o, const std::string& command, const std::vector<ContigResult>& all, const std::string& bam_check) {
+  FILE* f = fopen((o.outfile + ".log").c_str(), "w");
+  if (!f) return;
+  const std::string echo = param_echo(o, command);
+  fputs(echo.c_str(), f);
+  fputs(bam_check.c_str(), f);
+  for (const ContigResult& r : all) if (r.done) fputs(r.log.c_str(), f);
+  fprintf(f, "\n%s\n", echo.c_str());
+  fputs("exit\n", f);
+  fclose(f);
+}
+
 int do_decode(const Opt& o) {
   BamReader br(o.threads); std::string err;
   {   // what the GPU decoder is given: where the alignment records start
@@ -818,6 +857,27 @@ int main(int argc, char** argv) {
     if (failed.load()) rc_all = 1;
   }
   write_table(o, results);
+  {
+    std::string command, check;
+    for (int i = 0; i < argc; ++i) command += std::string(argv[i]) + " ";
+    if (!o.bamfile.empty()) {   // "#Check bam header for 1-22XY" (rsi.cpp:2114-2131): every target without "MT" / "." in its name, then those with reads
+      BamHeader h; long long co = 0, sk = 0; std::string e3;
+      if (read_bam_header(o.bamfile, &h, &co, &sk, &e3)) {
+        std::vector<BaiRef> bai;
+        const bool have_idx = read_bai(o.bamfile, h.name.size(), &bai);
+        check = "#Check bam header for 1-22XY \n";
+        std::string pop = "#BAM has reads on :";
+        for (size_t i = 0; i < h.name.size(); ++i) {
+          if (h.name[i].find("MT") != std::string::npos || h.name[i].find(".") != std::string::npos) continue;
+          check += h.name[i] + "\t" + std::to_string(h.len[i]) + "\t" + std::to_string(i) + "\t0\t536870912\n";
+          const bool has = have_idx ? bai[i].has_reads : (i < results.size() && (results[i].done || !results[i].err.empty()));
+          if (has) pop += " " + h.name[i];
+        }
+        check += pop + "\n";
+      }
+    }
+    write_log(o, command, results, check);
+  }
   if (getenv("RSICNV_TIMING")) fprintf(stderr, "#timing: total %.3f s\n", now_s() - t_main);
   fprintf(stderr, "output written to %s\n", o.outfile.c_str());
   for (auto& v : ctx) for (rsigpu_ctx* c : v) rsigpu_destroy(c);

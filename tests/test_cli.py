@@ -48,6 +48,17 @@ def _table(path):
     return [ln for ln in open(path).read().splitlines() if not ln.startswith("#input")]
 
 
+def log_lines(path, outname):
+    """<out>.log without what no other implementation can reproduce: the Vm* lines of /proc/<pid>/status and the command line
+    (it names the binary); the output file's name is normalised"""
+    out = []
+    for ln in open(path, newline="\n").read().split("\n"):
+        if ln.startswith("Vm") or ln.startswith("#command:"):
+            continue
+        out.append(ln.replace(outname, "OUT"))
+    return out
+
+
 @pytest.mark.gpu
 def test_cli_bam_two_contigs_matches_reference(cli, tmp_path):
     if not have_ref():
@@ -66,6 +77,8 @@ def test_cli_bam_two_contigs_matches_reference(cli, tmp_path):
     assert out.returncode == 0, out.stderr
     assert _table(str(tmp_path / "ours.txt")) == _table(str(tmp_path / "ref.txt")), out.stderr
     assert len(_table(str(tmp_path / "ours.txt"))) > 6
+    # <out>.log: parameter echo, BAM header check, per contig the loaders' and the detector's lines (per-L DEL-/DUP+ counts, level table ...)
+    assert log_lines(str(tmp_path / "ours.txt.log"), str(tmp_path / "ours.txt")) == log_lines(str(tmp_path / "ref.txt.log"), str(tmp_path / "ref.txt"))
     # the host decoder (zlib on threads) instead of the GPU one: same table
     out = subprocess.run([cli] + common + ["-hostdecode", "-o", str(tmp_path / "ours_h.txt")], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
@@ -76,11 +89,13 @@ def test_cli_bam_two_contigs_matches_reference(cli, tmp_path):
     out = subprocess.run([cli] + common + ["-o", str(tmp_path / "ours2.txt")], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
     assert _table(str(tmp_path / "ours2.txt")) == _table(str(tmp_path / "ref2.txt"))
+    assert log_lines(str(tmp_path / "ours2.txt.log"), str(tmp_path / "ours2.txt")) == log_lines(str(tmp_path / "ref2.txt.log"), str(tmp_path / "ref2.txt"))
     common = ["rsi", "-b", bam, "-f", fasta, "-c", "1", "-ALL", "-q", "0", "-Q", "10", "-np"]
     subprocess.run([REF_BIN] + common + ["-o", str(tmp_path / "ref3.txt")], check=True, capture_output=True)
     out = subprocess.run([cli] + common + ["-o", str(tmp_path / "ours3.txt")], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
     assert _table(str(tmp_path / "ours3.txt")) == _table(str(tmp_path / "ref3.txt"))
+    assert log_lines(str(tmp_path / "ours3.txt.log"), str(tmp_path / "ours3.txt")) == log_lines(str(tmp_path / "ref3.txt.log"), str(tmp_path / "ref3.txt"))
 
 
 @pytest.mark.gpu
@@ -100,6 +115,7 @@ def test_cli_depth_file_matches_reference(cli, tmp_path):
     out = subprocess.run([cli] + common + ["-o", str(tmp_path / "ours.txt")], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
     assert open(str(tmp_path / "ours.txt")).read() == open(str(tmp_path / "ref.txt")).read()
+    assert log_lines(str(tmp_path / "ours.txt.log"), str(tmp_path / "ours.txt")) == log_lines(str(tmp_path / "ref.txt.log"), str(tmp_path / "ref.txt"))
 
 
 def test_host_decoder_real_looking_records(cli, tmp_path):
@@ -139,6 +155,7 @@ def test_cli_real_looking_bam_matches_reference(cli, tmp_path):
     assert out.returncode == 0, out.stderr
     assert open(str(tmp_path / "gpus.txt.7_rd"), "rb").read() == open(str(tmp_path / "refs.txt.7_rd"), "rb").read()
     assert _table(str(tmp_path / "gpus.txt")) == _table(str(tmp_path / "refs.txt"))
+    assert log_lines(str(tmp_path / "gpus.txt.log"), str(tmp_path / "gpus.txt")) == log_lines(str(tmp_path / "refs.txt.log"), str(tmp_path / "refs.txt"))
 
 
 @pytest.mark.gpu

@@ -50,6 +50,8 @@ def test_config1_chr19_depth_file_cli_matches_reference(cli, tmp_path):
     assert out.returncode == 0, out.stderr
     assert open(str(tmp_path / "ours.txt")).read() == open(str(tmp_path / "ref.txt")).read()
     assert len(_table(str(tmp_path / "ref.txt"))) >= 12      # ~19 of the 20 planted events (the last marked run is never reported)
+    from test_cli import log_lines
+    assert log_lines(str(tmp_path / "ours.txt.log"), str(tmp_path / "ours.txt")) == log_lines(str(tmp_path / "ref.txt.log"), str(tmp_path / "ref.txt"))
 
 
 def test_config2_chr19_bam_cli_matches_reference(cli, tmp_path):
