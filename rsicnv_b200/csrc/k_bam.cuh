@@ -280,54 +280,71 @@ __device__ __forceinline__ void inf_symbol(InfState& S, const InfTabs& T, const 
 // The pending matches of all 32 lanes, copied by the whole warp.  A match byte i comes from i - dist, which for i >= dist is
 // a byte of the same match: the source is periodic, out[i] = src[i mod dist], so every byte can be read from data that was
 // complete before the copy began -- no byte depends on another one of this round.  The bytes of all lanes' matches are laid
-// end to end and dealt to the lanes 32 at a time (the owner of a byte is found by a search over the warp's prefix sums):
-// all loads of a round are independent and consecutive lanes touch consecutive addresses, instead of one lane copying
-// byte by byte (a load -> store -> load chain through L2) while 31 wait.
-struct InfPending { u8* a0; u8* a1; u32 v0, v1; };   // bytes loaded by the last round of inf_warp_copy, stored by the next call (a == nullptr: none)
+// end to end and dealt to the lanes INF_CPB consecutive bytes each, 32 * INF_CPB per round (one round covers nearly every
+// step: a match is ~10 bytes and about three lanes in four have one).  Who owns a flattened byte comes from shared memory
+// instead of a search over shuffles: every lane posts its match (destination, first flattened byte, length, distance) and
+// marks the byte where its match starts with its lane number; a running maximum over the marks, first inside the lane's
+// INF_CPB bytes and then across the lanes, names the owner of every byte.  All loads of a round are independent and
+// consecutive lanes touch consecutive addresses, instead of one lane copying byte by byte (a load -> store -> load chain
+// through L2) while 31 wait.
+#ifndef INF_CPB
+#define INF_CPB 8
+#endif
+struct InfPending { u8* a[INF_CPB]; u32 v[INF_CPB]; };   // bytes loaded by the last round of inf_warp_copy, stored by the next call (a == nullptr: none)
 
 __device__ __forceinline__ void inf_flush(InfPending& P) {
-  if (P.a0) { *P.a0 = (u8)P.v0; P.a0 = nullptr; }
-  if (P.a1) { *P.a1 = (u8)P.v1; P.a1 = nullptr; }
-}
-// owner of flattened byte t among the warp's matches: lane j (smallest j with incl_j > t), and the byte's source / destination
-__device__ __forceinline__ void inf_copy_assign(u32 t, u32 total, u32 incl, u32 len, u32 dist, u32 to_lo, u32 to_hi, u8** dstp, const u8** srcp) {
-  int lo = 0, hi = 31;
 #pragma unroll
-  for (int it = 0; it < 5; ++it) { const int mid = (lo + hi) >> 1; const u32 v = __shfl_sync(0xffffffffu, incl, mid); if (v > t) hi = mid; else lo = mid + 1; }
-  const int j = lo > 31 ? 31 : lo;
-  const u32 end_j = __shfl_sync(0xffffffffu, incl, j), len_j = __shfl_sync(0xffffffffu, len, j), dist_j = __shfl_sync(0xffffffffu, dist, j);
-  const u32 plo = __shfl_sync(0xffffffffu, to_lo, j), phi = __shfl_sync(0xffffffffu, to_hi, j);
-  *dstp = nullptr; *srcp = nullptr;
-  if (t < total) {
-    u8* tj = reinterpret_cast<u8*>((size_t)(((u64)phi << 32) | plo));
-    const u32 i = t - (end_j - len_j);
-    const u32 si = i < dist_j ? i : i % dist_j;
-    *dstp = tj + i; *srcp = tj - dist_j + si;
-  }
+  for (int k = 0; k < INF_CPB; ++k) if (P.a[k]) { *P.a[k] = (u8)P.v[k]; P.a[k] = nullptr; }
 }
-// 64 bytes per round (two per lane).  The loads of the LAST round are left in flight: their stores are issued by the next
-// call (or by inf_flush), after the next symbol has been decoded, so the L2 round trip of the copy overlaps the table
-// look-ups of the decode instead of adding to them.  Stores of a call are issued before its loads, with a warp barrier in
-// between (memory ordering among the lanes), because a match may read what the previous one wrote.
-__device__ __forceinline__ void inf_warp_copy(InfState& S, int lane, InfPending& P) {
+// The loads of the LAST round are left in flight: their stores are issued by the next call (or by inf_flush), after the
+// next symbols have been decoded, so the L2 round trip of the copy overlaps the table look-ups of the decode instead of
+// adding to them.  Stores of a call are issued before its loads, with a warp barrier in between (memory ordering among the
+// lanes), because a match may read what the previous one wrote.
+// mrec: 32 x uint4 of the warp (destination low/high, first flattened byte, length << 16 | distance - 1); mhead: 32 * INF_CPB mark bytes
+__device__ __forceinline__ void inf_warp_copy(InfState& S, int lane, InfPending& P, uint4* mrec, u8* mhead) {
   const u32 len = S.m_len;
   if (!__any_sync(0xffffffffu, len != 0)) return;
   u32 incl = len;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { const u32 up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += up; }
   const u32 total = __shfl_sync(0xffffffffu, incl, 31);
-  u8* const to = S.dst + S.o;
-  const u64 to_bits = (u64)(size_t)to;
-  const u32 to_lo = (u32)to_bits, to_hi = (u32)(to_bits >> 32);
-  for (u32 t0 = 0; t0 < total; t0 += 64) {
-    u8* d0; u8* d1; const u8* s0; const u8* s1;
-    inf_copy_assign(t0 + (u32)lane, total, incl, len, S.m_dist, to_lo, to_hi, &d0, &s0);
-    if (t0 + 32 < total) inf_copy_assign(t0 + 32 + (u32)lane, total, incl, len, S.m_dist, to_lo, to_hi, &d1, &s1);   // warp-uniform
-    else { d1 = nullptr; s1 = nullptr; }
+  const u32 excl = incl - len;
+  {
+    const u64 to_bits = (u64)(size_t)(S.dst + S.o);
+    mrec[lane] = make_uint4((u32)to_bits, (u32)(to_bits >> 32), excl, (len << 16) | (S.m_dist - 1u));
+  }
+  for (u32 t0 = 0; t0 < total; t0 += 32 * INF_CPB) {
+#pragma unroll
+    for (int k = 0; k < INF_CPB; k += 4) *reinterpret_cast<u32*>(mhead + lane * INF_CPB + k) = 0u;
+    __syncwarp();
+    if (len != 0 && excl < t0 + 32 * INF_CPB && incl > t0) mhead[excl > t0 ? excl - t0 : 0u] = (u8)(lane + 1);   // the match that straddles t0 marks byte 0
+    __syncwarp();
+    u32 own[INF_CPB], m = 0;
+#pragma unroll
+    for (int k = 0; k < INF_CPB; k += 4) {
+      const u32 hw = *reinterpret_cast<const u32*>(mhead + lane * INF_CPB + k);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { const u32 hq = (hw >> (8 * q)) & 255u; m = hq > m ? hq : m; own[k + q] = m; }
+    }
+    u32 sc = m;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const u32 up = __shfl_up_sync(0xffffffffu, sc, o); if (lane >= o) sc = up > sc ? up : sc; }
+    u32 carry = __shfl_up_sync(0xffffffffu, sc, 1);
+    if (lane == 0) carry = 0;
     inf_flush(P);
     __syncwarp();
-    if (s0) { P.v0 = *s0; P.a0 = d0; }
-    if (s1) { P.v1 = *s1; P.a1 = d1; }
+#pragma unroll
+    for (int k = 0; k < INF_CPB; ++k) {
+      const u32 t = t0 + (u32)(lane * INF_CPB + k);
+      if (t < total) {
+        const u32 j1 = own[k] > carry ? own[k] : carry;      // owner's lane + 1
+        const uint4 r = mrec[j1 - 1];
+        u8* tj = reinterpret_cast<u8*>((size_t)(((u64)r.y << 32) | r.x));
+        const u32 i = t - r.z, dist = (r.w & 0xffffu) + 1u;
+        const u32 si = i < dist ? i : i % dist;
+        P.a[k] = tj + i; P.v[k] = *(tj - dist + si);
+      }
+    }
   }
   S.o += len; S.m_len = 0;
 }
@@ -341,6 +358,8 @@ __global__ void __launch_bounds__(INF_NT, INF_MINB) k_bgzf_inflate(const u8* __r
   __shared__ u16 tab[120];
   __shared__ u16 cnts[INF_SSLOTS * INF_NT];
   __shared__ u16 sfast[(1 << INF_SB) * INF_NT];   // first-level literal/length table; doubles as the code-length code's table while a header is parsed
+  __shared__ uint4 mrec[INF_NT];                  // the matches of a copy round, one per lane
+  __shared__ __align__(8) u8 mhead[INF_NT * INF_CPB];   // who owns which flattened byte of the round
   __shared__ u16 sdist[(INF_DSH ? (1 << INF_DSH) : 1) * INF_NT];   // first-level distance table (optional; measured: 46.9 vs 48.0 ms with 6 bits, not worth the occupancy)
   {
     const u16 lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
@@ -367,13 +386,17 @@ __global__ void __launch_bounds__(INF_NT, INF_MINB) k_bgzf_inflate(const u8* __r
       S.dst = U + B.dst; S.dst_len = B.dst_len; S.phase = INF_HEADER;
     }
   }
-  InfPending P; P.a0 = nullptr; P.a1 = nullptr; P.v0 = 0; P.v1 = 0;
+  InfPending P;
+#pragma unroll
+  for (int k = 0; k < INF_CPB; ++k) { P.a[k] = nullptr; P.v[k] = 0; }
+  uint4* const wrec = mrec + (threadIdx.x & ~31u);
+  u8* const whead = mhead + (threadIdx.x & ~31u) * INF_CPB;
   while (__any_sync(0xffffffffu, S.phase != INF_DONE)) {
     // lanes that need a block header (table construction: long) go first and together; the others decode symbols
     if (__any_sync(0xffffffffu, S.phase == INF_HEADER)) { if (S.phase == INF_HEADER) { InfState H = S; inf_block_header(H, T); S = H; } }   // out of line: a copy keeps S in registers
     else {
 #pragma unroll 1
-      for (int it = 0; it < 8; ++it) { if (S.phase == INF_SYMS) inf_symbol(S, T, tab); __syncwarp(); inf_warp_copy(S, T.lane, P); }
+      for (int it = 0; it < 8; ++it) { if (S.phase == INF_SYMS) inf_symbol(S, T, tab); __syncwarp(); inf_warp_copy(S, T.lane, P, wrec, whead); }
     }
   }
   inf_flush(P);
