@@ -472,11 +472,21 @@ def main():
             t.join()
         return got
 
+    # warm-up: every worker context takes the rank's largest contig once (its device buffers then fit any contig: no
+    # cudaMalloc / cudaFree, which synchronise the whole device, inside the timed region), then one untimed pass
+    if big is not None:
+        for w, cx in enumerate(workers):
+            one(cx, wbufs[w], big)
     got = e2e_pass(1)
     assert all(got[i] == staged_calls[i] for i in mine), "the path from BAM bytes disagrees with the staged-reads path"
     barrier()
     t0 = time.perf_counter()
-    e2e_pass(a.steps)
+    pass_ms = []
+    for _ in range(a.steps):
+        tp = time.perf_counter()
+        e2e_pass(1)
+        torch.cuda.synchronize()
+        pass_ms.append(1e3 * (time.perf_counter() - tp))
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - t0)
     dprof = []
@@ -524,7 +534,8 @@ def main():
                     "how": "dominant streaming kernel (largest time among the HBM-bound kernels): algorithmic bytes per launch / average launch duration "
                            "(CUDA events on the context's stream, %d extra profiled steps on the rank's largest contig, %d bp)" % (a.profile_steps, L),
                     "top_kernel_by_time": kern[0]["kernel"], "top_kernel_ms": kern[0]["avg_ms"],
-                    "streaming_kernels": [{"kernel": k["kernel"], "gbs": k["gbs"], "frac": (k["gbs"] or 0) / peak, "ms": k["avg_ms"], "share_of_step": k["ms_per_step"] / tot_ms} for k in stream],
+                    "streaming_kernels": [{"kernel": k["kernel"], "gbs": k["gbs"], "frac": (k["gbs"] or 0) / peak, "ms": k["avg_ms"], "share_of_step": k["ms_per_step"] / tot_ms,
+                                           "traffic": ncu_traffic().get(k["kernel"])} for k in stream],
                     "streaming_share_of_step": sum(k["ms_per_step"] for k in stream) / tot_ms,
                     # the whole hot path against the same peak: algorithmic bytes of every stage / step time, all GPUs (per GPU: / n_gpus)
                     "path_achieved": path_gbs, "path_frac": path_gbs / (peak * world), "path_bytes_per_base": path_bytes / step_bases}
@@ -535,6 +546,7 @@ def main():
                 "e2e": {"value": step_bases * a.steps / (e2e_ms / 1e3) / 1e9, "unit": "Gbases/s",
                         "h2d_bytes_per_step": int(sum((bam_bytes[i] if bam else 4 * lens[i]) + lens[i] for i in range(len(lens)))),
                         "d2h_bytes_per_step": d2h * world if scaling == "weak" else d2h, "ms_per_step": e2e_ms / a.steps,
+                        "pass_ms_rank0": [round(x, 1) for x in pass_ms], "worker_contexts": len(workers),
                         "input": ("BAM file images (BGZF) + FASTA contigs in pinned host memory -> rsigpu_bam_feed/take -> rsigpu_run -> calls on the host" if bam else
                                   "depth arrays + FASTA contigs in pinned host memory -> rsigpu_set_depth -> rsigpu_run -> calls on the host")},
                 "gpu_launches": launches, "calls": int(len(table)), "table_sha1": hashlib.sha1("\n".join(table).encode()).hexdigest(), "roofline": roof,

@@ -215,6 +215,9 @@ int rsigpu_get_profile(const rsigpu_ctx* c, char* names, int32_t name_stride, fl
 int rsigpu_set_level0_mode(rsigpu_ctx* c, int mode);
 /* test hook: decoded bytes one rsigpu_bam_feed may produce (tests of the partial-consumption path; 5 GiB by default, >= 64 KiB) */
 int rsigpu_set_feed_limit(rsigpu_ctx* c, int64_t decoded_bytes);
+/* tuning / test hook: which inflate kernel rsigpu_bam_feed uses: 0 = by chunk size (default: a warp per BGZF block below
+ * 28,000 blocks, a lane per block above), 1 = always a lane per block, 2 = always a warp per block; same bytes either way */
+int rsigpu_set_inflate_mode(rsigpu_ctx* c, int mode);
 /* tuning hook: threads of the bin-level candidate kernel (multiple of 32, 32..1024) */
 int rsigpu_set_cand_threads(rsigpu_ctx* c, int threads);
 /* test hook: selected device-resident scalars of the last stage, as doubles; returns how many exist */

@@ -288,7 +288,7 @@ __device__ __forceinline__ void inf_symbol(InfState& S, const InfTabs& T, const 
 // consecutive lanes touch consecutive addresses, instead of one lane copying byte by byte (a load -> store -> load chain
 // through L2) while 31 wait.
 #ifndef INF_CPB
-#define INF_CPB 8
+#define INF_CPB 4
 #endif
 struct InfPending { u8* a[INF_CPB]; u32 v[INF_CPB]; };   // bytes loaded by the last round of inf_warp_copy, stored by the next call (a == nullptr: none)
 
@@ -351,7 +351,7 @@ __device__ __forceinline__ void inf_warp_copy(InfState& S, int lane, InfPending&
 
 // inflate: one thread per BGZF block of the chunk, the warp re-converged after every step
 #ifndef INF_MINB
-#define INF_MINB 1
+#define INF_MINB 16      // <= 64 registers: the inflate launches of several contigs fit an SM side by side
 #endif
 __global__ void __launch_bounds__(INF_NT, INF_MINB) k_bgzf_inflate(const u8* __restrict__ comp, const BgzfBlock* __restrict__ blk, int nblk, u8* __restrict__ U,
                                                          u16* __restrict__ tabs, int* __restrict__ err) {
@@ -402,6 +402,10 @@ __global__ void __launch_bounds__(INF_NT, INF_MINB) k_bgzf_inflate(const u8* __r
   inf_flush(P);
   if (S.rc) { atomicOr(err + 1, (int)BAM_ERR_INFLATE); atomicMax(err + 2, S.rc); }
 }
+
+}  // namespace rsigpu
+#include "k_inflate_warp.cuh"
+namespace rsigpu {
 
 // ---------------------------------------------------------------------------------------------
 // records
@@ -613,20 +617,26 @@ __global__ void k_bam_fields(BamChunk C, BamChain H, const int* __restrict__ rba
   if (blockIdx.x == 0 && threadIdx.x == 0) { S.cigar_off[info[0]] = (u32)info[1]; S.qual_off[info[0]] = (u64)info[2]; }
 }
 
-// CIGAR words and quality bytes: one warp per record
+// CIGAR words and quality bytes: eight lanes per record, four records per warp at a time -- the per-record chain of
+// dependent loads (record offset -> core fields -> payload) is latency, so four of them are kept in flight per warp
 __global__ void k_bam_payload(const u8* __restrict__ U, const i64* __restrict__ info, BamSoA S) {
   const int n = (int)info[0];
-  const int lane = (int)(threadIdx.x & 31);
-  const int wid = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), nw = (int)((gridDim.x * blockDim.x) >> 5);
-  for (int r = wid; r < n; r += nw) {
+  const int sub = (int)(threadIdx.x & 7);
+  const int gid = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 3), ng = (int)((gridDim.x * blockDim.x) >> 3);
+  for (int r = gid; r < n; r += ng) {
     const u8* q = U + S.rec[r];
     const u32 l_name = q[12], n_cig = (u32)q[16] | ((u32)q[17] << 8), l_seq = ld32u(q + 20);
     const u8* cg = q + 36 + l_name;
     u32* cd = S.cigar + S.cigar_off[r];
-    for (u32 j = (u32)lane; j < n_cig; j += 32) cd[j] = ld32u(cg + 4 * j);
+    for (u32 j = (u32)sub; j < n_cig; j += 8) cd[j] = ld32u(cg + 4 * j);
     const u8* qs = cg + 4 * n_cig + (l_seq + 1) / 2;
     u8* qd = S.qual + S.qual_off[r];
-    for (u32 j = (u32)lane; j < l_seq; j += 32) qd[j] = qs[j];
+    u32 j = (u32)sub;
+    for (; j + 24 < l_seq; j += 32) {          // four independent bytes per lane and trip
+      const u8 a0 = qs[j], a1 = qs[j + 8], a2 = qs[j + 16], a3 = qs[j + 24];
+      qd[j] = a0; qd[j + 8] = a1; qd[j + 16] = a2; qd[j + 24] = a3;
+    }
+    for (; j < l_seq; j += 8) qd[j] = qs[j];
   }
 }
 

@@ -268,20 +268,31 @@ __device__ __forceinline__ void rsi_scan_body(const float* __restrict__ t, const
     const int ilo = h + 1, ihi = nb - h - 1;        // valid centres: ilo <= i < ihi
     u32* hwb = hw + (size_t)(pbuf * 4) * NW;        // double-buffered hit words [length][sign][word]: one barrier per pair
     pbuf ^= 1;
+    // "sum <= sdel or sum >= sdup" as ONE unsigned compare: (sum - sdel - 1) mod 2^64 >= sdup - sdel - 1 (a range of 0 = always look closer)
+    const u64 rng0 = sdel0 < sdup0 ? (u64)sdup0 - (u64)sdel0 - 1ull : 0ull, rng1 = sdel1 < sdup1 ? (u64)sdup1 - (u64)sdel1 - 1ull : 0ull;
     int anyhit = 0;
     for (int w = warp; w < nwords; w += S_NT / 32) {
       const int ci = w * 32 + lane;                 // centre index within [0, NC)
       const int i = cbase + ci;
-      bool hd0 = false, hu0 = false, hd1 = false, hu1 = false;
-      if (ci < NC && i >= ilo && i < ihi) {
-        const int kw = i - h - base;                // smem index of the window start
+      bool hd0 = false, hu0 = false, hd1 = false, hu1 = false, near = false;
+      const bool valid = ci < NC && i >= ilo && i < ihi;
+      const int kw = i - h - base;                  // smem index of the window start
+      i64 s0 = 0, s1 = 0;
+      if (valid) {
         const i64 p0 = P[kw];
-        const i64 s0 = P[kw + L0] - p0;
+        s0 = P[kw + L0] - p0;
+        near = (u64)s0 - (u64)sdel0 - 1ull >= rng0;
+        if (nL == 2) { s1 = P[kw + L0 + 1] - p0; near = near || ((u64)s1 - (u64)sdel1 - 1ull >= rng1); }
+      }
+      if (!__any_sync(0xffffffffu, near)) {         // no window of this word reaches a threshold (nearly always)
+        if (lane == 0) { hwb[w] = 0u; hwb[NW + w] = 0u; hwb[2 * NW + w] = 0u; hwb[3 * NW + w] = 0u; }
+        continue;
+      }
+      if (valid) {
         hd0 = s0 <= sdel0; hu0 = s0 >= sdup0;
         if (hd0) hd0 = window_median_ok(medint, i - h, L0, (int)cle[kw + L0] - (int)cle[kw], limd, -1);
         if (hu0) hu0 = window_median_ok(medint, i - h, L0, (int)cge[kw + L0] - (int)cge[kw], limu, +1);
         if (nL == 2) {
-          const i64 s1 = P[kw + L0 + 1] - p0;
           hd1 = s1 <= sdel1; hu1 = s1 >= sdup1;
           if (hd1) hd1 = window_median_ok(medint, i - h, L0 + 1, (int)cle[kw + L0 + 1] - (int)cle[kw], limd, -1);
           if (hu1) hu1 = window_median_ok(medint, i - h, L0 + 1, (int)cge[kw + L0 + 1] - (int)cge[kw], limu, +1);

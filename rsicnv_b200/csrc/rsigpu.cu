@@ -155,6 +155,7 @@ struct rsigpu_ctx {
   std::vector<BamRun> b_runs;
   int b_nref = 0, b_tail_len = 0, b_rewalked = 0; bool b_active = false, b_first_feed = true;
   size_t b_umax = (size_t)5 << 30;   // decoded bytes one feed may produce (test hook: rsigpu_set_feed_limit)
+  int inflate_mode = 0;              // 0 = by chunk size, 1 = one lane per BGZF block, 2 = one warp per BGZF block (rsigpu_set_inflate_mode)
   // accounting
   long long h_cprof[16] = {};
   int64_t launches = 0;
@@ -566,7 +567,6 @@ int rsigpu_bam_feed(rsigpu_ctx* c, const uint8_t* bgzf, int64_t nbytes, int64_t 
   if (c->b_first_feed) { if ((size_t)skip > utotal) { c->fail("bam_feed: skip beyond the decoded chunk"); return RSIGPU_E_ARG; } }
   else if (skip != 0) { c->fail("bam_feed: skip is only meaningful on the first feed"); return RSIGPU_E_ARG; }
   CK(c->b_comp.ensure(off + 64)); CK(c->b_U.ensure((size_t)BAM_HEAD + utotal + 64)); CK(c->b_blk.ensure((size_t)nblk)); CK(c->b_bound.ensure((size_t)nblk + 1));
-  CK(c->b_tabs.ensure(RSI_INFLATE_TAB_BYTES(nblk) / 2));
   CK(c->b_first.ensure(nblk)); CK(c->b_endp.ensure(nblk)); CK(c->b_tailp.ensure(nblk)); CK(c->b_cnt.ensure(nblk)); CK(c->b_ncig.ensure(nblk)); CK(c->b_nq.ensure(nblk));
   CK(c->b_in.ensure(nblk)); CK(c->b_rbase.ensure(nblk)); CK(c->b_cbase.ensure(nblk)); CK(c->b_qbase.ensure(nblk)); CK(c->b_info.ensure(8)); CK(c->b_cnt32.ensure(4));
   TRACE(c, "feed: start");
@@ -577,7 +577,14 @@ int rsigpu_bam_feed(rsigpu_ctx* c, const uint8_t* bgzf, int64_t nbytes, int64_t 
   if (c->b_tail_len) CK(cudaMemcpyAsync(c->b_U.p + (BAM_HEAD - c->b_tail_len), c->b_carry.p, (size_t)c->b_tail_len, cudaMemcpyDeviceToDevice, c->stream));
   i64* info = c->b_info.p; int* err = c->b_cnt32.p;
   if (trace_on()) { cudaStreamSynchronize(c->stream); TRACE(c, "feed: H2D done"); }
-  KL(k_bgzf_inflate, (nblk + INF_NT - 1) / INF_NT, INF_NT, 0, c->b_comp.p, c->b_blk.p, nblk, c->b_U.p, c->b_tabs.p, err);
+  // two inflate kernels (k_inflate_warp.cuh): a warp per block costs time proportional to the chunk, a lane per block about
+  // the same 30-38 ms for any chunk up to a chr19-sized one
+  if (c->inflate_mode == 2 || (c->inflate_mode == 0 && nblk < (int)infw::INFW_MAX_BLOCKS))
+    KL(k_bgzf_inflate_warp, (nblk + infw::INFW_WARPS - 1) / infw::INFW_WARPS, infw::INFW_NT, 0, c->b_comp.p, (u32)((off + 3) / 4), c->b_blk.p, nblk, c->b_U.p, err);
+  else {
+    CK(c->b_tabs.ensure(RSI_INFLATE_TAB_BYTES(nblk) / 2));
+    KL(k_bgzf_inflate, (nblk + INF_NT - 1) / INF_NT, INF_NT, 0, c->b_comp.p, c->b_blk.p, nblk, c->b_U.p, c->b_tabs.p, err);
+  }
   BamChunk C; C.U = c->b_U.p; C.u_begin = c->b_first_feed ? (i64)BAM_HEAD + skip : (i64)BAM_HEAD - c->b_tail_len; C.u_end = (i64)(BAM_HEAD + utotal);
   C.bound = c->b_bound.p; C.nblk = nblk; C.n_ref = c->b_nref;
   BamChain H; H.first = c->b_first.p; H.endp = c->b_endp.p; H.tailp = c->b_tailp.p; H.cnt = c->b_cnt.p; H.ncig = c->b_ncig.p; H.nq = c->b_nq.p;
@@ -1489,6 +1496,11 @@ int rsigpu_set_level0_mode(rsigpu_ctx* c, int mode) {
   return RSIGPU_OK;
 }
 // test hook: decoded bytes one rsigpu_bam_feed may produce (partial-consumption path)
+int rsigpu_set_inflate_mode(rsigpu_ctx* c, int mode) {
+  if (!c || mode < 0 || mode > 2) return RSIGPU_E_ARG;
+  c->inflate_mode = mode;
+  return RSIGPU_OK;
+}
 int rsigpu_set_feed_limit(rsigpu_ctx* c, int64_t decoded_bytes) {
   if (!c || decoded_bytes < 65536) return RSIGPU_E_ARG;
   c->b_umax = (size_t)decoded_bytes;

@@ -11,6 +11,12 @@ from rsicnv_b200 import api, synth
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=[1, 2], ids=["lane-per-block", "warp-per-block"])
+def inflate_mode(request, monkeypatch):
+    """every test of this module runs with each of the two inflate kernels (rsigpu_set_inflate_mode through api.Context's env hook)"""
+    monkeypatch.setenv("RSIGPU_INFLATE_MODE", str(request.param))
+
+
 @pytest.mark.parametrize("level,strategy,chunk", [(1, 0, None), (6, 0, 70000), (0, 0, 150000), (9, zlib.Z_FIXED, 200000), (1, zlib.Z_HUFFMAN_ONLY, 90001)])
 def test_decode_matches_source_reads(gpu_lib, tmp_path, level, strategy, chunk):
     T.test_decode_matches_source_reads(gpu_lib, tmp_path, level, strategy, chunk)

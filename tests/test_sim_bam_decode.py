@@ -10,6 +10,11 @@ from rsicnv_b200 import api, synth
 
 FIELDS = ("pos", "mpos", "isize", "mtid", "flag", "mapq", "cigar_off", "cigar", "qual_off", "qual")
 
+@pytest.fixture(autouse=True, params=[1, 2], ids=["lane-per-block", "warp-per-block"])
+def inflate_mode(request, monkeypatch):
+    """every test of this module runs with each of the two inflate kernels (rsigpu_set_inflate_mode through api.Context's env hook)"""
+    monkeypatch.setenv("RSIGPU_INFLATE_MODE", str(request.param))
+
 
 def concat_reads(parts):
     out = {k: [] for k in FIELDS}

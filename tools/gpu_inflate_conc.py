@@ -14,7 +14,9 @@ path = "/tmp/prof.bam"
 synth.write_bam(path, [("19", L)], {0: reads}, level=1, random_seq=7, threads=32)
 data = np.fromfile(path, np.uint8)
 h = api.parse_bam_header(data)
-lib0 = api.load_library()
+LIB = sys.argv[3] if len(sys.argv) > 3 else None
+lib0 = api.load_library(LIB)
+print("library", LIB or api.DEFAULT_LIB, flush=True)
 pin = C.c_void_p(); assert lib0.rsigpu_pinned_alloc(C.c_size_t(len(data)), C.byref(pin)) == 0
 C.memmove(pin, data.ctypes.data, len(data))
 print("BAM image %.1f MB" % (len(data) / 1e6), flush=True)
@@ -27,7 +29,7 @@ def feed(cx):
     cx.bam_end()
     return t0, t1
 
-ctxs = [api.Context() for _ in range(max(KS))]
+ctxs = [api.Context(lib=LIB) for _ in range(max(KS))]
 for K in KS:
     pool = ThreadPoolExecutor(K)
     cs = ctxs[:K]
