@@ -15,7 +15,8 @@ Workloads (BASELINE.json configs):
 contexts; each step = pileup -> GC adjust -> cap -> bins -> RSI scan -> candidates -> RP/Q0 -> calls on the host), wall time of
 the K timed steps bracketed by barrier + torch.cuda.synchronize on both sides, max over ranks.  `e2e` = the same work starting
 from the BAM FILE's bytes in pinned host memory (H2D + BGZF inflate + record decode on the GPU inside the timed region) through
-the C ABI.  `--impl reference` times the unmodified reference CLI (oracle/_ref/rsicnv, built from /root/reference by
+the C ABI: the rank's contigs go to the decoder in batches of --e2e-batch-mb compressed bytes (rsigpu_bam_feed_parts: the byte
+ranges of several contigs inflated by one launch), then every contig is taken and run on its own.  `--impl reference` times the unmodified reference CLI (oracle/_ref/rsicnv, built from /root/reference by
 oracle/Makefile.ref) on the box's host cores on a bounded sample of the same workload.
 
 The whole-genome inputs are built from ONE seeded master contig (the longest): contig i is the master truncated to its length
@@ -270,6 +271,8 @@ def main():
     ap.add_argument("--profile-steps", type=int, default=2)
     ap.add_argument("--inflight", "--contigs-per-step", type=int, default=4, dest="inflight",
                     help="contigs in flight per GPU (one context + stream + host thread each, as the CLI runs them)")
+    ap.add_argument("--e2e-batch-mb", type=int, default=1800, help="e2e leg: compressed MiB of BAM one decoder feed takes (the contigs of a batch are inflated by one launch; "
+                                                                      "a feed holds at most 2 GiB compressed and, here, 10 GiB decoded)")
     ap.add_argument("--no-cli", action="store_true", help="skip the CLI / one-core reference comparison at the end (N=1)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -422,64 +425,97 @@ def main():
     torch.cuda.empty_cache()
 
     # ---- end-to-end leg: host bytes -> H2D -> (BGZF inflate + record decode) -> hot path -> calls on the host, every step.
-    # K worker contexts, each with its own host thread, take this rank's contigs longest first; no barrier between contigs.
-    workers = [mk() for _ in range(min(K, max(1, len(mine))))]
-    wbufs = [(api.Cnv * 65536)() for _ in workers]
+    # BAM: the rank's contigs are grouped into batches of <= --e2e-batch-mb of compressed bytes; a worker (host thread + one
+    # decoder context + one contig context) decodes a batch with ONE rsigpu_bam_feed_parts call -- one inflate launch over the
+    # blocks of all its contigs, which is what the GPU decodes efficiently -- then takes and runs the contigs one by one while
+    # the other workers decode.  Depth files: one contig per work item.
     import queue
+    if bam:
+        limit = int(a.e2e_batch_mb) << 20
+        batches = []                                  # first-fit decreasing
+        for i in sorted(mine, key=lambda i: -bam_bytes[i]):
+            for b in batches:
+                if sum(bam_bytes[j] for j in b) + bam_bytes[i] <= limit:
+                    b.append(i); break
+            else:
+                batches.append([i])
+        items = batches
+    else:
+        items = [[i] for i in mine]
+    nwork = min(K, max(1, len(items)))
+    decoders = [mk() for _ in range(nwork)] if bam else []
+    for d in decoders:
+        d.set_feed_limit(10 << 30)          # decoded bytes one feed may produce (level-1 BGZF of BAM records inflates ~4.9x)
+    workers = [mk() for _ in range(nwork)]
+    wbufs = [(api.Cnv * 65536)() for _ in workers]
+    phase_s = [[0.0, 0.0, 0.0, 0.0] for _ in workers]      # host wall time per worker: feed_parts, set_reference, take, run
 
-    def file_one(cx, out, i):
-        """BAM file bytes (pinned host memory) -> BGZF inflate + record decode on the GPU -> pileup -> ... -> calls on the host"""
-        cx.set_reference_ptr(fa_pin.data_ptr(), lens[i])
-        cx.pileup_begin()
-        cx.bam_begin(1)
-        off = 0; n = bam_bytes[i]
-        while off < n:
-            consumed, runs = cx.bam_feed(bam_pin.data_ptr() + rec_off + off, n - off, skip=0)
-            for r, (tid, nr) in enumerate(runs):
-                if tid == 0:
-                    cx.bam_take(r, cx)
-            if consumed == 0:
-                break
-            off += consumed
-        cx.bam_end(); cx.have_reads()
-        return cx.run_count(out, 65536)
+    def batch_one(w, batch):
+        """BAM file bytes (pinned host memory) of every contig of the batch -> BGZF inflate + record decode on the GPU (one chunk) ->
+        per contig: pileup -> ... -> calls on the host"""
+        dec, cx, out = decoders[w], workers[w], wbufs[w]
+        ph = phase_s[w]
+        t0 = time.perf_counter()
+        dec.bam_begin(1)
+        runs = dec.bam_feed_parts([(bam_pin.data_ptr() + rec_off, bam_bytes[i]) for i in batch])
+        t1 = time.perf_counter(); ph[0] += t1 - t0
+        res = {}
+        for r, (tid, nr, part) in enumerate(runs):
+            i = batch[part]
+            t1 = time.perf_counter()
+            cx.set_reference_ptr(fa_pin.data_ptr(), lens[i])
+            cx.pileup_begin()
+            t2 = time.perf_counter(); ph[1] += t2 - t1
+            dec.bam_take(r, cx)
+            cx.have_reads()
+            t3 = time.perf_counter(); ph[2] += t3 - t2
+            res[i] = cx.run_count(out, 65536)
+            ph[3] += time.perf_counter() - t3
+        dec.bam_end()
+        return res
 
-    def depth_one(cx, out, i):
+    def depth_one(w, batch):
+        cx, i = workers[w], batch[0]
         cx.set_reference_ptr(fa_pin.data_ptr(), lens[i])
         cx.set_depth_ptr(dp_pin.data_ptr(), lens[i])
-        return cx.run_count(out, 65536)
+        return {i: cx.run_count(wbufs[w], 65536)}
 
-    one = file_one if bam else depth_one
+    one = batch_one if bam else depth_one
 
     def e2e_pass(nsteps):
         q = queue.Queue()
         for _ in range(nsteps):
-            for i in mine:
-                q.put(i)
+            for b in sorted(items, key=lambda b: -sum((bam_bytes[j] if bam else lens[j]) for j in b)):
+                q.put(b)
         got = {}
 
         def work(w):
             while True:
                 try:
-                    i = q.get_nowait()
+                    b = q.get_nowait()
                 except queue.Empty:
                     return
-                got[i] = one(workers[w], wbufs[w], i)
-        ths = [threading.Thread(target=work, args=(w,)) for w in range(len(workers))]
+                got.update(one(w, b))
+        ths = [threading.Thread(target=work, args=(w,)) for w in range(nwork)]
         for t in ths:
             t.start()
         for t in ths:
             t.join()
         return got
 
-    # warm-up: every worker context takes the rank's largest contig once (its device buffers then fit any contig: no
-    # cudaMalloc / cudaFree, which synchronise the whole device, inside the timed region), then one untimed pass
-    if big is not None:
-        for w, cx in enumerate(workers):
-            one(cx, wbufs[w], big)
+    # warm-up: every worker takes the largest work item once (its device buffers then fit any item: no cudaMalloc / cudaFree,
+    # which synchronise the whole device, inside the timed region), then one untimed pass
+    if items:
+        biggest = max(items, key=lambda b: sum((bam_bytes[j] if bam else lens[j]) for j in b))
+        for w in range(nwork):
+            one(w, biggest)
+            if big is not None and big not in biggest:
+                one(w, [big])
     got = e2e_pass(1)
     assert all(got[i] == staged_calls[i] for i in mine), "the path from BAM bytes disagrees with the staged-reads path"
     barrier()
+    for ph in phase_s:
+        ph[:] = [0.0, 0.0, 0.0, 0.0]
     t0 = time.perf_counter()
     pass_ms = []
     for _ in range(a.steps):
@@ -489,13 +525,15 @@ def main():
         pass_ms.append(1e3 * (time.perf_counter() - tp))
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - t0)
-    dprof = []
-    if bam and big is not None:
-        workers[0].set_profile(True)
-        file_one(workers[0], wbufs[0], big)
-        dprof = [(nm, ms, n) for nm, ms, n in workers[0].profile() if nm.startswith("k_bgzf") or nm.startswith("k_bam")]
-        workers[0].set_profile(False)
-    for cx in workers:
+    dprof = []; dprof_batch = None
+    if bam and items:
+        biggest = max(items, key=lambda b: sum(bam_bytes[j] for j in b))
+        decoders[0].set_profile(True)
+        batch_one(0, biggest)
+        dprof = [(nm, ms, n) for nm, ms, n in decoders[0].profile() if nm.startswith("k_bgzf") or nm.startswith("k_bam")]
+        decoders[0].set_profile(False)
+        dprof_batch = {"contigs": len(biggest), "compressed_bytes": int(sum(bam_bytes[j] for j in biggest)), "bases": int(sum(lens[j] for j in biggest))}
+    for cx in workers + decoders:
         cx.close()
 
     t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
@@ -546,8 +584,9 @@ def main():
                 "e2e": {"value": step_bases * a.steps / (e2e_ms / 1e3) / 1e9, "unit": "Gbases/s",
                         "h2d_bytes_per_step": int(sum((bam_bytes[i] if bam else 4 * lens[i]) + lens[i] for i in range(len(lens)))),
                         "d2h_bytes_per_step": d2h * world if scaling == "weak" else d2h, "ms_per_step": e2e_ms / a.steps,
-                        "pass_ms_rank0": [round(x, 1) for x in pass_ms], "worker_contexts": len(workers),
-                        "input": ("BAM file images (BGZF) + FASTA contigs in pinned host memory -> rsigpu_bam_feed/take -> rsigpu_run -> calls on the host" if bam else
+                        "pass_ms_rank0": [round(x, 1) for x in pass_ms], "workers": nwork, "work_items": len(items),
+                        "worker_wall_ms_per_step_rank0": [dict(zip(("feed_parts", "set_reference", "take", "run"), [round(1e3 * x / a.steps, 1) for x in ph])) for ph in phase_s],
+                        "input": ("BAM file images (BGZF) + FASTA contigs in pinned host memory -> rsigpu_bam_feed_parts (the contigs of a batch decoded as one chunk) / take -> rsigpu_run per contig -> calls on the host" if bam else
                                   "depth arrays + FASTA contigs in pinned host memory -> rsigpu_set_depth -> rsigpu_run -> calls on the host")},
                 "gpu_launches": launches, "calls": int(len(table)), "table_sha1": hashlib.sha1("\n".join(table).encode()).hexdigest(), "roofline": roof,
                 "largest_contig_stage_ms": stages,
@@ -556,11 +595,9 @@ def main():
                           "kernels: CUDA events around every launch of one context in extra profiled steps",
                 "kernels": kern[:14]}
         if dprof:
-            n = n_reads[big]
-            dec_bytes = int(qo[n] * 3 // 2 + 38 * n + 4 * co[n])
-            line["decode_kernels"] = [{"kernel": nm, "launches": nl, "ms": ms,
-                                       **({"compressed_bytes": bam_bytes[big], "decoded_bytes": dec_bytes, "decoded_gbs": dec_bytes / 1e9 / (ms / 1e3)} if nm == "k_bgzf_inflate" else {})}
-                                      for nm, ms, nl in sorted(dprof, key=lambda x: -x[1])]
+            line["decode_kernels"] = [{"kernel": nm, "launches": nl, "ms": ms} for nm, ms, nl in sorted(dprof, key=lambda x: -x[1])]
+            line["decode_batch"] = dict(dprof_batch, what="the largest e2e work item: the record blocks of these contigs decoded by one rsigpu_bam_feed_parts call "
+                                                         "(decode_kernels = CUDA-event times of that call's kernels)")
         if world == 1 and not a.no_cli:
             # release this process's pinned buffers before other processes (the CLIs) are timed
             if bam:

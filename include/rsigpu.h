@@ -142,10 +142,17 @@ int rsigpu_pileup_commit(rsigpu_ctx* c);   /* only marks the staged batches comp
  *                                   itself or a context on another GPU).  Runs are valid until the next feed.
  *   end()                           fails if the file stopped inside a record.
  * HOST pointers (pinned memory from rsigpu_pinned_alloc makes the copy asynchronous and full speed). */
-typedef struct rsigpu_bam_run { int32_t tid; int32_t reserved_; int64_t n_reads; } rsigpu_bam_run;
+typedef struct rsigpu_bam_run { int32_t tid; int32_t part; int64_t n_reads; } rsigpu_bam_run;   /* part: which range of rsigpu_bam_feed_parts (0 for rsigpu_bam_feed) */
 int rsigpu_bam_begin(rsigpu_ctx* c, int32_t n_ref);
 int rsigpu_bam_feed(rsigpu_ctx* c, const uint8_t* bgzf, int64_t nbytes, int64_t skip, int64_t* consumed, rsigpu_bam_run* runs, int32_t cap,
                     int32_t* n_runs);
+/* Several byte ranges decoded as ONE chunk (one inflate launch over all their blocks: the GPU decodes a large chunk far
+ * more efficiently than several small ones).  Every range is a whole number of BGZF blocks that begins at a record start and
+ * ends at a record end -- e.g. the records of one contig each, cut at the virtual offsets of the .bai when they fall on
+ * block boundaries -- and starts a new run (runs[i].part says which range a run came from).  All or nothing: the ranges
+ * must fit one feed (2 GiB compressed, 5 GiB decoded); nothing is carried over. */
+int rsigpu_bam_feed_parts(rsigpu_ctx* c, int32_t n_parts, const uint8_t* const* parts, const int64_t* nbytes, rsigpu_bam_run* runs, int32_t cap,
+                          int32_t* n_runs);
 int rsigpu_bam_take(rsigpu_ctx* c, int32_t run, rsigpu_ctx* dst);
 /* only the records of the run with pos in [pos_lo, pos_hi) (a part of a contig split over several GPUs, rsigpu_split_run) */
 int rsigpu_bam_take_range(rsigpu_ctx* c, int32_t run, rsigpu_ctx* dst, int32_t pos_lo, int32_t pos_hi);
@@ -213,7 +220,8 @@ int rsigpu_get_profile(const rsigpu_ctx* c, char* names, int32_t name_stride, fl
 /* test hook: filterstatus' level-0 float sum (rsi.cpp:967-974) as 0 = one sequential FADD chain,
  * 1 = the exact one-block scan form, 2 = the exact multi-block form (default); all must give identical bits. */
 int rsigpu_set_level0_mode(rsigpu_ctx* c, int mode);
-/* test hook: decoded bytes one rsigpu_bam_feed may produce (tests of the partial-consumption path; 5 GiB by default, >= 64 KiB) */
+/* decoded bytes one rsigpu_bam_feed / rsigpu_bam_feed_parts may produce: bounds the decoder's buffers (5 GiB by default, >= 64 KiB;
+ * the tests of the partial-consumption path set it small, bench.py raises it to batch more contigs per feed) */
 int rsigpu_set_feed_limit(rsigpu_ctx* c, int64_t decoded_bytes);
 /* tuning / test hook: which inflate kernel rsigpu_bam_feed uses: 0 = by chunk size (default: a warp per BGZF block below
  * 28,000 blocks, a lane per block above), 1 = always a lane per block, 2 = always a warp per block; same bytes either way */

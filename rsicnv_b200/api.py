@@ -71,7 +71,7 @@ EXPORTS = ("rsigpu_default_params", "rsigpu_create", "rsigpu_destroy", "rsigpu_l
            "rsigpu_set_depth", "rsigpu_pileup_begin", "rsigpu_pileup_push", "rsigpu_pileup_end", "rsigpu_load_finish", "rsigpu_detectcnv",
            "rsigpu_sd_filters", "rsigpu_cnv_stat", "rsigpu_get_calls", "rsigpu_run", "rsigpu_get_chr_stats", "rsigpu_get_array",
            "rsigpu_format_row", "rsigpu_launch_count", "rsigpu_last_stage_ms", "rsigpu_set_profile", "rsigpu_get_profile",
-           "rsigpu_get_log", "rsigpu_reads_begin", "rsigpu_stat_calls", "rsigpu_bam_take_range", "rsigpu_split_range", "rsigpu_split_run", "rsigpu_split_p2p_bytes", "rsigpu_set_level0_mode", "rsigpu_set_feed_limit", "rsigpu_set_inflate_mode", "rsigpu_set_cand_threads", "rsigpu_debug_state", "rsigpu_pileup_commit", "rsigpu_bam_begin", "rsigpu_bam_feed", "rsigpu_bam_take",
+           "rsigpu_get_log", "rsigpu_reads_begin", "rsigpu_stat_calls", "rsigpu_bam_take_range", "rsigpu_split_range", "rsigpu_split_run", "rsigpu_split_p2p_bytes", "rsigpu_set_level0_mode", "rsigpu_set_feed_limit", "rsigpu_set_inflate_mode", "rsigpu_set_cand_threads", "rsigpu_debug_state", "rsigpu_pileup_commit", "rsigpu_bam_begin", "rsigpu_bam_feed", "rsigpu_bam_feed_parts", "rsigpu_bam_take",
            "rsigpu_bam_end", "rsigpu_bam_run_field", "rsigpu_pinned_alloc", "rsigpu_pinned_free")
 
 _libs: dict[str, C.CDLL] = {}
@@ -102,7 +102,7 @@ def _ptr(a):
 
 
 class BamRun(C.Structure):
-    _fields_ = [("tid", C.c_int32), ("reserved_", C.c_int32), ("n_reads", C.c_int64)]
+    _fields_ = [("tid", C.c_int32), ("part", C.c_int32), ("n_reads", C.c_int64)]
 
 
 def parse_bam_header(data) -> dict:
@@ -250,6 +250,21 @@ class Context:
         consumed = C.c_int64(0); nr = C.c_int32(0)
         self._ck(self.lib.rsigpu_bam_feed(self.h, ptr, C.c_int64(n), C.c_int64(skip), C.byref(consumed), runs, C.c_int32(4096), C.byref(nr)))
         return int(consumed.value), [(runs[i].tid, int(runs[i].n_reads)) for i in range(min(nr.value, 4096))]
+
+    def bam_feed_parts(self, parts: list):
+        """parts: [(host address, nbytes), ...] or uint8 arrays -- whole BGZF blocks each, record-aligned at both ends -- decoded as
+        ONE chunk (rsigpu_bam_feed_parts).  Returns [(tid, n_reads, part), ...]"""
+        keep = []; ptrs = (C.c_void_p * len(parts))(); sizes = (C.c_int64 * len(parts))()
+        for j, pt in enumerate(parts):
+            if isinstance(pt, tuple):
+                ptrs[j] = C.c_void_p(pt[0]); sizes[j] = int(pt[1])
+            else:
+                a = np.ascontiguousarray(pt, dtype=np.uint8); keep.append(a)
+                ptrs[j] = a.ctypes.data; sizes[j] = len(a)
+        self._keep = keep
+        runs = (BamRun * 4096)(); nr = C.c_int32(0)
+        self._ck(self.lib.rsigpu_bam_feed_parts(self.h, C.c_int32(len(parts)), ptrs, sizes, runs, C.c_int32(4096), C.byref(nr)))
+        return [(runs[i].tid, int(runs[i].n_reads), int(runs[i].part)) for i in range(min(nr.value, 4096))]
 
     def bam_take(self, run: int, dst: "Context"):
         rc = self.lib.rsigpu_bam_take(self.h, C.c_int32(run), dst.h)

@@ -151,7 +151,7 @@ struct rsigpu_ctx {
   DevBuf<u8> b_comp, b_U, b_carry, b_mapq, b_qual; DevBuf<BgzfBlock> b_blk; DevBuf<u16> b_flag, b_tabs; DevBuf<u32> b_cigoff, b_cig; DevBuf<u64> b_qoff;
   DevBuf<int> b_cnt, b_ncig, b_rbase, b_cbase, b_cnt32, b_runstart, b_tid, b_pos, b_mpos, b_isize, b_mtid;
   DevBuf<i64> b_bound, b_first, b_endp, b_tailp, b_in, b_info, b_rec, b_nq, b_qbase, b_runinfo;
-  struct BamRun { int tid; i64 r0, r1, c0, c1, q0, q1; };
+  struct BamRun { int tid, part; i64 r0, r1, c0, c1, q0, q1; };
   std::vector<BamRun> b_runs;
   int b_nref = 0, b_tail_len = 0, b_rewalked = 0; bool b_active = false, b_first_feed = true;
   size_t b_umax = (size_t)5 << 30;   // decoded bytes one feed may produce (test hook: rsigpu_set_feed_limit)
@@ -527,21 +527,34 @@ int rsigpu_bam_begin(rsigpu_ctx* c, int32_t n_ref) {
   return RSIGPU_OK;
 }
 
-int rsigpu_bam_feed(rsigpu_ctx* c, const uint8_t* bgzf, int64_t nbytes, int64_t skip, int64_t* consumed, rsigpu_bam_run* runs, int32_t cap, int32_t* n_runs) {
-  if (!c || !bgzf || nbytes < 0 || !consumed || !n_runs || skip < 0) return RSIGPU_E_ARG;
+// One feed over `nparts` byte ranges.  One range: the streaming form (a partial block at the end is left to the caller, a record
+// cut by the end is carried).  Several ranges: each is a whole number of BGZF blocks that begins at a record start and ends at
+// a record end (the records of one contig, say); they are decoded as ONE chunk -- one inflate launch over all their blocks --
+// and every range starts a new run.
+static int bam_feed_impl(rsigpu_ctx* c, int nparts, const uint8_t* const* ptrs, const int64_t* sizes, int64_t skip, int64_t* consumed, rsigpu_bam_run* runs, int32_t cap, int32_t* n_runs) {
+  if (!c || nparts < 1 || !ptrs || !sizes || !n_runs || skip < 0) return RSIGPU_E_ARG;
+  for (int j = 0; j < nparts; ++j) if (!ptrs[j] || sizes[j] < 0) return RSIGPU_E_ARG;
+  const bool multi = nparts > 1;
+  if (!multi && !consumed) return RSIGPU_E_ARG;
   if (!c->b_active) { c->fail("bam_feed: call rsigpu_bam_begin first"); return RSIGPU_E_ARG; }
   cudaSetDevice(c->device);
-  *consumed = 0; *n_runs = 0; c->b_runs.clear();
+  if (consumed) *consumed = 0;
+  *n_runs = 0; c->b_runs.clear();
+  if (multi && c->b_tail_len) { c->fail("bam_feed_parts: a record of the previous feed is still incomplete"); return RSIGPU_E_ARG; }
   // BGZF block headers (bgzf.c:258-275): gzip magic, FEXTRA, the 'B','C' subfield carries the block size
   const size_t U_MAX = c->b_umax, C_MAX = (size_t)1 << 31;
   std::vector<BgzfBlock> blk; std::vector<i64> bound;
-  size_t off = 0, utotal = 0;
+  size_t off = 0, utotal = 0;          // off: bytes of the packed compressed chunk so far (all parts)
   bound.push_back((i64)BAM_HEAD);
-  while (off + 18 <= (size_t)nbytes) {
-    const uint8_t* h = bgzf + off;
+  std::vector<size_t> part_off((size_t)nparts + 1, 0); std::vector<int> part_blk((size_t)nparts, 0);
+  for (int pj = 0; pj < nparts; ++pj) {
+  const uint8_t* bgzf = ptrs[pj]; const size_t nbytes = (size_t)sizes[pj]; const size_t base = off;
+  part_off[(size_t)pj] = base; part_blk[(size_t)pj] = (int)blk.size();
+  while (off - base + 18 <= (size_t)nbytes) {
+    const uint8_t* h = bgzf + (off - base);
     if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) { c->fail("bam_feed: not a BGZF block header"); return RSIGPU_E_ARG; }
     const size_t xlen = (size_t)h[10] | ((size_t)h[11] << 8);
-    if (off + 12 + xlen > (size_t)nbytes) break;
+    if (off - base + 12 + xlen > (size_t)nbytes) break;
     size_t bsize = 0; bool found = false;
     for (size_t x = 0; x + 4 <= xlen;) {
       const uint8_t* sf = h + 12 + x; const size_t sl = (size_t)sf[2] | ((size_t)sf[3] << 8);
@@ -549,7 +562,7 @@ int rsigpu_bam_feed(rsigpu_ctx* c, const uint8_t* bgzf, int64_t nbytes, int64_t 
       x += 4 + sl;
     }
     if (!found || bsize < 12 + xlen + 8) { c->fail("bam_feed: gzip member without a BGZF size field"); return RSIGPU_E_ARG; }
-    if (off + bsize > (size_t)nbytes) break;
+    if (off - base + bsize > (size_t)nbytes) break;
     const uint8_t* foot = h + bsize - 8;
     const size_t ulen = (size_t)foot[4] | ((size_t)foot[5] << 8) | ((size_t)foot[6] << 16) | ((size_t)foot[7] << 24);
     if (ulen > 65536) { c->fail("bam_feed: BGZF block larger than 64 KiB"); return RSIGPU_E_ARG; }
@@ -559,9 +572,12 @@ int rsigpu_bam_feed(rsigpu_ctx* c, const uint8_t* bgzf, int64_t nbytes, int64_t 
     utotal += ulen; off += bsize;
     bound.push_back((i64)(BAM_HEAD + utotal));
   }
+  if (multi && off - base != nbytes) { c->fail("bam_feed_parts: a part is not a whole number of BGZF blocks, or the parts exceed one feed's capacity"); return RSIGPU_E_RANGE; }
+  }
+  part_off[(size_t)nparts] = off;
   const int nblk = (int)blk.size();
   if (nblk == 0) {
-    if ((size_t)nbytes >= ((size_t)1 << 17)) { c->fail("bam_feed: no whole BGZF block in 128 KiB"); return RSIGPU_E_ARG; }
+    if ((size_t)sizes[0] >= ((size_t)1 << 17)) { c->fail("bam_feed: no whole BGZF block in 128 KiB"); return RSIGPU_E_ARG; }
     return RSIGPU_OK;
   }
   if (c->b_first_feed) { if ((size_t)skip > utotal) { c->fail("bam_feed: skip beyond the decoded chunk"); return RSIGPU_E_ARG; } }
@@ -570,7 +586,8 @@ int rsigpu_bam_feed(rsigpu_ctx* c, const uint8_t* bgzf, int64_t nbytes, int64_t 
   CK(c->b_first.ensure(nblk)); CK(c->b_endp.ensure(nblk)); CK(c->b_tailp.ensure(nblk)); CK(c->b_cnt.ensure(nblk)); CK(c->b_ncig.ensure(nblk)); CK(c->b_nq.ensure(nblk));
   CK(c->b_in.ensure(nblk)); CK(c->b_rbase.ensure(nblk)); CK(c->b_cbase.ensure(nblk)); CK(c->b_qbase.ensure(nblk)); CK(c->b_info.ensure(8)); CK(c->b_cnt32.ensure(4));
   TRACE(c, "feed: start");
-  CK(cudaMemcpyAsync(c->b_comp.p, bgzf, off, cudaMemcpyHostToDevice, c->stream));
+  for (int pj = 0; pj < nparts; ++pj) if (part_off[(size_t)pj + 1] > part_off[(size_t)pj])
+    CK(cudaMemcpyAsync(c->b_comp.p + part_off[(size_t)pj], ptrs[pj], part_off[(size_t)pj + 1] - part_off[(size_t)pj], cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->b_blk.p, blk.data(), (size_t)nblk * sizeof(BgzfBlock), cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->b_bound.p, bound.data(), ((size_t)nblk + 1) * 8, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemsetAsync(c->b_info.p, 0, 8 * 8, c->stream)); CK(cudaMemsetAsync(c->b_cnt32.p, 0, 4 * 4, c->stream));
@@ -610,14 +627,23 @@ int rsigpu_bam_feed(rsigpu_ctx* c, const uint8_t* bgzf, int64_t nbytes, int64_t 
     KL(k_bam_fields, (nblk + 127) / 128, 128, 0, C, H, c->b_rbase.p, c->b_cbase.p, c->b_qbase.p, info, S);
     KL(k_bam_payload, c->n_sm * 8, 256, 0, c->b_U.p, info, S);
     KL(k_bam_runs, grid_for((int)std::min<size_t>(n, 1u << 30), 1024, c->n_sm * 8), 256, 0, c->b_tid.p, info, c->b_runstart.p, (int)LIST_CAP, err);
+    std::vector<int> part_rec;           // first record of every part (each part starts a run whatever its refID)
+    if (multi) {
+      part_rec.resize((size_t)nparts);
+      for (int pj = 0; pj < nparts; ++pj) CK(cudaMemcpyAsync(&part_rec[(size_t)pj], c->b_rbase.p + part_blk[(size_t)pj], 4, cudaMemcpyDeviceToHost, c->stream));
+    }
     CK(cudaMemcpyAsync(he, err, 4 * 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     if (he[1] & BAM_ERR_RUNS) { c->fail("bam_feed: more than 65536 refID runs in one chunk (the BAM is not coordinate-sorted)"); return RSIGPU_E_RANGE; }
-    const int nr = he[0];
+    int nr = he[0];
     std::vector<int> rs((size_t)nr);
     CK(cudaMemcpyAsync(rs.data(), c->b_runstart.p, (size_t)nr * 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    if (multi) { for (int pj = 0; pj < nparts; ++pj) if (part_blk[(size_t)pj] < (pj + 1 < nparts ? part_blk[(size_t)pj + 1] : nblk) && (size_t)part_rec[(size_t)pj] < n) rs.push_back(part_rec[(size_t)pj]); }
     std::sort(rs.begin(), rs.end());
+    rs.erase(std::unique(rs.begin(), rs.end()), rs.end());
+    if (rs.size() > (size_t)LIST_CAP) { c->fail("bam_feed: more than 65536 runs in one chunk"); return RSIGPU_E_RANGE; }
+    nr = (int)rs.size();
     CK(cudaMemcpyAsync(c->b_runstart.p, rs.data(), (size_t)nr * 4, cudaMemcpyHostToDevice, c->stream));
     KL(k_bam_run_info, 1, 256, 0, c->b_runstart.p, nr, S, c->b_runinfo.p);
     std::vector<i64> ri(3 * (size_t)nr);
@@ -625,12 +651,15 @@ int rsigpu_bam_feed(rsigpu_ctx* c, const uint8_t* bgzf, int64_t nbytes, int64_t 
     CK(cudaStreamSynchronize(c->stream));
     for (int i = 0; i < nr; ++i) {
       rsigpu_ctx::BamRun R; R.tid = (int)ri[3 * (size_t)i]; R.r0 = rs[(size_t)i]; R.c0 = ri[3 * (size_t)i + 1]; R.q0 = ri[3 * (size_t)i + 2];
+      R.part = 0;
+      if (multi) { while (R.part + 1 < nparts && part_rec[(size_t)R.part + 1] <= rs[(size_t)i] && part_blk[(size_t)R.part + 1] < nblk) ++R.part; }
       R.r1 = i + 1 < nr ? rs[(size_t)i + 1] : (i64)n; R.c1 = i + 1 < nr ? ri[3 * (size_t)i + 4] : (i64)ncg; R.q1 = i + 1 < nr ? ri[3 * (size_t)i + 5] : nq64;
       c->b_runs.push_back(R);
     }
   }
   // the record cut by the end of this chunk is kept for the next feed (it goes in front of that chunk's first block)
   const i64 tail_len = (i64)(BAM_HEAD + utotal) - tail_start;
+  if (multi && tail_len > 0) { c->fail("bam_feed_parts: the last part ends inside a record"); return RSIGPU_E_ARG; }
   if (tail_len > 0) {
     if (tail_start < (i64)BAM_HEAD || tail_len > (i64)BAM_HEAD) { c->fail("bam_feed: an alignment record longer than the decoder's carry buffer (16 MiB)"); return RSIGPU_E_RANGE; }
     CK(c->b_carry.ensure((size_t)BAM_HEAD));
@@ -639,10 +668,21 @@ int rsigpu_bam_feed(rsigpu_ctx* c, const uint8_t* bgzf, int64_t nbytes, int64_t 
   }
   c->b_tail_len = tail_len > 0 ? (int)tail_len : 0;
   TRACE(c, "feed: end");
-  *consumed = (int64_t)off;
+  if (consumed) *consumed = (int64_t)off;
   *n_runs = (int32_t)c->b_runs.size();
-  for (int i = 0; i < (int)c->b_runs.size() && i < cap && runs; ++i) { runs[i].tid = c->b_runs[(size_t)i].tid; runs[i].reserved_ = 0; runs[i].n_reads = c->b_runs[(size_t)i].r1 - c->b_runs[(size_t)i].r0; }
+  for (int i = 0; i < (int)c->b_runs.size() && i < cap && runs; ++i) { runs[i].tid = c->b_runs[(size_t)i].tid; runs[i].part = c->b_runs[(size_t)i].part; runs[i].n_reads = c->b_runs[(size_t)i].r1 - c->b_runs[(size_t)i].r0; }
   return RSIGPU_OK;
+}
+
+int rsigpu_bam_feed(rsigpu_ctx* c, const uint8_t* bgzf, int64_t nbytes, int64_t skip, int64_t* consumed, rsigpu_bam_run* runs, int32_t cap, int32_t* n_runs) {
+  if (!bgzf || !consumed) return RSIGPU_E_ARG;
+  const uint8_t* p[1] = {bgzf}; const int64_t n[1] = {nbytes};
+  return bam_feed_impl(c, 1, p, n, skip, consumed, runs, cap, n_runs);
+}
+int rsigpu_bam_feed_parts(rsigpu_ctx* c, int32_t n_parts, const uint8_t* const* parts, const int64_t* nbytes, rsigpu_bam_run* runs, int32_t cap, int32_t* n_runs) {
+  if (n_parts < 1) return RSIGPU_E_ARG;
+  if (n_parts == 1) { int64_t consumed = 0; const int rc = bam_feed_impl(c, 1, parts, nbytes, 0, &consumed, runs, cap, n_runs); if (rc == RSIGPU_OK && consumed != nbytes[0]) { c->fail("bam_feed_parts: a part is not a whole number of BGZF blocks"); return RSIGPU_E_RANGE; } return rc; }
+  return bam_feed_impl(c, n_parts, parts, nbytes, 0, nullptr, runs, cap, n_runs);
 }
 
 int rsigpu_bam_take(rsigpu_ctx* c, int32_t run, rsigpu_ctx* dst) {

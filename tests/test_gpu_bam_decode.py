@@ -52,3 +52,7 @@ def test_large_file_all_fields(gpu_lib, tmp_path):
     got, h = T.decode_file(gpu_lib, path, 32 << 20)
     assert sorted(got) == [0]
     T.assert_same_reads(got[0], reads)
+
+
+def test_feed_parts_equals_separate_feeds(gpu_lib, tmp_path):
+    T.test_feed_parts_equals_separate_feeds(gpu_lib, tmp_path)

@@ -327,3 +327,34 @@ def test_separate_decoder_and_two_destinations(sim_lib, tmp_path):
         assert np.array_equal(c.array(api.ARR_RAW_DEPTH), w)
         c.close()
     dec.close()
+
+
+def test_feed_parts_equals_separate_feeds(sim_lib, tmp_path):
+    """rsigpu_bam_feed_parts: the record blocks of three files (same refID 0 in each: only the part boundary separates them) decoded
+    as ONE chunk give, per part, exactly what each file gives alone; a part that ends inside a record is refused"""
+    files = []
+    for k, (L, seed) in enumerate(((70000, 41), (30000, 42), (50000, 43))):
+        fa, reads = make_reads(L, seed, cov=5)
+        path = str(tmp_path / f"p{k}.bam")
+        ix = synth.write_bam_aligned(path, "19", L, reads, level=1, random_seq=3, threads=1)
+        data = np.fromfile(path, np.uint8)
+        files.append((data[int(ix["rec_off"]):int(ix["blk_end"][-1])], reads))
+    ctx = api.Context(lib=sim_lib)
+    ctx.bam_begin(1)
+    runs = ctx.bam_feed_parts([f[0] for f in files])
+    assert [(t, p) for t, n, p in runs] == [(0, 0), (0, 1), (0, 2)]
+    for i, (tid, n, part) in enumerate(runs):
+        assert n == len(files[part][1]["pos"])
+        assert_same_reads(ctx.bam_run_reads(i), files[part][1])
+    ctx.bam_end()
+    # one part alone goes through the same entry point
+    ctx.bam_begin(1)
+    runs = ctx.bam_feed_parts([files[1][0]])
+    assert len(runs) == 1 and runs[0][1] == len(files[1][1]["pos"])
+    ctx.bam_end()
+    # a part cut in the middle of a BGZF block, and parts whose last record is incomplete
+    ctx.bam_begin(1)
+    with pytest.raises(api.RsiGpuError):
+        ctx.bam_feed_parts([files[0][0][:-7], files[1][0]])
+    ctx.bam_end()
+    ctx.close()
