@@ -271,7 +271,7 @@ def main():
     ap.add_argument("--profile-steps", type=int, default=2)
     ap.add_argument("--inflight", "--contigs-per-step", type=int, default=4, dest="inflight",
                     help="contigs in flight per GPU (one context + stream + host thread each, as the CLI runs them)")
-    ap.add_argument("--e2e-batch-mb", type=int, default=1800, help="e2e leg: compressed MiB of BAM one decoder feed takes (the contigs of a batch are inflated by one launch; "
+    ap.add_argument("--e2e-batch-mb", type=int, default=1000, help="e2e leg: compressed MiB of BAM one decoder feed takes (the contigs of a batch are inflated by one launch; "
                                                                       "a feed holds at most 2 GiB compressed and, here, 10 GiB decoded)")
     ap.add_argument("--no-cli", action="store_true", help="skip the CLI / one-core reference comparison at the end (N=1)")
     a = ap.parse_args()

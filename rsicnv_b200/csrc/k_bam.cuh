@@ -604,13 +604,22 @@ __global__ void k_bam_fields(BamChunk C, BamChain H, const int* __restrict__ rba
   int r = n ? rbase[k] : 0; u32 co = n ? (u32)cbase[k] : 0u; u64 qo = n ? (u64)qbase[k] : 0ull;
   for (int i = 0; __any_sync(0xffffffffu, i < n); ++i) {      // warp-uniform trip count: the lanes walk 32 different blocks in step
     if (i < n) {
-      const u8* q = C.U + p;
-      const u32 bs = ld32u(q), bmq = ld32u(q + 12), fnc = ld32u(q + 16);
-      S.rec[r] = p; S.tid[r] = (int)ld32u(q + 4); S.pos[r] = (int)ld32u(q + 8);
+      // the 36 bytes of block_size + core as ten ALIGNED words and funnel shifts (records start at any byte; the lanes of a warp
+      // read 32 different blocks, so every load instruction is 32 transactions: 10 instead of 36 byte loads)
+      const u32* wq = reinterpret_cast<const u32*>(C.U + (p & ~3ll));
+      const u32 sh = (u32)(p & 3ll) * 8u;
+      u32 w[10];
+#pragma unroll
+      for (int k = 0; k < 10; ++k) w[k] = wq[k];
+      u32 f[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) f[k] = __funnelshift_r(w[k], w[k + 1], sh);     // f[k] = the little-endian word at p + 4k
+      const u32 bs = f[0], bmq = f[3], fnc = f[4];
+      S.rec[r] = p; S.tid[r] = (int)f[1]; S.pos[r] = (int)f[2];
       S.mapq[r] = (u8)((bmq >> 8) & 0xffu); S.flag[r] = (u16)(fnc >> 16);
-      S.mtid[r] = (int)ld32u(q + 24); S.mpos[r] = (int)ld32u(q + 28); S.isize[r] = (int)ld32u(q + 32);
+      S.mtid[r] = (int)f[6]; S.mpos[r] = (int)f[7]; S.isize[r] = (int)f[8];
       S.cigar_off[r] = co; S.qual_off[r] = qo;
-      co += fnc & 0xffffu; qo += (u64)ld32u(q + 20);
+      co += fnc & 0xffffu; qo += (u64)f[5];
       p += 4 + (i64)bs; ++r;
     }
   }

@@ -369,6 +369,7 @@ template <class T> inline T atomicExch(T* p, T v) { T o = *p; *p = v; return o; 
 template <class T> inline T atomicCAS(T* p, T c, T v) { T o = *p; if (o == c) *p = v; return o; }
 
 // ---- intrinsics
+inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) { sh &= 31u; return sh ? (lo >> sh) | (hi << (32u - sh)) : lo; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }
