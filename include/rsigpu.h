@@ -167,7 +167,9 @@ void rsigpu_pinned_free(void* p);
  * context's stream except where a result is copied to the host. */
 int rsigpu_load_finish(rsigpu_ctx* c);   /* checkgccontent + apply_cap + concatenate_data + RDmedian/RDsd: gccontent.cpp:95, loaddata.cpp:229, 48, rsi.cpp:2202 */
 int rsigpu_detectcnv(rsigpu_ctx* c);     /* detectcnv, rsi.cpp:1795-1945 */
-int rsigpu_sd_filters(rsigpu_ctx* c);    /* sd_filters, rsi.cpp:1753-1792 */
+int rsigpu_sd_filters(rsigpu_ctx* c);    /* sd_filters, rsi.cpp:1753-1792.  The filter itself runs on the device at the end of detectcnv's last
+                                            kernel (k_cand_c: sd_filter_list); this entry point only marks the filtered list as the one
+                                            rsigpu_cnv_stat / rsigpu_get_calls use, so that the seams stay the reference's */
 int rsigpu_cnv_stat(rsigpu_ctx* c);      /* cnv_stat + bam_rd_pr_stats, pairrd.cpp:622-748, 112-260 (BAM input only) */
 int rsigpu_get_calls(rsigpu_ctx* c, rsigpu_cnv* out, int32_t cap, int32_t* n);  /* rows write_cnv_to_file would print */
 

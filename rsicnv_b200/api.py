@@ -237,6 +237,13 @@ class Context:
     def bam_begin(self, n_ref: int):
         self._ck(self.lib.rsigpu_bam_begin(self.h, C.c_int32(n_ref)))
 
+    RUN_CAP = 65536      # the decoder's own limit of refID runs per feed: nothing is ever truncated
+
+    def _run_buf(self):
+        if getattr(self, "_runs", None) is None:
+            self._runs = (BamRun * self.RUN_CAP)()
+        return self._runs
+
     def bam_feed(self, data, nbytes: int | None = None, skip: int = 0):
         """data: uint8 numpy array (or an integer host address with nbytes) that starts at a BGZF block boundary.
         Returns (bytes consumed, [(tid, n_reads), ...]) -- the runs stay valid until the next feed."""
@@ -246,10 +253,10 @@ class Context:
             data = np.ascontiguousarray(data, dtype=np.uint8)
             self._keep = [data]
             ptr, n = _ptr(data), (len(data) if nbytes is None else int(nbytes))
-        runs = (BamRun * 4096)()
+        runs = self._run_buf()
         consumed = C.c_int64(0); nr = C.c_int32(0)
-        self._ck(self.lib.rsigpu_bam_feed(self.h, ptr, C.c_int64(n), C.c_int64(skip), C.byref(consumed), runs, C.c_int32(4096), C.byref(nr)))
-        return int(consumed.value), [(runs[i].tid, int(runs[i].n_reads)) for i in range(min(nr.value, 4096))]
+        self._ck(self.lib.rsigpu_bam_feed(self.h, ptr, C.c_int64(n), C.c_int64(skip), C.byref(consumed), runs, C.c_int32(self.RUN_CAP), C.byref(nr)))
+        return int(consumed.value), [(runs[i].tid, int(runs[i].n_reads)) for i in range(nr.value)]
 
     def bam_feed_parts(self, parts: list):
         """parts: [(host address, nbytes), ...] or uint8 arrays -- whole BGZF blocks each, record-aligned at both ends -- decoded as
@@ -262,9 +269,9 @@ class Context:
                 a = np.ascontiguousarray(pt, dtype=np.uint8); keep.append(a)
                 ptrs[j] = a.ctypes.data; sizes[j] = len(a)
         self._keep = keep
-        runs = (BamRun * 4096)(); nr = C.c_int32(0)
-        self._ck(self.lib.rsigpu_bam_feed_parts(self.h, C.c_int32(len(parts)), ptrs, sizes, runs, C.c_int32(4096), C.byref(nr)))
-        return [(runs[i].tid, int(runs[i].n_reads), int(runs[i].part)) for i in range(min(nr.value, 4096))]
+        runs = self._run_buf(); nr = C.c_int32(0)
+        self._ck(self.lib.rsigpu_bam_feed_parts(self.h, C.c_int32(len(parts)), ptrs, sizes, runs, C.c_int32(self.RUN_CAP), C.byref(nr)))
+        return [(runs[i].tid, int(runs[i].n_reads), int(runs[i].part)) for i in range(nr.value)]
 
     def bam_take(self, run: int, dst: "Context"):
         rc = self.lib.rsigpu_bam_take(self.h, C.c_int32(run), dst.h)

@@ -7,12 +7,15 @@
 //   bam_read1 / bam1_core_t  samtools-0.1.18/bam.c:179-210, bam.h:131-155 (32-byte core, name, CIGAR, 4-bit seq, qual)
 //   the per-record fields load_data_from_bam and cnv_stat read  loaddata.cpp:312-335, pairrd.cpp:622-748
 //
-// Design.  A BGZF block (<= 64 KiB decoded) is an independent raw-deflate stream, and a chr19-sized BAM
-// holds ~65 k of them: one THREAD inflates one block.  Its Huffman decode has three levels: a 6-bit direct
-// table in shared memory (the frequent literal/length codes), 9/6-bit direct tables in global memory
-// (per thread, warp-interleaved, L1/L2 resident) and the canonical count/symbol walk for longer codes.
-// The 32 lanes of a warp (32 different streams) are kept converged -- one symbol per lane per step, table
-// construction as a separate phase -- and the LZ77 matches of all lanes are copied by the whole warp.
+// Design.  A BGZF block (<= 64 KiB decoded) is an independent raw-deflate stream, and a chr19-sized BAM holds ~36 k of
+// them.  Two inflate kernels, picked per feed by the number of blocks (rsigpu.cu): here one THREAD inflates one block --
+// 32 unrelated streams per warp in lock-step, latency-bound, a launch costs 30-38 ms for anything up to a chr19-sized
+// chunk and ~58 ms for an 80 k-block one -- and k_inflate_warp.cuh gives a block to a whole warp (time proportional to
+// the bytes; better below ~28 k blocks).  This kernel's Huffman decode has three levels: a 6-bit direct table in shared
+// memory (the frequent literal/length codes), 9/6-bit direct tables in global memory (per thread, warp-interleaved,
+// L1/L2 resident) and the canonical count/symbol walk for longer codes.  The 32 lanes of a warp are kept converged -- a few
+// symbols per lane per step, table construction as a separate phase -- and the LZ77 matches of all lanes are copied by
+// the whole warp.
 // BAM records are a linked list (each starts with its own length) and may straddle BGZF blocks, so their
 // starts are found speculatively and then proven: every block guesses its first record start with a
 // plausibility test and walks the list to the end of the block (k_bam_chain); one CTA checks that each
