@@ -127,8 +127,12 @@ __device__ __forceinline__ bool w_interior(int w0, int L) { return w0 >= GC_WIN 
 // Pass A: mean of the positive depths and the per-stratum depth sums / counts (5 B/base read; checkgccontent's table,
 // gccontent.cpp:95-150).  Every warp has a PRIVATE table wtab[A_ROWS + 1][32 lanes] of packed (count << 40 | sum) words: lane
 // l only ever touches column l, so the per-base update is a plain conflict-free 8-byte read-modify-write -- no atomics, no
-// warp votes.  Rows cover the strata [gc_base, gc_base + A_ROWS) around the contig's mean GC count; a base outside goes to
-// the spare row (never read) and is redone afterwards through a block table with shared-memory atomics.  The update is
+// warp votes.  Rows cover A_ROWS = 64 of the 202 strata, and the window FOLLOWS the data: a warp works through a contiguous
+// range of warp-tiles (the GC level of a genome changes over tens of kilobases, far slower than a tile), checks the mean
+// window count of every tile and, when it has drifted out of the middle half of the rows, adds its table into the block
+// table and re-centres (a few hundred instructions against ~7 k per tile).  A base outside the rows goes to the spare row
+// (never read) and is redone through the block table with shared-memory atomics -- rare now; with ONE window per contig,
+// centred on the contig's mean, 40 % of the kernel's stall samples sat on those atomics (profiles/r2_streaming_gc_table_lines.txt).  The update is
 // branch-free and software-pipelined: the next base's word is loaded BEFORE the current one is stored, and forwarded in
 // registers when both are the same row (every second base), so a lane's chain of updates never waits for shared memory.
 // A lane adds < 2^16 bases of depth < 2^24 to one word.
@@ -136,11 +140,25 @@ __device__ __forceinline__ bool w_interior(int w0, int L) { return w0 >= GC_WIN 
 #define RSI_A_WARP_BYTES ((size_t)2 * W_STAGE + W_BITS + (size_t)(A_ROWS + 1) * 256)
 #define RSI_SMEM_A ((size_t)A_NW * RSI_A_WARP_BYTES + (size_t)GC_STRATA * 12 + 16)
 // wt0 .. wt1: the warp-tiles this launch covers (the whole contig, or one part of a contig split over several GPUs)
+// the warp's private table [A_ROWS + 1][32 lanes] added into the block table at strata gbase .. gbase + A_ROWS - 1 and cleared
+// (row A_ROWS only parks the bases whose stratum lies outside: they are counted on the overflow path)
+__device__ __forceinline__ void a_flush_rows(u64* wtab, int lane, int gbase, u64* osum, u32* ocnt) {
+  __syncwarp();
+  for (int row = lane; row < A_ROWS; row += 32) {
+    u64 sum = 0, cnt = 0;
+    for (int l = 0; l < 32; ++l) { u64* e = &wtab[(size_t)row * 32 + ((l + lane) & 31)]; sum += *e & ((1ull << 40) - 1); cnt += *e >> 40; *e = 0ull; }
+    const int g = gbase + row;
+    if (cnt && g < GC_STRATA) { atomicAdd(&osum[g], sum); atomicAdd(&ocnt[g], (u32)cnt); }
+  }
+  __syncwarp();
+}
+
 __global__ void __launch_bounds__(A_NT) k_gc_table(const int* __restrict__ rd, const u8* __restrict__ fa, DevState* st, int wt0, int wt1) {
   RSI_DYN_SMEM(smem);
   RSI_CTA_SETUP(c);
   __shared__ __align__(8) u64 s_bar[A_NW * 2];
-  const int L = st->L, do_gc = st->gc_on, gbase = st->gc_base;
+  const int L = st->L, do_gc = st->gc_on;
+  int gbase = st->gc_base;             // first stratum of THIS warp's private table: re-centred when the local GC level drifts away
   const int tid = c.tid, lane = tid & 31, warp = tid >> 5;
   unsigned char* wsm = smem + (size_t)warp * RSI_A_WARP_BYTES;
   u32* gcb = reinterpret_cast<u32*>(wsm + 2 * W_STAGE);
@@ -156,14 +174,17 @@ __global__ void __launch_bounds__(A_NT) k_gc_table(const int* __restrict__ rd, c
   c.sync();
   u64* col = wtab + lane;
   const int nwt = imin((L + W_T - 1) / W_T, wt1);
-  const int gw = wt0 + (int)blockIdx.x * A_NW + warp, GW = (int)gridDim.x * A_NW;
+  // every warp takes a CONTIGUOUS range of warp-tiles (~50 kb of a chr19-sized contig): the GC level of neighbouring
+  // tiles is similar, so the 64 rows of the private table can follow it
+  const int GW = (int)gridDim.x * A_NW, per = (imax(nwt - wt0, 0) + GW - 1) / GW;
+  const int gw = wt0 + ((int)blockIdx.x * A_NW + warp) * per, gw_end = imin(gw + per, nwt);
   if (lane == 0)
-    for (int s = 0; s < 2; ++s) { const int t = gw + s * GW; if (t < nwt) w_issue(wsm + s * W_STAGE, &bar[s], t, rd, fa, do_gc); }
+    for (int s = 0; s < 2; ++s) { const int t = gw + s; if (t < gw_end) w_issue(wsm + s * W_STAGE, &bar[s], t, rd, fa, do_gc); }
   u64 psum = 0, pcnt = 0;
   u64 zsum = 0; u32 zcnt = 0;          // stratum 0 (windows without any G/C: the N stretches) is kept in registers
   int vmin = 0x7fffffff, vmax = -0x7fffffff - 1;
   int it = 0;
-  for (int wt = gw; wt < nwt; wt += GW, ++it) {
+  for (int wt = gw; wt < gw_end; ++wt, ++it) {
     const int s = it & 1;
     unsigned char* stage = wsm + s * W_STAGE;
     mbar_wait(&bar[s], (u32)(it >> 1) & 1u);
@@ -188,7 +209,18 @@ __global__ void __launch_bounds__(A_NT) k_gc_table(const int* __restrict__ rd, c
       vmin = imin(vmin, orx < 0 ? -1 : 0); vmax = imax(vmax, orx < 0 ? 0x7fffffff : orx);
       if (do_gc) {
         const int q = lane * W_CH;               // p - w0; bit index of base p is q + W_FL
-        const int g0 = w_gc_count(gcb, q + W_FL - GC_WIN / 2) - gbase;
+        const int gabs = w_gc_count(gcb, q + W_FL - GC_WIN / 2);
+        {   // keep the table centred on the tile's GC level (mean of the 32 chunk-start windows)
+          int gm = gabs;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) gm += __shfl_xor_sync(0xffffffffu, gm, o);
+          gm >>= 5;
+          if (gm != 0 && (gm < gbase + A_ROWS / 4 || gm >= gbase + 3 * A_ROWS / 4)) {
+            const int nb = imax(0, imin(gm - A_ROWS / 2, (int)GC_STRATA - A_ROWS));
+            if (nb != gbase) { a_flush_rows(wtab, lane, gbase, osum, ocnt); gbase = nb; }
+          }
+        }
+        const int g0 = gabs - gbase;
         const u32 inw = w_bits32(gcb, q + W_FL + GC_WIN / 2 + 1), outw = w_bits32(gcb, q + W_FL - GC_WIN / 2);
         const u32 plus = inw & ~outw, minus = outw & ~inw;      // the window count moves by bit(p+101) - bit(p-100) per base
         u32 ovf = 0;
@@ -262,24 +294,14 @@ __global__ void __launch_bounds__(A_NT) k_gc_table(const int* __restrict__ rd, c
     }
     psum += tsum; pcnt += tcnt;
     __syncwarp();                                  // every lane is done with stage s and with the bit string
-    const int t2 = wt + 2 * GW;
-    if (lane == 0 && t2 < nwt) w_issue(stage, &bar[s], t2, rd, fa, do_gc);
+    const int t2 = wt + 2;
+    if (lane == 0 && t2 < gw_end) w_issue(stage, &bar[s], t2, rd, fa, do_gc);
   }
+  if (do_gc) a_flush_rows(wtab, lane, gbase, osum, ocnt);
   c.sync();
   if (do_gc) {
     zsum = c.reduce(zsum, SumOp()); zcnt = c.reduce(zcnt, SumOp());
     if (tid == 0 && zcnt) { atomicAdd(&osum[0], zsum); atomicAdd(&ocnt[0], zcnt); }
-    // column sums of the private tables: thread (row, part) adds A_NW / 4 warps x 32 lanes of its row into the block table
-    {
-      const int row = tid & (A_ROWS - 1), part = tid / A_ROWS;          // A_NT / A_ROWS = 4 parts
-      u64 sum = 0, cnt = 0;
-      for (int w = part * (A_NW / 4); w < (part + 1) * (A_NW / 4); ++w) {
-        const u64* t = reinterpret_cast<const u64*>(smem + (size_t)w * RSI_A_WARP_BYTES + 2 * W_STAGE + W_BITS);
-        for (int l = 0; l < 32; ++l) { const u64 e = t[(size_t)row * 32 + ((l + tid) & 31)]; sum += e & ((1ull << 40) - 1); cnt += e >> 40; }
-      }
-      const int g = gbase + row;
-      if (cnt && g < GC_STRATA) { atomicAdd(&osum[g], sum); atomicAdd(&ocnt[g], (u32)cnt); }
-    }
     c.sync();
     for (int g = tid; g < GC_STRATA; g += A_NT)
       if (ocnt[g]) { atomicAdd(&st->gc_sum[g], osum[g]); atomicAdd(&st->gc_cnt[g], (u64)ocnt[g]); }
@@ -327,7 +349,19 @@ __global__ void k_gc_finalize(const u8* __restrict__ fa, DevState* st) {
 // touches its own chunk) and the warp then writes its tile out with coalesced stores, 16 bytes per lane where the
 // destination allows.  The value histogram uses one private column per lane again: vh[B_K][32] u16 per warp (a lane adds
 // < 2^16 bases to one counter), updated branch-free; values outside the window are redone after the chunk.
-// Dynamic shared memory per warp: 2 stages | bit string | vh;  per block: tab[GC_STRATA][16] f64 | N intervals (beg, end, cum)
+// int(RD * mean / tab + 0.5) exactly as the reference rounds it (gccontent.cpp:80: every operation a correctly rounded double
+// operation, no FMA), without paying for a double division per base: the quotient is first taken as a product with the
+// table's reciprocal -- within a few ulp of the true quotient -- and the division itself is only done when that estimate
+// lands so close to an integer boundary that the few ulp could matter (or is not finite).
+__device__ __forceinline__ int gc_adjusted(int x, double mean, double2 te) {
+  const double a = __dmul_rn((double)x, mean);
+  const double r = __dadd_rn(__dmul_rn(a, te.y), 0.5);
+  const int n = (int)r;
+  const double f = r - (double)n, d = r * 1e-12;
+  if (f > d && f < 1.0 - d) return n;
+  return (int)(__dadd_rn(__ddiv_rn(a, te.x), 0.5));
+}
+// Dynamic shared memory per warp: 2 stages | bit string | vh;  per block: tab[GC_STRATA][8] (f64 value, f64 reciprocal) | N intervals (beg, end, cum)
 #define RSI_B_WARP_BYTES ((size_t)2 * W_STAGE + W_BITS + (size_t)(B_K + 1) * 64)
 #define RSI_SMEM_B ((size_t)B_NW * RSI_B_WARP_BYTES + (size_t)GC_STRATA * 16 * 8 + (size_t)B_NCACHE * 12 + 16)
 __global__ void __launch_bounds__(B_NT) k_gc_adjust(const int* __restrict__ rd, const u8* __restrict__ fa, int* __restrict__ rdc,
@@ -345,14 +379,15 @@ __global__ void __launch_bounds__(B_NT) k_gc_adjust(const int* __restrict__ rd, 
   int* nc = reinterpret_cast<int*>(tab + GC_STRATA * 16);               // beg[B_NCACHE] | end[B_NCACHE] | cum[B_NCACHE]
   u64* bar = s_bar + warp * 2;
   for (int k = lane; k < B_K * 16; k += 32) reinterpret_cast<u32*>(vh)[k] = 0u;
-  if (do_gc) for (int k = tid; k < GC_STRATA * 16; k += B_NT) tab[k] = st->gc_tab[k >> 4];   // 16 copies: the lanes of a half-warp read 16 different bank pairs
+  // (table value, its reciprocal) per stratum, 8 copies: the lanes of a quarter-warp read 8 different bank quads
+  if (do_gc) for (int k = tid; k < GC_STRATA * 8; k += B_NT) { const double t = st->gc_tab[k >> 3]; tab[2 * k] = t; tab[2 * k + 1] = 1.0 / t; }
   const bool ncached = nn <= B_NCACHE;
   if (ncached) for (int k = tid; k < nn; k += B_NT) { nc[k] = nbeg[k]; nc[B_NCACHE + k] = nend[k]; nc[2 * B_NCACHE + k] = ncum[k]; }
   const int* nb_ = ncached ? nc : nbeg; const int* ne_ = ncached ? nc + B_NCACHE : nend; const int* nm_ = ncached ? nc + 2 * B_NCACHE : ncum;
   if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
   c.sync();
   u16* vcol = vh + lane;
-  const double* tcol = tab + (lane & 15);
+  const double2* tcol = reinterpret_cast<const double2*>(tab) + (lane & 7);
   const double mean = st->rdmean;
   const int hb = st->hist_base, s20 = st->s20, r20 = st->r20, gstar = st->gstar;
   const int q0 = s20 + r20 - GC_WIN;   // first overwritten position of the pseudo-slice (r20 >= 2)
@@ -398,7 +433,7 @@ __global__ void __launch_bounds__(B_NT) k_gc_adjust(const int* __restrict__ rd, 
         for (int j = 0; j < W_CH; ++j) {
           const u32 mk = (1u << j) - 1u;
           const int g = g0 + __popc(plus & mk) - __popc(minus & mk);
-          xs[j] = (int)(__dadd_rn(__ddiv_rn(__dmul_rn((double)xs[j], mean), tcol[g * 16]), 0.5));
+          xs[j] = gc_adjusted(xs[j], mean, tcol[g * 8]);
         }
 #pragma unroll
         for (int j4 = 0; j4 < W_CH / 4; ++j4) *reinterpret_cast<int4*>(x4 + j4 * 4) = make_int4(xs[j4 * 4], xs[j4 * 4 + 1], xs[j4 * 4 + 2], xs[j4 * 4 + 3]);
@@ -439,7 +474,7 @@ __global__ void __launch_bounds__(B_NT) k_gc_adjust(const int* __restrict__ rd, 
           int g;
           if (r20 >= 2 && p >= q0 && p < q0 + r20) { x = rd[p + GC_WIN - r20]; g = gstar; }
           else g = w_gc_count(gcb, gc_lo(p, L) - w0 + W_FL);
-          x = (int)(__dadd_rn(__ddiv_rn(__dmul_rn((double)x, mean), tcol[g * 16]), 0.5));
+          x = gc_adjusted(x, mean, tcol[g * 8]);
           x4[j] = x;
         }
         count_slow(x);

@@ -39,6 +39,7 @@ struct dim3 {
 };
 struct int4 { int x, y, z, w; };
 struct uint4 { unsigned x, y, z, w; };
+struct double2 { double x, y; };
 struct int2 { int x, y; };
 struct uint2 { unsigned x, y; };
 struct float4 { float x, y, z, w; };
