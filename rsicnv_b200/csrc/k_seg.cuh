@@ -84,17 +84,42 @@ __global__ void __launch_bounds__(1024) k_run_argmax(const float* __restrict__ t
       carry += tot;
     }
     c.sync();
+    // For one length L the score is a monotone function of |sum/L - tmedian| (every rounding step is monotone), so its
+    // maximum over the starts is reached at the largest or at the smallest window sum: a thread owns a length and keeps the
+    // two extreme sums (integer compares, no double division per window), scores them, and only the winning length is
+    // then searched for the FIRST start that reaches the maximum (the reference's order: L ascending, start ascending).
+    // Lengths are dealt in mirror pairs (1 + u, n - u): n + 1 windows per pair, and the lanes of a warp have almost equal
+    // trip counts; lane u reads P[j + 1 + u]: consecutive addresses.
     SegBest best; best.v = 0.0; best.key = ~0ull;
-    for (int L = 1; L <= n; ++L) {
-      const double dL = (double)L, sL = sqrt(dL);
-      for (int j = c.tid; j + L <= n; j += c.nthr) {
-        const double sum = (double)(P[j + L] - P[j]) * (1.0 / 68719476736.0);
-        const double sc = __dmul_rn(fabs(__ddiv_rn(sum, dL) - tmed), sL);
-        const u64 key = ((u64)L << 32) | (u64)j;
-        if (sc > best.v || (sc == best.v && key < best.key)) { best.v = sc; best.key = key; }
+    const int half = (n + 1) / 2;
+    for (int u = c.tid; u < half; u += c.nthr) {
+#pragma unroll 1
+      for (int side = 0; side < 2; ++side) {
+        const int L = side == 0 ? 1 + u : n - u;
+        if (side == 1 && L == 1 + u) break;           // the middle length of an odd n: once
+        i64 mx = -0x7fffffffffffffffll - 1, mn = 0x7fffffffffffffffll;
+        const i64* PL = P + L;
+        for (int j = 0; j + L <= n; ++j) { const i64 sj = PL[j] - P[j]; mx = sj > mx ? sj : mx; mn = sj < mn ? sj : mn; }
+        const double dL = (double)L, sL = sqrt(dL);
+        const double s_hi = __dmul_rn(fabs(__ddiv_rn((double)mx * (1.0 / 68719476736.0), dL) - tmed), sL);
+        const double s_lo = __dmul_rn(fabs(__ddiv_rn((double)mn * (1.0 / 68719476736.0), dL) - tmed), sL);
+        const double sc = s_hi > s_lo ? s_hi : s_lo;
+        if (sc > best.v || (sc == best.v && (u64)L < best.key)) { best.v = sc; best.key = (u64)L; }
       }
     }
     best = c.reduce(best, SegBestOp());
+    if (best.v > 0.0 && best.key != ~0ull) {          // first start of the winning length with that score
+      const int L = (int)best.key;
+      const double dL = (double)L, sL = sqrt(dL);
+      int jf = 0x7fffffff;
+      for (int j = c.tid; j + L <= n; j += c.nthr) {
+        const double sum = (double)(P[j + L] - P[j]) * (1.0 / 68719476736.0);
+        const double sc = __dmul_rn(fabs(__ddiv_rn(sum, dL) - tmed), sL);
+        if (sc == best.v) { jf = j; break; }
+      }
+      jf = c.reduce(jf, MinOp());
+      best.key = ((u64)L << 32) | (u64)(unsigned)jf;
+    }
     if (c.tid == 0) {
       int ns = a, ne = b;
       if (best.v > 0.0 && best.key != ~0ull) { const int L = (int)(best.key >> 32), j = (int)(best.key & 0xffffffffu); ns = a + j; ne = a + j + L - 1; }
