@@ -119,7 +119,7 @@ RSI_DEVN void cta_hist_stat(const Cta& c, const CandScratch& S, const T* x, int 
     }
     for (; i < n; i += c.nthr) { double v = (double)x[i]; mn = v < mn ? v : mn; mx = v > mx ? v : mx; sm += v; }
   }
-  mn = c.reduce(mn, MinOp()); mx = c.reduce(mx, MaxOp()); sm = c.reduce(sm, SumOp());
+  mn = c.reduce_ol(mn, MinOp()); mx = c.reduce_ol(mx, MaxOp()); sm = c.reduce_ol(sm, SumOp());
   q[0] = mn; q[1] = sm / (double)n; q[2] = mx;
   if ((mx - mn) < dy) return;
   const size_t np = (size_t)((mx - mn) / dy + 2);
@@ -156,7 +156,7 @@ RSI_DEVN void cta_hist_stat(const Cta& c, const CandScratch& S, const T* x, int 
   long long local = 0;
   for (size_t b = b0; b < b1; ++b) local += H[b];
   long long tot;
-  long long run = c.scan_excl(local, &tot);
+  long long run = c.scan_excl_ol(local, &tot);
   if (c.tid == 0) { c.bc[8] = q[0]; c.bc[9] = q[1]; c.bc[10] = q[2]; }
   c.sync();
   for (size_t b = b0; b < b1; ++b) {
@@ -248,7 +248,7 @@ RSI_DEVN int cta_find_first(const Cta& c, const int* RD, int lo, int hi, int dir
       const int j = base + k * c.nthr + c.tid;
       if (j < len && j < best && nb_accept(RD[dir > 0 ? lo + j : hi - j], flag, up, lw)) best = j;
     }
-    best = c.reduce(best, MinOp());
+    best = c.reduce_ol(best, MinOp());
     if (best != 0x7fffffff) return dir > 0 ? lo + best : hi - best;
   }
   return -1;
@@ -326,7 +326,7 @@ RSI_DEVN void cnv_test_stats(const Cta& c, const CandCfg& P, const CandScratch& 
     }
   }
   c.sync();
-  s1 = c.reduce(s1, SumOp()); s2 = c.reduce(s2, SumOp());
+  s1 = c.reduce_ol(s1, SumOp()); s2 = c.reduce_ol(s2, SumOp());
   cand_tick(c, S, 5, &t0);
   double rq[3], cq[3];
   cta_hist_stat(c, S, S.rm, nr, 0.01, rq);
@@ -336,7 +336,7 @@ RSI_DEVN void cnv_test_stats(const Cta& c, const CandCfg& P, const CandScratch& 
   long long a1 = 0, a2 = 0;
 #pragma unroll 4
   for (int i = c.tid; i < ncnv; i += c.nthr) { long long v = cnv[i]; a1 += v; a2 += v * v; }
-  a1 = c.reduce(a1, SumOp()); a2 = c.reduce(a2, SumOp());
+  a1 = c.reduce_ol(a1, SumOp()); a2 = c.reduce_ol(a2, SumOp());
   cand_tick(c, S, 8, &t0);
   if (c.tid == 0) {
     double rmean = s1 / double(nr);
@@ -496,7 +496,7 @@ RSI_DEVN void edge_refine(const Cta& c, const int* RD, int n, Cnv* cv) {
   const int ndd = ne - ns;
   long long a = 0;
   for (int j = c.tid; j < len; j += c.nthr) a += (long long)RD[ns - len + j] - (long long)RD[ns + j];
-  const long long dd0 = c.reduce(a, SumOp());
+  const long long dd0 = c.reduce_ol(a, SumOp());
   const int tail0 = ndd - 2 * disp;
   ValIdx headbest; headbest.v = 0.0; headbest.i = -1;   // running extremum over the head window
   ValIdx tailbest; tailbest.v = 0.0; tailbest.i = -1;
@@ -548,8 +548,8 @@ RSI_DEVN void edge_refine(const Cta& c, const int* RD, int n, Cnv* cv) {
   // per-thread candidates are each thread's first strict maximum in ascending j; merge with first-index ties
   if (headbest.i < 0) { headbest.v = 0.0; headbest.i = 0x7fffffffffffll; }
   if (tailbest.i < 0) { tailbest.v = 0.0; tailbest.i = 0x7fffffffffffll; }
-  headbest = c.reduce(headbest, ArgMaxFirst());
-  tailbest = c.reduce(tailbest, ArgMaxFirst());
+  headbest = c.reduce_ol(headbest, ArgMaxFirst());
+  tailbest = c.reduce_ol(tailbest, ArgMaxFirst());
   c.sync();
   if (c.tid == 0) {
     if (headbest.v > 0.0 && headbest.i > 0 && headbest.i < ndd) cv->start = ns + (int)headbest.i;
@@ -561,7 +561,7 @@ RSI_DEVN void edge_refine(const Cta& c, const int* RD, int n, Cnv* cv) {
 RSI_DEVN double cta_mean(const Cta& c, const int* RD, int lo, int hi) {  // mean_tp: exact integer sum / count
   long long a = 0;
   for (int j = lo + c.tid; j <= hi; j += c.nthr) a += RD[j];
-  a = c.reduce(a, SumOp());
+  a = c.reduce_ol(a, SumOp());
   return (double)a / double(hi - lo + 1);
 }
 

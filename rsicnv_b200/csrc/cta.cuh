@@ -132,6 +132,13 @@ struct Cta {
     *total = all;
     return before + base + inc - v;
   }
+  // out-of-line forms for the candidate kernels: their time is instruction FETCH (k_cand_a: 300 KB of SASS that one block runs
+  // through once), and ~100 inlined copies of these two are a quarter of it.  The streaming kernels keep the inline forms: a
+  // call inside their tile loops costs far more than it saves (k_pileup_tile 0.49 -> 1.48 ms when tried).
+  template <class T, class Op>
+  RSI_DEVN T reduce_ol(T v, Op op) const { return reduce(v, op); }
+  template <class T>
+  RSI_DEVN T scan_excl_ol(T v, T* total) const { return scan_excl(v, total); }
   template <class T>
   static RSI_DEV T shfl_up_any(T v, int d) {
     unsigned w[sizeof(T) / 4];
@@ -164,6 +171,8 @@ struct Cta {
   void sync() const {}
   template <class T, class Op> T reduce(T v, Op) const { return v; }
   template <class T> T scan_excl(T v, T* total) const { *total = v; return T(0); }
+  template <class T, class Op> T reduce_ol(T v, Op op) const { return reduce(v, op); }
+  template <class T> T scan_excl_ol(T v, T* total) const { return scan_excl(v, total); }
 };
 inline void cta_atomic_inc(unsigned* p) { *p += 1u; }
 inline void cta_hist_add(unsigned* h, size_t b, bool valid) { if (valid) h[b] += 1u; }

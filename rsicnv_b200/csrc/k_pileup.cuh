@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(1024) k_cnv_stat(ReadSoA R, Cnv* calls, int nc
         ++rp;
       }
     }
-    qall = c.reduce(qall, SumOp()); q0 = c.reduce(q0, SumOp()); rp = c.reduce(rp, SumOp());
+    qall = c.reduce_ol(qall, SumOp()); q0 = c.reduce_ol(q0, SumOp()); rp = c.reduce_ol(rp, SumOp());
     if (c.tid == 0) { calls[k].q0 = (double)q0 / ((double)qall + 0.00001); calls[k].rp = (int)rp; }
     c.sync();
   }

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(1024) k_run_argmax(const float* __restrict__ t
       const int j = j0 + c.tid;
       const i64 v = j < n ? (i64)((double)t[a + j] * 68719476736.0) : 0;
       i64 tot;
-      const i64 ex = c.scan_excl(v, &tot);
+      const i64 ex = c.scan_excl_ol(v, &tot);
       if (j < n) P[j + 1] = carry + ex + v;
       carry += tot;
     }
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(1024) k_run_argmax(const float* __restrict__ t
         if (sc > best.v || (sc == best.v && (u64)L < best.key)) { best.v = sc; best.key = (u64)L; }
       }
     }
-    best = c.reduce(best, SegBestOp());
+    best = c.reduce_ol(best, SegBestOp());
     if (best.v > 0.0 && best.key != ~0ull) {          // first start of the winning length with that score
       const int L = (int)best.key;
       const double dL = (double)L, sL = sqrt(dL);
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(1024) k_run_argmax(const float* __restrict__ t
         const double sc = __dmul_rn(fabs(__ddiv_rn(sum, dL) - tmed), sL);
         if (sc == best.v) { jf = j; break; }
       }
-      jf = c.reduce(jf, MinOp());
+      jf = c.reduce_ol(jf, MinOp());
       best.key = ((u64)L << 32) | (u64)(unsigned)jf;
     }
     if (c.tid == 0) {
