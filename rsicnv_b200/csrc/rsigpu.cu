@@ -363,6 +363,7 @@ int rsigpu_create(int device, const rsigpu_params* p, rsigpu_ctx** out) {
   ok = ok && cudaEventCreate(&c->ev_part) == cudaSuccess && cudaEventCreate(&c->ev_lead) == cudaSuccess;
   ok = ok && cudaMalloc((void**)&c->d_st, sizeof(DevState)) == cudaSuccess;
   ok = ok && cudaMallocHost((void**)&c->h_st, sizeof(DevState)) == cudaSuccess;
+  if (ok) memset(c->h_st, 0, sizeof(DevState));      // a context that only decodes never fills it; the debug / log getters read it
   for (int k = 0; k < 8 && ok; ++k) ok = cudaEventCreate(&c->ev[k]) == cudaSuccess;
   ok = ok && c->d_hist_all.ensure(HIST_ALL_BINS) == cudaSuccess && c->d_chist.ensure((size_t)MAD_CLASSES * CHIST_RCAP) == cudaSuccess;
   ok = ok && c->d_thist.ensure(CHIST_RCAP) == cudaSuccess && c->d_tothist.ensure(CHIST_RCAP) == cudaSuccess;
@@ -1521,7 +1522,7 @@ int rsigpu_debug_state(const rsigpu_ctx* c, double* out, int32_t cap) {
                       (double)h->capv, (double)h->hist_base, (double)h->chist_R, h->rdmedian, h->rdsd, h->rdmad, (double)h->max_binsum, (double)h->gstar,
                       h->gc_tab[80], h->gc_tab[90], h->gc_tab[100], (double)h->gc_cnt[90], h->tmedian, h->tsigma, h->tlamda, (double)h->Lmax,
                       (double)h->lbreak_del, (double)h->lbreak_dup, (double)h->n_runs, (double)h->n_nonzero, (double)h->st_lo, (double)h->st_hi,
-                      (double)h->lvl_sum[-h->st_lo < 0 ? 0 : -h->st_lo], (double)h->filt_on, (double)h->cand_redone};
+                      (double)h->lvl_sum[(-h->st_lo < 0 || -h->st_lo >= 2 * LMAX_CAP + 3) ? 0 : -h->st_lo], (double)h->filt_on, (double)h->cand_redone};
   const int n = (int)(sizeof v / sizeof v[0]);
   for (int k = 0; k < n && k < cap; ++k) out[k] = v[k];
   for (int k = 0; k < 16 && n + k < cap; ++k) out[n + k] = (double)c->h_cprof[k];   // candidate-stage phase clocks (profile mode)
