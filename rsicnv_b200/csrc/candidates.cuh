@@ -193,6 +193,21 @@ RSI_DEV bool nb_accept(int v, int flag, double up, double lo) {
 // Every WARP takes a contiguous segment of a super-chunk sized to what is still wanted; lanes read
 // stride-1 (coalesced), __ballot_sync + popc give the compaction offsets, one exchange of the 32 warp
 // counts per super-chunk.
+// Sum of the per-warp slots (16-byte stride, one value per warp of the whole group, in a cluster: global memory) before
+// `warp` and over all `nw` warps: the lanes of a warp read 32 slots at a time and add up by shuffles, instead of every
+// thread reading every slot (up to 256 dependent-latency loads per thread in an 8-CTA cluster).
+template <class T>
+RSI_DEV void cta_slot_sums(const unsigned char* slots, int warp, int nw, int lane, T* before, T* total) {
+  T b = 0, t = 0;
+  for (int w0 = 0; w0 < nw; w0 += 32) {
+    const int w = w0 + lane;
+    const T v = w < nw ? *reinterpret_cast<const volatile T*>(slots + 16 * w) : (T)0;
+    t += v; if (w < warp) b += v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { b += __shfl_xor_sync(0xffffffffu, b, o); t += __shfl_xor_sync(0xffffffffu, t, o); }
+  *before = b; *total = t;
+}
 RSI_DEVN int cta_collect(const Cta& c, const int* RD, int lo, int hi, int dir, int flag, double up, double lw, int want, int* dst) {
   int got = 0, pos = 0;
   const int len = hi - lo + 1;
@@ -213,7 +228,7 @@ RSI_DEVN int cta_collect(const Cta& c, const int* RD, int lo, int hi, int dir, i
     if (lane == 0) *reinterpret_cast<int*>(slots + 16 * warp) = cnt;
     c.sync();
     int base = 0, tot = 0;
-    for (int w = 0; w < nw; ++w) { const int v = *reinterpret_cast<volatile int*>(slots + 16 * w); if (w < warp) base += v; tot += v; }
+    cta_slot_sums<int>(slots, warp, nw, lane, &base, &tot);
     int off = got + base;
     for (int j0 = w0; j0 < w1 && off < want; j0 += 32) {
       const int j = j0 + lane;
@@ -269,8 +284,8 @@ RSI_DEVN void cta_prefix_i32(const Cta& c, const int* ref, int n, long long* pre
   c.sync();
   if (lane == 0) *reinterpret_cast<long long*>(slots + 16 * warp) = loc;
   c.sync();
-  long long carry = 0;
-  for (int w = 0; w < warp; ++w) carry += *reinterpret_cast<volatile long long*>(slots + 16 * w);
+  long long carry = 0, all_ = 0;
+  cta_slot_sums<long long>(slots, warp, nw, lane, &carry, &all_);
   if (c.tid == 0) pref[0] = 0;
   for (int j0 = w0; j0 < w1; j0 += 32) {
     const int j = j0 + lane;
@@ -517,8 +532,9 @@ RSI_DEVN void edge_refine(const Cta& c, const int* RD, int n, Cnv* cv) {
     c.sync();
     if (lane == 0) *reinterpret_cast<long long*>(slots + 16 * warp) = loc;
     c.sync();
-    long long carry = dd0;
-    for (int w = 0; w < warp; ++w) carry += *reinterpret_cast<volatile long long*>(slots + 16 * w);
+    long long carry = 0, all_ = 0;
+    cta_slot_sums<long long>(slots, warp, nw, lane, &carry, &all_);
+    carry += dd0;
     for (int j0 = w0; j0 < w1; j0 += 32) {
       const int j = j0 + lane;
       long long inc = 0;
