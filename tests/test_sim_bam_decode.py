@@ -357,4 +357,10 @@ def test_feed_parts_equals_separate_feeds(sim_lib, tmp_path):
     with pytest.raises(api.RsiGpuError):
         ctx.bam_feed_parts([files[0][0][:-7], files[1][0]])
     ctx.bam_end()
+    # all or nothing: parts that do not fit one feed's decoded-size limit are refused, not cut
+    ctx.set_feed_limit(1 << 17)
+    ctx.bam_begin(1)
+    with pytest.raises(api.RsiGpuError):
+        ctx.bam_feed_parts([f[0] for f in files])
+    ctx.bam_end()
     ctx.close()
